@@ -1,0 +1,145 @@
+/*
+ * b200q4.h -- C ABI of the B200 (sm_100a) back-end for vsim's Q4_0 / Q4_1
+ * mul_mat hot path.  Plain C, plain pointers and sizes; no CUDA, torch or C++
+ * types cross this boundary.  Implemented by libb200q4.so
+ * (vsim_b200/csrc/*.cu).  There is NO CPU fallback behind any entry point: if
+ * no sm_100 device is usable every call fails loudly (see error convention).
+ *
+ * What it replaces in the reference (NAIST-Archlab/vsim; file:line):
+ *   - imax.c:52-142     init_xmax()            -> b200q4_init()
+ *   - imax.c:1133-2292  imax_ggml_compute_forward_mul_mat_q4_0_f32()
+ *                                              -> b200q4_mul_mat() behind the same-named
+ *                                                 hook in vsim_b200/csrc/imax_b200.c
+ *   - imax.c:2145-2148  per-call xmax_cpyin of the whole weight tensor
+ *                                              -> b200q4_weight_upload(): once per tensor
+ *   - ggml.c:209-298    quantize_row_q4_0 / quantize_row_q4_1 (INIT phase,
+ *                       ggml.c:5024-5041, 5302-5320) -> fused into b200q4_mul_mat();
+ *                       b200q4_quantize_rows() exposes the byte-exact row image
+ *   - ggml.c:472-553    ggml_vec_dot_q4_0 / _q4_1 (COMPUTE phase, ggml.c:5350-5390,
+ *                       imax.c:1205-1229)      -> the GEMV / tile kernels
+ *   - ggml.c:5118-5164, 5391-5440  transposed-src0 branch (ggml_vec_mad_q4_*)
+ *                                              -> b200q4_mul_mat_transposed()
+ *
+ * Data formats are the reference's, unchanged (ggml.c:204-298, 895-915):
+ *   Q4_0 row  = K/32 blocks of { float d; uint8_t qs[16] }            (20 B each)
+ *   Q4_1 row  = float min[K/32]; float d[K/32]; uint8_t qs[K/32][16]  (24 B/block, SoA)
+ *   byte j of qs holds element 2j in the low nibble, 2j+1 in the high nibble.
+ * Weights are handed over in that format and re-tiled ON THE DEVICE at upload;
+ * the host copy is never modified.
+ *
+ * Error convention.  The reference's hook has no error channel (printf +
+ * exit(1), imax.c:2042-2049).  Here every int-returning function returns
+ * B200Q4_OK (0) or a negative B200Q4_E* code and records a message readable
+ * with b200q4_last_error(); the ggml hook in imax_b200.c turns any failure
+ * into fprintf(stderr) + exit(1) exactly like the reference.
+ *
+ * Threading: calls are serialised internally (one device context per process,
+ * one stream); the ggml hook may be entered from any pool thread.
+ */
+#ifndef B200Q4_H
+#define B200Q4_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200Q4_ABI_VERSION 1
+
+/* enum ggml_type values (ggml.h:217-226) */
+#define B200Q4_TYPE_Q4_0 0
+#define B200Q4_TYPE_Q4_1 1
+#define B200Q4_QK 32
+
+#define B200Q4_OK          0
+#define B200Q4_EINVAL     -1   /* bad argument (shape, type, NULL, stride)           */
+#define B200Q4_ENODEV     -2   /* no CUDA device / not sm_100 / init not called       */
+#define B200Q4_ECUDA      -3   /* a CUDA runtime call or kernel failed                */
+#define B200Q4_ENOMEM     -4   /* device or pinned-host allocation failed             */
+
+typedef struct b200q4_weight b200q4_weight;   /* opaque: one weight tensor resident in HBM */
+
+/* ---- life cycle ---------------------------------------------------------- */
+int  b200q4_abi_version(void);
+/* Select `device` (>= 0), require compute capability 10.x, create the stream
+ * and scratch buffers.  Idempotent for the same device.  (imax.c:52 init_xmax) */
+int  b200q4_init(int device);
+void b200q4_shutdown(void);
+const char *b200q4_last_error(void);
+/* Fills name (<= cap bytes), SM count and total HBM bytes of the active device. */
+int  b200q4_device_info(char *name, size_t cap, int *sm_count, size_t *hbm_bytes);
+
+/* ---- weights --------------------------------------------------------------
+ * rows: N rows in the reference's row format for `type`, `row_stride` bytes
+ * apart (src0->nb[1]; pass 0 for tightly packed).  K % 32 == 0.  The tensor is
+ * copied to the device once and re-tiled there.  Returns NULL on failure.    */
+b200q4_weight *b200q4_weight_upload(int type, const void *rows, int N, int K, size_t row_stride);
+/* Row shard [row0, row0+nrows) of the same host tensor (multi-GPU row split,
+ * the split the reference's threads use at imax.c:1185-1188).               */
+b200q4_weight *b200q4_weight_upload_rows(int type, const void *rows, int N, int K,
+                                         size_t row_stride, int row0, int nrows);
+void   b200q4_weight_free(b200q4_weight *w);
+int    b200q4_weight_rows(const b200q4_weight *w);      /* N of this (shard of the) tensor */
+int    b200q4_weight_cols(const b200q4_weight *w);      /* K */
+int    b200q4_weight_type(const b200q4_weight *w);
+size_t b200q4_weight_device_bytes(const b200q4_weight *w);
+/* Reads the tensor back from HBM in the reference's row format (round-trip check). */
+int    b200q4_weight_download(const b200q4_weight *w, void *rows_out, size_t row_stride);
+
+/* ---- the operator: HOST buffers in, HOST buffers out ----------------------
+ * Y[m][n] = sum_k dequant(W[n][k]) * dequant(quantize_row(X[m])[k]),
+ * m < M, n < N: ggml_compute_forward_mul_mat_q4_{0,1}_f32 for non-transposed
+ * src0 (INIT + COMPUTE phases).  x: M rows of K floats, x_stride bytes apart
+ * (src1->nb[1]); y: M rows of N floats, y_stride bytes apart (dst->nb[1]).
+ * y is completely written when the call returns.                            */
+int b200q4_mul_mat(const b200q4_weight *w, const float *x, int M, size_t x_stride,
+                   float *y, size_t y_stride);
+/* Same, but the activations arrive already quantized by the reference's INIT
+ * phase: wdata = M rows in the row format of the weight's type (params->wdata,
+ * ggml.c:5033-5034).  This is what an UNPATCHED ggml.c hands to the hook.    */
+int b200q4_mul_mat_wdata(const b200q4_weight *w, const void *wdata, int M,
+                         float *y, size_t y_stride);
+
+/* quantize_row_q4_0 / _q4_1 over M rows: out receives M * (K/32)*{20|24} bytes,
+ * byte-identical to the reference (scales as raw fp32 bits, then nibbles).  */
+int b200q4_quantize_rows(int type, const float *x, int M, int K, size_t x_stride, void *out);
+
+/* Transposed src0 (nb01 < nb00; ggml.c:5118-5164 / 5391-5440): wt holds K rows
+ * of N quantized values (N % 32 == 0), activations stay fp32.
+ * Y[m][n] = sum_k dequant(Wt[k][n]) * X[m][k].                               */
+b200q4_weight *b200q4_weight_upload_transposed(int type, const void *rows, int N, int K, size_t row_stride);
+int b200q4_mul_mat_transposed(const b200q4_weight *wt, const float *x, int M, size_t x_stride,
+                              float *y, size_t y_stride);
+
+/* ---- device-resident variants (pointers are DEVICE pointers) ---------------
+ * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ * library's own stream).  Used by callers that keep activations in HBM
+ * (bench.py `value`, the multi-GPU path).                                   */
+int b200q4_mul_mat_dev(const b200q4_weight *w, const float *d_x, int M, size_t x_stride,
+                       float *d_y, size_t y_stride, void *stream);
+int b200q4_quantize_rows_dev(int type, const float *d_x, int M, int K, size_t x_stride,
+                             void *d_out, void *stream);
+int b200q4_sync(void *stream);
+
+/* Pinned host memory for callers that want zero-staging H2D/D2H copies.      */
+void *b200q4_host_alloc(size_t bytes);
+void  b200q4_host_free(void *p);
+
+/* ---- introspection used by bench.py / tests -------------------------------- */
+/* Number of kernels this library has launched since init (or the last reset). */
+uint64_t b200q4_launch_count(void);
+void     b200q4_launch_count_reset(void);
+/* Name of the kernel variant b200q4_mul_mat would pick for (type, M, N, K).  */
+const char *b200q4_kernel_for(int type, int M, int N, int K);
+/* Times `iters` back-to-back device-resident mul_mats with CUDA events on the
+ * library stream, rotating over `nw` weight handles (L2 defeat); returns the
+ * mean milliseconds per call or a negative error code.                      */
+double b200q4_time_mul_mat_dev(b200q4_weight *const *ws, int nw, const float *d_x, int M,
+                               float *d_y, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Q4_H */

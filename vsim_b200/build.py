@@ -1,0 +1,55 @@
+"""In-tree build of libb200q4.so (CUDA kernels + C ABI + the imax hook) for sm_100a.
+
+`python -m vsim_b200.build` or `vsim_b200.build.build_library()`.  nvcc
+cross-compiles without a GPU; the resulting .so is git-ignored but travels
+to the GPU box with the repository snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libb200q4.so"
+SOURCES = [CSRC / "q4_api.cu", CSRC / "imax_b200.c"]
+DEPS = SOURCES + [CSRC / "q4_kernels.cuh", PKG.parent / "include" / "b200q4.h",
+                  PKG.parent / "include" / "b200q4_ggml_abi.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def nvcc_path() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(cand).exists():
+        raise RuntimeError("nvcc not found: the B200 back-end cannot be built (no CPU fallback exists)")
+    return cand
+
+
+def is_stale() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in DEPS)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not is_stale():
+        return LIB
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES)]
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libb200q4.so")
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,190 @@
+/*
+ * imax_b200.c -- the B200 stand-in for the reference's imax.c.
+ *
+ * Link this file (plus libb200q4.so) INSTEAD OF imax.c / emax7lib.c and the
+ * unmodified ggml.c, vsim.cpp and monitor.c of NAIST-Archlab/vsim run their
+ * Q4_0 mul_mat COMPUTE phase on the GPU:
+ *
+ *   vsim.cpp:788   init_xmax();                                  -> below
+ *   ggml.c:5115    imax_ggml_compute_forward_mul_mat_q4_0_f32(0, 0, params, src0, src1, dst);
+ *                                                                -> below, same six arguments
+ *                  (ggml.c has no prototype for it -- implicit declaration --
+ *                   so the plain C ABI of imax.c:1133-1139 is the contract)
+ *
+ * and, with the three-line ggml.c patch shown in INTEGRATION.md, the Q4_1
+ * twin imax_ggml_compute_forward_mul_mat_q4_1_f32 replaces ggml.c:5350-5390.
+ *
+ * Semantics kept from the reference hook:
+ *   - called in the COMPUTE phase by every pool thread (ggml.c:8566-8588);
+ *     thread ith == 0 does the whole operator, the others return at once (the
+ *     scheduler's barriers, ggml.c:8590-8607, make that safe; the CGRA body
+ *     demands nth == 1 outright, imax.c:2042);
+ *   - 2-D operands only, anything else prints and exit(1)s (imax.c:2042-2049);
+ *   - dst is completely written in host memory on return;
+ *   - no error channel: any failure prints to stderr and exit(1)s.
+ * Differences by design:
+ *   - the weight tensor is uploaded ONCE (keyed by src0->data, immutable after
+ *     vsim.cpp:440) instead of xmax_cpyin'ing it on every call (imax.c:2145);
+ *   - activations are quantized on the device from src1->data (bit-identical
+ *     codes); set B200Q4_USE_WDATA=1 to consume the rows the CPU INIT phase
+ *     left in params->wdata instead.
+ * Environment: B200Q4_DEVICE (default 0), B200Q4_USE_WDATA (default 0),
+ *              B200Q4_VERBOSE (default 0).
+ */
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/b200q4.h"
+
+#ifdef B200Q4_HAVE_GGML_H
+#include <signal.h>
+#include "ggml.h"
+#include "../../include/b200q4_ggml_abi.h"
+typedef struct ggml_tensor hook_tensor;
+struct ggml_compute_params {            /* private to ggml.c:1052-1060; imax.c:1115 re-declares it too */
+    int type; int ith, nth; size_t wsize; void *wdata;
+};
+typedef struct ggml_compute_params hook_params;
+_Static_assert(sizeof(struct ggml_tensor) == sizeof(struct b200q4_ggml_tensor), "ggml_tensor size");
+_Static_assert(offsetof(struct ggml_tensor, ne)   == offsetof(struct b200q4_ggml_tensor, ne),   "ne");
+_Static_assert(offsetof(struct ggml_tensor, nb)   == offsetof(struct b200q4_ggml_tensor, nb),   "nb");
+_Static_assert(offsetof(struct ggml_tensor, src0) == offsetof(struct b200q4_ggml_tensor, src0), "src0");
+_Static_assert(offsetof(struct ggml_tensor, data) == offsetof(struct b200q4_ggml_tensor, data), "data");
+#else
+#include "../../include/b200q4_ggml_abi.h"
+typedef struct b200q4_ggml_tensor hook_tensor;
+typedef struct b200q4_ggml_compute_params hook_params;
+#endif
+
+#define HOOK_TASK_COMPUTE 1
+
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static int g_ready = 0, g_use_wdata = 0, g_verbose = 0;
+
+struct reg_entry { const void *key; int type, N, K; b200q4_weight *w; };
+static struct reg_entry *g_reg = NULL;
+static size_t g_reg_cap = 0, g_reg_n = 0;
+
+static void die(const char *what)
+{
+    fprintf(stderr, "imax_b200: %s: %s\n", what, b200q4_last_error());
+    exit(1);
+}
+
+/* imax.c:52 init_xmax(): the reference allocates its staging arenas here; we
+ * bind the GPU.  Safe to call more than once. */
+void init_xmax(void)
+{
+    pthread_mutex_lock(&g_mu);
+    if (!g_ready) {
+        const char *dev = getenv("B200Q4_DEVICE");
+        const char *uw = getenv("B200Q4_USE_WDATA");
+        const char *vb = getenv("B200Q4_VERBOSE");
+        g_use_wdata = uw && atoi(uw) != 0;
+        g_verbose = vb && atoi(vb) != 0;
+        if (b200q4_init(dev ? atoi(dev) : 0) != B200Q4_OK) die("init_xmax");
+        if (g_verbose) {
+            char name[128]; int sms = 0; size_t hbm = 0;
+            b200q4_device_info(name, sizeof name, &sms, &hbm);
+            printf("imax_b200: %s, %d SMs, %.1f GB HBM\n", name, sms, hbm / 1e9);
+        }
+        g_ready = 1;
+    }
+    pthread_mutex_unlock(&g_mu);
+}
+
+static b200q4_weight *resident_weight(const hook_tensor *src0)
+{
+    const void *key = src0->data;
+    const int type = (int)src0->type, K = src0->ne[0], N = src0->ne[1];
+    size_t mask, h;
+    if (g_reg_cap == 0 || g_reg_n * 2 >= g_reg_cap) {          /* grow + rehash */
+        size_t ncap = g_reg_cap ? g_reg_cap * 2 : 1024;
+        struct reg_entry *nr = (struct reg_entry *)calloc(ncap, sizeof *nr);
+        if (!nr) { fprintf(stderr, "imax_b200: out of host memory\n"); exit(1); }
+        for (size_t i = 0; i < g_reg_cap; i++)
+            if (g_reg[i].key) {
+                size_t j = ((size_t)g_reg[i].key >> 4) * 0x9E3779B97F4A7C15ull & (ncap - 1);
+                while (nr[j].key) j = (j + 1) & (ncap - 1);
+                nr[j] = g_reg[i];
+            }
+        free(g_reg);
+        g_reg = nr; g_reg_cap = ncap;
+    }
+    mask = g_reg_cap - 1;
+    h = ((size_t)key >> 4) * 0x9E3779B97F4A7C15ull & mask;
+    while (g_reg[h].key) {
+        if (g_reg[h].key == key && g_reg[h].type == type && g_reg[h].N == N && g_reg[h].K == K)
+            return g_reg[h].w;
+        h = (h + 1) & mask;
+    }
+    b200q4_weight *w = b200q4_weight_upload(type, src0->data, N, K, src0->nb[1]);
+    if (!w) die("weight upload");
+    if (g_verbose) printf("imax_b200: resident weight %p type=%d N=%d K=%d (%zu B)\n", key, type, N, K, b200q4_weight_device_bytes(w));
+    g_reg[h].key = key; g_reg[h].type = type; g_reg[h].N = N; g_reg[h].K = K; g_reg[h].w = w;
+    g_reg_n++;
+    return w;
+}
+
+static void hook_mul_mat(int want_type, const char *who, const hook_params *params,
+                         const hook_tensor *src0, const hook_tensor *src1, hook_tensor *dst)
+{
+    if (params->type != HOOK_TASK_COMPUTE || params->ith != 0) return;
+    if (!g_ready) init_xmax();
+    if ((int)src0->type != want_type || src0->ne[2] != 1 || src0->ne[3] != 1 ||
+        src1->ne[2] != 1 || src1->ne[3] != 1 || src0->ne[0] != src1->ne[0] ||
+        dst->ne[0] != src0->ne[1] || dst->ne[1] != src1->ne[1] ||
+        src1->nb[0] != sizeof(float) || dst->nb[0] != sizeof(float)) {
+        /* the CGRA body of the reference refuses the same way (imax.c:2042-2049) */
+        fprintf(stderr, "%s: unsupported operands: src0 type=%d ne=[%d,%d,%d,%d] src1 ne=[%d,%d,%d,%d]\n", who,
+                (int)src0->type, src0->ne[0], src0->ne[1], src0->ne[2], src0->ne[3],
+                src1->ne[0], src1->ne[1], src1->ne[2], src1->ne[3]);
+        exit(1);
+    }
+    pthread_mutex_lock(&g_mu);
+    b200q4_weight *w = resident_weight(src0);
+    pthread_mutex_unlock(&g_mu);
+    const int M = src1->ne[1];
+    int rc;
+    if (g_use_wdata)
+        rc = b200q4_mul_mat_wdata(w, params->wdata, M, (float *)dst->data, dst->nb[1]);
+    else
+        rc = b200q4_mul_mat(w, (const float *)src1->data, M, src1->nb[1], (float *)dst->data, dst->nb[1]);
+    if (rc != B200Q4_OK) die(who);
+}
+
+/* imax.c:1133-1139.  THREAD and LANE are the reference's IMAX lane selectors
+ * (always 0, ggml.c:5115); a single GPU context serves every lane. */
+void imax_ggml_compute_forward_mul_mat_q4_0_f32(int THREAD, int LANE, const hook_params *params,
+                                                const hook_tensor *src0, const hook_tensor *src1,
+                                                hook_tensor *dst)
+{
+    (void)THREAD; (void)LANE;
+    hook_mul_mat(B200Q4_TYPE_Q4_0, "imax_ggml_compute_forward_mul_mat_q4_0_f32", params, src0, src1, dst);
+}
+
+/* New twin for GGML_TYPE_Q4_1 weights; replaces the in-file loop at ggml.c:5350-5390
+ * (see INTEGRATION.md for the call site to add). */
+void imax_ggml_compute_forward_mul_mat_q4_1_f32(int THREAD, int LANE, const hook_params *params,
+                                                const hook_tensor *src0, const hook_tensor *src1,
+                                                hook_tensor *dst)
+{
+    (void)THREAD; (void)LANE;
+    hook_mul_mat(B200Q4_TYPE_Q4_1, "imax_ggml_compute_forward_mul_mat_q4_1_f32", params, src0, src1, dst);
+}
+
+/* Frees every resident weight and the device context (the reference never
+ * tears its arenas down; provided for embedders and tests). */
+void b200q4_hook_shutdown(void)
+{
+    pthread_mutex_lock(&g_mu);
+    for (size_t i = 0; i < g_reg_cap; i++)
+        if (g_reg[i].key) b200q4_weight_free(g_reg[i].w);
+    free(g_reg);
+    g_reg = NULL; g_reg_cap = 0; g_reg_n = 0;
+    if (g_ready) b200q4_shutdown();
+    g_ready = 0;
+    pthread_mutex_unlock(&g_mu);
+}

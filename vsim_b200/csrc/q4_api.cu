@@ -1,0 +1,516 @@
+// q4_api.cu -- the C ABI of include/b200q4.h on top of q4_kernels.cuh.
+// Host-side plumbing only: device selection, weight residency, scratch
+// buffers, kernel selection and launch.  No CPU compute path exists here: if
+// CUDA is unusable every entry point fails with B200Q4_ENODEV / B200Q4_ECUDA.
+#include "../../include/b200q4.h"
+#include "q4_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+using namespace b200q4;
+
+struct b200q4_weight {
+    int type, N, K, nb, C, n_tiles;
+    bool transposed;
+    uint8_t *d_wt;       // wtile (or raw reference rows when transposed)
+    size_t wt_bytes;
+    int *d_counters;     // one per 16-row tile
+};
+
+namespace {
+
+struct Ctx {
+    int device = -1;
+    int sms = 0;
+    int smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint8_t *d_aq = nullptr; size_t aq_cap = 0;
+    float *d_ap = nullptr;   size_t ap_cap = 0;
+    float *d_partial = nullptr; size_t partial_cap = 0;
+    float *d_x = nullptr;    size_t x_cap = 0;
+    float *d_y = nullptr;    size_t y_cap = 0;
+    uint8_t *d_tmp = nullptr; size_t tmp_cap = 0;
+    uint64_t launches = 0;
+    std::recursive_mutex mu;
+    std::string err;
+};
+Ctx g;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g.err = buf;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(B200Q4_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+template <typename T>
+int ensure(T *&p, size_t &cap, size_t need_bytes)
+{
+    if (need_bytes <= cap) return B200Q4_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = need_bytes + need_bytes / 4 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200Q4_ENOMEM, "cudaMalloc(%zu) failed", want);
+    }
+    cap = want;
+    return B200Q4_OK;
+}
+
+int need_init()
+{
+    if (g.device < 0) return fail(B200Q4_ENODEV, "b200q4_init() has not succeeded; no CPU fallback exists");
+    return B200Q4_OK;
+}
+
+// ---- kernel selection -------------------------------------------------------
+struct Plan { int NT; int Mc; size_t smem; const char *name; };
+
+// rows of X handled per launch: as many as the activation pack allows in shared memory
+Plan plan_for(int type, int M, int nbp)
+{
+    const size_t per_row = (size_t)nbp * (32 + ap_floats(type) * 4);
+    const size_t budget = (size_t)(g.smem_optin > 0 ? g.smem_optin : 232448) - 1024;
+    int mc = (int)(budget / per_row);
+    if (mc > 16) mc = 16;
+    if (mc > M) mc = M;
+    if (mc < 1) mc = 0;
+    Plan p;
+    p.Mc = mc;
+    p.NT = mc > 8 ? 2 : 1;
+    p.smem = per_row * mc;
+    p.name = type == 0 ? (p.NT == 1 ? "q4_0_gemv_imma_nt1" : "q4_0_gemv_imma_nt2")
+                       : (p.NT == 1 ? "q4_1_gemv_imma_nt1" : "q4_1_gemv_imma_nt2");
+    return p;
+}
+
+template <int QT, int NT, int PD>
+int launch_gemv(const GemvParams &p, int grid, size_t smem, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(q4_gemv_kernel<QT, NT, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                g.smem_optin));
+        attr_set = true;
+    }
+    q4_gemv_kernel<QT, NT, PD><<<grid, GEMV_THREADS, smem, st>>>(p);
+    g.launches++;
+    CK(cudaGetLastError());
+    return B200Q4_OK;
+}
+
+// one pass of the hot path for Mc <= 16 activation rows whose apack is already in g.d_aq/g.d_ap
+int run_gemv(const b200q4_weight *w, int Mc, const Plan &pl, float *d_y, size_t y_stride_f, cudaStream_t st)
+{
+    GemvParams p;
+    p.wt = w->d_wt; p.aq = g.d_aq; p.ap = g.d_ap; p.y = d_y; p.partial = g.d_partial; p.counters = w->d_counters;
+    p.y_stride = y_stride_f;
+    p.U = (long)w->n_tiles * w->C;
+    p.N = w->N; p.M = Mc; p.C = w->C; p.n_tiles = w->n_tiles;
+    long warps = (long)g.sms * GEMV_WARPS;
+    p.Weff = (int)(p.U < warps ? p.U : warps);
+    const int grid = (p.Weff + GEMV_WARPS - 1) / GEMV_WARPS;
+    if (w->type == 0) return pl.NT == 1 ? launch_gemv<0, 1, 4>(p, grid, pl.smem, st) : launch_gemv<0, 2, 4>(p, grid, pl.smem, st);
+    return pl.NT == 1 ? launch_gemv<1, 1, 3>(p, grid, pl.smem, st) : launch_gemv<1, 2, 3>(p, grid, pl.smem, st);
+}
+
+int ensure_scratch(const b200q4_weight *w, int Mc)
+{
+    const int nbp = w->C * CHUNK_BLKS;
+    int rc;
+    if ((rc = ensure(g.d_aq, g.aq_cap, (size_t)nbp * Mc * 32))) return rc;
+    if ((rc = ensure(g.d_ap, g.ap_cap, (size_t)nbp * Mc * 16))) return rc;
+    if ((rc = ensure(g.d_partial, g.partial_cap, (size_t)2 * g.sms * GEMV_WARPS * 2 * 4 * 32 * sizeof(float)))) return rc;
+    return B200Q4_OK;
+}
+
+int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x_stride, float *d_y,
+                       size_t y_stride, cudaStream_t st, const uint8_t *d_wdata)
+{
+    if (!w || w->transposed || M < 0 || (!d_x && !d_wdata) || !d_y) return fail(B200Q4_EINVAL, "mul_mat: bad argument");
+    if ((x_stride % 4) || (y_stride % 4)) return fail(B200Q4_EINVAL, "mul_mat: strides must be multiples of 4 bytes");
+    if (M == 0 || w->N == 0) return B200Q4_OK;
+    const int nbp = w->C * CHUNK_BLKS;
+    const Plan pl = plan_for(w->type, M, nbp);
+    if (pl.Mc < 1) return fail(B200Q4_EINVAL, "mul_mat: K=%d too large for the shared-memory activation pack", w->K);
+    int rc;
+    if ((rc = ensure_scratch(w, pl.Mc))) return rc;
+    const size_t rbw = (size_t)w->nb * (w->type == 0 ? 20 : 24);
+    for (int m0 = 0; m0 < M; m0 += pl.Mc) {
+        const int mc = (M - m0 < pl.Mc) ? M - m0 : pl.Mc;
+        Plan p2 = pl;
+        if (mc != pl.Mc) p2 = plan_for(w->type, mc, nbp);
+        const long warps = (long)nbp * mc;
+        const int blocks = (int)((warps * 32 + 255) / 256);
+        if (d_wdata) {
+            const uint8_t *src = d_wdata + (size_t)m0 * rbw;
+            if (w->type == 0) pack_wdata_kernel<0><<<blocks, 256, 0, st>>>(src, mc, w->nb, nbp, g.d_aq, g.d_ap);
+            else              pack_wdata_kernel<1><<<blocks, 256, 0, st>>>(src, mc, w->nb, nbp, g.d_aq, g.d_ap);
+        } else {
+            const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(d_x) + (size_t)m0 * x_stride);
+            if (w->type == 0) pack_act_kernel<0><<<blocks, 256, 0, st>>>(src, x_stride / 4, mc, w->nb, nbp, g.d_aq, g.d_ap);
+            else              pack_act_kernel<1><<<blocks, 256, 0, st>>>(src, x_stride / 4, mc, w->nb, nbp, g.d_aq, g.d_ap);
+        }
+        g.launches++;
+        CK(cudaGetLastError());
+        float *yo = reinterpret_cast<float *>(reinterpret_cast<char *>(d_y) + (size_t)m0 * y_stride);
+        if ((rc = run_gemv(w, mc, p2, yo, y_stride / 4, st))) return rc;
+    }
+    return B200Q4_OK;
+}
+
+b200q4_weight *upload_impl(int type, const void *rows, int N, int K, size_t row_stride, bool transposed)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (need_init()) return nullptr;
+    // for the transposed form the quantized axis is N (rows are K long in count, N wide in values)
+    const int qlen = transposed ? N : K, nrows = transposed ? K : N;
+    if ((type != 0 && type != 1) || !rows || N < 0 || K < 0 || qlen % QK != 0) {
+        fail(B200Q4_EINVAL, "weight_upload: bad argument (type=%d N=%d K=%d)", type, N, K);
+        return nullptr;
+    }
+    const int nb = qlen / QK;
+    const size_t rb = (size_t)nb * (type == 0 ? 20 : 24);
+    if (row_stride == 0) row_stride = rb;
+    if (row_stride < rb) { fail(B200Q4_EINVAL, "weight_upload: row_stride < row bytes"); return nullptr; }
+    b200q4_weight *w = new b200q4_weight();
+    w->type = type; w->N = N; w->K = K; w->nb = nb; w->transposed = transposed;
+    w->d_wt = nullptr; w->d_counters = nullptr;
+    const size_t raw = rb * (size_t)nrows;
+    auto bail = [&](int code, const char *what) { fail(code, "weight_upload: %s", what); b200q4_weight_free(w); return (b200q4_weight *)nullptr; };
+    if (transposed) {
+        w->C = 0; w->n_tiles = 0; w->wt_bytes = raw;
+        if (raw && cudaMalloc(&w->d_wt, raw) != cudaSuccess) return bail(B200Q4_ENOMEM, "cudaMalloc failed");
+        if (raw && cudaMemcpy2D(w->d_wt, rb, rows, row_stride, rb, nrows, cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(B200Q4_ECUDA, "H2D copy failed");
+        return w;
+    }
+    w->C = (nb + CHUNK_BLKS - 1) / CHUNK_BLKS;
+    w->n_tiles = (N + TILE_ROWS - 1) / TILE_ROWS;
+    w->wt_bytes = (size_t)w->n_tiles * w->C * chunk_bytes(type);
+    if (w->wt_bytes == 0) return w;
+    if (cudaMalloc(&w->d_wt, w->wt_bytes) != cudaSuccess) return bail(B200Q4_ENOMEM, "cudaMalloc(wtile) failed");
+    if (cudaMalloc(&w->d_counters, sizeof(int) * (size_t)w->n_tiles) != cudaSuccess) return bail(B200Q4_ENOMEM, "cudaMalloc(counters) failed");
+    if (cudaMemsetAsync(w->d_counters, 0, sizeof(int) * (size_t)w->n_tiles, g.stream) != cudaSuccess) return bail(B200Q4_ECUDA, "memset failed");
+    uint8_t *d_raw = nullptr;
+    if (cudaMalloc(&d_raw, raw) != cudaSuccess) return bail(B200Q4_ENOMEM, "cudaMalloc(staging) failed");
+    if (cudaMemcpy2DAsync(d_raw, rb, rows, row_stride, rb, N, cudaMemcpyHostToDevice, g.stream) != cudaSuccess) {
+        cudaFree(d_raw);
+        return bail(B200Q4_ECUDA, "H2D copy failed");
+    }
+    const long slots = (long)w->n_tiles * w->C * (chunk_bytes(type) / 16);
+    const int blocks = (int)((slots + 255) / 256);
+    if (type == 0) repack_kernel<0><<<blocks, 256, 0, g.stream>>>(d_raw, N, nb, w->n_tiles, w->C, w->d_wt);
+    else           repack_kernel<1><<<blocks, 256, 0, g.stream>>>(d_raw, N, nb, w->n_tiles, w->C, w->d_wt);
+    g.launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    cudaFree(d_raw);
+    if (e != cudaSuccess) return bail(B200Q4_ECUDA, cudaGetErrorString(e));
+    return w;
+}
+
+} // namespace
+
+extern "C" {
+
+int b200q4_abi_version(void) { return B200Q4_ABI_VERSION; }
+
+const char *b200q4_last_error(void) { return g.err.c_str(); }
+
+int b200q4_init(int device)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (g.device == device && g.device >= 0) return B200Q4_OK;
+    if (g.device >= 0) return fail(B200Q4_EINVAL, "already initialised on device %d", g.device);
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(B200Q4_ENODEV, "no CUDA device visible; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(B200Q4_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(B200Q4_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&g.ev0));
+    CK(cudaEventCreate(&g.ev1));
+    g.sms = prop.multiProcessorCount;
+    g.smem_optin = (int)prop.sharedMemPerBlockOptin;
+    g.device = device;
+    g.launches = 0;
+    return B200Q4_OK;
+}
+
+void b200q4_shutdown(void)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (g.device < 0) return;
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(g.stream);
+    cudaFree(g.d_aq); cudaFree(g.d_ap); cudaFree(g.d_partial); cudaFree(g.d_x); cudaFree(g.d_y); cudaFree(g.d_tmp);
+    g.d_aq = nullptr; g.d_ap = nullptr; g.d_partial = nullptr; g.d_x = nullptr; g.d_y = nullptr; g.d_tmp = nullptr;
+    g.aq_cap = g.ap_cap = g.partial_cap = g.x_cap = g.y_cap = g.tmp_cap = 0;
+    cudaEventDestroy(g.ev0); cudaEventDestroy(g.ev1);
+    cudaStreamDestroy(g.stream);
+    g.stream = nullptr;
+    g.device = -1;
+}
+
+int b200q4_device_info(char *name, size_t cap, int *sm_count, size_t *hbm_bytes)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, g.device));
+    if (name && cap) { strncpy(name, prop.name, cap - 1); name[cap - 1] = 0; }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (hbm_bytes) *hbm_bytes = prop.totalGlobalMem;
+    return B200Q4_OK;
+}
+
+b200q4_weight *b200q4_weight_upload(int type, const void *rows, int N, int K, size_t row_stride)
+{
+    return upload_impl(type, rows, N, K, row_stride, false);
+}
+
+b200q4_weight *b200q4_weight_upload_rows(int type, const void *rows, int N, int K, size_t row_stride, int row0, int nrows)
+{
+    if (K < 0 || K % QK != 0 || row0 < 0 || nrows < 0 || (long)row0 + nrows > N) {
+        fail(B200Q4_EINVAL, "weight_upload_rows: bad shard [%d,+%d) of %d rows", row0, nrows, N);
+        return nullptr;
+    }
+    const size_t rb = (size_t)(K / QK) * (type == 0 ? 20 : 24);
+    if (row_stride == 0) row_stride = rb;
+    return upload_impl(type, rows ? (const char *)rows + (size_t)row0 * row_stride : nullptr, nrows, K, row_stride, false);
+}
+
+b200q4_weight *b200q4_weight_upload_transposed(int type, const void *rows, int N, int K, size_t row_stride)
+{
+    return upload_impl(type, rows, N, K, row_stride, true);
+}
+
+void b200q4_weight_free(b200q4_weight *w)
+{
+    if (!w) return;
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (g.device >= 0) {
+        cudaStreamSynchronize(g.stream);
+        cudaFree(w->d_wt);
+        cudaFree(w->d_counters);
+    }
+    delete w;
+}
+
+int b200q4_weight_rows(const b200q4_weight *w) { return w ? w->N : B200Q4_EINVAL; }
+int b200q4_weight_cols(const b200q4_weight *w) { return w ? w->K : B200Q4_EINVAL; }
+int b200q4_weight_type(const b200q4_weight *w) { return w ? w->type : B200Q4_EINVAL; }
+size_t b200q4_weight_device_bytes(const b200q4_weight *w) { return w ? w->wt_bytes : 0; }
+
+int b200q4_weight_download(const b200q4_weight *w, void *rows_out, size_t row_stride)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    if (!w || !rows_out) return fail(B200Q4_EINVAL, "weight_download: bad argument");
+    const size_t rb = (size_t)w->nb * (w->type == 0 ? 20 : 24);
+    if (row_stride == 0) row_stride = rb;
+    const int nrows = w->transposed ? w->K : w->N;
+    if (nrows == 0 || rb == 0) return B200Q4_OK;
+    if (w->transposed) {
+        CK(cudaMemcpy2D(rows_out, row_stride, w->d_wt, rb, rb, nrows, cudaMemcpyDeviceToHost));
+        return B200Q4_OK;
+    }
+    if (int rc = ensure(g.d_tmp, g.tmp_cap, rb * (size_t)nrows)) return rc;
+    const long n = (long)w->N * w->nb;
+    const int blocks = (int)((n + 255) / 256);
+    if (w->type == 0) unpack_kernel<0><<<blocks, 256, 0, g.stream>>>(w->d_wt, w->N, w->nb, w->C, g.d_tmp);
+    else              unpack_kernel<1><<<blocks, 256, 0, g.stream>>>(w->d_wt, w->N, w->nb, w->C, g.d_tmp);
+    g.launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2DAsync(rows_out, row_stride, g.d_tmp, rb, rb, nrows, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return B200Q4_OK;
+}
+
+int b200q4_mul_mat_dev(const b200q4_weight *w, const float *d_x, int M, size_t x_stride, float *d_y,
+                       size_t y_stride, void *stream)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    if (!w) return fail(B200Q4_EINVAL, "mul_mat_dev: NULL weight");
+    if (x_stride == 0) x_stride = (size_t)w->K * 4;
+    if (y_stride == 0) y_stride = (size_t)w->N * 4;
+    return mul_mat_dev_locked(w, d_x, M, x_stride, d_y, y_stride, stream ? (cudaStream_t)stream : g.stream, nullptr);
+}
+
+int b200q4_mul_mat(const b200q4_weight *w, const float *x, int M, size_t x_stride, float *y, size_t y_stride)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    if (!w || w->transposed || M < 0 || (M > 0 && (!x || !y))) return fail(B200Q4_EINVAL, "mul_mat: bad argument");
+    if (x_stride == 0) x_stride = (size_t)w->K * 4;
+    if (y_stride == 0) y_stride = (size_t)w->N * 4;
+    if (x_stride < (size_t)w->K * 4 || y_stride < (size_t)w->N * 4) return fail(B200Q4_EINVAL, "mul_mat: stride smaller than a row");
+    if (M == 0 || w->N == 0) return B200Q4_OK;
+    if (int rc = ensure(g.d_x, g.x_cap, (size_t)M * w->K * 4)) return rc;
+    if (int rc = ensure(g.d_y, g.y_cap, (size_t)M * w->N * 4)) return rc;
+    CK(cudaMemcpy2DAsync(g.d_x, (size_t)w->K * 4, x, x_stride, (size_t)w->K * 4, M, cudaMemcpyHostToDevice, g.stream));
+    if (int rc = mul_mat_dev_locked(w, g.d_x, M, (size_t)w->K * 4, g.d_y, (size_t)w->N * 4, g.stream, nullptr)) return rc;
+    CK(cudaMemcpy2DAsync(y, y_stride, g.d_y, (size_t)w->N * 4, (size_t)w->N * 4, M, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return B200Q4_OK;
+}
+
+int b200q4_mul_mat_wdata(const b200q4_weight *w, const void *wdata, int M, float *y, size_t y_stride)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    if (!w || w->transposed || M < 0 || (M > 0 && (!wdata || !y))) return fail(B200Q4_EINVAL, "mul_mat_wdata: bad argument");
+    if (y_stride == 0) y_stride = (size_t)w->N * 4;
+    if (y_stride < (size_t)w->N * 4) return fail(B200Q4_EINVAL, "mul_mat_wdata: stride smaller than a row");
+    if (M == 0 || w->N == 0) return B200Q4_OK;
+    const size_t rb = (size_t)w->nb * (w->type == 0 ? 20 : 24);
+    if (int rc = ensure(g.d_tmp, g.tmp_cap, rb * (size_t)M)) return rc;
+    if (int rc = ensure(g.d_y, g.y_cap, (size_t)M * w->N * 4)) return rc;
+    CK(cudaMemcpyAsync(g.d_tmp, wdata, rb * (size_t)M, cudaMemcpyHostToDevice, g.stream));
+    if (int rc = mul_mat_dev_locked(w, nullptr, M, (size_t)w->K * 4, g.d_y, (size_t)w->N * 4, g.stream, g.d_tmp)) return rc;
+    CK(cudaMemcpy2DAsync(y, y_stride, g.d_y, (size_t)w->N * 4, (size_t)w->N * 4, M, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return B200Q4_OK;
+}
+
+int b200q4_quantize_rows_dev(int type, const float *d_x, int M, int K, size_t x_stride, void *d_out, void *stream)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    if ((type != 0 && type != 1) || M < 0 || K < 0 || K % QK != 0 || (M > 0 && K > 0 && (!d_x || !d_out)))
+        return fail(B200Q4_EINVAL, "quantize_rows: bad argument");
+    if (x_stride == 0) x_stride = (size_t)K * 4;
+    if (x_stride % 4) return fail(B200Q4_EINVAL, "quantize_rows: stride must be a multiple of 4 bytes");
+    if (M == 0 || K == 0) return B200Q4_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
+    const int nb = K / QK;
+    const long warps = (long)nb * M;
+    const int blocks = (int)((warps * 32 + 255) / 256);
+    if (type == 0) quantize_rows_ref_kernel<0><<<blocks, 256, 0, st>>>(d_x, x_stride / 4, M, nb, (uint8_t *)d_out);
+    else           quantize_rows_ref_kernel<1><<<blocks, 256, 0, st>>>(d_x, x_stride / 4, M, nb, (uint8_t *)d_out);
+    g.launches++;
+    CK(cudaGetLastError());
+    return B200Q4_OK;
+}
+
+int b200q4_quantize_rows(int type, const float *x, int M, int K, size_t x_stride, void *out)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    if ((type != 0 && type != 1) || M < 0 || K < 0 || K % QK != 0 || (M > 0 && K > 0 && (!x || !out)))
+        return fail(B200Q4_EINVAL, "quantize_rows: bad argument");
+    if (M == 0 || K == 0) return B200Q4_OK;
+    if (x_stride == 0) x_stride = (size_t)K * 4;
+    const size_t rb = (size_t)(K / QK) * (type == 0 ? 20 : 24);
+    if (int rc = ensure(g.d_x, g.x_cap, (size_t)M * K * 4)) return rc;
+    if (int rc = ensure(g.d_tmp, g.tmp_cap, rb * (size_t)M)) return rc;
+    CK(cudaMemcpy2DAsync(g.d_x, (size_t)K * 4, x, x_stride, (size_t)K * 4, M, cudaMemcpyHostToDevice, g.stream));
+    if (int rc = b200q4_quantize_rows_dev(type, g.d_x, M, K, (size_t)K * 4, g.d_tmp, g.stream)) return rc;
+    CK(cudaMemcpyAsync(out, g.d_tmp, rb * (size_t)M, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return B200Q4_OK;
+}
+
+int b200q4_mul_mat_transposed(const b200q4_weight *wt, const float *x, int M, size_t x_stride, float *y, size_t y_stride)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    if (!wt || !wt->transposed || M < 0 || (M > 0 && (!x || !y))) return fail(B200Q4_EINVAL, "mul_mat_transposed: bad argument");
+    const int N = wt->N, K = wt->K;
+    if (x_stride == 0) x_stride = (size_t)K * 4;
+    if (y_stride == 0) y_stride = (size_t)N * 4;
+    if (M == 0 || N == 0) return B200Q4_OK;
+    if (int rc = ensure(g.d_x, g.x_cap, (size_t)M * (K > 0 ? K : 1) * 4)) return rc;
+    if (int rc = ensure(g.d_y, g.y_cap, (size_t)M * N * 4)) return rc;
+    if (K > 0) CK(cudaMemcpy2DAsync(g.d_x, (size_t)K * 4, x, x_stride, (size_t)K * 4, M, cudaMemcpyHostToDevice, g.stream));
+    dim3 grid((N + 127) / 128, M);
+    if (wt->type == 0) mul_mat_transposed_kernel<0><<<grid, 128, 0, g.stream>>>(wt->d_wt, N, K, g.d_x, K, M, g.d_y, N);
+    else               mul_mat_transposed_kernel<1><<<grid, 128, 0, g.stream>>>(wt->d_wt, N, K, g.d_x, K, M, g.d_y, N);
+    g.launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2DAsync(y, y_stride, g.d_y, (size_t)N * 4, (size_t)N * 4, M, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return B200Q4_OK;
+}
+
+int b200q4_sync(void *stream)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    CK(cudaStreamSynchronize(stream ? (cudaStream_t)stream : g.stream));
+    return B200Q4_OK;
+}
+
+void *b200q4_host_alloc(size_t bytes)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (need_init()) return nullptr;
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        fail(B200Q4_ENOMEM, "cudaMallocHost(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void b200q4_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+uint64_t b200q4_launch_count(void) { return g.launches; }
+void b200q4_launch_count_reset(void) { g.launches = 0; }
+
+const char *b200q4_kernel_for(int type, int M, int N, int K)
+{
+    (void)N;
+    if ((type != 0 && type != 1) || K <= 0 || K % QK) return "invalid";
+    const int nbp = ((K / QK + CHUNK_BLKS - 1) / CHUNK_BLKS) * CHUNK_BLKS;
+    return plan_for(type, M < 1 ? 1 : M, nbp).name;
+}
+
+double b200q4_time_mul_mat_dev(b200q4_weight *const *ws, int nw, const float *d_x, int M, float *d_y, int iters)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    if (!ws || nw < 1 || iters < 1) return fail(B200Q4_EINVAL, "time_mul_mat_dev: bad argument");
+    if (cudaEventRecord(g.ev0, g.stream) != cudaSuccess) return fail(B200Q4_ECUDA, "event record failed");
+    for (int i = 0; i < iters; i++) {
+        const b200q4_weight *w = ws[i % nw];
+        if (int rc = mul_mat_dev_locked(w, d_x, M, (size_t)w->K * 4, d_y, (size_t)w->N * 4, g.stream, nullptr)) return rc;
+    }
+    if (cudaEventRecord(g.ev1, g.stream) != cudaSuccess) return fail(B200Q4_ECUDA, "event record failed");
+    if (cudaEventSynchronize(g.ev1) != cudaSuccess) return fail(B200Q4_ECUDA, "event sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+    return (double)ms / iters;
+}
+
+} // extern "C"
