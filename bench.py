@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: Q4 mul_mat GB/s and % of HBM peak.
+
+Workload (BASELINE.json configs[1]): Q4_0 / Q4_1 mul_mat microbench, K=4096, N=16384 weight rows
+per GPU, M in {1, 8, 64, 512}.  One *step* = one pass of the hot path (activation-row quantization +
+q4 x q4 block dot products = ggml_compute_forward_mul_mat_q4_0_f32's INIT + COMPUTE phases) for the
+headline point Q4_0, M=1 (the decode GEMV the north star quotes its 80 %-of-HBM target on); the other
+(type, M) points are timed the same way and reported under "points".
+
+  value      algorithmic GB/s ( W + 4MK + 4MN bytes per call, SURVEY.md section 8d ) with all inputs
+             resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e        the same metric through the C ABI call a ggml hook makes (b200q4_mul_mat) with HOST
+             buffers: H2D of X and D2H of Y inside the timed region
+  roofline   the dominant kernel (q4_gemv) timed alone with CUDA events, against MEASURED_PEAKS.json
+  cpu_baseline  the reference's own scalar CPU path (oracle/_ref, else the oracle port) on this box
+
+L2: every timed loop rotates over enough distinct weight tensors (> 3x the 126 MB L2) that no call
+finds its weights cached.  N>1: each rank owns a 16384-row shard of a (16384*N)-row tensor (row
+split of imax.c:1185-1188), X is replicated, the fp32 output slices are all-gathered over NCCL;
+weak scaling.  `--impl reference` times the reference CPU implementation on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+K_DIM, N_ROWS = 4096, 16384
+METRIC = "Q4 mul_mat GB/s & %HBM peak"
+L2_BYTES = 126e6
+
+
+def alg_bytes(qt: int, m: int, n: int = N_ROWS, k: int = K_DIM) -> int:
+    return n * (k // 32) * (20 if qt == 0 else 24) + 4 * m * k + 4 * m * n
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock, power and throttle reasons through NVML while the GPU phase runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:            # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                self.samples.append((sm, rs, util))
+            except Exception:             # noqa: BLE001
+                pass
+            time.sleep(0.01)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+            getattr(nv, "nvmlClocksEventReasonApplicationsClocksSetting", 0x2): "applications_clocks_setting",
+        }
+        busy = [s for s in self.samples if s[2] > 0] or self.samples
+        reasons = set()
+        for _, rs, _ in busy:
+            for bit, nm in names.items():
+                if rs & bit:
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median([s[0] for s in busy])), "sm_max_mhz": float(self.max_sm),
+                "reasons": sorted(reasons), "samples": len(busy)}
+
+
+def make_weights(vs, qt: int, count: int, seed: int, n: int = N_ROWS, k: int = K_DIM):
+    """Random-init fp32 U(-0.05, 0.05) weights, quantized to the reference row format by the product's
+    own GPU quantizer (byte-identical to quantize_row_q4_x, tests/test_gpu_parity.py), then uploaded."""
+    rng = np.random.default_rng(seed)
+    ws, first_bytes = [], None
+    for i in range(count):
+        wf = rng.uniform(-0.05, 0.05, (n, k)).astype(np.float32)
+        wq = vs.quantize_rows(qt, wf)
+        if first_bytes is None:
+            first_bytes = wq
+        ws.append(vs.Q4Weight(qt, wq, n, k))
+    return ws, first_bytes
+
+
+def cpu_baseline(qt: int, m: int, wq: np.ndarray, x: np.ndarray, budget_s: float = 12.0):
+    """The reference's CPU path on this box's host cores (rank 0, N=1 only).  The one place bench.py
+    touches oracle/: as the measured baseline, never on the product path."""
+    import oracle as orc
+    cores = os.cpu_count() or 1
+    nth = min(cores, 16)                    # MAX_NTHREAD 16, ggml.h:181
+    nbytes = alg_bytes(qt, m)
+    if orc.have_reference():
+        ref = orc.Reference()
+        kind = "reference"
+        _, us1 = ref.mul_mat(qt, wq, N_ROWS, K_DIM, x, nth=nth, reps=1, return_time=True)
+        reps = int(max(3, min(200, budget_s / max(us1 * 1e-6, 1e-4))))
+        _, us = ref.mul_mat(qt, wq, N_ROWS, K_DIM, x, nth=nth, reps=reps, return_time=True)
+        sample = (f"oracle/_ref (reference ggml.c+imax.c, Makefile-ubuntu flags) ggml_graph_compute of one "
+                  f"Q4_{qt} mul_mat K={K_DIM} N={N_ROWS} M={m}, best of {reps} calls, {nth} threads")
+    else:
+        o = orc.Oracle()
+        kind = "port"
+        t0 = time.perf_counter(); o.mul_mat(qt, wq, N_ROWS, K_DIM, x, nth=nth); us1 = (time.perf_counter() - t0) * 1e6
+        reps = int(max(3, min(200, budget_s / max(us1 * 1e-6, 1e-4))))
+        us = us1
+        for _ in range(reps):
+            t0 = time.perf_counter(); o.mul_mat(qt, wq, N_ROWS, K_DIM, x, nth=nth)
+            us = min(us, (time.perf_counter() - t0) * 1e6)
+        sample = (f"oracle port (q4_oracle.c) of one Q4_{qt} mul_mat K={K_DIM} N={N_ROWS} M={m}, "
+                  f"best of {reps} calls, {nth} threads")
+    return {"value": nbytes / (us * 1e-6) / 1e9, "unit": "GB/s", "cores": nth, "kind": kind,
+            "sample": sample, "ms_per_call": us / 1e3}
+
+
+def run_reference(args) -> int:
+    """--impl reference: the reference's own CPU implementation of the path, same config/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle as orc
+    qt, m = 0, 1
+    rng = np.random.default_rng(1234)
+    o = orc.Oracle()
+    have_ref = orc.have_reference()
+    impl = orc.Reference() if have_ref else o
+    wq = impl.quantize_rows(qt, rng.uniform(-0.05, 0.05, (N_ROWS, K_DIM)).astype(np.float32))
+    x = np.random.default_rng(5678).standard_normal((m, K_DIM)).astype(np.float32)
+    cores = os.cpu_count() or 1
+    nth = min(cores, 16)
+    steps, warm = args.steps, args.warmup
+    steps = min(steps, 2000)
+
+    def one():
+        if have_ref:
+            impl.mul_mat(qt, wq, N_ROWS, K_DIM, x, nth=nth)
+        else:
+            impl.mul_mat(qt, wq, N_ROWS, K_DIM, x, nth=nth)
+    for _ in range(warm):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    nbytes = alg_bytes(qt, m)
+    val = nbytes * steps / dt / 1e9
+    kind = "reference" if have_ref else "port"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (scalar fp32 dequant-dot, ggml.c:472-553)", "data": "synthetic",
+        "config": {"workload": f"Q4_0 mul_mat microbench K={K_DIM} N={N_ROWS} M={m} (BASELINE.json configs[1])",
+                   "step": "one ggml_mul_mat + ggml_graph_compute on host memory (includes the reference's per-call "
+                           "ggml_init/memcpy of the harness)" if have_ref else "one q4o_mul_mat call",
+                   "threads": nth},
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": nth, "kind": kind,
+                         "sample": f"{steps} timed calls after {warm} warm-up, {nth} threads, wall clock"},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-points", action="store_true", help="skip the (type, M) sweep")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import vsim_b200 as vs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 back-end has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    vs.init(local)
+    L = vs.load_library()
+    peak, peak_src = measured_peak()
+    sampler = ClockSampler(local)
+    stream = torch.cuda.Stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- data ---------------------------------------------------------------------------------
+    nw = 10                                                     # 10 x 42 MB = 420 MB  >  3 x L2
+    w0, w0_bytes = make_weights(vs, 0, nw, seed=1234 + rank)
+    x_host = np.random.default_rng(5678).standard_normal((512, K_DIM)).astype(np.float32)
+    d_x = torch.from_numpy(x_host).cuda()
+    d_y = torch.empty(512, N_ROWS * world, device="cuda", dtype=torch.float32)
+    d_yloc = torch.empty(512, N_ROWS, device="cuda", dtype=torch.float32)
+    handles0 = (C.c_void_p * nw)(*[w.handle for w in w0])
+
+    def step(i: int, m: int, ws, st):
+        """one pass of the hot path on device-resident inputs (+ the all-gather of output slices at N>1)"""
+        w = ws[i % len(ws)]
+        rc = L.b200q4_mul_mat_dev(w.handle, d_x.data_ptr(), m, K_DIM * 4, d_yloc.data_ptr(), N_ROWS * 4, st.cuda_stream)
+        if rc:
+            raise RuntimeError(vs.lib._err(L))
+        if world > 1:
+            # Y is [M][N_total]: rank r's slice is columns [r*N, (r+1)*N); gather as [world][M][N]
+            dist.all_gather_into_tensor(d_y.view(-1)[: world * m * N_ROWS].view(world, m, N_ROWS), d_yloc[:m])
+
+    def timed(m: int, ws, steps: int, warm: int):
+        with torch.cuda.stream(stream):
+            for i in range(warm):
+                step(i, m, ws, stream)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(steps):
+                step(warm + i, m, ws, stream)
+            e1.record(stream)
+            barrier()
+            ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler.start()
+    # ---- headline: Q4_0, M=1, K steps -----------------------------------------------------------
+    M_HEAD = 1
+    vs.launch_count_reset()
+    ms_total = timed(M_HEAD, w0, args.steps, args.warmup)
+    launches_total = vs.launch_count()
+    launches_timed = launches_total * args.steps // (args.steps + args.warmup)
+    ms_step = ms_total / args.steps
+    value = alg_bytes(0, M_HEAD) * world / (ms_step * 1e-3) / 1e9
+
+    # ---- roofline: the dominant kernel alone (pack once, then the GEMV kernel back to back) --------
+    kern_ms = L.b200q4_time_mul_mat_dev(handles0, nw, d_x.data_ptr(), M_HEAD, d_yloc.data_ptr(), max(args.steps, 200))
+    if kern_ms < 0:
+        raise RuntimeError(vs.lib._err(L))
+    achieved = alg_bytes(0, M_HEAD) / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.load(open(tp)).get("q4_0_m1_dram_bytes_per_launch")
+        except Exception:                  # noqa: BLE001
+            traffic = None
+
+    # ---- e2e: host buffers through the C ABI --------------------------------------------------------
+    hx = L.b200q4_host_alloc(M_HEAD * K_DIM * 4)
+    hy = L.b200q4_host_alloc(M_HEAD * N_ROWS * 4)
+    C.memmove(hx, x_host.ctypes.data, M_HEAD * K_DIM * 4)
+    for i in range(args.warmup):
+        L.b200q4_mul_mat(w0[i % nw].handle, hx, M_HEAD, K_DIM * 4, hy, N_ROWS * 4)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        rc = L.b200q4_mul_mat(w0[(args.warmup + i) % nw].handle, hx, M_HEAD, K_DIM * 4, hy, N_ROWS * 4)
+        if rc:
+            raise RuntimeError(vs.lib._err(L))
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = alg_bytes(0, M_HEAD) * world * args.steps / e2e_s / 1e9
+    y_e2e = np.ctypeslib.as_array(C.cast(hy, C.POINTER(C.c_float)), shape=(M_HEAD, N_ROWS)).copy()
+
+    # ---- the other (type, M) points -----------------------------------------------------------------
+    points = []
+    if not args.no_points:
+        w1, w1_bytes = make_weights(vs, 1, nw, seed=4321 + rank)
+        for qt, ws in ((0, w0), (1, w1)):
+            for m in (1, 8, 64, 512):
+                iters = {1: 300, 8: 300, 64: 100, 512: 20}[m]
+                ms = timed(m, ws, iters, 5) / iters
+                gbs = alg_bytes(qt, m) * world / (ms * 1e-3) / 1e9
+                points.append({"type": f"q4_{qt}", "M": m, "us_per_call": ms * 1e3, "GBps": gbs,
+                               "frac_hbm_peak": gbs / (peak * world),
+                               "TFLOPs": 2.0 * m * N_ROWS * world * K_DIM / (ms * 1e-3) / 1e12,
+                               "kernel": vs.kernel_for(qt, m, N_ROWS, K_DIM)})
+        for w in w1:
+            w.free()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- CPU baseline (rank 0, N=1) --------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(0, M_HEAD, w0_bytes, x_host[:M_HEAD])
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/s8 -> s32 block sums (IMMA), fp32 scales", "data": "synthetic",
+            "config": {
+                "workload": f"Q4_0 mul_mat microbench K={K_DIM} N={N_ROWS} M={M_HEAD} per GPU (BASELINE.json configs[1]; "
+                            f"decode GEMV); other (type, M) points under 'points'",
+                "weights": "random-init fp32 U(-0.05,0.05), seed 1234, quantized to the reference Q4 row format",
+                "activations": "fp32 N(0,1), seed 5678, quantized on the device every step",
+                "l2": f"defeated: every loop rotates over {nw} distinct {alg_bytes(0, 0) / 1e6:.0f} MB weight tensors "
+                      f"({nw * alg_bytes(0, 0) / 1e6:.0f} MB > 3x the 126 MB L2)",
+                "parallelism": "single GPU" if world == 1 else
+                               f"{world}-way row shard of a {N_ROWS * world}-row tensor + NCCL all-gather of fp32 output slices",
+                "kernel": vs.kernel_for(0, M_HEAD, N_ROWS, K_DIM),
+                "frac_hbm_peak": value / (peak * world),
+            },
+            "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": M_HEAD * K_DIM * 4,
+                    "d2h_bytes_per_step": M_HEAD * N_ROWS * 4, "us_per_call": e2e_s / args.steps * 1e6,
+                    "api": "b200q4_mul_mat (C ABI, pinned host X and Y, synchronous)"},
+            "gpu_launches": int(launches_timed),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "pack_act_kernel + q4_gemv_kernel (Q4_0, M=1), CUDA events on the library stream, "
+                                   "back-to-back launches rotating weights",
+                         "algorithmic_bytes_per_launch": alg_bytes(0, M_HEAD), "us_per_launch": kern_ms * 1e3},
+            "clocks": sampler.summary(),
+            "points": points,
+            "checksum_y": float(np.abs(y_e2e).sum()),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    L.b200q4_host_free(hx)
+    L.b200q4_host_free(hy)
+    for w in w0:
+        w.free()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
