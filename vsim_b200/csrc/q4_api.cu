@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -32,6 +33,9 @@ struct Ctx {
     uint8_t *d_aq = nullptr; size_t aq_cap = 0;
     float *d_ap = nullptr;   size_t ap_cap = 0;
     float *d_partial = nullptr; size_t partial_cap = 0;
+    int *d_ticket = nullptr;         // [2] task ticket + CTAs-done, self-resetting
+    int gemv_version = 2;            // B200Q4_GEMV=1 selects the register-ring kernel (A/B testing)
+    bool use_pdl = true;             // B200Q4_PDL=0 disables programmatic dependent launch
     float *d_x = nullptr;    size_t x_cap = 0;
     float *d_y = nullptr;    size_t y_cap = 0;
     uint8_t *d_tmp = nullptr; size_t tmp_cap = 0;
@@ -82,63 +86,139 @@ int need_init()
 }
 
 // ---- kernel selection -------------------------------------------------------
-struct Plan { int NT; int Mc; size_t smem; const char *name; };
+// MP = padded activation rows per launch: 2 -> "chain4" decode kernel (fused activation
+// quantization when the input is fp32), 8 -> one IMMA per block.
+struct Plan { int MP; size_t smem; const char *name; };
 
-// rows of X handled per launch: as many as the activation pack allows in shared memory
+// shared memory of the GEMV kernel: codes always in the 8-column form, parameter planes [nbp][MP]
+size_t apack_bytes(int type, int nbp, int MP) { return (size_t)nbp * (8 * 32 + (size_t)MP * (type == 0 ? 1 : 3) * 4); }
+
 Plan plan_for(int type, int M, int nbp)
 {
-    const size_t per_row = (size_t)nbp * (32 + ap_floats(type) * 4);
-    const size_t budget = (size_t)(g.smem_optin > 0 ? g.smem_optin : 232448) - 1024;
-    int mc = (int)(budget / per_row);
-    if (mc > 16) mc = 16;
-    if (mc > M) mc = M;
-    if (mc < 1) mc = 0;
+    const size_t budget = (size_t)(g.smem_optin > 0 ? g.smem_optin : 232448);
     Plan p;
-    p.Mc = mc;
-    p.NT = mc > 8 ? 2 : 1;
-    p.smem = per_row * mc;
-    p.name = type == 0 ? (p.NT == 1 ? "q4_0_gemv_imma_nt1" : "q4_0_gemv_imma_nt2")
-                       : (p.NT == 1 ? "q4_1_gemv_imma_nt1" : "q4_1_gemv_imma_nt2");
+    p.MP = (M <= 2 || apack_bytes(type, nbp, 8) > budget) ? 2 : 8;
+    p.smem = apack_bytes(type, nbp, p.MP);
+    if (p.smem > budget) { p.MP = 0; p.smem = 0; p.name = "none"; return p; }
+    p.name = type == 0 ? (p.MP == 2 ? "q4_0_gemv_imma_chain4" : "q4_0_gemv_imma_m8")
+                       : (p.MP == 2 ? "q4_1_gemv_imma_chain4" : "q4_1_gemv_imma_m8");
     return p;
 }
 
-template <int QT, int NT, int PD>
+template <int QT, int MP, int PD, bool FUSED>
 int launch_gemv(const GemvParams &p, int grid, size_t smem, cudaStream_t st)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        CK(cudaFuncSetAttribute(q4_gemv_kernel<QT, NT, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CK(cudaFuncSetAttribute(q4_gemv_kernel<QT, MP, PD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 g.smem_optin));
         attr_set = true;
     }
-    q4_gemv_kernel<QT, NT, PD><<<grid, GEMV_THREADS, smem, st>>>(p);
+    q4_gemv_kernel<QT, MP, PD, FUSED><<<grid, GEMV_THREADS, smem, st>>>(p);
     g.launches++;
     CK(cudaGetLastError());
     return B200Q4_OK;
 }
 
-// one pass of the hot path for Mc <= 16 activation rows whose apack is already in g.d_aq/g.d_ap
-int run_gemv(const b200q4_weight *w, int Mc, const Plan &pl, float *d_y, size_t y_stride_f, cudaStream_t st)
+// ---- pipelined decode kernel (q4_gemv_pipe_kernel) ---------------------------------------------
+struct PipePlan { int MP, stages, PP, TS, ntasks; size_t smem; };
+
+PipePlan pipe_plan(const b200q4_weight *w, int M)
+{
+    PipePlan pp{};
+    const int type = w->type, nbp = w->C * CHUNK_BLKS;
+    const size_t budget = (size_t)(g.smem_optin > 0 ? g.smem_optin : 232448);
+    const size_t stage = (size_t)PIPE_CONSUMERS * chunk_bytes(type) + (size_t)PIPE_CONSUMERS * 512;
+    auto fixed = [&](int MP) {
+        const size_t planes = ((size_t)(type == 0 ? 1 : 3) * nbp * MP * 4 + 15) & ~(size_t)15;
+        return (size_t)nbp * MP * 32 + planes + 3 * PIPE_MAX_STAGES * 8 + PIPE_MAX_STAGES * 16 + 256;
+    };
+    pp.MP = (M <= 2) ? 2 : 8;
+    if (pp.MP == 8 && fixed(8) + 2 * stage > budget) pp.MP = 2;
+    if (fixed(pp.MP) + 2 * stage > budget) { pp.MP = 0; return pp; }
+    long st = (long)((budget - fixed(pp.MP)) / stage);
+    pp.stages = (int)(st > PIPE_MAX_STAGES ? PIPE_MAX_STAGES : st);
+    pp.smem = fixed(pp.MP) + (size_t)pp.stages * stage;
+    const int C = w->C;
+    if (C >= PIPE_CONSUMERS) {
+        pp.PP = (C + 63) / 64;
+        pp.TS = (C + pp.PP - 1) / pp.PP;
+        pp.ntasks = w->n_tiles * pp.PP;
+    } else {
+        pp.PP = 1;
+        const int G = 32 / C > 0 ? 32 / C : 1;
+        pp.TS = G * C;
+        pp.ntasks = (int)(((long)w->n_tiles * C + pp.TS - 1) / pp.TS);
+    }
+    return pp;
+}
+
+template <int QT, int MP, bool FUSED>
+int launch_pipe(const PipeParams &p, int grid, size_t smem, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(q4_gemv_pipe_kernel<QT, MP, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_optin));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PIPE_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g.use_pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, q4_gemv_pipe_kernel<QT, MP, FUSED>, p));
+    g.launches++;
+    return B200Q4_OK;
+}
+
+int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, const float *d_x, size_t x_stride_f,
+             float *d_y, size_t y_stride_f, cudaStream_t st)
+{
+    PipeParams p;
+    p.wt = w->d_wt; p.x = d_x; p.aq = g.d_aq; p.ap = g.d_ap; p.y = d_y; p.partial = g.d_partial;
+    p.tile_counters = w->d_counters; p.ticket = g.d_ticket;
+    p.x_stride = x_stride_f; p.y_stride = y_stride_f;
+    p.U = w->n_tiles * w->C; p.N = w->N; p.M = mc; p.C = w->C; p.n_tiles = w->n_tiles; p.nb = w->nb;
+    p.ntasks = pl.ntasks; p.PP = pl.PP; p.TS = pl.TS; p.stages = pl.stages;
+    const int grid = pl.ntasks < g.sms ? pl.ntasks : g.sms;
+    if (w->type == 0) {
+        if (pl.MP == 2) return fused ? launch_pipe<0, 2, true>(p, grid, pl.smem, st) : launch_pipe<0, 2, false>(p, grid, pl.smem, st);
+        return launch_pipe<0, 8, false>(p, grid, pl.smem, st);
+    }
+    if (pl.MP == 2) return fused ? launch_pipe<1, 2, true>(p, grid, pl.smem, st) : launch_pipe<1, 2, false>(p, grid, pl.smem, st);
+    return launch_pipe<1, 8, false>(p, grid, pl.smem, st);
+}
+
+// one pass of the hot path for mc <= MP activation rows.  fused: quantize from d_x inside the
+// kernel (MP == 2 only); otherwise the apack is already in g.d_aq / g.d_ap.
+int run_gemv(const b200q4_weight *w, int mc, const Plan &pl, bool fused, const float *d_x, size_t x_stride_f,
+             float *d_y, size_t y_stride_f, cudaStream_t st)
 {
     GemvParams p;
-    p.wt = w->d_wt; p.aq = g.d_aq; p.ap = g.d_ap; p.y = d_y; p.partial = g.d_partial; p.counters = w->d_counters;
-    p.y_stride = y_stride_f;
-    p.U = (long)w->n_tiles * w->C;
-    p.N = w->N; p.M = Mc; p.C = w->C; p.n_tiles = w->n_tiles;
+    p.wt = w->d_wt; p.x = d_x; p.aq = g.d_aq; p.ap = g.d_ap; p.y = d_y; p.partial = g.d_partial; p.counters = w->d_counters;
+    p.x_stride = x_stride_f; p.y_stride = y_stride_f;
+    if ((long)w->n_tiles * w->C > 0x7fffffffL) return fail(B200Q4_EINVAL, "tensor too large: %ld units", (long)w->n_tiles * w->C);
+    p.U = w->n_tiles * w->C;
+    p.N = w->N; p.M = mc; p.C = w->C; p.n_tiles = w->n_tiles; p.nb = w->nb;
     long warps = (long)g.sms * GEMV_WARPS;
     p.Weff = (int)(p.U < warps ? p.U : warps);
     const int grid = (p.Weff + GEMV_WARPS - 1) / GEMV_WARPS;
-    if (w->type == 0) return pl.NT == 1 ? launch_gemv<0, 1, 4>(p, grid, pl.smem, st) : launch_gemv<0, 2, 4>(p, grid, pl.smem, st);
-    return pl.NT == 1 ? launch_gemv<1, 1, 3>(p, grid, pl.smem, st) : launch_gemv<1, 2, 3>(p, grid, pl.smem, st);
+    if (w->type == 0) {
+        if (pl.MP == 2) return fused ? launch_gemv<0, 2, 4, true>(p, grid, pl.smem, st) : launch_gemv<0, 2, 4, false>(p, grid, pl.smem, st);
+        return launch_gemv<0, 8, 4, false>(p, grid, pl.smem, st);
+    }
+    if (pl.MP == 2) return fused ? launch_gemv<1, 2, 4, true>(p, grid, pl.smem, st) : launch_gemv<1, 2, 4, false>(p, grid, pl.smem, st);
+    return launch_gemv<1, 8, 4, false>(p, grid, pl.smem, st);
 }
 
-int ensure_scratch(const b200q4_weight *w, int Mc)
+int ensure_scratch(const b200q4_weight *w, int MP)
 {
     const int nbp = w->C * CHUNK_BLKS;
     int rc;
-    if ((rc = ensure(g.d_aq, g.aq_cap, (size_t)nbp * Mc * 32))) return rc;
-    if ((rc = ensure(g.d_ap, g.ap_cap, (size_t)nbp * Mc * 16))) return rc;
-    if ((rc = ensure(g.d_partial, g.partial_cap, (size_t)2 * g.sms * GEMV_WARPS * 2 * 4 * 32 * sizeof(float)))) return rc;
+    if ((rc = ensure(g.d_aq, g.aq_cap, (size_t)nbp * MP * 32))) return rc;
+    if ((rc = ensure(g.d_ap, g.ap_cap, (size_t)nbp * MP * 12))) return rc;
+    if ((rc = ensure(g.d_partial, g.partial_cap, (size_t)2 * g.sms * GEMV_WARPS * 128 * sizeof(float)))) return rc;
     return B200Q4_OK;
 }
 
@@ -148,31 +228,47 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
     if (!w || w->transposed || M < 0 || (!d_x && !d_wdata) || !d_y) return fail(B200Q4_EINVAL, "mul_mat: bad argument");
     if ((x_stride % 4) || (y_stride % 4)) return fail(B200Q4_EINVAL, "mul_mat: strides must be multiples of 4 bytes");
     if (M == 0 || w->N == 0) return B200Q4_OK;
+    if ((long)w->n_tiles * w->C > 0x7fffffffL) return fail(B200Q4_EINVAL, "tensor too large");
     const int nbp = w->C * CHUNK_BLKS;
-    const Plan pl = plan_for(w->type, M, nbp);
-    if (pl.Mc < 1) return fail(B200Q4_EINVAL, "mul_mat: K=%d too large for the shared-memory activation pack", w->K);
+    const bool v2 = g.gemv_version == 2;
+    PipePlan pp{};
+    Plan pl{};
+    int MP;
+    if (v2) {
+        pp = pipe_plan(w, M);
+        MP = pp.MP;
+    } else {
+        pl = plan_for(w->type, M, nbp);
+        MP = pl.MP;
+    }
+    if (MP < 1) return fail(B200Q4_EINVAL, "mul_mat: K=%d too large for the shared-memory activation pack", w->K);
     int rc;
-    if ((rc = ensure_scratch(w, pl.Mc))) return rc;
+    if ((rc = ensure_scratch(w, MP))) return rc;
+    if (v2 && pp.PP > 1 && (rc = ensure(g.d_partial, g.partial_cap, (size_t)pp.ntasks * 128 * sizeof(float)))) return rc;
     const size_t rbw = (size_t)w->nb * (w->type == 0 ? 20 : 24);
-    for (int m0 = 0; m0 < M; m0 += pl.Mc) {
-        const int mc = (M - m0 < pl.Mc) ? M - m0 : pl.Mc;
-        Plan p2 = pl;
-        if (mc != pl.Mc) p2 = plan_for(w->type, mc, nbp);
-        const long warps = (long)nbp * mc;
-        const int blocks = (int)((warps * 32 + 255) / 256);
-        if (d_wdata) {
-            const uint8_t *src = d_wdata + (size_t)m0 * rbw;
-            if (w->type == 0) pack_wdata_kernel<0><<<blocks, 256, 0, st>>>(src, mc, w->nb, nbp, g.d_aq, g.d_ap);
-            else              pack_wdata_kernel<1><<<blocks, 256, 0, st>>>(src, mc, w->nb, nbp, g.d_aq, g.d_ap);
-        } else {
-            const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(d_x) + (size_t)m0 * x_stride);
-            if (w->type == 0) pack_act_kernel<0><<<blocks, 256, 0, st>>>(src, x_stride / 4, mc, w->nb, nbp, g.d_aq, g.d_ap);
-            else              pack_act_kernel<1><<<blocks, 256, 0, st>>>(src, x_stride / 4, mc, w->nb, nbp, g.d_aq, g.d_ap);
-        }
-        g.launches++;
-        CK(cudaGetLastError());
+    for (int m0 = 0; m0 < M; m0 += MP) {
+        const int mc = (M - m0 < MP) ? M - m0 : MP;
+        const float *xs = d_x ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(d_x) + (size_t)m0 * x_stride) : nullptr;
         float *yo = reinterpret_cast<float *>(reinterpret_cast<char *>(d_y) + (size_t)m0 * y_stride);
-        if ((rc = run_gemv(w, mc, p2, yo, y_stride / 4, st))) return rc;
+        // the fused prologue reads X with 128-bit loads
+        const bool fused = (MP == 2) && !d_wdata && (reinterpret_cast<uintptr_t>(xs) % 16 == 0) && (x_stride % 16 == 0);
+        if (!fused) {
+            const long warps = (long)nbp * MP;
+            const int blocks = (int)((warps * 32 + 255) / 256);
+            if (d_wdata) {
+                const uint8_t *src = d_wdata + (size_t)m0 * rbw;
+                if (w->type == 0) pack_wdata_kernel<0><<<blocks, 256, 0, st>>>(src, mc, MP, w->nb, nbp, g.d_aq, g.d_ap);
+                else              pack_wdata_kernel<1><<<blocks, 256, 0, st>>>(src, mc, MP, w->nb, nbp, g.d_aq, g.d_ap);
+            } else {
+                if (w->type == 0) pack_act_kernel<0><<<blocks, 256, 0, st>>>(xs, x_stride / 4, mc, MP, w->nb, nbp, g.d_aq, g.d_ap);
+                else              pack_act_kernel<1><<<blocks, 256, 0, st>>>(xs, x_stride / 4, mc, MP, w->nb, nbp, g.d_aq, g.d_ap);
+            }
+            g.launches++;
+            CK(cudaGetLastError());
+        }
+        if (v2) rc = run_pipe(w, mc, pp, fused, xs, x_stride / 4, yo, y_stride / 4, st);
+        else    rc = run_gemv(w, mc, pl, fused, xs, x_stride / 4, yo, y_stride / 4, st);
+        if (rc) return rc;
     }
     return B200Q4_OK;
 }
@@ -257,6 +353,10 @@ int b200q4_init(int device)
     CK(cudaEventCreate(&g.ev1));
     g.sms = prop.multiProcessorCount;
     g.smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CK(cudaMalloc(&g.d_ticket, 2 * sizeof(int)));
+    CK(cudaMemset(g.d_ticket, 0, 2 * sizeof(int)));
+    if (const char *e = getenv("B200Q4_GEMV")) g.gemv_version = atoi(e) == 1 ? 1 : 2;
+    if (const char *e = getenv("B200Q4_PDL")) g.use_pdl = atoi(e) != 0;
     g.device = device;
     g.launches = 0;
     return B200Q4_OK;
@@ -268,6 +368,7 @@ void b200q4_shutdown(void)
     if (g.device < 0) return;
     cudaSetDevice(g.device);
     cudaStreamSynchronize(g.stream);
+    cudaFree(g.d_ticket); g.d_ticket = nullptr;
     cudaFree(g.d_aq); cudaFree(g.d_ap); cudaFree(g.d_partial); cudaFree(g.d_x); cudaFree(g.d_y); cudaFree(g.d_tmp);
     g.d_aq = nullptr; g.d_ap = nullptr; g.d_partial = nullptr; g.d_x = nullptr; g.d_y = nullptr; g.d_tmp = nullptr;
     g.aq_cap = g.ap_cap = g.partial_cap = g.x_cap = g.y_cap = g.tmp_cap = 0;
@@ -492,8 +593,10 @@ const char *b200q4_kernel_for(int type, int M, int N, int K)
 {
     (void)N;
     if ((type != 0 && type != 1) || K <= 0 || K % QK) return "invalid";
-    const int nbp = ((K / QK + CHUNK_BLKS - 1) / CHUNK_BLKS) * CHUNK_BLKS;
-    return plan_for(type, M < 1 ? 1 : M, nbp).name;
+    const int mp = (M <= 2) ? 2 : 8;
+    if (g.gemv_version == 1)
+        return type == 0 ? (mp == 2 ? "q4_0_gemv_imma_chain4" : "q4_0_gemv_imma_m8") : (mp == 2 ? "q4_1_gemv_imma_chain4" : "q4_1_gemv_imma_m8");
+    return type == 0 ? (mp == 2 ? "q4_0_gemv_pipe_chain4" : "q4_0_gemv_pipe_m8") : (mp == 2 ? "q4_1_gemv_pipe_chain4" : "q4_1_gemv_pipe_m8");
 }
 
 double b200q4_time_mul_mat_dev(b200q4_weight *const *ws, int nw, const float *d_x, int M, float *d_y, int iters)

@@ -6,12 +6,12 @@
 // loops; the formulation is:
 //
 //   Y[m][n] = sum_blk d0[n,blk] * d1[m,blk] * ISUM[m,n,blk]                 (Q4_0)
-//   ISUM    = sum_{k in blk} (q0-8)(q1-8) = sum q0*a - 8*sum a,  a = q1-8    (exact, int32)
+//   ISUM    = sum_{k in blk} (q0-8)(q1-8)                                    (exact, int32)
 //   Y[m][n] = sum_blk d0*(d1*P + m1*S0) + m0*Z                              (Q4_1)
 //   P = sum q0*q1, S0 = sum q0, Z = d1*sum q1 + 32*m1                       (P, S0 exact)
 //
 // i.e. the 32-element integer block sums are computed exactly on the tensor
-// pipe (mma.sync m16n8k32 u8 x s8 -> s32: one instruction = 16 weight rows x
+// pipe (mma.sync m16n8k32 s8 x s8 -> s32: one instruction = 16 weight rows x
 // one quant block x 8 activation rows) and only the per-block fp32 scale
 // products are rounded -- tighter than the reference's own sequential fp32 sum.
 //
@@ -28,11 +28,12 @@
 //   region with 128-bit loads and the registers it receives ARE the mma A
 //   fragments (after two LOP3 per word to split nibbles).
 //
-// Activation pack ("apack", rebuilt per call by pack_act_kernel, ~1 us):
-//   aq[blk][m][32 B]: the 32 codes of block blk of row m as bytes (s8 = q-8 for
-//                     Q4_0, u8 = q for Q4_1), ordered so that an 8-byte read at
-//                     +8t is the mma B fragment of lane (g=m%8, t);
-//   ap[blk][m]:       Q4_0 {d1, -8*sum(a) as int bits}; Q4_1 {d1, m1, Z, 0}.
+// Activation pack ("apack"; built in shared memory by the GEMV prologue for M <= 2, by
+// pack_act_kernel otherwise), MP = padded row count (2 or 8):
+//   aq[blk][MP][32 B]: the 32 codes of block blk of row m as bytes (s8 = q-8 for
+//                      Q4_0, u8 = q for Q4_1), ordered so that the 8 bytes at +8t
+//                      are the mma B fragment of lane (g, t) for that row;
+//   ap planes [blk][MP] floats: d1 (Q4_0); d1, m1, Z = d1*sum(q1)+32*m1 (Q4_1).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -152,55 +153,121 @@ __device__ __forceinline__ BlockQ quantize_block(float x)
     return q;
 }
 
-// Writes one block's apack record (32 code bytes + parameters); aq/ap may be global or shared.
+// Writes one block's apack record: 32 code bytes at aq_rec and the block parameters into the
+// parameter planes (plane 0: d1; Q4_1 also plane 1: m1, plane 2: Z).  ap_rec points at this
+// (block,row)'s slot of plane 0; `plane` is the plane stride in floats.  Global or shared memory.
 template <int QT>
-__device__ __forceinline__ void emit_apack(const BlockQ &q, int lane, uint8_t *aq_rec, float *ap_rec)
+__device__ __forceinline__ void emit_apack(const BlockQ &q, int lane, uint8_t *aq_rec, float *ap_rec, int plane)
 {
     const int a = (QT == 0) ? (q.code & 15) - 8 : (q.code & 15);
     aq_rec[apack_byte_of(lane)] = (uint8_t)(int8_t)a;
-    int s = a;
+    if (QT == 0) {
+        if (lane == 0) ap_rec[0] = q.d;
+    } else {
+        int s = a;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-        if (QT == 0) {
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
             ap_rec[0] = q.d;
-            ap_rec[1] = __int_as_float(-8 * s);
-        } else {
-            ap_rec[0] = q.d;
-            ap_rec[1] = q.mn;
-            ap_rec[2] = fmaf(q.d, (float)s, 32.0f * q.mn);     // Z = sum_k dequant(a_k)
-            ap_rec[3] = 0.0f;
+            ap_rec[plane] = q.mn;
+            ap_rec[2 * plane] = fmaf(q.d, (float)s, 32.0f * q.mn);     // Z = sum_k dequant(a_k)
         }
     }
 }
 
-// fp32 rows -> apack.  grid: nbp*M warps.  Blocks >= nb (padding up to a multiple of 4) are zero.
+// Quad-parallel quantizer used by the fused GEMV prologue: a lane owns 8 consecutive elements
+// (element 8*tq .. 8*tq+7 of a block, tq = lane & 3), the 4 lanes of a quad own one block.  Same
+// arithmetic as quantize_block (bit-identical codes and scales), 8x fewer steps per block; its 8
+// codes are exactly words 2tq / 2tq+1 of the apack record, written with one 8-byte store.
+// All 32 lanes must call it (shuffles); `valid` masks the stores.
 template <int QT>
-__global__ void pack_act_kernel(const float *__restrict__ x, size_t x_stride, int M, int nb, int nbp,
+__device__ __forceinline__ void quantize8_emit(const float *x8, bool valid, int lane, uint8_t *aq_rec, float *ap_rec, int plane)
+{
+    const int tq = lane & 3, qbase = lane & 28;
+    float v[8];
+    if (valid) {
+        const float4 lo = *reinterpret_cast<const float4 *>(x8), hi = *reinterpret_cast<const float4 *>(x8 + 4);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = 0.0f;
+    }
+    int a[8];
+    float d, mn = 0.0f;
+    if (QT == 0) {
+        float amax = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+        d = __fdiv_rn(amax, 7.0f);
+        const float id = (d != 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = (int)(int8_t)round_to_int_ref(__fmul_rn(v[i], id));   // = code - 8
+    } else {
+        // strict left-to-right scans (ggml.c:268-274): first of several equal extrema wins
+        float lmn = v[0], lmx = v[0];
+#pragma unroll
+        for (int i = 1; i < 8; i++) { if (v[i] < lmn) lmn = v[i]; if (v[i] > lmx) lmx = v[i]; }
+        mn = __shfl_sync(0xffffffffu, lmn, qbase);
+        float mx = __shfl_sync(0xffffffffu, lmx, qbase);
+#pragma unroll
+        for (int j = 1; j < 4; j++) {
+            const float omn = __shfl_sync(0xffffffffu, lmn, qbase + j), omx = __shfl_sync(0xffffffffu, lmx, qbase + j);
+            if (omn < mn) mn = omn;
+            if (omx > mx) mx = omx;
+        }
+        d = __fdiv_rn(__fsub_rn(mx, mn), 15.0f);
+        const float id = (d != 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = (int)(uint8_t)round_to_int_ref(__fmul_rn(__fsub_rn(v[i], mn), id));
+    }
+    const uint32_t even = (uint32_t)(a[0] & 255) | ((uint32_t)(a[2] & 255) << 8) | ((uint32_t)(a[4] & 255) << 16) | ((uint32_t)(a[6] & 255) << 24);
+    const uint32_t odd  = (uint32_t)(a[1] & 255) | ((uint32_t)(a[3] & 255) << 8) | ((uint32_t)(a[5] & 255) << 16) | ((uint32_t)(a[7] & 255) << 24);
+    if (valid) *reinterpret_cast<uint2 *>(aq_rec + tq * 8) = make_uint2(even, odd);
+    if (QT == 0) {
+        if (valid && tq == 0) ap_rec[0] = d;
+    } else {
+        int sum = a[0] + a[1] + a[2] + a[3] + a[4] + a[5] + a[6] + a[7];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        if (valid && tq == 0) {
+            ap_rec[0] = d;
+            ap_rec[plane] = mn;
+            ap_rec[2 * plane] = fmaf(d, (float)sum, 32.0f * mn);
+        }
+    }
+}
+
+// fp32 rows -> apack [nbp][MP][32] + planes.  grid: nbp*MP warps.  Rows >= M and blocks >= nb
+// (padding up to a multiple of 4) are zero records.
+template <int QT>
+__global__ void pack_act_kernel(const float *__restrict__ x, size_t x_stride, int M, int MP, int nb, int nbp,
                                 uint8_t *__restrict__ aq, float *__restrict__ ap)
 {
     const int lane = threadIdx.x & 31;
     const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= (long)nbp * M) return;
-    const int blk = (int)(w / M), m = (int)(w - (long)blk * M);
-    const float xv = (blk < nb) ? x[(size_t)m * x_stride + (size_t)blk * QK + lane] : 0.0f;
+    if (w >= (long)nbp * MP) return;
+    const int blk = (int)(w / MP), m = (int)(w - (long)blk * MP);
+    const bool real = (blk < nb) && (m < M);
+    const float xv = real ? x[(size_t)m * x_stride + (size_t)blk * QK + lane] : 0.0f;
     BlockQ q = quantize_block<QT>(xv);
-    if (blk >= nb) { q.d = 0.0f; q.mn = 0.0f; q.code = (QT == 0) ? 8 : 0; }
-    emit_apack<QT>(q, lane, aq + ((size_t)blk * M + m) * 32, ap + ((size_t)blk * M + m) * ap_floats(QT));
+    if (!real) { q.d = 0.0f; q.mn = 0.0f; q.code = (QT == 0) ? 8 : 0; }
+    emit_apack<QT>(q, lane, aq + ((size_t)blk * MP + m) * 32, ap + (size_t)blk * MP + m, nbp * MP);
 }
 
 // reference-format quantized rows (params->wdata image) -> apack  (unpatched-ggml hook path)
 template <int QT>
-__global__ void pack_wdata_kernel(const uint8_t *__restrict__ wdata, int M, int nb, int nbp,
+__global__ void pack_wdata_kernel(const uint8_t *__restrict__ wdata, int M, int MP, int nb, int nbp,
                                   uint8_t *__restrict__ aq, float *__restrict__ ap)
 {
     const int lane = threadIdx.x & 31;
     const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= (long)nbp * M) return;
-    const int blk = (int)(w / M), m = (int)(w - (long)blk * M);
+    if (w >= (long)nbp * MP) return;
+    const int blk = (int)(w / MP), m = (int)(w - (long)blk * MP);
     BlockQ q;
     q.d = 0.0f; q.mn = 0.0f; q.code = (QT == 0) ? 8 : 0;
-    if (blk < nb) {
+    if (blk < nb && m < M) {
         if (QT == 0) {
             const uint8_t *b = wdata + ((size_t)m * nb + blk) * 20;
             q.d = *reinterpret_cast<const float *>(b);
@@ -214,7 +281,7 @@ __global__ void pack_wdata_kernel(const uint8_t *__restrict__ wdata, int M, int 
             q.code = (lane & 1) ? (v >> 4) : (v & 15);
         }
     }
-    emit_apack<QT>(q, lane, aq + ((size_t)blk * M + m) * 32, ap + ((size_t)blk * M + m) * ap_floats(QT));
+    emit_apack<QT>(q, lane, aq + ((size_t)blk * MP + m) * 32, ap + (size_t)blk * MP + m, nbp * MP);
 }
 
 // fp32 rows -> the reference's quantized row image, byte for byte
@@ -340,7 +407,9 @@ __global__ void unpack_kernel(const uint8_t *__restrict__ wt, int N, int nb, int
 }
 
 // ---------------------------------------------------------------------------
-// The decode kernel: dequant-fused skinny GEMM, M <= 8*NT activation rows.
+// The decode kernel: dequant-fused skinny GEMM for M <= MP activation rows
+// (MP = 2: decode GEMV, activation quantization fused into the prologue;
+//  MP = 8: prompt chunks / small batches).
 //
 // Persistent grid (one 16-warp CTA per SM).  The weight stream is cut into
 // "units" (one 1280/1536-byte chunk each = 16 rows x 4 blocks); the U units of
@@ -352,27 +421,39 @@ __global__ void unpack_kernel(const uint8_t *__restrict__ wt, int N, int nb, int
 // counter) adds the slots in warp order -- a fixed order, so results are
 // bit-reproducible run to run -- and stores Y.
 //
-// Per unit a lane issues 2 x LDG.128 (nibbles) + 2 (4 for Q4_1) x LDG.128
-// (scales), PD units ahead of use (register ring), then per quant block:
-// 4 LOP3/SHF to split nibbles into the u8 A fragment, one 8-byte LDS for the
-// B fragment, one IMMA, and 4 scale FMAs.
+// Per unit a lane issues 2 x LDG.128 (nibbles) + 2 (4 for Q4_1) x LDG.32
+// (scales), PD units ahead of use (register ring).  Nibbles become the A
+// fragment with 3 ALU ops per word:
+//   Q4_0: lo = ((w<<4) & 0xF0F0F0F0) ^ 0x80808080, hi = (w & 0xF0F0F0F0) ^ 0x80808080
+//         = 16*(q-8) as s8 (the XOR flips the nibble's top bit into a sign bit);
+//         the factor 16 is removed exactly (x 0.0625) when Y is stored;
+//   Q4_1: lo = w & 0x0F0F0F0F, hi = (w>>4) & 0x0F0F0F0F = q as u8.
+// MP = 2 ("chain4"): the 8 columns of the m16n8k32 tile are used as
+//   (block 4c+i, row m) -> column 2i+m; the four blocks' B fragments are
+//   one-hot in their column pair, so the four IMMAs of a unit accumulate into
+//   ONE D fragment and lane (g,t) ends up with the integer sums of block 4c+t
+//   for rows g/g+8 -- exactly the block whose scale d0[g][t] it loaded.  One
+//   I2F + FMUL + FFMA round per unit instead of four, no shuffles.
+// MP = 8: one IMMA per block, D column pair (2t,2t+1) = activation rows; the
+//   scale of block i comes from lane (g,i) of the quad by shuffle.
 // ---------------------------------------------------------------------------
 struct GemvParams {
     const uint8_t *wt;      // wtile
-    const uint8_t *aq;      // apack codes  [nbp][M][32]
-    const float   *ap;      // apack params [nbp][M][2|4]
+    const float   *x;       // fp32 activations (fused quantization, MP == 2)
+    const uint8_t *aq;      // apack codes  [nbp][MP][32]        (non-fused)
+    const float   *ap;      // apack planes [NP][nbp][MP] floats (non-fused)
     float         *y;
-    float         *partial; // [2*Weff][NT*4*32]
+    float         *partial; // [2*Weff][4*32]
     int           *counters;// [n_tiles], zero between launches
+    size_t         x_stride;// floats
     size_t         y_stride;// floats
-    long           U;       // n_tiles * C
-    int            N, M, C, n_tiles;
+    int            U;       // n_tiles * C  (< 2^31, checked on the host)
+    int            N, M, C, n_tiles, nb;
     int            Weff;    // warps that own a non-empty unit range
 };
 
 template <int QT> struct Frag;
-// sa/sb: lane (g,t) keeps d0 of rows g / g+8 for block 4c+t only; the other three blocks'
-// scales live in the neighbouring lanes of the quad and are fetched by shuffle at use.
+// sa/sb: lane (g,t) keeps d0 of rows g / g+8 for block 4c+t only.
 template <> struct Frag<0> { uint4 qa, qb; float sa, sb; };
 template <> struct Frag<1> { uint4 qa, qb; float sa, sb, ma, mb; };
 __device__ __forceinline__ float ldg_stream_f1(const void *p)
@@ -395,73 +476,150 @@ __device__ __forceinline__ void load_frag(Frag<QT> &f, const uint8_t *chunk, int
     }
 }
 
-__device__ __forceinline__ float f4_get(const float4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 __device__ __forceinline__ uint32_t u4_get(const uint4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
-template <int QT, int NT>
-__device__ __forceinline__ void compute_unit(const Frag<QT> &f, int blk0, const uint8_t *s_aq, const float *s_ap,
-                                             int M, int g, int t, float (&acc)[NT][4])
+// (a & b) ^ c in ONE LOP3 (immLut 0x6a); b and c are passed in registers on purpose -- with two
+// immediates the compiler has to emit two LOP3s.
+__device__ __forceinline__ uint32_t and_xor(uint32_t a, uint32_t b, uint32_t c)
 {
-    const int quad = (g << 2);
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+template <int QT>
+__device__ __forceinline__ void make_a(uint32_t (&a)[4], uint32_t wa, uint32_t wb, uint32_t kmask, uint32_t ksign)
+{
+    if constexpr (QT == 0) {
+        a[0] = and_xor(wa << 4, kmask, ksign);
+        a[1] = and_xor(wb << 4, kmask, ksign);
+        a[2] = and_xor(wa, kmask, ksign);
+        a[3] = and_xor(wb, kmask, ksign);
+    } else {
+        a[0] = wa & 0x0F0F0F0Fu;
+        a[1] = wb & 0x0F0F0F0Fu;
+        a[2] = (wa >> 4) & 0x0F0F0F0Fu;
+        a[3] = (wb >> 4) & 0x0F0F0F0Fu;
+    }
+}
+
+// D = A*B + C; A s8 (Q4_0) or u8 (Q4_1), B s8 (Q4_0) or u8 (Q4_1)
+template <int QT>
+__device__ __forceinline__ void imma(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const int (&c)[4])
+{
+    if constexpr (QT == 0)
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+                     : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
+    else
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+                     : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
+}
+
+// ---- MP == 2: four blocks chained into one D fragment ------------------------------------------
+// Shared-memory apack for this mode is the 8-column form [blk][8][32 B] in which block 4c+i only
+// populates columns 2i (row 0) and 2i+1 (row 1); parameter planes are [blk][2].
+template <int QT>
+__device__ __forceinline__ void compute_unit_chain4(const Frag<QT> &f, int c, const uint8_t *s_aq, const float *s_ap,
+                                                    int plane, int lane, uint32_t kmask, uint32_t ksign, float (&acc)[4])
+{
+    const int g = lane >> 2, t = lane & 3;
+    const uint8_t *bp = s_aq + c * 1024 + lane * 8;
+    const float2 d1 = *reinterpret_cast<const float2 *>(s_ap + (c * 4 + t) * 2);
+    int d[4] = {0, 0, 0, 0};
+    int s[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < CHUNK_BLKS; i++) {
-        const uint32_t wa = u4_get(f.qa, i), wb = u4_get(f.qb, i);
-        const uint32_t a[4] = { wa & 0x0F0F0F0Fu, wb & 0x0F0F0F0Fu, (wa >> 4) & 0x0F0F0F0Fu, (wb >> 4) & 0x0F0F0F0Fu };
-        const float d0a = __shfl_sync(0xffffffffu, f.sa, quad | i), d0b = __shfl_sync(0xffffffffu, f.sb, quad | i);
-        const int blk = blk0 + i;
-        int s0[4];
-        if constexpr (QT == 1)      // S0[row] = sum of the row's 32 weight codes: A x ones
-            mma_16x8x32<false>(s0, a, 0x01010101u, 0x01010101u, 0, 0, 0, 0);
+        uint32_t a[4];
+        make_a<QT>(a, u4_get(f.qa, i), u4_get(f.qb, i), kmask, ksign);
+        const uint2 b = *reinterpret_cast<const uint2 *>(bp + i * 256);
+        imma<QT>(d, a, b.x, b.y, d);
+        if constexpr (QT == 1) {           // S0 = sum of the block's weight codes: ones in column 2i only
+            const uint32_t one = (g == 2 * i) ? 0x01010101u : 0u;
+            imma<QT>(s, a, one, one, s);
+        }
+    }
+    if constexpr (QT == 0) {
+        acc[0] = fmaf(f.sa * d1.x, (float)d[0], acc[0]);
+        acc[1] = fmaf(f.sa * d1.y, (float)d[1], acc[1]);
+        acc[2] = fmaf(f.sb * d1.x, (float)d[2], acc[2]);
+        acc[3] = fmaf(f.sb * d1.y, (float)d[3], acc[3]);
+    } else {
+        const float2 m1 = *reinterpret_cast<const float2 *>(s_ap + plane + (c * 4 + t) * 2);
+        const float2 z  = *reinterpret_cast<const float2 *>(s_ap + 2 * plane + (c * 4 + t) * 2);
+        const float sa0 = (float)s[0], sb0 = (float)s[2];
+        // d0*(d1*P + m1*S0) + m0*Z
+        acc[0] += fmaf(f.sa, fmaf(d1.x, (float)d[0], m1.x * sa0), f.ma * z.x);
+        acc[1] += fmaf(f.sa, fmaf(d1.y, (float)d[1], m1.y * sa0), f.ma * z.y);
+        acc[2] += fmaf(f.sb, fmaf(d1.x, (float)d[2], m1.x * sb0), f.mb * z.x);
+        acc[3] += fmaf(f.sb, fmaf(d1.y, (float)d[3], m1.y * sb0), f.mb * z.y);
+    }
+}
+
+// ---- MP == 8: one IMMA per block, columns = activation rows ---------------------------------------
+template <int QT>
+__device__ __forceinline__ void compute_unit_m8(const Frag<QT> &f, int c, const uint8_t *s_aq, const float *s_ap,
+                                                int plane, int lane, uint32_t kmask, uint32_t ksign, float (&acc)[4])
+{
+    const int t = lane & 3, quad = lane & 28;
+    const int zero[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int j = 0; j < NT; j++) {
-            const int mb = 8 * j + g;                 // activation row feeding this lane's B fragment
-            uint2 b = make_uint2(0u, 0u);
-            if (mb < M) b = *reinterpret_cast<const uint2 *>(s_aq + ((size_t)blk * M + mb) * 32 + t * 8);
-            const int m0 = 8 * j + 2 * t, m1 = m0 + 1; // activation rows of this lane's D columns
-            int d[4];
-            if constexpr (QT == 0) {
-                float2 p0 = make_float2(0.f, 0.f), p1 = make_float2(0.f, 0.f);
-                if (m0 < M) p0 = *reinterpret_cast<const float2 *>(s_ap + ((size_t)blk * M + m0) * 2);
-                if (m1 < M) p1 = *reinterpret_cast<const float2 *>(s_ap + ((size_t)blk * M + m1) * 2);
-                const int c0 = __float_as_int(p0.y), c1 = __float_as_int(p1.y);
-                mma_16x8x32<true>(d, a, b.x, b.y, c0, c1, c0, c1);
-                acc[j][0] = fmaf(d0a * p0.x, (float)d[0], acc[j][0]);
-                acc[j][1] = fmaf(d0a * p1.x, (float)d[1], acc[j][1]);
-                acc[j][2] = fmaf(d0b * p0.x, (float)d[2], acc[j][2]);
-                acc[j][3] = fmaf(d0b * p1.x, (float)d[3], acc[j][3]);
-            } else {
-                float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-                if (m0 < M) p0 = *reinterpret_cast<const float4 *>(s_ap + ((size_t)blk * M + m0) * 4);
-                if (m1 < M) p1 = *reinterpret_cast<const float4 *>(s_ap + ((size_t)blk * M + m1) * 4);
-                mma_16x8x32<false>(d, a, b.x, b.y, 0, 0, 0, 0);
-                const float m0a = __shfl_sync(0xffffffffu, f.ma, quad | i), m0b = __shfl_sync(0xffffffffu, f.mb, quad | i);
-                const float sa0 = (float)s0[0], sb0 = (float)s0[2];
-                // d0*(d1*P + m1*S0) + m0*Z
-                acc[j][0] += fmaf(d0a, fmaf(p0.x, (float)d[0], p0.y * sa0), m0a * p0.z);
-                acc[j][1] += fmaf(d0a, fmaf(p1.x, (float)d[1], p1.y * sa0), m0a * p1.z);
-                acc[j][2] += fmaf(d0b, fmaf(p0.x, (float)d[2], p0.y * sb0), m0b * p0.z);
-                acc[j][3] += fmaf(d0b, fmaf(p1.x, (float)d[3], p1.y * sb0), m0b * p1.z);
-            }
+    for (int i = 0; i < CHUNK_BLKS; i++) {
+        uint32_t a[4];
+        make_a<QT>(a, u4_get(f.qa, i), u4_get(f.qb, i), kmask, ksign);
+        const int blk = c * 4 + i;
+        const uint2 b = *reinterpret_cast<const uint2 *>(s_aq + blk * 256 + lane * 8);
+        const float2 d1 = *reinterpret_cast<const float2 *>(s_ap + blk * 8 + 2 * t);
+        const float d0a = __shfl_sync(0xffffffffu, f.sa, quad | i), d0b = __shfl_sync(0xffffffffu, f.sb, quad | i);
+        int d[4];
+        imma<QT>(d, a, b.x, b.y, zero);
+        if constexpr (QT == 0) {
+            acc[0] = fmaf(d0a * d1.x, (float)d[0], acc[0]);
+            acc[1] = fmaf(d0a * d1.y, (float)d[1], acc[1]);
+            acc[2] = fmaf(d0b * d1.x, (float)d[2], acc[2]);
+            acc[3] = fmaf(d0b * d1.y, (float)d[3], acc[3]);
+        } else {
+            int s[4];
+            imma<QT>(s, a, 0x01010101u, 0x01010101u, zero);
+            const float2 m1 = *reinterpret_cast<const float2 *>(s_ap + plane + blk * 8 + 2 * t);
+            const float2 z  = *reinterpret_cast<const float2 *>(s_ap + 2 * plane + blk * 8 + 2 * t);
+            const float m0a = __shfl_sync(0xffffffffu, f.ma, quad | i), m0b = __shfl_sync(0xffffffffu, f.mb, quad | i);
+            const float sa0 = (float)s[0], sb0 = (float)s[2];
+            acc[0] += fmaf(d0a, fmaf(d1.x, (float)d[0], m1.x * sa0), m0a * z.x);
+            acc[1] += fmaf(d0a, fmaf(d1.y, (float)d[1], m1.y * sa0), m0a * z.y);
+            acc[2] += fmaf(d0b, fmaf(d1.x, (float)d[2], m1.x * sb0), m0b * z.x);
+            acc[3] += fmaf(d0b, fmaf(d1.y, (float)d[3], m1.y * sb0), m0b * z.y);
         }
     }
 }
 
-__device__ __forceinline__ long unit_start(long w, long U, int Weff) { return (w * U) / Weff; }
-__device__ __forceinline__ int warp_of_unit(long u, long U, int Weff) { return (int)(((u + 1) * Weff - 1) / U); }
+__device__ __forceinline__ int unit_start(int w, int U, int Weff) { return (int)(((long)w * U) / Weff); }
+__device__ __forceinline__ int warp_of_unit(int u, int U, int Weff) { return (int)((((long)u + 1) * Weff - 1) / U); }
 
-template <int NT>
-__device__ __noinline__ void flush_tile(const GemvParams &p, int T, long s0, long s1, int wid, int lane,
-                                        float (&acc)[NT][4])
+// End of a warp's segment [s0,s1) of tile T: combine with the other warps that share the
+// tile (fixed order) and store Y.  acc: MP==2: lane (g,t) holds rows g/g+8 x m=0/1 summed over
+// blocks == t (mod 4) -> quad-reduced here; MP==8: rows g/g+8 x m=2t/2t+1.
+// Arguments by value: keeps the caller's accumulators in registers (no local-memory round trip).
+template <int QT, int MP>
+__device__ __noinline__ void flush_tile(const GemvParams &p, int T, int s0, int s1, int wid, int lane,
+                                        float a0, float a1, float a2, float a3)
 {
-    const long tb = (long)T * p.C, te = tb + p.C;
+    float acc[4] = {a0, a1, a2, a3};
+    if (MP == 2) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
+            acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
+        }
+    }
+    const int tb = T * p.C, te = tb + p.C;
     if (!(s0 == tb && s1 == te)) {
         const int wf = warp_of_unit(tb, p.U, p.Weff), wl = warp_of_unit(te - 1, p.U, p.Weff);
         const int slot = 2 * wid + (tb <= unit_start(wid, p.U, p.Weff) ? 0 : 1);
-        float *ws = p.partial + (size_t)slot * (NT * 4 * 32);
+        float *ws = p.partial + (size_t)slot * 128;
 #pragma unroll
-        for (int j = 0; j < NT; j++)
-#pragma unroll
-            for (int r = 0; r < 4; r++) ws[(j * 4 + r) * 32 + lane] = acc[j][r];
+        for (int r = 0; r < 4; r++) ws[r * 32 + lane] = acc[r];
         __threadfence();
         __syncwarp();
         int old = 0;
@@ -470,51 +628,47 @@ __device__ __noinline__ void flush_tile(const GemvParams &p, int T, long s0, lon
         if (old != wl - wf) return;                 // not the last contributor
         __threadfence();
 #pragma unroll
-        for (int j = 0; j < NT; j++)
-#pragma unroll
-            for (int r = 0; r < 4; r++) acc[j][r] = 0.0f;
+        for (int r = 0; r < 4; r++) acc[r] = 0.0f;
         for (int w = wf; w <= wl; w++) {            // fixed order: reproducible rounding
             const int sl = 2 * w + (tb <= unit_start(w, p.U, p.Weff) ? 0 : 1);
-            const float *rs = p.partial + (size_t)sl * (NT * 4 * 32);
+            const float *rs = p.partial + (size_t)sl * 128;
 #pragma unroll
-            for (int j = 0; j < NT; j++)
-#pragma unroll
-                for (int r = 0; r < 4; r++) acc[j][r] += __ldcg(rs + (j * 4 + r) * 32 + lane);
+            for (int r = 0; r < 4; r++) acc[r] += __ldcg(rs + r * 32 + lane);
         }
         if (lane == 0) p.counters[T] = 0;           // ready for the next launch
     }
+    const float post = (QT == 0) ? 0.0625f : 1.0f;  // undo the 16x of the shifted-nibble A operand (exact)
     const int g = lane >> 2, t = lane & 3;
     const int n0 = T * TILE_ROWS + g, n1 = n0 + 8;
-#pragma unroll
-    for (int j = 0; j < NT; j++) {
-        const int m0 = 8 * j + 2 * t, m1 = m0 + 1;
-        if (m0 < p.M) {
-            if (n0 < p.N) p.y[(size_t)m0 * p.y_stride + n0] = acc[j][0];
-            if (n1 < p.N) p.y[(size_t)m0 * p.y_stride + n1] = acc[j][2];
-        }
-        if (m1 < p.M) {
-            if (n0 < p.N) p.y[(size_t)m1 * p.y_stride + n0] = acc[j][1];
-            if (n1 < p.N) p.y[(size_t)m1 * p.y_stride + n1] = acc[j][3];
-        }
+    int m0, m1;
+    if (MP == 2) { if (t != 0) return; m0 = 0; m1 = 1; }
+    else { m0 = 2 * t; m1 = m0 + 1; }
+    if (m0 < p.M) {
+        if (n0 < p.N) p.y[(size_t)m0 * p.y_stride + n0] = acc[0] * post;
+        if (n1 < p.N) p.y[(size_t)m0 * p.y_stride + n1] = acc[2] * post;
+    }
+    if (m1 < p.M) {
+        if (n0 < p.N) p.y[(size_t)m1 * p.y_stride + n0] = acc[1] * post;
+        if (n1 < p.N) p.y[(size_t)m1 * p.y_stride + n1] = acc[3] * post;
     }
 }
 
-template <int QT, int NT, int PD>
+template <int QT, int MP, int PD, bool FUSED>
 __global__ void __launch_bounds__(GEMV_THREADS, 1) q4_gemv_kernel(const GemvParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int CH = chunk_bytes(QT);
-    constexpr int APF = ap_floats(QT);
+    constexpr int NP = (QT == 0) ? 1 : 3;
     const int nbp = p.C * CHUNK_BLKS;
-    const size_t aq_bytes = (size_t)nbp * p.M * 32;
-    const size_t ap_bytes = (size_t)nbp * p.M * APF * 4;
+    const int plane = nbp * MP;                         // floats per parameter plane
+    const size_t aq_bytes = (size_t)nbp * 8 * 32;       // shared-memory codes are always the 8-column form
     uint8_t *s_aq = smem;
     float *s_ap = reinterpret_cast<float *>(smem + aq_bytes);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wid = blockIdx.x * GEMV_WARPS + warp;
     const bool active = wid < p.Weff;
-    long u0 = 0, u1 = 0;
+    int u0 = 0, u1 = 0;
     Frag<QT> buf[PD];
     if (active) {                                    // start the weight stream before staging activations
         u0 = unit_start(wid, p.U, p.Weff);
@@ -523,47 +677,431 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) q4_gemv_kernel(const GemvPara
         for (int i = 0; i < PD; i++)
             if (u0 + i < u1) load_frag<QT>(buf[i], p.wt + (size_t)(u0 + i) * CH, lane);
     }
-    {   // apack: global (L2) -> shared, 16 B per thread per step
+    if constexpr (MP == 2) {
+        // zero the whole pack (columns of other blocks, padded rows/blocks must read as 0)
+        const size_t total16 = (aq_bytes + (size_t)NP * plane * 4) / 16;
+        for (size_t i = threadIdx.x; i < total16; i += GEMV_THREADS)
+            reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        if constexpr (FUSED) {
+            // quantize the activation rows straight into shared memory (every CTA redundantly:
+            // M*K*4 bytes from L2, no second kernel, no global round trip)
+            const int items = p.M * p.nb * 4;                 // one item = 8 consecutive elements
+            for (int base = 0; base < items; base += GEMV_THREADS) {
+                const int id = base + (int)threadIdx.x;
+                const bool valid = id < items;
+                const int bq = valid ? (id >> 2) : 0;          // (m, blk) index
+                const int m = bq / p.nb, blk = bq - m * p.nb;
+                quantize8_emit<QT>(p.x + (size_t)m * p.x_stride + (size_t)blk * QK + (lane & 3) * 8, valid, lane,
+                                   s_aq + ((size_t)blk * 8 + 2 * (blk & 3) + m) * 32, s_ap + (size_t)blk * 2 + m, plane);
+            }
+        } else {
+            // global apack [nbp][2][32] -> 8-column form; planes copied as they are
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.aq);
+            for (int i = threadIdx.x; i < nbp * 4; i += GEMV_THREADS) {       // 16-byte pieces
+                const int blk = i >> 2, m = (i >> 1) & 1, piece = i & 1;
+                reinterpret_cast<uint4 *>(s_aq + ((size_t)blk * 8 + 2 * (blk & 3) + m) * 32)[piece] = src[i];
+            }
+            const uint4 *src2 = reinterpret_cast<const uint4 *>(p.ap);
+            uint4 *dst2 = reinterpret_cast<uint4 *>(s_ap);
+            for (size_t i = threadIdx.x; i < (size_t)NP * plane * 4 / 16; i += GEMV_THREADS) dst2[i] = src2[i];
+        }
+    } else {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.aq);
         uint4 *dst = reinterpret_cast<uint4 *>(s_aq);
         for (size_t i = threadIdx.x; i < aq_bytes / 16; i += GEMV_THREADS) dst[i] = src[i];
         const uint4 *src2 = reinterpret_cast<const uint4 *>(p.ap);
         uint4 *dst2 = reinterpret_cast<uint4 *>(s_ap);
-        for (size_t i = threadIdx.x; i < ap_bytes / 16; i += GEMV_THREADS) dst2[i] = src2[i];
+        for (size_t i = threadIdx.x; i < (size_t)NP * plane * 4 / 16; i += GEMV_THREADS) dst2[i] = src2[i];
     }
     __syncthreads();
     if (!active) return;
 
-    const int g = lane >> 2, t = lane & 3;
-    float acc[NT][4];
-#pragma unroll
-    for (int j = 0; j < NT; j++)
-#pragma unroll
-        for (int r = 0; r < 4; r++) acc[j][r] = 0.0f;
+    // nibble-split constants kept in registers (see and_xor)
+    uint32_t kmask = 0xF0F0F0F0u, ksign = 0x80808080u;
+    asm volatile("" : "+r"(kmask), "+r"(ksign));
 
-    int T = (int)(u0 / p.C);
-    int c = (int)(u0 - (long)T * p.C);
-    long seg0 = u0;
-    for (long ub = u0; ub < u1; ub += PD) {
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    int T = u0 / p.C;
+    int c = u0 - T * p.C;
+    int seg0 = u0;
+    const uint8_t *wp = p.wt + (size_t)(u0 + PD) * CH;
+    for (int ub = u0; ub < u1; ub += PD) {
 #pragma unroll
         for (int i = 0; i < PD; i++) {
-            const long u = ub + i;
+            const int u = ub + i;
             if (u < u1) {
-                const Frag<QT> cur = buf[i];
-                if (u + PD < u1) load_frag<QT>(buf[i], p.wt + (size_t)(u + PD) * CH, lane);
-                compute_unit<QT, NT>(cur, c * CHUNK_BLKS, s_aq, s_ap, p.M, g, t, acc);
+                if constexpr (MP == 2) compute_unit_chain4<QT>(buf[i], c, s_aq, s_ap, plane, lane, kmask, ksign, acc);
+                else                   compute_unit_m8<QT>(buf[i], c, s_aq, s_ap, plane, lane, kmask, ksign, acc);
+                if (u + PD < u1) load_frag<QT>(buf[i], wp, lane);
+                wp += CH;
                 ++c;
                 if (c == p.C || u + 1 == u1) {
-                    flush_tile<NT>(p, T, seg0, u + 1, wid, lane, acc);
-#pragma unroll
-                    for (int j = 0; j < NT; j++)
-#pragma unroll
-                        for (int r = 0; r < 4; r++) acc[j][r] = 0.0f;
+                    flush_tile<QT, MP>(p, T, seg0, u + 1, wid, lane, acc[0], acc[1], acc[2], acc[3]);
+                    acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
                     if (c == p.C) { c = 0; ++T; }
                     seg0 = u + 1;
                 }
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The decode kernel, pipelined form (the one b200q4_mul_mat uses):
+//
+//   producer warp   walks "tasks" (<= 64 consecutive units inside one 16-row tile, or a few whole
+//                   tiles when a tile is shorter than 16 units) handed out by an atomic ticket
+//                   counter -- dynamic scheduling: a slow SM simply takes fewer tasks -- and
+//                   streams them into a ring of shared-memory stages, one cp.async.bulk (TMA 1-D
+//                   bulk copy, 16 units = 20/24 KB) per stage, completion on an mbarrier.
+//   16 consumer     warp w takes unit w of the stage: 4 LDS for the A-fragment words and scales,
+//   warps           3 ALU/word nibble split, IMMA against the B fragments of the activation pack,
+//                   scale FMAs, then ONE 16-byte store per lane of its per-unit partial sums.
+//                   Stateless between stages.
+//   reducer warp    adds the per-unit partials of a stage in unit order (fixed -> bit-reproducible),
+//                   carries the tile accumulator across stages, and at the end of a tile (or tile
+//                   piece) stores Y, or -- when a tile is split over several tasks (K > 8192) --
+//                   parks the piece in a workspace slot; the last piece to arrive (atomic counter)
+//                   adds the slots in piece order and stores Y.
+//
+// Bytes in flight per SM = (stages-1) x 20 KB, independent of registers; weights never touch the
+// register file before they are needed.  Programmatic dependent launch: the weight stream of launch
+// i+1 starts while launch i drains; everything that depends on the previous kernel (X, Y, workspace,
+// ticket counter) is touched only after cudaGridDependencySynchronize().
+// ---------------------------------------------------------------------------
+constexpr int PIPE_CONSUMERS = 16;                      // consumer warps = units per stage
+constexpr int PIPE_THREADS = (PIPE_CONSUMERS + 2) * 32; // + producer warp + reducer warp
+constexpr int PIPE_MAX_STAGES = 8;
+
+struct PipeParams {
+    const uint8_t *wt;
+    const float   *x;        // fused quantization (MP == 2)
+    const uint8_t *aq;       // global apack (non-fused)
+    const float   *ap;
+    float         *y;
+    float         *partial;  // [ntasks][128] floats, used when a tile spans several tasks
+    int           *tile_counters;
+    int           *ticket;   // [2]: next task, CTAs done   (self-resetting)
+    size_t         x_stride, y_stride;   // floats
+    int            U, N, M, C, n_tiles, nb;
+    int            ntasks;   // tasks in the launch
+    int            PP;       // pieces (tasks) per tile when C >= 16, else 1
+    int            TS;       // units per task
+    int            stages;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+
+// first unit and unit count of task t
+__device__ __forceinline__ void task_range(const PipeParams &p, int t, int &u0, int &n)
+{
+    if (p.C >= PIPE_CONSUMERS) {                         // PP pieces per tile, TS units each (last shorter)
+        const int T = t / p.PP, piece = t - T * p.PP;
+        const int off = piece * p.TS;
+        u0 = T * p.C + off;
+        n = min(p.TS, p.C - off);
+    } else {                                            // short tiles: TS = whole tiles
+        u0 = t * p.TS;
+        n = min(p.TS, p.U - u0);
+    }
+}
+
+template <int QT>
+__device__ __forceinline__ void load_frag_smem(Frag<QT> &f, const uint8_t *chunk, int lane)
+{
+    f.qa = *reinterpret_cast<const uint4 *>(chunk + lane * 16);
+    f.qb = *reinterpret_cast<const uint4 *>(chunk + 512 + lane * 16);
+    f.sa = *reinterpret_cast<const float *>(chunk + 1024 + lane * 4);
+    f.sb = *reinterpret_cast<const float *>(chunk + 1024 + 128 + lane * 4);
+    if constexpr (QT == 1) {
+        f.ma = *reinterpret_cast<const float *>(chunk + 1280 + lane * 4);
+        f.mb = *reinterpret_cast<const float *>(chunk + 1280 + 128 + lane * 4);
+    }
+}
+
+// MP == 2 on the compact pack [blk][2][32]: the B fragment of (block 4c + g/2, row g&1) is
+// lane-linear (c*256 + lane*8); `bmask[i]` is all-ones in the lanes whose block is 4c+i, so
+// block i's IMMA sees that block's codes in columns 2i, 2i+1 and zeros elsewhere.
+template <int QT>
+__device__ __forceinline__ void compute_unit_chain4c(const Frag<QT> &f, int c, const uint8_t *s_aq, const float *s_ap,
+                                                     int plane, int lane, uint32_t kmask, uint32_t ksign,
+                                                     const uint32_t (&bmask)[4], float (&acc)[4])
+{
+    const int g = lane >> 2, t = lane & 3;
+    const uint2 breg = *reinterpret_cast<const uint2 *>(s_aq + c * 256 + lane * 8);
+    const float2 d1 = *reinterpret_cast<const float2 *>(s_ap + (c * 4 + t) * 2);
+    int d[4] = {0, 0, 0, 0};
+    int s[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < CHUNK_BLKS; i++) {
+        uint32_t a[4];
+        make_a<QT>(a, u4_get(f.qa, i), u4_get(f.qb, i), kmask, ksign);
+        imma<QT>(d, a, breg.x & bmask[i], breg.y & bmask[i], d);
+        if constexpr (QT == 1) {
+            const uint32_t one = (g == 2 * i) ? 0x01010101u : 0u;
+            imma<QT>(s, a, one, one, s);
+        }
+    }
+    if constexpr (QT == 0) {
+        acc[0] = (f.sa * d1.x) * (float)d[0];
+        acc[1] = (f.sa * d1.y) * (float)d[1];
+        acc[2] = (f.sb * d1.x) * (float)d[2];
+        acc[3] = (f.sb * d1.y) * (float)d[3];
+    } else {
+        const float2 m1 = *reinterpret_cast<const float2 *>(s_ap + plane + (c * 4 + t) * 2);
+        const float2 z  = *reinterpret_cast<const float2 *>(s_ap + 2 * plane + (c * 4 + t) * 2);
+        const float sa0 = (float)s[0], sb0 = (float)s[2];
+        acc[0] = fmaf(f.sa, fmaf(d1.x, (float)d[0], m1.x * sa0), f.ma * z.x);
+        acc[1] = fmaf(f.sa, fmaf(d1.y, (float)d[1], m1.y * sa0), f.ma * z.y);
+        acc[2] = fmaf(f.sb, fmaf(d1.x, (float)d[2], m1.x * sb0), f.mb * z.x);
+        acc[3] = fmaf(f.sb, fmaf(d1.y, (float)d[3], m1.y * sb0), f.mb * z.y);
+    }
+}
+
+// Reducer: end of the run of units [.., u_last] of tile T inside task `task`.
+template <int QT, int MP>
+__device__ __forceinline__ void pipe_emit(const PipeParams &p, int T, int task, int lane, float (&acc)[4])
+{
+    if (MP == 2) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
+            acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
+        }
+    }
+    if (p.C >= PIPE_CONSUMERS && p.PP > 1) {            // the tile is split over PP tasks
+        float *ws = p.partial + (size_t)task * 128;
+#pragma unroll
+        for (int r = 0; r < 4; r++) ws[r * 32 + lane] = acc[r];
+        __threadfence();
+        __syncwarp();
+        int old = 0;
+        if (lane == 0) old = atomicAdd(p.tile_counters + T, 1);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old != p.PP - 1) return;
+        __threadfence();
+#pragma unroll
+        for (int r = 0; r < 4; r++) acc[r] = 0.0f;
+        for (int k = 0; k < p.PP; k++) {                // piece order: reproducible rounding
+            const float *rs = p.partial + (size_t)(T * p.PP + k) * 128;
+#pragma unroll
+            for (int r = 0; r < 4; r++) acc[r] += __ldcg(rs + r * 32 + lane);
+        }
+        if (lane == 0) p.tile_counters[T] = 0;
+    }
+    const float post = (QT == 0) ? 0.0625f : 1.0f;
+    const int g = lane >> 2, t = lane & 3;
+    const int n0 = T * TILE_ROWS + g, n1 = n0 + 8;
+    int m0, m1;
+    if (MP == 2) { if (t != 0) return; m0 = 0; m1 = 1; }
+    else { m0 = 2 * t; m1 = m0 + 1; }
+    if (m0 < p.M) {
+        if (n0 < p.N) p.y[(size_t)m0 * p.y_stride + n0] = acc[0] * post;
+        if (n1 < p.N) p.y[(size_t)m0 * p.y_stride + n1] = acc[2] * post;
+    }
+    if (m1 < p.M) {
+        if (n0 < p.N) p.y[(size_t)m1 * p.y_stride + n0] = acc[1] * post;
+        if (n1 < p.N) p.y[(size_t)m1 * p.y_stride + n1] = acc[3] * post;
+    }
+}
+
+template <int QT, int MP, bool FUSED>
+__global__ void __launch_bounds__(PIPE_THREADS, 1) q4_gemv_pipe_kernel(const PipeParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int CH = chunk_bytes(QT);
+    constexpr int NP = (QT == 0) ? 1 : 3;
+    constexpr int STAGE_BYTES = PIPE_CONSUMERS * CH;
+    const int nbp = p.C * CHUNK_BLKS;
+    const int plane = nbp * MP;
+    // shared-memory map: [stages x STAGE_BYTES][red: stages x 16 x 512 B][apack codes][planes][barriers][desc]
+    uint8_t *s_stage = smem;
+    float   *s_red = reinterpret_cast<float *>(smem + (size_t)p.stages * STAGE_BYTES);
+    uint8_t *s_aq = reinterpret_cast<uint8_t *>(s_red) + (size_t)p.stages * PIPE_CONSUMERS * 512;
+    float   *s_ap = reinterpret_cast<float *>(s_aq + (size_t)nbp * MP * 32);
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_ap) + (((size_t)NP * plane * 4 + 15) & ~(size_t)15));
+    uint64_t *bar_empty = bar_full + PIPE_MAX_STAGES;
+    uint64_t *bar_done = bar_empty + PIPE_MAX_STAGES;       // consumers finished a stage's partials
+    int4     *s_desc = reinterpret_cast<int4 *>(bar_done + PIPE_MAX_STAGES);   // {first unit, n units (<0 = stop), chunk index of first unit, task}
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.stages; i++) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], PIPE_CONSUMERS + 1);
+            mbar_init(&bar_done[i], PIPE_CONSUMERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cudaTriggerProgrammaticLaunchCompletion();           // let the next launch start streaming early
+
+    if (warp == PIPE_CONSUMERS) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            int it = 0;
+            int task = blockIdx.x;                       // first task is static: no dependency on the previous launch
+            bool synced = false;
+            while (task < p.ntasks) {
+                int u0, n;
+                task_range(p, task, u0, n);
+                int c0 = u0 % p.C;
+                for (int r = 0; r < n; r += PIPE_CONSUMERS, ++it) {
+                    const int s = it % p.stages;
+                    if (it >= p.stages) mbar_wait(&bar_empty[s], ((it / p.stages) - 1) & 1);
+                    const int cnt = min(PIPE_CONSUMERS, n - r);
+                    s_desc[s] = make_int4(u0 + r, cnt, c0, task);
+                    c0 = (c0 + cnt) % p.C;
+                    mbar_arrive_expect_tx(&bar_full[s], (uint32_t)cnt * CH);
+                    bulk_g2s(s_stage + (size_t)s * STAGE_BYTES, p.wt + (size_t)(u0 + r) * CH, (uint32_t)cnt * CH, &bar_full[s]);
+                }
+                if (!synced) { cudaGridDependencySynchronize(); synced = true; }
+                task = gridDim.x + atomicAdd(p.ticket, 1);
+            }
+            if (!synced) cudaGridDependencySynchronize();
+            {   // stop marker
+                const int s = it % p.stages;
+                if (it >= p.stages) mbar_wait(&bar_empty[s], ((it / p.stages) - 1) & 1);
+                s_desc[s] = make_int4(0, -1, 0, 0);
+                mbar_arrive(&bar_full[s]);
+            }
+            // the last CTA to run out of tasks re-arms the ticket counter for the next launch
+            if (atomicAdd(p.ticket + 1, 1) == (int)gridDim.x - 1) { p.ticket[0] = 0; p.ticket[1] = 0; __threadfence(); }
+        }
+        return;
+    }
+
+    if (warp == PIPE_CONSUMERS + 1) {
+        // ===================== reducer =====================
+        cudaGridDependencySynchronize();
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        int curT = -1, curTask = -1;
+        for (int it = 0;; ++it) {
+            const int s = it % p.stages;
+            mbar_wait(&bar_full[s], (it / p.stages) & 1);
+            const int4 dsc = s_desc[s];
+            if (dsc.y < 0) break;
+            const int task = dsc.w;
+            int T = (dsc.x - dsc.z) / p.C;               // one division per stage
+            int left = p.C - dsc.z;                      // units of tile T from dsc.x on
+            mbar_wait(&bar_done[s], (it / p.stages) & 1);
+            const float *red = s_red + (size_t)s * PIPE_CONSUMERS * 128 + lane * 4;
+            int j = 0;
+            while (j < dsc.y) {
+                if (T != curT || task != curTask) {
+                    if (curT >= 0) pipe_emit<QT, MP>(p, curT, curTask, lane, acc);
+                    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+                    curT = T; curTask = task;
+                }
+                const int run = min(dsc.y - j, left);    // units of this stage that belong to tile T
+                if (run == PIPE_CONSUMERS) {             // common case: the whole stage is one tile
+                    float4 v[PIPE_CONSUMERS];
+#pragma unroll
+                    for (int k = 0; k < PIPE_CONSUMERS; k++) v[k] = *reinterpret_cast<const float4 *>(red + k * 128);
+#pragma unroll
+                    for (int k = 0; k < PIPE_CONSUMERS; k++) { acc[0] += v[k].x; acc[1] += v[k].y; acc[2] += v[k].z; acc[3] += v[k].w; }
+                } else {
+                    for (int k = j; k < j + run; k++) {
+                        const float4 v = *reinterpret_cast<const float4 *>(red + k * 128);
+                        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+                    }
+                }
+                j += run;
+                left -= run;
+                if (left == 0) { ++T; left = p.C; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[s]);
+        }
+        if (curT >= 0) pipe_emit<QT, MP>(p, curT, curTask, lane, acc);
+        return;
+    }
+
+    // ===================== consumers =====================
+    cudaGridDependencySynchronize();                     // X may be the previous kernel's output
+    const int ctid = threadIdx.x;                        // 0 .. 511
+    constexpr int CTHREADS = PIPE_CONSUMERS * 32;
+    if constexpr (FUSED) {
+        // padded blocks (nb .. nbp) and the unused row of an M=1 call must read as zero
+        const size_t total16 = ((size_t)nbp * MP * 32 + (((size_t)NP * plane * 4 + 15) & ~(size_t)15)) / 16;
+        for (size_t i = ctid; i < total16; i += CTHREADS) reinterpret_cast<uint4 *>(s_aq)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("bar.sync 1, %0;" :: "n"(CTHREADS) : "memory");
+        const int items = p.M * p.nb * 4;
+        for (int base = 0; base < items; base += CTHREADS) {
+            const int id = base + ctid;
+            const bool valid = id < items;
+            const int bq = valid ? (id >> 2) : 0;
+            const int m = bq / p.nb, blk = bq - m * p.nb;
+            quantize8_emit<QT>(p.x + (size_t)m * p.x_stride + (size_t)blk * QK + (lane & 3) * 8, valid, lane,
+                               s_aq + ((size_t)blk * MP + m) * 32, s_ap + (size_t)blk * MP + m, plane);
+        }
+    } else {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.aq);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_aq);
+        for (size_t i = ctid; i < (size_t)nbp * MP * 32 / 16; i += CTHREADS) dst[i] = src[i];
+        const uint4 *src2 = reinterpret_cast<const uint4 *>(p.ap);
+        uint4 *dst2 = reinterpret_cast<uint4 *>(s_ap);
+        for (size_t i = ctid; i < (size_t)NP * plane * 4 / 16; i += CTHREADS) dst2[i] = src2[i];
+    }
+    asm volatile("bar.sync 1, %0;" :: "n"(CTHREADS) : "memory");
+
+    uint32_t kmask = 0xF0F0F0F0u, ksign = 0x80808080u;
+    asm volatile("" : "+r"(kmask), "+r"(ksign));
+    uint32_t bmask[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) bmask[i] = ((lane >> 3) == i) ? 0xFFFFFFFFu : 0u;
+
+    for (int it = 0;; ++it) {
+        const int s = it % p.stages;
+        mbar_wait(&bar_full[s], (it / p.stages) & 1);
+        const int4 dsc = s_desc[s];
+        if (dsc.y < 0) break;
+        if (warp < dsc.y) {
+            int c = dsc.z + warp;
+            while (c >= p.C) c -= p.C;
+            Frag<QT> f;
+            load_frag_smem<QT>(f, s_stage + (size_t)s * STAGE_BYTES + (size_t)warp * CH, lane);
+            float acc[4];
+            if constexpr (MP == 2) compute_unit_chain4c<QT>(f, c, s_aq, s_ap, plane, lane, kmask, ksign, bmask, acc);
+            else {
+                acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+                compute_unit_m8<QT>(f, c, s_aq, s_ap, plane, lane, kmask, ksign, acc);
+            }
+            *reinterpret_cast<float4 *>(s_red + ((size_t)s * PIPE_CONSUMERS + warp) * 128 + lane * 4) =
+                make_float4(acc[0], acc[1], acc[2], acc[3]);
+        }
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&bar_done[s]); mbar_arrive(&bar_empty[s]); }
     }
 }
 
