@@ -166,17 +166,17 @@ def run_reference(args) -> int:
     steps, warm = args.steps, args.warmup
     steps = min(steps, 2000)
 
-    def one():
-        if have_ref:
+    if have_ref:
+        # weights resident in one ggml context (as vsim.cpp loads them once); each step = one
+        # ggml_graph_compute of the mul_mat node: INIT (quantize_row_q4_0) + COMPUTE (IMAX hook)
+        _, dt = impl.mul_mat_steps(qt, wq, N_ROWS, K_DIM, x, nth, warm, steps)
+    else:
+        for _ in range(warm):
             impl.mul_mat(qt, wq, N_ROWS, K_DIM, x, nth=nth)
-        else:
+        t0 = time.perf_counter()
+        for _ in range(steps):
             impl.mul_mat(qt, wq, N_ROWS, K_DIM, x, nth=nth)
-    for _ in range(warm):
-        one()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one()
-    dt = time.perf_counter() - t0
+        dt = time.perf_counter() - t0
     nbytes = alg_bytes(qt, m)
     val = nbytes * steps / dt / 1e9
     kind = "reference" if have_ref else "port"
@@ -185,8 +185,8 @@ def run_reference(args) -> int:
         "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (scalar fp32 dequant-dot, ggml.c:472-553)", "data": "synthetic",
         "config": {"workload": f"Q4_0 mul_mat microbench K={K_DIM} N={N_ROWS} M={m} (BASELINE.json configs[1])",
-                   "step": "one ggml_mul_mat + ggml_graph_compute on host memory (includes the reference's per-call "
-                           "ggml_init/memcpy of the harness)" if have_ref else "one q4o_mul_mat call",
+                   "step": "one ggml_graph_compute of a resident ggml_mul_mat node (reference ggml.c scheduler, "
+                           "quantize_row_q4_0 + IMAX-hook scalar loop, host memory)" if have_ref else "one q4o_mul_mat call",
                    "threads": nth},
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": nth, "kind": kind,
                          "sample": f"{steps} timed calls after {warm} warm-up, {nth} threads, wall clock"},
@@ -360,8 +360,8 @@ def main() -> int:
             "gpu_launches": int(launches_timed),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "pack_act_kernel + q4_gemv_kernel (Q4_0, M=1), CUDA events on the library stream, "
-                                   "back-to-back launches rotating weights",
+                         "kernel": "q4_gemv_pipe_kernel<Q4_0, chain4, fused quantization> (M=1: one launch per call), CUDA events on "
+                                   "the library stream around back-to-back launches rotating weights",
                          "algorithmic_bytes_per_launch": alg_bytes(0, M_HEAD), "us_per_launch": kern_ms * 1e3},
             "clocks": sampler.summary(),
             "points": points,

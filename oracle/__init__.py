@@ -146,6 +146,9 @@ class Reference:
         L.ref_mul_mat.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_int, C.c_int]
         L.ref_mul_mat.restype = C.c_double
+        L.ref_mul_mat_steps.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.ref_mul_mat_steps.restype = C.c_double
         L.ref_mul_mat_transposed.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                              C.c_int, C.c_void_p, C.c_int]
         L.ref_mul_mat_transposed.restype = C.c_double
@@ -182,6 +185,18 @@ class Reference:
         if us < 0:
             raise RuntimeError("ref_mul_mat failed")
         return (y, us) if return_time else y
+
+    def mul_mat_steps(self, qtype: int, w: np.ndarray, n: int, k: int, x: np.ndarray, nth: int,
+                      warmup: int, steps: int):
+        """warmup + steps ggml_graph_compute calls on one resident graph; returns (Y, seconds for the timed steps)."""
+        w = np.ascontiguousarray(w, dtype=np.uint8)
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, k)
+        m = x.shape[0]
+        y = np.empty((m, n), dtype=np.float32)
+        us = self.lib.ref_mul_mat_steps(qtype, w.ctypes.data, n, k, x.ctypes.data, m, y.ctypes.data, nth, warmup, steps)
+        if us < 0:
+            raise RuntimeError("ref_mul_mat_steps failed")
+        return y, us * 1e-6
 
     def mul_mat_transposed(self, qtype: int, wt: np.ndarray, n: int, k: int, x: np.ndarray,
                            nth: int = 1) -> np.ndarray:

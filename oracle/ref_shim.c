@@ -80,6 +80,35 @@ double ref_mul_mat(int type, const void *W, int N, int K,
     return best;
 }
 
+/* Timing form for bench.py --impl reference: the tensors and the graph are built once (as vsim.cpp
+ * loads weights once), then `warmup` untimed and `steps` timed ggml_graph_compute calls; returns
+ * the wall time of the timed calls in microseconds (or -1). */
+double ref_mul_mat_steps(int type, const void *W, int N, int K, const float *X, int M, float *Y,
+                         int n_threads, int warmup, int steps)
+{
+    const size_t wbytes = (size_t)N * (K / 32) * (type == 0 ? 20 : 24);
+    const size_t mem = wbytes + (size_t)M * K * 4 + (size_t)M * N * 4
+                     + (size_t)M * (K / 32) * 24 + 64 * 64 + (1u << 20);
+    struct ggml_init_params ip = { mem, NULL };
+    struct ggml_context *ctx = ggml_init(ip);
+    if (!ctx) return -1.0;
+    struct ggml_tensor *w = ggml_new_tensor_2d(ctx, (enum ggml_type)type, K, N);
+    struct ggml_tensor *x = ggml_new_tensor_2d(ctx, GGML_TYPE_F32, K, M);
+    memcpy(w->data, W, wbytes);
+    memcpy(x->data, X, (size_t)M * K * 4);
+    struct ggml_tensor *y = ggml_mul_mat(ctx, w, x);
+    struct ggml_cgraph gf = ggml_build_forward(y);
+    gf.n_threads = n_threads;
+    for (int r = 0; r < warmup; r++) ggml_graph_compute(ctx, &gf);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int r = 0; r < steps; r++) ggml_graph_compute(ctx, &gf);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    memcpy(Y, y->data, (size_t)M * N * 4);
+    ggml_free(ctx);
+    return (t1.tv_sec - t0.tv_sec) * 1e6 + (t1.tv_nsec - t0.tv_nsec) / 1e3;
+}
+
 /* Same, but src0 is the transposed view of a [N][K]-shaped quantized tensor
  * stored as K rows of N values (ggml_transpose -> nb01 < nb00 branch,
  * ggml.c:5118-5164 / 5391-5440). */

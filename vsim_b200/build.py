@@ -40,6 +40,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB
     cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES)]
+    if os.environ.get("B200Q4_TIMELINE"):          # development: per-CTA %globaltimer stamps (tools/timeline.py)
+        cmd.insert(1, "-DB200Q4_TIMELINE")
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)

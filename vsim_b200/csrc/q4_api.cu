@@ -33,8 +33,8 @@ struct Ctx {
     uint8_t *d_aq = nullptr; size_t aq_cap = 0;
     float *d_ap = nullptr;   size_t ap_cap = 0;
     float *d_partial = nullptr; size_t partial_cap = 0;
+    unsigned long long *d_dbg = nullptr;   // B200Q4_DBG=1: per-CTA timeline of the last decode launch
     int *d_ticket = nullptr;         // [2] task ticket + CTAs-done, self-resetting
-    int gemv_version = 2;            // B200Q4_GEMV=1 selects the register-ring kernel (A/B testing)
     bool use_pdl = true;             // B200Q4_PDL=0 disables programmatic dependent launch
     float *d_x = nullptr;    size_t x_cap = 0;
     float *d_y = nullptr;    size_t y_cap = 0;
@@ -85,60 +85,28 @@ int need_init()
     return B200Q4_OK;
 }
 
-// ---- kernel selection -------------------------------------------------------
-// MP = padded activation rows per launch: 2 -> "chain4" decode kernel (fused activation
-// quantization when the input is fp32), 8 -> one IMMA per block.
-struct Plan { int MP; size_t smem; const char *name; };
-
-// shared memory of the GEMV kernel: codes always in the 8-column form, parameter planes [nbp][MP]
-size_t apack_bytes(int type, int nbp, int MP) { return (size_t)nbp * (8 * 32 + (size_t)MP * (type == 0 ? 1 : 3) * 4); }
-
-Plan plan_for(int type, int M, int nbp)
-{
-    const size_t budget = (size_t)(g.smem_optin > 0 ? g.smem_optin : 232448);
-    Plan p;
-    p.MP = (M <= 2 || apack_bytes(type, nbp, 8) > budget) ? 2 : 8;
-    p.smem = apack_bytes(type, nbp, p.MP);
-    if (p.smem > budget) { p.MP = 0; p.smem = 0; p.name = "none"; return p; }
-    p.name = type == 0 ? (p.MP == 2 ? "q4_0_gemv_imma_chain4" : "q4_0_gemv_imma_m8")
-                       : (p.MP == 2 ? "q4_1_gemv_imma_chain4" : "q4_1_gemv_imma_m8");
-    return p;
-}
-
-template <int QT, int MP, int PD, bool FUSED>
-int launch_gemv(const GemvParams &p, int grid, size_t smem, cudaStream_t st)
-{
-    static bool attr_set = false;
-    if (!attr_set) {
-        CK(cudaFuncSetAttribute(q4_gemv_kernel<QT, MP, PD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                g.smem_optin));
-        attr_set = true;
-    }
-    q4_gemv_kernel<QT, MP, PD, FUSED><<<grid, GEMV_THREADS, smem, st>>>(p);
-    g.launches++;
-    CK(cudaGetLastError());
-    return B200Q4_OK;
-}
-
 // ---- pipelined decode kernel (q4_gemv_pipe_kernel) ---------------------------------------------
-struct PipePlan { int MP, stages, PP, TS, ntasks; size_t smem; };
+struct PipePlan { int MP, stages, PP, TS, ntasks; bool b8; size_t smem; };
 
 PipePlan pipe_plan(const b200q4_weight *w, int M)
 {
     PipePlan pp{};
     const int type = w->type, nbp = w->C * CHUNK_BLKS;
     const size_t budget = (size_t)(g.smem_optin > 0 ? g.smem_optin : 232448);
-    const size_t stage = (size_t)PIPE_CONSUMERS * chunk_bytes(type) + (size_t)PIPE_CONSUMERS * 512;
-    auto fixed = [&](int MP) {
-        const size_t planes = ((size_t)(type == 0 ? 1 : 3) * nbp * MP * 4 + 15) & ~(size_t)15;
-        return (size_t)nbp * MP * 32 + planes + 3 * PIPE_MAX_STAGES * 8 + PIPE_MAX_STAGES * 16 + 256;
+    auto stage_of = [&](int MP) { return (size_t)PIPE_CONSUMERS * chunk_bytes(type) + (size_t)PIPE_CONSUMERS * (MP == 2 ? 128 : 512); };
+    auto fixed = [&](int MP, bool b8) {
+        const size_t planes = ((size_t)(type == 0 ? 2 : 3) * nbp * MP * 4 + 15) & ~(size_t)15;
+        return (size_t)nbp * (MP == 2 && b8 ? 256 : MP * 32) + planes + 3 * PIPE_MAX_STAGES * 8 + PIPE_MAX_STAGES * 16 + 256;
     };
     pp.MP = (M <= 2) ? 2 : 8;
-    if (pp.MP == 8 && fixed(8) + 2 * stage > budget) pp.MP = 2;
-    if (fixed(pp.MP) + 2 * stage > budget) { pp.MP = 0; return pp; }
-    long st = (long)((budget - fixed(pp.MP)) / stage);
+    if (pp.MP == 8 && fixed(8, false) + 2 * stage_of(8) > budget) pp.MP = 2;
+    const size_t stage = stage_of(pp.MP);
+    // 8-column code layout (no per-IMMA masking) whenever it still leaves >= 5 stages of ring
+    pp.b8 = pp.MP == 2 && fixed(2, true) + 5 * stage <= budget;
+    if (fixed(pp.MP, pp.b8) + 2 * stage > budget) { pp.MP = 0; return pp; }
+    long st = (long)((budget - fixed(pp.MP, pp.b8)) / stage);
     pp.stages = (int)(st > PIPE_MAX_STAGES ? PIPE_MAX_STAGES : st);
-    pp.smem = fixed(pp.MP) + (size_t)pp.stages * stage;
+    pp.smem = fixed(pp.MP, pp.b8) + (size_t)pp.stages * stage;
     const int C = w->C;
     if (C >= PIPE_CONSUMERS) {
         pp.PP = (C + 63) / 64;
@@ -153,12 +121,12 @@ PipePlan pipe_plan(const b200q4_weight *w, int M)
     return pp;
 }
 
-template <int QT, int MP, bool FUSED>
+template <int QT, int MP, bool FUSED, bool M1, bool B8>
 int launch_pipe(const PipeParams &p, int grid, size_t smem, cudaStream_t st)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        CK(cudaFuncSetAttribute(q4_gemv_pipe_kernel<QT, MP, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_optin));
+        CK(cudaFuncSetAttribute(q4_gemv_pipe_kernel<QT, MP, FUSED, M1, B8>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_optin));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -167,7 +135,7 @@ int launch_pipe(const PipeParams &p, int grid, size_t smem, cudaStream_t st)
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = g.use_pdl ? 1 : 0;
-    CK(cudaLaunchKernelEx(&cfg, q4_gemv_pipe_kernel<QT, MP, FUSED>, p));
+    CK(cudaLaunchKernelEx(&cfg, q4_gemv_pipe_kernel<QT, MP, FUSED, M1, B8>, p));
     g.launches++;
     return B200Q4_OK;
 }
@@ -181,35 +149,22 @@ int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, con
     p.x_stride = x_stride_f; p.y_stride = y_stride_f;
     p.U = w->n_tiles * w->C; p.N = w->N; p.M = mc; p.C = w->C; p.n_tiles = w->n_tiles; p.nb = w->nb;
     p.ntasks = pl.ntasks; p.PP = pl.PP; p.TS = pl.TS; p.stages = pl.stages;
+    p.dbg = g.d_dbg;
     const int grid = pl.ntasks < g.sms ? pl.ntasks : g.sms;
-    if (w->type == 0) {
-        if (pl.MP == 2) return fused ? launch_pipe<0, 2, true>(p, grid, pl.smem, st) : launch_pipe<0, 2, false>(p, grid, pl.smem, st);
-        return launch_pipe<0, 8, false>(p, grid, pl.smem, st);
-    }
-    if (pl.MP == 2) return fused ? launch_pipe<1, 2, true>(p, grid, pl.smem, st) : launch_pipe<1, 2, false>(p, grid, pl.smem, st);
-    return launch_pipe<1, 8, false>(p, grid, pl.smem, st);
-}
-
-// one pass of the hot path for mc <= MP activation rows.  fused: quantize from d_x inside the
-// kernel (MP == 2 only); otherwise the apack is already in g.d_aq / g.d_ap.
-int run_gemv(const b200q4_weight *w, int mc, const Plan &pl, bool fused, const float *d_x, size_t x_stride_f,
-             float *d_y, size_t y_stride_f, cudaStream_t st)
-{
-    GemvParams p;
-    p.wt = w->d_wt; p.x = d_x; p.aq = g.d_aq; p.ap = g.d_ap; p.y = d_y; p.partial = g.d_partial; p.counters = w->d_counters;
-    p.x_stride = x_stride_f; p.y_stride = y_stride_f;
-    if ((long)w->n_tiles * w->C > 0x7fffffffL) return fail(B200Q4_EINVAL, "tensor too large: %ld units", (long)w->n_tiles * w->C);
-    p.U = w->n_tiles * w->C;
-    p.N = w->N; p.M = mc; p.C = w->C; p.n_tiles = w->n_tiles; p.nb = w->nb;
-    long warps = (long)g.sms * GEMV_WARPS;
-    p.Weff = (int)(p.U < warps ? p.U : warps);
-    const int grid = (p.Weff + GEMV_WARPS - 1) / GEMV_WARPS;
-    if (w->type == 0) {
-        if (pl.MP == 2) return fused ? launch_gemv<0, 2, 4, true>(p, grid, pl.smem, st) : launch_gemv<0, 2, 4, false>(p, grid, pl.smem, st);
-        return launch_gemv<0, 8, 4, false>(p, grid, pl.smem, st);
-    }
-    if (pl.MP == 2) return fused ? launch_gemv<1, 2, 4, true>(p, grid, pl.smem, st) : launch_gemv<1, 2, 4, false>(p, grid, pl.smem, st);
-    return launch_gemv<1, 8, 4, false>(p, grid, pl.smem, st);
+    const bool m1 = mc == 1 && fused;
+#define PIPE_DISPATCH(QT)                                                                                          \
+    if (pl.MP == 8) return launch_pipe<QT, 8, false, false, false>(p, grid, pl.smem, st);                          \
+    if (fused) {                                                                                                   \
+        if (pl.b8) return m1 ? launch_pipe<QT, 2, true, true, true>(p, grid, pl.smem, st)                          \
+                             : launch_pipe<QT, 2, true, false, true>(p, grid, pl.smem, st);                        \
+        return m1 ? launch_pipe<QT, 2, true, true, false>(p, grid, pl.smem, st)                                    \
+                  : launch_pipe<QT, 2, true, false, false>(p, grid, pl.smem, st);                                  \
+    }                                                                                                              \
+    return pl.b8 ? launch_pipe<QT, 2, false, false, true>(p, grid, pl.smem, st)                                    \
+                 : launch_pipe<QT, 2, false, false, false>(p, grid, pl.smem, st);
+    if (w->type == 0) { PIPE_DISPATCH(0) }
+    PIPE_DISPATCH(1)
+#undef PIPE_DISPATCH
 }
 
 int ensure_scratch(const b200q4_weight *w, int MP)
@@ -218,7 +173,6 @@ int ensure_scratch(const b200q4_weight *w, int MP)
     int rc;
     if ((rc = ensure(g.d_aq, g.aq_cap, (size_t)nbp * MP * 32))) return rc;
     if ((rc = ensure(g.d_ap, g.ap_cap, (size_t)nbp * MP * 12))) return rc;
-    if ((rc = ensure(g.d_partial, g.partial_cap, (size_t)2 * g.sms * GEMV_WARPS * 128 * sizeof(float)))) return rc;
     return B200Q4_OK;
 }
 
@@ -230,21 +184,12 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
     if (M == 0 || w->N == 0) return B200Q4_OK;
     if ((long)w->n_tiles * w->C > 0x7fffffffL) return fail(B200Q4_EINVAL, "tensor too large");
     const int nbp = w->C * CHUNK_BLKS;
-    const bool v2 = g.gemv_version == 2;
-    PipePlan pp{};
-    Plan pl{};
-    int MP;
-    if (v2) {
-        pp = pipe_plan(w, M);
-        MP = pp.MP;
-    } else {
-        pl = plan_for(w->type, M, nbp);
-        MP = pl.MP;
-    }
+    const PipePlan pp = pipe_plan(w, M);
+    const int MP = pp.MP;
     if (MP < 1) return fail(B200Q4_EINVAL, "mul_mat: K=%d too large for the shared-memory activation pack", w->K);
     int rc;
     if ((rc = ensure_scratch(w, MP))) return rc;
-    if (v2 && pp.PP > 1 && (rc = ensure(g.d_partial, g.partial_cap, (size_t)pp.ntasks * 128 * sizeof(float)))) return rc;
+    if (pp.PP > 1 && (rc = ensure(g.d_partial, g.partial_cap, (size_t)pp.ntasks * 128 * sizeof(float)))) return rc;
     const size_t rbw = (size_t)w->nb * (w->type == 0 ? 20 : 24);
     for (int m0 = 0; m0 < M; m0 += MP) {
         const int mc = (M - m0 < MP) ? M - m0 : MP;
@@ -266,9 +211,7 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
             g.launches++;
             CK(cudaGetLastError());
         }
-        if (v2) rc = run_pipe(w, mc, pp, fused, xs, x_stride / 4, yo, y_stride / 4, st);
-        else    rc = run_gemv(w, mc, pl, fused, xs, x_stride / 4, yo, y_stride / 4, st);
-        if (rc) return rc;
+        if ((rc = run_pipe(w, mc, pp, fused, xs, x_stride / 4, yo, y_stride / 4, st))) return rc;
     }
     return B200Q4_OK;
 }
@@ -355,8 +298,11 @@ int b200q4_init(int device)
     g.smem_optin = (int)prop.sharedMemPerBlockOptin;
     CK(cudaMalloc(&g.d_ticket, 2 * sizeof(int)));
     CK(cudaMemset(g.d_ticket, 0, 2 * sizeof(int)));
-    if (const char *e = getenv("B200Q4_GEMV")) g.gemv_version = atoi(e) == 1 ? 1 : 2;
     if (const char *e = getenv("B200Q4_PDL")) g.use_pdl = atoi(e) != 0;
+    if (const char *e = getenv("B200Q4_DBG")) if (atoi(e) != 0) {
+        CK(cudaMalloc(&g.d_dbg, 256 * 16 * sizeof(unsigned long long)));
+        CK(cudaMemset(g.d_dbg, 0, 256 * 16 * sizeof(unsigned long long)));
+    }
     g.device = device;
     g.launches = 0;
     return B200Q4_OK;
@@ -586,6 +532,14 @@ void b200q4_host_free(void *p)
     if (p) cudaFreeHost(p);
 }
 
+// development aid (not part of b200q4.h): copies the [256][16] timeline of the last decode launch
+int b200q4_debug_timeline(unsigned long long *out)
+{
+    if (!g.d_dbg) return B200Q4_EINVAL;
+    cudaStreamSynchronize(g.stream);
+    return cudaMemcpy(out, g.d_dbg, 256 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : B200Q4_ECUDA;
+}
+
 uint64_t b200q4_launch_count(void) { return g.launches; }
 void b200q4_launch_count_reset(void) { g.launches = 0; }
 
@@ -594,8 +548,6 @@ const char *b200q4_kernel_for(int type, int M, int N, int K)
     (void)N;
     if ((type != 0 && type != 1) || K <= 0 || K % QK) return "invalid";
     const int mp = (M <= 2) ? 2 : 8;
-    if (g.gemv_version == 1)
-        return type == 0 ? (mp == 2 ? "q4_0_gemv_imma_chain4" : "q4_0_gemv_imma_m8") : (mp == 2 ? "q4_1_gemv_imma_chain4" : "q4_1_gemv_imma_m8");
     return type == 0 ? (mp == 2 ? "q4_0_gemv_pipe_chain4" : "q4_0_gemv_pipe_m8") : (mp == 2 ? "q4_1_gemv_pipe_chain4" : "q4_1_gemv_pipe_m8");
 }
 

@@ -153,23 +153,25 @@ __device__ __forceinline__ BlockQ quantize_block(float x)
     return q;
 }
 
-// Writes one block's apack record: 32 code bytes at aq_rec and the block parameters into the
-// parameter planes (plane 0: d1; Q4_1 also plane 1: m1, plane 2: Z).  ap_rec points at this
-// (block,row)'s slot of plane 0; `plane` is the plane stride in floats.  Global or shared memory.
+// Writes one block's apack record: 32 code bytes at aq_rec (even elements -- the low-nibble plane --
+// pre-multiplied by 16, see "Fragment helpers") and the block parameters into the parameter planes:
+//   Q4_0: plane 0 = d1, plane 1 = -128*sum(a) (int bits);   Q4_1: d1/16, m1/16, Z = d1*sum(q1)+32*m1.
+// ap_rec points at this (block,row)'s slot of plane 0; `plane` is the plane stride in floats.
 template <int QT>
 __device__ __forceinline__ void emit_apack(const BlockQ &q, int lane, uint8_t *aq_rec, float *ap_rec, int plane)
 {
     const int a = (QT == 0) ? (q.code & 15) - 8 : (q.code & 15);
-    aq_rec[apack_byte_of(lane)] = (uint8_t)(int8_t)a;
-    if (QT == 0) {
-        if (lane == 0) ap_rec[0] = q.d;
-    } else {
-        int s = a;
+    aq_rec[apack_byte_of(lane)] = (uint8_t)((lane & 1) ? a : a * 16);
+    int s = a;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) {
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        if (QT == 0) {
             ap_rec[0] = q.d;
-            ap_rec[plane] = q.mn;
+            ap_rec[plane] = __int_as_float(-128 * s);
+        } else {
+            ap_rec[0] = q.d * 0.0625f;
+            ap_rec[plane] = q.mn * 0.0625f;
             ap_rec[2 * plane] = fmaf(q.d, (float)s, 32.0f * q.mn);     // Z = sum_k dequant(a_k)
         }
     }
@@ -222,18 +224,20 @@ __device__ __forceinline__ void quantize8_emit(const float *x8, bool valid, int 
 #pragma unroll
         for (int i = 0; i < 8; i++) a[i] = (int)(uint8_t)round_to_int_ref(__fmul_rn(__fsub_rn(v[i], mn), id));
     }
-    const uint32_t even = (uint32_t)(a[0] & 255) | ((uint32_t)(a[2] & 255) << 8) | ((uint32_t)(a[4] & 255) << 16) | ((uint32_t)(a[6] & 255) << 24);
+    const uint32_t even = (uint32_t)((a[0] * 16) & 255) | ((uint32_t)((a[2] * 16) & 255) << 8) |
+                          ((uint32_t)((a[4] * 16) & 255) << 16) | ((uint32_t)((a[6] * 16) & 255) << 24);
     const uint32_t odd  = (uint32_t)(a[1] & 255) | ((uint32_t)(a[3] & 255) << 8) | ((uint32_t)(a[5] & 255) << 16) | ((uint32_t)(a[7] & 255) << 24);
     if (valid) *reinterpret_cast<uint2 *>(aq_rec + tq * 8) = make_uint2(even, odd);
-    if (QT == 0) {
-        if (valid && tq == 0) ap_rec[0] = d;
-    } else {
-        int sum = a[0] + a[1] + a[2] + a[3] + a[4] + a[5] + a[6] + a[7];
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        if (valid && tq == 0) {
+    int sum = a[0] + a[1] + a[2] + a[3] + a[4] + a[5] + a[6] + a[7];
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    if (valid && tq == 0) {
+        if (QT == 0) {
             ap_rec[0] = d;
-            ap_rec[plane] = mn;
+            ap_rec[plane] = __int_as_float(-128 * sum);
+        } else {
+            ap_rec[0] = d * 0.0625f;
+            ap_rec[plane] = mn * 0.0625f;
             ap_rec[2 * plane] = fmaf(d, (float)sum, 32.0f * mn);
         }
     }
@@ -407,108 +411,36 @@ __global__ void unpack_kernel(const uint8_t *__restrict__ wt, int N, int nb, int
 }
 
 // ---------------------------------------------------------------------------
-// The decode kernel: dequant-fused skinny GEMM for M <= MP activation rows
-// (MP = 2: decode GEMV, activation quantization fused into the prologue;
-//  MP = 8: prompt chunks / small batches).
+// Fragment helpers shared by the decode kernels.
 //
-// Persistent grid (one 16-warp CTA per SM).  The weight stream is cut into
-// "units" (one 1280/1536-byte chunk each = 16 rows x 4 blocks); the U units of
-// the tensor, in memory order, are dealt out as one contiguous range per warp
-// (+-1 unit), so every SM moves the same number of bytes whatever N and K are
-// (N=4096 has only 256 row tiles for 148 SMs; whole-tile scheduling would idle
-// 14% of the chip).  A warp whose range cuts a 16-row tile writes its partial
-// sums to a workspace slot; the last warp to arrive at that tile (atomic
-// counter) adds the slots in warp order -- a fixed order, so results are
-// bit-reproducible run to run -- and stores Y.
-//
-// Per unit a lane issues 2 x LDG.128 (nibbles) + 2 (4 for Q4_1) x LDG.32
-// (scales), PD units ahead of use (register ring).  Nibbles become the A
-// fragment with 3 ALU ops per word:
-//   Q4_0: lo = ((w<<4) & 0xF0F0F0F0) ^ 0x80808080, hi = (w & 0xF0F0F0F0) ^ 0x80808080
-//         = 16*(q-8) as s8 (the XOR flips the nibble's top bit into a sign bit);
-//         the factor 16 is removed exactly (x 0.0625) when Y is stored;
-//   Q4_1: lo = w & 0x0F0F0F0F, hi = (w>>4) & 0x0F0F0F0F = q as u8.
-// MP = 2 ("chain4"): the 8 columns of the m16n8k32 tile are used as
-//   (block 4c+i, row m) -> column 2i+m; the four blocks' B fragments are
-//   one-hot in their column pair, so the four IMMAs of a unit accumulate into
-//   ONE D fragment and lane (g,t) ends up with the integer sums of block 4c+t
-//   for rows g/g+8 -- exactly the block whose scale d0[g][t] it loaded.  One
-//   I2F + FMUL + FFMA round per unit instead of four, no shuffles.
-// MP = 8: one IMMA per block, D column pair (2t,2t+1) = activation rows; the
-//   scale of block i comes from lane (g,i) of the quad by shuffle.
+// Nibbles become the u8 A fragment with ONE LOP3 per plane:
+//     lo = w & 0x0F0F0F0F  (= q),      hi = w & 0xF0F0F0F0  (= 16 q)
+// and the activation pack stores the even-element (lo-plane) codes pre-multiplied by 16, so both
+// planes contribute 16*q0*a.  For Q4_0 (a = q1-8, s8) the -8 of the weight code is restored by
+// starting the IMMA accumulator at -128*sum(a) (apack plane 1); the common factor 16 is removed
+// exactly (x 0.0625) when Y is stored.  For Q4_1 the planes d1 and m1 are stored pre-divided by 16.
 // ---------------------------------------------------------------------------
-struct GemvParams {
-    const uint8_t *wt;      // wtile
-    const float   *x;       // fp32 activations (fused quantization, MP == 2)
-    const uint8_t *aq;      // apack codes  [nbp][MP][32]        (non-fused)
-    const float   *ap;      // apack planes [NP][nbp][MP] floats (non-fused)
-    float         *y;
-    float         *partial; // [2*Weff][4*32]
-    int           *counters;// [n_tiles], zero between launches
-    size_t         x_stride;// floats
-    size_t         y_stride;// floats
-    int            U;       // n_tiles * C  (< 2^31, checked on the host)
-    int            N, M, C, n_tiles, nb;
-    int            Weff;    // warps that own a non-empty unit range
-};
-
 template <int QT> struct Frag;
 // sa/sb: lane (g,t) keeps d0 of rows g / g+8 for block 4c+t only.
 template <> struct Frag<0> { uint4 qa, qb; float sa, sb; };
 template <> struct Frag<1> { uint4 qa, qb; float sa, sb, ma, mb; };
-__device__ __forceinline__ float ldg_stream_f1(const void *p)
-{
-    float r;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
-    return r;
-}
-
-template <int QT>
-__device__ __forceinline__ void load_frag(Frag<QT> &f, const uint8_t *chunk, int lane)
-{
-    f.qa = ldg_stream_u4(chunk + lane * 16);
-    f.qb = ldg_stream_u4(chunk + 512 + lane * 16);
-    f.sa = ldg_stream_f1(chunk + 1024 + lane * 4);          // d0[g][t]      (128 B per warp)
-    f.sb = ldg_stream_f1(chunk + 1024 + 128 + lane * 4);    // d0[g+8][t]
-    if constexpr (QT == 1) {
-        f.ma = ldg_stream_f1(chunk + 1280 + lane * 4);
-        f.mb = ldg_stream_f1(chunk + 1280 + 128 + lane * 4);
-    }
-}
 
 __device__ __forceinline__ uint32_t u4_get(const uint4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
-// (a & b) ^ c in ONE LOP3 (immLut 0x6a); b and c are passed in registers on purpose -- with two
-// immediates the compiler has to emit two LOP3s.
-__device__ __forceinline__ uint32_t and_xor(uint32_t a, uint32_t b, uint32_t c)
+__device__ __forceinline__ void make_a(uint32_t (&a)[4], uint32_t wa, uint32_t wb)
 {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
+    a[0] = wa & 0x0F0F0F0Fu;
+    a[1] = wb & 0x0F0F0F0Fu;
+    a[2] = wa & 0xF0F0F0F0u;
+    a[3] = wb & 0xF0F0F0F0u;
 }
 
-template <int QT>
-__device__ __forceinline__ void make_a(uint32_t (&a)[4], uint32_t wa, uint32_t wb, uint32_t kmask, uint32_t ksign)
-{
-    if constexpr (QT == 0) {
-        a[0] = and_xor(wa << 4, kmask, ksign);
-        a[1] = and_xor(wb << 4, kmask, ksign);
-        a[2] = and_xor(wa, kmask, ksign);
-        a[3] = and_xor(wb, kmask, ksign);
-    } else {
-        a[0] = wa & 0x0F0F0F0Fu;
-        a[1] = wb & 0x0F0F0F0Fu;
-        a[2] = (wa >> 4) & 0x0F0F0F0Fu;
-        a[3] = (wb >> 4) & 0x0F0F0F0Fu;
-    }
-}
-
-// D = A*B + C; A s8 (Q4_0) or u8 (Q4_1), B s8 (Q4_0) or u8 (Q4_1)
+// D = A*B + C; A u8, B s8 (Q4_0) or u8 (Q4_1)
 template <int QT>
 __device__ __forceinline__ void imma(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const int (&c)[4])
 {
     if constexpr (QT == 0)
-        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
                      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
                      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
     else
@@ -517,232 +449,44 @@ __device__ __forceinline__ void imma(int (&d)[4], const uint32_t (&a)[4], uint32
                      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
 }
 
-// ---- MP == 2: four blocks chained into one D fragment ------------------------------------------
-// Shared-memory apack for this mode is the 8-column form [blk][8][32 B] in which block 4c+i only
-// populates columns 2i (row 0) and 2i+1 (row 1); parameter planes are [blk][2].
-template <int QT>
-__device__ __forceinline__ void compute_unit_chain4(const Frag<QT> &f, int c, const uint8_t *s_aq, const float *s_ap,
-                                                    int plane, int lane, uint32_t kmask, uint32_t ksign, float (&acc)[4])
-{
-    const int g = lane >> 2, t = lane & 3;
-    const uint8_t *bp = s_aq + c * 1024 + lane * 8;
-    const float2 d1 = *reinterpret_cast<const float2 *>(s_ap + (c * 4 + t) * 2);
-    int d[4] = {0, 0, 0, 0};
-    int s[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < CHUNK_BLKS; i++) {
-        uint32_t a[4];
-        make_a<QT>(a, u4_get(f.qa, i), u4_get(f.qb, i), kmask, ksign);
-        const uint2 b = *reinterpret_cast<const uint2 *>(bp + i * 256);
-        imma<QT>(d, a, b.x, b.y, d);
-        if constexpr (QT == 1) {           // S0 = sum of the block's weight codes: ones in column 2i only
-            const uint32_t one = (g == 2 * i) ? 0x01010101u : 0u;
-            imma<QT>(s, a, one, one, s);
-        }
-    }
-    if constexpr (QT == 0) {
-        acc[0] = fmaf(f.sa * d1.x, (float)d[0], acc[0]);
-        acc[1] = fmaf(f.sa * d1.y, (float)d[1], acc[1]);
-        acc[2] = fmaf(f.sb * d1.x, (float)d[2], acc[2]);
-        acc[3] = fmaf(f.sb * d1.y, (float)d[3], acc[3]);
-    } else {
-        const float2 m1 = *reinterpret_cast<const float2 *>(s_ap + plane + (c * 4 + t) * 2);
-        const float2 z  = *reinterpret_cast<const float2 *>(s_ap + 2 * plane + (c * 4 + t) * 2);
-        const float sa0 = (float)s[0], sb0 = (float)s[2];
-        // d0*(d1*P + m1*S0) + m0*Z
-        acc[0] += fmaf(f.sa, fmaf(d1.x, (float)d[0], m1.x * sa0), f.ma * z.x);
-        acc[1] += fmaf(f.sa, fmaf(d1.y, (float)d[1], m1.y * sa0), f.ma * z.y);
-        acc[2] += fmaf(f.sb, fmaf(d1.x, (float)d[2], m1.x * sb0), f.mb * z.x);
-        acc[3] += fmaf(f.sb, fmaf(d1.y, (float)d[3], m1.y * sb0), f.mb * z.y);
-    }
-}
-
-// ---- MP == 8: one IMMA per block, columns = activation rows ---------------------------------------
+// ---- MP == 8: one IMMA per block, D column pair (2t, 2t+1) = activation rows; the scale of
+// block i comes from lane (g,i) of the quad by shuffle.  apack [blk][8][32], planes [blk][8].
 template <int QT>
 __device__ __forceinline__ void compute_unit_m8(const Frag<QT> &f, int c, const uint8_t *s_aq, const float *s_ap,
-                                                int plane, int lane, uint32_t kmask, uint32_t ksign, float (&acc)[4])
+                                                int plane, int lane, float (&acc)[4])
 {
     const int t = lane & 3, quad = lane & 28;
-    const int zero[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < CHUNK_BLKS; i++) {
         uint32_t a[4];
-        make_a<QT>(a, u4_get(f.qa, i), u4_get(f.qb, i), kmask, ksign);
+        make_a(a, u4_get(f.qa, i), u4_get(f.qb, i));
         const int blk = c * 4 + i;
         const uint2 b = *reinterpret_cast<const uint2 *>(s_aq + blk * 256 + lane * 8);
         const float2 d1 = *reinterpret_cast<const float2 *>(s_ap + blk * 8 + 2 * t);
         const float d0a = __shfl_sync(0xffffffffu, f.sa, quad | i), d0b = __shfl_sync(0xffffffffu, f.sb, quad | i);
         int d[4];
-        imma<QT>(d, a, b.x, b.y, zero);
         if constexpr (QT == 0) {
+            const int2 cr = *reinterpret_cast<const int2 *>(s_ap + plane + blk * 8 + 2 * t);
+            const int ci[4] = {cr.x, cr.y, cr.x, cr.y};
+            imma<QT>(d, a, b.x, b.y, ci);
             acc[0] = fmaf(d0a * d1.x, (float)d[0], acc[0]);
             acc[1] = fmaf(d0a * d1.y, (float)d[1], acc[1]);
             acc[2] = fmaf(d0b * d1.x, (float)d[2], acc[2]);
             acc[3] = fmaf(d0b * d1.y, (float)d[3], acc[3]);
         } else {
+            const int zero[4] = {0, 0, 0, 0};
             int s[4];
-            imma<QT>(s, a, 0x01010101u, 0x01010101u, zero);
+            imma<QT>(d, a, b.x, b.y, zero);
+            imma<QT>(s, a, 0x10101010u, 0x01010101u, zero);      // 16 * sum of the block's weight codes
             const float2 m1 = *reinterpret_cast<const float2 *>(s_ap + plane + blk * 8 + 2 * t);
             const float2 z  = *reinterpret_cast<const float2 *>(s_ap + 2 * plane + blk * 8 + 2 * t);
             const float m0a = __shfl_sync(0xffffffffu, f.ma, quad | i), m0b = __shfl_sync(0xffffffffu, f.mb, quad | i);
             const float sa0 = (float)s[0], sb0 = (float)s[2];
+            // d0*(d1*P + m1*S0) + m0*Z   (d1, m1 stored /16; P, S0 computed x16)
             acc[0] += fmaf(d0a, fmaf(d1.x, (float)d[0], m1.x * sa0), m0a * z.x);
             acc[1] += fmaf(d0a, fmaf(d1.y, (float)d[1], m1.y * sa0), m0a * z.y);
             acc[2] += fmaf(d0b, fmaf(d1.x, (float)d[2], m1.x * sb0), m0b * z.x);
             acc[3] += fmaf(d0b, fmaf(d1.y, (float)d[3], m1.y * sb0), m0b * z.y);
-        }
-    }
-}
-
-__device__ __forceinline__ int unit_start(int w, int U, int Weff) { return (int)(((long)w * U) / Weff); }
-__device__ __forceinline__ int warp_of_unit(int u, int U, int Weff) { return (int)((((long)u + 1) * Weff - 1) / U); }
-
-// End of a warp's segment [s0,s1) of tile T: combine with the other warps that share the
-// tile (fixed order) and store Y.  acc: MP==2: lane (g,t) holds rows g/g+8 x m=0/1 summed over
-// blocks == t (mod 4) -> quad-reduced here; MP==8: rows g/g+8 x m=2t/2t+1.
-// Arguments by value: keeps the caller's accumulators in registers (no local-memory round trip).
-template <int QT, int MP>
-__device__ __noinline__ void flush_tile(const GemvParams &p, int T, int s0, int s1, int wid, int lane,
-                                        float a0, float a1, float a2, float a3)
-{
-    float acc[4] = {a0, a1, a2, a3};
-    if (MP == 2) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
-            acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
-        }
-    }
-    const int tb = T * p.C, te = tb + p.C;
-    if (!(s0 == tb && s1 == te)) {
-        const int wf = warp_of_unit(tb, p.U, p.Weff), wl = warp_of_unit(te - 1, p.U, p.Weff);
-        const int slot = 2 * wid + (tb <= unit_start(wid, p.U, p.Weff) ? 0 : 1);
-        float *ws = p.partial + (size_t)slot * 128;
-#pragma unroll
-        for (int r = 0; r < 4; r++) ws[r * 32 + lane] = acc[r];
-        __threadfence();
-        __syncwarp();
-        int old = 0;
-        if (lane == 0) old = atomicAdd(p.counters + T, 1);
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if (old != wl - wf) return;                 // not the last contributor
-        __threadfence();
-#pragma unroll
-        for (int r = 0; r < 4; r++) acc[r] = 0.0f;
-        for (int w = wf; w <= wl; w++) {            // fixed order: reproducible rounding
-            const int sl = 2 * w + (tb <= unit_start(w, p.U, p.Weff) ? 0 : 1);
-            const float *rs = p.partial + (size_t)sl * 128;
-#pragma unroll
-            for (int r = 0; r < 4; r++) acc[r] += __ldcg(rs + r * 32 + lane);
-        }
-        if (lane == 0) p.counters[T] = 0;           // ready for the next launch
-    }
-    const float post = (QT == 0) ? 0.0625f : 1.0f;  // undo the 16x of the shifted-nibble A operand (exact)
-    const int g = lane >> 2, t = lane & 3;
-    const int n0 = T * TILE_ROWS + g, n1 = n0 + 8;
-    int m0, m1;
-    if (MP == 2) { if (t != 0) return; m0 = 0; m1 = 1; }
-    else { m0 = 2 * t; m1 = m0 + 1; }
-    if (m0 < p.M) {
-        if (n0 < p.N) p.y[(size_t)m0 * p.y_stride + n0] = acc[0] * post;
-        if (n1 < p.N) p.y[(size_t)m0 * p.y_stride + n1] = acc[2] * post;
-    }
-    if (m1 < p.M) {
-        if (n0 < p.N) p.y[(size_t)m1 * p.y_stride + n0] = acc[1] * post;
-        if (n1 < p.N) p.y[(size_t)m1 * p.y_stride + n1] = acc[3] * post;
-    }
-}
-
-template <int QT, int MP, int PD, bool FUSED>
-__global__ void __launch_bounds__(GEMV_THREADS, 1) q4_gemv_kernel(const GemvParams p)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int CH = chunk_bytes(QT);
-    constexpr int NP = (QT == 0) ? 1 : 3;
-    const int nbp = p.C * CHUNK_BLKS;
-    const int plane = nbp * MP;                         // floats per parameter plane
-    const size_t aq_bytes = (size_t)nbp * 8 * 32;       // shared-memory codes are always the 8-column form
-    uint8_t *s_aq = smem;
-    float *s_ap = reinterpret_cast<float *>(smem + aq_bytes);
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wid = blockIdx.x * GEMV_WARPS + warp;
-    const bool active = wid < p.Weff;
-    int u0 = 0, u1 = 0;
-    Frag<QT> buf[PD];
-    if (active) {                                    // start the weight stream before staging activations
-        u0 = unit_start(wid, p.U, p.Weff);
-        u1 = unit_start(wid + 1, p.U, p.Weff);
-#pragma unroll
-        for (int i = 0; i < PD; i++)
-            if (u0 + i < u1) load_frag<QT>(buf[i], p.wt + (size_t)(u0 + i) * CH, lane);
-    }
-    if constexpr (MP == 2) {
-        // zero the whole pack (columns of other blocks, padded rows/blocks must read as 0)
-        const size_t total16 = (aq_bytes + (size_t)NP * plane * 4) / 16;
-        for (size_t i = threadIdx.x; i < total16; i += GEMV_THREADS)
-            reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
-        __syncthreads();
-        if constexpr (FUSED) {
-            // quantize the activation rows straight into shared memory (every CTA redundantly:
-            // M*K*4 bytes from L2, no second kernel, no global round trip)
-            const int items = p.M * p.nb * 4;                 // one item = 8 consecutive elements
-            for (int base = 0; base < items; base += GEMV_THREADS) {
-                const int id = base + (int)threadIdx.x;
-                const bool valid = id < items;
-                const int bq = valid ? (id >> 2) : 0;          // (m, blk) index
-                const int m = bq / p.nb, blk = bq - m * p.nb;
-                quantize8_emit<QT>(p.x + (size_t)m * p.x_stride + (size_t)blk * QK + (lane & 3) * 8, valid, lane,
-                                   s_aq + ((size_t)blk * 8 + 2 * (blk & 3) + m) * 32, s_ap + (size_t)blk * 2 + m, plane);
-            }
-        } else {
-            // global apack [nbp][2][32] -> 8-column form; planes copied as they are
-            const uint4 *src = reinterpret_cast<const uint4 *>(p.aq);
-            for (int i = threadIdx.x; i < nbp * 4; i += GEMV_THREADS) {       // 16-byte pieces
-                const int blk = i >> 2, m = (i >> 1) & 1, piece = i & 1;
-                reinterpret_cast<uint4 *>(s_aq + ((size_t)blk * 8 + 2 * (blk & 3) + m) * 32)[piece] = src[i];
-            }
-            const uint4 *src2 = reinterpret_cast<const uint4 *>(p.ap);
-            uint4 *dst2 = reinterpret_cast<uint4 *>(s_ap);
-            for (size_t i = threadIdx.x; i < (size_t)NP * plane * 4 / 16; i += GEMV_THREADS) dst2[i] = src2[i];
-        }
-    } else {
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.aq);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_aq);
-        for (size_t i = threadIdx.x; i < aq_bytes / 16; i += GEMV_THREADS) dst[i] = src[i];
-        const uint4 *src2 = reinterpret_cast<const uint4 *>(p.ap);
-        uint4 *dst2 = reinterpret_cast<uint4 *>(s_ap);
-        for (size_t i = threadIdx.x; i < (size_t)NP * plane * 4 / 16; i += GEMV_THREADS) dst2[i] = src2[i];
-    }
-    __syncthreads();
-    if (!active) return;
-
-    // nibble-split constants kept in registers (see and_xor)
-    uint32_t kmask = 0xF0F0F0F0u, ksign = 0x80808080u;
-    asm volatile("" : "+r"(kmask), "+r"(ksign));
-
-    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    int T = u0 / p.C;
-    int c = u0 - T * p.C;
-    int seg0 = u0;
-    const uint8_t *wp = p.wt + (size_t)(u0 + PD) * CH;
-    for (int ub = u0; ub < u1; ub += PD) {
-#pragma unroll
-        for (int i = 0; i < PD; i++) {
-            const int u = ub + i;
-            if (u < u1) {
-                if constexpr (MP == 2) compute_unit_chain4<QT>(buf[i], c, s_aq, s_ap, plane, lane, kmask, ksign, acc);
-                else                   compute_unit_m8<QT>(buf[i], c, s_aq, s_ap, plane, lane, kmask, ksign, acc);
-                if (u + PD < u1) load_frag<QT>(buf[i], wp, lane);
-                wp += CH;
-                ++c;
-                if (c == p.C || u + 1 == u1) {
-                    flush_tile<QT, MP>(p, T, seg0, u + 1, wid, lane, acc[0], acc[1], acc[2], acc[3]);
-                    acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
-                    if (c == p.C) { c = 0; ++T; }
-                    seg0 = u + 1;
-                }
-            }
         }
     }
 }
@@ -773,6 +517,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) q4_gemv_kernel(const GemvPara
 constexpr int PIPE_CONSUMERS = 16;                      // consumer warps = units per stage
 constexpr int PIPE_THREADS = (PIPE_CONSUMERS + 2) * 32; // + producer warp + reducer warp
 constexpr int PIPE_MAX_STAGES = 8;
+constexpr int PIPE_STATIC_TASKS = 3;                    // per CTA, before the first ticket is drawn
 
 struct PipeParams {
     const uint8_t *wt;
@@ -789,7 +534,23 @@ struct PipeParams {
     int            PP;       // pieces (tasks) per tile when C >= 16, else 1
     int            TS;       // units per task
     int            stages;
+    unsigned long long *dbg;   // optional timeline [grid][16] of %globaltimer stamps (B200Q4_DBG=1), else NULL
 };
+
+__device__ __forceinline__ unsigned long long gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Timeline stamps are compiled in only with -DB200Q4_TIMELINE (tools/timeline.py builds that way).
+#ifdef B200Q4_TIMELINE
+#define PIPE_STAMP(slot) do { if (p.dbg) p.dbg[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+#define PIPE_DBG(stmt) do { stmt; } while (0)
+#else
+#define PIPE_STAMP(slot) do { } while (0)
+#define PIPE_DBG(stmt) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *b, int count)
@@ -816,23 +577,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
             "}\n" : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
     }
 }
+__device__ __forceinline__ bool mbar_test(uint64_t *b, uint32_t parity)      // non-blocking
+{
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
 }
 
-// first unit and unit count of task t
-__device__ __forceinline__ void task_range(const PipeParams &p, int t, int &u0, int &n)
+// First unit u0, unit count n, tile T and chunk index c0 of the first unit of task t.
+// No integer division on the common path (the producer is one thread; a division costs ~150
+// cycles of pure latency there).
+__device__ __forceinline__ void task_range(const PipeParams &p, int t, int &u0, int &n, int &T, int &c0)
 {
     if (p.C >= PIPE_CONSUMERS) {                         // PP pieces per tile, TS units each (last shorter)
-        const int T = t / p.PP, piece = t - T * p.PP;
-        const int off = piece * p.TS;
-        u0 = T * p.C + off;
-        n = min(p.TS, p.C - off);
-    } else {                                            // short tiles: TS = whole tiles
+        int piece = 0;
+        T = t;
+        if (p.PP > 1) { T = t / p.PP; piece = t - T * p.PP; }
+        c0 = piece * p.TS;
+        u0 = T * p.C + c0;
+        n = min(p.TS, p.C - c0);
+    } else {                                            // short tiles: a task = TS/C whole tiles
         u0 = t * p.TS;
         n = min(p.TS, p.U - u0);
+        T = t * (p.TS / p.C);
+        c0 = 0;
     }
 }
 
@@ -849,60 +627,79 @@ __device__ __forceinline__ void load_frag_smem(Frag<QT> &f, const uint8_t *chunk
     }
 }
 
-// MP == 2 on the compact pack [blk][2][32]: the B fragment of (block 4c + g/2, row g&1) is
-// lane-linear (c*256 + lane*8); `bmask[i]` is all-ones in the lanes whose block is 4c+i, so
-// block i's IMMA sees that block's codes in columns 2i, 2i+1 and zeros elsewhere.
-template <int QT>
+// MP == 2 ("chain4") on the compact pack [blk][2][32]: the 8 columns of the m16n8k32 tile are used as
+// (block 4c+i, row m) -> column 2i+m.  The B fragment of (block 4c + g/2, row g&1) is lane-linear
+// (c*256 + lane*8) and is fed to block i's IMMA only by the lanes that own block i (zeros
+// elsewhere), so the four IMMAs of a unit accumulate into ONE D fragment and lane (g,t) ends up
+// with the integer sums of block 4c+t for rows g/g+8 -- exactly the block whose scale d0[g][t] it
+// loaded: one I2F + FMUL round per unit, no shuffles.  M1: only row 0 exists.
+// B8: the codes sit in shared memory in the 8-column form [blk][8][32 B] (block 4c+i populated only
+// in columns 2i, 2i+1), so each IMMA's B fragment is one 8-byte load with an immediate offset;
+// otherwise the compact form [blk][2][32 B] is read once per unit and masked per block (large K).
+template <int QT, bool M1, bool B8>
 __device__ __forceinline__ void compute_unit_chain4c(const Frag<QT> &f, int c, const uint8_t *s_aq, const float *s_ap,
-                                                     int plane, int lane, uint32_t kmask, uint32_t ksign,
-                                                     const uint32_t (&bmask)[4], float (&acc)[4])
+                                                     int plane, int lane, float (&acc)[4])
 {
     const int g = lane >> 2, t = lane & 3;
-    const uint2 breg = *reinterpret_cast<const uint2 *>(s_aq + c * 256 + lane * 8);
+    const uint8_t *bp = s_aq + (B8 ? c * 1024 : c * 256) + lane * 8;
+    uint2 breg = make_uint2(0u, 0u);
+    if constexpr (!B8) breg = *reinterpret_cast<const uint2 *>(bp);
     const float2 d1 = *reinterpret_cast<const float2 *>(s_ap + (c * 4 + t) * 2);
     int d[4] = {0, 0, 0, 0};
     int s[4] = {0, 0, 0, 0};
+    if constexpr (QT == 0) {
+        const int2 cr = *reinterpret_cast<const int2 *>(s_ap + plane + (c * 4 + t) * 2);
+        d[0] = cr.x; d[1] = cr.y; d[2] = cr.x; d[3] = cr.y;
+    }
 #pragma unroll
     for (int i = 0; i < CHUNK_BLKS; i++) {
         uint32_t a[4];
-        make_a<QT>(a, u4_get(f.qa, i), u4_get(f.qb, i), kmask, ksign);
-        imma<QT>(d, a, breg.x & bmask[i], breg.y & bmask[i], d);
+        make_a(a, u4_get(f.qa, i), u4_get(f.qb, i));
+        if constexpr (B8) {
+            const uint2 b = *reinterpret_cast<const uint2 *>(bp + i * 256);
+            imma<QT>(d, a, b.x, b.y, d);
+        } else {
+            const bool mine = (g >> 1) == i;
+            imma<QT>(d, a, mine ? breg.x : 0u, mine ? breg.y : 0u, d);
+        }
         if constexpr (QT == 1) {
-            const uint32_t one = (g == 2 * i) ? 0x01010101u : 0u;
-            imma<QT>(s, a, one, one, s);
+            const bool col = g == 2 * i;                 // ones in column 2i only: 16 * S0 of block i
+            imma<QT>(s, a, col ? 0x10101010u : 0u, col ? 0x01010101u : 0u, s);
         }
     }
     if constexpr (QT == 0) {
         acc[0] = (f.sa * d1.x) * (float)d[0];
-        acc[1] = (f.sa * d1.y) * (float)d[1];
         acc[2] = (f.sb * d1.x) * (float)d[2];
-        acc[3] = (f.sb * d1.y) * (float)d[3];
+        if constexpr (M1) { acc[1] = 0.f; acc[3] = 0.f; }
+        else {
+            acc[1] = (f.sa * d1.y) * (float)d[1];
+            acc[3] = (f.sb * d1.y) * (float)d[3];
+        }
     } else {
         const float2 m1 = *reinterpret_cast<const float2 *>(s_ap + plane + (c * 4 + t) * 2);
         const float2 z  = *reinterpret_cast<const float2 *>(s_ap + 2 * plane + (c * 4 + t) * 2);
         const float sa0 = (float)s[0], sb0 = (float)s[2];
         acc[0] = fmaf(f.sa, fmaf(d1.x, (float)d[0], m1.x * sa0), f.ma * z.x);
-        acc[1] = fmaf(f.sa, fmaf(d1.y, (float)d[1], m1.y * sa0), f.ma * z.y);
         acc[2] = fmaf(f.sb, fmaf(d1.x, (float)d[2], m1.x * sb0), f.mb * z.x);
-        acc[3] = fmaf(f.sb, fmaf(d1.y, (float)d[3], m1.y * sb0), f.mb * z.y);
+        if constexpr (M1) { acc[1] = 0.f; acc[3] = 0.f; }
+        else {
+            acc[1] = fmaf(f.sa, fmaf(d1.y, (float)d[1], m1.y * sa0), f.ma * z.y);
+            acc[3] = fmaf(f.sb, fmaf(d1.y, (float)d[3], m1.y * sb0), f.mb * z.y);
+        }
     }
 }
 
-// Reducer: end of the run of units [.., u_last] of tile T inside task `task`.
+// Reducer: a run of units of tile T inside task `task` is complete.
+//   MP == 2: lane (g, r) carries ONE value: row g + 8*(r>>1), activation row m = r&1 (the consumers
+//            already reduced over the quad);   MP == 8: lane (g,t) carries rows g/g+8 x m = 2t, 2t+1.
 template <int QT, int MP>
 __device__ __forceinline__ void pipe_emit(const PipeParams &p, int T, int task, int lane, float (&acc)[4])
 {
-    if (MP == 2) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
-            acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
-        }
-    }
+    constexpr int NV = (MP == 2) ? 1 : 4;
     if (p.C >= PIPE_CONSUMERS && p.PP > 1) {            // the tile is split over PP tasks
         float *ws = p.partial + (size_t)task * 128;
 #pragma unroll
-        for (int r = 0; r < 4; r++) ws[r * 32 + lane] = acc[r];
+        for (int r = 0; r < NV; r++) ws[r * 32 + lane] = acc[r];
         __threadfence();
         __syncwarp();
         int old = 0;
@@ -911,90 +708,107 @@ __device__ __forceinline__ void pipe_emit(const PipeParams &p, int T, int task, 
         if (old != p.PP - 1) return;
         __threadfence();
 #pragma unroll
-        for (int r = 0; r < 4; r++) acc[r] = 0.0f;
+        for (int r = 0; r < NV; r++) acc[r] = 0.0f;
         for (int k = 0; k < p.PP; k++) {                // piece order: reproducible rounding
             const float *rs = p.partial + (size_t)(T * p.PP + k) * 128;
 #pragma unroll
-            for (int r = 0; r < 4; r++) acc[r] += __ldcg(rs + r * 32 + lane);
+            for (int r = 0; r < NV; r++) acc[r] += __ldcg(rs + r * 32 + lane);
         }
         if (lane == 0) p.tile_counters[T] = 0;
     }
-    const float post = (QT == 0) ? 0.0625f : 1.0f;
+    const float post = (QT == 0) ? 0.0625f : 1.0f;       // undo the 16x of the A/B code scaling (exact)
     const int g = lane >> 2, t = lane & 3;
-    const int n0 = T * TILE_ROWS + g, n1 = n0 + 8;
-    int m0, m1;
-    if (MP == 2) { if (t != 0) return; m0 = 0; m1 = 1; }
-    else { m0 = 2 * t; m1 = m0 + 1; }
-    if (m0 < p.M) {
-        if (n0 < p.N) p.y[(size_t)m0 * p.y_stride + n0] = acc[0] * post;
-        if (n1 < p.N) p.y[(size_t)m0 * p.y_stride + n1] = acc[2] * post;
-    }
-    if (m1 < p.M) {
-        if (n0 < p.N) p.y[(size_t)m1 * p.y_stride + n0] = acc[1] * post;
-        if (n1 < p.N) p.y[(size_t)m1 * p.y_stride + n1] = acc[3] * post;
+    if (MP == 2) {
+        const int m = t & 1, n = T * TILE_ROWS + g + 8 * (t >> 1);
+        if (m < p.M && n < p.N) p.y[(size_t)m * p.y_stride + n] = acc[0] * post;
+    } else {
+        const int n0 = T * TILE_ROWS + g, n1 = n0 + 8;
+        const int m0 = 2 * t, m1 = m0 + 1;
+        if (m0 < p.M) {
+            if (n0 < p.N) p.y[(size_t)m0 * p.y_stride + n0] = acc[0] * post;
+            if (n1 < p.N) p.y[(size_t)m0 * p.y_stride + n1] = acc[2] * post;
+        }
+        if (m1 < p.M) {
+            if (n0 < p.N) p.y[(size_t)m1 * p.y_stride + n0] = acc[1] * post;
+            if (n1 < p.N) p.y[(size_t)m1 * p.y_stride + n1] = acc[3] * post;
+        }
     }
 }
 
-template <int QT, int MP, bool FUSED>
+template <int QT, int MP, bool FUSED, bool M1, bool B8>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) q4_gemv_pipe_kernel(const PipeParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int CH = chunk_bytes(QT);
-    constexpr int NP = (QT == 0) ? 1 : 3;
+    constexpr int NP = (QT == 0) ? 2 : 3;
     constexpr int STAGE_BYTES = PIPE_CONSUMERS * CH;
     const int nbp = p.C * CHUNK_BLKS;
     const int plane = nbp * MP;
     // shared-memory map: [stages x STAGE_BYTES][red: stages x 16 x 512 B][apack codes][planes][barriers][desc]
     uint8_t *s_stage = smem;
     float   *s_red = reinterpret_cast<float *>(smem + (size_t)p.stages * STAGE_BYTES);
-    uint8_t *s_aq = reinterpret_cast<uint8_t *>(s_red) + (size_t)p.stages * PIPE_CONSUMERS * 512;
-    float   *s_ap = reinterpret_cast<float *>(s_aq + (size_t)nbp * MP * 32);
+    uint8_t *s_aq = reinterpret_cast<uint8_t *>(s_red) + (size_t)p.stages * PIPE_CONSUMERS * (MP == 2 ? 128 : 512);
+    constexpr int AQ_BLK = (MP == 2 && B8) ? 256 : MP * 32;    // code bytes per block in shared memory
+    float   *s_ap = reinterpret_cast<float *>(s_aq + (size_t)nbp * AQ_BLK);
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_ap) + (((size_t)NP * plane * 4 + 15) & ~(size_t)15));
     uint64_t *bar_empty = bar_full + PIPE_MAX_STAGES;
     uint64_t *bar_done = bar_empty + PIPE_MAX_STAGES;       // consumers finished a stage's partials
-    int4     *s_desc = reinterpret_cast<int4 *>(bar_done + PIPE_MAX_STAGES);   // {first unit, n units (<0 = stop), chunk index of first unit, task}
+    int4     *s_desc = reinterpret_cast<int4 *>(bar_done + PIPE_MAX_STAGES);   // {n units (<0 = stop), chunk index of first unit, tile of first unit, task}
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stages; i++) {
             mbar_init(&bar_full[i], 1);
-            mbar_init(&bar_empty[i], PIPE_CONSUMERS + 1);
+            mbar_init(&bar_empty[i], 1);                 // released by the reducer (which waited for every consumer)
             mbar_init(&bar_done[i], PIPE_CONSUMERS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (threadIdx.x == 0) PIPE_STAMP(0);
     cudaTriggerProgrammaticLaunchCompletion();           // let the next launch start streaming early
 
     if (warp == PIPE_CONSUMERS) {
         // ===================== producer =====================
         if (lane == 0) {
-            int it = 0;
-            int task = blockIdx.x;                       // first task is static: no dependency on the previous launch
-            bool synced = false;
-            while (task < p.ntasks) {
-                int u0, n;
-                task_range(p, task, u0, n);
-                int c0 = u0 % p.C;
-                for (int r = 0; r < n; r += PIPE_CONSUMERS, ++it) {
-                    const int s = it % p.stages;
-                    if (it >= p.stages) mbar_wait(&bar_empty[s], ((it / p.stages) - 1) & 1);
+            int s = 0;                                   // stage index
+            uint32_t ph = 1;                             // parity to wait for on bar_empty (first lap: passes at once)
+            auto issue_task = [&](int task) {
+                int u0, n, T, c0;
+                task_range(p, task, u0, n, T, c0);
+                for (int r = 0; r < n; r += PIPE_CONSUMERS) {
+                    mbar_wait(&bar_empty[s], ph);
                     const int cnt = min(PIPE_CONSUMERS, n - r);
-                    s_desc[s] = make_int4(u0 + r, cnt, c0, task);
-                    c0 = (c0 + cnt) % p.C;
+                    s_desc[s] = make_int4(cnt, c0, T, task);
+                    c0 += cnt;
+                    while (c0 >= p.C) { c0 -= p.C; ++T; }
                     mbar_arrive_expect_tx(&bar_full[s], (uint32_t)cnt * CH);
                     bulk_g2s(s_stage + (size_t)s * STAGE_BYTES, p.wt + (size_t)(u0 + r) * CH, (uint32_t)cnt * CH, &bar_full[s]);
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
-                if (!synced) { cudaGridDependencySynchronize(); synced = true; }
-                task = gridDim.x + atomicAdd(p.ticket, 1);
+            };
+            // The first PIPE_STATIC_TASKS tasks of every CTA are static (task = b + k*grid): they
+            // need nothing from the previous launch, so under programmatic dependent launch the
+            // whole stage ring is already filling while the previous kernel drains.
+            for (int k = 0; k < PIPE_STATIC_TASKS; k++) {
+                const int task = (int)blockIdx.x + k * (int)gridDim.x;
+                if (task < p.ntasks) issue_task(task);
             }
-            if (!synced) cudaGridDependencySynchronize();
-            {   // stop marker
-                const int s = it % p.stages;
-                if (it >= p.stages) mbar_wait(&bar_empty[s], ((it / p.stages) - 1) & 1);
-                s_desc[s] = make_int4(0, -1, 0, 0);
-                mbar_arrive(&bar_full[s]);
+            PIPE_STAMP(1);
+            cudaGridDependencySynchronize();
+            PIPE_STAMP(2);
+            // then dynamic tickets, fetched one task ahead so the atomic's latency hides behind the copies
+            const int base = PIPE_STATIC_TASKS * (int)gridDim.x;
+            int cur = base + atomicAdd(p.ticket, 1);
+            while (cur < p.ntasks) {
+                const int nxt = base + atomicAdd(p.ticket, 1);
+                issue_task(cur);
+                cur = nxt;
             }
+            mbar_wait(&bar_empty[s], ph);                // stop marker
+            s_desc[s] = make_int4(-1, 0, 0, 0);
+            mbar_arrive(&bar_full[s]);
+            PIPE_STAMP(8);
             // the last CTA to run out of tasks re-arms the ticket counter for the next launch
             if (atomicAdd(p.ticket + 1, 1) == (int)gridDim.x - 1) { p.ticket[0] = 0; p.ticket[1] = 0; __threadfence(); }
         }
@@ -1004,36 +818,66 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) q4_gemv_pipe_kernel(const Pip
     if (warp == PIPE_CONSUMERS + 1) {
         // ===================== reducer =====================
         cudaGridDependencySynchronize();
+        constexpr int RW = (MP == 2) ? 32 : 128;         // floats per unit in the reduction ring
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         int curT = -1, curTask = -1;
-        for (int it = 0;; ++it) {
-            const int s = it % p.stages;
-            mbar_wait(&bar_full[s], (it / p.stages) & 1);
+        int s = 0;
+        uint32_t ph = 0;
+        for (;;) {
+            // bar_done implies bar_full (every consumer passed it), so one wait per stage suffices;
+            // the stop marker carries no consumer arrivals and is announced on bar_full alone.
+            if (!mbar_test(&bar_done[s], ph)) {
+                mbar_wait(&bar_full[s], ph);
+                if (s_desc[s].x < 0) break;
+                mbar_wait(&bar_done[s], ph);
+            }
             const int4 dsc = s_desc[s];
-            if (dsc.y < 0) break;
+            if (dsc.x < 0) break;
             const int task = dsc.w;
-            int T = (dsc.x - dsc.z) / p.C;               // one division per stage
-            int left = p.C - dsc.z;                      // units of tile T from dsc.x on
-            mbar_wait(&bar_done[s], (it / p.stages) & 1);
-            const float *red = s_red + (size_t)s * PIPE_CONSUMERS * 128 + lane * 4;
+            int T = dsc.z;
+            int left = p.C - dsc.y;                      // units of tile T from the stage's first unit on
+            const float *red = s_red + (size_t)s * PIPE_CONSUMERS * RW + (MP == 2 ? lane : lane * 4);
             int j = 0;
-            while (j < dsc.y) {
+            while (j < dsc.x) {
                 if (T != curT || task != curTask) {
                     if (curT >= 0) pipe_emit<QT, MP>(p, curT, curTask, lane, acc);
                     acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
                     curT = T; curTask = task;
                 }
-                const int run = min(dsc.y - j, left);    // units of this stage that belong to tile T
-                if (run == PIPE_CONSUMERS) {             // common case: the whole stage is one tile
-                    float4 v[PIPE_CONSUMERS];
+                const int run = min(dsc.x - j, left);    // units of this stage that belong to tile T
+                if (run == PIPE_CONSUMERS) {
+                    // common case, the whole stage is one tile: four independent chains of four
+                    // (fixed association -> bit-reproducible, a quarter of the dependent latency)
+                    if constexpr (MP == 2) {
+                        float v[PIPE_CONSUMERS];
 #pragma unroll
-                    for (int k = 0; k < PIPE_CONSUMERS; k++) v[k] = *reinterpret_cast<const float4 *>(red + k * 128);
+                        for (int k = 0; k < PIPE_CONSUMERS; k++) v[k] = red[k * RW];
+                        acc[0] += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])) +
+                                  (((v[8] + v[9]) + (v[10] + v[11])) + ((v[12] + v[13]) + (v[14] + v[15])));
+                    } else {
+                        float4 v[PIPE_CONSUMERS];
 #pragma unroll
-                    for (int k = 0; k < PIPE_CONSUMERS; k++) { acc[0] += v[k].x; acc[1] += v[k].y; acc[2] += v[k].z; acc[3] += v[k].w; }
+                        for (int k = 0; k < PIPE_CONSUMERS; k++) v[k] = *reinterpret_cast<const float4 *>(red + k * RW);
+                        float4 q[4];
+#pragma unroll
+                        for (int h = 0; h < 4; h++) {
+                            q[h].x = (v[4 * h].x + v[4 * h + 1].x) + (v[4 * h + 2].x + v[4 * h + 3].x);
+                            q[h].y = (v[4 * h].y + v[4 * h + 1].y) + (v[4 * h + 2].y + v[4 * h + 3].y);
+                            q[h].z = (v[4 * h].z + v[4 * h + 1].z) + (v[4 * h + 2].z + v[4 * h + 3].z);
+                            q[h].w = (v[4 * h].w + v[4 * h + 1].w) + (v[4 * h + 2].w + v[4 * h + 3].w);
+                        }
+                        acc[0] += (q[0].x + q[1].x) + (q[2].x + q[3].x);
+                        acc[1] += (q[0].y + q[1].y) + (q[2].y + q[3].y);
+                        acc[2] += (q[0].z + q[1].z) + (q[2].z + q[3].z);
+                        acc[3] += (q[0].w + q[1].w) + (q[2].w + q[3].w);
+                    }
                 } else {
                     for (int k = j; k < j + run; k++) {
-                        const float4 v = *reinterpret_cast<const float4 *>(red + k * 128);
-                        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+                        if constexpr (MP == 2) acc[0] += red[k * RW];
+                        else {
+                            const float4 v = *reinterpret_cast<const float4 *>(red + k * RW);
+                            acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+                        }
                     }
                 }
                 j += run;
@@ -1042,20 +886,36 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) q4_gemv_pipe_kernel(const Pip
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[s]);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (curT >= 0) pipe_emit<QT, MP>(p, curT, curTask, lane, acc);
+        if (lane == 0) PIPE_STAMP(7);
         return;
     }
 
     // ===================== consumers =====================
     cudaGridDependencySynchronize();                     // X may be the previous kernel's output
+    if (threadIdx.x == 0) PIPE_STAMP(3);
     const int ctid = threadIdx.x;                        // 0 .. 511
     constexpr int CTHREADS = PIPE_CONSUMERS * 32;
+    // where (block, row m)'s 32 code bytes live in shared memory
+    auto rec_of = [&](int blk, int m) { return s_aq + (size_t)blk * AQ_BLK + ((MP == 2 && B8) ? (2 * (blk & 3) + m) * 32 : m * 32); };
     if constexpr (FUSED) {
-        // padded blocks (nb .. nbp) and the unused row of an M=1 call must read as zero
-        const size_t total16 = ((size_t)nbp * MP * 32 + (((size_t)NP * plane * 4 + 15) & ~(size_t)15)) / 16;
-        for (size_t i = ctid; i < total16; i += CTHREADS) reinterpret_cast<uint4 *>(s_aq)[i] = make_uint4(0u, 0u, 0u, 0u);
-        asm volatile("bar.sync 1, %0;" :: "n"(CTHREADS) : "memory");
+        // Everything quantization does not write must read as zero: the unused columns of the
+        // 8-column form, the records of padded blocks (nb .. nbp: weight scale 0, but 0 x garbage
+        // could be NaN) and row 1 of an M = 1 call.  Quantization writes disjoint bytes, so no
+        // barrier is needed in between.
+        for (int i = ctid; i < nbp * AQ_BLK / 8; i += CTHREADS) {
+            const int blk = i / (AQ_BLK / 8), w8 = i - blk * (AQ_BLK / 8);      // 8-byte piece w8 of block blk
+            const int col = w8 >> 2;                                            // 32-byte record index inside the block
+            const int m = (MP == 2 && B8) ? col - 2 * (blk & 3) : col;
+            const bool live = blk < p.nb && m >= 0 && m < p.M;
+            if (!live) reinterpret_cast<uint2 *>(s_aq + (size_t)blk * AQ_BLK)[w8] = make_uint2(0u, 0u);
+        }
+        for (int i = ctid; i < NP * nbp * MP; i += CTHREADS) {
+            const int e = i % (nbp * MP), blk = e / MP, m = e - blk * MP;
+            if (blk >= p.nb || m >= p.M) s_ap[i] = 0.0f;
+        }
         const int items = p.M * p.nb * 4;
         for (int base = 0; base < items; base += CTHREADS) {
             const int id = base + ctid;
@@ -1063,46 +923,128 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) q4_gemv_pipe_kernel(const Pip
             const int bq = valid ? (id >> 2) : 0;
             const int m = bq / p.nb, blk = bq - m * p.nb;
             quantize8_emit<QT>(p.x + (size_t)m * p.x_stride + (size_t)blk * QK + (lane & 3) * 8, valid, lane,
-                               s_aq + ((size_t)blk * MP + m) * 32, s_ap + (size_t)blk * MP + m, plane);
+                               rec_of(blk, m), s_ap + (size_t)blk * MP + m, plane);
         }
     } else {
+        // global apack is always the compact form [nbp][MP][32]
         const uint4 *src = reinterpret_cast<const uint4 *>(p.aq);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_aq);
-        for (size_t i = ctid; i < (size_t)nbp * MP * 32 / 16; i += CTHREADS) dst[i] = src[i];
+        if constexpr (MP == 2 && B8) {
+            for (int i = ctid; i < nbp * 16; i += CTHREADS) {                   // 16-byte pieces of the 8-column form
+                const int blk = i >> 4, col = (i >> 1) & 7, piece = i & 1;
+                const int m = col - 2 * (blk & 3);
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (m >= 0 && m < 2) v = src[(blk * 2 + m) * 2 + piece];
+                reinterpret_cast<uint4 *>(s_aq)[i] = v;
+            }
+        } else {
+            uint4 *dst = reinterpret_cast<uint4 *>(s_aq);
+            for (size_t i = ctid; i < (size_t)nbp * MP * 32 / 16; i += CTHREADS) dst[i] = src[i];
+        }
         const uint4 *src2 = reinterpret_cast<const uint4 *>(p.ap);
         uint4 *dst2 = reinterpret_cast<uint4 *>(s_ap);
         for (size_t i = ctid; i < (size_t)NP * plane * 4 / 16; i += CTHREADS) dst2[i] = src2[i];
     }
     asm volatile("bar.sync 1, %0;" :: "n"(CTHREADS) : "memory");
 
-    uint32_t kmask = 0xF0F0F0F0u, ksign = 0x80808080u;
-    asm volatile("" : "+r"(kmask), "+r"(ksign));
-    uint32_t bmask[4];
+    if (threadIdx.x == 0) PIPE_STAMP(4);
+    // Two stages per iteration when the second one has already landed: the two units' IMMA chains
+    // are independent, so their latencies overlap (a warp owns only 4 issue slots' worth of
+    // neighbours on its scheduler; one unit at a time leaves the pipes idle between dependent ops).
+    auto next_stage = [&](int &s, uint32_t &ph) { if (++s == p.stages) { s = 0; ph ^= 1; } };
+    // chunk index of this warp's unit in a stage; T receives its tile
+    auto unit_of = [&](const int4 &dsc, int &T) { int c = dsc.y + warp; T = dsc.z; while (c >= p.C) { c -= p.C; ++T; } return c; };
+    auto run_unit = [&](const Frag<QT> &f, int c, float (&acc)[4]) {
+        if constexpr (MP == 2) compute_unit_chain4c<QT, M1, B8>(f, c, s_aq, s_ap, plane, lane, acc);
+        else {
+            acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+            compute_unit_m8<QT>(f, c, s_aq, s_ap, plane, lane, acc);
+        }
+    };
+    auto put = [&](int s, float (&acc)[4]) {
+        if constexpr (MP == 2) {
+            // quad reduction here (the consumers have the slack, the single reducer warp does not):
+            // afterwards every lane of the quad holds all four sums; lane t keeps value t.
 #pragma unroll
-    for (int i = 0; i < 4; i++) bmask[i] = ((lane >> 3) == i) ? 0xFFFFFFFFu : 0u;
-
-    for (int it = 0;; ++it) {
-        const int s = it % p.stages;
-        mbar_wait(&bar_full[s], (it / p.stages) & 1);
-        const int4 dsc = s_desc[s];
-        if (dsc.y < 0) break;
-        if (warp < dsc.y) {
-            int c = dsc.z + warp;
-            while (c >= p.C) c -= p.C;
-            Frag<QT> f;
-            load_frag_smem<QT>(f, s_stage + (size_t)s * STAGE_BYTES + (size_t)warp * CH, lane);
-            float acc[4];
-            if constexpr (MP == 2) compute_unit_chain4c<QT>(f, c, s_aq, s_ap, plane, lane, kmask, ksign, bmask, acc);
-            else {
-                acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-                compute_unit_m8<QT>(f, c, s_aq, s_ap, plane, lane, kmask, ksign, acc);
+            for (int r = 0; r < 4; r++) {
+                acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
+                acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
             }
+            const int t = lane & 3;
+            // value index r = 2*(row half) + m  <->  acc[] order is {g:m0, g:m1, g+8:m0, g+8:m1}
+            const float v = t == 0 ? acc[0] : t == 1 ? acc[1] : t == 2 ? acc[2] : acc[3];
+            s_red[((size_t)s * PIPE_CONSUMERS + warp) * 32 + lane] = v;
+        } else {
             *reinterpret_cast<float4 *>(s_red + ((size_t)s * PIPE_CONSUMERS + warp) * 128 + lane * 4) =
                 make_float4(acc[0], acc[1], acc[2], acc[3]);
         }
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&bar_done[s]); mbar_arrive(&bar_empty[s]); }
+    };
+    auto put_zero = [&](int s) {
+        if constexpr (MP == 2) s_red[((size_t)s * PIPE_CONSUMERS + warp) * 32 + lane] = 0.f;
+        else *reinterpret_cast<float4 *>(s_red + ((size_t)s * PIPE_CONSUMERS + warp) * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    int s = 0;
+    uint32_t ph = 0;
+    bool first = true;
+    int cr = 0;
+    for (;;) {
+        mbar_wait(&bar_full[s], ph);
+        if (first && threadIdx.x == 0) { PIPE_STAMP(5); } first = false;
+        const int4 d0 = s_desc[s];
+        if (d0.x < 0) break;
+        PIPE_DBG(if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && cr < 24) p.dbg[3000 + cr * 4 + 0] = gtimer(););
+        int s1 = s; uint32_t ph1 = ph;
+        next_stage(s1, ph1);
+        bool two = mbar_test(&bar_full[s1], ph1);
+        int4 d1 = make_int4(-1, 0, 0, 0);
+        if (two) { d1 = s_desc[s1]; two = d1.x >= 0; }
+        if (two) {
+            const bool h0 = warp < d0.x, h1 = warp < d1.x;
+            Frag<QT> f0, f1;
+            float a0[4], a1[4];
+            if (h0) load_frag_smem<QT>(f0, s_stage + (size_t)s * STAGE_BYTES + (size_t)warp * CH, lane);
+            if (h1) load_frag_smem<QT>(f1, s_stage + (size_t)s1 * STAGE_BYTES + (size_t)warp * CH, lane);
+            if (h0 && h1) {                      // the common, fully interleavable case
+                int T0, T1;
+                const int c0 = unit_of(d0, T0), c1 = unit_of(d1, T1);
+                run_unit(f0, c0, a0);
+                run_unit(f1, c1, a1);
+                if (T0 == T1 && d0.w == d1.w) {  // same tile, same task: one partial for both units
+                    a0[0] += a1[0]; a0[1] += a1[1]; a0[2] += a1[2]; a0[3] += a1[3];
+                    a1[0] = a1[1] = a1[2] = a1[3] = 0.f;
+                    put(s, a0);
+                    put_zero(s1);
+                } else {
+                    put(s, a0);
+                    put(s1, a1);
+                }
+            } else {
+                int T;
+                if (h0) { run_unit(f0, unit_of(d0, T), a0); put(s, a0); }
+                if (h1) { run_unit(f1, unit_of(d1, T), a1); put(s1, a1); }
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&bar_done[s]); mbar_arrive(&bar_done[s1]); }
+            PIPE_DBG(if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && cr < 24) { p.dbg[3000 + cr * 4 + 1] = gtimer(); p.dbg[3000 + cr * 4 + 2] = 2; });
+            ++cr;
+            s = s1; ph = ph1;
+            next_stage(s, ph);
+        } else {
+            if (warp < d0.x) {
+                Frag<QT> f0;
+                float a0[4];
+                int T;
+                load_frag_smem<QT>(f0, s_stage + (size_t)s * STAGE_BYTES + (size_t)warp * CH, lane);
+                run_unit(f0, unit_of(d0, T), a0);
+                put(s, a0);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_done[s]);
+            PIPE_DBG(if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && cr < 24) { p.dbg[3000 + cr * 4 + 1] = gtimer(); p.dbg[3000 + cr * 4 + 2] = 1; });
+            ++cr;
+            next_stage(s, ph);
+        }
     }
+    if (threadIdx.x == 0) PIPE_STAMP(6);
 }
 
 // ---------------------------------------------------------------------------
