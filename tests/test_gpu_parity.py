@@ -146,7 +146,13 @@ def test_wdata_entry_equals_fp32_entry_bitwise(gpu, oracle, qt, tag):
         w = gpu.Q4Weight(qt, wq, n, k)
         y1 = gpu.mul_mat(w, x)
         y2 = gpu.mul_mat_wdata(w, oracle.quantize_rows(qt, x), m)
-        assert np.array_equal(y1.view(np.uint32), y2.view(np.uint32)), (n, k, m)
+        if m == 1:
+            # M = 1 with fp32 input runs the fused "octet" kernel, the wdata entry the two-row kernel:
+            # same codes, different (fixed) summation trees -> equal to fp32 rounding.  One wrong
+            # 4-bit code would move an output by ~1e-3 of the row scale.
+            assert np.abs(y1 - y2).max() <= 4e-6 * np.abs(y2).max(), (n, k, m)
+        else:
+            assert np.array_equal(y1.view(np.uint32), y2.view(np.uint32)), (n, k, m)
         w.free()
 
 
@@ -208,13 +214,18 @@ def test_run_to_run_determinism_and_batch_consistency(gpu, oracle, qt, tag):
     y8a = gpu.mul_mat(w, x)
     y8b = gpu.mul_mat(w, x)
     assert np.array_equal(y8a.view(np.uint32), y8b.view(np.uint32))        # fixed-order partial sums
-    # a row computed alone (decode kernel) and inside a pair use the same arithmetic: identical bits
+    # a row inside a pair is independent of its partner: identical bits whatever the other row is
+    y2a = gpu.mul_mat(w, x[2:4])
+    y2b = gpu.mul_mat(w, np.stack([x[7], x[3]]))
+    assert np.array_equal(y2a[1:2].view(np.uint32), y2b[1:2].view(np.uint32))
+    # alone (octet kernel), in a pair (chain4) or in a batch of 8 (one IMMA per block) the
+    # summation trees differ: equal to fp32 rounding
     y1 = gpu.mul_mat(w, x[3:4])
-    y2p = gpu.mul_mat(w, x[2:4])
-    assert np.array_equal(y1.view(np.uint32), y2p[1:2].view(np.uint32))
-    # inside a batch of 8 (one IMMA per block, different summation tree): equal to rounding
-    assert_close(y1, y8a[3:4])
-    assert np.abs(y1 - y8a[3:4]).max() <= 4e-6 * np.abs(y8a[3:4]).max()
+    y1b = gpu.mul_mat(w, x[3:4])
+    assert np.array_equal(y1.view(np.uint32), y1b.view(np.uint32))
+    for other in (y2a[1:2], y8a[3:4]):
+        assert_close(y1, other)
+        assert np.abs(y1 - other).max() <= 4e-6 * np.abs(other).max()
     # scaling the activations by a power of two scales the result exactly
     y2 = gpu.mul_mat(w, x * np.float32(4.0))
     assert np.array_equal((y8a * np.float32(4.0)).view(np.uint32), y2.view(np.uint32))

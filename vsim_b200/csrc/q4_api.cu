@@ -5,6 +5,9 @@
 #include "../../include/b200q4.h"
 #include "q4_kernels.cuh"
 
+using b200q4::PIPE_MAX_STAGES;
+using b200q4::PIPE_TILE_SPLIT;
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +31,8 @@ struct Ctx {
     int device = -1;
     int sms = 0;
     int smem_optin = 0;
+    int smem_per_sm = 0;
+    bool two_ctas = false;           // B200Q4_TWO_CTAS=1: two 8-consumer CTAs per SM when they fit (measured slower: 11.3 vs 9.2 us)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint8_t *d_aq = nullptr; size_t aq_cap = 0;
@@ -86,31 +91,47 @@ int need_init()
 }
 
 // ---- pipelined decode kernel (q4_gemv_pipe_kernel) ---------------------------------------------
-struct PipePlan { int MP, stages, PP, TS, ntasks; bool b8; size_t smem; };
+struct PipePlan { int MP, stages, PP, TS, ntasks, ncw; bool b8, m1; size_t smem; };
 
-PipePlan pipe_plan(const b200q4_weight *w, int M)
+// m1: a single activation row that the kernel will quantize itself (fused) -> octet mode
+PipePlan pipe_plan(const b200q4_weight *w, int M, bool can_fuse)
 {
     PipePlan pp{};
-    const int type = w->type, nbp = w->C * CHUNK_BLKS;
-    const size_t budget = (size_t)(g.smem_optin > 0 ? g.smem_optin : 232448);
-    auto stage_of = [&](int MP) { return (size_t)PIPE_CONSUMERS * chunk_bytes(type) + (size_t)PIPE_CONSUMERS * (MP == 2 ? 128 : 512); };
-    auto fixed = [&](int MP, bool b8) {
-        const size_t planes = ((size_t)(type == 0 ? 2 : 3) * nbp * MP * 4 + 15) & ~(size_t)15;
-        return (size_t)nbp * (MP == 2 && b8 ? 256 : MP * 32) + planes + 3 * PIPE_MAX_STAGES * 8 + PIPE_MAX_STAGES * 16 + 256;
+    const int type = w->type;
+    const size_t optin = (size_t)(g.smem_optin > 0 ? g.smem_optin : 232448);
+    auto stage_of = [&](int MP, int ncw) { return (size_t)2 * ncw * chunk_bytes(type) + (size_t)2 * ncw * (MP == 2 ? 128 : 512); };
+    auto fixed = [&](int MP, bool m1, bool b8) {
+        const int rows = m1 ? 1 : MP;
+        const int nbp = m1 ? ((w->C * CHUNK_BLKS + 7) & ~7) : w->C * CHUNK_BLKS;   // M1 pads to whole octets
+        const size_t planes = ((size_t)(type == 0 ? 2 : 3) * nbp * rows * 4 + 15) & ~(size_t)15;
+        return (size_t)nbp * (MP == 2 && b8 ? 256 : rows * 32) + planes + 3 * PIPE_MAX_STAGES * 8 + PIPE_MAX_STAGES * 16 + 256;
     };
     pp.MP = (M <= 2) ? 2 : 8;
-    if (pp.MP == 8 && fixed(8, false) + 2 * stage_of(8) > budget) pp.MP = 2;
-    const size_t stage = stage_of(pp.MP);
-    // 8-column code layout (no per-IMMA masking) whenever it still leaves >= 5 stages of ring
-    pp.b8 = pp.MP == 2 && fixed(2, true) + 5 * stage <= budget;
-    if (fixed(pp.MP, pp.b8) + 2 * stage > budget) { pp.MP = 0; return pp; }
-    long st = (long)((budget - fixed(pp.MP, pp.b8)) / stage);
-    pp.stages = (int)(st > PIPE_MAX_STAGES ? PIPE_MAX_STAGES : st);
-    pp.smem = fixed(pp.MP, pp.b8) + (size_t)pp.stages * stage;
+    if (pp.MP == 8 && fixed(8, false, false) + 2 * stage_of(8, 16) > optin) pp.MP = 2;
+    pp.m1 = pp.MP == 2 && M == 1 && can_fuse;
+    // Preferred: two CTAs of 8 consumer warps per SM (each gets half of the SM's shared memory minus
+    // the 1 KB the hardware reserves per CTA) with the 8-column code layout and >= 3 stages of ring.
+    const size_t half = (size_t)(g.smem_per_sm > 0 ? g.smem_per_sm : 233472) / 2 - 1024;
+    if (g.two_ctas && pp.MP == 2 && fixed(2, pp.m1, true) + 3 * stage_of(2, 8) <= half) {
+        pp.ncw = 8; pp.b8 = true;
+        long st = (long)((half - fixed(2, pp.m1, true)) / stage_of(2, 8));
+        pp.stages = (int)(st > PIPE_MAX_STAGES ? PIPE_MAX_STAGES : st);
+        pp.smem = fixed(2, pp.m1, true) + (size_t)pp.stages * stage_of(2, 8);
+    } else {
+        pp.ncw = 16;
+        const size_t stage = stage_of(pp.MP, 16);
+        pp.b8 = pp.MP == 2 && fixed(2, pp.m1, true) + 3 * stage <= optin;
+        if (fixed(pp.MP, pp.m1, pp.b8) + 2 * stage > optin) { pp.MP = 0; return pp; }
+        long st = (long)((optin - fixed(pp.MP, pp.m1, pp.b8)) / stage);
+        pp.stages = (int)(st > PIPE_MAX_STAGES ? PIPE_MAX_STAGES : st);
+        pp.smem = fixed(pp.MP, pp.m1, pp.b8) + (size_t)pp.stages * stage;
+    }
     const int C = w->C;
-    if (C >= PIPE_CONSUMERS) {
+    if (C >= PIPE_TILE_SPLIT) {
         pp.PP = (C + 63) / 64;
         pp.TS = (C + pp.PP - 1) / pp.PP;
+        pp.TS = (pp.TS + 1) & ~1;                      // even: unit pairs stay aligned to quant-block octets
+        pp.PP = (C + pp.TS - 1) / pp.TS;
         pp.ntasks = w->n_tiles * pp.PP;
     } else {
         pp.PP = 1;
@@ -121,21 +142,23 @@ PipePlan pipe_plan(const b200q4_weight *w, int M)
     return pp;
 }
 
-template <int QT, int MP, bool FUSED, bool M1, bool B8>
+template <int QT, int MP, bool FUSED, bool M1, bool B8, int NCW>
 int launch_pipe(const PipeParams &p, int grid, size_t smem, cudaStream_t st)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        CK(cudaFuncSetAttribute(q4_gemv_pipe_kernel<QT, MP, FUSED, M1, B8>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_optin));
+        CK(cudaFuncSetAttribute(q4_gemv_pipe_kernel<QT, MP, FUSED, M1, B8, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_optin));
+        if (NCW == 8)
+            CK(cudaFuncSetAttribute(q4_gemv_pipe_kernel<QT, MP, FUSED, M1, B8, NCW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PIPE_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3((NCW + 2) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = g.use_pdl ? 1 : 0;
-    CK(cudaLaunchKernelEx(&cfg, q4_gemv_pipe_kernel<QT, MP, FUSED, M1, B8>, p));
+    CK(cudaLaunchKernelEx(&cfg, q4_gemv_pipe_kernel<QT, MP, FUSED, M1, B8, NCW>, p));
     g.launches++;
     return B200Q4_OK;
 }
@@ -150,18 +173,24 @@ int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, con
     p.U = w->n_tiles * w->C; p.N = w->N; p.M = mc; p.C = w->C; p.n_tiles = w->n_tiles; p.nb = w->nb;
     p.ntasks = pl.ntasks; p.PP = pl.PP; p.TS = pl.TS; p.stages = pl.stages;
     p.dbg = g.d_dbg;
-    const int grid = pl.ntasks < g.sms ? pl.ntasks : g.sms;
-    const bool m1 = mc == 1 && fused;
+    const int slots = g.sms * (pl.ncw == 8 ? 2 : 1);
+    const int grid = pl.ntasks < slots ? pl.ntasks : slots;
+    const bool m1 = pl.m1 && fused && mc == 1;
 #define PIPE_DISPATCH(QT)                                                                                          \
-    if (pl.MP == 8) return launch_pipe<QT, 8, false, false, false>(p, grid, pl.smem, st);                          \
-    if (fused) {                                                                                                   \
-        if (pl.b8) return m1 ? launch_pipe<QT, 2, true, true, true>(p, grid, pl.smem, st)                          \
-                             : launch_pipe<QT, 2, true, false, true>(p, grid, pl.smem, st);                        \
-        return m1 ? launch_pipe<QT, 2, true, true, false>(p, grid, pl.smem, st)                                    \
-                  : launch_pipe<QT, 2, true, false, false>(p, grid, pl.smem, st);                                  \
+    if (pl.ncw == 8) {                                 /* MP == 2, B8 */                                           \
+        if (fused) return m1 ? launch_pipe<QT, 2, true, true, true, 8>(p, grid, pl.smem, st)                       \
+                             : launch_pipe<QT, 2, true, false, true, 8>(p, grid, pl.smem, st);                     \
+        return launch_pipe<QT, 2, false, false, true, 8>(p, grid, pl.smem, st);                                    \
     }                                                                                                              \
-    return pl.b8 ? launch_pipe<QT, 2, false, false, true>(p, grid, pl.smem, st)                                    \
-                 : launch_pipe<QT, 2, false, false, false>(p, grid, pl.smem, st);
+    if (pl.MP == 8) return launch_pipe<QT, 8, false, false, false, 16>(p, grid, pl.smem, st);                      \
+    if (fused) {                                                                                                   \
+        if (pl.b8) return m1 ? launch_pipe<QT, 2, true, true, true, 16>(p, grid, pl.smem, st)                      \
+                             : launch_pipe<QT, 2, true, false, true, 16>(p, grid, pl.smem, st);                    \
+        return m1 ? launch_pipe<QT, 2, true, true, false, 16>(p, grid, pl.smem, st)                                \
+                  : launch_pipe<QT, 2, true, false, false, 16>(p, grid, pl.smem, st);                              \
+    }                                                                                                              \
+    return pl.b8 ? launch_pipe<QT, 2, false, false, true, 16>(p, grid, pl.smem, st)                                \
+                 : launch_pipe<QT, 2, false, false, false, 16>(p, grid, pl.smem, st);
     if (w->type == 0) { PIPE_DISPATCH(0) }
     PIPE_DISPATCH(1)
 #undef PIPE_DISPATCH
@@ -184,7 +213,9 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
     if (M == 0 || w->N == 0) return B200Q4_OK;
     if ((long)w->n_tiles * w->C > 0x7fffffffL) return fail(B200Q4_EINVAL, "tensor too large");
     const int nbp = w->C * CHUNK_BLKS;
-    const PipePlan pp = pipe_plan(w, M);
+    // the fused prologue reads X with 128-bit loads
+    const bool can_fuse = !d_wdata && d_x && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0) && (x_stride % 16 == 0);
+    const PipePlan pp = pipe_plan(w, M, can_fuse);
     const int MP = pp.MP;
     if (MP < 1) return fail(B200Q4_EINVAL, "mul_mat: K=%d too large for the shared-memory activation pack", w->K);
     int rc;
@@ -195,8 +226,7 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
         const int mc = (M - m0 < MP) ? M - m0 : MP;
         const float *xs = d_x ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(d_x) + (size_t)m0 * x_stride) : nullptr;
         float *yo = reinterpret_cast<float *>(reinterpret_cast<char *>(d_y) + (size_t)m0 * y_stride);
-        // the fused prologue reads X with 128-bit loads
-        const bool fused = (MP == 2) && !d_wdata && (reinterpret_cast<uintptr_t>(xs) % 16 == 0) && (x_stride % 16 == 0);
+        const bool fused = (MP == 2) && can_fuse;
         if (!fused) {
             const long warps = (long)nbp * MP;
             const int blocks = (int)((warps * 32 + 255) / 256);
@@ -296,6 +326,8 @@ int b200q4_init(int device)
     CK(cudaEventCreate(&g.ev1));
     g.sms = prop.multiProcessorCount;
     g.smem_optin = (int)prop.sharedMemPerBlockOptin;
+    g.smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+    if (const char *e = getenv("B200Q4_TWO_CTAS")) g.two_ctas = atoi(e) != 0;
     CK(cudaMalloc(&g.d_ticket, 2 * sizeof(int)));
     CK(cudaMemset(g.d_ticket, 0, 2 * sizeof(int)));
     if (const char *e = getenv("B200Q4_PDL")) g.use_pdl = atoi(e) != 0;

@@ -183,17 +183,11 @@ __device__ __forceinline__ void emit_apack(const BlockQ &q, int lane, uint8_t *a
 // codes are exactly words 2tq / 2tq+1 of the apack record, written with one 8-byte store.
 // All 32 lanes must call it (shuffles); `valid` masks the stores.
 template <int QT>
-__device__ __forceinline__ void quantize8_emit(const float *x8, bool valid, int lane, uint8_t *aq_rec, float *ap_rec, int plane)
+__device__ __forceinline__ void quantize8_emit(float4 lo, float4 hi, bool valid, int lane, uint8_t *aq_rec, float *ap_rec, int plane)
 {
     const int tq = lane & 3, qbase = lane & 28;
     float v[8];
-    if (valid) {
-        const float4 lo = *reinterpret_cast<const float4 *>(x8), hi = *reinterpret_cast<const float4 *>(x8 + 4);
-        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = 0.0f;
-    }
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
     int a[8];
     float d, mn = 0.0f;
     if (QT == 0) {
@@ -498,32 +492,40 @@ __device__ __forceinline__ void compute_unit_m8(const Frag<QT> &f, int c, const 
 //                   tiles when a tile is shorter than 16 units) handed out by an atomic ticket
 //                   counter -- dynamic scheduling: a slow SM simply takes fewer tasks -- and
 //                   streams them into a ring of shared-memory stages, one cp.async.bulk (TMA 1-D
-//                   bulk copy, 16 units = 20/24 KB) per stage, completion on an mbarrier.
-//   16 consumer     warp w takes unit w of the stage: 4 LDS for the A-fragment words and scales,
-//   warps           3 ALU/word nibble split, IMMA against the B fragments of the activation pack,
-//                   scale FMAs, then ONE 16-byte store per lane of its per-unit partial sums.
+//                   bulk copy, 32 units = 40/48 KB) per stage, completion on an mbarrier.
+//   16 consumer     warp w takes units 2w, 2w+1 of the stage: LDS for the A-fragment words and
+//   warps           scales, one LOP3 per nibble plane, IMMA against the B fragments of the activation
+//                   pack, scale FMAs, a quad reduction and one store of its partial sums.
 //                   Stateless between stages.
+//                   M = 1 ("octet"): the two units are 8 consecutive quant blocks; block j feeds
+//                   MMA column j, so all eight IMMAs accumulate into one D fragment and lane (g,t)
+//                   ends up with the integer sums of blocks 2t, 2t+1 for rows g, g+8.
+//                   M = 2 ("chain4"): per unit, (block i, row m) -> column 2i+m.
+//                   M <= 8 ("m8"):    per block one IMMA, columns = activation rows.
 //   reducer warp    adds the per-unit partials of a stage in unit order (fixed -> bit-reproducible),
 //                   carries the tile accumulator across stages, and at the end of a tile (or tile
 //                   piece) stores Y, or -- when a tile is split over several tasks (K > 8192) --
 //                   parks the piece in a workspace slot; the last piece to arrive (atomic counter)
 //                   adds the slots in piece order and stores Y.
 //
-// Bytes in flight per SM = (stages-1) x 20 KB, independent of registers; weights never touch the
+// Bytes in flight per SM = (stages-1) x 40 KB, independent of registers; weights never touch the
 // register file before they are needed.  Programmatic dependent launch: the weight stream of launch
 // i+1 starts while launch i drains; everything that depends on the previous kernel (X, Y, workspace,
 // ticket counter) is touched only after cudaGridDependencySynchronize().
 // ---------------------------------------------------------------------------
-constexpr int PIPE_CONSUMERS = 16;                      // consumer warps = units per stage
-constexpr int PIPE_THREADS = (PIPE_CONSUMERS + 2) * 32; // + producer warp + reducer warp
-constexpr int PIPE_MAX_STAGES = 8;
+// NCW consumer warps per CTA (template parameter): 16 with one CTA per SM, or 8 with two CTAs per SM
+// (half-size stages and ring).  Two co-resident CTAs let the next launch's CTA start streaming on
+// an SM while the other CTA of the previous launch is still in its tail, so HBM never idles
+// between back-to-back mul_mats.
+constexpr int PIPE_TILE_SPLIT = 16;                     // tiles of >= this many units are scheduled as tile pieces
+constexpr int PIPE_MAX_STAGES = 6;
 constexpr int PIPE_STATIC_TASKS = 3;                    // per CTA, before the first ticket is drawn
 
 struct PipeParams {
     const uint8_t *wt;
-    const float   *x;        // fused quantization (MP == 2)
-    const uint8_t *aq;       // global apack (non-fused)
-    const float   *ap;
+    const float   *x;        // fused quantization (M <= 2)
+    const uint8_t *aq;       // global apack (non-fused): compact [nbp][MP][32]
+    const float   *ap;       //   planes [NP][nbp][MP]
     float         *y;
     float         *partial;  // [ntasks][128] floats, used when a tile spans several tasks
     int           *tile_counters;
@@ -534,7 +536,7 @@ struct PipeParams {
     int            PP;       // pieces (tasks) per tile when C >= 16, else 1
     int            TS;       // units per task
     int            stages;
-    unsigned long long *dbg;   // optional timeline [grid][16] of %globaltimer stamps (B200Q4_DBG=1), else NULL
+    unsigned long long *dbg; // optional timeline (B200Q4_TIMELINE builds), else NULL
 };
 
 __device__ __forceinline__ unsigned long long gtimer()
@@ -546,10 +548,8 @@ __device__ __forceinline__ unsigned long long gtimer()
 // Timeline stamps are compiled in only with -DB200Q4_TIMELINE (tools/timeline.py builds that way).
 #ifdef B200Q4_TIMELINE
 #define PIPE_STAMP(slot) do { if (p.dbg) p.dbg[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
-#define PIPE_DBG(stmt) do { stmt; } while (0)
 #else
 #define PIPE_STAMP(slot) do { } while (0)
-#define PIPE_DBG(stmt) do { } while (0)
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -599,7 +599,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // cycles of pure latency there).
 __device__ __forceinline__ void task_range(const PipeParams &p, int t, int &u0, int &n, int &T, int &c0)
 {
-    if (p.C >= PIPE_CONSUMERS) {                         // PP pieces per tile, TS units each (last shorter)
+    if (p.C >= PIPE_TILE_SPLIT) {                        // PP pieces per tile, TS units each (last shorter)
         int piece = 0;
         T = t;
         if (p.PP > 1) { T = t / p.PP; piece = t - T * p.PP; }
@@ -627,16 +627,12 @@ __device__ __forceinline__ void load_frag_smem(Frag<QT> &f, const uint8_t *chunk
     }
 }
 
-// MP == 2 ("chain4") on the compact pack [blk][2][32]: the 8 columns of the m16n8k32 tile are used as
-// (block 4c+i, row m) -> column 2i+m.  The B fragment of (block 4c + g/2, row g&1) is lane-linear
-// (c*256 + lane*8) and is fed to block i's IMMA only by the lanes that own block i (zeros
-// elsewhere), so the four IMMAs of a unit accumulate into ONE D fragment and lane (g,t) ends up
-// with the integer sums of block 4c+t for rows g/g+8 -- exactly the block whose scale d0[g][t] it
-// loaded: one I2F + FMUL round per unit, no shuffles.  M1: only row 0 exists.
-// B8: the codes sit in shared memory in the 8-column form [blk][8][32 B] (block 4c+i populated only
-// in columns 2i, 2i+1), so each IMMA's B fragment is one 8-byte load with an immediate offset;
-// otherwise the compact form [blk][2][32 B] is read once per unit and masked per block (large K).
-template <int QT, bool M1, bool B8>
+// ---- M == 2 ("chain4"): the 8 columns of the m16n8k32 tile are (block 4c+i, row m) -> column 2i+m.
+// The four IMMAs of a unit accumulate into ONE D fragment and lane (g,t) ends up with the integer
+// sums of block 4c+t for rows g/g+8 -- exactly the block whose scale d0[g][t] it loaded.
+// B8: codes in the 8-column form [blk][8][32 B] (block 4c+i only in columns 2i, 2i+1): one 8-byte
+// load per IMMA.  Otherwise the compact form [blk][2][32 B], read once and masked per block.
+template <int QT, bool B8>
 __device__ __forceinline__ void compute_unit_chain4c(const Frag<QT> &f, int c, const uint8_t *s_aq, const float *s_ap,
                                                      int plane, int lane, float (&acc)[4])
 {
@@ -669,34 +665,115 @@ __device__ __forceinline__ void compute_unit_chain4c(const Frag<QT> &f, int c, c
     }
     if constexpr (QT == 0) {
         acc[0] = (f.sa * d1.x) * (float)d[0];
+        acc[1] = (f.sa * d1.y) * (float)d[1];
         acc[2] = (f.sb * d1.x) * (float)d[2];
-        if constexpr (M1) { acc[1] = 0.f; acc[3] = 0.f; }
-        else {
-            acc[1] = (f.sa * d1.y) * (float)d[1];
-            acc[3] = (f.sb * d1.y) * (float)d[3];
-        }
+        acc[3] = (f.sb * d1.y) * (float)d[3];
     } else {
         const float2 m1 = *reinterpret_cast<const float2 *>(s_ap + plane + (c * 4 + t) * 2);
         const float2 z  = *reinterpret_cast<const float2 *>(s_ap + 2 * plane + (c * 4 + t) * 2);
         const float sa0 = (float)s[0], sb0 = (float)s[2];
         acc[0] = fmaf(f.sa, fmaf(d1.x, (float)d[0], m1.x * sa0), f.ma * z.x);
+        acc[1] = fmaf(f.sa, fmaf(d1.y, (float)d[1], m1.y * sa0), f.ma * z.y);
         acc[2] = fmaf(f.sb, fmaf(d1.x, (float)d[2], m1.x * sb0), f.mb * z.x);
-        if constexpr (M1) { acc[1] = 0.f; acc[3] = 0.f; }
-        else {
-            acc[1] = fmaf(f.sa, fmaf(d1.y, (float)d[1], m1.y * sa0), f.ma * z.y);
-            acc[3] = fmaf(f.sb, fmaf(d1.y, (float)d[3], m1.y * sb0), f.mb * z.y);
-        }
+        acc[3] = fmaf(f.sb, fmaf(d1.y, (float)d[3], m1.y * sb0), f.mb * z.y);
     }
 }
 
-// Reducer: a run of units of tile T inside task `task` is complete.
-//   MP == 2: lane (g, r) carries ONE value: row g + 8*(r>>1), activation row m = r&1 (the consumers
-//            already reduced over the quad);   MP == 8: lane (g,t) carries rows g/g+8 x m = 2t, 2t+1.
-template <int QT, int MP>
+// ---- M == 1 ("octet"): blocks 8o .. 8o+7 of a tile = the units with chunk index 2o (chE) and 2o+1
+// (chO); either may be absent (NULL).  Block j feeds MMA column j, so lane (g,t)'s D registers are
+// the integer sums of blocks 2t, 2t+1 for rows g (d[0], d[1]) and g+8 (d[2], d[3]); that lane
+// reads those two blocks' scales from the unit that holds them (t < 2: chE, else chO).
+// Codes: B8 form [blk][8][32 B] with block b's row in column b&7, or compact [blk][32 B];
+// planes [blk] (one activation row).  Returns the lane's scaled sums for rows g and g+8.
+template <int QT, bool B8>
+__device__ __forceinline__ void compute_octet(const uint8_t *chE, const uint8_t *chO, int o, const uint8_t *s_aq,
+                                              const float *s_ap, int plane, int lane, float &v0, float &v2)
+{
+    const int g = lane >> 2, t = lane & 3;
+    const uint8_t *mine = (t >> 1) ? chO : chE;
+    float2 sA = make_float2(0.f, 0.f), sB = sA, mA = sA, mB = sA;
+    if (mine) {
+        const uint8_t *sp = mine + 1024 + (g * 4 + 2 * (t & 1)) * 4;
+        sA = *reinterpret_cast<const float2 *>(sp);
+        sB = *reinterpret_cast<const float2 *>(sp + 128);
+        if constexpr (QT == 1) {
+            mA = *reinterpret_cast<const float2 *>(sp + 256);
+            mB = *reinterpret_cast<const float2 *>(sp + 384);
+        }
+    }
+    const float2 d1 = *reinterpret_cast<const float2 *>(s_ap + o * 8 + 2 * t);
+    uint2 breg = make_uint2(0u, 0u);
+    if constexpr (!B8) breg = *reinterpret_cast<const uint2 *>(s_aq + o * 256 + lane * 8);
+    int dE[4] = {0, 0, 0, 0}, dO[4] = {0, 0, 0, 0};
+    int sE[4] = {0, 0, 0, 0}, sO[4] = {0, 0, 0, 0};
+    if constexpr (QT == 0) {
+        const int2 cr = *reinterpret_cast<const int2 *>(s_ap + plane + o * 8 + 2 * t);
+        dE[0] = cr.x; dE[1] = cr.y; dE[2] = cr.x; dE[3] = cr.y;       // own columns only matter; one copy suffices
+    }
+    if (chE) {
+        const uint4 qa = *reinterpret_cast<const uint4 *>(chE + lane * 16), qb = *reinterpret_cast<const uint4 *>(chE + 512 + lane * 16);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t a[4];
+            make_a(a, u4_get(qa, i), u4_get(qb, i));
+            if constexpr (B8) {
+                const uint2 b = *reinterpret_cast<const uint2 *>(s_aq + (o * 8 + i) * 256 + lane * 8);
+                imma<QT>(dE, a, b.x, b.y, dE);
+            } else {
+                const bool col = g == i;
+                imma<QT>(dE, a, col ? breg.x : 0u, col ? breg.y : 0u, dE);
+            }
+            if constexpr (QT == 1) {
+                const bool col = g == i;
+                imma<QT>(sE, a, col ? 0x10101010u : 0u, col ? 0x01010101u : 0u, sE);
+            }
+        }
+    }
+    if (chO) {
+        const uint4 qa = *reinterpret_cast<const uint4 *>(chO + lane * 16), qb = *reinterpret_cast<const uint4 *>(chO + 512 + lane * 16);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t a[4];
+            make_a(a, u4_get(qa, i), u4_get(qb, i));
+            if constexpr (B8) {
+                const uint2 b = *reinterpret_cast<const uint2 *>(s_aq + (o * 8 + 4 + i) * 256 + lane * 8);
+                imma<QT>(dO, a, b.x, b.y, dO);
+            } else {
+                const bool col = g == 4 + i;
+                imma<QT>(dO, a, col ? breg.x : 0u, col ? breg.y : 0u, dO);
+            }
+            if constexpr (QT == 1) {
+                const bool col = g == 4 + i;
+                imma<QT>(sO, a, col ? 0x10101010u : 0u, col ? 0x01010101u : 0u, sO);
+            }
+        }
+    }
+    // the two halves populate disjoint columns: D = dE + dO.  A lane whose half is absent has
+    // zero scales (sA = sB = 0), so whatever its columns hold contributes nothing.
+    const float p0 = (float)(dE[0] + dO[0]), p1 = (float)(dE[1] + dO[1]), p2 = (float)(dE[2] + dO[2]), p3 = (float)(dE[3] + dO[3]);
+    if constexpr (QT == 0) {
+        v0 = fmaf(sA.x * d1.x, p0, (sA.y * d1.y) * p1);
+        v2 = fmaf(sB.x * d1.x, p2, (sB.y * d1.y) * p3);
+    } else {
+        const float2 m1 = *reinterpret_cast<const float2 *>(s_ap + plane + o * 8 + 2 * t);
+        const float2 z  = *reinterpret_cast<const float2 *>(s_ap + 2 * plane + o * 8 + 2 * t);
+        const float s0 = (float)(sE[0] + sO[0]), s1 = (float)(sE[1] + sO[1]), s2 = (float)(sE[2] + sO[2]), s3 = (float)(sE[3] + sO[3]);
+        // d0*(d1*P + m1*S0) + m0*Z per block, two blocks per lane and row; an absent half has Z
+        // multiplied by m0 = 0 and everything else by d0 = 0
+        v0 = fmaf(sA.x, fmaf(d1.x, p0, m1.x * s0), mA.x * z.x) + fmaf(sA.y, fmaf(d1.y, p1, m1.y * s1), mA.y * z.y);
+        v2 = fmaf(sB.x, fmaf(d1.x, p2, m1.x * s2), mB.x * z.x) + fmaf(sB.y, fmaf(d1.y, p3, m1.y * s3), mB.y * z.y);
+    }
+}
+
+// Reducer: a run of units of tile T inside task `task` is complete.  Lane roles:
+//   M1:      lane l < 16 carries row l (activation row 0);
+//   MP == 2: lane (g, r) carries row g + 8*(r>>1), activation row m = r&1;
+//   MP == 8: lane (g, t) carries rows g/g+8 x m = 2t, 2t+1 in acc[0..3].
+template <int QT, int MP, bool M1>
 __device__ __forceinline__ void pipe_emit(const PipeParams &p, int T, int task, int lane, float (&acc)[4])
 {
     constexpr int NV = (MP == 2) ? 1 : 4;
-    if (p.C >= PIPE_CONSUMERS && p.PP > 1) {            // the tile is split over PP tasks
+    if (p.C >= PIPE_TILE_SPLIT && p.PP > 1) {           // the tile is split over PP tasks
         float *ws = p.partial + (size_t)task * 128;
 #pragma unroll
         for (int r = 0; r < NV; r++) ws[r * 32 + lane] = acc[r];
@@ -718,7 +795,10 @@ __device__ __forceinline__ void pipe_emit(const PipeParams &p, int T, int task, 
     }
     const float post = (QT == 0) ? 0.0625f : 1.0f;       // undo the 16x of the A/B code scaling (exact)
     const int g = lane >> 2, t = lane & 3;
-    if (MP == 2) {
+    if (M1) {
+        const int n = T * TILE_ROWS + lane;
+        if (lane < TILE_ROWS && n < p.N) p.y[n] = acc[0] * post;
+    } else if (MP == 2) {
         const int m = t & 1, n = T * TILE_ROWS + g + 8 * (t >> 1);
         if (m < p.M && n < p.N) p.y[(size_t)m * p.y_stride + n] = acc[0] * post;
     } else {
@@ -735,20 +815,27 @@ __device__ __forceinline__ void pipe_emit(const PipeParams &p, int T, int task, 
     }
 }
 
-template <int QT, int MP, bool FUSED, bool M1, bool B8>
-__global__ void __launch_bounds__(PIPE_THREADS, 1) q4_gemv_pipe_kernel(const PipeParams p)
+// M1: exactly one activation row, fused quantization (rows stored: 1).  MP: padded row count of the
+// other modes (2 or 8).  B8: 256-byte-per-block code layout (no per-IMMA masking).
+template <int QT, int MP, bool FUSED, bool M1, bool B8, int NCW>
+__global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe_kernel(const PipeParams p)
 {
+    constexpr int PIPE_CONSUMERS = NCW;                  // consumer warps
+    constexpr int PIPE_UNITS = 2 * NCW;                  // units per stage
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int CH = chunk_bytes(QT);
     constexpr int NP = (QT == 0) ? 2 : 3;
-    constexpr int STAGE_BYTES = PIPE_CONSUMERS * CH;
-    const int nbp = p.C * CHUNK_BLKS;
-    const int plane = nbp * MP;
-    // shared-memory map: [stages x STAGE_BYTES][red: stages x 16 x 512 B][apack codes][planes][barriers][desc]
+    constexpr int STAGE_BYTES = PIPE_UNITS * CH;
+    constexpr int ROWS = M1 ? 1 : MP;                          // activation rows stored per block
+    constexpr int RW = (MP == 2) ? 32 : 128;                   // floats per unit in the reduction ring
+    constexpr int AQ_BLK = (MP == 2 && B8) ? 256 : ROWS * 32;  // code bytes per block in shared memory
+    // blocks held in the shared-memory pack: whole chunks; M1 reads whole octets (8 blocks), so pad to 8
+    const int nbp = M1 ? ((p.C * CHUNK_BLKS + 7) & ~7) : p.C * CHUNK_BLKS;
+    const int plane = nbp * ROWS;
+    // shared-memory map: [stages x STAGE_BYTES][red ring][apack codes][planes][barriers][desc]
     uint8_t *s_stage = smem;
     float   *s_red = reinterpret_cast<float *>(smem + (size_t)p.stages * STAGE_BYTES);
-    uint8_t *s_aq = reinterpret_cast<uint8_t *>(s_red) + (size_t)p.stages * PIPE_CONSUMERS * (MP == 2 ? 128 : 512);
-    constexpr int AQ_BLK = (MP == 2 && B8) ? 256 : MP * 32;    // code bytes per block in shared memory
+    uint8_t *s_aq = reinterpret_cast<uint8_t *>(s_red + (size_t)p.stages * PIPE_UNITS * RW);
     float   *s_ap = reinterpret_cast<float *>(s_aq + (size_t)nbp * AQ_BLK);
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_ap) + (((size_t)NP * plane * 4 + 15) & ~(size_t)15));
     uint64_t *bar_empty = bar_full + PIPE_MAX_STAGES;
@@ -776,9 +863,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) q4_gemv_pipe_kernel(const Pip
             auto issue_task = [&](int task) {
                 int u0, n, T, c0;
                 task_range(p, task, u0, n, T, c0);
-                for (int r = 0; r < n; r += PIPE_CONSUMERS) {
+                for (int r = 0; r < n; r += PIPE_UNITS) {
                     mbar_wait(&bar_empty[s], ph);
-                    const int cnt = min(PIPE_CONSUMERS, n - r);
+                    const int cnt = min(PIPE_UNITS, n - r);
                     s_desc[s] = make_int4(cnt, c0, T, task);
                     c0 += cnt;
                     while (c0 >= p.C) { c0 -= p.C; ++T; }
@@ -818,7 +905,6 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) q4_gemv_pipe_kernel(const Pip
     if (warp == PIPE_CONSUMERS + 1) {
         // ===================== reducer =====================
         cudaGridDependencySynchronize();
-        constexpr int RW = (MP == 2) ? 32 : 128;         // floats per unit in the reduction ring
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         int curT = -1, curTask = -1;
         int s = 0;
@@ -836,43 +922,39 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) q4_gemv_pipe_kernel(const Pip
             const int task = dsc.w;
             int T = dsc.z;
             int left = p.C - dsc.y;                      // units of tile T from the stage's first unit on
-            const float *red = s_red + (size_t)s * PIPE_CONSUMERS * RW + (MP == 2 ? lane : lane * 4);
+            const float *red = s_red + (size_t)s * PIPE_UNITS * RW + (MP == 2 ? lane : lane * 4);
             int j = 0;
             while (j < dsc.x) {
                 if (T != curT || task != curTask) {
-                    if (curT >= 0) pipe_emit<QT, MP>(p, curT, curTask, lane, acc);
+                    if (curT >= 0) pipe_emit<QT, MP, M1>(p, curT, curTask, lane, acc);
                     acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
                     curT = T; curTask = task;
                 }
                 const int run = min(dsc.x - j, left);    // units of this stage that belong to tile T
-                if (run == PIPE_CONSUMERS) {
-                    // common case, the whole stage is one tile: four independent chains of four
-                    // (fixed association -> bit-reproducible, a quarter of the dependent latency)
-                    if constexpr (MP == 2) {
-                        float v[PIPE_CONSUMERS];
+                if (run == PIPE_UNITS && MP == 2) {
+                    // common case, the whole stage is one tile: eight independent chains of four
+                    // (fixed association -> bit-reproducible, short dependent latency)
+                    float v[PIPE_UNITS];
 #pragma unroll
-                        for (int k = 0; k < PIPE_CONSUMERS; k++) v[k] = red[k * RW];
-                        acc[0] += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])) +
-                                  (((v[8] + v[9]) + (v[10] + v[11])) + ((v[12] + v[13]) + (v[14] + v[15])));
-                    } else {
-                        float4 v[PIPE_CONSUMERS];
+                    for (int k = 0; k < PIPE_UNITS; k++) v[k] = red[k * RW];
+                    float q[PIPE_UNITS / 4];
 #pragma unroll
-                        for (int k = 0; k < PIPE_CONSUMERS; k++) v[k] = *reinterpret_cast<const float4 *>(red + k * RW);
-                        float4 q[4];
-#pragma unroll
-                        for (int h = 0; h < 4; h++) {
-                            q[h].x = (v[4 * h].x + v[4 * h + 1].x) + (v[4 * h + 2].x + v[4 * h + 3].x);
-                            q[h].y = (v[4 * h].y + v[4 * h + 1].y) + (v[4 * h + 2].y + v[4 * h + 3].y);
-                            q[h].z = (v[4 * h].z + v[4 * h + 1].z) + (v[4 * h + 2].z + v[4 * h + 3].z);
-                            q[h].w = (v[4 * h].w + v[4 * h + 1].w) + (v[4 * h + 2].w + v[4 * h + 3].w);
-                        }
-                        acc[0] += (q[0].x + q[1].x) + (q[2].x + q[3].x);
-                        acc[1] += (q[0].y + q[1].y) + (q[2].y + q[3].y);
-                        acc[2] += (q[0].z + q[1].z) + (q[2].z + q[3].z);
-                        acc[3] += (q[0].w + q[1].w) + (q[2].w + q[3].w);
-                    }
+                    for (int h = 0; h < PIPE_UNITS / 4; h++) q[h] = (v[4 * h] + v[4 * h + 1]) + (v[4 * h + 2] + v[4 * h + 3]);
+                    if constexpr (PIPE_UNITS == 32) acc[0] += ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+                    else                           acc[0] += (q[0] + q[1]) + (q[2] + q[3]);
                 } else {
-                    for (int k = j; k < j + run; k++) {
+                    int k = j;
+                    for (; k + 4 <= j + run; k += 4) {   // fixed grouping by four
+                        if constexpr (MP == 2) {
+                            acc[0] += (red[k * RW] + red[(k + 1) * RW]) + (red[(k + 2) * RW] + red[(k + 3) * RW]);
+                        } else {
+                            const float4 a = *reinterpret_cast<const float4 *>(red + k * RW), b = *reinterpret_cast<const float4 *>(red + (k + 1) * RW);
+                            const float4 c = *reinterpret_cast<const float4 *>(red + (k + 2) * RW), d = *reinterpret_cast<const float4 *>(red + (k + 3) * RW);
+                            acc[0] += (a.x + b.x) + (c.x + d.x); acc[1] += (a.y + b.y) + (c.y + d.y);
+                            acc[2] += (a.z + b.z) + (c.z + d.z); acc[3] += (a.w + b.w) + (c.w + d.w);
+                        }
+                    }
+                    for (; k < j + run; k++) {
                         if constexpr (MP == 2) acc[0] += red[k * RW];
                         else {
                             const float4 v = *reinterpret_cast<const float4 *>(red + k * RW);
@@ -888,7 +970,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) q4_gemv_pipe_kernel(const Pip
             if (lane == 0) mbar_arrive(&bar_empty[s]);
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        if (curT >= 0) pipe_emit<QT, MP>(p, curT, curTask, lane, acc);
+        if (curT >= 0) pipe_emit<QT, MP, M1>(p, curT, curTask, lane, acc);
         if (lane == 0) PIPE_STAMP(7);
         return;
     }
@@ -899,31 +981,65 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) q4_gemv_pipe_kernel(const Pip
     const int ctid = threadIdx.x;                        // 0 .. 511
     constexpr int CTHREADS = PIPE_CONSUMERS * 32;
     // where (block, row m)'s 32 code bytes live in shared memory
-    auto rec_of = [&](int blk, int m) { return s_aq + (size_t)blk * AQ_BLK + ((MP == 2 && B8) ? (2 * (blk & 3) + m) * 32 : m * 32); };
+    auto rec_of = [&](int blk, int m) {
+        if constexpr (MP == 2 && B8) return s_aq + (size_t)blk * 256 + (M1 ? (blk & 7) : 2 * (blk & 3) + m) * 32;
+        else return s_aq + ((size_t)blk * ROWS + m) * 32;
+    };
     if constexpr (FUSED) {
+        // Issue the activation loads first (one item = 8 consecutive elements of one block; the
+        // first FUSED_ITEMS items of a thread are held in registers) so that their L2 latency
+        // overlaps the zero-fill below.
+        constexpr int FUSED_ITEMS = 2;
+        const int items = p.M * p.nb * 4;
+        float4 xlo[FUSED_ITEMS], xhi[FUSED_ITEMS];
+#pragma unroll
+        for (int it = 0; it < FUSED_ITEMS; it++) {
+            const int id = it * CTHREADS + ctid;
+            xlo[it] = make_float4(0.f, 0.f, 0.f, 0.f); xhi[it] = xlo[it];
+            if (id < items) {
+                const int bq = id >> 2, m = bq / p.nb, blk = bq - m * p.nb;
+                const float4 *src = reinterpret_cast<const float4 *>(p.x + (size_t)m * p.x_stride + (size_t)blk * QK + (lane & 3) * 8);
+                xlo[it] = src[0]; xhi[it] = src[1];
+            }
+        }
         // Everything quantization does not write must read as zero: the unused columns of the
         // 8-column form, the records of padded blocks (nb .. nbp: weight scale 0, but 0 x garbage
-        // could be NaN) and row 1 of an M = 1 call.  Quantization writes disjoint bytes, so no
-        // barrier is needed in between.
+        // could be NaN) and row 1 of an M = 1 call in the two-row layout.  Quantization writes
+        // disjoint bytes, so no barrier is needed in between.
         for (int i = ctid; i < nbp * AQ_BLK / 8; i += CTHREADS) {
             const int blk = i / (AQ_BLK / 8), w8 = i - blk * (AQ_BLK / 8);      // 8-byte piece w8 of block blk
             const int col = w8 >> 2;                                            // 32-byte record index inside the block
-            const int m = (MP == 2 && B8) ? col - 2 * (blk & 3) : col;
+            int m = col;
+            if constexpr (MP == 2 && B8) m = M1 ? (col == (blk & 7) ? 0 : -1) : col - 2 * (blk & 3);
             const bool live = blk < p.nb && m >= 0 && m < p.M;
             if (!live) reinterpret_cast<uint2 *>(s_aq + (size_t)blk * AQ_BLK)[w8] = make_uint2(0u, 0u);
         }
-        for (int i = ctid; i < NP * nbp * MP; i += CTHREADS) {
-            const int e = i % (nbp * MP), blk = e / MP, m = e - blk * MP;
-            if (blk >= p.nb || m >= p.M) s_ap[i] = 0.0f;
+        for (int pl = 0; pl < NP; pl++) {
+            for (int i = p.nb * ROWS + ctid; i < nbp * ROWS; i += CTHREADS) s_ap[pl * plane + i] = 0.0f;   // padded blocks
+            if (ROWS == 2 && p.M == 1)
+                for (int blk = ctid; blk < p.nb; blk += CTHREADS) s_ap[pl * plane + blk * 2 + 1] = 0.0f;  // absent row
         }
-        const int items = p.M * p.nb * 4;
-        for (int base = 0; base < items; base += CTHREADS) {
+#pragma unroll
+        for (int it = 0; it < FUSED_ITEMS; it++) {
+            const int id = it * CTHREADS + ctid;
+            const bool valid = id < items;
+            if (it * CTHREADS < items) {                 // warp-uniform: shuffles inside
+                const int bq = valid ? (id >> 2) : 0;
+                const int m = bq / p.nb, blk = bq - m * p.nb;
+                quantize8_emit<QT>(xlo[it], xhi[it], valid, lane, rec_of(blk, m), s_ap + (size_t)blk * ROWS + m, plane);
+            }
+        }
+        for (int base = FUSED_ITEMS * CTHREADS; base < items; base += CTHREADS) {      // long rows (K > 8192)
             const int id = base + ctid;
             const bool valid = id < items;
             const int bq = valid ? (id >> 2) : 0;
             const int m = bq / p.nb, blk = bq - m * p.nb;
-            quantize8_emit<QT>(p.x + (size_t)m * p.x_stride + (size_t)blk * QK + (lane & 3) * 8, valid, lane,
-                               rec_of(blk, m), s_ap + (size_t)blk * MP + m, plane);
+            float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+            if (valid) {
+                const float4 *src = reinterpret_cast<const float4 *>(p.x + (size_t)m * p.x_stride + (size_t)blk * QK + (lane & 3) * 8);
+                lo = src[0]; hi = src[1];
+            }
+            quantize8_emit<QT>(lo, hi, valid, lane, rec_of(blk, m), s_ap + (size_t)blk * ROWS + m, plane);
         }
     } else {
         // global apack is always the compact form [nbp][MP][32]
@@ -945,104 +1061,102 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) q4_gemv_pipe_kernel(const Pip
         for (size_t i = ctid; i < (size_t)NP * plane * 4 / 16; i += CTHREADS) dst2[i] = src2[i];
     }
     asm volatile("bar.sync 1, %0;" :: "n"(CTHREADS) : "memory");
-
     if (threadIdx.x == 0) PIPE_STAMP(4);
-    // Two stages per iteration when the second one has already landed: the two units' IMMA chains
-    // are independent, so their latencies overlap (a warp owns only 4 issue slots' worth of
-    // neighbours on its scheduler; one unit at a time leaves the pipes idle between dependent ops).
-    auto next_stage = [&](int &s, uint32_t &ph) { if (++s == p.stages) { s = 0; ph ^= 1; } };
-    // chunk index of this warp's unit in a stage; T receives its tile
-    auto unit_of = [&](const int4 &dsc, int &T) { int c = dsc.y + warp; T = dsc.z; while (c >= p.C) { c -= p.C; ++T; } return c; };
-    auto run_unit = [&](const Frag<QT> &f, int c, float (&acc)[4]) {
-        if constexpr (MP == 2) compute_unit_chain4c<QT, M1, B8>(f, c, s_aq, s_ap, plane, lane, acc);
-        else {
-            acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-            compute_unit_m8<QT>(f, c, s_aq, s_ap, plane, lane, acc);
-        }
-    };
-    auto put = [&](int s, float (&acc)[4]) {
+
+    const int uA = 2 * warp, uB = uA + 1;                // this warp's units in every stage
+    // chunk index (and tile) of unit u of a stage
+    auto chunk_of = [&](const int4 &dsc, int u, int &T) { int c = dsc.y + u; T = dsc.z; while (c >= p.C) { c -= p.C; ++T; } return c; };
+    // partial sums -> reduction ring
+    auto put4 = [&](float *slot, float (&acc)[4]) {
         if constexpr (MP == 2) {
             // quad reduction here (the consumers have the slack, the single reducer warp does not):
-            // afterwards every lane of the quad holds all four sums; lane t keeps value t.
+            // afterwards every lane of the quad holds all four sums; lane t keeps value t
+            // (value index = 2*(row half) + m, the order of acc[]).
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
                 acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
             }
             const int t = lane & 3;
-            // value index r = 2*(row half) + m  <->  acc[] order is {g:m0, g:m1, g+8:m0, g+8:m1}
-            const float v = t == 0 ? acc[0] : t == 1 ? acc[1] : t == 2 ? acc[2] : acc[3];
-            s_red[((size_t)s * PIPE_CONSUMERS + warp) * 32 + lane] = v;
+            slot[lane] = t == 0 ? acc[0] : t == 1 ? acc[1] : t == 2 ? acc[2] : acc[3];
         } else {
-            *reinterpret_cast<float4 *>(s_red + ((size_t)s * PIPE_CONSUMERS + warp) * 128 + lane * 4) =
-                make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4 *>(slot + lane * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         }
     };
-    auto put_zero = [&](int s) {
-        if constexpr (MP == 2) s_red[((size_t)s * PIPE_CONSUMERS + warp) * 32 + lane] = 0.f;
-        else *reinterpret_cast<float4 *>(s_red + ((size_t)s * PIPE_CONSUMERS + warp) * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto put_zero = [&](float *slot) {
+        if constexpr (MP == 2) slot[lane] = 0.f;
+        else *reinterpret_cast<float4 *>(slot + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    // M1: rows g (v0) and g+8 (v2) -> lanes 0..15 of the slot hold rows 0..15
+    auto put_rows = [&](float *slot, float v0, float v2) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, 1); v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, 1); v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
+        const int g = lane >> 2, t = lane & 3;
+        if (t < 2) slot[g + 8 * t] = t ? v2 : v0;
+    };
+
     int s = 0;
     uint32_t ph = 0;
     bool first = true;
-    int cr = 0;
     for (;;) {
         mbar_wait(&bar_full[s], ph);
         if (first && threadIdx.x == 0) { PIPE_STAMP(5); } first = false;
-        const int4 d0 = s_desc[s];
-        if (d0.x < 0) break;
-        PIPE_DBG(if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && cr < 24) p.dbg[3000 + cr * 4 + 0] = gtimer(););
-        int s1 = s; uint32_t ph1 = ph;
-        next_stage(s1, ph1);
-        bool two = mbar_test(&bar_full[s1], ph1);
-        int4 d1 = make_int4(-1, 0, 0, 0);
-        if (two) { d1 = s_desc[s1]; two = d1.x >= 0; }
-        if (two) {
-            const bool h0 = warp < d0.x, h1 = warp < d1.x;
-            Frag<QT> f0, f1;
-            float a0[4], a1[4];
-            if (h0) load_frag_smem<QT>(f0, s_stage + (size_t)s * STAGE_BYTES + (size_t)warp * CH, lane);
-            if (h1) load_frag_smem<QT>(f1, s_stage + (size_t)s1 * STAGE_BYTES + (size_t)warp * CH, lane);
-            if (h0 && h1) {                      // the common, fully interleavable case
-                int T0, T1;
-                const int c0 = unit_of(d0, T0), c1 = unit_of(d1, T1);
-                run_unit(f0, c0, a0);
-                run_unit(f1, c1, a1);
-                if (T0 == T1 && d0.w == d1.w) {  // same tile, same task: one partial for both units
-                    a0[0] += a1[0]; a0[1] += a1[1]; a0[2] += a1[2]; a0[3] += a1[3];
-                    a1[0] = a1[1] = a1[2] = a1[3] = 0.f;
-                    put(s, a0);
-                    put_zero(s1);
-                } else {
-                    put(s, a0);
-                    put(s1, a1);
+        const int4 dsc = s_desc[s];
+        if (dsc.x < 0) break;
+        const bool hA = uA < dsc.x, hB = uB < dsc.x;
+        int TA = 0, TB = 0;
+        const int cA = chunk_of(dsc, uA, TA), cB = chunk_of(dsc, uB, TB);
+        const uint8_t *chA = s_stage + (size_t)s * STAGE_BYTES + (size_t)uA * CH, *chB = chA + CH;
+        float *slotA = s_red + ((size_t)s * PIPE_UNITS + uA) * RW, *slotB = slotA + RW;
+        if constexpr (M1) {
+            if (hA && hB && TA == TB && !(cA & 1)) {     // an aligned octet: the common case
+                float v0, v2;
+                compute_octet<QT, B8>(chA, chB, cA >> 1, s_aq, s_ap, plane, lane, v0, v2);
+                put_rows(slotA, v0, v2);
+                if (lane < TILE_ROWS) slotB[lane] = 0.f;
+            } else {                                     // half octets (odd start, tile boundary, ragged tail)
+                if (hA) {
+                    float v0, v2;
+                    compute_octet<QT, B8>((cA & 1) ? nullptr : chA, (cA & 1) ? chA : nullptr, cA >> 1, s_aq, s_ap, plane, lane, v0, v2);
+                    put_rows(slotA, v0, v2);
                 }
-            } else {
-                int T;
-                if (h0) { run_unit(f0, unit_of(d0, T), a0); put(s, a0); }
-                if (h1) { run_unit(f1, unit_of(d1, T), a1); put(s1, a1); }
+                if (hB) {
+                    float v0, v2;
+                    compute_octet<QT, B8>((cB & 1) ? nullptr : chB, (cB & 1) ? chB : nullptr, cB >> 1, s_aq, s_ap, plane, lane, v0, v2);
+                    put_rows(slotB, v0, v2);
+                }
             }
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(&bar_done[s]); mbar_arrive(&bar_done[s1]); }
-            PIPE_DBG(if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && cr < 24) { p.dbg[3000 + cr * 4 + 1] = gtimer(); p.dbg[3000 + cr * 4 + 2] = 2; });
-            ++cr;
-            s = s1; ph = ph1;
-            next_stage(s, ph);
         } else {
-            if (warp < d0.x) {
-                Frag<QT> f0;
-                float a0[4];
-                int T;
-                load_frag_smem<QT>(f0, s_stage + (size_t)s * STAGE_BYTES + (size_t)warp * CH, lane);
-                run_unit(f0, unit_of(d0, T), a0);
-                put(s, a0);
+            Frag<QT> fA, fB;
+            float aA[4], aB[4];
+            if (hA) load_frag_smem<QT>(fA, chA, lane);
+            if (hB) load_frag_smem<QT>(fB, chB, lane);
+            auto run_unit = [&](const Frag<QT> &f, int c, float (&acc)[4]) {
+                if constexpr (MP == 2) compute_unit_chain4c<QT, B8>(f, c, s_aq, s_ap, plane, lane, acc);
+                else {
+                    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+                    compute_unit_m8<QT>(f, c, s_aq, s_ap, plane, lane, acc);
+                }
+            };
+            if (hA && hB) {
+                run_unit(fA, cA, aA);
+                run_unit(fB, cB, aB);
+                if (TA == TB) {                          // same tile: one partial for both units
+                    aA[0] += aB[0]; aA[1] += aB[1]; aA[2] += aB[2]; aA[3] += aB[3];
+                    put4(slotA, aA);
+                    put_zero(slotB);
+                } else {
+                    put4(slotA, aA);
+                    put4(slotB, aB);
+                }
+            } else if (hA) {
+                run_unit(fA, cA, aA);
+                put4(slotA, aA);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_done[s]);
-            PIPE_DBG(if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && cr < 24) { p.dbg[3000 + cr * 4 + 1] = gtimer(); p.dbg[3000 + cr * 4 + 2] = 1; });
-            ++cr;
-            next_stage(s, ph);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_done[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
     }
     if (threadIdx.x == 0) PIPE_STAMP(6);
 }
