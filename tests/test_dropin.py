@@ -1,0 +1,89 @@
+"""The drop-in proof: the reference's own sources (ggml.c graph executor, vsim.cpp NeoX graph,
+monitor.c) linked against libb200q4.so instead of imax.c, compared with the unmodified reference
+build.  Built by `make -C oracle b200` into oracle/_ref/ (needs /root/reference at build time; the
+binaries travel to the GPU box)."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import Q4_0, Q4_1, REF_DIR
+
+REF_BIN = REF_DIR / "vsim-ubuntu"
+B200_BIN = REF_DIR / "vsim-b200"
+B200_LIB = REF_DIR / "libggml_b200.so"
+
+
+def test_dropin_binaries_link_only_the_hook_symbols():
+    """CPU: the patched reference build resolves exactly the hook symbols from libb200q4.so."""
+    if not B200_LIB.exists():
+        pytest.skip("oracle/_ref/libggml_b200.so not built")
+    out = subprocess.run(["nm", "-D", "--undefined-only", str(B200_LIB)], capture_output=True, text=True).stdout
+    ours = sorted(set(re.findall(r"\b(init_xmax|imax_ggml_compute_forward_mul_mat_q4_[01]_f32|b200q4_\w+)\b", out)))
+    assert ours == ["imax_ggml_compute_forward_mul_mat_q4_0_f32", "imax_ggml_compute_forward_mul_mat_q4_1_f32"], ours
+
+
+def _run(binary, model, prompt="1 2 3 4 5", n_predict=8, logits=False, threads=4):
+    cmd = [str(binary), "gptneox", "-m", str(model), "--prompt", prompt, "--seed", "42", "--threads", str(threads),
+           "--n_predict", str(n_predict), "--top_k", "1", "--top_p", "1.0", "--temp", "1.0", "--repeat_penalty", "1.0"]
+    if logits:
+        cmd.append("--return_logits")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:] + r.stdout[-2000:]
+    return r.stdout
+
+
+def _tokens(stdout):
+    body = stdout.split("<|BEGIN>")[1].split("<END|>")[0]
+    return [int(t) for t in body.split()]
+
+
+def _logits(stdout):
+    rows = [np.array(l.split()[1:-1] if l.rstrip().endswith("<END|>") else l.split()[1:], dtype=np.float64)
+            for l in stdout.splitlines() if l.startswith("logits:")]
+    return np.stack(rows)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("qt,tag", [(Q4_0, "q4_0"), (Q4_1, "q4_1")])
+def test_reference_graph_executor_on_b200_backend(qt, tag):
+    """ggml_mul_mat + ggml_graph_compute of the reference, hook served by the GPU, vs the CPU reference."""
+    if not B200_LIB.exists():
+        pytest.skip("oracle/_ref/libggml_b200.so not built")
+    from oracle import Reference
+    ref = Reference()
+    L = C.CDLL(str(B200_LIB))
+    L.ref_mul_mat.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.ref_mul_mat.restype = C.c_double
+    rng = np.random.default_rng(21)
+    for n, k, m, nth in ((320, 1024, 1, 1), (777, 512, 5, 4), (64, 64, 9, 8)):
+        wq = ref.quantize_rows(qt, rng.uniform(-0.05, 0.05, (n, k)).astype(np.float32))
+        x = rng.standard_normal((m, k)).astype(np.float32)
+        y = np.empty((m, n), np.float32)
+        assert L.ref_mul_mat(qt, wq.ctypes.data, n, k, x.ctypes.data, m, y.ctypes.data, nth, 1) >= 0
+        yr = ref.mul_mat(qt, wq, n, k, x, nth=nth)
+        assert np.all(np.abs(y - yr) <= 1e-3 * np.abs(yr) + 1e-5 * np.abs(yr).max()), (n, k, m)
+        assert np.linalg.norm(y - yr) / np.linalg.norm(yr) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("qt,tag", [(Q4_0, "q4_0"), (Q4_1, "q4_1")])
+def test_vsim_neox_end_to_end_tokens_and_logits(tmp_path, qt, tag):
+    """Tiny random GPT-NeoX through the reference's main program: greedy token stream and prompt
+    logits of the GPU-backed binary vs the unmodified CPU binary."""
+    if not (REF_BIN.exists() and B200_BIN.exists()):
+        pytest.skip("oracle/_ref vsim binaries not built")
+    from tests.helpers.neox_file import write_neox
+    model = tmp_path / f"tiny-{tag}.bin"
+    write_neox(model, qt)
+    lr = _logits(_run(REF_BIN, model, logits=True))
+    lg = _logits(_run(B200_BIN, model, logits=True))
+    assert lr.shape == lg.shape and lr.shape[1] == 256
+    # north_star: logits within 1e-3 relative (of the row's scale)
+    assert np.abs(lg - lr).max() <= 1e-3 * np.abs(lr).max(), np.abs(lg - lr).max() / np.abs(lr).max()
+    tr = _tokens(_run(REF_BIN, model, n_predict=12))
+    tg = _tokens(_run(B200_BIN, model, n_predict=12))
+    assert tr == tg, (tr, tg)
