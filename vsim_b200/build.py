@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libb200q4.so"
 SOURCES = [CSRC / "q4_api.cu", CSRC / "imax_b200.c"]
-DEPS = SOURCES + [CSRC / "q4_kernels.cuh", PKG.parent / "include" / "b200q4.h",
+DEPS = SOURCES + [CSRC / "q4_kernels.cuh", CSRC / "q4_tile.cuh", PKG.parent / "include" / "b200q4.h",
                   PKG.parent / "include" / "b200q4_ggml_abi.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

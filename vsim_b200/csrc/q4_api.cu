@@ -4,6 +4,7 @@
 // CUDA is unusable every entry point fails with B200Q4_ENODEV / B200Q4_ECUDA.
 #include "../../include/b200q4.h"
 #include "q4_kernels.cuh"
+#include "q4_tile.cuh"
 
 using b200q4::PIPE_MAX_STAGES;
 using b200q4::PIPE_TILE_SPLIT;
@@ -44,6 +45,10 @@ struct Ctx {
     float *d_x = nullptr;    size_t x_cap = 0;
     float *d_y = nullptr;    size_t y_cap = 0;
     uint8_t *d_tmp = nullptr; size_t tmp_cap = 0;
+    uint8_t *d_tpack = nullptr; size_t tpack_cap = 0;           // tile kernel: activation stages
+    float *d_tpartial = nullptr; size_t tpartial_cap = 0;        // tile kernel: split-K pieces
+    int *d_tcounters = nullptr; size_t tcounters_cap = 0;        // tile kernel: split-K arrival counters (self-resetting)
+    int tile_min_m = 3;              // M >= this runs the tcgen05 tile kernel (B200Q4_TILE_MIN_M overrides; 0 = never)
     uint64_t launches = 0;
     std::recursive_mutex mu;
     std::string err;
@@ -196,6 +201,100 @@ int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, con
 #undef PIPE_DISPATCH
 }
 
+
+// ---- tcgen05 tile kernel (q4_tile_kernel) -------------------------------------------------------
+struct TilePlan { int MT, m_tiles, n_tiles, PP, PC, ntasks, nraw, nact; size_t smem; };
+
+TilePlan tile_plan(const b200q4_weight *w, int M)
+{
+    TilePlan tp{};
+    tp.MT = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128;
+    tp.m_tiles = (M + tp.MT - 1) / tp.MT;
+    tp.n_tiles = (w->n_tiles + TK_T16 - 1) / TK_T16;
+    const long base = (long)tp.n_tiles * tp.m_tiles;
+    const int sms = g.sms > 0 ? g.sms : 148;
+    // Split K over PP pieces when the tiles alone cannot keep every SM streaming (small M: the kernel
+    // is HBM-bound and an idle SM is lost bandwidth).  Cost model in chunk times: waves x (chunks per
+    // piece + pipeline fill/drain + combine).  Large M keeps PP = 1 (the pieces would cost more
+    // traffic than the weights).
+    tp.PP = 1; tp.PC = w->C;
+    if (tp.MT <= 64) {
+        double best = 1e30;
+        const int maxpp = w->C < 16 ? w->C : 16;
+        for (int pp = 1; pp <= maxpp; pp++) {
+            const int pc = (w->C + pp - 1) / pp, ppe = (w->C + pc - 1) / pc;
+            const long tasks = base * ppe;
+            const long waves = (tasks + sms - 1) / sms;
+            const double cost = (double)waves * (pc + 1.0 + (ppe > 1 ? 0.5 + 0.02 * tp.MT : 0.0));
+            if (cost < best - 1e-9) { best = cost; tp.PP = ppe; tp.PC = pc; }
+        }
+    }
+    tp.ntasks = (int)(base * tp.PP);
+    const size_t optin = (size_t)(g.smem_optin > 0 ? g.smem_optin : 232448);
+    tp.nact = tp.MT >= 128 ? 3 : 4;
+    long nraw = ((long)optin - (long)tk_smem_bytes(w->type, tp.MT, 0, tp.nact)) / tk_raw_stage(w->type);
+    if (nraw > TK_MAX_RAW) nraw = TK_MAX_RAW;
+    tp.nraw = (int)nraw;
+    tp.smem = tk_smem_bytes(w->type, tp.MT, tp.nraw, tp.nact);
+    return tp;
+}
+
+template <int QT, int MT>
+int launch_tile(const TileParams &p, int grid, size_t smem, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(q4_tile_kernel<QT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_optin));
+        attr_set = true;
+    }
+    q4_tile_kernel<QT, MT><<<grid, TK_THREADS, smem, st>>>(p);
+    g.launches++;
+    CK(cudaGetLastError());
+    return B200Q4_OK;
+}
+
+int run_tile(const b200q4_weight *w, const float *d_x, size_t x_stride_f, const uint8_t *d_wdata, int M,
+             float *d_y, size_t y_stride_f, cudaStream_t st)
+{
+    const TilePlan tp = tile_plan(w, M);
+    if (tp.nraw < 2) return fail(B200Q4_EINVAL, "tile kernel: shared memory too small");
+    int rc;
+    const size_t stage = (size_t)tk_act_stage(w->type, tp.MT);
+    if ((rc = ensure(g.d_tpack, g.tpack_cap, (size_t)tp.m_tiles * w->C * stage))) return rc;
+    if (tp.PP > 1) {
+        if ((rc = ensure(g.d_tpartial, g.tpartial_cap, (size_t)tp.ntasks * tp.MT * TK_ROWS * sizeof(float)))) return rc;
+        const size_t need = (size_t)tp.n_tiles * tp.m_tiles * sizeof(int);
+        if (need > g.tcounters_cap) {
+            if ((rc = ensure(g.d_tcounters, g.tcounters_cap, need))) return rc;
+            CK(cudaMemsetAsync(g.d_tcounters, 0, g.tcounters_cap, st));
+        }
+    }
+    const long warps = (long)tp.m_tiles * w->C * CHUNK_BLKS * tp.MT;
+    const int blocks = (int)((warps * 32 + 255) / 256);
+#define TILE_PACK(QT)                                                                                                  \
+    if (d_wdata) tile_pack_kernel<QT, true><<<blocks, 256, 0, st>>>(nullptr, 0, d_wdata, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack); \
+    else         tile_pack_kernel<QT, false><<<blocks, 256, 0, st>>>(d_x, x_stride_f, nullptr, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack);
+    if (w->type == 0) { TILE_PACK(0) } else { TILE_PACK(1) }
+#undef TILE_PACK
+    g.launches++;
+    CK(cudaGetLastError());
+    TileParams p;
+    p.wt = w->d_wt; p.tpack = g.d_tpack; p.y = d_y; p.partial = g.d_tpartial; p.counters = g.d_tcounters;
+    p.y_stride = y_stride_f; p.N = w->N; p.M = M; p.C = w->C; p.n_t16 = w->n_tiles; p.m_tiles = tp.m_tiles;
+    p.PP = tp.PP; p.PC = tp.PC; p.ntasks = tp.ntasks; p.nraw = tp.nraw; p.nact = tp.nact;
+    const int grid = tp.ntasks < g.sms ? tp.ntasks : g.sms;
+#define TILE_DISPATCH(QT)                                                              \
+    switch (tp.MT) {                                                                   \
+    case 16:  return launch_tile<QT, 16>(p, grid, tp.smem, st);                        \
+    case 32:  return launch_tile<QT, 32>(p, grid, tp.smem, st);                        \
+    case 64:  return launch_tile<QT, 64>(p, grid, tp.smem, st);                        \
+    default:  return launch_tile<QT, 128>(p, grid, tp.smem, st);                       \
+    }
+    if (w->type == 0) { TILE_DISPATCH(0) }
+    TILE_DISPATCH(1)
+#undef TILE_DISPATCH
+}
+
 int ensure_scratch(const b200q4_weight *w, int MP)
 {
     const int nbp = w->C * CHUNK_BLKS;
@@ -212,6 +311,8 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
     if ((x_stride % 4) || (y_stride % 4)) return fail(B200Q4_EINVAL, "mul_mat: strides must be multiples of 4 bytes");
     if (M == 0 || w->N == 0) return B200Q4_OK;
     if ((long)w->n_tiles * w->C > 0x7fffffffL) return fail(B200Q4_EINVAL, "tensor too large");
+    if (g.tile_min_m > 0 && M >= g.tile_min_m)
+        return run_tile(w, d_x, x_stride / 4, d_wdata, M, d_y, y_stride / 4, st);
     const int nbp = w->C * CHUNK_BLKS;
     // the fused prologue reads X with 128-bit loads
     const bool can_fuse = !d_wdata && d_x && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0) && (x_stride % 16 == 0);
@@ -331,6 +432,7 @@ int b200q4_init(int device)
     CK(cudaMalloc(&g.d_ticket, 2 * sizeof(int)));
     CK(cudaMemset(g.d_ticket, 0, 2 * sizeof(int)));
     if (const char *e = getenv("B200Q4_PDL")) g.use_pdl = atoi(e) != 0;
+    if (const char *e = getenv("B200Q4_TILE_MIN_M")) g.tile_min_m = atoi(e);
     if (const char *e = getenv("B200Q4_DBG")) if (atoi(e) != 0) {
         CK(cudaMalloc(&g.d_dbg, 256 * 16 * sizeof(unsigned long long)));
         CK(cudaMemset(g.d_dbg, 0, 256 * 16 * sizeof(unsigned long long)));
@@ -348,6 +450,9 @@ void b200q4_shutdown(void)
     cudaStreamSynchronize(g.stream);
     cudaFree(g.d_ticket); g.d_ticket = nullptr;
     cudaFree(g.d_aq); cudaFree(g.d_ap); cudaFree(g.d_partial); cudaFree(g.d_x); cudaFree(g.d_y); cudaFree(g.d_tmp);
+    cudaFree(g.d_tpack); cudaFree(g.d_tpartial); cudaFree(g.d_tcounters);
+    g.d_tpack = nullptr; g.d_tpartial = nullptr; g.d_tcounters = nullptr;
+    g.tpack_cap = g.tpartial_cap = g.tcounters_cap = 0;
     g.d_aq = nullptr; g.d_ap = nullptr; g.d_partial = nullptr; g.d_x = nullptr; g.d_y = nullptr; g.d_tmp = nullptr;
     g.aq_cap = g.ap_cap = g.partial_cap = g.x_cap = g.y_cap = g.tmp_cap = 0;
     cudaEventDestroy(g.ev0); cudaEventDestroy(g.ev1);
@@ -579,6 +684,7 @@ const char *b200q4_kernel_for(int type, int M, int N, int K)
 {
     (void)N;
     if ((type != 0 && type != 1) || K <= 0 || K % QK) return "invalid";
+    if (g.tile_min_m > 0 && M >= g.tile_min_m) return type == 0 ? "q4_0_tile_tcgen05" : "q4_1_tile_tcgen05";
     const int mp = (M <= 2) ? 2 : 8;
     return type == 0 ? (mp == 2 ? "q4_0_gemv_pipe_chain4" : "q4_0_gemv_pipe_m8") : (mp == 2 ? "q4_1_gemv_pipe_chain4" : "q4_1_gemv_pipe_m8");
 }
