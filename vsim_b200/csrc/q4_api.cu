@@ -48,6 +48,7 @@ struct Ctx {
     uint8_t *d_tpack = nullptr; size_t tpack_cap = 0;           // tile kernel: activation stages
     float *d_tpartial = nullptr; size_t tpartial_cap = 0;        // tile kernel: split-K pieces
     int *d_tcounters = nullptr; size_t tcounters_cap = 0;        // tile kernel: split-K arrival counters (self-resetting)
+    int tile_big_mt = 256;           // activation rows per tile once M > 128 (B200Q4_TILE_BIG_MT=128|256)
     int tile_min_m = 3;              // M >= this runs the tcgen05 tile kernel (B200Q4_TILE_MIN_M overrides; 0 = never)
     uint64_t launches = 0;
     std::recursive_mutex mu;
@@ -203,39 +204,34 @@ int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, con
 
 
 // ---- tcgen05 tile kernel (q4_tile_kernel) -------------------------------------------------------
-struct TilePlan { int MT, m_tiles, n_tiles, PP, PC, ntasks, nraw, nact; size_t smem; };
+struct TilePlan { int MT, m_tiles, n_tiles, ntiles, grid, nraw, nact, nconv; size_t smem; };
 
 TilePlan tile_plan(const b200q4_weight *w, int M)
 {
     TilePlan tp{};
-    tp.MT = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128;
+    const int big = g.tile_big_mt;                                            // 128 or 256 activation rows per tile for large M
+    tp.MT = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : (M <= 128 || big < 256) ? 128 : 256;
     tp.m_tiles = (M + tp.MT - 1) / tp.MT;
     tp.n_tiles = (w->n_tiles + TK_T16 - 1) / TK_T16;
-    const long base = (long)tp.n_tiles * tp.m_tiles;
+    tp.ntiles = tp.n_tiles * tp.m_tiles;
+    const long steps = (long)tp.ntiles * w->C;                                // stream-K: chunk steps are dealt out evenly
     const int sms = g.sms > 0 ? g.sms : 148;
-    // Split K over PP pieces when the tiles alone cannot keep every SM streaming (small M: the kernel
-    // is HBM-bound and an idle SM is lost bandwidth).  Cost model in chunk times: waves x (chunks per
-    // piece + pipeline fill/drain + combine).  Large M keeps PP = 1 (the pieces would cost more
-    // traffic than the weights).
-    tp.PP = 1; tp.PC = w->C;
-    if (tp.MT <= 64) {
-        double best = 1e30;
-        const int maxpp = w->C < 16 ? w->C : 16;
-        for (int pp = 1; pp <= maxpp; pp++) {
-            const int pc = (w->C + pp - 1) / pp, ppe = (w->C + pc - 1) / pc;
-            const long tasks = base * ppe;
-            const long waves = (tasks + sms - 1) / sms;
-            const double cost = (double)waves * (pc + 1.0 + (ppe > 1 ? 0.5 + 0.02 * tp.MT : 0.0));
-            if (cost < best - 1e-9) { best = cost; tp.PP = ppe; tp.PC = pc; }
-        }
-    }
-    tp.ntasks = (int)(base * tp.PP);
+    tp.grid = (int)(steps < sms ? steps : sms);
+    // shared-memory rings: activation stages, converted-operand slots, and whatever is left for raw weight stages
     const size_t optin = (size_t)(g.smem_optin > 0 ? g.smem_optin : 232448);
-    tp.nact = tp.MT >= 128 ? 3 : 4;
-    long nraw = ((long)optin - (long)tk_smem_bytes(w->type, tp.MT, 0, tp.nact)) / tk_raw_stage(w->type);
+    const int qt = w->type;
+    tp.nact = tp.MT >= 256 ? 2 : tp.MT >= 128 ? 3 : 4;
+    tp.nconv = tp.MT >= 256 ? 3 : 4;
+    long nraw = ((long)optin - (long)tk_smem_bytes(qt, tp.MT, 0, tp.nact, tp.nconv)) / tk_raw_stage(qt);
+    while (nraw < 3 && tp.nconv > 2) {
+        tp.nconv--;
+        nraw = ((long)optin - (long)tk_smem_bytes(qt, tp.MT, 0, tp.nact, tp.nconv)) / tk_raw_stage(qt);
+    }
     if (nraw > TK_MAX_RAW) nraw = TK_MAX_RAW;
     tp.nraw = (int)nraw;
-    tp.smem = tk_smem_bytes(w->type, tp.MT, tp.nraw, tp.nact);
+    // small M: the kernel streams weights; spend the spare shared memory on more converted slots too
+    while (tp.nconv < TK_MAX_CONV && tp.nraw > 10) { tp.nconv++; tp.nraw -= 2; }
+    tp.smem = tk_smem_bytes(qt, tp.MT, tp.nraw, tp.nact, tp.nconv);
     return tp;
 }
 
@@ -257,17 +253,16 @@ int run_tile(const b200q4_weight *w, const float *d_x, size_t x_stride_f, const 
              float *d_y, size_t y_stride_f, cudaStream_t st)
 {
     const TilePlan tp = tile_plan(w, M);
-    if (tp.nraw < 2) return fail(B200Q4_EINVAL, "tile kernel: shared memory too small");
+    if (tp.nraw < 2 || tp.smem > (size_t)g.smem_optin) return fail(B200Q4_EINVAL, "tile kernel: shared memory too small");
+    if ((long)tp.ntiles * w->C > 0x7fffffffL) return fail(B200Q4_EINVAL, "tile kernel: tensor too large");
     int rc;
     const size_t stage = (size_t)tk_act_stage(w->type, tp.MT);
     if ((rc = ensure(g.d_tpack, g.tpack_cap, (size_t)tp.m_tiles * w->C * stage))) return rc;
-    if (tp.PP > 1) {
-        if ((rc = ensure(g.d_tpartial, g.tpartial_cap, (size_t)tp.ntasks * tp.MT * TK_ROWS * sizeof(float)))) return rc;
-        const size_t need = (size_t)tp.n_tiles * tp.m_tiles * sizeof(int);
-        if (need > g.tcounters_cap) {
-            if ((rc = ensure(g.d_tcounters, g.tcounters_cap, need))) return rc;
-            CK(cudaMemsetAsync(g.d_tcounters, 0, g.tcounters_cap, st));
-        }
+    if ((rc = ensure(g.d_tpartial, g.tpartial_cap, (size_t)tp.grid * 2 * tp.MT * TK_ROWS * sizeof(float)))) return rc;
+    const size_t need = (size_t)tp.ntiles * sizeof(int);
+    if (need > g.tcounters_cap) {
+        if ((rc = ensure(g.d_tcounters, g.tcounters_cap, need))) return rc;
+        CK(cudaMemsetAsync(g.d_tcounters, 0, g.tcounters_cap, st));
     }
     const long warps = (long)tp.m_tiles * w->C * CHUNK_BLKS * tp.MT;
     const int blocks = (int)((warps * 32 + 255) / 256);
@@ -281,14 +276,15 @@ int run_tile(const b200q4_weight *w, const float *d_x, size_t x_stride_f, const 
     TileParams p;
     p.wt = w->d_wt; p.tpack = g.d_tpack; p.y = d_y; p.partial = g.d_tpartial; p.counters = g.d_tcounters;
     p.y_stride = y_stride_f; p.N = w->N; p.M = M; p.C = w->C; p.n_t16 = w->n_tiles; p.m_tiles = tp.m_tiles;
-    p.PP = tp.PP; p.PC = tp.PC; p.ntasks = tp.ntasks; p.nraw = tp.nraw; p.nact = tp.nact;
-    const int grid = tp.ntasks < g.sms ? tp.ntasks : g.sms;
+    p.ntiles = tp.ntiles; p.nraw = tp.nraw; p.nact = tp.nact; p.nconv = tp.nconv;
+    p.dbg = g.d_dbg;
 #define TILE_DISPATCH(QT)                                                              \
     switch (tp.MT) {                                                                   \
-    case 16:  return launch_tile<QT, 16>(p, grid, tp.smem, st);                        \
-    case 32:  return launch_tile<QT, 32>(p, grid, tp.smem, st);                        \
-    case 64:  return launch_tile<QT, 64>(p, grid, tp.smem, st);                        \
-    default:  return launch_tile<QT, 128>(p, grid, tp.smem, st);                       \
+    case 16:  return launch_tile<QT, 16>(p, tp.grid, tp.smem, st);                     \
+    case 32:  return launch_tile<QT, 32>(p, tp.grid, tp.smem, st);                     \
+    case 64:  return launch_tile<QT, 64>(p, tp.grid, tp.smem, st);                     \
+    case 128: return launch_tile<QT, 128>(p, tp.grid, tp.smem, st);                    \
+    default:  return launch_tile<QT, 256>(p, tp.grid, tp.smem, st);                    \
     }
     if (w->type == 0) { TILE_DISPATCH(0) }
     TILE_DISPATCH(1)
@@ -433,6 +429,7 @@ int b200q4_init(int device)
     CK(cudaMemset(g.d_ticket, 0, 2 * sizeof(int)));
     if (const char *e = getenv("B200Q4_PDL")) g.use_pdl = atoi(e) != 0;
     if (const char *e = getenv("B200Q4_TILE_MIN_M")) g.tile_min_m = atoi(e);
+    if (const char *e = getenv("B200Q4_TILE_BIG_MT")) g.tile_big_mt = atoi(e) >= 256 ? 256 : 128;
     if (const char *e = getenv("B200Q4_DBG")) if (atoi(e) != 0) {
         CK(cudaMalloc(&g.d_dbg, 256 * 16 * sizeof(unsigned long long)));
         CK(cudaMemset(g.d_dbg, 0, 256 * 16 * sizeof(unsigned long long)));

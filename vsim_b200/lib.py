@@ -44,7 +44,10 @@ def load_library(build: bool = True) -> C.CDLL:
     if _LIB is not None:
         return _LIB
     from . import build as _b
-    if build:
+    import os
+    if os.environ.get("B200Q4_LIB"):              # development: an experimental build of the same sources
+        path = os.environ["B200Q4_LIB"]
+    elif build:
         path = _b.build_library()
     else:
         path = _b.LIB
