@@ -48,8 +48,7 @@ struct Ctx {
     uint8_t *d_tpack = nullptr; size_t tpack_cap = 0;           // tile kernel: activation stages
     float *d_tpartial = nullptr; size_t tpartial_cap = 0;        // tile kernel: split-K pieces
     int *d_tcounters = nullptr; size_t tcounters_cap = 0;        // tile kernel: split-K arrival counters (self-resetting)
-    int tile_big_mt = 256;           // activation rows per tile once M > 128 (B200Q4_TILE_BIG_MT=128|256)
-    int tile_min_m = 3;              // M >= this runs the tcgen05 tile kernel (B200Q4_TILE_MIN_M overrides; 0 = never)
+    int tile_min_m = 9;              // M >= this runs the tcgen05 tile kernel, below it the decode kernel (B200Q4_TILE_MIN_M overrides; 0 = never)
     uint64_t launches = 0;
     std::recursive_mutex mu;
     std::string err;
@@ -209,8 +208,9 @@ struct TilePlan { int MT, m_tiles, n_tiles, ntiles, grid, nraw, nact, nconv; siz
 TilePlan tile_plan(const b200q4_weight *w, int M)
 {
     TilePlan tp{};
-    const int big = g.tile_big_mt;                                            // 128 or 256 activation rows per tile for large M
-    tp.MT = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : (M <= 128 || big < 256) ? 128 : 256;
+    const int qt = w->type;
+    const int cap = tk_max_mt(qt);                                            // 128 (Q4_0) / 64 (Q4_1): the TMEM map
+    tp.MT = M <= 16 ? 16 : M <= 32 ? 32 : (M <= 64 || cap == 64) ? 64 : 128;
     tp.m_tiles = (M + tp.MT - 1) / tp.MT;
     tp.n_tiles = (w->n_tiles + TK_T16 - 1) / TK_T16;
     tp.ntiles = tp.n_tiles * tp.m_tiles;
@@ -219,18 +219,14 @@ TilePlan tile_plan(const b200q4_weight *w, int M)
     tp.grid = (int)(steps < sms ? steps : sms);
     // shared-memory rings: activation stages, converted-operand slots, and whatever is left for raw weight stages
     const size_t optin = (size_t)(g.smem_optin > 0 ? g.smem_optin : 232448);
-    const int qt = w->type;
-    tp.nact = tp.MT >= 256 ? 2 : tp.MT >= 128 ? 3 : 4;
-    tp.nconv = tp.MT >= 256 ? 3 : 4;
-    long nraw = ((long)optin - (long)tk_smem_bytes(qt, tp.MT, 0, tp.nact, tp.nconv)) / tk_raw_stage(qt);
-    while (nraw < 3 && tp.nconv > 2) {
-        tp.nconv--;
-        nraw = ((long)optin - (long)tk_smem_bytes(qt, tp.MT, 0, tp.nact, tp.nconv)) / tk_raw_stage(qt);
-    }
+    tp.nact = tp.MT >= 128 ? 2 : 3;
+    tp.nconv = 3;
+    auto raw_fit = [&]() { return ((long)optin - (long)tk_smem_bytes(qt, tp.MT, 0, tp.nact, tp.nconv)) / tk_raw_stage(qt); };
+    long nraw = raw_fit();
+    while (nraw < 3 && tp.nconv > 2) { tp.nconv--; nraw = raw_fit(); }
+    while (nraw < 3 && tp.nact > 2) { tp.nact--; nraw = raw_fit(); }
     if (nraw > TK_MAX_RAW) nraw = TK_MAX_RAW;
     tp.nraw = (int)nraw;
-    // small M: the kernel streams weights; spend the spare shared memory on more converted slots too
-    while (tp.nconv < TK_MAX_CONV && tp.nraw > 10) { tp.nconv++; tp.nraw -= 2; }
     tp.smem = tk_smem_bytes(qt, tp.MT, tp.nraw, tp.nact, tp.nconv);
     return tp;
 }
@@ -282,11 +278,12 @@ int run_tile(const b200q4_weight *w, const float *d_x, size_t x_stride_f, const 
     switch (tp.MT) {                                                                   \
     case 16:  return launch_tile<QT, 16>(p, tp.grid, tp.smem, st);                     \
     case 32:  return launch_tile<QT, 32>(p, tp.grid, tp.smem, st);                     \
-    case 64:  return launch_tile<QT, 64>(p, tp.grid, tp.smem, st);                     \
-    case 128: return launch_tile<QT, 128>(p, tp.grid, tp.smem, st);                    \
-    default:  return launch_tile<QT, 256>(p, tp.grid, tp.smem, st);                    \
+    default:  return launch_tile<QT, 64>(p, tp.grid, tp.smem, st);                     \
     }
-    if (w->type == 0) { TILE_DISPATCH(0) }
+    if (w->type == 0) {
+        if (tp.MT == 128) return launch_tile<0, 128>(p, tp.grid, tp.smem, st);
+        TILE_DISPATCH(0)
+    }
     TILE_DISPATCH(1)
 #undef TILE_DISPATCH
 }
@@ -429,7 +426,6 @@ int b200q4_init(int device)
     CK(cudaMemset(g.d_ticket, 0, 2 * sizeof(int)));
     if (const char *e = getenv("B200Q4_PDL")) g.use_pdl = atoi(e) != 0;
     if (const char *e = getenv("B200Q4_TILE_MIN_M")) g.tile_min_m = atoi(e);
-    if (const char *e = getenv("B200Q4_TILE_BIG_MT")) g.tile_big_mt = atoi(e) >= 256 ? 256 : 128;
     if (const char *e = getenv("B200Q4_DBG")) if (atoi(e) != 0) {
         CK(cudaMalloc(&g.d_dbg, 256 * 16 * sizeof(unsigned long long)));
         CK(cudaMemset(g.d_dbg, 0, 256 * 16 * sizeof(unsigned long long)));

@@ -1,43 +1,50 @@
 // q4_tile.cuh -- the batched (M >= 3) Q4_0/Q4_1 mul_mat kernel for sm_100a: TMA-staged weight tiles,
-// nibble -> 8-bit expansion into shared memory, tcgen05 MMA with TMEM accumulators, fp32 block
-// scaling on the CUDA cores.
+// nibble -> 8-bit expansion into shared memory, tcgen05 MMA with TMEM accumulators; the per-block
+// fp32 scale products are ALSO formed on the tensor core, so the CUDA cores do one FFMA per
+// (m, n, quant block) with both operands read from TMEM.
 //
 // Reference semantics: ggml_compute_forward_mul_mat_q4_{0,1}_f32 (ggml.c:4891-5453) with the block
 // dot products of ggml.c:472-553 / imax.c:1205-1229.  Same exact-integer formulation as the decode
 // kernel (q4_kernels.cuh):
 //
-//   Q4_0:  Y[m][n] = sum_blk d0[n,blk] * d1[m,blk] * ( P - 8*Sa ),   P = sum_k q0*a, a = q1-8, Sa = sum_k a
-//   Q4_1:  Y[m][n] = sum_blk d0*d1*P + (d0*S0)*m1 + m0*Z,             P = sum_k q0*q1, S0 = sum_k q0,
-//                                                                     Z = d1*sum(q1) + 32*m1
+//   Q4_0:  Y[m][n] = sum_blk (d0[n,blk] * d1[m,blk]) * I,    I = sum_k (q0-8)(q1-8)           (I exact)
+//   Q4_1:  Y[m][n] = sum_blk (d0*d1) * I + (d0*S0)*m1 + m0*Z   with the codes CENTRED, d*q + m = d*(q-8) + (m + 8d):
+//                    I as above, S0 = sum_k (q0-8), m0 := m0 + 8*d0, m1 := m1 + 8*d1, Z = d1*sum(q1-8) + 32*m1
+//                    (I, S0 exact).  Centring keeps every term small; with raw codes d0*d1*P and d0*S0*m1 are
+//                    two large numbers that nearly cancel in every block.
 //
-// The 32-element sums P are ONE tcgen05.mma each (kind::f8f6f4, M=128 weight rows x N=MT activation
-// rows x K=32 = one quant block) and they are exact:
-//   * a weight nibble q0 in [0,15], left as the byte 0x0q, IS the e4m3 number q0 * 2^-9 (e4m3
-//     subnormals 0x01..0x07 = 1..7 * 2^-9 continue linearly into the first binade 0x08..0x0F =
-//     8..15 * 2^-9).  So "dequantizing" the weights into the MMA operand is one AND (low nibbles) or
-//     one shift + AND (high nibbles) per 4 elements -- no table, no arithmetic.
-//   * the activation codes are written by our own pack kernel as e4m3 bytes of a*2^5 (Q4_0, |a|<=8)
-//     or q1*2^4 (Q4_1, q1<=15): small integers times a power of two are exact in e4m3.
-//   * every product is a multiple of 2^-4 / 2^-5 below 2^8; 32 of them sum exactly in fp32.
-// So TMEM holds D = P/16 (Q4_0) or P/32 (Q4_1) exactly, one fresh accumulator tile per quant block,
-// and the per-block fp32 scales -- different for every (n, blk) and (m, blk), which is what keeps a
-// plain GEMM from doing this job -- are applied by the epilogue warps:
-//   Q4_0:  acc[m] = fma(d0[n], fma(D, d1[m], e[m]), acc[m])        e = -0.5*d1*Sa        (x16 at the store)
-//   Q4_1:  acc[m] = fma(m0[n], Z'[m], fma(w1[n], m1'[m], fma(d0[n], d1[m]*D, acc[m])))   (x32 at the store)
-// Only those fp32 scale products are rounded.  The epilogue (2 or 4 FFMA per (m, n, block)) is what
-// bounds the kernel once M is large; below M ~ 48 the weight stream (HBM) bounds it.
+// Per quant block (K = 32) and per 128 weight rows x MT activation rows the tensor core runs:
+//   1. V  = A x B      kind::f8f6f4, fresh accumulator.  A = the weight nibbles: a nibble q0 in [0,15]
+//                      left as the byte 0x0q IS the e4m3 number q0 * 2^-9 (the e4m3 subnormals 1..7 * 2^-9
+//                      continue linearly into the first binade 8..15 * 2^-9), so "dequantizing" is one AND
+//                      (low nibbles) or shift + AND (high nibbles) per 4 elements.  B = the activation codes,
+//                      written by our pack kernel as e4m3 bytes of (q1-8)*2^5.
+//                      Every product is a small multiple of 2^-4; 32 of them sum exactly in fp32.
+//   2. V += A8 x B     A8 = a constant tile of -8 * 2^-9: restores the "-8" of the weight codes,
+//                      V = I / 16 exactly.
+//   3. T  = A3 x B3    kind::f16 (bf16, K = 16): d0 = a1+a2+a3 and d1 = b1+b2+b3 split exactly into three
+//                      bf16 pieces each; the nine K slots hold (a_i, b_j), so T[n][m] = d0[n] * d1[m] to
+//                      fp32 accuracy (products exact, one fp32 accumulation), replicated over the tile by
+//                      the MMA itself -- this is the "broadcast" that shared memory is too narrow for
+//                      (8 B of scales per value per lane through a 128 B/cycle LSU bounded the first
+//                      version of this kernel at 1/4 of its FMA rate).
+//   4. R  = A4 x B4    (Q4_1 only) the rank-2 term (d0*S0)*m1' + m0*Z' with bf16 pieces in 12 K slots, a
+//                      fresh tile per block, added by the epilogue (a running sum kept on the tensor core
+//                      drifts: its accumulate step truncates).
+// and the epilogue warps do   acc[m] = fma(T[m], V[m], acc[m]) (+ R[m])   (packed FFMA2), x16 at the store.
+// The kernel is bounded by TMEM read bandwidth (8 B per value; ~400 B/cycle/SM measured with
+// tools/tmembench.cu) for large M, by the weight stream (HBM) for small M.
 //
-// Warp roles (512 threads, one CTA per SM, persistent over tasks):
-//   warp 0      producer: cp.async.bulk (TMA 1-D) of weight chunks (8 x 1280/1536 B per 128 rows x 4
-//               blocks, straight from the decode kernel's "wtile" layout -- one weight copy in HBM
-//               serves both kernels) and of activation stages (codes already in the UMMA canonical
-//               K-major layout + column scales), each ring with full/empty mbarriers.
-//   warp 1      MMA issuer (one thread): 4 tcgen05.mma per chunk into alternating TMEM buffers,
-//               tcgen05.commit to the epilogue and back to the rings.
+// Warp roles (512 threads, one CTA per SM, persistent; register budgets moved with setmaxnreg):
+//   warp 0      producer: cp.async.bulk (TMA 1-D) of weight chunks, 8 x 1280/1536 B per 128 rows x 4
+//               blocks straight from the decode kernel's "wtile" layout (one weight copy in HBM serves
+//               both kernels); full/empty mbarriers.
+//   warp 3      producer of the activation stages (codes + bf16 scale pieces, already in operand layout).
+//   warp 1      MMA issuer (one elected thread), tcgen05.commit to the epilogue and back to the rings.
 //   warp 2      TMEM allocator (512 columns).
-//   warps 4-7   converters: nibble words -> e4m3 bytes in the UMMA canonical layout (no swizzle: core
-//               matrix = 8 rows x 16 B), row scales (d0, d0*S0, m0) into a small ring.
-//   warps 8-15  epilogue: tcgen05.ld (32 lanes x 32 bit), scale FMAs, final store / split-K combine.
+//   warps 4-7   converters: nibble words -> bytes in the UMMA canonical layout (K-major, no swizzle: core
+//               matrix = 8 rows x 16 B), bf16 pieces of d0 (and d0*S0, m0).
+//   warps 8-15  epilogue: tcgen05.ld x16 double-buffered, FFMA2, final store / stream-K combine.
 #pragma once
 #include "q4_kernels.cuh"
 
@@ -48,21 +55,25 @@ constexpr int TK_T16 = TK_ROWS / TILE_ROWS;  // wtile tiles per tile
 constexpr int TK_CONV_WARPS = 4;
 constexpr int TK_EPI_WARPS = 8;
 constexpr int TK_THREADS = (4 + TK_CONV_WARPS + TK_EPI_WARPS) * 32;
-constexpr int TK_MAX_RAW = 16, TK_MAX_ACT = 8, TK_MAX_CONV = 8;
+constexpr int TK_MAX_RAW = 16, TK_MAX_ACT = 8, TK_MAX_CONV = 8, TK_MAX_TM = 4;
 // register budgets after setmaxnreg (launch: 512 threads x 128): 128*(40 + 72 + 2*200) = 65536
 constexpr int TK_REGS_MISC = 40, TK_REGS_CONV = 72, TK_REGS_EPI = 200;
+constexpr int TK_OP_TILE = TK_ROWS * 32;     // one 128-row operand tile of one block (fp8 K=32 or bf16 K=16)
 
-__host__ __device__ constexpr int tk_ncs(int qt) { return qt == 0 ? 2 : 4; }     // column-scale floats per (m, blk)
-__host__ __device__ constexpr int tk_nrs(int qt) { return qt == 0 ? 1 : 3; }     // row-scale planes per (n, blk)
-__host__ __device__ constexpr int tk_act_stage(int qt, int mt) { return CHUNK_BLKS * mt * 32 + CHUNK_BLKS * mt * tk_ncs(qt) * 4; }
+__host__ __device__ constexpr int tk_nop(int qt) { return qt == 0 ? 2 : 3; }          // operand tiles per block and side
+__host__ __device__ constexpr int tk_max_mt(int qt) { return qt == 0 ? 128 : 64; }
+__host__ __device__ constexpr int tk_act_stage(int qt, int mt) { return CHUNK_BLKS * mt * 32 * tk_nop(qt); }
 __host__ __device__ constexpr int tk_raw_stage(int qt) { return TK_T16 * chunk_bytes(qt); }
-__host__ __device__ constexpr int tk_conv_slot(int qt) { return CHUNK_BLKS * TK_ROWS * 32 + CHUNK_BLKS * tk_nrs(qt) * TK_ROWS * 4; }
-__host__ __device__ constexpr int tk_bar_bytes() { return (2 * TK_MAX_RAW + 2 * TK_MAX_ACT + 2 * TK_MAX_CONV + 4) * 8 + 64; }
+__host__ __device__ constexpr int tk_conv_slot(int qt) { return CHUNK_BLKS * TK_OP_TILE * tk_nop(qt); }
+__host__ __device__ constexpr int tk_bar_bytes() { return (2 * TK_MAX_RAW + 2 * TK_MAX_ACT + 2 * TK_MAX_CONV + 2 * TK_MAX_TM + 2) * 8 + 64; }
 __host__ __device__ inline size_t tk_smem_bytes(int qt, int mt, int nraw, int nact, int nconv)
 {
-    return 1024 + (size_t)nraw * tk_raw_stage(qt) + (size_t)nact * tk_act_stage(qt, mt) +
+    return (size_t)TK_OP_TILE + (size_t)nraw * tk_raw_stage(qt) + (size_t)nact * tk_act_stage(qt, mt) +
            (size_t)nconv * tk_conv_slot(qt) + tk_bar_bytes();
 }
+// blocks per TMEM buffer; two buffers of G x [V | T (| R)] x MT columns: Q4_0 2 x 256 (2 x 128 at MT = 16), Q4_1 2 x 192
+__host__ __device__ constexpr int tk_g(int qt, int mt) { return qt == 0 ? (128 / mt < CHUNK_BLKS ? 128 / mt : CHUNK_BLKS) : (64 / mt < CHUNK_BLKS ? 64 / mt : CHUNK_BLKS); }
+__host__ __device__ constexpr int tk_nbuf(int qt) { return 2; }
 
 struct TileParams {
     const uint8_t *wt;       // wtile
@@ -99,17 +110,63 @@ __device__ __forceinline__ uint32_t e4m3_of_int(int v, int s)
     return sign | ((uint32_t)(7 + s + k) << 3) | man;
 }
 
+// x = h1 + h2 + h3 exactly, each a bf16 (returned as its 16 bits): 8 + 8 + 8 significand bits
+__device__ __forceinline__ void bf16_split3(float x, uint32_t &h1, uint32_t &h2, uint32_t &h3)
+{
+    const uint32_t u = __float_as_uint(x);
+    h1 = u >> 16;
+    const float r = __fsub_rn(x, __uint_as_float(u & 0xFFFF0000u));           // exact
+    const uint32_t ur = __float_as_uint(r);
+    h2 = ur >> 16;
+    const float r2 = __fsub_rn(r, __uint_as_float(ur & 0xFFFF0000u));         // exact, <= 8 significant bits
+    h3 = __float_as_uint(r2) >> 16;
+}
+// the 16 K slots of a rank-1 product x*y: slot 3(i-1)+(j-1) holds (x_i, y_j); 9..15 are zero
+__device__ __forceinline__ void bf16_slots_left(float x, uint4 &lo, uint32_t &hi0)    // x_1 x_1 x_1 x_2 x_2 x_2 x_3 x_3 | x_3
+{
+    uint32_t a1, a2, a3;
+    bf16_split3(x, a1, a2, a3);
+    lo = make_uint4(a1 | (a1 << 16), a1 | (a2 << 16), a2 | (a2 << 16), a3 | (a3 << 16));
+    hi0 = a3;
+}
+__device__ __forceinline__ void bf16_slots_right(float y, uint4 &lo, uint32_t &hi0)   // y_1 y_2 y_3 y_1 y_2 y_3 y_1 y_2 | y_3
+{
+    uint32_t b1, b2, b3;
+    bf16_split3(y, b1, b2, b3);
+    lo = make_uint4(b1 | (b2 << 16), b3 | (b1 << 16), b2 | (b3 << 16), b1 | (b2 << 16));
+    hi0 = b3;
+}
+// the rank-2 term x*y + z*w in 12 slots: pairs (1,1) (1,2) (2,1) (2,2) (1,3) (3,1) of each product
+// (the dropped pairs are below 2^-23 of the product)
+__device__ __forceinline__ void bf16_slots2_left(float x, float z, uint4 &lo, uint4 &hi)
+{
+    uint32_t a1, a2, a3, c1, c2, c3;
+    bf16_split3(x, a1, a2, a3);
+    bf16_split3(z, c1, c2, c3);
+    lo = make_uint4(a1 | (a1 << 16), a2 | (a2 << 16), a1 | (a3 << 16), c1 | (c1 << 16));
+    hi = make_uint4(c2 | (c2 << 16), c1 | (c3 << 16), 0u, 0u);
+}
+__device__ __forceinline__ void bf16_slots2_right(float y, float w, uint4 &lo, uint4 &hi)
+{
+    uint32_t b1, b2, b3, e1, e2, e3;
+    bf16_split3(y, b1, b2, b3);
+    bf16_split3(w, e1, e2, e3);
+    lo = make_uint4(b1 | (b2 << 16), b1 | (b2 << 16), b3 | (b1 << 16), e1 | (e2 << 16));
+    hi = make_uint4(e1 | (e2 << 16), e3 | (e1 << 16), 0u, 0u);
+}
+
 // K position (byte inside the block's 32-byte operand row) of element e: the converter emits, per
 // nibble word t (elements 8t .. 8t+7), the four low nibbles (even elements) then the four high ones.
 __device__ __forceinline__ int tk_kpos(int e) { return (e & 24) + ((e & 1) << 2) + ((e & 7) >> 1); }
 
-// Byte offset of (row r, K position p) inside one block's operand tile in the UMMA canonical K-major
+// Byte offset of (row r, K byte p) inside one block's operand tile in the UMMA canonical K-major
 // no-swizzle layout: core matrix = 8 rows x 16 B contiguous; K-adjacent core matrices 128 B apart
 // (LBO), 8-row groups 256 B apart (SBO).
 __device__ __forceinline__ int tk_operand_off(int r, int p) { return (r >> 3) * 256 + (p >> 4) * 128 + (r & 7) * 16 + (p & 15); }
 
 // ---- activation pack for the tile kernel ----------------------------------------------------------
-// One warp per (stage row m_local, block) of every (m tile, chunk) stage, padding included.
+// Stage (m tile, chunk) = [4 blocks x codes tile][4 blocks x scale-piece tile]([4 blocks x rank-2 tile]),
+// every tile MT rows x 32 B in operand layout.  One warp per (stage row m_local, block), padding included.
 // SRC_WDATA: rows already quantized by the reference's INIT phase (params->wdata image).
 template <int QT, bool SRC_WDATA>
 __global__ void tile_pack_kernel(const float *__restrict__ x, size_t x_stride, const uint8_t *__restrict__ wdata,
@@ -127,7 +184,7 @@ __global__ void tile_pack_kernel(const float *__restrict__ x, size_t x_stride, c
     const int m = mt * MT + ml, blk = c * CHUNK_BLKS + bi;
     const bool real = (m < M) && (blk < nb);
     BlockQ q;
-    q.d = 0.0f; q.mn = 0.0f; q.code = (QT == 0) ? 8 : 0;
+    q.d = 0.0f; q.mn = 0.0f; q.code = 8;                 // padding: centred code 0, zero scales
     if (SRC_WDATA) {
         if (real) {
             if (QT == 0) {
@@ -146,28 +203,31 @@ __global__ void tile_pack_kernel(const float *__restrict__ x, size_t x_stride, c
     } else {
         const float xv = real ? x[(size_t)m * x_stride + (size_t)blk * QK + lane] : 0.0f;
         q = quantize_block<QT>(xv);
-        if (!real) { q.d = 0.0f; q.mn = 0.0f; q.code = (QT == 0) ? 8 : 0; }
+        if (!real) { q.d = 0.0f; q.mn = 0.0f; q.code = 8; }
     }
-    const int a = (QT == 0) ? (q.code & 15) - 8 : (q.code & 15);
+    const int a = (q.code & 15) - 8;
     uint8_t *stage = tpack + ((size_t)mt * C + c) * tk_act_stage(QT, MT);
-    stage[(size_t)bi * MT * 32 + tk_operand_off(ml, tk_kpos(lane))] = (uint8_t)e4m3_of_int(a, QT == 0 ? 5 : 4);
-    int s = a;
+    const size_t tile = (size_t)MT * 32, plane = (size_t)CHUNK_BLKS * tile;
+    stage[(size_t)bi * tile + tk_operand_off(ml, tk_kpos(lane))] = (uint8_t)e4m3_of_int(a, 5);
+    if (QT == 1) {
+        int s = a;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-        // column scales, stored per PAIR of columns so that one LDS.128 feeds one packed FFMA2:
-        //   Q4_0: {d1_a, d1_b, e_a, e_b}          Q4_1: {d1_a, d1_b, m1'_a, m1'_b, Z'_a, Z'_b, 0, 0}
-        float *cs = reinterpret_cast<float *>(stage + (size_t)CHUNK_BLKS * MT * 32) +
-                    ((size_t)bi * (MT / 2) + (ml >> 1)) * (2 * tk_ncs(QT)) + (ml & 1);
-        if (QT == 0) {
-            cs[0] = q.d;
-            cs[2] = -0.5f * (q.d * (float)s);
-        } else {
-            cs[0] = q.d;
-            cs[2] = q.mn * 0.03125f;
-            cs[4] = fmaf(q.d, (float)s, 32.0f * q.mn) * 0.03125f;
-            cs[6] = 0.0f;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 1) {                                 // rank-2 right factors: m1' = m1c/16, Z' = (d1*sum(q1-8) + 32*m1c)/16
+            uint4 lo, hi;
+            const float m1c = __fadd_rn(q.mn, 8.0f * q.d);
+            bf16_slots2_right(m1c * 0.0625f, fmaf(q.d, (float)s, 32.0f * m1c) * 0.0625f, lo, hi);
+            uint8_t *t4 = stage + 2 * plane + (size_t)bi * tile;
+            *reinterpret_cast<uint4 *>(t4 + tk_operand_off(ml, 0)) = lo;
+            *reinterpret_cast<uint4 *>(t4 + tk_operand_off(ml, 16)) = hi;
         }
+    }
+    if (lane == 0) {                                     // the nine slots of d1
+        uint4 lo; uint32_t hi0;
+        bf16_slots_right(q.d, lo, hi0);
+        uint8_t *t3 = stage + plane + (size_t)bi * tile;
+        *reinterpret_cast<uint4 *>(t3 + tk_operand_off(ml, 0)) = lo;
+        *reinterpret_cast<uint4 *>(t3 + tk_operand_off(ml, 16)) = make_uint4(hi0, 0u, 0u, 0u);
     }
 }
 
@@ -190,57 +250,73 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
 {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) | (1ull << 46);
 }
-// instruction descriptor: D = F32, A = B = E4M3, both K-major, N = n, M = 128
-__host__ __device__ constexpr uint32_t umma_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TK_ROWS >> 4) << 24); }
+// instruction descriptors: D = F32, both operands K-major, M = 128, N = n; A = B = E4M3 or BF16
+__host__ __device__ constexpr uint32_t umma_idesc_f8(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TK_ROWS >> 4) << 24); }
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TK_ROWS >> 4) << 24); }
 
-__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
-        "}\n" :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(0u) : "memory");
+        "}\n" :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
-// tcgen05.wait::ld, carrying the loaded registers as in/out operands: the compiler must not move
-// their uses above the wait (it does not know the load is asynchronous).
-template <int NV>
-__device__ __forceinline__ void tmem_wait_ld(float (&v)[NV])
-{
-    static_assert(NV == 8 || NV == 16, "unsupported width");
-    uint32_t *u = reinterpret_cast<uint32_t *>(v);
-    if constexpr (NV == 8)
-        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]) :: "memory");
-    else
-        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]),
-                     "+r"(u[8]), "+r"(u[9]), "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15]) :: "memory");
-}
 
-// NV 32-bit columns of this warp's 32 TMEM lanes -> v[0..NV)
+// NV 32-bit columns of this warp's 32 TMEM lanes -> v[0..NV).  (x16 is the fast shape: x32 measured
+// 4x slower per byte, tools/tmembench.cu.)
 template <int NV>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[NV])
 {
-    static_assert(NV == 8 || NV == 16 || NV == 32, "unsupported tcgen05.ld width");
+    static_assert(NV == 8 || NV == 16, "unsupported tcgen05.ld width");
     uint32_t *u = reinterpret_cast<uint32_t *>(v);
     if constexpr (NV == 8) {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "r"(taddr) : "memory");
-    } else if constexpr (NV == 16) {
+    } else {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
                        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]) : "r"(taddr) : "memory");
-    } else {
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                     "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                     : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-                       "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
-                       "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
-                       "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31]) : "r"(taddr) : "memory");
     }
+}
+// tcgen05.wait::ld, carrying the loaded registers as in/out operands: the compiler must not move
+// their uses above the wait (it does not know the load is asynchronous).
+template <int NV>
+__device__ __forceinline__ void tmem_wait_ld(float (&a)[NV], float (&b)[NV])
+{
+    static_assert(NV == 8 || NV == 16, "unsupported width");
+    uint32_t *u = reinterpret_cast<uint32_t *>(a), *w = reinterpret_cast<uint32_t *>(b);
+    if constexpr (NV == 8)
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]),
+                     "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]) :: "memory");
+    else
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]),
+                     "+r"(u[8]), "+r"(u[9]), "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15]),
+                     "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]),
+                     "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]) :: "memory");
+}
+
+template <int NV>
+__device__ __forceinline__ void tmem_wait_ld3(float (&a)[NV], float (&b)[NV], float (&c)[NV])
+{
+    tmem_wait_ld<NV>(a, b);
+    uint32_t *u = reinterpret_cast<uint32_t *>(c);
+#pragma unroll
+    for (int i = 0; i < NV; i++) asm volatile("" : "+r"(u[i]));      // same ordering constraint for the third tile
 }
 
 // one lane of a converged warp (the compiler keeps what that lane computes from warp-uniform inputs in
@@ -263,7 +339,8 @@ typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void upk2(f32x2 v, float &a, float &b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(R)); }
 template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(R)); }
@@ -289,36 +366,41 @@ __device__ __forceinline__ int tk_owner(const TileParams &p, int x, int G)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// MT: activation rows per tile (MMA N): 16, 32, 64, 128 or 256.  A TMEM buffer holds G = min(4, 256/MT)
-// block accumulators (G * MT <= 256 columns); two buffers alternate.
+// MT: activation rows per tile (MMA N): 16, 32, 64 (and 128 for Q4_0).
+// TMEM: NBUF buffers of G blocks x [V: MT columns | T: MT columns (| R: MT columns, Q4_1)].
 // ---------------------------------------------------------------------------------------------------
 template <int QT, int MT>
 __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams p)
 {
+    static_assert(MT <= tk_max_mt(QT), "tile too wide for the TMEM map");
     constexpr int CH = chunk_bytes(QT);
-    constexpr int NCS = tk_ncs(QT), NRS = tk_nrs(QT);
-    constexpr int RAW_STAGE = tk_raw_stage(QT), ACT_STAGE = tk_act_stage(QT, MT);
-    constexpr int CONV_SLOT = tk_conv_slot(QT);
-    constexpr int CONV_A = CHUNK_BLKS * TK_ROWS * 32;                         // operand bytes of a conv slot; row scales follow
-    constexpr int G = (256 / MT) < CHUNK_BLKS ? (256 / MT) : CHUNK_BLKS;      // blocks per TMEM buffer
+    constexpr int RAW_STAGE = tk_raw_stage(QT), ACT_STAGE = tk_act_stage(QT, MT), CONV_SLOT = tk_conv_slot(QT);
+    constexpr int B_TILE = MT * 32;                                           // one block's activation-side operand tile
+    constexpr int A_PLANE = CHUNK_BLKS * TK_OP_TILE, B_PLANE = CHUNK_BLKS * B_TILE;
+    constexpr int G = tk_g(QT, MT);                                           // blocks per TMEM buffer
     constexpr int STEPS = CHUNK_BLKS / G;                                     // TMEM buffers per chunk
+    constexpr int NBUF = tk_nbuf(QT);
+    constexpr int NT = tk_nop(QT);                                            // TMEM tiles per block: V, T (, R)
+    constexpr int BUFC = G * NT * MT;                                         // columns per TMEM buffer
+    static_assert(NBUF * BUFC <= 512, "TMEM map");
     constexpr int HC = MT / 2;                                                // columns per epilogue thread
     constexpr int LW = HC >= 16 ? 16 : HC;                                    // columns per tcgen05.ld
-    constexpr int NSB = HC / LW;                                              // loads per block
-    constexpr uint32_t IDESC = umma_idesc(MT);
+    constexpr int NSB = HC / LW;                                              // loads per block and operand
+    constexpr uint32_t IDESC8 = umma_idesc_f8(MT), IDESC16 = umma_idesc_bf16(MT);
 
     // (plain pointer arithmetic on the shared array only: an integer round trip would make every
     // access below a generic LD/ST instead of LDS/STS; the no-swizzle operand layout needs 16 B alignment)
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *s_conv = smem;                                                   // [nconv][4 blocks x 128 rows x 32 B | row scales [4][NRS][128]]
-    uint8_t *s_act = s_conv + (size_t)p.nconv * CONV_SLOT;                    // [nact][ACT_STAGE]
+    uint8_t *s_a8 = smem;                                                     // the constant -8 * 2^-9 tile
+    uint8_t *s_conv = s_a8 + TK_OP_TILE;                                      // [nconv][A | A3 (| A4)] x 4 blocks
+    uint8_t *s_act = s_conv + (size_t)p.nconv * CONV_SLOT;                    // [nact][B | B3 (| B4)] x 4 blocks
     uint8_t *s_rawr = s_act + (size_t)p.nact * ACT_STAGE;                     // [nraw][RAW_STAGE]
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_rawr + (size_t)p.nraw * RAW_STAGE);
     uint64_t *raw_full = bars, *raw_empty = raw_full + TK_MAX_RAW;
     uint64_t *act_full = raw_empty + TK_MAX_RAW, *act_empty = act_full + TK_MAX_ACT;
     uint64_t *conv_full = act_empty + TK_MAX_ACT, *conv_empty = conv_full + TK_MAX_CONV;
-    uint64_t *tm_full = conv_empty + TK_MAX_CONV, *tm_empty = tm_full + 2;
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(tm_empty + 2);
+    uint64_t *tm_full = conv_empty + TK_MAX_CONV, *tm_empty = tm_full + TK_MAX_TM;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(tm_empty + TK_MAX_TM);
     int      *s_flag = reinterpret_cast<int *>(s_tmem + 1);
 
     const int lane = threadIdx.x & 31;
@@ -326,10 +408,15 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
     const int G_ = (int)gridDim.x;
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nraw; i++) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], TK_CONV_WARPS); }
-        for (int i = 0; i < p.nact; i++) { mbar_init(&act_full[i], 1); mbar_init(&act_empty[i], 1 + TK_EPI_WARPS); }
-        for (int i = 0; i < p.nconv; i++) { mbar_init(&conv_full[i], TK_CONV_WARPS); mbar_init(&conv_empty[i], 1 + TK_EPI_WARPS); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], TK_EPI_WARPS); }
+        for (int i = 0; i < p.nact; i++) { mbar_init(&act_full[i], 1); mbar_init(&act_empty[i], 1); }
+        for (int i = 0; i < p.nconv; i++) { mbar_init(&conv_full[i], TK_CONV_WARPS); mbar_init(&conv_empty[i], 1); }
+        for (int i = 0; i < NBUF; i++) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], TK_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        for (int i = threadIdx.x; i < TK_OP_TILE / 16; i += TK_THREADS)
+            reinterpret_cast<uint4 *>(s_a8)[i] = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
+        fence_proxy_async();
     }
     if (warp == 2) tmem_alloc(s_tmem, 512);
     tc_fence_before();
@@ -398,29 +485,38 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
         } else if (warp == 1 && elect_one()) {
             // ===================== MMA issuer =====================
             TK_PROF_DECL;
-            RingPos ar(p.nact), cr(p.nconv), tr(2);
+            RingPos ar(p.nact), cr(p.nconv), tr(NBUF);
+            const uint32_t a8 = smem_u32(s_a8);
             for (int x = rg.lo; x < rg.hi; x++) {
-                TK_WAIT(&conv_full[cr.idx], cr.ph, 5);
-                TK_WAIT(&act_full[ar.idx], ar.ph, 6);
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(s_conv + (size_t)cr.idx * CONV_SLOT);
-                const uint32_t b_base = smem_u32(s_act + (size_t)ar.idx * ACT_STAGE);
-#pragma unroll
-                for (int st = 0; st < STEPS; st++) {
-                    TK_WAIT(&tm_empty[tr.idx], tr.ph ^ 1u, 7);
+                {
+                    TK_WAIT(&conv_full[cr.idx], cr.ph, 5);
+                    TK_WAIT(&act_full[ar.idx], ar.ph, 6);
                     tc_fence_after();
+                    const uint32_t a_base = smem_u32(s_conv + (size_t)cr.idx * CONV_SLOT);
+                    const uint32_t b_base = smem_u32(s_act + (size_t)ar.idx * ACT_STAGE);
 #pragma unroll
-                    for (int g = 0; g < G; g++) {
-                        const int bi = st * G + g;
-                        umma_f8(tmem + (uint32_t)(tr.idx * 256 + g * MT), umma_desc(a_base + bi * (TK_ROWS * 32)),
-                                umma_desc(b_base + bi * (MT * 32)), IDESC);
+                    for (int st = 0; st < STEPS; st++) {
+                        TK_WAIT(&tm_empty[tr.idx], tr.ph ^ 1u, 7);
+                        tc_fence_after();
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+                            const int bi = st * G + g;
+                            const uint32_t dv = tmem + (uint32_t)(tr.idx * BUFC + g * NT * MT);
+                            const uint64_t bd = umma_desc(b_base + bi * B_TILE);
+                            umma_f8(dv, umma_desc(a_base + bi * TK_OP_TILE), bd, IDESC8, 0u);
+                            umma_f8(dv, umma_desc(a8), bd, IDESC8, 1u);
+                            umma_bf16(dv + MT, umma_desc(a_base + A_PLANE + bi * TK_OP_TILE), umma_desc(b_base + B_PLANE + bi * B_TILE), IDESC16, 0u);
+                            if constexpr (QT == 1)
+                                umma_bf16(dv + 2 * MT, umma_desc(a_base + 2 * A_PLANE + bi * TK_OP_TILE),
+                                          umma_desc(b_base + 2 * B_PLANE + bi * B_TILE), IDESC16, 0u);
+                        }
+                        umma_commit(&tm_full[tr.idx]);
+                        tr.next();
                     }
-                    umma_commit(&tm_full[tr.idx]);
-                    tr.next();
+                    umma_commit(&conv_empty[cr.idx]);
+                    umma_commit(&act_empty[ar.idx]);
+                    cr.next(); ar.next();
                 }
-                umma_commit(&conv_empty[cr.idx]);
-                umma_commit(&act_empty[ar.idx]);
-                cr.next(); ar.next();
             }
             TK_PROF_FLUSH(4, true);
         }
@@ -436,7 +532,6 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
             TK_WAIT(&conv_empty[cr.idx], cr.ph ^ 1u, 10);
             const uint8_t *raw = s_rawr + (size_t)rr.idx * RAW_STAGE;
             uint8_t *conv = s_conv + (size_t)cr.idx * CONV_SLOT;
-            float *rs = reinterpret_cast<float *>(conv + CONV_A);
             uint4 q[4];
             float d0[4], m0[4];
 #pragma unroll
@@ -448,19 +543,22 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int tile = 2 * cw + (u >> 1), half = u & 1;
-                const int row = tile * 16 + half * 8 + g;
-                uint8_t *dst = conv + (tile * 2 + half) * 256 + (t >> 1) * 128 + g * 16 + (t & 1) * 8;
+                const int rgp = (2 * cw + (u >> 1)) * 2 + (u & 1);           // 8-row group of this lane's row
+                uint8_t *dst = conv + rgp * 256 + (t >> 1) * 128 + g * 16 + (t & 1) * 8;
                 int s0[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const uint32_t wv = u4_get(q[u], i);
                     const uint32_t lo = wv & 0x0F0F0F0Fu, hi = (wv >> 4) & 0x0F0F0F0Fu;
-                    *reinterpret_cast<uint2 *>(dst + i * (TK_ROWS * 32)) = make_uint2(lo, hi);
+                    *reinterpret_cast<uint2 *>(dst + i * TK_OP_TILE) = make_uint2(lo, hi);
                     if constexpr (QT == 1) s0[i] = __dp4a(lo, 0x01010101u, __dp4a(hi, 0x01010101u, 0u));
                 }
-                // lane (g, t) forwards the row scales of block t
-                rs[(t * NRS + 0) * TK_ROWS + row] = d0[u];
+                // lane (g, t) writes the scale pieces of block t for its row
+                uint8_t *d3 = conv + A_PLANE + t * TK_OP_TILE + rgp * 256 + g * 16;
+                uint4 lo; uint32_t hi0;
+                bf16_slots_left(d0[u], lo, hi0);
+                *reinterpret_cast<uint4 *>(d3) = lo;
+                *reinterpret_cast<uint4 *>(d3 + 128) = make_uint4(hi0, 0u, 0u, 0u);
                 if constexpr (QT == 1) {
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
@@ -468,8 +566,11 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
                         s0[i] += __shfl_xor_sync(0xffffffffu, s0[i], 2);
                     }
                     const int mine = t == 0 ? s0[0] : t == 1 ? s0[1] : t == 2 ? s0[2] : s0[3];
-                    rs[(t * NRS + 1) * TK_ROWS + row] = d0[u] * (float)mine;
-                    rs[(t * NRS + 2) * TK_ROWS + row] = m0[u];
+                    uint4 l4, h4;
+                    bf16_slots2_left(d0[u] * (float)(mine - 256), __fadd_rn(m0[u], 8.0f * d0[u]), l4, h4);   // centred: S0 - 8*32, m0 + 8*d0
+                    uint8_t *d4 = conv + 2 * A_PLANE + t * TK_OP_TILE + rgp * 256 + g * 16;
+                    *reinterpret_cast<uint4 *>(d4) = l4;
+                    *reinterpret_cast<uint4 *>(d4 + 128) = h4;
                 }
             }
             fence_proxy_async();                         // generic-proxy stores -> visible to the tensor core's reads
@@ -487,7 +588,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
         const int etid = ew * 32 + lane;
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * HC);
         TK_PROF_DECL;
-        RingPos ar(p.nact), cr(p.nconv), tr(2);
+        RingPos tr(NBUF);
         int x = rg.lo;
         while (x < rg.hi) {
             const int tile = x / p.C, c0 = x - tile * p.C;
@@ -497,21 +598,20 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
 #pragma unroll
             for (int j = 0; j < HC / 2; j++) acc[j] = 0ull;
             for (int c = 0; c < nc; c++) {
-                TK_WAIT(&conv_full[cr.idx], cr.ph, 12);  // row scales written by the converters
-                TK_WAIT(&act_full[ar.idx], ar.ph, 13);   // column scales landed (TMA)
-                const float *rs = reinterpret_cast<const float *>(s_conv + (size_t)cr.idx * CONV_SLOT + CONV_A);
-                const float *cs = reinterpret_cast<const float *>(s_act + (size_t)ar.idx * ACT_STAGE + CHUNK_BLKS * MT * 32) + (size_t)(h * HC / 2) * (2 * NCS);
-                // software pipeline over the chunk's (block, 16-column) loads: load i+1 is in flight
-                // while the FFMA2s of load i run
+                // software pipeline over the chunk's (block, 16-column) loads: V and T of load i+1 are
+                // in flight while the FFMA2s of load i run
                 constexpr int NL = CHUNK_BLKS * NSB;
-                float v[2][LW];
+                float v[2][LW], s[2][LW], r[2][QT == 1 ? LW : 1];
                 TK_WAIT(&tm_full[tr.idx], tr.ph, 14);
                 tc_fence_after();
-                tmem_ld<LW>(t_lane + (uint32_t)(tr.idx * 256), v[0]);
+                tmem_ld<LW>(t_lane + (uint32_t)(tr.idx * BUFC), v[0]);
+                tmem_ld<LW>(t_lane + (uint32_t)(tr.idx * BUFC + MT), s[0]);
+                if constexpr (QT == 1) tmem_ld<LW>(t_lane + (uint32_t)(tr.idx * BUFC + 2 * MT), r[0]);
 #pragma unroll
                 for (int i = 0; i < NL; i++) {
                     const int bi = i / NSB, sb = i % NSB, g = bi % G;
-                    tmem_wait_ld<LW>(v[i & 1]);
+                    if constexpr (QT == 1) tmem_wait_ld3<LW>(v[i & 1], s[i & 1], r[i & 1]);
+                    else                   tmem_wait_ld<LW>(v[i & 1], s[i & 1]);
                     if (g == G - 1 && sb == NSB - 1) {   // that was the last read of this TMEM buffer: hand it back
                         tc_fence_before();
                         __syncwarp();
@@ -524,42 +624,21 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
                             TK_WAIT(&tm_full[tr.idx], tr.ph, 14);
                             tc_fence_after();
                         }
-                        tmem_ld<LW>(t_lane + (uint32_t)(tr.idx * 256 + gn * MT + sn * LW), v[(i + 1) & 1]);
+                        const uint32_t col = (uint32_t)(tr.idx * BUFC + gn * NT * MT + sn * LW);
+                        tmem_ld<LW>(t_lane + col, v[(i + 1) & 1]);
+                        tmem_ld<LW>(t_lane + col + MT, s[(i + 1) & 1]);
+                        if constexpr (QT == 1) tmem_ld<LW>(t_lane + col + 2 * MT, r[(i + 1) & 1]);
                     }
-                    const float d0 = rs[(bi * NRS + 0) * TK_ROWS + row];
-                    const f32x2 d02 = pk2(d0, d0);
-                    const float *csb = cs + ((size_t)bi * (MT / 2) + sb * (LW / 2)) * (2 * NCS);
-                    if constexpr (QT == 0) {
 #pragma unroll
-                        for (int j = 0; j < LW / 2; j++) {
-#ifdef TK_EXP_NOLDS
-                            const float4 s2 = make_float4(d0, d0, 1.0f, 2.0f);
-#else
-                            const float4 s2 = *reinterpret_cast<const float4 *>(csb + j * 4);          // d1_a, d1_b, e_a, e_b
-#endif
-                            const f32x2 t2 = fma2(pk2(v[i & 1][2 * j], v[i & 1][2 * j + 1]), pk2(s2.x, s2.y), pk2(s2.z, s2.w));
-                            acc[sb * (LW / 2) + j] = fma2(d02, t2, acc[sb * (LW / 2) + j]);
-                        }
-                    } else {
-                        const float w1 = rs[(bi * NRS + 1) * TK_ROWS + row], m0 = rs[(bi * NRS + 2) * TK_ROWS + row];
-                        const f32x2 w12 = pk2(w1, w1), m02 = pk2(m0, m0);
-#pragma unroll
-                        for (int j = 0; j < LW / 2; j++) {
-                            const float4 sa = *reinterpret_cast<const float4 *>(csb + j * 8);          // d1_a, d1_b, m1'_a, m1'_b
-                            const float2 sz = *reinterpret_cast<const float2 *>(csb + j * 8 + 4);      // Z'_a, Z'_b
-                            const f32x2 t2 = mul2(pk2(v[i & 1][2 * j], v[i & 1][2 * j + 1]), pk2(sa.x, sa.y));
-                            f32x2 a2 = fma2(d02, t2, acc[sb * (LW / 2) + j]);
-                            a2 = fma2(w12, pk2(sa.z, sa.w), a2);
-                            acc[sb * (LW / 2) + j] = fma2(m02, pk2(sz.x, sz.y), a2);
-                        }
+                    for (int j = 0; j < LW / 2; j++) {
+                        f32x2 a2 = fma2(pk2(s[i & 1][2 * j], s[i & 1][2 * j + 1]), pk2(v[i & 1][2 * j], v[i & 1][2 * j + 1]), acc[sb * (LW / 2) + j]);
+                        if constexpr (QT == 1) a2 = add2(a2, pk2(r[i & 1][2 * j], r[i & 1][2 * j + 1]));
+                        acc[sb * (LW / 2) + j] = a2;
                     }
                 }
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(&conv_empty[cr.idx]); mbar_arrive(&act_empty[ar.idx]); }
-                cr.next(); ar.next();
             }
             // ---- this CTA's share of the tile is done: store, or park the piece and let the last one combine ----
-            const float post = (QT == 0) ? 16.0f : 32.0f;
+            const float post = 16.0f;
             const int n = nt * TK_ROWS + row;
             const int mbase = mt * MT + h * HC;
             const bool whole = (c0 == 0) && (nc == p.C);
