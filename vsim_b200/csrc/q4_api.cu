@@ -239,9 +239,14 @@ int launch_tile(const TileParams &p, int grid, size_t smem, cudaStream_t st)
         CK(cudaFuncSetAttribute(q4_tile_kernel<QT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_optin));
         attr_set = true;
     }
-    q4_tile_kernel<QT, MT><<<grid, TK_THREADS, smem, st>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TK_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g.use_pdl ? 1 : 0;     // starts streaming weights while the pack kernel runs
+    CK(cudaLaunchKernelEx(&cfg, q4_tile_kernel<QT, MT>, p));
     g.launches++;
-    CK(cudaGetLastError());
     return B200Q4_OK;
 }
 
@@ -668,6 +673,16 @@ int b200q4_debug_timeline(unsigned long long *out)
     if (!g.d_dbg) return B200Q4_EINVAL;
     cudaStreamSynchronize(g.stream);
     return cudaMemcpy(out, g.d_dbg, 256 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : B200Q4_ECUDA;
+}
+
+// development / test knob (not part of b200q4.h): smallest M that runs the tcgen05 tile kernel
+// (0 = never); returns the previous value.
+int b200q4_debug_set_tile_min_m(int m)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    const int old = g.tile_min_m;
+    g.tile_min_m = m;
+    return old;
 }
 
 uint64_t b200q4_launch_count(void) { return g.launches; }

@@ -121,20 +121,20 @@ __device__ __forceinline__ void bf16_split3(float x, uint32_t &h1, uint32_t &h2,
     const float r2 = __fsub_rn(r, __uint_as_float(ur & 0xFFFF0000u));         // exact, <= 8 significant bits
     h3 = __float_as_uint(r2) >> 16;
 }
-// the 16 K slots of a rank-1 product x*y: slot 3(i-1)+(j-1) holds (x_i, y_j); 9..15 are zero
-__device__ __forceinline__ void bf16_slots_left(float x, uint4 &lo, uint32_t &hi0)    // x_1 x_1 x_1 x_2 x_2 x_2 x_3 x_3 | x_3
+// K slots 0..7 of a rank-1 product x*y hold the piece pairs (1,1) (1,2) (1,3) (2,1) (2,2) (2,3) (3,1) (3,2)
+// -- one 16-byte store per operand row; (3,3) is below 2^-32 of the product and dropped; slots 8..15
+// (the second core matrix) stay zero.
+__device__ __forceinline__ uint4 bf16_slots_left(float x)     // x_1 x_1 x_1 x_2 x_2 x_2 x_3 x_3
 {
     uint32_t a1, a2, a3;
     bf16_split3(x, a1, a2, a3);
-    lo = make_uint4(a1 | (a1 << 16), a1 | (a2 << 16), a2 | (a2 << 16), a3 | (a3 << 16));
-    hi0 = a3;
+    return make_uint4(a1 | (a1 << 16), a1 | (a2 << 16), a2 | (a2 << 16), a3 | (a3 << 16));
 }
-__device__ __forceinline__ void bf16_slots_right(float y, uint4 &lo, uint32_t &hi0)   // y_1 y_2 y_3 y_1 y_2 y_3 y_1 y_2 | y_3
+__device__ __forceinline__ uint4 bf16_slots_right(float y)    // y_1 y_2 y_3 y_1 y_2 y_3 y_1 y_2
 {
     uint32_t b1, b2, b3;
     bf16_split3(y, b1, b2, b3);
-    lo = make_uint4(b1 | (b2 << 16), b3 | (b1 << 16), b2 | (b3 << 16), b1 | (b2 << 16));
-    hi0 = b3;
+    return make_uint4(b1 | (b2 << 16), b3 | (b1 << 16), b2 | (b3 << 16), b1 | (b2 << 16));
 }
 // the rank-2 term x*y + z*w in 12 slots: pairs (1,1) (1,2) (2,1) (2,2) (1,3) (3,1) of each product
 // (the dropped pairs are below 2^-23 of the product)
@@ -155,9 +155,10 @@ __device__ __forceinline__ void bf16_slots2_right(float y, float w, uint4 &lo, u
     hi = make_uint4(e1 | (e2 << 16), e3 | (e1 << 16), 0u, 0u);
 }
 
-// K position (byte inside the block's 32-byte operand row) of element e: the converter emits, per
-// nibble word t (elements 8t .. 8t+7), the four low nibbles (even elements) then the four high ones.
-__device__ __forceinline__ int tk_kpos(int e) { return (e & 24) + ((e & 1) << 2) + ((e & 7) >> 1); }
+// K position (byte inside the block's 32-byte operand row) of element e: the low nibbles (even
+// elements) of nibble word t form bytes 4t..4t+3, the high nibbles (odd elements) bytes 16+4t..16+4t+3,
+// so the converter's two 32-bit stores per word are each one contiguous 128 B per warp.
+__device__ __forceinline__ int tk_kpos(int e) { return ((e & 1) << 4) + ((e >> 3) << 2) + ((e & 7) >> 1); }
 
 // Byte offset of (row r, K byte p) inside one block's operand tile in the UMMA canonical K-major
 // no-swizzle layout: core matrix = 8 rows x 16 B contiguous; K-adjacent core matrices 128 B apart
@@ -172,6 +173,7 @@ template <int QT, bool SRC_WDATA>
 __global__ void tile_pack_kernel(const float *__restrict__ x, size_t x_stride, const uint8_t *__restrict__ wdata,
                                  int M, int MT, int nb, int C, int m_tiles, uint8_t *__restrict__ tpack)
 {
+    cudaTriggerProgrammaticLaunchCompletion();           // the tile kernel may start its weight stream now
     const int lane = threadIdx.x & 31;
     const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long total = (long)m_tiles * C * CHUNK_BLKS * MT;
@@ -222,12 +224,10 @@ __global__ void tile_pack_kernel(const float *__restrict__ x, size_t x_stride, c
             *reinterpret_cast<uint4 *>(t4 + tk_operand_off(ml, 16)) = hi;
         }
     }
-    if (lane == 0) {                                     // the nine slots of d1
-        uint4 lo; uint32_t hi0;
-        bf16_slots_right(q.d, lo, hi0);
+    if (lane == 0) {                                     // the eight slots of d1 (the upper eight stay zero)
         uint8_t *t3 = stage + plane + (size_t)bi * tile;
-        *reinterpret_cast<uint4 *>(t3 + tk_operand_off(ml, 0)) = lo;
-        *reinterpret_cast<uint4 *>(t3 + tk_operand_off(ml, 16)) = make_uint4(hi0, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(t3 + tk_operand_off(ml, 0)) = bf16_slots_right(q.d);
+        *reinterpret_cast<uint4 *>(t3 + tk_operand_off(ml, 16)) = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
@@ -416,6 +416,12 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
     {
         for (int i = threadIdx.x; i < TK_OP_TILE / 16; i += TK_THREADS)
             reinterpret_cast<uint4 *>(s_a8)[i] = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
+        // K slots 8..15 of the scale-piece tiles (second core matrix of every 8-row group) are zero for good
+        for (int i = threadIdx.x; i < p.nconv * CHUNK_BLKS * (TK_ROWS / 8) * 8; i += TK_THREADS) {
+            const int piece = i & 7, grp = (i >> 3) % (TK_ROWS / 8), blk = (i >> 3) / (TK_ROWS / 8);     // blk over all slots
+            const int slot = blk / CHUNK_BLKS, bi = blk % CHUNK_BLKS;
+            reinterpret_cast<uint4 *>(s_conv + (size_t)slot * CONV_SLOT + A_PLANE + bi * TK_OP_TILE + grp * 256 + 128)[piece] = make_uint4(0u, 0u, 0u, 0u);
+        }
         fence_proxy_async();
     }
     if (warp == 2) tmem_alloc(s_tmem, 512);
@@ -463,6 +469,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
         } else if (warp == 3 && elect_one()) {
             // ===================== producer: activation stages =====================
             TK_PROF_DECL;
+            cudaGridDependencySynchronize();             // the pack kernel's output
             RingPos ar(p.nact);
             const uint32_t act0 = smem_u32(s_act);
             int x = rg.lo;
@@ -524,7 +531,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
     } else if (warp < 4 + TK_CONV_WARPS) {
         // ===================== converters =====================
         reg_dec<TK_REGS_CONV>();
-        const int cw = warp - 4, g = lane >> 2, t = lane & 3;
+        const int cw = warp - 4;
         TK_PROF_DECL;
         RingPos rr(p.nraw), cr(p.nconv);
         for (int x = rg.lo; x < rg.hi; x++) {
@@ -532,43 +539,44 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
             TK_WAIT(&conv_empty[cr.idx], cr.ph ^ 1u, 10);
             const uint8_t *raw = s_rawr + (size_t)rr.idx * RAW_STAGE;
             uint8_t *conv = s_conv + (size_t)cr.idx * CONV_SLOT;
+            // nibble words: lane (g, t) = (row g of an 8-row group, word t); scale path: lane (g2, t2) =
+            // (row g2, block t2) so that 8 consecutive lanes store 8 consecutive 16-byte operand rows
+            const int g2 = lane & 7, t2 = lane >> 3;
             uint4 q[4];
             float d0[4], m0[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {                    // all loads first
                 const uint8_t *ch = raw + (2 * cw + (u >> 1)) * CH;
                 q[u] = *reinterpret_cast<const uint4 *>(ch + (u & 1) * 512 + lane * 16);
-                d0[u] = *reinterpret_cast<const float *>(ch + 1024 + (((u & 1) * 8 + g) * 4 + t) * 4);
-                if constexpr (QT == 1) m0[u] = *reinterpret_cast<const float *>(ch + 1280 + (((u & 1) * 8 + g) * 4 + t) * 4);
+                d0[u] = *reinterpret_cast<const float *>(ch + 1024 + (((u & 1) * 8 + g2) * 4 + t2) * 4);
+                if constexpr (QT == 1) m0[u] = *reinterpret_cast<const float *>(ch + 1280 + (((u & 1) * 8 + g2) * 4 + t2) * 4);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int rgp = (2 * cw + (u >> 1)) * 2 + (u & 1);           // 8-row group of this lane's row
-                uint8_t *dst = conv + rgp * 256 + (t >> 1) * 128 + g * 16 + (t & 1) * 8;
+                uint8_t *dst = conv + rgp * 256 + lane * 4;                  // = g * 16 + t * 4: one contiguous 128 B per warp and store
                 int s0[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const uint32_t wv = u4_get(q[u], i);
                     const uint32_t lo = wv & 0x0F0F0F0Fu, hi = (wv >> 4) & 0x0F0F0F0Fu;
-                    *reinterpret_cast<uint2 *>(dst + i * TK_OP_TILE) = make_uint2(lo, hi);
+                    *reinterpret_cast<uint32_t *>(dst + i * TK_OP_TILE) = lo;
+                    *reinterpret_cast<uint32_t *>(dst + i * TK_OP_TILE + 128) = hi;
                     if constexpr (QT == 1) s0[i] = __dp4a(lo, 0x01010101u, __dp4a(hi, 0x01010101u, 0u));
                 }
-                // lane (g, t) writes the scale pieces of block t for its row
-                uint8_t *d3 = conv + A_PLANE + t * TK_OP_TILE + rgp * 256 + g * 16;
-                uint4 lo; uint32_t hi0;
-                bf16_slots_left(d0[u], lo, hi0);
-                *reinterpret_cast<uint4 *>(d3) = lo;
-                *reinterpret_cast<uint4 *>(d3 + 128) = make_uint4(hi0, 0u, 0u, 0u);
+                *reinterpret_cast<uint4 *>(conv + A_PLANE + t2 * TK_OP_TILE + rgp * 256 + g2 * 16) = bf16_slots_left(d0[u]);
                 if constexpr (QT == 1) {
+                    int mine = 0;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
+                    for (int i = 0; i < 4; i++) {            // row sums of the codes of block i live in the quad of row g
                         s0[i] += __shfl_xor_sync(0xffffffffu, s0[i], 1);
                         s0[i] += __shfl_xor_sync(0xffffffffu, s0[i], 2);
+                        const int v = __shfl_sync(0xffffffffu, s0[i], g2 * 4);
+                        if (i == t2) mine = v;
                     }
-                    const int mine = t == 0 ? s0[0] : t == 1 ? s0[1] : t == 2 ? s0[2] : s0[3];
                     uint4 l4, h4;
                     bf16_slots2_left(d0[u] * (float)(mine - 256), __fadd_rn(m0[u], 8.0f * d0[u]), l4, h4);   // centred: S0 - 8*32, m0 + 8*d0
-                    uint8_t *d4 = conv + 2 * A_PLANE + t * TK_OP_TILE + rgp * 256 + g * 16;
+                    uint8_t *d4 = conv + 2 * A_PLANE + t2 * TK_OP_TILE + rgp * 256 + g2 * 16;
                     *reinterpret_cast<uint4 *>(d4) = l4;
                     *reinterpret_cast<uint4 *>(d4 + 128) = h4;
                 }
@@ -588,6 +596,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
         const int etid = ew * 32 + lane;
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * HC);
         TK_PROF_DECL;
+        cudaGridDependencySynchronize();                 // Y, the piece workspace and its counters belong to earlier launches until now
         RingPos tr(NBUF);
         int x = rg.lo;
         while (x < rg.hi) {
