@@ -39,7 +39,9 @@ def test_abi_version_and_kernel_names():
     L = vsim_b200.load_library()
     assert L.b200q4_abi_version() == 1
     assert vsim_b200.kernel_for(vsim_b200.Q4_0, 1, 16384, 4096) == "q4_0_gemv_pipe_chain4"
-    assert vsim_b200.kernel_for(vsim_b200.Q4_1, 16, 16384, 4096) == "q4_1_gemv_pipe_m8"
+    assert vsim_b200.kernel_for(vsim_b200.Q4_1, 8, 16384, 4096) == "q4_1_gemv_pipe_m8"
+    assert vsim_b200.kernel_for(vsim_b200.Q4_1, 16, 16384, 4096) == "q4_1_tile_tcgen05"
+    assert vsim_b200.kernel_for(vsim_b200.Q4_0, 512, 16384, 4096) == "q4_0_tile_tcgen05"
     assert vsim_b200.kernel_for(7, 1, 16, 64) == "invalid"
 
 
