@@ -892,6 +892,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
                 issue_task(cur);
                 cur = nxt;
             }
+            PIPE_STAMP(10);                              // last copy issued
             mbar_wait(&bar_empty[s], ph);                // stop marker
             s_desc[s] = make_int4(-1, 0, 0, 0);
             mbar_arrive(&bar_full[s]);
@@ -976,7 +977,6 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
     }
 
     // ===================== consumers =====================
-    cudaGridDependencySynchronize();                     // X may be the previous kernel's output
     if (threadIdx.x == 0) PIPE_STAMP(3);
     const int ctid = threadIdx.x;                        // 0 .. 511
     constexpr int CTHREADS = PIPE_CONSUMERS * 32;
@@ -985,6 +985,26 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
         if constexpr (MP == 2 && B8) return s_aq + (size_t)blk * 256 + (M1 ? (blk & 7) : 2 * (blk & 3) + m) * 32;
         else return s_aq + ((size_t)blk * ROWS + m) * 32;
     };
+    if constexpr (FUSED) {
+        // Everything quantization does not write must read as zero: the unused columns of the
+        // 8-column form, the records of padded blocks (nb .. nbp: weight scale 0, but 0 x garbage
+        // could be NaN) and row 1 of an M = 1 call in the two-row layout.  None of it depends on X, so it
+        // is done BEFORE the grid dependency resolves (quantization writes disjoint bytes).
+        for (int i = ctid; i < nbp * AQ_BLK / 8; i += CTHREADS) {
+            const int blk = i / (AQ_BLK / 8), w8 = i - blk * (AQ_BLK / 8);      // 8-byte piece w8 of block blk
+            const int col = w8 >> 2;                                            // 32-byte record index inside the block
+            int m = col;
+            if constexpr (MP == 2 && B8) m = M1 ? (col == (blk & 7) ? 0 : -1) : col - 2 * (blk & 3);
+            const bool live = blk < p.nb && m >= 0 && m < p.M;
+            if (!live) reinterpret_cast<uint2 *>(s_aq + (size_t)blk * AQ_BLK)[w8] = make_uint2(0u, 0u);
+        }
+        for (int pl = 0; pl < NP; pl++) {
+            for (int i = p.nb * ROWS + ctid; i < nbp * ROWS; i += CTHREADS) s_ap[pl * plane + i] = 0.0f;   // padded blocks
+            if (ROWS == 2 && p.M == 1)
+                for (int blk = ctid; blk < p.nb; blk += CTHREADS) s_ap[pl * plane + blk * 2 + 1] = 0.0f;  // absent row
+        }
+    }
+    cudaGridDependencySynchronize();                     // X may be the previous kernel's output
     if constexpr (FUSED) {
         // Issue the activation loads first (one item = 8 consecutive elements of one block; the
         // first FUSED_ITEMS items of a thread are held in registers) so that their L2 latency
@@ -1001,23 +1021,6 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
                 const float4 *src = reinterpret_cast<const float4 *>(p.x + (size_t)m * p.x_stride + (size_t)blk * QK + (lane & 3) * 8);
                 xlo[it] = src[0]; xhi[it] = src[1];
             }
-        }
-        // Everything quantization does not write must read as zero: the unused columns of the
-        // 8-column form, the records of padded blocks (nb .. nbp: weight scale 0, but 0 x garbage
-        // could be NaN) and row 1 of an M = 1 call in the two-row layout.  Quantization writes
-        // disjoint bytes, so no barrier is needed in between.
-        for (int i = ctid; i < nbp * AQ_BLK / 8; i += CTHREADS) {
-            const int blk = i / (AQ_BLK / 8), w8 = i - blk * (AQ_BLK / 8);      // 8-byte piece w8 of block blk
-            const int col = w8 >> 2;                                            // 32-byte record index inside the block
-            int m = col;
-            if constexpr (MP == 2 && B8) m = M1 ? (col == (blk & 7) ? 0 : -1) : col - 2 * (blk & 3);
-            const bool live = blk < p.nb && m >= 0 && m < p.M;
-            if (!live) reinterpret_cast<uint2 *>(s_aq + (size_t)blk * AQ_BLK)[w8] = make_uint2(0u, 0u);
-        }
-        for (int pl = 0; pl < NP; pl++) {
-            for (int i = p.nb * ROWS + ctid; i < nbp * ROWS; i += CTHREADS) s_ap[pl * plane + i] = 0.0f;   // padded blocks
-            if (ROWS == 2 && p.M == 1)
-                for (int blk = ctid; blk < p.nb; blk += CTHREADS) s_ap[pl * plane + blk * 2 + 1] = 0.0f;  // absent row
         }
 #pragma unroll
         for (int it = 0; it < FUSED_ITEMS; it++) {
@@ -1101,6 +1104,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
     for (;;) {
         mbar_wait(&bar_full[s], ph);
         if (first && threadIdx.x == 0) { PIPE_STAMP(5); } first = false;
+        if (threadIdx.x == 0) PIPE_STAMP(9);             // (timeline builds) ends up holding the arrival of the last stage
         const int4 dsc = s_desc[s];
         if (dsc.x < 0) break;
         const bool hA = uA < dsc.x, hB = uB < dsc.x;
