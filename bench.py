@@ -155,6 +155,75 @@ def cpu_baseline(qt: int, m: int, wq: np.ndarray, x: np.ndarray, budget_s: float
             "sample": sample, "ms_per_call": us / 1e3}
 
 
+# GPT-J-6B (BASELINE.json configs[2]): n_embd 4096, 28 layers, vocab 50400 -- the Q4 mul_mats of one decode step
+GPTJ_LAYERS, GPTJ_EMBD, GPTJ_FF, GPTJ_VOCAB = 28, 4096, 16384, 50400
+
+
+def model_decode(vs, L, torch, dist, rank, world, stream, peak, tokens=24):
+    """GPT-J-6B-shaped decode: the 28 x 6 + 1 Q4_0 mul_mats of one token (M=1), device-resident, back to back.
+    Only the hot path of this repository -- norms, rope, attention and sampling of the reference graph are
+    not run -- so this is the mul_mat share of a token, an upper bound on tok/s.
+    N>1: every tensor is row-sharded, each mul_mat is followed by an all-gather of its output slice."""
+    rng = np.random.default_rng(77 + rank)
+
+    def rand_q4_0(n, k):
+        raw = rng.integers(0, 256, size=(n, k // 32 * 20), dtype=np.uint8)
+        raw.reshape(n, k // 32, 20)[:, :, :4] = np.full((n, k // 32), 0.01, np.float32).view(np.uint8).reshape(n, k // 32, 4)
+        return raw
+
+    E, F, V = GPTJ_EMBD, GPTJ_FF, GPTJ_VOCAB
+    shapes = [(E, E)] * 4 + [(F, E), (E, F)]                       # q, k, v, o, fc_in, fc_out  (N, K)
+    host = [rand_q4_0(n // world, k) for n, k in shapes]           # one layer's bytes, uploaded 28 times into distinct HBM
+    layers = [[vs.Q4Weight(0, host[j], shapes[j][0] // world, shapes[j][1]) for j in range(6)] for _ in range(GPTJ_LAYERS)]
+    head = vs.Q4Weight(0, rand_q4_0(V // world, E), V // world, E)
+    wbytes = (sum(h.size for h in host) * GPTJ_LAYERS + head.device_bytes)
+    d_in = torch.randn(1, F, device="cuda", dtype=torch.float32)
+    d_out = torch.empty(1, max(F, V), device="cuda", dtype=torch.float32)
+    d_full = torch.empty(world, max(F, V) // world, device="cuda", dtype=torch.float32)
+
+    def one(w, n, k, st):
+        rc = L.b200q4_mul_mat_dev(w.handle, d_in.data_ptr(), 1, k * 4, d_out.data_ptr(), (n // world) * 4, st.cuda_stream)
+        if rc:
+            raise RuntimeError(vs.lib._err(L))
+        if world > 1:
+            dist.all_gather_into_tensor(d_full.view(-1)[:n].view(world, n // world), d_out.view(-1)[: n // world])
+
+    def token(st):
+        for lw in layers:
+            for j, (n, k) in enumerate(shapes):
+                one(lw[j], n, k, st)
+        one(head, V, E, st)
+
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            token(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(tokens):
+            token(stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / tokens
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    for lw in layers:
+        for w in lw:
+            w.free()
+    head.free()
+    gbs = wbytes / (ms * 1e-3) / 1e9
+    return {"model": "GPT-J-6B shapes (n_embd 4096, 28 layers, vocab 50400), Q4_0, random-init, batch 1",
+            "scope": "the 169 Q4_0 mul_mats of one decode step only (no norm/rope/attention/sampling): mul_mat share of a token",
+            "tok_per_s": 1e3 / ms, "ms_per_token": ms, "mul_mats_per_token": GPTJ_LAYERS * 6 + 1,
+            "weight_bytes_per_gpu": int(wbytes), "weight_GBps_per_gpu": gbs, "frac_hbm_peak": gbs / peak,
+            "parallelism": "single GPU" if world == 1 else f"row shards over {world} GPUs + NCCL all-gather per mul_mat",
+            "tokens_timed": tokens}
+
+
 def prefill_roofline(points, tpeak, tpeak_src, world):
     """The M=512 point of the tcgen05 tile kernel against the measured dense bf16 tensor peak (the judge's
     yardstick for the prefill path); the kernel's own bound is TMEM read bandwidth, see DESIGN.md."""
@@ -224,6 +293,7 @@ def main() -> int:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-points", action="store_true", help="skip the (type, M) sweep")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-model", action="store_true", help="skip the GPT-J-6B-shaped decode leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -350,6 +420,9 @@ def main() -> int:
                                "kernel": vs.kernel_for(qt, m, N_ROWS, K_DIM)})
         for w in w1:
             w.free()
+    model = None
+    if not args.no_model:
+        model = model_decode(vs, L, torch, dist, rank, world, stream, peak)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -389,6 +462,7 @@ def main() -> int:
             "clocks": sampler.summary(),
             "points": points,
             "roofline_prefill": prefill_roofline(points, tpeak, tpeak_src, world),
+            "model_decode": model,
             "checksum_y": float(np.abs(y_e2e).sum()),
         }
         if cpu is not None:
