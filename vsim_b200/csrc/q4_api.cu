@@ -41,6 +41,8 @@ struct Ctx {
     float *d_partial = nullptr; size_t partial_cap = 0;
     unsigned long long *d_dbg = nullptr;   // B200Q4_DBG=1: per-CTA timeline of the last decode launch
     int *d_ticket = nullptr;         // [2] task ticket + CTAs-done, self-resetting
+    int *d_done = nullptr;           // fused all-gather: CTAs that finished their peer stores, self-resetting
+    float *d_yloc = nullptr; size_t yloc_cap = 0;   // sharded tile-kernel launches: local slice before the scatter
     bool use_pdl = true;             // B200Q4_PDL=0 disables programmatic dependent launch
     float *d_x = nullptr;    size_t x_cap = 0;
     float *d_y = nullptr;    size_t y_cap = 0;
@@ -169,9 +171,10 @@ int launch_pipe(const PipeParams &p, int grid, size_t smem, cudaStream_t st)
 }
 
 int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, const float *d_x, size_t x_stride_f,
-             float *d_y, size_t y_stride_f, cudaStream_t st)
+             float *d_y, size_t y_stride_f, cudaStream_t st, const PeerOut *peer)
 {
     PipeParams p;
+    if (peer) p.peer = *peer; else { p.peer = PeerOut{}; p.peer.world = 1; }
     p.wt = w->d_wt; p.x = d_x; p.aq = g.d_aq; p.ap = g.d_ap; p.y = d_y; p.partial = g.d_partial;
     p.tile_counters = w->d_counters; p.ticket = g.d_ticket;
     p.x_stride = x_stride_f; p.y_stride = y_stride_f;
@@ -303,14 +306,25 @@ int ensure_scratch(const b200q4_weight *w, int MP)
 }
 
 int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x_stride, float *d_y,
-                       size_t y_stride, cudaStream_t st, const uint8_t *d_wdata)
+                       size_t y_stride, cudaStream_t st, const uint8_t *d_wdata, const PeerOut *peer = nullptr)
 {
-    if (!w || w->transposed || M < 0 || (!d_x && !d_wdata) || !d_y) return fail(B200Q4_EINVAL, "mul_mat: bad argument");
+    if (!w || w->transposed || M < 0 || (!d_x && !d_wdata) || (!d_y && !peer)) return fail(B200Q4_EINVAL, "mul_mat: bad argument");
     if ((x_stride % 4) || (y_stride % 4)) return fail(B200Q4_EINVAL, "mul_mat: strides must be multiples of 4 bytes");
     if (M == 0 || w->N == 0) return B200Q4_OK;
     if ((long)w->n_tiles * w->C > 0x7fffffffL) return fail(B200Q4_EINVAL, "tensor too large");
-    if (g.tile_min_m > 0 && M >= g.tile_min_m)
-        return run_tile(w, d_x, x_stride / 4, d_wdata, M, d_y, y_stride / 4, st);
+    if (g.tile_min_m > 0 && M >= g.tile_min_m) {
+        if (!peer) return run_tile(w, d_x, x_stride / 4, d_wdata, M, d_y, y_stride / 4, st);
+        // sharded: the tile kernel writes this rank's slice locally, a copy kernel stores it into every rank's Y
+        if (int rc = ensure(g.d_yloc, g.yloc_cap, (size_t)M * w->N * sizeof(float))) return rc;
+        if (int rc = run_tile(w, d_x, x_stride / 4, d_wdata, M, g.d_yloc, (size_t)w->N, st)) return rc;
+        const long total = (long)M * w->N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 4 * g.sms) blocks = 4 * g.sms;
+        scatter_slice_kernel<<<blocks, 256, 0, st>>>(g.d_yloc, (size_t)w->N, M, w->N, y_stride / 4, *peer);
+        g.launches++;
+        CK(cudaGetLastError());
+        return B200Q4_OK;
+    }
     const int nbp = w->C * CHUNK_BLKS;
     // the fused prologue reads X with 128-bit loads
     const bool can_fuse = !d_wdata && d_x && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0) && (x_stride % 16 == 0);
@@ -340,7 +354,13 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
             g.launches++;
             CK(cudaGetLastError());
         }
-        if ((rc = run_pipe(w, mc, pp, fused, xs, x_stride / 4, yo, y_stride / 4, st))) return rc;
+        PeerOut po;
+        if (peer) {                                      // rows m0.. of every rank's Y; only the last launch signals
+            po = *peer;
+            for (int r = 0; r < po.world; r++) po.y[r] = reinterpret_cast<float *>(reinterpret_cast<char *>(po.y[r]) + (size_t)m0 * y_stride);
+            if (m0 + MP < M) po.done = nullptr;
+        }
+        if ((rc = run_pipe(w, mc, pp, fused, xs, x_stride / 4, yo, y_stride / 4, st, peer ? &po : nullptr))) return rc;
     }
     return B200Q4_OK;
 }
@@ -429,6 +449,8 @@ int b200q4_init(int device)
     if (const char *e = getenv("B200Q4_TWO_CTAS")) g.two_ctas = atoi(e) != 0;
     CK(cudaMalloc(&g.d_ticket, 2 * sizeof(int)));
     CK(cudaMemset(g.d_ticket, 0, 2 * sizeof(int)));
+    CK(cudaMalloc(&g.d_done, sizeof(int)));
+    CK(cudaMemset(g.d_done, 0, sizeof(int)));
     if (const char *e = getenv("B200Q4_PDL")) g.use_pdl = atoi(e) != 0;
     if (const char *e = getenv("B200Q4_TILE_MIN_M")) g.tile_min_m = atoi(e);
     if (const char *e = getenv("B200Q4_DBG")) if (atoi(e) != 0) {
@@ -447,6 +469,8 @@ void b200q4_shutdown(void)
     cudaSetDevice(g.device);
     cudaStreamSynchronize(g.stream);
     cudaFree(g.d_ticket); g.d_ticket = nullptr;
+    cudaFree(g.d_done); g.d_done = nullptr;
+    cudaFree(g.d_yloc); g.d_yloc = nullptr; g.yloc_cap = 0;
     cudaFree(g.d_aq); cudaFree(g.d_ap); cudaFree(g.d_partial); cudaFree(g.d_x); cudaFree(g.d_y); cudaFree(g.d_tmp);
     cudaFree(g.d_tpack); cudaFree(g.d_tpartial); cudaFree(g.d_tcounters);
     g.d_tpack = nullptr; g.d_tpartial = nullptr; g.d_tcounters = nullptr;
@@ -543,6 +567,51 @@ int b200q4_mul_mat_dev(const b200q4_weight *w, const float *d_x, int M, size_t x
     if (x_stride == 0) x_stride = (size_t)w->K * 4;
     if (y_stride == 0) y_stride = (size_t)w->N * 4;
     return mul_mat_dev_locked(w, d_x, M, x_stride, d_y, y_stride, stream ? (cudaStream_t)stream : g.stream, nullptr);
+}
+
+int b200q4_mul_mat_dev_allgather(const b200q4_weight *w, const float *d_x, int M, size_t x_stride,
+                                 float *const *y_peers, int world, int rank, int col0, size_t y_stride,
+                                 uint32_t *const *flag_peers, uint32_t seq, void *stream)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    if (!w || !y_peers || !flag_peers || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || col0 < 0)
+        return fail(B200Q4_EINVAL, "mul_mat_dev_allgather: bad argument (world=%d rank=%d)", world, rank);
+    if (x_stride == 0) x_stride = (size_t)w->K * 4;
+    if (y_stride < (size_t)(col0 + w->N) * 4) return fail(B200Q4_EINVAL, "mul_mat_dev_allgather: y_stride smaller than col0 + shard rows");
+    cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
+    PeerOut po{};
+    for (int r = 0; r < world; r++) {
+        if (!y_peers[r] || !flag_peers[r]) return fail(B200Q4_EINVAL, "mul_mat_dev_allgather: NULL peer pointer");
+        po.y[r] = y_peers[r]; po.flag[r] = flag_peers[r];
+    }
+    po.done = g.d_done; po.world = world; po.rank = rank; po.col0 = col0; po.seq = seq;
+    if (M == 0 || w->N == 0) {                           // nothing to store: still publish the sequence number
+        scatter_slice_kernel<<<1, 32, 0, st>>>(nullptr, 0, 0, 0, y_stride / 4, po);
+        g.launches++;
+        CK(cudaGetLastError());
+        return B200Q4_OK;
+    }
+    // a single rank degenerates to the plain call on its own buffer (PeerOut.world == 1 stores through p.y)
+    if (world == 1) {
+        if (int rc = mul_mat_dev_locked(w, d_x, M, x_stride, y_peers[0] + col0, y_stride, st, nullptr)) return rc;
+        scatter_slice_kernel<<<1, 32, 0, st>>>(nullptr, 0, 0, 0, y_stride / 4, po);
+        g.launches++;
+        CK(cudaGetLastError());
+        return B200Q4_OK;
+    }
+    return mul_mat_dev_locked(w, d_x, M, x_stride, nullptr, y_stride, st, nullptr, &po);
+}
+
+int b200q4_wait_flags(const uint32_t *local_flags, int world, uint32_t seq, void *stream)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    if (!local_flags || world < 1 || world > MAX_PEERS) return fail(B200Q4_EINVAL, "wait_flags: bad argument");
+    wait_flags_kernel<<<1, 32, 0, stream ? (cudaStream_t)stream : g.stream>>>(local_flags, world, seq);
+    g.launches++;
+    CK(cudaGetLastError());
+    return B200Q4_OK;
 }
 
 int b200q4_mul_mat(const b200q4_weight *w, const float *x, int M, size_t x_stride, float *y, size_t y_stride)

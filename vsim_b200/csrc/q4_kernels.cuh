@@ -521,6 +521,69 @@ constexpr int PIPE_TILE_SPLIT = 16;                     // tiles of >= this many
 constexpr int PIPE_MAX_STAGES = 6;
 constexpr int PIPE_STATIC_TASKS = 3;                    // per CTA, before the first ticket is drawn
 
+constexpr int MAX_PEERS = 8;
+struct PeerOut {
+    float    *y[MAX_PEERS];      // rank r's full Y [M][y_stride] (y[rank] is local memory)
+    uint32_t *flag[MAX_PEERS];   // rank r's arrival flags [world]
+    int      *done;              // local CTA-completion counter (self-resetting)
+    int       world, rank, col0; // col0: first output column of this rank's shard
+    uint32_t  seq;
+};
+
+// one output element: locally, or into every rank's Y at this shard's column offset
+__device__ __forceinline__ void store_y(float *y, const PeerOut &po, size_t idx, float v)
+{
+    if (po.world <= 1) { y[idx] = v; return; }
+#pragma unroll 1
+    for (int r = 0; r < po.world; r++) po.y[r][idx + po.col0] = v;
+}
+// after a CTA's last store: the last CTA of the launch publishes the sequence number to every rank
+__device__ __forceinline__ void peer_signal(const PeerOut &po, int lane)
+{
+    if (po.world <= 1 || !po.done) return;               // done == NULL: an earlier launch of a multi-launch call
+    __threadfence_system();                              // this warp's peer stores are ordered before the counter
+    __syncwarp();
+    if (lane == 0) {
+        if (atomicAdd(po.done, 1) == (int)gridDim.x - 1) {
+            *po.done = 0;
+            __threadfence_system();
+            for (int r = 0; r < po.world; r++)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(po.flag[r] + po.rank), "r"(po.seq) : "memory");
+        }
+    }
+}
+// blocks the stream until every rank's flag has reached seq (lane r watches rank r)
+__global__ void wait_flags_kernel(const uint32_t *flags, int world, uint32_t seq)
+{
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+        if ((int32_t)(v - seq) >= 0) break;
+        __nanosleep(32);
+    }
+}
+// unfused variant for launches whose kernel has no peer epilogue (the tile kernel): copies this rank's
+// [M][ncols] slice from a local buffer into every rank's Y, then signals like peer_signal
+__global__ void scatter_slice_kernel(const float *__restrict__ src, size_t src_stride, int M, int ncols, size_t y_stride, PeerOut po)
+{
+    const long total = (long)M * ncols;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / ncols), n = (int)(i - (long)m * ncols);
+        const float v = src[(size_t)m * src_stride + n];
+        for (int r = 0; r < po.world; r++) po.y[r][(size_t)m * y_stride + po.col0 + n] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(po.done, 1) == (int)gridDim.x - 1) {
+        *po.done = 0;
+        __threadfence_system();
+        for (int r = 0; r < po.world; r++)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(po.flag[r] + po.rank), "r"(po.seq) : "memory");
+    }
+}
+
 struct PipeParams {
     const uint8_t *wt;
     const float   *x;        // fused quantization (M <= 2)
@@ -537,6 +600,10 @@ struct PipeParams {
     int            TS;       // units per task
     int            stages;
     unsigned long long *dbg; // optional timeline (B200Q4_TIMELINE builds), else NULL
+    // Row-sharded launch with the all-gather fused into the epilogue (world > 1): this rank's output
+    // columns are stored straight into every rank's Y over NVLink (peer-mapped pointers), then the last
+    // CTA signals `seq` into slot `rank` of every rank's flag array.
+    PeerOut        peer;
 };
 
 __device__ __forceinline__ unsigned long long gtimer()
@@ -797,20 +864,20 @@ __device__ __forceinline__ void pipe_emit(const PipeParams &p, int T, int task, 
     const int g = lane >> 2, t = lane & 3;
     if (M1) {
         const int n = T * TILE_ROWS + lane;
-        if (lane < TILE_ROWS && n < p.N) p.y[n] = acc[0] * post;
+        if (lane < TILE_ROWS && n < p.N) store_y(p.y, p.peer, n, acc[0] * post);
     } else if (MP == 2) {
         const int m = t & 1, n = T * TILE_ROWS + g + 8 * (t >> 1);
-        if (m < p.M && n < p.N) p.y[(size_t)m * p.y_stride + n] = acc[0] * post;
+        if (m < p.M && n < p.N) store_y(p.y, p.peer, (size_t)m * p.y_stride + n, acc[0] * post);
     } else {
         const int n0 = T * TILE_ROWS + g, n1 = n0 + 8;
         const int m0 = 2 * t, m1 = m0 + 1;
         if (m0 < p.M) {
-            if (n0 < p.N) p.y[(size_t)m0 * p.y_stride + n0] = acc[0] * post;
-            if (n1 < p.N) p.y[(size_t)m0 * p.y_stride + n1] = acc[2] * post;
+            if (n0 < p.N) store_y(p.y, p.peer, (size_t)m0 * p.y_stride + n0, acc[0] * post);
+            if (n1 < p.N) store_y(p.y, p.peer, (size_t)m0 * p.y_stride + n1, acc[2] * post);
         }
         if (m1 < p.M) {
-            if (n0 < p.N) p.y[(size_t)m1 * p.y_stride + n0] = acc[1] * post;
-            if (n1 < p.N) p.y[(size_t)m1 * p.y_stride + n1] = acc[3] * post;
+            if (n0 < p.N) store_y(p.y, p.peer, (size_t)m1 * p.y_stride + n0, acc[1] * post);
+            if (n1 < p.N) store_y(p.y, p.peer, (size_t)m1 * p.y_stride + n1, acc[3] * post);
         }
     }
 }
@@ -972,6 +1039,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (curT >= 0) pipe_emit<QT, MP, M1>(p, curT, curTask, lane, acc);
+        peer_signal(p.peer, lane);
         if (lane == 0) PIPE_STAMP(7);
         return;
     }

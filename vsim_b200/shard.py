@@ -1,0 +1,103 @@
+"""Row-sharded Q4 mul_mat across the GPUs of one node.
+
+The split is the one the reference's threads use (imax.c:1185-1188): rank g of G owns weight rows
+[g*N/G, (g+1)*N/G) of every tensor, X is replicated (each rank quantizes it locally, bit-identically),
+and the fp32 output slices are all-gathered.  No reduction crosses GPUs, so the result equals the
+single-GPU one bit for bit.
+
+Two exchange paths:
+  * PeerOutput    -- the product path on NVLink: symmetric (peer-mapped) Y buffers; the mul_mat kernel's
+                     epilogue stores its slice into every rank's Y and publishes a sequence flag
+                     (b200q4_mul_mat_dev_allgather + b200q4_wait_flags).  No collective call per mul_mat.
+  * all_gather_rows -- torch.distributed all-gather of [M][N/G] slices (NCCL on GPUs, gloo in the CPU
+                     tests of this host logic); the baseline the fused path is measured against.
+torch is used for device memory and process groups only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(n: int, world: int, rank: int) -> tuple[int, int]:
+    """(first row, row count) of rank's shard.  N must divide evenly (every listed model does)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"bad rank {rank} of {world}")
+    if n % world:
+        raise ValueError(f"{n} weight rows do not split evenly over {world} ranks: this tensor stays replicated")
+    return rank * (n // world), n // world
+
+
+def assemble(slices: torch.Tensor) -> torch.Tensor:
+    """[world][M][N/world] gathered slices -> Y [M][N] (rank r's rows are output columns [r*N/G, (r+1)*N/G))."""
+    world, m, ns = slices.shape
+    return slices.permute(1, 0, 2).reshape(m, world * ns)
+
+
+def all_gather_rows(y_local: torch.Tensor, group=None) -> torch.Tensor:
+    """Collective baseline: all-gather the [M][N/world] slices and assemble Y [M][N] on every rank."""
+    world = dist.get_world_size(group)
+    m, ns = y_local.shape
+    out = torch.empty((world * m, ns), dtype=y_local.dtype, device=y_local.device)       # rank-major concatenation
+    dist.all_gather_into_tensor(out, y_local.contiguous(), group=group)
+    return assemble(out.view(world, m, ns))
+
+
+class PeerOutput:
+    """Symmetric Y buffers + arrival flags for the fused all-gather epilogue.
+
+    Two Y buffers alternate: rank A may begin storing call k+1's slice into rank B while B still reads
+    call k's Y as its next input; A cannot reach call k+2 (the same buffer again) before B has finished
+    call k+1, because A's wait for k+1 needs B's flag."""
+
+    def __init__(self, lib, max_m: int, n_total: int, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.L = lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("at most 8 ranks (one NVSwitch domain)")
+        self.max_m, self.n_total = max_m, n_total
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.y, self.y_hdl = [], []
+        for _ in range(2):
+            t = symm.empty(max_m * n_total, dtype=torch.float32, device=dev)
+            self.y.append(t)
+            self.y_hdl.append(symm.rendezvous(t, self.group))
+        self.flags = symm.empty(16, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        self.f_hdl = symm.rendezvous(self.flags, self.group)
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+        vp = C.c_void_p
+        self._yptrs = [(vp * self.world)(*[int(p) for p in h.buffer_ptrs]) for h in self.y_hdl]
+        self._fptrs = (vp * self.world)(*[int(p) for p in self.f_hdl.buffer_ptrs])
+        self.seq = 0
+        self._st = torch.cuda.Stream(device=dev)     # used when the caller is on the legacy default stream
+
+    def mul_mat(self, w, d_x: torch.Tensor, m: int, n_total: int | None = None, stream=None) -> torch.Tensor:
+        """Y[M][n_total] = mul_mat over the row shards of all ranks; `w` is this rank's shard (n_total/world rows)."""
+        n_total = n_total or self.n_total
+        if m > self.max_m or n_total > self.n_total or w.n * self.world != n_total:
+            raise ValueError("shape does not fit the symmetric buffers / shard size")
+        self.seq += 1
+        b = self.seq & 1
+        cur = stream if stream is not None else torch.cuda.current_stream()
+        # The C ABI reads a NULL stream as "the library's own stream", which is not ordered with torch's
+        # legacy default stream: hop onto a private stream, ordered both ways with the caller's.
+        hop = cur.cuda_stream == 0
+        if hop:
+            self._st.wait_stream(cur)
+        st = self._st.cuda_stream if hop else cur.cuda_stream
+        rc = self.L.b200q4_mul_mat_dev_allgather(w.handle, d_x.data_ptr(), m, w.k * 4, self._yptrs[b], self.world, self.rank,
+                                                 self.rank * w.n, n_total * 4, self._fptrs, self.seq, st)
+        if rc == 0:
+            rc = self.L.b200q4_wait_flags(self.flags.data_ptr(), self.world, self.seq, st)
+        if rc:
+            from .lib import B200Q4Error, _err
+            raise B200Q4Error(f"b200q4_mul_mat_dev_allgather failed (rc={rc}): {_err(self.L)}")
+        if hop:
+            cur.wait_stream(self._st)
+        return self.y[b][: m * n_total].view(m, n_total)
