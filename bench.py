@@ -159,7 +159,7 @@ def cpu_baseline(qt: int, m: int, wq: np.ndarray, x: np.ndarray, budget_s: float
 GPTJ_LAYERS, GPTJ_EMBD, GPTJ_FF, GPTJ_VOCAB = 28, 4096, 16384, 50400
 
 
-def model_decode(vs, L, torch, dist, rank, world, stream, peak, tokens=24):
+def model_decode(vs, L, torch, dist, rank, world, stream, peak, use_nccl, tokens=24):
     """GPT-J-6B-shaped decode: the 28 x 6 + 1 Q4_0 mul_mats of one token (M=1), device-resident, back to back.
     Only the hot path of this repository -- norms, rope, attention and sampling of the reference graph are
     not run -- so this is the mul_mat share of a token, an upper bound on tok/s.
@@ -180,8 +180,15 @@ def model_decode(vs, L, torch, dist, rank, world, stream, peak, tokens=24):
     d_in = torch.randn(1, F, device="cuda", dtype=torch.float32)
     d_out = torch.empty(1, max(F, V), device="cuda", dtype=torch.float32)
     d_full = torch.empty(world, max(F, V) // world, device="cuda", dtype=torch.float32)
+    po = None
+    if world > 1 and not use_nccl:
+        from vsim_b200.shard import PeerOutput
+        po = PeerOutput(L, 1, max(F, V))
 
     def one(w, n, k, st):
+        if po is not None:                                 # all-gather fused into the kernel epilogue; the next call waits for it
+            po.mul_mat(w, d_in, 1, n_total=n, stream=st, wait=False)
+            return
         rc = L.b200q4_mul_mat_dev(w.handle, d_in.data_ptr(), 1, k * 4, d_out.data_ptr(), (n // world) * 4, st.cuda_stream)
         if rc:
             raise RuntimeError(vs.lib._err(L))
@@ -194,16 +201,32 @@ def model_decode(vs, L, torch, dist, rank, world, stream, peak, tokens=24):
                 one(lw[j], n, k, st)
         one(head, V, E, st)
 
+    mode = "eager launches"
     with torch.cuda.stream(stream):
         for _ in range(3):
             token(stream)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        run = lambda: token(stream)
+        if po is not None or world == 1:                   # (an NCCL collective per mul_mat is left eager)
+            try:                                           # one token = one CUDA graph: 169 launches replayed without host work
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    token(stream)
+                graph.replay()
+                torch.cuda.synchronize()
+                run = graph.replay
+                mode = "one CUDA graph per token"
+            except Exception as e:                         # noqa: BLE001
+                mode = f"eager launches (graph capture failed: {type(e).__name__})"
+                torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(tokens):
-            token(stream)
+            run()
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / tokens
@@ -220,8 +243,10 @@ def model_decode(vs, L, torch, dist, rank, world, stream, peak, tokens=24):
             "scope": "the 169 Q4_0 mul_mats of one decode step only (no norm/rope/attention/sampling): mul_mat share of a token",
             "tok_per_s": 1e3 / ms, "ms_per_token": ms, "mul_mats_per_token": GPTJ_LAYERS * 6 + 1,
             "weight_bytes_per_gpu": int(wbytes), "weight_GBps_per_gpu": gbs, "frac_hbm_peak": gbs / peak,
-            "parallelism": "single GPU" if world == 1 else f"row shards over {world} GPUs + NCCL all-gather per mul_mat",
-            "tokens_timed": tokens}
+            "parallelism": "single GPU" if world == 1 else
+                           f"row shards over {world} GPUs + " + ("NCCL all-gather per mul_mat" if use_nccl else
+                                                               "all-gather fused into the mul_mat epilogue (peer stores over NVLink + flags)"),
+            "tokens_timed": tokens, "launch": mode}
 
 
 def prefill_roofline(points, tpeak, tpeak_src, world):
@@ -294,6 +319,7 @@ def main() -> int:
     ap.add_argument("--no-points", action="store_true", help="skip the (type, M) sweep")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-model", action="store_true", help="skip the GPT-J-6B-shaped decode leg")
+    ap.add_argument("--nccl", action="store_true", help="N>1: exchange output slices with an NCCL all-gather instead of the fused epilogue")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -333,9 +359,17 @@ def main() -> int:
     d_yloc = torch.empty(512, N_ROWS, device="cuda", dtype=torch.float32)
     handles0 = (C.c_void_p * nw)(*[w.handle for w in w0])
 
-    def step(i: int, m: int, ws, st):
+    po = None
+    if world > 1 and not args.nccl:
+        from vsim_b200.shard import PeerOutput
+        po = PeerOutput(L, 512, N_ROWS * world)
+
+    def step(i: int, m: int, ws, st, nccl=False):
         """one pass of the hot path on device-resident inputs (+ the all-gather of output slices at N>1)"""
         w = ws[i % len(ws)]
+        if po is not None and not nccl:                    # N>1 product path: slices stored straight into every rank's Y;
+            po.mul_mat(w, d_x, m, stream=st, wait=False)   # the next step's kernel waits for this exchange before it reads X
+            return
         rc = L.b200q4_mul_mat_dev(w.handle, d_x.data_ptr(), m, K_DIM * 4, d_yloc.data_ptr(), N_ROWS * 4, st.cuda_stream)
         if rc:
             raise RuntimeError(vs.lib._err(L))
@@ -343,15 +377,15 @@ def main() -> int:
             # Y is [M][N_total]: rank r's slice is columns [r*N, (r+1)*N); gather as [world][M][N]
             dist.all_gather_into_tensor(d_y.view(-1)[: world * m * N_ROWS].view(world, m, N_ROWS), d_yloc[:m])
 
-    def timed(m: int, ws, steps: int, warm: int):
+    def timed(m: int, ws, steps: int, warm: int, nccl=False):
         with torch.cuda.stream(stream):
             for i in range(warm):
-                step(i, m, ws, stream)
+                step(i, m, ws, stream, nccl)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for i in range(steps):
-                step(warm + i, m, ws, stream)
+                step(warm + i, m, ws, stream, nccl)
             e1.record(stream)
             barrier()
             ms = e0.elapsed_time(e1)
@@ -420,9 +454,14 @@ def main() -> int:
                                "kernel": vs.kernel_for(qt, m, N_ROWS, K_DIM)})
         for w in w1:
             w.free()
+    exchange = None
+    if world > 1 and po is not None:                       # the same M=1 step with an NCCL all-gather, for comparison
+        ms_nccl = timed(M_HEAD, w0, min(args.steps, 200), 5, nccl=True) / min(args.steps, 200)
+        exchange = {"fused_peer_store_us_per_step": ms_step * 1e3, "nccl_all_gather_us_per_step": ms_nccl * 1e3,
+                    "bytes_per_rank_per_step": M_HEAD * N_ROWS * 4}
     model = None
     if not args.no_model:
-        model = model_decode(vs, L, torch, dist, rank, world, stream, peak)
+        model = model_decode(vs, L, torch, dist, rank, world, stream, peak, args.nccl)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -446,7 +485,9 @@ def main() -> int:
                 "l2": f"defeated: every loop rotates over {nw} distinct {alg_bytes(0, 0) / 1e6:.0f} MB weight tensors "
                       f"({nw * alg_bytes(0, 0) / 1e6:.0f} MB > 3x the 126 MB L2)",
                 "parallelism": "single GPU" if world == 1 else
-                               f"{world}-way row shard of a {N_ROWS * world}-row tensor + NCCL all-gather of fp32 output slices",
+                               f"{world}-way row shard of a {N_ROWS * world}-row tensor; fp32 output slices " +
+                               ("all-gathered with NCCL" if po is None else
+                                "stored into every rank's Y by the kernel epilogue (peer memory over NVLink) + sequence flags"),
                 "kernel": vs.kernel_for(0, M_HEAD, N_ROWS, K_DIM),
                 "frac_hbm_peak": value / (peak * world),
             },
@@ -463,6 +504,7 @@ def main() -> int:
             "points": points,
             "roofline_prefill": prefill_roofline(points, tpeak, tpeak_src, world),
             "model_decode": model,
+            "exchange": exchange,
             "checksum_y": float(np.abs(y_e2e).sum()),
         }
         if cpu is not None:

@@ -127,19 +127,28 @@ int b200q4_quantize_rows_dev(int type, const float *d_x, int M, int K, size_t x_
  * (imax.c:1185-1188: thread ith owns rows [ith*ceil(N/nth), ...)); here rank
  * `rank` of `world` GPUs owns the shard `w` (b200q4_weight_upload_rows), X is
  * replicated, and the kernel's epilogue stores this rank's output columns
- * [col0, col0 + rows(w)) straight into EVERY rank's Y over NVLink:
- * y_peers[r] is rank r's Y base (M rows, y_stride bytes apart) mapped into this
- * process (CUDA IPC / symmetric memory; y_peers[rank] is local).  When the last
- * store of the launch is out, `seq` is written to flag_peers[r][rank] for every
- * r.  b200q4_wait_flags() then holds `stream` until local_flags[0..world) have
- * all reached seq, i.e. until every rank's slice has landed in this rank's Y.
+ * [col0, col0 + rows(w)) straight into EVERY rank's Y over NVLink.
+ *   y_peers[b*world + r]  rank r's Y buffer b (b = 0, 1; M rows, y_stride bytes
+ *                         apart) mapped into this process (CUDA IPC / symmetric
+ *                         memory; entry `rank` is local).  Two buffers alternate.
+ *   flag_peers[r]         rank r's arrival flags (uint32[world]), likewise mapped.
+ *   seq_counter           a zero-initialised uint32 in THIS rank's memory.  The
+ *                         sequencing is on the device (no per-call host value, so
+ *                         calls can be captured in a CUDA graph): exchange number
+ *                         s = *seq_counter + 1 goes to buffer s & 1; when the last
+ *                         store is out, s is written to flag_peers[r][rank] for all
+ *                         r and to *seq_counter.
+ * Before it reads X a call waits until exchange *seq_counter (the previous one,
+ * normally the producer of its X) has landed from every rank.  The consumer of
+ * the LAST exchange of a chain calls b200q4_wait_flags(), which holds `stream`
+ * until flag_peers[rank][0..world) have all reached *seq_counter.
  * No reduction crosses GPUs: the result equals the single-GPU one bit for bit.
  * world <= 8.  Decode shapes (M <= 8) store from the GEMV epilogue itself;
  * larger M computes the slice locally and a copy kernel scatters it.        */
 int b200q4_mul_mat_dev_allgather(const b200q4_weight *w, const float *d_x, int M, size_t x_stride,
                                  float *const *y_peers, int world, int rank, int col0, size_t y_stride,
-                                 uint32_t *const *flag_peers, uint32_t seq, void *stream);
-int b200q4_wait_flags(const uint32_t *local_flags, int world, uint32_t seq, void *stream);
+                                 uint32_t *const *flag_peers, uint32_t *seq_counter, void *stream);
+int b200q4_wait_flags(const uint32_t *local_flags, int world, const uint32_t *seq_counter, void *stream);
 int b200q4_sync(void *stream);
 
 /* Pinned host memory for callers that want zero-staging H2D/D2H copies.      */

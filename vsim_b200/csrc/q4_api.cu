@@ -50,6 +50,8 @@ struct Ctx {
     uint8_t *d_tpack = nullptr; size_t tpack_cap = 0;           // tile kernel: activation stages
     float *d_tpartial = nullptr; size_t tpartial_cap = 0;        // tile kernel: split-K pieces
     int *d_tcounters = nullptr; size_t tcounters_cap = 0;        // tile kernel: split-K arrival counters (self-resetting)
+    int fuse_max_k = 1 << 30;        // B200Q4_FUSE_MAX_K: longer rows are quantized by a separate pack kernel instead of every CTA's prologue
+    int fuse_max_k = 1 << 30;        // B200Q4_FUSE_MAX_K: longer rows are quantized by a separate pack kernel instead of every CTA's prologue
     int tile_min_m = 9;              // M >= this runs the tcgen05 tile kernel, below it the decode kernel (B200Q4_TILE_MIN_M overrides; 0 = never)
     uint64_t launches = 0;
     std::recursive_mutex mu;
@@ -314,8 +316,11 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
     if ((long)w->n_tiles * w->C > 0x7fffffffL) return fail(B200Q4_EINVAL, "tensor too large");
     if (g.tile_min_m > 0 && M >= g.tile_min_m) {
         if (!peer) return run_tile(w, d_x, x_stride / 4, d_wdata, M, d_y, y_stride / 4, st);
-        // sharded: the tile kernel writes this rank's slice locally, a copy kernel stores it into every rank's Y
+        // sharded: wait for the previous exchange (X), let the tile kernel write this rank's slice locally,
+        // then a copy kernel stores it into every rank's Y
         if (int rc = ensure(g.d_yloc, g.yloc_cap, (size_t)M * w->N * sizeof(float))) return rc;
+        wait_flags_kernel<<<1, 32, 0, st>>>(peer->local_flags, peer->world, peer->seq_ctr);
+        g.launches++;
         if (int rc = run_tile(w, d_x, x_stride / 4, d_wdata, M, g.d_yloc, (size_t)w->N, st)) return rc;
         const long total = (long)M * w->N;
         int blocks = (int)((total + 255) / 256);
@@ -327,7 +332,7 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
     }
     const int nbp = w->C * CHUNK_BLKS;
     // the fused prologue reads X with 128-bit loads
-    const bool can_fuse = !d_wdata && d_x && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0) && (x_stride % 16 == 0);
+    const bool can_fuse = !d_wdata && d_x && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0) && (x_stride % 16 == 0) && w->K <= g.fuse_max_k;
     const PipePlan pp = pipe_plan(w, M, can_fuse);
     const int MP = pp.MP;
     if (MP < 1) return fail(B200Q4_EINVAL, "mul_mat: K=%d too large for the shared-memory activation pack", w->K);
@@ -357,7 +362,9 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
         PeerOut po;
         if (peer) {                                      // rows m0.. of every rank's Y; only the last launch signals
             po = *peer;
-            for (int r = 0; r < po.world; r++) po.y[r] = reinterpret_cast<float *>(reinterpret_cast<char *>(po.y[r]) + (size_t)m0 * y_stride);
+            for (int b = 0; b < 2; b++)
+                for (int r = 0; r < po.world; r++)
+                    po.y[b][r] = reinterpret_cast<float *>(reinterpret_cast<char *>(po.y[b][r]) + (size_t)m0 * y_stride);
             if (m0 + MP < M) po.done = nullptr;
         }
         if ((rc = run_pipe(w, mc, pp, fused, xs, x_stride / 4, yo, y_stride / 4, st, peer ? &po : nullptr))) return rc;
@@ -453,6 +460,8 @@ int b200q4_init(int device)
     CK(cudaMemset(g.d_done, 0, sizeof(int)));
     if (const char *e = getenv("B200Q4_PDL")) g.use_pdl = atoi(e) != 0;
     if (const char *e = getenv("B200Q4_TILE_MIN_M")) g.tile_min_m = atoi(e);
+    if (const char *e = getenv("B200Q4_FUSE_MAX_K")) g.fuse_max_k = atoi(e);
+    if (const char *e = getenv("B200Q4_FUSE_MAX_K")) g.fuse_max_k = atoi(e);
     if (const char *e = getenv("B200Q4_DBG")) if (atoi(e) != 0) {
         CK(cudaMalloc(&g.d_dbg, 256 * 16 * sizeof(unsigned long long)));
         CK(cudaMemset(g.d_dbg, 0, 256 * 16 * sizeof(unsigned long long)));
@@ -571,30 +580,31 @@ int b200q4_mul_mat_dev(const b200q4_weight *w, const float *d_x, int M, size_t x
 
 int b200q4_mul_mat_dev_allgather(const b200q4_weight *w, const float *d_x, int M, size_t x_stride,
                                  float *const *y_peers, int world, int rank, int col0, size_t y_stride,
-                                 uint32_t *const *flag_peers, uint32_t seq, void *stream)
+                                 uint32_t *const *flag_peers, uint32_t *seq_counter, void *stream)
 {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (int rc = need_init()) return rc;
-    if (!w || !y_peers || !flag_peers || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || col0 < 0)
+    if (!w || !y_peers || !flag_peers || !seq_counter || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || col0 < 0)
         return fail(B200Q4_EINVAL, "mul_mat_dev_allgather: bad argument (world=%d rank=%d)", world, rank);
     if (x_stride == 0) x_stride = (size_t)w->K * 4;
     if (y_stride < (size_t)(col0 + w->N) * 4) return fail(B200Q4_EINVAL, "mul_mat_dev_allgather: y_stride smaller than col0 + shard rows");
     cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
     PeerOut po{};
     for (int r = 0; r < world; r++) {
-        if (!y_peers[r] || !flag_peers[r]) return fail(B200Q4_EINVAL, "mul_mat_dev_allgather: NULL peer pointer");
-        po.y[r] = y_peers[r]; po.flag[r] = flag_peers[r];
+        if (!y_peers[r] || !y_peers[world + r] || !flag_peers[r]) return fail(B200Q4_EINVAL, "mul_mat_dev_allgather: NULL peer pointer");
+        po.y[0][r] = y_peers[r]; po.y[1][r] = y_peers[world + r]; po.flag[r] = flag_peers[r];
     }
-    po.done = g.d_done; po.world = world; po.rank = rank; po.col0 = col0; po.seq = seq;
-    if (M == 0 || w->N == 0) {                           // nothing to store: still publish the sequence number
-        scatter_slice_kernel<<<1, 32, 0, st>>>(nullptr, 0, 0, 0, y_stride / 4, po);
-        g.launches++;
-        CK(cudaGetLastError());
-        return B200Q4_OK;
-    }
-    // a single rank degenerates to the plain call on its own buffer (PeerOut.world == 1 stores through p.y)
-    if (world == 1) {
-        if (int rc = mul_mat_dev_locked(w, d_x, M, x_stride, y_peers[0] + col0, y_stride, st, nullptr)) return rc;
+    po.local_flags = flag_peers[rank]; po.seq_ctr = seq_counter;
+    po.done = g.d_done; po.world = world; po.rank = rank; po.col0 = col0;
+    if (M == 0 || w->N == 0 || world == 1) {
+        // nothing to exchange: a single rank runs the plain kernel on the buffer the sequence number selects
+        // (the host mirrors the counter: exchange s uses buffer s & 1), then publishes like any other launch
+        if (world == 1 && M > 0 && w->N > 0) {
+            uint32_t seq_now = 0;
+            CK(cudaMemcpyAsync(&seq_now, seq_counter, sizeof seq_now, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (int rc = mul_mat_dev_locked(w, d_x, M, x_stride, y_peers[((seq_now + 1) & 1u) ? world : 0] + col0, y_stride, st, nullptr)) return rc;
+        }
         scatter_slice_kernel<<<1, 32, 0, st>>>(nullptr, 0, 0, 0, y_stride / 4, po);
         g.launches++;
         CK(cudaGetLastError());
@@ -603,12 +613,12 @@ int b200q4_mul_mat_dev_allgather(const b200q4_weight *w, const float *d_x, int M
     return mul_mat_dev_locked(w, d_x, M, x_stride, nullptr, y_stride, st, nullptr, &po);
 }
 
-int b200q4_wait_flags(const uint32_t *local_flags, int world, uint32_t seq, void *stream)
+int b200q4_wait_flags(const uint32_t *local_flags, int world, const uint32_t *seq_counter, void *stream)
 {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (int rc = need_init()) return rc;
-    if (!local_flags || world < 1 || world > MAX_PEERS) return fail(B200Q4_EINVAL, "wait_flags: bad argument");
-    wait_flags_kernel<<<1, 32, 0, stream ? (cudaStream_t)stream : g.stream>>>(local_flags, world, seq);
+    if (!local_flags || !seq_counter || world < 1 || world > MAX_PEERS) return fail(B200Q4_EINVAL, "wait_flags: bad argument");
+    wait_flags_kernel<<<1, 32, 0, stream ? (cudaStream_t)stream : g.stream>>>(local_flags, world, seq_counter);
     g.launches++;
     CK(cudaGetLastError());
     return B200Q4_OK;

@@ -522,22 +522,45 @@ constexpr int PIPE_MAX_STAGES = 6;
 constexpr int PIPE_STATIC_TASKS = 3;                    // per CTA, before the first ticket is drawn
 
 constexpr int MAX_PEERS = 8;
+// Fused all-gather state.  Sequencing lives on the device so that a launch (or a captured CUDA graph of
+// launches) needs no per-call host values: *seq_ctr counts this rank's completed exchanges; exchange
+// number s = *seq_ctr + 1 stores into Y buffer s & 1 (two buffers alternate: a fast rank may already be
+// storing exchange s+1 into a peer that still reads exchange s as its next input) and publishes s in
+// slot `rank` of every rank's flag array.  A launch first waits until all of exchange *seq_ctr has landed
+// locally -- its X is normally that exchange's Y.
 struct PeerOut {
-    float    *y[MAX_PEERS];      // rank r's full Y [M][y_stride] (y[rank] is local memory)
+    float    *y[2][MAX_PEERS];   // [buffer][rank]: rank r's full Y [M][y_stride] (y[.][rank] is local memory)
     uint32_t *flag[MAX_PEERS];   // rank r's arrival flags [world]
-    int      *done;              // local CTA-completion counter (self-resetting)
+    const uint32_t *local_flags; // this rank's flag array (= flag[rank])
+    uint32_t *seq_ctr;           // local exchange counter
+    int      *done;              // local CTA-completion counter (self-resetting); NULL: do not signal
     int       world, rank, col0; // col0: first output column of this rank's shard
-    uint32_t  seq;
 };
 
-// one output element: locally, or into every rank's Y at this shard's column offset
-__device__ __forceinline__ void store_y(float *y, const PeerOut &po, size_t idx, float v)
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until rank r's flag has reached `exp` (call with r < world)
+__device__ __forceinline__ void peer_wait_one(const uint32_t *flags, int r, uint32_t exp)
+{
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+        if ((int32_t)(v - exp) >= 0) break;
+        __nanosleep(32);
+    }
+}
+// one output element: locally, or into every rank's Y (buffer b) at this shard's column offset
+__device__ __forceinline__ void store_y(float *y, const PeerOut &po, int b, size_t idx, float v)
 {
     if (po.world <= 1) { y[idx] = v; return; }
 #pragma unroll 1
-    for (int r = 0; r < po.world; r++) po.y[r][idx + po.col0] = v;
+    for (int r = 0; r < po.world; r++) po.y[b][r][idx + po.col0] = v;
 }
-// after a CTA's last store: the last CTA of the launch publishes the sequence number to every rank
+// after a CTA's last store: the last CTA of the launch publishes the exchange number to every rank
 __device__ __forceinline__ void peer_signal(const PeerOut &po, int lane)
 {
     if (po.world <= 1 || !po.done) return;               // done == NULL: an earlier launch of a multi-launch call
@@ -547,40 +570,40 @@ __device__ __forceinline__ void peer_signal(const PeerOut &po, int lane)
         if (atomicAdd(po.done, 1) == (int)gridDim.x - 1) {
             *po.done = 0;
             __threadfence_system();
+            const uint32_t seq = ld_volatile_u32(po.seq_ctr) + 1;
             for (int r = 0; r < po.world; r++)
-                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(po.flag[r] + po.rank), "r"(po.seq) : "memory");
+                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(po.flag[r] + po.rank), "r"(seq) : "memory");
+            *po.seq_ctr = seq;
         }
     }
 }
-// blocks the stream until every rank's flag has reached seq (lane r watches rank r)
-__global__ void wait_flags_kernel(const uint32_t *flags, int world, uint32_t seq)
+// holds the stream until exchange *seq_ctr has landed from every rank (lane r watches rank r)
+__global__ void wait_flags_kernel(const uint32_t *flags, int world, const uint32_t *seq_ctr)
 {
     const int r = threadIdx.x;
     if (r >= world) return;
-    for (;;) {
-        uint32_t v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
-        if ((int32_t)(v - seq) >= 0) break;
-        __nanosleep(32);
-    }
+    peer_wait_one(flags, r, ld_volatile_u32(seq_ctr));
 }
 // unfused variant for launches whose kernel has no peer epilogue (the tile kernel): copies this rank's
 // [M][ncols] slice from a local buffer into every rank's Y, then signals like peer_signal
 __global__ void scatter_slice_kernel(const float *__restrict__ src, size_t src_stride, int M, int ncols, size_t y_stride, PeerOut po)
 {
+    const int b = (int)((ld_volatile_u32(po.seq_ctr) + 1) & 1u);
     const long total = (long)M * ncols;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int m = (int)(i / ncols), n = (int)(i - (long)m * ncols);
         const float v = src[(size_t)m * src_stride + n];
-        for (int r = 0; r < po.world; r++) po.y[r][(size_t)m * y_stride + po.col0 + n] = v;
+        for (int r = 0; r < po.world; r++) po.y[b][r][(size_t)m * y_stride + po.col0 + n] = v;
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0 && atomicAdd(po.done, 1) == (int)gridDim.x - 1) {
         *po.done = 0;
         __threadfence_system();
+        const uint32_t seq = ld_volatile_u32(po.seq_ctr) + 1;
         for (int r = 0; r < po.world; r++)
-            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(po.flag[r] + po.rank), "r"(po.seq) : "memory");
+            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(po.flag[r] + po.rank), "r"(seq) : "memory");
+        *po.seq_ctr = seq;
     }
 }
 
@@ -837,7 +860,7 @@ __device__ __forceinline__ void compute_octet(const uint8_t *chE, const uint8_t 
 //   MP == 2: lane (g, r) carries row g + 8*(r>>1), activation row m = r&1;
 //   MP == 8: lane (g, t) carries rows g/g+8 x m = 2t, 2t+1 in acc[0..3].
 template <int QT, int MP, bool M1>
-__device__ __forceinline__ void pipe_emit(const PipeParams &p, int T, int task, int lane, float (&acc)[4])
+__device__ __forceinline__ void pipe_emit(const PipeParams &p, int T, int task, int lane, float (&acc)[4], int pb)
 {
     constexpr int NV = (MP == 2) ? 1 : 4;
     if (p.C >= PIPE_TILE_SPLIT && p.PP > 1) {           // the tile is split over PP tasks
@@ -864,20 +887,20 @@ __device__ __forceinline__ void pipe_emit(const PipeParams &p, int T, int task, 
     const int g = lane >> 2, t = lane & 3;
     if (M1) {
         const int n = T * TILE_ROWS + lane;
-        if (lane < TILE_ROWS && n < p.N) store_y(p.y, p.peer, n, acc[0] * post);
+        if (lane < TILE_ROWS && n < p.N) store_y(p.y, p.peer, pb, n, acc[0] * post);
     } else if (MP == 2) {
         const int m = t & 1, n = T * TILE_ROWS + g + 8 * (t >> 1);
-        if (m < p.M && n < p.N) store_y(p.y, p.peer, (size_t)m * p.y_stride + n, acc[0] * post);
+        if (m < p.M && n < p.N) store_y(p.y, p.peer, pb, (size_t)m * p.y_stride + n, acc[0] * post);
     } else {
         const int n0 = T * TILE_ROWS + g, n1 = n0 + 8;
         const int m0 = 2 * t, m1 = m0 + 1;
         if (m0 < p.M) {
-            if (n0 < p.N) store_y(p.y, p.peer, (size_t)m0 * p.y_stride + n0, acc[0] * post);
-            if (n1 < p.N) store_y(p.y, p.peer, (size_t)m0 * p.y_stride + n1, acc[2] * post);
+            if (n0 < p.N) store_y(p.y, p.peer, pb, (size_t)m0 * p.y_stride + n0, acc[0] * post);
+            if (n1 < p.N) store_y(p.y, p.peer, pb, (size_t)m0 * p.y_stride + n1, acc[2] * post);
         }
         if (m1 < p.M) {
-            if (n0 < p.N) store_y(p.y, p.peer, (size_t)m1 * p.y_stride + n0, acc[1] * post);
-            if (n1 < p.N) store_y(p.y, p.peer, (size_t)m1 * p.y_stride + n1, acc[3] * post);
+            if (n0 < p.N) store_y(p.y, p.peer, pb, (size_t)m1 * p.y_stride + n0, acc[1] * post);
+            if (n1 < p.N) store_y(p.y, p.peer, pb, (size_t)m1 * p.y_stride + n1, acc[3] * post);
         }
     }
 }
@@ -973,6 +996,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
     if (warp == PIPE_CONSUMERS + 1) {
         // ===================== reducer =====================
         cudaGridDependencySynchronize();
+        const int pb = p.peer.world > 1 ? (int)((ld_volatile_u32(p.peer.seq_ctr) + 1) & 1u) : 0;   // this exchange's Y buffer
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         int curT = -1, curTask = -1;
         int s = 0;
@@ -994,7 +1018,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             int j = 0;
             while (j < dsc.x) {
                 if (T != curT || task != curTask) {
-                    if (curT >= 0) pipe_emit<QT, MP, M1>(p, curT, curTask, lane, acc);
+                    if (curT >= 0) pipe_emit<QT, MP, M1>(p, curT, curTask, lane, acc, pb);
                     acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
                     curT = T; curTask = task;
                 }
@@ -1038,7 +1062,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             if (lane == 0) mbar_arrive(&bar_empty[s]);
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        if (curT >= 0) pipe_emit<QT, MP, M1>(p, curT, curTask, lane, acc);
+        if (curT >= 0) pipe_emit<QT, MP, M1>(p, curT, curTask, lane, acc, pb);
         peer_signal(p.peer, lane);
         if (lane == 0) PIPE_STAMP(7);
         return;
@@ -1073,6 +1097,11 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
         }
     }
     cudaGridDependencySynchronize();                     // X may be the previous kernel's output
+    if (p.peer.world > 1) {
+        // ... or the previous exchange's Y: wait until every rank's slice of it has landed here
+        if (ctid < p.peer.world) peer_wait_one(p.peer.local_flags, ctid, ld_volatile_u32(p.peer.seq_ctr));
+        asm volatile("bar.sync 1, %0;" :: "n"(CTHREADS) : "memory");
+    }
     if constexpr (FUSED) {
         // Issue the activation loads first (one item = 8 consecutive elements of one block; the
         // first FUSED_ITEMS items of a thread are held in registers) so that their L2 latency

@@ -78,8 +78,8 @@ def load_library(build: bool = True) -> C.CDLL:
         "b200q4_mul_mat_dev": (i, [vp, vp, i, sz, vp, sz, vp]),
         "b200q4_quantize_rows_dev": (i, [i, vp, i, i, sz, vp, vp]),
         "b200q4_sync": (i, [vp]),
-        "b200q4_mul_mat_dev_allgather": (i, [vp, vp, i, sz, C.POINTER(vp), i, i, i, sz, C.POINTER(vp), C.c_uint32, vp]),
-        "b200q4_wait_flags": (i, [vp, i, C.c_uint32, vp]),
+        "b200q4_mul_mat_dev_allgather": (i, [vp, vp, i, sz, C.POINTER(vp), i, i, i, sz, C.POINTER(vp), vp, vp]),
+        "b200q4_wait_flags": (i, [vp, i, vp, vp]),
         "b200q4_host_alloc": (vp, [sz]),
         "b200q4_host_free": (None, [vp]),
         "b200q4_launch_count": (C.c_uint64, []),

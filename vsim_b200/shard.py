@@ -48,9 +48,11 @@ def all_gather_rows(y_local: torch.Tensor, group=None) -> torch.Tensor:
 class PeerOutput:
     """Symmetric Y buffers + arrival flags for the fused all-gather epilogue.
 
-    Two Y buffers alternate: rank A may begin storing call k+1's slice into rank B while B still reads
-    call k's Y as its next input; A cannot reach call k+2 (the same buffer again) before B has finished
-    call k+1, because A's wait for k+1 needs B's flag."""
+    Two Y buffers alternate: rank A may begin storing exchange s+1 into rank B while B still reads
+    exchange s as its next input; A cannot reach exchange s+2 (the same buffer again) before B has
+    finished s+1, because every call first waits for the previous exchange to have landed from all ranks.
+    The exchange counter lives on the device (calls can be captured in a CUDA graph); this object mirrors
+    it on the host to know which buffer a call's result is in."""
 
     def __init__(self, lib, max_m: int, n_total: int, group=None):
         import torch.distributed._symmetric_memory as symm
@@ -69,35 +71,50 @@ class PeerOutput:
         self.flags = symm.empty(16, dtype=torch.int32, device=dev)
         self.flags.zero_()
         self.f_hdl = symm.rendezvous(self.flags, self.group)
+        self.seq_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
         torch.cuda.synchronize()
         dist.barrier(self.group)
         vp = C.c_void_p
-        self._yptrs = [(vp * self.world)(*[int(p) for p in h.buffer_ptrs]) for h in self.y_hdl]
+        self._yptrs = (vp * (2 * self.world))(*[int(p) for h in self.y_hdl for p in h.buffer_ptrs])     # [buffer][rank]
         self._fptrs = (vp * self.world)(*[int(p) for p in self.f_hdl.buffer_ptrs])
-        self.seq = 0
+        self.seq = 0                                 # host mirror of the device counter
         self._st = torch.cuda.Stream(device=dev)     # used when the caller is on the legacy default stream
 
-    def mul_mat(self, w, d_x: torch.Tensor, m: int, n_total: int | None = None, stream=None) -> torch.Tensor:
-        """Y[M][n_total] = mul_mat over the row shards of all ranks; `w` is this rank's shard (n_total/world rows)."""
-        n_total = n_total or self.n_total
-        if m > self.max_m or n_total > self.n_total or w.n * self.world != n_total:
-            raise ValueError("shape does not fit the symmetric buffers / shard size")
-        self.seq += 1
-        b = self.seq & 1
+    def _stream(self, stream):
         cur = stream if stream is not None else torch.cuda.current_stream()
         # The C ABI reads a NULL stream as "the library's own stream", which is not ordered with torch's
         # legacy default stream: hop onto a private stream, ordered both ways with the caller's.
         hop = cur.cuda_stream == 0
         if hop:
             self._st.wait_stream(cur)
-        st = self._st.cuda_stream if hop else cur.cuda_stream
-        rc = self.L.b200q4_mul_mat_dev_allgather(w.handle, d_x.data_ptr(), m, w.k * 4, self._yptrs[b], self.world, self.rank,
-                                                 self.rank * w.n, n_total * 4, self._fptrs, self.seq, st)
-        if rc == 0:
-            rc = self.L.b200q4_wait_flags(self.flags.data_ptr(), self.world, self.seq, st)
+        return cur, hop, (self._st.cuda_stream if hop else cur.cuda_stream)
+
+    def _check(self, rc):
         if rc:
             from .lib import B200Q4Error, _err
-            raise B200Q4Error(f"b200q4_mul_mat_dev_allgather failed (rc={rc}): {_err(self.L)}")
+            raise B200Q4Error(f"fused all-gather call failed (rc={rc}): {_err(self.L)}")
+
+    def mul_mat(self, w, d_x: torch.Tensor, m: int, n_total: int | None = None, stream=None, wait: bool = True) -> torch.Tensor:
+        """Y[M][n_total] = mul_mat over the row shards of all ranks; `w` is this rank's shard (n_total/world rows).
+        wait=False: the next call on this object consumes the result (it waits for the exchange itself);
+        wait=True: the stream is held until every rank's slice has landed (for any other consumer)."""
+        n_total = n_total or self.n_total
+        if m > self.max_m or n_total > self.n_total or w.n * self.world != n_total:
+            raise ValueError("shape does not fit the symmetric buffers / shard size")
+        cur, hop, st = self._stream(stream)
+        self.seq += 1
+        b = self.seq & 1
+        self._check(self.L.b200q4_mul_mat_dev_allgather(w.handle, d_x.data_ptr(), m, w.k * 4, self._yptrs, self.world, self.rank,
+                                                        self.rank * w.n, n_total * 4, self._fptrs, self.seq_ctr.data_ptr(), st))
+        if wait:
+            self._check(self.L.b200q4_wait_flags(self.flags.data_ptr(), self.world, self.seq_ctr.data_ptr(), st))
         if hop:
             cur.wait_stream(self._st)
         return self.y[b][: m * n_total].view(m, n_total)
+
+    def wait(self, stream=None):
+        """Hold the stream until the latest exchange has landed from every rank."""
+        cur, hop, st = self._stream(stream)
+        self._check(self.L.b200q4_wait_flags(self.flags.data_ptr(), self.world, self.seq_ctr.data_ptr(), st))
+        if hop:
+            cur.wait_stream(self._st)
