@@ -51,7 +51,6 @@ struct Ctx {
     float *d_tpartial = nullptr; size_t tpartial_cap = 0;        // tile kernel: split-K pieces
     int *d_tcounters = nullptr; size_t tcounters_cap = 0;        // tile kernel: split-K arrival counters (self-resetting)
     int fuse_max_k = 1 << 30;        // B200Q4_FUSE_MAX_K: longer rows are quantized by a separate pack kernel instead of every CTA's prologue
-    int fuse_max_k = 1 << 30;        // B200Q4_FUSE_MAX_K: longer rows are quantized by a separate pack kernel instead of every CTA's prologue
     int tile_min_m = 9;              // M >= this runs the tcgen05 tile kernel, below it the decode kernel (B200Q4_TILE_MIN_M overrides; 0 = never)
     uint64_t launches = 0;
     std::recursive_mutex mu;
@@ -460,7 +459,6 @@ int b200q4_init(int device)
     CK(cudaMemset(g.d_done, 0, sizeof(int)));
     if (const char *e = getenv("B200Q4_PDL")) g.use_pdl = atoi(e) != 0;
     if (const char *e = getenv("B200Q4_TILE_MIN_M")) g.tile_min_m = atoi(e);
-    if (const char *e = getenv("B200Q4_FUSE_MAX_K")) g.fuse_max_k = atoi(e);
     if (const char *e = getenv("B200Q4_FUSE_MAX_K")) g.fuse_max_k = atoi(e);
     if (const char *e = getenv("B200Q4_DBG")) if (atoi(e) != 0) {
         CK(cudaMalloc(&g.d_dbg, 256 * 16 * sizeof(unsigned long long)));
