@@ -131,17 +131,21 @@ int b200q4_quantize_rows_dev(int type, const float *d_x, int M, int K, size_t x_
  *   y_peers[b*world + r]  rank r's Y buffer b (b = 0, 1; M rows, y_stride bytes
  *                         apart) mapped into this process (CUDA IPC / symmetric
  *                         memory; entry `rank` is local).  Two buffers alternate.
- *   flag_peers[r]         rank r's arrival flags (uint32[world]), likewise mapped.
+ *   flag_peers[r]         rank r's arrival counters (zero-initialised uint32[world]),
+ *                         likewise mapped: slot `src` counts what rank `src` has
+ *                         delivered to r.
  *   seq_counter           a zero-initialised uint32 in THIS rank's memory.  The
  *                         sequencing is on the device (no per-call host value, so
  *                         calls can be captured in a CUDA graph): exchange number
- *                         s = *seq_counter + 1 goes to buffer s & 1; when the last
- *                         store is out, s is written to flag_peers[r][rank] for all
- *                         r and to *seq_counter.
+ *                         s = *seq_counter + 1 goes to buffer s & 1.  Every thread
+ *                         block orders its own peer stores (one system fence) and
+ *                         then adds its share to flag_peers[r][rank] on all r; the
+ *                         shares of one exchange sum to 4096, so exchange s has
+ *                         landed from `rank` when that slot reaches 4096 * s.
  * Before it reads X a call waits until exchange *seq_counter (the previous one,
  * normally the producer of its X) has landed from every rank.  The consumer of
  * the LAST exchange of a chain calls b200q4_wait_flags(), which holds `stream`
- * until flag_peers[rank][0..world) have all reached *seq_counter.
+ * until flag_peers[rank][0..world) have all reached 4096 * *seq_counter.
  * No reduction crosses GPUs: the result equals the single-GPU one bit for bit.
  * world <= 8.  Decode shapes (M <= 8) store from the GEMV epilogue itself;
  * larger M computes the slice locally and a copy kernel scatters it.        */

@@ -232,6 +232,34 @@ def test_run_to_run_determinism_and_batch_consistency(gpu, oracle, qt, tag):
     w.free()
 
 
+@pytest.mark.parametrize("qt,tag", TYPES)
+@pytest.mark.parametrize("n,k,m", [(1024, 16384, 1), (100, 24576, 1), (333, 8192, 2), (50, 160, 1), (4096, 4096, 1),
+                                   (77, 96, 2), (2048, 16384, 2), (16, 32, 1)])
+def test_pack_kernel_path_equals_fused_prologue(gpu, oracle, qt, tag, n, k, m):
+    """Decode, M <= 2: activations quantized once by the pack kernel (long rows, K >= 8192 by default) or inside
+    every CTA's prologue (short rows) -- the codes and the summation order are the same, so the bits are."""
+    import ctypes as C
+    L = gpu.load_library()
+    L.b200q4_debug_set_fuse_max_k.restype = C.c_int
+    L.b200q4_debug_set_fuse_max_k.argtypes = [C.c_int]
+    rng = np.random.default_rng(n + k + m)
+    wq = oracle.quantize_rows(qt, rng.uniform(-0.05, 0.05, (n, k)).astype(np.float32))
+    x = rng.standard_normal((m, k)).astype(np.float32)
+    w = gpu.Q4Weight(qt, wq, n, k)
+    old = L.b200q4_debug_set_fuse_max_k(0)                 # always the pack kernel
+    try:
+        y_pack = gpu.mul_mat(w, x)
+        L.b200q4_debug_set_fuse_max_k(1 << 30)             # always the fused prologue
+        y_fused = gpu.mul_mat(w, x)
+    finally:
+        L.b200q4_debug_set_fuse_max_k(old)
+    y_default = gpu.mul_mat(w, x)
+    assert np.array_equal(y_pack.view(np.uint32), y_fused.view(np.uint32))
+    assert np.array_equal(y_default.view(np.uint32), y_fused.view(np.uint32))
+    assert_close(y_pack, oracle.mul_mat(qt, wq, n, k, x, nth=8), f"{tag} N={n} K={k} M={m} pack path")
+    w.free()
+
+
 # ---- BASELINE.json microbench shape, full size -----------------------------------
 @pytest.mark.parametrize("qt,tag", TYPES)
 @pytest.mark.parametrize("m", [1, 8])

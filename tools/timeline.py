@@ -6,8 +6,11 @@ os.environ["B200Q4_DBG"] = "1"
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import vsim_b200
 from vsim_b200 import lib as vlib
-n, k, qt = 16384, 4096, int(sys.argv[1]) if len(sys.argv) > 1 else 0
+qt = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 16384
+k = int(sys.argv[4]) if len(sys.argv) > 4 else 4096
+print(f"== timeline qt={qt} M={m} N={n} K={k}")
 vsim_b200.init(0)
 L = vsim_b200.load_library()
 rng = np.random.default_rng(0)

@@ -50,7 +50,8 @@ struct Ctx {
     uint8_t *d_tpack = nullptr; size_t tpack_cap = 0;           // tile kernel: activation stages
     float *d_tpartial = nullptr; size_t tpartial_cap = 0;        // tile kernel: split-K pieces
     int *d_tcounters = nullptr; size_t tcounters_cap = 0;        // tile kernel: split-K arrival counters (self-resetting)
-    int fuse_max_k = 1 << 30;        // B200Q4_FUSE_MAX_K: longer rows are quantized by a separate pack kernel instead of every CTA's prologue
+    int fuse_max_k = 8191;           // B200Q4_FUSE_MAX_K: longer rows are quantized ONCE by a pack kernel (PDL-chained) instead of in every
+                                     // CTA's prologue (K = 16384: 64 KB of activations per CTA, 6+ us on the critical path of every launch)
     int tile_min_m = 9;              // M >= this runs the tcgen05 tile kernel, below it the decode kernel (B200Q4_TILE_MIN_M overrides; 0 = never)
     uint64_t launches = 0;
     std::recursive_mutex mu;
@@ -101,8 +102,8 @@ int need_init()
 // ---- pipelined decode kernel (q4_gemv_pipe_kernel) ---------------------------------------------
 struct PipePlan { int MP, stages, PP, TS, ntasks, ncw; bool b8, m1; size_t smem; };
 
-// m1: a single activation row that the kernel will quantize itself (fused) -> octet mode
-PipePlan pipe_plan(const b200q4_weight *w, int M, bool can_fuse)
+// m1: a single activation row -> octet mode (codes quantized by the kernel itself when `fuse`, else by pack_*_kernel with MP = 1)
+PipePlan pipe_plan(const b200q4_weight *w, int M, bool fuse)
 {
     PipePlan pp{};
     const int type = w->type;
@@ -116,7 +117,7 @@ PipePlan pipe_plan(const b200q4_weight *w, int M, bool can_fuse)
     };
     pp.MP = (M <= 2) ? 2 : 8;
     if (pp.MP == 8 && fixed(8, false, false) + 2 * stage_of(8, 16) > optin) pp.MP = 2;
-    pp.m1 = pp.MP == 2 && M == 1 && can_fuse;
+    pp.m1 = pp.MP == 2 && M == 1 && (fuse || !g.two_ctas);
     // Preferred: two CTAs of 8 consumer warps per SM (each gets half of the SM's shared memory minus
     // the 1 KB the hardware reserves per CTA) with the 8-column code layout and >= 3 stages of ring.
     const size_t half = (size_t)(g.smem_per_sm > 0 ? g.smem_per_sm : 233472) / 2 - 1024;
@@ -171,6 +172,20 @@ int launch_pipe(const PipeParams &p, int grid, size_t smem, cudaStream_t st)
     return B200Q4_OK;
 }
 
+// small helper kernels that take part in programmatic dependent launch (they call
+// cudaGridDependencySynchronize themselves): launched with the PDL attribute so they do not serialise the stream
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), int blocks, int threads, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g.use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, const float *d_x, size_t x_stride_f,
              float *d_y, size_t y_stride_f, cudaStream_t st, const PeerOut *peer)
 {
@@ -184,7 +199,7 @@ int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, con
     p.dbg = g.d_dbg;
     const int slots = g.sms * (pl.ncw == 8 ? 2 : 1);
     const int grid = pl.ntasks < slots ? pl.ntasks : slots;
-    const bool m1 = pl.m1 && fused && mc == 1;
+    const bool m1 = pl.m1 && mc == 1;
 #define PIPE_DISPATCH(QT)                                                                                          \
     if (pl.ncw == 8) {                                 /* MP == 2, B8 */                                           \
         if (fused) return m1 ? launch_pipe<QT, 2, true, true, true, 8>(p, grid, pl.smem, st)                       \
@@ -198,6 +213,8 @@ int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, con
         return m1 ? launch_pipe<QT, 2, true, true, false, 16>(p, grid, pl.smem, st)                                \
                   : launch_pipe<QT, 2, true, false, false, 16>(p, grid, pl.smem, st);                              \
     }                                                                                                              \
+    if (m1) return pl.b8 ? launch_pipe<QT, 2, false, true, true, 16>(p, grid, pl.smem, st)                         \
+                         : launch_pipe<QT, 2, false, true, false, 16>(p, grid, pl.smem, st);                       \
     return pl.b8 ? launch_pipe<QT, 2, false, false, true, 16>(p, grid, pl.smem, st)                                \
                  : launch_pipe<QT, 2, false, false, false, 16>(p, grid, pl.smem, st);
     if (w->type == 0) { PIPE_DISPATCH(0) }
@@ -299,7 +316,7 @@ int run_tile(const b200q4_weight *w, const float *d_x, size_t x_stride_f, const 
 
 int ensure_scratch(const b200q4_weight *w, int MP)
 {
-    const int nbp = w->C * CHUNK_BLKS;
+    const int nbp = (w->C * CHUNK_BLKS + 7) & ~7;
     int rc;
     if ((rc = ensure(g.d_aq, g.aq_cap, (size_t)nbp * MP * 32))) return rc;
     if ((rc = ensure(g.d_ap, g.ap_cap, (size_t)nbp * MP * 12))) return rc;
@@ -329,34 +346,33 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
         CK(cudaGetLastError());
         return B200Q4_OK;
     }
-    const int nbp = w->C * CHUNK_BLKS;
     // the fused prologue reads X with 128-bit loads
-    const bool can_fuse = !d_wdata && d_x && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0) && (x_stride % 16 == 0) && w->K <= g.fuse_max_k;
-    const PipePlan pp = pipe_plan(w, M, can_fuse);
+    const bool fuse = !d_wdata && d_x && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0) && (x_stride % 16 == 0) && w->K <= g.fuse_max_k;
+    const PipePlan pp = pipe_plan(w, M, fuse);
     const int MP = pp.MP;
     if (MP < 1) return fail(B200Q4_EINVAL, "mul_mat: K=%d too large for the shared-memory activation pack", w->K);
     int rc;
     if ((rc = ensure_scratch(w, MP))) return rc;
     if (pp.PP > 1 && (rc = ensure(g.d_partial, g.partial_cap, (size_t)pp.ntasks * 128 * sizeof(float)))) return rc;
     const size_t rbw = (size_t)w->nb * (w->type == 0 ? 20 : 24);
+    // global pack geometry = what the kernel's shared-memory copy expects: octet mode keeps ONE row per block and pads to whole octets
+    const int prow = pp.m1 ? 1 : MP;
+    const int nbp = pp.m1 ? ((w->C * CHUNK_BLKS + 7) & ~7) : w->C * CHUNK_BLKS;
     for (int m0 = 0; m0 < M; m0 += MP) {
         const int mc = (M - m0 < MP) ? M - m0 : MP;
         const float *xs = d_x ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(d_x) + (size_t)m0 * x_stride) : nullptr;
         float *yo = reinterpret_cast<float *>(reinterpret_cast<char *>(d_y) + (size_t)m0 * y_stride);
-        const bool fused = (MP == 2) && can_fuse;
+        const bool fused = (MP == 2) && fuse;
         if (!fused) {
-            const long warps = (long)nbp * MP;
+            const long warps = (long)nbp * prow;
             const int blocks = (int)((warps * 32 + 255) / 256);
             if (d_wdata) {
                 const uint8_t *src = d_wdata + (size_t)m0 * rbw;
-                if (w->type == 0) pack_wdata_kernel<0><<<blocks, 256, 0, st>>>(src, mc, MP, w->nb, nbp, g.d_aq, g.d_ap);
-                else              pack_wdata_kernel<1><<<blocks, 256, 0, st>>>(src, mc, MP, w->nb, nbp, g.d_aq, g.d_ap);
+                CK(launch_pdl(w->type == 0 ? pack_wdata_kernel<0> : pack_wdata_kernel<1>, blocks, 256, st, src, mc, prow, w->nb, nbp, g.d_aq, g.d_ap));
             } else {
-                if (w->type == 0) pack_act_kernel<0><<<blocks, 256, 0, st>>>(xs, x_stride / 4, mc, MP, w->nb, nbp, g.d_aq, g.d_ap);
-                else              pack_act_kernel<1><<<blocks, 256, 0, st>>>(xs, x_stride / 4, mc, MP, w->nb, nbp, g.d_aq, g.d_ap);
+                CK(launch_pdl(w->type == 0 ? pack_act_kernel<0> : pack_act_kernel<1>, blocks, 256, st, xs, x_stride / 4, mc, prow, w->nb, nbp, g.d_aq, g.d_ap));
             }
             g.launches++;
-            CK(cudaGetLastError());
         }
         PeerOut po;
         if (peer) {                                      // rows m0.. of every rank's Y; only the last launch signals
@@ -759,6 +775,16 @@ int b200q4_debug_set_tile_min_m(int m)
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     const int old = g.tile_min_m;
     g.tile_min_m = m;
+    return old;
+}
+
+// development / test knob (not part of b200q4.h): longest row (K) whose activations the decode kernel
+// quantizes in its own prologue; longer rows go through the pack kernel.  Returns the previous value.
+int b200q4_debug_set_fuse_max_k(int k)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    const int old = g.fuse_max_k;
+    g.fuse_max_k = k;
     return old;
 }
 

@@ -243,6 +243,10 @@ template <int QT>
 __global__ void pack_act_kernel(const float *__restrict__ x, size_t x_stride, int M, int MP, int nb, int nbp,
                                 uint8_t *__restrict__ aq, float *__restrict__ ap)
 {
+    // Programmatic dependent launch on both sides: the decode kernel that follows may start (and stream
+    // weights) at once; this kernel itself waits for the previous one, which still reads aq/ap and may write X.
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
     const int lane = threadIdx.x & 31;
     const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= (long)nbp * MP) return;
@@ -259,6 +263,8 @@ template <int QT>
 __global__ void pack_wdata_kernel(const uint8_t *__restrict__ wdata, int M, int MP, int nb, int nbp,
                                   uint8_t *__restrict__ aq, float *__restrict__ ap)
 {
+    cudaTriggerProgrammaticLaunchCompletion();           // see pack_act_kernel
+    cudaGridDependencySynchronize();
     const int lane = threadIdx.x & 31;
     const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= (long)nbp * MP) return;
@@ -434,11 +440,11 @@ template <int QT>
 __device__ __forceinline__ void imma(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const int (&c)[4])
 {
     if constexpr (QT == 0)
-        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+        asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
                      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
                      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
     else
-        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+        asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
                      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
                      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
 }
@@ -446,10 +452,19 @@ __device__ __forceinline__ void imma(int (&d)[4], const uint32_t (&a)[4], uint32
 // ---- MP == 8: one IMMA per block, D column pair (2t, 2t+1) = activation rows; the scale of
 // block i comes from lane (g,i) of the quad by shuffle.  apack [blk][8][32], planes [blk][8].
 template <int QT>
-__device__ __forceinline__ void compute_unit_m8(const Frag<QT> &f, int c, const uint8_t *s_aq, const float *s_ap,
+__device__ __forceinline__ void compute_unit_m8(const Frag<QT> &f, const uint8_t *chunk, int c, const uint8_t *s_aq, const float *s_ap,
                                                 int plane, int lane, float (&acc)[4])
 {
-    const int t = lane & 3, quad = lane & 28;
+    const int t = lane & 3, g = lane >> 2;
+    // the four block scales of rows g / g+8: one 16-byte load each (the quad reads the same address)
+    const float4 d0a4 = *reinterpret_cast<const float4 *>(chunk + 1024 + g * 16), d0b4 = *reinterpret_cast<const float4 *>(chunk + 1024 + 128 + g * 16);
+    const float d0av[4] = {d0a4.x, d0a4.y, d0a4.z, d0a4.w}, d0bv[4] = {d0b4.x, d0b4.y, d0b4.z, d0b4.w};
+    float m0av[4] = {0.f, 0.f, 0.f, 0.f}, m0bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (QT == 1) {
+        const float4 a4 = *reinterpret_cast<const float4 *>(chunk + 1280 + g * 16), b4 = *reinterpret_cast<const float4 *>(chunk + 1280 + 128 + g * 16);
+        m0av[0] = a4.x; m0av[1] = a4.y; m0av[2] = a4.z; m0av[3] = a4.w;
+        m0bv[0] = b4.x; m0bv[1] = b4.y; m0bv[2] = b4.z; m0bv[3] = b4.w;
+    }
 #pragma unroll
     for (int i = 0; i < CHUNK_BLKS; i++) {
         uint32_t a[4];
@@ -457,30 +472,34 @@ __device__ __forceinline__ void compute_unit_m8(const Frag<QT> &f, int c, const 
         const int blk = c * 4 + i;
         const uint2 b = *reinterpret_cast<const uint2 *>(s_aq + blk * 256 + lane * 8);
         const float2 d1 = *reinterpret_cast<const float2 *>(s_ap + blk * 8 + 2 * t);
-        const float d0a = __shfl_sync(0xffffffffu, f.sa, quad | i), d0b = __shfl_sync(0xffffffffu, f.sb, quad | i);
+        const float d0a = d0av[i], d0b = d0bv[i];
+        // int32 -> fp32 without the conversion pipe: the IMMA accumulator starts at the bit pattern of
+        // 1.5 * 2^23, so the result register IS the float 12582912 + sum (|sum| < 2^18, exact); one FADD removes it.
+        constexpr int MAGIC_I = 0x4B400000;
+        constexpr float MAGIC_F = 12582912.0f;
         int d[4];
         if constexpr (QT == 0) {
             const int2 cr = *reinterpret_cast<const int2 *>(s_ap + plane + blk * 8 + 2 * t);
-            const int ci[4] = {cr.x, cr.y, cr.x, cr.y};
+            const int ci[4] = {cr.x + MAGIC_I, cr.y + MAGIC_I, cr.x + MAGIC_I, cr.y + MAGIC_I};
             imma<QT>(d, a, b.x, b.y, ci);
-            acc[0] = fmaf(d0a * d1.x, (float)d[0], acc[0]);
-            acc[1] = fmaf(d0a * d1.y, (float)d[1], acc[1]);
-            acc[2] = fmaf(d0b * d1.x, (float)d[2], acc[2]);
-            acc[3] = fmaf(d0b * d1.y, (float)d[3], acc[3]);
+            acc[0] = fmaf(d0a * d1.x, __int_as_float(d[0]) - MAGIC_F, acc[0]);
+            acc[1] = fmaf(d0a * d1.y, __int_as_float(d[1]) - MAGIC_F, acc[1]);
+            acc[2] = fmaf(d0b * d1.x, __int_as_float(d[2]) - MAGIC_F, acc[2]);
+            acc[3] = fmaf(d0b * d1.y, __int_as_float(d[3]) - MAGIC_F, acc[3]);
         } else {
-            const int zero[4] = {0, 0, 0, 0};
+            const int magic[4] = {MAGIC_I, MAGIC_I, MAGIC_I, MAGIC_I};
             int s[4];
-            imma<QT>(d, a, b.x, b.y, zero);
-            imma<QT>(s, a, 0x10101010u, 0x01010101u, zero);      // 16 * sum of the block's weight codes
+            imma<QT>(d, a, b.x, b.y, magic);
+            imma<QT>(s, a, 0x10101010u, 0x01010101u, magic);     // 16 * sum of the block's weight codes
             const float2 m1 = *reinterpret_cast<const float2 *>(s_ap + plane + blk * 8 + 2 * t);
             const float2 z  = *reinterpret_cast<const float2 *>(s_ap + 2 * plane + blk * 8 + 2 * t);
-            const float m0a = __shfl_sync(0xffffffffu, f.ma, quad | i), m0b = __shfl_sync(0xffffffffu, f.mb, quad | i);
-            const float sa0 = (float)s[0], sb0 = (float)s[2];
+            const float m0a = m0av[i], m0b = m0bv[i];
+            const float sa0 = __int_as_float(s[0]) - MAGIC_F, sb0 = __int_as_float(s[2]) - MAGIC_F;
             // d0*(d1*P + m1*S0) + m0*Z   (d1, m1 stored /16; P, S0 computed x16)
-            acc[0] += fmaf(d0a, fmaf(d1.x, (float)d[0], m1.x * sa0), m0a * z.x);
-            acc[1] += fmaf(d0a, fmaf(d1.y, (float)d[1], m1.y * sa0), m0a * z.y);
-            acc[2] += fmaf(d0b, fmaf(d1.x, (float)d[2], m1.x * sb0), m0b * z.x);
-            acc[3] += fmaf(d0b, fmaf(d1.y, (float)d[3], m1.y * sb0), m0b * z.y);
+            acc[0] += fmaf(d0a, fmaf(d1.x, __int_as_float(d[0]) - MAGIC_F, m1.x * sa0), m0a * z.x);
+            acc[1] += fmaf(d0a, fmaf(d1.y, __int_as_float(d[1]) - MAGIC_F, m1.y * sa0), m0a * z.y);
+            acc[2] += fmaf(d0b, fmaf(d1.x, __int_as_float(d[2]) - MAGIC_F, m1.x * sb0), m0b * z.x);
+            acc[3] += fmaf(d0b, fmaf(d1.y, __int_as_float(d[3]) - MAGIC_F, m1.y * sb0), m0b * z.y);
         }
     }
 }
@@ -525,13 +544,18 @@ constexpr int MAX_PEERS = 8;
 // Fused all-gather state.  Sequencing lives on the device so that a launch (or a captured CUDA graph of
 // launches) needs no per-call host values: *seq_ctr counts this rank's completed exchanges; exchange
 // number s = *seq_ctr + 1 stores into Y buffer s & 1 (two buffers alternate: a fast rank may already be
-// storing exchange s+1 into a peer that still reads exchange s as its next input) and publishes s in
-// slot `rank` of every rank's flag array.  A launch first waits until all of exchange *seq_ctr has landed
-// locally -- its X is normally that exchange's Y.
+// storing exchange s+1 into a peer that still reads exchange s as its next input).
+// Arrival counters: slot `src` of rank r's flag array counts what rank `src` has delivered to r.  Every CTA,
+// after ordering its own peer stores (fence.sys = one NVLink round trip), adds its share straight into the
+// slot on every rank -- one more one-way trip; no "last CTA" hand-off, no second fence.  The shares of one
+// exchange always sum to PEER_UNIT (CTA 0 adds the remainder), so exchange s has fully landed from `src`
+// exactly when the slot reaches s * PEER_UNIT, whatever the grid size of the launches involved.
+// A launch first waits until all of exchange *seq_ctr has landed locally -- its X is normally that exchange's Y.
+constexpr uint32_t PEER_UNIT = 4096;                     // > any grid size used here
 struct PeerOut {
     float    *y[2][MAX_PEERS];   // [buffer][rank]: rank r's full Y [M][y_stride] (y[.][rank] is local memory)
-    uint32_t *flag[MAX_PEERS];   // rank r's arrival flags [world]
-    const uint32_t *local_flags; // this rank's flag array (= flag[rank])
+    uint32_t *flag[MAX_PEERS];   // rank r's arrival counters [world]
+    const uint32_t *local_flags; // this rank's counters (= flag[rank])
     uint32_t *seq_ctr;           // local exchange counter
     int      *done;              // local CTA-completion counter (self-resetting); NULL: do not signal
     int       world, rank, col0; // col0: first output column of this rank's shard
@@ -543,14 +567,15 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p)
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// spin until rank r's flag has reached `exp` (call with r < world)
-__device__ __forceinline__ void peer_wait_one(const uint32_t *flags, int r, uint32_t exp)
+// spin until rank r's arrival counter shows exchange `seq` complete (call with r < world)
+__device__ __forceinline__ void peer_wait_one(const uint32_t *flags, int r, uint32_t seq)
 {
+    const uint32_t exp = seq * PEER_UNIT;
     for (;;) {
         uint32_t v;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
         if ((int32_t)(v - exp) >= 0) break;
-        __nanosleep(32);
+        __nanosleep(20);
     }
 }
 // one output element: locally, or into every rank's Y (buffer b) at this shard's column offset
@@ -560,22 +585,28 @@ __device__ __forceinline__ void store_y(float *y, const PeerOut &po, int b, size
 #pragma unroll 1
     for (int r = 0; r < po.world; r++) po.y[b][r][idx + po.col0] = v;
 }
-// after a CTA's last store: the last CTA of the launch publishes the exchange number to every rank
+// this CTA's share of the exchange, added by thread r (< world) into rank r's counter for this source rank
+__device__ __forceinline__ void peer_add_share(const PeerOut &po, int r)
+{
+    const uint32_t share = blockIdx.x == 0 ? PEER_UNIT - (gridDim.x - 1) : 1u;
+    asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" :: "l"(po.flag[r] + po.rank), "r"(share) : "memory");
+}
+// local bookkeeping (off the critical path): the last CTA of the launch advances the exchange counter
+__device__ __forceinline__ void peer_count_done(const PeerOut &po)
+{
+    if (atomicAdd(po.done, 1) == (int)gridDim.x - 1) {
+        *po.done = 0;
+        *po.seq_ctr = ld_volatile_u32(po.seq_ctr) + 1;
+    }
+}
+// after a warp's last peer store (only the reducer warp stores Y)
 __device__ __forceinline__ void peer_signal(const PeerOut &po, int lane)
 {
     if (po.world <= 1 || !po.done) return;               // done == NULL: an earlier launch of a multi-launch call
-    __threadfence_system();                              // this warp's peer stores are ordered before the counter
-    __syncwarp();
-    if (lane == 0) {
-        if (atomicAdd(po.done, 1) == (int)gridDim.x - 1) {
-            *po.done = 0;
-            __threadfence_system();
-            const uint32_t seq = ld_volatile_u32(po.seq_ctr) + 1;
-            for (int r = 0; r < po.world; r++)
-                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(po.flag[r] + po.rank), "r"(seq) : "memory");
-            *po.seq_ctr = seq;
-        }
-    }
+    __threadfence_system();                              // every lane: its peer stores are performed system-wide ...
+    __syncwarp();                                        // ... before any lane's signal
+    if (lane < po.world) peer_add_share(po, lane);
+    if (lane == 0) peer_count_done(po);
 }
 // holds the stream until exchange *seq_ctr has landed from every rank (lane r watches rank r)
 __global__ void wait_flags_kernel(const uint32_t *flags, int world, const uint32_t *seq_ctr)
@@ -597,14 +628,8 @@ __global__ void scatter_slice_kernel(const float *__restrict__ src, size_t src_s
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(po.done, 1) == (int)gridDim.x - 1) {
-        *po.done = 0;
-        __threadfence_system();
-        const uint32_t seq = ld_volatile_u32(po.seq_ctr) + 1;
-        for (int r = 0; r < po.world; r++)
-            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(po.flag[r] + po.rank), "r"(seq) : "memory");
-        *po.seq_ctr = seq;
-    }
+    if ((int)threadIdx.x < po.world) peer_add_share(po, threadIdx.x);
+    if (threadIdx.x == 0) peer_count_done(po);
 }
 
 struct PipeParams {
@@ -1142,19 +1167,19 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             quantize8_emit<QT>(lo, hi, valid, lane, rec_of(blk, m), s_ap + (size_t)blk * ROWS + m, plane);
         }
     } else {
-        // global apack is always the compact form [nbp][MP][32]
+        // global apack is always the compact form [nbp][ROWS][32] (+ planes [NP][nbp * ROWS]), same nbp as here
         const uint4 *src = reinterpret_cast<const uint4 *>(p.aq);
         if constexpr (MP == 2 && B8) {
             for (int i = ctid; i < nbp * 16; i += CTHREADS) {                   // 16-byte pieces of the 8-column form
                 const int blk = i >> 4, col = (i >> 1) & 7, piece = i & 1;
-                const int m = col - 2 * (blk & 3);
+                const int m = M1 ? (col == (blk & 7) ? 0 : -1) : col - 2 * (blk & 3);
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (m >= 0 && m < 2) v = src[(blk * 2 + m) * 2 + piece];
+                if (m >= 0 && m < ROWS) v = src[(blk * ROWS + m) * 2 + piece];
                 reinterpret_cast<uint4 *>(s_aq)[i] = v;
             }
         } else {
             uint4 *dst = reinterpret_cast<uint4 *>(s_aq);
-            for (size_t i = ctid; i < (size_t)nbp * MP * 32 / 16; i += CTHREADS) dst[i] = src[i];
+            for (size_t i = ctid; i < (size_t)nbp * ROWS * 32 / 16; i += CTHREADS) dst[i] = src[i];
         }
         const uint4 *src2 = reinterpret_cast<const uint4 *>(p.ap);
         uint4 *dst2 = reinterpret_cast<uint4 *>(s_ap);
@@ -1232,16 +1257,16 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             float aA[4], aB[4];
             if (hA) load_frag_smem<QT>(fA, chA, lane);
             if (hB) load_frag_smem<QT>(fB, chB, lane);
-            auto run_unit = [&](const Frag<QT> &f, int c, float (&acc)[4]) {
+            auto run_unit = [&](const Frag<QT> &f, const uint8_t *chunk, int c, float (&acc)[4]) {
                 if constexpr (MP == 2) compute_unit_chain4c<QT, B8>(f, c, s_aq, s_ap, plane, lane, acc);
                 else {
                     acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-                    compute_unit_m8<QT>(f, c, s_aq, s_ap, plane, lane, acc);
+                    compute_unit_m8<QT>(f, chunk, c, s_aq, s_ap, plane, lane, acc);
                 }
             };
             if (hA && hB) {
-                run_unit(fA, cA, aA);
-                run_unit(fB, cB, aB);
+                run_unit(fA, chA, cA, aA);
+                run_unit(fB, chB, cB, aB);
                 if (TA == TB) {                          // same tile: one partial for both units
                     aA[0] += aB[0]; aA[1] += aB[1]; aA[2] += aB[2]; aA[3] += aB[3];
                     put4(slotA, aA);
@@ -1251,7 +1276,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
                     put4(slotB, aB);
                 }
             } else if (hA) {
-                run_unit(fA, cA, aA);
+                run_unit(fA, chA, cA, aA);
                 put4(slotA, aA);
             }
         }
