@@ -30,27 +30,29 @@ def _worker(rank, world, port, q):
         vs.init(rank)
         L = vs.load_library()
         orc = Oracle()
-        n, k = 1024, 2048
-        po = PeerOutput(L, 64, n)
-        for qt in (0, 1):
-            rng = np.random.default_rng(11 + qt)
-            wq = orc.quantize_rows(qt, rng.uniform(-0.05, 0.05, (n, k)).astype(np.float32))
-            full = vs.Q4Weight(qt, wq, n, k)
-            r0, nr = shard_rows(n, world, rank)
-            shard = vs.Q4Weight(qt, wq, n, k, row0=r0, nrows=nr)
-            for m in (1, 2, 5, 8, 20, 64):               # decode kernel epilogue (<= 8) and tile kernel + scatter
-                x = rng.standard_normal((m, k)).astype(np.float32)
-                d_x = torch.from_numpy(x).cuda()
-                for rep in range(3):                      # both ping-pong buffers, repeated sequence numbers
-                    y = po.mul_mat(shard, d_x, m).clone()
-                torch.cuda.synchronize()
-                y_one = vs.mul_mat(full, x)               # single-GPU result of the same call
-                got = y.cpu().numpy()
-                if not np.array_equal(got.view(np.uint32), y_one.view(np.uint32)):
-                    # slices of a shard are summed over differently placed stream-K pieces (tile kernel): rounding only
-                    if m <= 8 or np.abs(got - y_one).max() > 6e-6 * np.abs(y_one).max():
-                        ok, msg = False, f"rank {rank} qt {qt} M {m}: max diff {np.abs(got - y_one).max()}"
-            full.free(); shard.free()
+        po = PeerOutput(L, 64, 1024)
+        # K = 2048: one K-slice per tile (the GEMV epilogue stores to the peers itself);
+        # K = 8192: K-sliced launches (the finalize kernel adds the parked pieces, stores to the peers and signals)
+        for n, k in ((1024, 2048), (512, 8192)):
+            for qt in (0, 1):
+                rng = np.random.default_rng(11 + qt + k)
+                wq = orc.quantize_rows(qt, rng.uniform(-0.05, 0.05, (n, k)).astype(np.float32))
+                full = vs.Q4Weight(qt, wq, n, k)
+                r0, nr = shard_rows(n, world, rank)
+                shard = vs.Q4Weight(qt, wq, n, k, row0=r0, nrows=nr)
+                for m in (1, 2, 5, 8, 20, 64):               # decode kernel epilogue (<= 8) and tile kernel + scatter
+                    x = rng.standard_normal((m, k)).astype(np.float32)
+                    d_x = torch.from_numpy(x).cuda()
+                    for rep in range(3):                      # both ping-pong buffers, repeated sequence numbers
+                        y = po.mul_mat(shard, d_x, m, n_total=n).clone()
+                    torch.cuda.synchronize()
+                    y_one = vs.mul_mat(full, x)               # single-GPU result of the same call
+                    got = y.cpu().numpy()
+                    if not np.array_equal(got.view(np.uint32), y_one.view(np.uint32)):
+                        # slices of a shard are summed over differently placed stream-K pieces (tile kernel): rounding only
+                        if m <= 8 or np.abs(got - y_one).max() > 6e-6 * np.abs(y_one).max():
+                            ok, msg = False, f"rank {rank} qt {qt} K {k} M {m}: max diff {np.abs(got - y_one).max()}"
+                full.free(); shard.free()
         dist.barrier()
     except Exception as e:                                # noqa: BLE001
         ok, msg = False, f"rank {rank}: {e!r}"

@@ -102,7 +102,10 @@ def test_mul_mat_golden(gpu, golden, qt, tag):
 @pytest.mark.parametrize("qt,tag", TYPES)
 @pytest.mark.parametrize("n,k,m", [(16, 64, 1), (17, 96, 2), (1, 32, 1), (50, 160, 8), (333, 2048, 5),
                                    (4096, 4096, 1), (2048, 5120, 9), (512, 16384, 8), (256, 24576, 3),
-                                   (640, 1024, 16), (300, 512, 17), (128, 256, 40)])
+                                   (640, 1024, 16), (300, 512, 17), (128, 256, 40),
+                                   # K > 4096: K-sliced decode launches (2..6 piece classes, ragged last slice)
+                                   (700, 5120, 1), (300, 6144, 2), (130, 4128, 1), (257, 20480, 4), (64, 8192, 8),
+                                   (1000, 24576, 1), (33, 4160, 7), (2000, 16384, 1), (6144, 24576, 2)])
 def test_mul_mat_random_vs_oracle(gpu, oracle, qt, tag, n, k, m):
     rng = np.random.default_rng(n * 131 + k * 7 + m)
     wq = oracle.quantize_rows(qt, rng.uniform(-0.05, 0.05, (n, k)).astype(np.float32))
@@ -236,8 +239,9 @@ def test_run_to_run_determinism_and_batch_consistency(gpu, oracle, qt, tag):
 @pytest.mark.parametrize("n,k,m", [(1024, 16384, 1), (100, 24576, 1), (333, 8192, 2), (50, 160, 1), (4096, 4096, 1),
                                    (77, 96, 2), (2048, 16384, 2), (16, 32, 1)])
 def test_pack_kernel_path_equals_fused_prologue(gpu, oracle, qt, tag, n, k, m):
-    """Decode, M <= 2: activations quantized once by the pack kernel (long rows, K >= 8192 by default) or inside
-    every CTA's prologue (short rows) -- the codes and the summation order are the same, so the bits are."""
+    """Decode, M <= 2: activations quantized once by the pack kernel (pre-quantized / unaligned inputs, or the
+    B200Q4_FUSE_MAX_K knob) or inside the CTAs' prologues (default) -- the codes and the summation order are the
+    same, so the bits are.  K > 4096 also exercises K-slicing (piece classes, parked pieces, batched arrival)."""
     import ctypes as C
     L = gpu.load_library()
     L.b200q4_debug_set_fuse_max_k.restype = C.c_int
@@ -257,6 +261,26 @@ def test_pack_kernel_path_equals_fused_prologue(gpu, oracle, qt, tag, n, k, m):
     assert np.array_equal(y_pack.view(np.uint32), y_fused.view(np.uint32))
     assert np.array_equal(y_default.view(np.uint32), y_fused.view(np.uint32))
     assert_close(y_pack, oracle.mul_mat(qt, wq, n, k, x, nth=8), f"{tag} N={n} K={k} M={m} pack path")
+    w.free()
+
+
+@pytest.mark.parametrize("qt,tag", TYPES)
+def test_k_sliced_many_pieces_per_cta(gpu, oracle, qt, tag):
+    """K = 8192 (two K-slices), N = 40000: each CTA parks more than 32 pieces, so the parked-piece list is
+    flushed mid-stream as well as at the end; twice on the same tensor (the arrival counters re-arm themselves)."""
+    rng = np.random.default_rng(99)
+    n, k = 40000, 8192
+    wf = rng.random((n, k), dtype=np.float32)
+    wf -= np.float32(0.5)
+    wf *= np.float32(0.1)
+    wq = oracle.quantize_rows(qt, wf)
+    del wf
+    x = rng.standard_normal((1, k)).astype(np.float32)
+    w = gpu.Q4Weight(qt, wq, n, k)
+    y = gpu.mul_mat(w, x)
+    y2 = gpu.mul_mat(w, x)
+    assert np.array_equal(y.view(np.uint32), y2.view(np.uint32))
+    assert assert_close(y, oracle.mul_mat(qt, wq, n, k, x, nth=8), f"{tag} N={n} K={k}") < 1e-5
     w.free()
 
 

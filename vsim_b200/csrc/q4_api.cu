@@ -50,9 +50,10 @@ struct Ctx {
     uint8_t *d_tpack = nullptr; size_t tpack_cap = 0;           // tile kernel: activation stages
     float *d_tpartial = nullptr; size_t tpartial_cap = 0;        // tile kernel: split-K pieces
     int *d_tcounters = nullptr; size_t tcounters_cap = 0;        // tile kernel: split-K arrival counters (self-resetting)
-    int fuse_max_k = 8191;           // B200Q4_FUSE_MAX_K: longer rows are quantized ONCE by a pack kernel (PDL-chained) instead of in every
-                                     // CTA's prologue (K = 16384: 64 KB of activations per CTA, 6+ us on the critical path of every launch)
+    int fuse_max_k = 1 << 30;        // B200Q4_FUSE_MAX_K: longer rows are quantized once by a PDL-chained pack kernel instead of in the
+                                     // CTAs' prologues (K-slicing bounds a prologue to 128 quant blocks, so fusing is the default for any K)
     int tile_min_m = 9;              // M >= this runs the tcgen05 tile kernel, below it the decode kernel (B200Q4_TILE_MIN_M overrides; 0 = never)
+    int pipe_flags = 0;              // B200Q4_PIPE_FLAGS: development knobs of the decode kernel (PipeParams::flags)
     uint64_t launches = 0;
     std::recursive_mutex mu;
     std::string err;
@@ -100,25 +101,49 @@ int need_init()
 }
 
 // ---- pipelined decode kernel (q4_gemv_pipe_kernel) ---------------------------------------------
-struct PipePlan { int MP, stages, PP, TS, ntasks, ncw; bool b8, m1; size_t smem; };
+struct PipePlan { int MP, stages, PP, TS, ntasks, ncw, nbp, gnbp; bool b8, m1; size_t smem; };
 
-// m1: a single activation row -> octet mode (codes quantized by the kernel itself when `fuse`, else by pack_*_kernel with MP = 1)
+constexpr int PIPE_MAX_CLASSES = 62;                   // K-slices per tile the ticket array has room for (K <= 253,952)
+
+// K-slicing geometry (see q4_gemv_pipe_kernel): PP pieces per tile of TS units each; PP = 1 -> unsliced
+void slice_geometry(int C, int &PP, int &TS, int &ntasks, int n_tiles)
+{
+    if (C > 32) {                                       // more than one stage per tile: slice, one stage or less per piece
+        PP = (C + 31) / 32;
+        TS = (C + PP - 1) / PP;
+        TS = (TS + 1) & ~1;                            // even: unit pairs stay aligned to quant-block octets
+        PP = (C + TS - 1) / TS;
+        ntasks = n_tiles * PP;
+    } else if (C >= PIPE_TILE_SPLIT) {                  // one task = one tile
+        PP = 1; TS = C; ntasks = n_tiles;
+    } else {                                            // short tiles: a task = TS/C whole tiles
+        PP = 1;
+        const int G = 32 / C > 0 ? 32 / C : 1;
+        TS = G * C;
+        ntasks = (int)(((long)n_tiles * C + TS - 1) / TS);
+    }
+}
+
+// m1: a single activation row -> octet mode (codes quantized by the kernel itself when `fuse`, else by pack_*_kernel with one row)
 PipePlan pipe_plan(const b200q4_weight *w, int M, bool fuse)
 {
     PipePlan pp{};
     const int type = w->type;
+    slice_geometry(w->C, pp.PP, pp.TS, pp.ntasks, w->n_tiles);
     const size_t optin = (size_t)(g.smem_optin > 0 ? g.smem_optin : 232448);
     auto stage_of = [&](int MP, int ncw) { return (size_t)2 * ncw * chunk_bytes(type) + (size_t)2 * ncw * (MP == 2 ? 128 : 512); };
+    // quant blocks a CTA keeps in shared memory: its K-slice, or the whole (padded) row
+    auto nbp_of = [&](bool m1) { return pp.PP > 1 ? pp.TS * CHUNK_BLKS : (m1 ? ((w->C * CHUNK_BLKS + 7) & ~7) : w->C * CHUNK_BLKS); };
     auto fixed = [&](int MP, bool m1, bool b8) {
         const int rows = m1 ? 1 : MP;
-        const int nbp = m1 ? ((w->C * CHUNK_BLKS + 7) & ~7) : w->C * CHUNK_BLKS;   // M1 pads to whole octets
+        const int nbp = nbp_of(m1);
         const size_t planes = ((size_t)(type == 0 ? 2 : 3) * nbp * rows * 4 + 15) & ~(size_t)15;
-        return (size_t)nbp * (MP == 2 && b8 ? 256 : rows * 32) + planes + 3 * PIPE_MAX_STAGES * 8 + PIPE_MAX_STAGES * 16 + 256;
+        return (size_t)nbp * (MP == 2 && b8 ? 256 : rows * 32) + planes + 3 * PIPE_MAX_STAGES * 8 + PIPE_MAX_STAGES * 16 + 128 + 256;
     };
     pp.MP = (M <= 2) ? 2 : 8;
     if (pp.MP == 8 && fixed(8, false, false) + 2 * stage_of(8, 16) > optin) pp.MP = 2;
     pp.m1 = pp.MP == 2 && M == 1 && (fuse || !g.two_ctas);
-    // Preferred: two CTAs of 8 consumer warps per SM (each gets half of the SM's shared memory minus
+    // Optional: two CTAs of 8 consumer warps per SM (each gets half of the SM's shared memory minus
     // the 1 KB the hardware reserves per CTA) with the 8-column code layout and >= 3 stages of ring.
     const size_t half = (size_t)(g.smem_per_sm > 0 ? g.smem_per_sm : 233472) / 2 - 1024;
     if (g.two_ctas && pp.MP == 2 && fixed(2, pp.m1, true) + 3 * stage_of(2, 8) <= half) {
@@ -135,19 +160,8 @@ PipePlan pipe_plan(const b200q4_weight *w, int M, bool fuse)
         pp.stages = (int)(st > PIPE_MAX_STAGES ? PIPE_MAX_STAGES : st);
         pp.smem = fixed(pp.MP, pp.m1, pp.b8) + (size_t)pp.stages * stage;
     }
-    const int C = w->C;
-    if (C >= PIPE_TILE_SPLIT) {
-        pp.PP = (C + 63) / 64;
-        pp.TS = (C + pp.PP - 1) / pp.PP;
-        pp.TS = (pp.TS + 1) & ~1;                      // even: unit pairs stay aligned to quant-block octets
-        pp.PP = (C + pp.TS - 1) / pp.TS;
-        pp.ntasks = w->n_tiles * pp.PP;
-    } else {
-        pp.PP = 1;
-        const int G = 32 / C > 0 ? 32 / C : 1;
-        pp.TS = G * C;
-        pp.ntasks = (int)(((long)w->n_tiles * C + pp.TS - 1) / pp.TS);
-    }
+    pp.nbp = nbp_of(pp.m1);
+    pp.gnbp = pp.PP > 1 ? pp.PP * pp.TS * CHUNK_BLKS : pp.nbp;     // global pack: every slice fully backed
     return pp;
 }
 
@@ -192,10 +206,10 @@ int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, con
     PipeParams p;
     if (peer) p.peer = *peer; else { p.peer = PeerOut{}; p.peer.world = 1; }
     p.wt = w->d_wt; p.x = d_x; p.aq = g.d_aq; p.ap = g.d_ap; p.y = d_y; p.partial = g.d_partial;
-    p.tile_counters = w->d_counters; p.ticket = g.d_ticket;
+    p.ticket = g.d_ticket;
     p.x_stride = x_stride_f; p.y_stride = y_stride_f;
     p.U = w->n_tiles * w->C; p.N = w->N; p.M = mc; p.C = w->C; p.n_tiles = w->n_tiles; p.nb = w->nb;
-    p.ntasks = pl.ntasks; p.PP = pl.PP; p.TS = pl.TS; p.stages = pl.stages;
+    p.ntasks = pl.ntasks; p.PP = pl.PP; p.TS = pl.TS; p.stages = pl.stages; p.gnbp = pl.gnbp; p.flags = g.pipe_flags;
     p.dbg = g.d_dbg;
     const int slots = g.sms * (pl.ncw == 8 ? 2 : 1);
     const int grid = pl.ntasks < slots ? pl.ntasks : slots;
@@ -314,9 +328,8 @@ int run_tile(const b200q4_weight *w, const float *d_x, size_t x_stride_f, const 
 #undef TILE_DISPATCH
 }
 
-int ensure_scratch(const b200q4_weight *w, int MP)
+int ensure_scratch(int nbp, int MP)
 {
-    const int nbp = (w->C * CHUNK_BLKS + 7) & ~7;
     int rc;
     if ((rc = ensure(g.d_aq, g.aq_cap, (size_t)nbp * MP * 32))) return rc;
     if ((rc = ensure(g.d_ap, g.ap_cap, (size_t)nbp * MP * 12))) return rc;
@@ -351,13 +364,14 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
     const PipePlan pp = pipe_plan(w, M, fuse);
     const int MP = pp.MP;
     if (MP < 1) return fail(B200Q4_EINVAL, "mul_mat: K=%d too large for the shared-memory activation pack", w->K);
+    if (pp.PP > PIPE_MAX_CLASSES) return fail(B200Q4_EINVAL, "mul_mat: K=%d too large (more than %d K-slices)", w->K, PIPE_MAX_CLASSES);
     int rc;
-    if ((rc = ensure_scratch(w, MP))) return rc;
+    if ((rc = ensure_scratch(pp.gnbp, MP))) return rc;
     if (pp.PP > 1 && (rc = ensure(g.d_partial, g.partial_cap, (size_t)pp.ntasks * 128 * sizeof(float)))) return rc;
     const size_t rbw = (size_t)w->nb * (w->type == 0 ? 20 : 24);
     // global pack geometry = what the kernel's shared-memory copy expects: octet mode keeps ONE row per block and pads to whole octets
     const int prow = pp.m1 ? 1 : MP;
-    const int nbp = pp.m1 ? ((w->C * CHUNK_BLKS + 7) & ~7) : w->C * CHUNK_BLKS;
+    const int nbp = pp.gnbp;
     for (int m0 = 0; m0 < M; m0 += MP) {
         const int mc = (M - m0 < MP) ? M - m0 : MP;
         const float *xs = d_x ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(d_x) + (size_t)m0 * x_stride) : nullptr;
@@ -383,6 +397,22 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
             if (m0 + MP < M) po.done = nullptr;
         }
         if ((rc = run_pipe(w, mc, pp, fused, xs, x_stride / 4, yo, y_stride / 4, st, peer ? &po : nullptr))) return rc;
+        if (pp.PP > 1) {                                 // K-sliced: the pieces are parked, this adds them up and stores Y
+            PeerOut fo;
+            if (peer) fo = po; else { fo = PeerOut{}; fo.world = 1; }
+            const long total = (long)mc * w->N;
+            int blocks = (int)((total + 127) / 128);
+            if (blocks > 8 * g.sms) blocks = 8 * g.sms;
+            const bool m1 = pp.m1 && mc == 1;
+            cudaError_t e;
+#define FIN(QT) (m1 ? launch_pdl(pipe_finalize_kernel<QT, 2, true>, blocks, 128, st, (const float *)g.d_partial, pp.PP, w->N, mc, yo, y_stride / 4, fo) \
+               : MP == 2 ? launch_pdl(pipe_finalize_kernel<QT, 2, false>, blocks, 128, st, (const float *)g.d_partial, pp.PP, w->N, mc, yo, y_stride / 4, fo) \
+                         : launch_pdl(pipe_finalize_kernel<QT, 8, false>, blocks, 128, st, (const float *)g.d_partial, pp.PP, w->N, mc, yo, y_stride / 4, fo))
+            e = w->type == 0 ? FIN(0) : FIN(1);
+#undef FIN
+            CK(e);
+            g.launches++;
+        }
     }
     return B200Q4_OK;
 }
@@ -469,13 +499,14 @@ int b200q4_init(int device)
     g.smem_optin = (int)prop.sharedMemPerBlockOptin;
     g.smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     if (const char *e = getenv("B200Q4_TWO_CTAS")) g.two_ctas = atoi(e) != 0;
-    CK(cudaMalloc(&g.d_ticket, 2 * sizeof(int)));
-    CK(cudaMemset(g.d_ticket, 0, 2 * sizeof(int)));
+    CK(cudaMalloc(&g.d_ticket, (2 + PIPE_MAX_CLASSES) * sizeof(int)));
+    CK(cudaMemset(g.d_ticket, 0, (2 + PIPE_MAX_CLASSES) * sizeof(int)));
     CK(cudaMalloc(&g.d_done, sizeof(int)));
     CK(cudaMemset(g.d_done, 0, sizeof(int)));
     if (const char *e = getenv("B200Q4_PDL")) g.use_pdl = atoi(e) != 0;
     if (const char *e = getenv("B200Q4_TILE_MIN_M")) g.tile_min_m = atoi(e);
     if (const char *e = getenv("B200Q4_FUSE_MAX_K")) g.fuse_max_k = atoi(e);
+    if (const char *e = getenv("B200Q4_PIPE_FLAGS")) g.pipe_flags = atoi(e);
     if (const char *e = getenv("B200Q4_DBG")) if (atoi(e) != 0) {
         CK(cudaMalloc(&g.d_dbg, 256 * 16 * sizeof(unsigned long long)));
         CK(cudaMemset(g.d_dbg, 0, 256 * 16 * sizeof(unsigned long long)));

@@ -522,10 +522,16 @@ __device__ __forceinline__ void compute_unit_m8(const Frag<QT> &f, const uint8_t
 //                   M = 2 ("chain4"): per unit, (block i, row m) -> column 2i+m.
 //                   M <= 8 ("m8"):    per block one IMMA, columns = activation rows.
 //   reducer warp    adds the per-unit partials of a stage in unit order (fixed -> bit-reproducible),
-//                   carries the tile accumulator across stages, and at the end of a tile (or tile
-//                   piece) stores Y, or -- when a tile is split over several tasks (K > 8192) --
-//                   parks the piece in a workspace slot; the last piece to arrive (atomic counter)
-//                   adds the slots in piece order and stores Y.
+//                   carries the tile accumulator across stages, and at the end of a tile stores Y.
+//
+// Long rows (K > 4096, i.e. more than 32 units per tile) are K-SLICED: a tile is cut into PP pieces of
+// TS <= 32 units and CTA b is bound to piece class b % PP -- it only ever needs the activations of its
+// own K-slice, so the prologue quantizes (and shared memory holds) at most 128 quant blocks whatever K
+// is, and the stage ring keeps its full depth.  Each class draws tiles from its own ticket counter.
+// A finished piece is parked in a workspace slot with plain stores (no fence, no atomic: nothing sits
+// between two stages of the stream, and the launch ends like an unsliced one); pipe_finalize_kernel,
+// chained behind it with programmatic dependent launch, adds the PP slots of every tile in piece order
+// (reproducible rounding) and stores Y while the NEXT decode launch is already filling its stage ring.
 //
 // Bytes in flight per SM = (stages-1) x 40 KB, independent of registers; weights never touch the
 // register file before they are needed.  Programmatic dependent launch: the weight stream of launch
@@ -639,13 +645,14 @@ struct PipeParams {
     const float   *ap;       //   planes [NP][nbp][MP]
     float         *y;
     float         *partial;  // [ntasks][128] floats, used when a tile spans several tasks
-    int           *tile_counters;
-    int           *ticket;   // [2]: next task, CTAs done   (self-resetting)
+    int           *ticket;   // [0] next task (unsliced), [1] CTAs done, [2 + c] next tile of piece class c   (self-resetting)
     size_t         x_stride, y_stride;   // floats
     int            U, N, M, C, n_tiles, nb;
     int            ntasks;   // tasks in the launch
-    int            PP;       // pieces (tasks) per tile when C >= 16, else 1
+    int            PP;       // K-slices (pieces) per tile; 1 = unsliced
     int            TS;       // units per task
+    int            gnbp;     // quant blocks per row in the global apack (non-fused launches): plane stride = gnbp * rows
+    int            flags;    // development knob: 1 = the reducer polls its barriers instead of try_wait (measured: no gain)
     int            stages;
     unsigned long long *dbg; // optional timeline (B200Q4_TIMELINE builds), else NULL
     // Row-sharded launch with the all-gather fused into the epilogue (world > 1): this rank's output
@@ -692,6 +699,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
             "}\n" : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
     }
 }
+__device__ __forceinline__ bool mbar_test(uint64_t *b, uint32_t parity);
+__device__ __forceinline__ void mbar_spin(uint64_t *b, uint32_t parity)      // busy polling, never suspends
+{
+    while (!mbar_test(b, parity)) { }
+}
 __device__ __forceinline__ bool mbar_test(uint64_t *b, uint32_t parity)      // non-blocking
 {
     uint32_t done;
@@ -714,13 +726,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // cycles of pure latency there).
 __device__ __forceinline__ void task_range(const PipeParams &p, int t, int &u0, int &n, int &T, int &c0)
 {
-    if (p.C >= PIPE_TILE_SPLIT) {                        // PP pieces per tile, TS units each (last shorter)
-        int piece = 0;
+    if (p.C >= PIPE_TILE_SPLIT) {                        // one whole tile (unsliced: C <= 32)
         T = t;
-        if (p.PP > 1) { T = t / p.PP; piece = t - T * p.PP; }
-        c0 = piece * p.TS;
-        u0 = T * p.C + c0;
-        n = min(p.TS, p.C - c0);
+        c0 = 0;
+        u0 = T * p.C;
+        n = p.C;
     } else {                                            // short tiles: a task = TS/C whole tiles
         u0 = t * p.TS;
         n = min(p.TS, p.U - u0);
@@ -880,34 +890,13 @@ __device__ __forceinline__ void compute_octet(const uint8_t *chE, const uint8_t 
     }
 }
 
-// Reducer: a run of units of tile T inside task `task` is complete.  Lane roles:
+// Reducer: the sums of tile T are complete (acc): store Y.  Lane roles:
 //   M1:      lane l < 16 carries row l (activation row 0);
 //   MP == 2: lane (g, r) carries row g + 8*(r>>1), activation row m = r&1;
 //   MP == 8: lane (g, t) carries rows g/g+8 x m = 2t, 2t+1 in acc[0..3].
 template <int QT, int MP, bool M1>
-__device__ __forceinline__ void pipe_emit(const PipeParams &p, int T, int task, int lane, float (&acc)[4], int pb)
+__device__ __forceinline__ void pipe_store(const PipeParams &p, int T, int lane, const float (&acc)[4], int pb)
 {
-    constexpr int NV = (MP == 2) ? 1 : 4;
-    if (p.C >= PIPE_TILE_SPLIT && p.PP > 1) {           // the tile is split over PP tasks
-        float *ws = p.partial + (size_t)task * 128;
-#pragma unroll
-        for (int r = 0; r < NV; r++) ws[r * 32 + lane] = acc[r];
-        __threadfence();
-        __syncwarp();
-        int old = 0;
-        if (lane == 0) old = atomicAdd(p.tile_counters + T, 1);
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if (old != p.PP - 1) return;
-        __threadfence();
-#pragma unroll
-        for (int r = 0; r < NV; r++) acc[r] = 0.0f;
-        for (int k = 0; k < p.PP; k++) {                // piece order: reproducible rounding
-            const float *rs = p.partial + (size_t)(T * p.PP + k) * 128;
-#pragma unroll
-            for (int r = 0; r < NV; r++) acc[r] += __ldcg(rs + r * 32 + lane);
-        }
-        if (lane == 0) p.tile_counters[T] = 0;
-    }
     const float post = (QT == 0) ? 0.0625f : 1.0f;       // undo the 16x of the A/B code scaling (exact)
     const int g = lane >> 2, t = lane & 3;
     if (M1) {
@@ -930,6 +919,45 @@ __device__ __forceinline__ void pipe_emit(const PipeParams &p, int T, int task, 
     }
 }
 
+// K-sliced launches, second half: Y[m][n] = sum over the PP parked pieces of tile n/16, in piece order
+// (reproducible rounding).  One thread per output; the slot index of (m, row) mirrors the lane roles of
+// pipe_store.  PDL on both sides: it waits for the decode kernel that parked the pieces, and the next decode
+// launch may already be filling its stage ring while this runs (it needs no shared memory, so both fit on an SM).
+// With peers (fused all-gather) it is this kernel that stores into every rank's Y and signals.
+template <int QT, int MP, bool M1>
+__global__ void pipe_finalize_kernel(const float *__restrict__ partial, int PP, int N, int M, float *y, size_t y_stride, PeerOut po)
+{
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
+    const int pb = po.world > 1 ? (int)((ld_volatile_u32(po.seq_ctr) + 1) & 1u) : 0;
+    const float post = (QT == 0) ? 0.0625f : 1.0f;       // undo the 16x of the A/B code scaling (exact)
+    const long total = (long)M * N;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / N), n = (int)(i - (long)m * N);
+        const int T = n / TILE_ROWS, row = n % TILE_ROWS, g = row & 7, hi = row >> 3;
+        int q;                                           // slot index = r * 32 + lane of the reducer that parked it
+        if (M1) q = row;
+        else if (MP == 2) q = 4 * g + (m + 2 * hi);
+        else q = ((m & 1) + 2 * hi) * 32 + 4 * g + (m >> 1);
+        const float *rs = partial + (size_t)T * PP * 128 + q;
+        float a = 0.f;
+        for (int k0 = 0; k0 < PP; k0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = (k0 + k < PP) ? __ldcg(rs + (size_t)(k0 + k) * 128) : 0.f;   // loads first
+#pragma unroll
+            for (int k = 0; k < 8; k++) a += v[k];       // absent pieces add +0
+        }
+        store_y(y, po, pb, (size_t)m * y_stride + n, a * post);
+    }
+    if (po.world > 1 && po.done) {
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < po.world) peer_add_share(po, threadIdx.x);
+        if (threadIdx.x == 0) peer_count_done(po);
+    }
+}
+
 // M1: exactly one activation row, fused quantization (rows stored: 1).  MP: padded row count of the
 // other modes (2 or 8).  B8: 256-byte-per-block code layout (no per-IMMA masking).
 template <int QT, int MP, bool FUSED, bool M1, bool B8, int NCW>
@@ -944,8 +972,14 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
     constexpr int ROWS = M1 ? 1 : MP;                          // activation rows stored per block
     constexpr int RW = (MP == 2) ? 32 : 128;                   // floats per unit in the reduction ring
     constexpr int AQ_BLK = (MP == 2 && B8) ? 256 : ROWS * 32;  // code bytes per block in shared memory
-    // blocks held in the shared-memory pack: whole chunks; M1 reads whole octets (8 blocks), so pad to 8
-    const int nbp = M1 ? ((p.C * CHUNK_BLKS + 7) & ~7) : p.C * CHUNK_BLKS;
+    // K-slicing: this CTA's piece class, the first chunk / quant block of its slice
+    const bool sliced = p.PP > 1;
+    const int cls = sliced ? (int)blockIdx.x % p.PP : 0;
+    const int cbase = cls * p.TS, blk0 = cbase * CHUNK_BLKS;
+    // blocks held in the shared-memory pack: whole chunks (of the slice); M1 reads whole octets (8 blocks), so pad
+    // to 8 (TS is even, so a slice is whole octets already)
+    const int nbp = sliced ? p.TS * CHUNK_BLKS : (M1 ? ((p.C * CHUNK_BLKS + 7) & ~7) : p.C * CHUNK_BLKS);
+    const int nb_l = min(p.nb - blk0, nbp);              // quant blocks of the slice that exist (>= 1)
     const int plane = nbp * ROWS;
     // shared-memory map: [stages x STAGE_BYTES][red ring][apack codes][planes][barriers][desc]
     uint8_t *s_stage = smem;
@@ -958,6 +992,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
     int4     *s_desc = reinterpret_cast<int4 *>(bar_done + PIPE_MAX_STAGES);   // {n units (<0 = stop), chunk index of first unit, tile of first unit, task}
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stages; i++) {
             mbar_init(&bar_full[i], 1);
@@ -975,9 +1010,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
         if (lane == 0) {
             int s = 0;                                   // stage index
             uint32_t ph = 1;                             // parity to wait for on bar_empty (first lap: passes at once)
-            auto issue_task = [&](int task) {
-                int u0, n, T, c0;
-                task_range(p, task, u0, n, T, c0);
+            auto issue = [&](int u0, int n, int T, int c0, int task) {
                 for (int r = 0; r < n; r += PIPE_UNITS) {
                     mbar_wait(&bar_empty[s], ph);
                     const int cnt = min(PIPE_UNITS, n - r);
@@ -989,22 +1022,35 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             };
-            // The first PIPE_STATIC_TASKS tasks of every CTA are static (task = b + k*grid): they
-            // need nothing from the previous launch, so under programmatic dependent launch the
-            // whole stage ring is already filling while the previous kernel drains.
+            // task t of this CTA's sequence: unsliced = task number, sliced = tile number (piece `cls` of it)
+            auto issue_seq = [&](int t) {
+                if (sliced) issue(t * p.C + cbase, min(p.TS, p.C - cbase), t, cbase, t * p.PP + cls);
+                else {
+                    int u0, n, T, c0;
+                    task_range(p, t, u0, n, T, c0);
+                    issue(u0, n, T, c0, t);
+                }
+            };
+            // The first PIPE_STATIC_TASKS tasks of every CTA are static (task = b + k*grid; sliced: tile =
+            // idx + k*ncls inside the CTA's class): they need nothing from the previous launch, so under
+            // programmatic dependent launch the whole stage ring is already filling while the previous kernel drains.
+            const int idx = sliced ? (int)blockIdx.x / p.PP : (int)blockIdx.x;
+            const int ncls = sliced ? ((int)gridDim.x - cls + p.PP - 1) / p.PP : (int)gridDim.x;     // CTAs in this class
+            const int limit = sliced ? p.n_tiles : p.ntasks;
             for (int k = 0; k < PIPE_STATIC_TASKS; k++) {
-                const int task = (int)blockIdx.x + k * (int)gridDim.x;
-                if (task < p.ntasks) issue_task(task);
+                const int t = idx + k * ncls;
+                if (t < limit) issue_seq(t);
             }
             PIPE_STAMP(1);
             cudaGridDependencySynchronize();
             PIPE_STAMP(2);
             // then dynamic tickets, fetched one task ahead so the atomic's latency hides behind the copies
-            const int base = PIPE_STATIC_TASKS * (int)gridDim.x;
-            int cur = base + atomicAdd(p.ticket, 1);
-            while (cur < p.ntasks) {
-                const int nxt = base + atomicAdd(p.ticket, 1);
-                issue_task(cur);
+            int *tk = sliced ? p.ticket + 2 + cls : p.ticket;
+            const int base = PIPE_STATIC_TASKS * ncls;
+            int cur = base + atomicAdd(tk, 1);
+            while (cur < limit) {
+                const int nxt = base + atomicAdd(tk, 1);
+                issue_seq(cur);
                 cur = nxt;
             }
             PIPE_STAMP(10);                              // last copy issued
@@ -1013,7 +1059,11 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             mbar_arrive(&bar_full[s]);
             PIPE_STAMP(8);
             // the last CTA to run out of tasks re-arms the ticket counter for the next launch
-            if (atomicAdd(p.ticket + 1, 1) == (int)gridDim.x - 1) { p.ticket[0] = 0; p.ticket[1] = 0; __threadfence(); }
+            if (atomicAdd(p.ticket + 1, 1) == (int)gridDim.x - 1) {
+                p.ticket[0] = 0; p.ticket[1] = 0;
+                for (int c = 0; c < p.PP; c++) p.ticket[2 + c] = 0;
+                __threadfence();
+            }
         }
         return;
     }
@@ -1026,13 +1076,23 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
         int curT = -1, curTask = -1;
         int s = 0;
         uint32_t ph = 0;
+        constexpr int NV = (MP == 2) ? 1 : 4;
+        // sliced launches: a finished piece is parked in its workspace slot with plain stores -- no fence, no
+        // atomic; pipe_finalize_kernel (the next launch in the stream) adds the pieces and stores Y
+        auto emit = [&](int T, int task) {
+            if (!sliced) { pipe_store<QT, MP, M1>(p, T, lane, acc, pb); return; }
+            float *ws = p.partial + (size_t)task * 128;
+#pragma unroll
+            for (int r = 0; r < NV; r++) ws[r * 32 + lane] = acc[r];
+        };
         for (;;) {
             // bar_done implies bar_full (every consumer passed it), so one wait per stage suffices;
             // the stop marker carries no consumer arrivals and is announced on bar_full alone.
+            // (pure polling: the one reducer warp should notice a finished stage at once, not after a suspended try_wait)
             if (!mbar_test(&bar_done[s], ph)) {
-                mbar_wait(&bar_full[s], ph);
+                if (p.flags & 1) mbar_spin(&bar_full[s], ph); else mbar_wait(&bar_full[s], ph);
                 if (s_desc[s].x < 0) break;
-                mbar_wait(&bar_done[s], ph);
+                if (p.flags & 1) mbar_spin(&bar_done[s], ph); else mbar_wait(&bar_done[s], ph);
             }
             const int4 dsc = s_desc[s];
             if (dsc.x < 0) break;
@@ -1043,7 +1103,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             int j = 0;
             while (j < dsc.x) {
                 if (T != curT || task != curTask) {
-                    if (curT >= 0) pipe_emit<QT, MP, M1>(p, curT, curTask, lane, acc, pb);
+                    if (curT >= 0) emit(curT, curTask);
                     acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
                     curT = T; curTask = task;
                 }
@@ -1087,8 +1147,8 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             if (lane == 0) mbar_arrive(&bar_empty[s]);
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        if (curT >= 0) pipe_emit<QT, MP, M1>(p, curT, curTask, lane, acc, pb);
-        peer_signal(p.peer, lane);
+        if (curT >= 0) emit(curT, curTask);
+        if (!sliced) peer_signal(p.peer, lane);
         if (lane == 0) PIPE_STAMP(7);
         return;
     }
@@ -1112,13 +1172,13 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             const int col = w8 >> 2;                                            // 32-byte record index inside the block
             int m = col;
             if constexpr (MP == 2 && B8) m = M1 ? (col == (blk & 7) ? 0 : -1) : col - 2 * (blk & 3);
-            const bool live = blk < p.nb && m >= 0 && m < p.M;
+            const bool live = blk < nb_l && m >= 0 && m < p.M;
             if (!live) reinterpret_cast<uint2 *>(s_aq + (size_t)blk * AQ_BLK)[w8] = make_uint2(0u, 0u);
         }
         for (int pl = 0; pl < NP; pl++) {
-            for (int i = p.nb * ROWS + ctid; i < nbp * ROWS; i += CTHREADS) s_ap[pl * plane + i] = 0.0f;   // padded blocks
+            for (int i = nb_l * ROWS + ctid; i < nbp * ROWS; i += CTHREADS) s_ap[pl * plane + i] = 0.0f;   // padded blocks
             if (ROWS == 2 && p.M == 1)
-                for (int blk = ctid; blk < p.nb; blk += CTHREADS) s_ap[pl * plane + blk * 2 + 1] = 0.0f;  // absent row
+                for (int blk = ctid; blk < nb_l; blk += CTHREADS) s_ap[pl * plane + blk * 2 + 1] = 0.0f;  // absent row
         }
     }
     cudaGridDependencySynchronize();                     // X may be the previous kernel's output
@@ -1132,15 +1192,16 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
         // first FUSED_ITEMS items of a thread are held in registers) so that their L2 latency
         // overlaps the zero-fill below.
         constexpr int FUSED_ITEMS = 2;
-        const int items = p.M * p.nb * 4;
+        const int items = p.M * nb_l * 4;
+        const float *xs = p.x + (size_t)blk0 * QK;       // this CTA's K-slice of every activation row
         float4 xlo[FUSED_ITEMS], xhi[FUSED_ITEMS];
 #pragma unroll
         for (int it = 0; it < FUSED_ITEMS; it++) {
             const int id = it * CTHREADS + ctid;
             xlo[it] = make_float4(0.f, 0.f, 0.f, 0.f); xhi[it] = xlo[it];
             if (id < items) {
-                const int bq = id >> 2, m = bq / p.nb, blk = bq - m * p.nb;
-                const float4 *src = reinterpret_cast<const float4 *>(p.x + (size_t)m * p.x_stride + (size_t)blk * QK + (lane & 3) * 8);
+                const int bq = id >> 2, m = bq / nb_l, blk = bq - m * nb_l;
+                const float4 *src = reinterpret_cast<const float4 *>(xs + (size_t)m * p.x_stride + (size_t)blk * QK + (lane & 3) * 8);
                 xlo[it] = src[0]; xhi[it] = src[1];
             }
         }
@@ -1150,7 +1211,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             const bool valid = id < items;
             if (it * CTHREADS < items) {                 // warp-uniform: shuffles inside
                 const int bq = valid ? (id >> 2) : 0;
-                const int m = bq / p.nb, blk = bq - m * p.nb;
+                const int m = bq / nb_l, blk = bq - m * nb_l;
                 quantize8_emit<QT>(xlo[it], xhi[it], valid, lane, rec_of(blk, m), s_ap + (size_t)blk * ROWS + m, plane);
             }
         }
@@ -1158,17 +1219,18 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             const int id = base + ctid;
             const bool valid = id < items;
             const int bq = valid ? (id >> 2) : 0;
-            const int m = bq / p.nb, blk = bq - m * p.nb;
+            const int m = bq / nb_l, blk = bq - m * nb_l;
             float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
             if (valid) {
-                const float4 *src = reinterpret_cast<const float4 *>(p.x + (size_t)m * p.x_stride + (size_t)blk * QK + (lane & 3) * 8);
+                const float4 *src = reinterpret_cast<const float4 *>(xs + (size_t)m * p.x_stride + (size_t)blk * QK + (lane & 3) * 8);
                 lo = src[0]; hi = src[1];
             }
             quantize8_emit<QT>(lo, hi, valid, lane, rec_of(blk, m), s_ap + (size_t)blk * ROWS + m, plane);
         }
     } else {
-        // global apack is always the compact form [nbp][ROWS][32] (+ planes [NP][nbp * ROWS]), same nbp as here
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.aq);
+        // global apack: compact form [gnbp][ROWS][32] + planes [NP][gnbp * ROWS] over the whole row; this CTA
+        // takes blocks blk0 .. blk0 + nbp (the host sizes gnbp so that every slice is fully backed)
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.aq) + (size_t)blk0 * ROWS * 2;
         if constexpr (MP == 2 && B8) {
             for (int i = ctid; i < nbp * 16; i += CTHREADS) {                   // 16-byte pieces of the 8-column form
                 const int blk = i >> 4, col = (i >> 1) & 7, piece = i & 1;
@@ -1179,11 +1241,13 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             }
         } else {
             uint4 *dst = reinterpret_cast<uint4 *>(s_aq);
-            for (size_t i = ctid; i < (size_t)nbp * ROWS * 32 / 16; i += CTHREADS) dst[i] = src[i];
+            for (int i = ctid; i < nbp * ROWS * 2; i += CTHREADS) dst[i] = src[i];
         }
-        const uint4 *src2 = reinterpret_cast<const uint4 *>(p.ap);
-        uint4 *dst2 = reinterpret_cast<uint4 *>(s_ap);
-        for (size_t i = ctid; i < (size_t)NP * plane * 4 / 16; i += CTHREADS) dst2[i] = src2[i];
+        const int pq = plane / 4;                                               // 16-byte pieces per plane here
+        for (int i = ctid; i < NP * pq; i += CTHREADS) {
+            const int pl = i / pq, j = i - pl * pq;
+            reinterpret_cast<uint4 *>(s_ap)[i] = reinterpret_cast<const uint4 *>(p.ap + ((size_t)pl * p.gnbp + blk0) * ROWS)[j];
+        }
     }
     asm volatile("bar.sync 1, %0;" :: "n"(CTHREADS) : "memory");
     if (threadIdx.x == 0) PIPE_STAMP(4);
@@ -1237,18 +1301,18 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
         if constexpr (M1) {
             if (hA && hB && TA == TB && !(cA & 1)) {     // an aligned octet: the common case
                 float v0, v2;
-                compute_octet<QT, B8>(chA, chB, cA >> 1, s_aq, s_ap, plane, lane, v0, v2);
+                compute_octet<QT, B8>(chA, chB, (cA - cbase) >> 1, s_aq, s_ap, plane, lane, v0, v2);
                 put_rows(slotA, v0, v2);
                 if (lane < TILE_ROWS) slotB[lane] = 0.f;
             } else {                                     // half octets (odd start, tile boundary, ragged tail)
                 if (hA) {
                     float v0, v2;
-                    compute_octet<QT, B8>((cA & 1) ? nullptr : chA, (cA & 1) ? chA : nullptr, cA >> 1, s_aq, s_ap, plane, lane, v0, v2);
+                    compute_octet<QT, B8>((cA & 1) ? nullptr : chA, (cA & 1) ? chA : nullptr, (cA - cbase) >> 1, s_aq, s_ap, plane, lane, v0, v2);
                     put_rows(slotA, v0, v2);
                 }
                 if (hB) {
                     float v0, v2;
-                    compute_octet<QT, B8>((cB & 1) ? nullptr : chB, (cB & 1) ? chB : nullptr, cB >> 1, s_aq, s_ap, plane, lane, v0, v2);
+                    compute_octet<QT, B8>((cB & 1) ? nullptr : chB, (cB & 1) ? chB : nullptr, (cB - cbase) >> 1, s_aq, s_ap, plane, lane, v0, v2);
                     put_rows(slotB, v0, v2);
                 }
             }
@@ -1265,8 +1329,8 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
                 }
             };
             if (hA && hB) {
-                run_unit(fA, chA, cA, aA);
-                run_unit(fB, chB, cB, aB);
+                run_unit(fA, chA, cA - cbase, aA);
+                run_unit(fB, chB, cB - cbase, aB);
                 if (TA == TB) {                          // same tile: one partial for both units
                     aA[0] += aB[0]; aA[1] += aB[1]; aA[2] += aB[2]; aA[3] += aB[3];
                     put4(slotA, aA);
@@ -1276,7 +1340,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
                     put4(slotB, aB);
                 }
             } else if (hA) {
-                run_unit(fA, chA, cA, aA);
+                run_unit(fA, chA, cA - cbase, aA);
                 put4(slotA, aA);
             }
         }
