@@ -10,14 +10,16 @@ headline point Q4_0, M=1 (the decode GEMV the north star quotes its 80 %-of-HBM 
   value      algorithmic GB/s ( W + 4MK + 4MN bytes per call, SURVEY.md section 8d ) with all inputs
              resident in HBM, CUDA events on the launching stream, max over ranks
   e2e        the same metric through the C ABI call a ggml hook makes (b200q4_mul_mat) with HOST
-             buffers: H2D of X and D2H of Y inside the timed region
+             buffers, X read from and Y written to host memory inside the timed region (pinned buffers:
+             a fetch kernel pulls X, the decode epilogue stores Y straight into the caller's buffer,
+             completion is a polled host word; pageable buffers take staged copies)
   roofline   the dominant kernel (q4_gemv) timed alone with CUDA events, against MEASURED_PEAKS.json
   cpu_baseline  the reference's own scalar CPU path (oracle/_ref, else the oracle port) on this box
 
 L2: every timed loop rotates over enough distinct weight tensors (> 3x the 126 MB L2) that no call
 finds its weights cached.  N>1: each rank owns a 16384-row shard of a (16384*N)-row tensor (row
-split of imax.c:1185-1188), X is replicated, the fp32 output slices are all-gathered over NCCL;
-weak scaling.  `--impl reference` times the reference CPU implementation on the same config.
+split of imax.c:1185-1188), X is replicated, the kernel epilogue stores the fp32 output slices into
+every rank's Y over NVLink (--nccl: an NCCL all-gather instead); weak scaling.  `--impl reference` times the reference CPU implementation on the same config.
 """
 from __future__ import annotations
 
@@ -156,11 +158,12 @@ def cpu_baseline(qt: int, m: int, wq: np.ndarray, x: np.ndarray, budget_s: float
 
 
 # GPT-J-6B (BASELINE.json configs[2]): n_embd 4096, 28 layers, vocab 50400 -- the Q4 mul_mats of one decode step
-GPTJ_LAYERS, GPTJ_EMBD, GPTJ_FF, GPTJ_VOCAB = 28, 4096, 16384, 50400
+# (name, layers, n_embd, n_ff, n_vocab) of the decode legs: BASELINE.json configs[2] and configs[4]
+MODELS = {"gptj6b": ("GPT-J-6B", 28, 4096, 16384, 50400), "neox20b": ("GPT-NeoX-20B", 44, 6144, 24576, 50432)}
 
 
-def model_decode(vs, L, torch, dist, rank, world, stream, peak, use_nccl, tokens=24):
-    """GPT-J-6B-shaped decode: the 28 x 6 + 1 Q4_0 mul_mats of one token (M=1), device-resident, back to back.
+def model_decode(vs, L, torch, dist, rank, world, stream, peak, use_nccl, which="gptj6b", tokens=24):
+    """GPT-J-6B- / GPT-NeoX-20B-shaped decode: the layers x 6 + 1 Q4_0 mul_mats of one token (M=1), device-resident, back to back.
     Only the hot path of this repository -- norms, rope, attention and sampling of the reference graph are
     not run -- so this is the mul_mat share of a token, an upper bound on tok/s.
     N>1: every tensor is row-sharded, each mul_mat is followed by an all-gather of its output slice."""
@@ -171,12 +174,12 @@ def model_decode(vs, L, torch, dist, rank, world, stream, peak, use_nccl, tokens
         raw.reshape(n, k // 32, 20)[:, :, :4] = np.full((n, k // 32), 0.01, np.float32).view(np.uint8).reshape(n, k // 32, 4)
         return raw
 
-    E, F, V = GPTJ_EMBD, GPTJ_FF, GPTJ_VOCAB
+    mname, NL, E, F, V = MODELS[which]
     shapes = [(E, E)] * 4 + [(F, E), (E, F)]                       # q, k, v, o, fc_in, fc_out  (N, K)
     host = [rand_q4_0(n // world, k) for n, k in shapes]           # one layer's bytes, uploaded 28 times into distinct HBM
-    layers = [[vs.Q4Weight(0, host[j], shapes[j][0] // world, shapes[j][1]) for j in range(6)] for _ in range(GPTJ_LAYERS)]
+    layers = [[vs.Q4Weight(0, host[j], shapes[j][0] // world, shapes[j][1]) for j in range(6)] for _ in range(NL)]
     head = vs.Q4Weight(0, rand_q4_0(V // world, E), V // world, E)
-    wbytes = (sum(h.size for h in host) * GPTJ_LAYERS + head.device_bytes)
+    wbytes = (sum(h.size for h in host) * NL + head.device_bytes)
     d_in = torch.randn(1, F, device="cuda", dtype=torch.float32)
     d_out = torch.empty(1, max(F, V), device="cuda", dtype=torch.float32)
     d_full = torch.empty(world, max(F, V) // world, device="cuda", dtype=torch.float32)
@@ -239,9 +242,9 @@ def model_decode(vs, L, torch, dist, rank, world, stream, peak, use_nccl, tokens
             w.free()
     head.free()
     gbs = wbytes / (ms * 1e-3) / 1e9
-    return {"model": "GPT-J-6B shapes (n_embd 4096, 28 layers, vocab 50400), Q4_0, random-init, batch 1",
-            "scope": "the 169 Q4_0 mul_mats of one decode step only (no norm/rope/attention/sampling): mul_mat share of a token",
-            "tok_per_s": 1e3 / ms, "ms_per_token": ms, "mul_mats_per_token": GPTJ_LAYERS * 6 + 1,
+    return {"model": f"{mname} shapes (n_embd {E}, {NL} layers, vocab {V}), Q4_0, random-init, batch 1",
+            "scope": f"the {NL * 6 + 1} Q4_0 mul_mats of one decode step only (no norm/rope/attention/sampling): mul_mat share of a token",
+            "tok_per_s": 1e3 / ms, "ms_per_token": ms, "mul_mats_per_token": NL * 6 + 1,
             "weight_bytes_per_gpu": int(wbytes), "weight_GBps_per_gpu": gbs, "frac_hbm_peak": gbs / peak,
             "parallelism": "single GPU" if world == 1 else
                            f"row shards over {world} GPUs + " + ("NCCL all-gather per mul_mat" if use_nccl else
@@ -318,7 +321,7 @@ def main() -> int:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-points", action="store_true", help="skip the (type, M) sweep")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-model", action="store_true", help="skip the GPT-J-6B-shaped decode leg")
+    ap.add_argument("--no-model", action="store_true", help="skip the GPT-J-6B- and GPT-NeoX-20B-shaped decode legs")
     ap.add_argument("--nccl", action="store_true", help="N>1: exchange output slices with an NCCL all-gather instead of the fused epilogue")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -480,9 +483,10 @@ def main() -> int:
         ms_nccl = timed(M_HEAD, w0, min(args.steps, 200), 5, nccl=True) / min(args.steps, 200)
         exchange = {"fused_peer_store_us_per_step": ms_step * 1e3, "nccl_all_gather_us_per_step": ms_nccl * 1e3,
                     "bytes_per_rank_per_step": M_HEAD * N_ROWS * 4}
-    model = None
+    model = model20 = None
     if not args.no_model:
-        model = model_decode(vs, L, torch, dist, rank, world, stream, peak, args.nccl)
+        model = model_decode(vs, L, torch, dist, rank, world, stream, peak, args.nccl, "gptj6b")
+        model20 = model_decode(vs, L, torch, dist, rank, world, stream, peak, args.nccl, "neox20b", tokens=12)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -515,7 +519,8 @@ def main() -> int:
             },
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": M_HEAD * K_DIM * 4,
                     "d2h_bytes_per_step": M_HEAD * N_ROWS * 4, "us_per_call": e2e_s / args.steps * 1e6,
-                    "api": "b200q4_mul_mat (C ABI, pinned host X and Y, synchronous)"},
+                    "api": "b200q4_mul_mat (C ABI, pinned host X and Y, synchronous): fetch kernel pulls X over PCIe, the decode "
+                           "epilogue stores Y into the host buffer, completion = polled host word"},
             "gpu_launches": int(launches_timed),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
@@ -526,6 +531,7 @@ def main() -> int:
             "points": points,
             "roofline_prefill": prefill_roofline(points, tpeak, tpeak_src, world),
             "model_decode": model,
+            "model_decode_neox20b": model20,
             "exchange": exchange,
             "checksum_y": float(np.abs(y_e2e).sum()),
         }

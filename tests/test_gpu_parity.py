@@ -284,6 +284,39 @@ def test_k_sliced_many_pieces_per_cta(gpu, oracle, qt, tag):
     w.free()
 
 
+@pytest.mark.parametrize("qt,tag", TYPES)
+@pytest.mark.parametrize("n,k,m", [(4096, 4096, 1), (1000, 16384, 1), (333, 2048, 2), (512, 8192, 8), (100, 256, 5)])
+def test_zero_copy_host_path_equals_copy_path(gpu, oracle, qt, tag, n, k, m):
+    """b200q4_mul_mat on PINNED host buffers (b200q4_host_alloc): X is pulled by a fetch kernel, Y is stored by the
+    decode epilogue straight into the caller's (strided) buffer, completion is a polled host word.  Same bits as
+    the staged-copy path that pageable buffers take; bytes outside the Y rows stay untouched."""
+    import ctypes as C
+    L = gpu.load_library()
+    rng = np.random.default_rng(n + 3 * k + m)
+    wq = oracle.quantize_rows(qt, rng.uniform(-0.05, 0.05, (n, k)).astype(np.float32))
+    x = rng.standard_normal((m, k)).astype(np.float32)
+    w = gpu.Q4Weight(qt, wq, n, k)
+    y_copy = gpu.mul_mat(w, x)                             # numpy arrays are pageable: staged copies
+    pad = 8                                                # y rows n + pad floats apart
+    L.b200q4_host_alloc.restype = C.c_void_p
+    hx = L.b200q4_host_alloc(m * k * 4)
+    hy = L.b200q4_host_alloc(m * (n + pad) * 4)
+    try:
+        C.memmove(hx, x.ctypes.data, m * k * 4)
+        ybuf = np.ctypeslib.as_array(C.cast(hy, C.POINTER(C.c_float)), shape=(m, n + pad))
+        ybuf[:] = 7.0
+        for _ in range(3):                                 # the completion word counts up
+            rc = L.b200q4_mul_mat(w.handle, C.c_void_p(hx), m, k * 4, C.c_void_p(hy), (n + pad) * 4)
+            assert rc == 0, gpu.lib._err(L)
+        assert np.array_equal(ybuf[:, :n].view(np.uint32), y_copy.view(np.uint32))
+        assert np.all(ybuf[:, n:] == 7.0)
+        assert_close(ybuf[:, :n].copy(), oracle.mul_mat(qt, wq, n, k, x, nth=8), f"{tag} zero-copy N={n} K={k} M={m}")
+    finally:
+        L.b200q4_host_free(C.c_void_p(hx))
+        L.b200q4_host_free(C.c_void_p(hy))
+    w.free()
+
+
 # ---- BASELINE.json microbench shape, full size -----------------------------------
 @pytest.mark.parametrize("qt,tag", TYPES)
 @pytest.mark.parametrize("m", [1, 8])

@@ -53,6 +53,9 @@ struct Ctx {
     int fuse_max_k = 1 << 30;        // B200Q4_FUSE_MAX_K: longer rows are quantized once by a PDL-chained pack kernel instead of in the
                                      // CTAs' prologues (K-slicing bounds a prologue to 128 quant blocks, so fusing is the default for any K)
     int tile_min_m = 9;              // M >= this runs the tcgen05 tile kernel, below it the decode kernel (B200Q4_TILE_MIN_M overrides; 0 = never)
+    bool zero_copy = true;           // B200Q4_ZERO_COPY=0: always stage host buffers through cudaMemcpy
+    uint32_t *h_flag = nullptr, *d_flag = nullptr;   // mapped host word the stream writes when a zero-copy call is complete
+    uint32_t hseq = 0;
     int pipe_flags = 0;              // B200Q4_PIPE_FLAGS: development knobs of the decode kernel (PipeParams::flags)
     uint64_t launches = 0;
     std::recursive_mutex mu;
@@ -417,6 +420,49 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
     return B200Q4_OK;
 }
 
+// ---- zero-copy host path (decode calls on pinned buffers) -------------------------------------------
+// X rows are pulled over PCIe ONCE by a tiny PDL-chained kernel (the decode kernel that follows is already
+// filling its stage ring meanwhile), Y is stored by the decode epilogue straight into the caller's buffer,
+// and completion is a word in mapped host memory that the calling thread polls -- no copy-engine round trips,
+// no stream-synchronize wake-up.
+__global__ void fetch_rows_kernel(const float *__restrict__ hx, size_t x_stride_f, int M, int K, float *__restrict__ dx)
+{
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
+    const int k4 = K / 4;
+    const long total = (long)M * k4;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / k4), j = (int)(i - (long)m * k4);
+        reinterpret_cast<float4 *>(dx)[i] = reinterpret_cast<const float4 *>(hx + (size_t)m * x_stride_f)[j];
+    }
+}
+__global__ void signal_host_kernel(uint32_t *flag, uint32_t v)
+{
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(flag) = v;
+}
+// device alias of a pinned (cudaHostAlloc / cudaHostRegister) host pointer, or NULL for pageable memory
+void *pinned_alias(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+// wait for the stream to write `seq` into the mapped word; falls back to the driver now and then so that a
+// faulted stream is reported instead of spinning forever
+int wait_host_flag(uint32_t seq)
+{
+    volatile uint32_t *f = g.h_flag;
+    for (unsigned spins = 0;; spins++) {
+        if (*f == seq) return B200Q4_OK;
+        if ((spins & 0x3fff) == 0x3fff) {
+            cudaError_t e = cudaStreamQuery(g.stream);
+            if (e == cudaSuccess) { if (*f == seq) return B200Q4_OK; CK(cudaStreamSynchronize(g.stream)); return B200Q4_OK; }
+            if (e != cudaErrorNotReady) return fail(B200Q4_ECUDA, "stream failed: %s", cudaGetErrorString(e));
+        }
+    }
+}
+
 b200q4_weight *upload_impl(int type, const void *rows, int N, int K, size_t row_stride, bool transposed)
 {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
@@ -507,6 +553,14 @@ int b200q4_init(int device)
     if (const char *e = getenv("B200Q4_TILE_MIN_M")) g.tile_min_m = atoi(e);
     if (const char *e = getenv("B200Q4_FUSE_MAX_K")) g.fuse_max_k = atoi(e);
     if (const char *e = getenv("B200Q4_PIPE_FLAGS")) g.pipe_flags = atoi(e);
+    if (const char *e = getenv("B200Q4_ZERO_COPY")) g.zero_copy = atoi(e) != 0;
+    if (cudaHostAlloc(reinterpret_cast<void **>(&g.h_flag), 64, cudaHostAllocMapped) == cudaSuccess &&
+        cudaHostGetDevicePointer(reinterpret_cast<void **>(&g.d_flag), g.h_flag, 0) == cudaSuccess) {
+        *g.h_flag = 0; g.hseq = 0;
+    } else {
+        cudaGetLastError();
+        g.h_flag = nullptr; g.d_flag = nullptr;          // no mapped memory: the copy path serves every call
+    }
     if (const char *e = getenv("B200Q4_DBG")) if (atoi(e) != 0) {
         CK(cudaMalloc(&g.d_dbg, 256 * 16 * sizeof(unsigned long long)));
         CK(cudaMemset(g.d_dbg, 0, 256 * 16 * sizeof(unsigned long long)));
@@ -522,6 +576,8 @@ void b200q4_shutdown(void)
     if (g.device < 0) return;
     cudaSetDevice(g.device);
     cudaStreamSynchronize(g.stream);
+    if (g.h_flag) cudaFreeHost(g.h_flag);
+    g.h_flag = nullptr; g.d_flag = nullptr;
     cudaFree(g.d_ticket); g.d_ticket = nullptr;
     cudaFree(g.d_done); g.d_done = nullptr;
     cudaFree(g.d_yloc); g.d_yloc = nullptr; g.yloc_cap = 0;
@@ -679,6 +735,23 @@ int b200q4_mul_mat(const b200q4_weight *w, const float *x, int M, size_t x_strid
     if (x_stride < (size_t)w->K * 4 || y_stride < (size_t)w->N * 4) return fail(B200Q4_EINVAL, "mul_mat: stride smaller than a row");
     if (M == 0 || w->N == 0) return B200Q4_OK;
     if (int rc = ensure(g.d_x, g.x_cap, (size_t)M * w->K * 4)) return rc;
+    const bool decode = !(g.tile_min_m > 0 && M >= g.tile_min_m);
+    if (g.zero_copy && decode && g.h_flag && reinterpret_cast<uintptr_t>(x) % 16 == 0 && x_stride % 16 == 0 && y_stride % 4 == 0) {
+        const float *xa = static_cast<const float *>(pinned_alias(x));
+        float *ya = xa ? static_cast<float *>(pinned_alias(y)) : nullptr;
+        if (xa && ya) {
+            const long total = (long)M * (w->K / 4);
+            const int blocks = (int)((total + 255) / 256);
+            CK(launch_pdl(fetch_rows_kernel, blocks, 256, g.stream, xa, x_stride / 4, M, w->K, g.d_x));
+            g.launches++;
+            if (int rc = mul_mat_dev_locked(w, g.d_x, M, (size_t)w->K * 4, ya, y_stride, g.stream, nullptr)) return rc;
+            const uint32_t seq = ++g.hseq;
+            signal_host_kernel<<<1, 1, 0, g.stream>>>(g.d_flag, seq);
+            g.launches++;
+            CK(cudaGetLastError());
+            return wait_host_flag(seq);
+        }
+    }
     if (int rc = ensure(g.d_y, g.y_cap, (size_t)M * w->N * 4)) return rc;
     CK(cudaMemcpy2DAsync(g.d_x, (size_t)w->K * 4, x, x_stride, (size_t)w->K * 4, M, cudaMemcpyHostToDevice, g.stream));
     if (int rc = mul_mat_dev_locked(w, g.d_x, M, (size_t)w->K * 4, g.d_y, (size_t)w->N * 4, g.stream, nullptr)) return rc;
