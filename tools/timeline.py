@@ -35,7 +35,8 @@ b = buf[:148].astype(np.int64)
 t0 = b[:, 0].min()
 names = {0: "kernel start", 1: "producer: static tasks issued", 2: "producer: past griddepsync", 3: "consumers: past griddepsync",
          4: "consumers: prologue done", 5: "consumer0: first stage landed", 10: "producer: last copy issued", 9: "consumer0: last stage landed (or stop)",
-         6: "consumer0: loop done", 7: "reducer done", 8: "producer done"}
+         6: "consumer0: loop done", 11: "reducer: last stage's partials seen", 12: "reducer: last stage summed",
+         13: "reducer: stop marker seen", 7: "reducer done", 8: "producer done"}
 for sidx, nm in names.items():
     v = (b[:, sidx] - t0) / 1e3
     print(f"{nm:34s} min {v.min():7.2f}  med {np.median(v):7.2f}  max {v.max():7.2f} us")

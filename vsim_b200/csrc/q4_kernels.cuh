@@ -1096,6 +1096,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             }
             const int4 dsc = s_desc[s];
             if (dsc.x < 0) break;
+            if (lane == 0) PIPE_STAMP(11);               // (timeline builds) the last stage's partials became visible
             const int task = dsc.w;
             int T = dsc.z;
             int left = p.C - dsc.y;                      // units of tile T from the stage's first unit on
@@ -1144,9 +1145,11 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
                 if (left == 0) { ++T; left = p.C; }
             }
             __syncwarp();
+            if (lane == 0) PIPE_STAMP(12);               // (timeline builds) the last stage is summed
             if (lane == 0) mbar_arrive(&bar_empty[s]);
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
+        if (lane == 0) PIPE_STAMP(13);                   // (timeline builds) stop marker seen
         if (curT >= 0) emit(curT, curTask);
         if (!sliced) peer_signal(p.peer, lane);
         if (lane == 0) PIPE_STAMP(7);
