@@ -391,7 +391,7 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
             }
             g.launches++;
         }
-        PeerOut po;
+        PeerOut po{};
         if (peer) {                                      // rows m0.. of every rank's Y; only the last launch signals
             po = *peer;
             for (int b = 0; b < 2; b++)
@@ -399,7 +399,13 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
                     po.y[b][r] = reinterpret_cast<float *>(reinterpret_cast<char *>(po.y[b][r]) + (size_t)m0 * y_stride);
             if (m0 + MP < M) po.done = nullptr;
         }
-        if ((rc = run_pipe(w, mc, pp, fused, xs, x_stride / 4, yo, y_stride / 4, st, peer ? &po : nullptr))) return rc;
+        PeerOut pk = po;                                 // the decode kernel stores to the peers but never signals
+        pk.done = nullptr;
+        if ((rc = run_pipe(w, mc, pp, fused, xs, x_stride / 4, yo, y_stride / 4, st, peer ? &pk : nullptr))) return rc;
+        if (peer && pp.PP == 1 && po.done) {             // last launch of an unsliced call: publish the exchange
+            CK(launch_pdl(peer_signal_kernel, 1, 32, st, po));
+            g.launches++;
+        }
         if (pp.PP > 1) {                                 // K-sliced: the pieces are parked, this adds them up and stores Y
             PeerOut fo;
             if (peer) fo = po; else { fo = PeerOut{}; fo.world = 1; }

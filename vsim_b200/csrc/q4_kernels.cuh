@@ -621,6 +621,20 @@ __global__ void wait_flags_kernel(const uint32_t *flags, int world, const uint32
     if (r >= world) return;
     peer_wait_one(flags, r, ld_volatile_u32(seq_ctr));
 }
+// Publishes an exchange whose peer stores were issued by the PREVIOUS kernel in the stream (the decode kernel's
+// epilogue).  PDL-chained: cudaGridDependencySynchronize returns once that kernel has completed and flushed its
+// stores, then one system fence and one add of the whole exchange per rank.  Keeping the NVLink round trip of
+// the fence out of the decode kernel lets its CTAs exit -- and the next launch start filling its stage ring --
+// 1.7 us earlier (tools/p2pbench).  <<<1, 32>>>
+__global__ void peer_signal_kernel(PeerOut po)
+{
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
+    __threadfence_system();
+    __syncwarp();
+    if ((int)threadIdx.x < po.world) peer_add_share(po, threadIdx.x);
+    if (threadIdx.x == 0) peer_count_done(po);
+}
 // unfused variant for launches whose kernel has no peer epilogue (the tile kernel): copies this rank's
 // [M][ncols] slice from a local buffer into every rank's Y, then signals like peer_signal
 __global__ void scatter_slice_kernel(const float *__restrict__ src, size_t src_stride, int M, int ncols, size_t y_stride, PeerOut po)
