@@ -266,10 +266,10 @@ def test_pack_kernel_path_equals_fused_prologue(gpu, oracle, qt, tag, n, k, m):
 
 @pytest.mark.parametrize("qt,tag", TYPES)
 def test_k_sliced_many_pieces_per_cta(gpu, oracle, qt, tag):
-    """K = 8192 (two K-slices), N = 40000: each CTA parks more than 32 pieces, so the parked-piece list is
-    flushed mid-stream as well as at the end; twice on the same tensor (the arrival counters re-arm themselves)."""
+    """K = 12288 (three K-slices), N = 30000: each CTA parks ~38 pieces for the finalize kernel; twice on the same
+    tensor (workspace slots and ticket counters are reused)."""
     rng = np.random.default_rng(99)
-    n, k = 40000, 8192
+    n, k = 30000, 12288
     wf = rng.random((n, k), dtype=np.float32)
     wf -= np.float32(0.5)
     wf *= np.float32(0.1)
@@ -314,6 +314,32 @@ def test_zero_copy_host_path_equals_copy_path(gpu, oracle, qt, tag, n, k, m):
     finally:
         L.b200q4_host_free(C.c_void_p(hx))
         L.b200q4_host_free(C.c_void_p(hy))
+    w.free()
+
+
+@pytest.mark.parametrize("qt,tag", TYPES)
+@pytest.mark.parametrize("n,k,m", [(700, 5120, 1), (300, 6144, 2), (130, 4128, 1), (64, 8192, 8), (1000, 8192, 1), (50, 4160, 5)])
+def test_k_slicing_forced_on_short_rows(gpu, oracle, qt, tag, n, k, m):
+    """By default rows of K <= 8192 (M <= 2) stay whole; forcing K-slicing from K > 2048 on must give the same
+    result up to the rounding of the piece-wise sums (and the oracle's bar either way)."""
+    import ctypes as C
+    L = gpu.load_library()
+    L.b200q4_debug_set_slice_min_c.restype = C.c_int
+    L.b200q4_debug_set_slice_min_c.argtypes = [C.c_int]
+    rng = np.random.default_rng(n + k + m)
+    wq = oracle.quantize_rows(qt, rng.uniform(-0.05, 0.05, (n, k)).astype(np.float32))
+    x = rng.standard_normal((m, k)).astype(np.float32)
+    w = gpu.Q4Weight(qt, wq, n, k)
+    y_default = gpu.mul_mat(w, x)
+    old = L.b200q4_debug_set_slice_min_c(16)
+    try:
+        y_sliced = gpu.mul_mat(w, x)
+    finally:
+        L.b200q4_debug_set_slice_min_c(old)
+    yr = oracle.mul_mat(qt, wq, n, k, x, nth=8)
+    assert_close(y_default, yr, f"{tag} default")
+    assert_close(y_sliced, yr, f"{tag} sliced")
+    assert np.abs(y_sliced - y_default).max() <= 4e-6 * np.abs(yr).max()
     w.free()
 
 

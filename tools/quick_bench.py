@@ -22,6 +22,8 @@ def main():
     shapes = [(16384, 4096)]
     if "--all" in sys.argv:
         shapes += [(4096, 4096), (4096, 16384), (50400, 4096), (6144, 24576)]
+    if "--neox" in sys.argv:
+        shapes = [(6144, 6144), (24576, 6144), (6144, 24576), (5120, 5120), (20480, 5120)]
     ms_list = [1, 8, 16, 64] if "--m" not in sys.argv else [int(v) for v in sys.argv[sys.argv.index("--m") + 1].split(",")]
     vsim_b200.init(0)
     L = vsim_b200.load_library()

@@ -56,6 +56,7 @@ struct Ctx {
     bool zero_copy = true;           // B200Q4_ZERO_COPY=0: always stage host buffers through cudaMemcpy
     uint32_t *h_flag = nullptr, *d_flag = nullptr;   // mapped host word the stream writes when a zero-copy call is complete
     uint32_t hseq = 0;
+    int slice_min_c = 0;             // B200Q4_SLICE_MIN_C: tiles longer than this many units (4 quant blocks each) are K-sliced; 0 = default rule
     int pipe_flags = 0;              // B200Q4_PIPE_FLAGS: development knobs of the decode kernel (PipeParams::flags)
     uint64_t launches = 0;
     std::recursive_mutex mu;
@@ -109,9 +110,13 @@ struct PipePlan { int MP, stages, PP, TS, ntasks, ncw, nbp, gnbp; bool b8, m1; s
 constexpr int PIPE_MAX_CLASSES = 62;                   // K-slices per tile the ticket array has room for (K <= 253,952)
 
 // K-slicing geometry (see q4_gemv_pipe_kernel): PP pieces per tile of TS units each; PP = 1 -> unsliced
-void slice_geometry(int C, int &PP, int &TS, int &ntasks, int n_tiles)
+void slice_geometry(int C, int MP, int &PP, int &TS, int &ntasks, int n_tiles)
 {
-    if (C > 32) {                                       // more than one stage per tile: slice, one stage or less per piece
+    // Measured (tools/quick_bench.py --neox): for M <= 2 a tile of up to two stages (K <= 8192) is faster whole --
+    // slicing buys a shorter prologue but costs the finalize launch on the dependency chain; the 8-row kernel's
+    // 256-byte-per-block pack makes slicing pay from K > 4096 on.
+    const int min_c = g.slice_min_c > 0 ? g.slice_min_c : (MP == 8 ? 32 : 64);
+    if (C > min_c) {                                    // slice: one stage or less per piece
         PP = (C + 31) / 32;
         TS = (C + PP - 1) / PP;
         TS = (TS + 1) & ~1;                            // even: unit pairs stay aligned to quant-block octets
@@ -132,7 +137,8 @@ PipePlan pipe_plan(const b200q4_weight *w, int M, bool fuse)
 {
     PipePlan pp{};
     const int type = w->type;
-    slice_geometry(w->C, pp.PP, pp.TS, pp.ntasks, w->n_tiles);
+    pp.MP = (M <= 2) ? 2 : 8;
+    slice_geometry(w->C, pp.MP, pp.PP, pp.TS, pp.ntasks, w->n_tiles);
     const size_t optin = (size_t)(g.smem_optin > 0 ? g.smem_optin : 232448);
     auto stage_of = [&](int MP, int ncw) { return (size_t)2 * ncw * chunk_bytes(type) + (size_t)2 * ncw * (MP == 2 ? 128 : 512); };
     // quant blocks a CTA keeps in shared memory: its K-slice, or the whole (padded) row
@@ -143,8 +149,10 @@ PipePlan pipe_plan(const b200q4_weight *w, int M, bool fuse)
         const size_t planes = ((size_t)(type == 0 ? 2 : 3) * nbp * rows * 4 + 15) & ~(size_t)15;
         return (size_t)nbp * (MP == 2 && b8 ? 256 : rows * 32) + planes + 3 * PIPE_MAX_STAGES * 8 + PIPE_MAX_STAGES * 16 + 128 + 256;
     };
-    pp.MP = (M <= 2) ? 2 : 8;
-    if (pp.MP == 8 && fixed(8, false, false) + 2 * stage_of(8, 16) > optin) pp.MP = 2;
+    if (pp.MP == 8 && fixed(8, false, false) + 2 * stage_of(8, 16) > optin) {     // (cannot happen with K-slicing; kept as a guard)
+        pp.MP = 2;
+        slice_geometry(w->C, pp.MP, pp.PP, pp.TS, pp.ntasks, w->n_tiles);
+    }
     pp.m1 = pp.MP == 2 && M == 1 && (fuse || !g.two_ctas);
     // Optional: two CTAs of 8 consumer warps per SM (each gets half of the SM's shared memory minus
     // the 1 KB the hardware reserves per CTA) with the 8-column code layout and >= 3 stages of ring.
@@ -559,6 +567,7 @@ int b200q4_init(int device)
     if (const char *e = getenv("B200Q4_TILE_MIN_M")) g.tile_min_m = atoi(e);
     if (const char *e = getenv("B200Q4_FUSE_MAX_K")) g.fuse_max_k = atoi(e);
     if (const char *e = getenv("B200Q4_PIPE_FLAGS")) g.pipe_flags = atoi(e);
+    if (const char *e = getenv("B200Q4_SLICE_MIN_C")) g.slice_min_c = atoi(e) < 16 ? 16 : atoi(e);
     if (const char *e = getenv("B200Q4_ZERO_COPY")) g.zero_copy = atoi(e) != 0;
     if (cudaHostAlloc(reinterpret_cast<void **>(&g.h_flag), 64, cudaHostAllocMapped) == cudaSuccess &&
         cudaHostGetDevicePointer(reinterpret_cast<void **>(&g.d_flag), g.h_flag, 0) == cudaSuccess) {
@@ -895,6 +904,16 @@ int b200q4_debug_set_fuse_max_k(int k)
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     const int old = g.fuse_max_k;
     g.fuse_max_k = k;
+    return old;
+}
+
+// development / test knob (not part of b200q4.h): tiles longer than this many units are K-sliced
+// (0 = the default rule: 64 for M <= 2, 32 for 3 <= M <= 8).  Returns the previous value.
+int b200q4_debug_set_slice_min_c(int c)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    const int old = g.slice_min_c;
+    g.slice_min_c = c;
     return old;
 }
 
