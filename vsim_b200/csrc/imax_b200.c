@@ -153,6 +153,24 @@ static void hook_mul_mat(int want_type, const char *who, const hook_params *para
     else
         rc = b200q4_mul_mat(w, (const float *)src1->data, M, src1->nb[1], (float *)dst->data, dst->nb[1]);
     if (rc != B200Q4_OK) die(who);
+    /* development aid: B200Q4_DUMP_DIR=<dir> writes the operands and the result of the first 400 calls
+     * ({type, N, K, M} ints, X rows, Y rows) for offline comparison against the oracle (tools/dropin_dump_check.py) */
+    {
+        static int dump_n = 0;
+        const char *dir = getenv("B200Q4_DUMP_DIR");
+        if (dir && dump_n < 400) {
+            char path[512];
+            snprintf(path, sizeof path, "%s/call_%04d.bin", dir, dump_n++);
+            FILE *f = fopen(path, "wb");
+            if (f) {
+                const int hdr[4] = {(int)src0->type, src0->ne[1], src0->ne[0], M};
+                fwrite(hdr, sizeof hdr, 1, f);
+                for (int m = 0; m < M; m++) fwrite((const char *)src1->data + (size_t)m * src1->nb[1], sizeof(float), (size_t)src0->ne[0], f);
+                for (int m = 0; m < M; m++) fwrite((const char *)dst->data + (size_t)m * dst->nb[1], sizeof(float), (size_t)src0->ne[1], f);
+                fclose(f);
+            }
+        }
+    }
 }
 
 /* imax.c:1133-1139.  THREAD and LANE are the reference's IMAX lane selectors
