@@ -155,6 +155,18 @@ int b200q4_mul_mat_dev_allgather(const b200q4_weight *w, const float *d_x, int M
 int b200q4_wait_flags(const uint32_t *local_flags, int world, const uint32_t *seq_counter, void *stream);
 int b200q4_sync(void *stream);
 
+/* ---- exact mode ----------------------------------------------------------------
+ * on != 0: every mul_mat entry point computes ggml_vec_dot_q4_0/_q4_1's own rounding
+ * sequence (ggml.c:484-510, 525-552 == imax.c:1210-1228: one strictly sequential
+ * fp32 chain per output, every product and sum individually rounded, no FMA), so Y
+ * is BIT-IDENTICAL to the reference CPU path and whole programs reproduce its logits
+ * and greedy token streams exactly.  Several times slower than the default kernels
+ * (whose exact-integer block sums are closer to the real-number result but differ in
+ * the last bits -- which the reference's fp16-table gelu and 4-bit activation
+ * re-quantization amplify downstream).  Returns the previous setting.  Also
+ * selectable with the environment variable B200Q4_EXACT=1 at b200q4_init().      */
+int b200q4_set_exact(int on);
+
 /* Pinned host memory for callers that want zero-staging H2D/D2H copies.      */
 void *b200q4_host_alloc(size_t bytes);
 void  b200q4_host_free(void *p);

@@ -26,12 +26,13 @@ def test_dropin_binaries_link_only_the_hook_symbols():
     assert ours == ["imax_ggml_compute_forward_mul_mat_q4_0_f32", "imax_ggml_compute_forward_mul_mat_q4_1_f32"], ours
 
 
-def _run(binary, model, prompt="1 2 3 4 5", n_predict=8, logits=False, threads=4):
+def _run(binary, model, prompt="1 2 3 4 5", n_predict=8, logits=False, threads=4, env=None):
     cmd = [str(binary), "gptneox", "-m", str(model), "--prompt", prompt, "--seed", "42", "--threads", str(threads),
            "--n_predict", str(n_predict), "--top_k", "1", "--top_p", "1.0", "--temp", "1.0", "--repeat_penalty", "1.0"]
     if logits:
         cmd.append("--return_logits")
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    import os
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, **(env or {})})
     assert r.returncode == 0, r.stderr[-2000:] + r.stdout[-2000:]
     return r.stdout
 
@@ -87,3 +88,22 @@ def test_vsim_neox_end_to_end_tokens_and_logits(tmp_path, qt, tag):
     tr = _tokens(_run(REF_BIN, model, n_predict=12))
     tg = _tokens(_run(B200_BIN, model, n_predict=12))
     assert tr == tg, (tr, tg)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("qt,tag", [(Q4_0, "q4_0"), (Q4_1, "q4_1")])
+def test_vsim_neox_exact_mode_reproduces_the_reference_bit_for_bit(tmp_path, qt, tag):
+    """B200Q4_EXACT=1: the GPU-backed program prints the SAME logits (every printed digit) and the same greedy
+    tokens as the unmodified CPU binary -- the mul_mat outputs are bit-identical, so nothing downstream can differ.
+    A wider and deeper model than the tolerance test above: n_embd 512, 6 layers, 24 generated tokens."""
+    if not (REF_BIN.exists() and B200_BIN.exists()):
+        pytest.skip("oracle/_ref vsim binaries not built")
+    from tests.helpers.neox_file import write_neox
+    model = tmp_path / f"exact-{tag}.bin"
+    write_neox(model, qt, n_vocab=512, n_embd=512, n_head=8, n_layer=6, n_rot=32, seed=3)
+    ex = {"B200Q4_EXACT": "1"}
+    lr = _logits(_run(REF_BIN, model, logits=True))
+    lg = _logits(_run(B200_BIN, model, logits=True, env=ex))
+    assert lr.shape == lg.shape
+    assert np.array_equal(lr, lg), np.abs(lr - lg).max()
+    assert _tokens(_run(REF_BIN, model, n_predict=24)) == _tokens(_run(B200_BIN, model, n_predict=24, env=ex))

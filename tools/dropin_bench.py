@@ -85,10 +85,13 @@ def write_model(path: Path, n_vocab, n_embd, n_head, n_layer, n_rot, seed=0, gai
     return path.stat().st_size
 
 
+GPU_ENV: dict = {}
+
+
 def prompt_logits(binary: Path, model: Path, threads: int, timeout: int):
     cmd = [str(binary), "gptneox", "-m", str(model), "--prompt", "1 2 3 4 5", "--seed", "42", "--threads", str(threads),
            "--n_predict", "1", "--top_k", "1", "--top_p", "1.0", "--temp", "1.0", "--repeat_penalty", "1.0", "--return_logits"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env={**os.environ, **(GPU_ENV if binary.name == "vsim-b200" else {})})
     rows = [np.array(l.split()[1:-1] if l.rstrip().endswith("<END|>") else l.split()[1:], dtype=np.float64)
             for l in r.stdout.splitlines() if l.startswith("logits:")]
     if r.returncode != 0 or not rows:
@@ -100,7 +103,7 @@ def run(binary: Path, model: Path, n_predict: int, threads: int, timeout: int):
     cmd = [str(binary), "gptneox", "-m", str(model), "--prompt", "1 2 3 4 5", "--seed", "42", "--threads", str(threads),
            "--n_predict", str(n_predict), "--top_k", "1", "--top_p", "1.0", "--temp", "1.0", "--repeat_penalty", "1.0"]
     t0 = time.perf_counter()
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env={**os.environ, **(GPU_ENV if binary.name == "vsim-b200" else {})})
     dt = time.perf_counter() - t0
     if r.returncode != 0:
         raise RuntimeError(f"{binary.name} failed: {r.stderr[-800:]}{r.stdout[-800:]}")
@@ -120,9 +123,12 @@ def main() -> int:
     ap.add_argument("--gain", type=float, default=0.5, help="per-matrix gain of the random model (see write_model)")
     ap.add_argument("--cpu-n", default="4,20", help="n_predict pair for the CPU build")
     ap.add_argument("--gpu-n", default="16,272", help="n_predict pair for the GPU-backed build (n_ctx is 512)")
+    ap.add_argument("--exact", action="store_true", help="GPU-backed build in exact mode (B200Q4_EXACT=1: bit-identical mul_mats)")
     ap.add_argument("--keep", action="store_true", help="keep the model file")
     ap.add_argument("--timeout", type=int, default=900)
     args = ap.parse_args()
+    if args.exact:
+        GPU_ENV["B200Q4_EXACT"] = "1"
     cpu_bin, gpu_bin = REF / "vsim-ubuntu", REF / "vsim-b200"
     if not (cpu_bin.exists() and gpu_bin.exists()):
         print(json.dumps({"unavailable": "oracle/_ref/vsim-ubuntu / vsim-b200 not built (make -C oracle needs /root/reference)"}))
@@ -152,7 +158,7 @@ def main() -> int:
             "threads": {"cpu_reference": args.threads, "b200_hook": args.gpu_threads}, "host_cores": os.cpu_count(),
             "prompt_logits_max_abs_diff_over_max_abs": float(np.abs(lg - lc).max() / np.abs(lc).max()),
             "prompt_logits_argmax": {"cpu_reference": int(lc.argmax()), "b200_hook": int(lg.argmax())},
-            "random_model_gain": args.gain,
+            "random_model_gain": args.gain, "b200_mode": "exact (B200Q4_EXACT=1)" if args.exact else "default",
             "n_predict": {"cpu_reference": c["n_predict"], "b200_hook": g["n_predict"]}, "prompt_tokens": 5,
             "t_predict_s": {"cpu_reference": c["t_predict_s"], "b200_hook": g["t_predict_s"]},
             "cpu_reference_ms_per_token": c["ms_per_token"], "b200_hook_ms_per_token": g["ms_per_token"],

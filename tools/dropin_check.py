@@ -16,10 +16,11 @@ def logits(binary, threads, env=None):
         return np.zeros(50400)
     return rows[0]
 res = {}
-for tag, b in (("cpu", d.REF / 'vsim-ubuntu'), ("gpu", d.REF / 'vsim-b200')):
+for tag, b, env in (("cpu", d.REF / 'vsim-ubuntu', None), ("gpu-default", d.REF / 'vsim-b200', None), ("gpu-exact", d.REF / 'vsim-b200', {"B200Q4_EXACT": "1"})):
     for th in (1, 4, 16):
-        res[(tag, th)] = logits(b, th)
-ref = res[("cpu", 1)]
+        res[(tag, th)] = logits(b, th, env)
 for k, v in res.items():
-    print(k, "argmax", v.argmax(), "max|diff vs cpu/1| / max", np.abs(v - ref).max() / np.abs(ref).max(), flush=True)
+    ref = res[("cpu", k[1])]
+    print(k, "argmax", v.argmax(), "max|diff vs cpu at the SAME thread count| / max", np.abs(v - ref).max() / np.abs(ref).max(),
+          "| vs cpu/1:", np.abs(v - res[("cpu", 1)]).max() / np.abs(ref).max(), flush=True)
 p.unlink()

@@ -154,7 +154,7 @@ static void hook_mul_mat(int want_type, const char *who, const hook_params *para
         rc = b200q4_mul_mat(w, (const float *)src1->data, M, src1->nb[1], (float *)dst->data, dst->nb[1]);
     if (rc != B200Q4_OK) die(who);
     /* development aid: B200Q4_DUMP_DIR=<dir> writes the operands and the result of the first 400 calls
-     * ({type, N, K, M} ints, X rows, Y rows) for offline comparison against the oracle (tools/dropin_dump_check.py) */
+     * ({type, N, K, M} ints, X rows, Y rows) for offline checking (tools/dropin_dump_check.py) */
     {
         static int dump_n = 0;
         const char *dir = getenv("B200Q4_DUMP_DIR");

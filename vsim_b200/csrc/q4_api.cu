@@ -56,6 +56,9 @@ struct Ctx {
     bool zero_copy = true;           // B200Q4_ZERO_COPY=0: always stage host buffers through cudaMemcpy
     uint32_t *h_flag = nullptr, *d_flag = nullptr;   // mapped host word the stream writes when a zero-copy call is complete
     uint32_t hseq = 0;
+    bool exact = false;              // b200q4_set_exact / B200Q4_EXACT=1: the reference's own fp32 rounding sequence (bit-identical Y)
+    uint8_t *d_exq = nullptr; size_t exq_cap = 0;       // exact mode: reference-format quantized activation rows
+    float *d_exdeq = nullptr; size_t exdeq_cap = 0;     // exact mode: the floats the reference's dot product forms from them
     int slice_min_c = 0;             // B200Q4_SLICE_MIN_C: tiles longer than this many units (4 quant blocks each) are K-sliced; 0 = default rule
     int pipe_flags = 0;              // B200Q4_PIPE_FLAGS: development knobs of the decode kernel (PipeParams::flags)
     uint64_t launches = 0;
@@ -339,6 +342,48 @@ int run_tile(const b200q4_weight *w, const float *d_x, size_t x_stride_f, const 
 #undef TILE_DISPATCH
 }
 
+// ---- exact mode: bit-identical to ggml_vec_dot_q4_0/_q4_1 (see q4_kernels.cuh) ----------------------------
+int run_exact(const b200q4_weight *w, const float *d_x, size_t x_stride_f, const uint8_t *d_wdata, int M,
+              float *d_y, size_t y_stride_f, cudaStream_t st)
+{
+    const size_t rb = (size_t)w->nb * (w->type == 0 ? 20 : 24);
+    int rc;
+    if ((rc = ensure(g.d_exdeq, g.exdeq_cap, (size_t)M * w->K * sizeof(float)))) return rc;
+    const uint8_t *rows = d_wdata;
+    if (!rows) {                                         // byte-exact quantize_row_q4_0/_q4_1 image of X
+        if ((rc = ensure(g.d_exq, g.exq_cap, rb * (size_t)M))) return rc;
+        const long warps = (long)w->nb * M;
+        const int blocks = (int)((warps * 32 + 255) / 256);
+        if (w->type == 0) quantize_rows_ref_kernel<0><<<blocks, 256, 0, st>>>(d_x, x_stride_f, M, w->nb, g.d_exq);
+        else              quantize_rows_ref_kernel<1><<<blocks, 256, 0, st>>>(d_x, x_stride_f, M, w->nb, g.d_exq);
+        g.launches++;
+        rows = g.d_exq;
+    }
+    {
+        const long total = (long)M * w->K;
+        const int blocks = (int)((total + 255) / 256);
+        if (w->type == 0) exact_dequant_act_kernel<0><<<blocks, 256, 0, st>>>(rows, M, w->nb, g.d_exdeq);
+        else              exact_dequant_act_kernel<1><<<blocks, 256, 0, st>>>(rows, M, w->nb, g.d_exdeq);
+        g.launches++;
+    }
+    const int blocks = (w->N + 127) / 128;
+    for (int m0 = 0; m0 < M; m0 += 8) {
+        const int mc = M - m0 < 8 ? M - m0 : 8;
+        const float *dq = g.d_exdeq + (size_t)m0 * w->K;
+        float *yo = d_y + (size_t)m0 * y_stride_f;
+#define EXACT(QT)                                                                                                             \
+        if (mc == 1)      mul_mat_exact_kernel<QT, 1><<<blocks, 128, 0, st>>>(w->d_wt, w->N, w->C, w->nb, dq, mc, w->K, yo, y_stride_f); \
+        else if (mc == 2) mul_mat_exact_kernel<QT, 2><<<blocks, 128, 0, st>>>(w->d_wt, w->N, w->C, w->nb, dq, mc, w->K, yo, y_stride_f); \
+        else if (mc <= 4) mul_mat_exact_kernel<QT, 4><<<blocks, 128, 0, st>>>(w->d_wt, w->N, w->C, w->nb, dq, mc, w->K, yo, y_stride_f); \
+        else              mul_mat_exact_kernel<QT, 8><<<blocks, 128, 0, st>>>(w->d_wt, w->N, w->C, w->nb, dq, mc, w->K, yo, y_stride_f);
+        if (w->type == 0) { EXACT(0) } else { EXACT(1) }
+#undef EXACT
+        g.launches++;
+    }
+    CK(cudaGetLastError());
+    return B200Q4_OK;
+}
+
 int ensure_scratch(int nbp, int MP)
 {
     int rc;
@@ -354,6 +399,21 @@ int mul_mat_dev_locked(const b200q4_weight *w, const float *d_x, int M, size_t x
     if ((x_stride % 4) || (y_stride % 4)) return fail(B200Q4_EINVAL, "mul_mat: strides must be multiples of 4 bytes");
     if (M == 0 || w->N == 0) return B200Q4_OK;
     if ((long)w->n_tiles * w->C > 0x7fffffffL) return fail(B200Q4_EINVAL, "tensor too large");
+    if (g.exact) {
+        if (!peer) return run_exact(w, d_x, x_stride / 4, d_wdata, M, d_y, y_stride / 4, st);
+        // sharded: the slice is computed locally, then stored into every rank's Y like the tile path below
+        if (int rc = ensure(g.d_yloc, g.yloc_cap, (size_t)M * w->N * sizeof(float))) return rc;
+        wait_flags_kernel<<<1, 32, 0, st>>>(peer->local_flags, peer->world, peer->seq_ctr);
+        g.launches++;
+        if (int rc = run_exact(w, d_x, x_stride / 4, d_wdata, M, g.d_yloc, (size_t)w->N, st)) return rc;
+        const long total = (long)M * w->N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 4 * g.sms) blocks = 4 * g.sms;
+        scatter_slice_kernel<<<blocks, 256, 0, st>>>(g.d_yloc, (size_t)w->N, M, w->N, y_stride / 4, *peer);
+        g.launches++;
+        CK(cudaGetLastError());
+        return B200Q4_OK;
+    }
     if (g.tile_min_m > 0 && M >= g.tile_min_m) {
         if (!peer) return run_tile(w, d_x, x_stride / 4, d_wdata, M, d_y, y_stride / 4, st);
         // sharded: wait for the previous exchange (X), let the tile kernel write this rank's slice locally,
@@ -569,6 +629,7 @@ int b200q4_init(int device)
     if (const char *e = getenv("B200Q4_PIPE_FLAGS")) g.pipe_flags = atoi(e);
     if (const char *e = getenv("B200Q4_SLICE_MIN_C")) g.slice_min_c = atoi(e) < 16 ? 16 : atoi(e);
     if (const char *e = getenv("B200Q4_ZERO_COPY")) g.zero_copy = atoi(e) != 0;
+    if (const char *e = getenv("B200Q4_EXACT")) g.exact = atoi(e) != 0;
     if (cudaHostAlloc(reinterpret_cast<void **>(&g.h_flag), 64, cudaHostAllocMapped) == cudaSuccess &&
         cudaHostGetDevicePointer(reinterpret_cast<void **>(&g.d_flag), g.h_flag, 0) == cudaSuccess) {
         *g.h_flag = 0; g.hseq = 0;
@@ -596,6 +657,8 @@ void b200q4_shutdown(void)
     cudaFree(g.d_ticket); g.d_ticket = nullptr;
     cudaFree(g.d_done); g.d_done = nullptr;
     cudaFree(g.d_yloc); g.d_yloc = nullptr; g.yloc_cap = 0;
+    cudaFree(g.d_exq); g.d_exq = nullptr; g.exq_cap = 0;
+    cudaFree(g.d_exdeq); g.d_exdeq = nullptr; g.exdeq_cap = 0;
     cudaFree(g.d_aq); cudaFree(g.d_ap); cudaFree(g.d_partial); cudaFree(g.d_x); cudaFree(g.d_y); cudaFree(g.d_tmp);
     cudaFree(g.d_tpack); cudaFree(g.d_tpartial); cudaFree(g.d_tcounters);
     g.d_tpack = nullptr; g.d_tpartial = nullptr; g.d_tcounters = nullptr;
@@ -853,6 +916,14 @@ int b200q4_mul_mat_transposed(const b200q4_weight *wt, const float *x, int M, si
     return B200Q4_OK;
 }
 
+int b200q4_set_exact(int on)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    const int old = g.exact ? 1 : 0;
+    g.exact = on != 0;
+    return old;
+}
+
 int b200q4_sync(void *stream)
 {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
@@ -924,6 +995,7 @@ const char *b200q4_kernel_for(int type, int M, int N, int K)
 {
     (void)N;
     if ((type != 0 && type != 1) || K <= 0 || K % QK) return "invalid";
+    if (g.exact) return type == 0 ? "q4_0_exact" : "q4_1_exact";
     if (g.tile_min_m > 0 && M >= g.tile_min_m) return type == 0 ? "q4_0_tile_tcgen05" : "q4_1_tile_tcgen05";
     const int mp = (M <= 2) ? 2 : 8;
     return type == 0 ? (mp == 2 ? "q4_0_gemv_pipe_chain4" : "q4_0_gemv_pipe_m8") : (mp == 2 ? "q4_1_gemv_pipe_chain4" : "q4_1_gemv_pipe_m8");

@@ -1369,6 +1369,107 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
 }
 
 // ---------------------------------------------------------------------------
+// Exact mode (b200q4_set_exact / B200Q4_EXACT=1): the reference's OWN rounding sequence, so that Y is
+// bit-identical to the CPU path and whole programs reproduce its logits and token streams exactly.
+// ggml_vec_dot_q4_0 (ggml.c:484-510 == imax.c:1210-1228) is
+//     sumf = 0;  for block i, for byte j:  f0 = d0*(lo0-8), f1 = d0*(hi0-8), f2 = d1*(lo1-8), f3 = d1*(hi1-8);
+//                                          sumf += f0*f2 + f1*f3;
+// with every * and + an individually rounded fp32 operation in exactly this order (the reference is built
+// -msse3: no FMA), and ggml_vec_dot_q4_1 (ggml.c:525-552) the same with f = d*q + m.  That is one strictly
+// sequential chain of K/2 additions per output: no tensor cores, no splitting of K, one thread per weight
+// row with the dequantized activation rows (f2, f3: a function of the activations alone) read as broadcast
+// loads.  Several times slower than the default kernels, whose block sums are exact integers and whose
+// results are closer to the real-number value -- but different in the last bits, which the reference's own
+// graph amplifies (its gelu goes through an fp16 table and every mul_mat re-quantizes its input to 4 bits:
+// a rounding-level difference flips codes downstream).
+// ---------------------------------------------------------------------------
+// reference-format quantized rows -> the floats the reference's dot product forms from them
+template <int QT>
+__global__ void exact_dequant_act_kernel(const uint8_t *__restrict__ rows, int M, int nb, float *__restrict__ deq)
+{
+    const long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)M * nb * QK;
+    if (id >= total) return;
+    const int e = (int)(id % QK);
+    const long bm = id / QK;
+    const int blk = (int)(bm % nb), m = (int)(bm / nb);
+    float v;
+    if (QT == 0) {
+        const uint8_t *b = rows + ((size_t)m * nb + blk) * 20;
+        const float d = *reinterpret_cast<const float *>(b);
+        const uint8_t byte = b[4 + (e >> 1)];
+        const int q = (e & 1) ? (byte >> 4) : (byte & 15);
+        v = __fmul_rn(d, (float)(q - 8));
+    } else {
+        const uint8_t *row = rows + (size_t)m * nb * 24;
+        const float mn = reinterpret_cast<const float *>(row)[blk], d = reinterpret_cast<const float *>(row)[nb + blk];
+        const uint8_t byte = row[(size_t)nb * 8 + (size_t)blk * 16 + (e >> 1)];
+        const int q = (e & 1) ? (byte >> 4) : (byte & 15);
+        v = __fadd_rn(__fmul_rn(d, (float)q), mn);
+    }
+    deq[id] = v;                                         // [m][blk*32 + e]
+}
+
+// one thread per weight row n, MB activation rows per thread; weights from the wtile layout
+template <int QT, int MB>
+__global__ void __launch_bounds__(128) mul_mat_exact_kernel(const uint8_t *__restrict__ wt, int N, int C, int nb,
+                                                            const float *__restrict__ deq, int M, int K,
+                                                            float *__restrict__ y, size_t y_stride)
+{
+    constexpr int CH = chunk_bytes(QT);
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int T = n / TILE_ROWS, r = n % TILE_ROWS, half = r >> 3, g = r & 7;
+    float sum[MB];
+#pragma unroll
+    for (int m = 0; m < MB; m++) sum[m] = 0.0f;
+    for (int c = 0; c < C; c++) {
+        const uint8_t *chunk = wt + ((size_t)T * C + c) * CH;
+        uint4 w[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) w[t] = *reinterpret_cast<const uint4 *>(chunk + half * 512 + (g * 4 + t) * 16);
+        const float4 d04 = *reinterpret_cast<const float4 *>(chunk + 1024 + r * 16);
+        float4 m04 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (QT == 1) m04 = *reinterpret_cast<const float4 *>(chunk + 1280 + r * 16);
+        const float d0v[4] = {d04.x, d04.y, d04.z, d04.w}, m0v[4] = {m04.x, m04.y, m04.z, m04.w};
+#pragma unroll
+        for (int i = 0; i < CHUNK_BLKS; i++) {
+            const int blk = c * CHUNK_BLKS + i;
+            if (blk >= nb) break;                        // padding blocks are not part of the reference's sum
+            const float d0 = d0v[i], m0 = m0v[i];
+            const float *a = deq + (size_t)blk * QK;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const uint32_t word = u4_get(w[t], i);   // bytes 4t .. 4t+3 of the block
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const uint32_t byte = (word >> (8 * b)) & 255u;
+                    const int j = 4 * t + b;
+                    float f0, f1;
+                    if (QT == 0) {
+                        f0 = __fmul_rn(d0, (float)((int)(byte & 15u) - 8));
+                        f1 = __fmul_rn(d0, (float)((int)(byte >> 4) - 8));
+                    } else {
+                        f0 = __fadd_rn(__fmul_rn(d0, (float)(byte & 15u)), m0);
+                        f1 = __fadd_rn(__fmul_rn(d0, (float)(byte >> 4)), m0);
+                    }
+#pragma unroll
+                    for (int m = 0; m < MB; m++) {
+                        if (m < M) {
+                            const float2 f23 = __ldg(reinterpret_cast<const float2 *>(a + (size_t)m * K + 2 * j));
+                            sum[m] = __fadd_rn(sum[m], __fadd_rn(__fmul_rn(f0, f23.x), __fmul_rn(f1, f23.y)));
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MB; m++)
+        if (m < M) y[(size_t)m * y_stride + n] = sum[m];
+}
+
+// ---------------------------------------------------------------------------
 // Transposed-src0 branch (ggml.c:5118-5164 / 5391-5440, ggml_vec_mad_q4_*):
 // Wt is K rows of N quantized values (reference row format, kept as is on the
 // device), activations are NOT quantized.  Y[m][n] = sum_k deq(Wt[k][n]) * X[m][k],
