@@ -478,6 +478,18 @@ def main() -> int:
                                "kernel": vs.kernel_for(qt, m, N_ROWS, K_DIM)})
         for w in w1:
             w.free()
+    # ---- exact mode (bit-identical to the reference's fp32 summation order), for the record ------------------
+    exact = None
+    if world == 1 and not args.no_points:
+        L.b200q4_set_exact(1)
+        try:
+            ms1 = timed(1, w0, 20, 3) / 20
+            ms8 = timed(8, w0, 20, 3) / 20
+        finally:
+            L.b200q4_set_exact(0)
+        exact = {"what": "b200q4_set_exact(1): the reference's own sequential fp32 rounding sequence, Y bit-identical to the CPU path",
+                 "q4_0_M1_us_per_call": ms1 * 1e3, "q4_0_M8_us_per_call": ms8 * 1e3,
+                 "q4_0_M1_GBps": alg_bytes(0, 1) / (ms1 * 1e-3) / 1e9}
     exchange = None
     if world > 1 and po is not None:                       # the same M=1 step with an NCCL all-gather, for comparison
         ms_nccl = timed(M_HEAD, w0, min(args.steps, 200), 5, nccl=True) / min(args.steps, 200)
@@ -530,6 +542,7 @@ def main() -> int:
             "clocks": sampler.summary(),
             "points": points,
             "roofline_prefill": prefill_roofline(points, tpeak, tpeak_src, world),
+            "exact_mode": exact,
             "model_decode": model,
             "model_decode_neox20b": model20,
             "exchange": exchange,
