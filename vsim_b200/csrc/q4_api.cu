@@ -366,7 +366,7 @@ int run_exact(const b200q4_weight *w, const float *d_x, size_t x_stride_f, const
         else              exact_dequant_act_kernel<1><<<blocks, 256, 0, st>>>(rows, M, w->nb, g.d_exdeq);
         g.launches++;
     }
-    const int blocks = (w->N + 127) / 128;
+    const int blocks = w->n_tiles;                       // one block per 16-row tile
     for (int m0 = 0; m0 < M; m0 += 8) {
         const int mc = M - m0 < 8 ? M - m0 : 8;
         const float *dq = g.d_exdeq + (size_t)m0 * w->K;

@@ -1410,41 +1410,61 @@ __global__ void exact_dequant_act_kernel(const uint8_t *__restrict__ rows, int M
     deq[id] = v;                                         // [m][blk*32 + e]
 }
 
-// one thread per weight row n, MB activation rows per thread; weights from the wtile layout
+// One 128-thread block per 16-row weight tile, MB activation rows per launch.  Per chunk (4 quant blocks = 64
+// byte pairs) the block works in two steps:
+//   produce  every thread (row r = tid / 8, pair group q = tid % 8) forms the eight terms s = f0*f2 + f1*f3 of
+//            its row -- independent work, all the rounding of the reference but none of its ordering -- and
+//            leaves them in shared memory, [m][pair][row];
+//   chain    lane (m, row) of the first 16*M threads adds the 64 terms of the chunk to its running sum in pair
+//            order: sumf = sumf + s, the reference's one serial dependency (one FADD per byte pair).
+// The chain step is the floor (K/2 dependent additions per output); the produce step keeps everything else
+// off it.
+constexpr int EXACT_PAIR_STRIDE = 17;                    // floats per pair row in shared memory (16 + 1: spreads the banks)
 template <int QT, int MB>
 __global__ void __launch_bounds__(128) mul_mat_exact_kernel(const uint8_t *__restrict__ wt, int N, int C, int nb,
                                                             const float *__restrict__ deq, int M, int K,
                                                             float *__restrict__ y, size_t y_stride)
 {
     constexpr int CH = chunk_bytes(QT);
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const int T = n / TILE_ROWS, r = n % TILE_ROWS, half = r >> 3, g = r & 7;
-    float sum[MB];
-#pragma unroll
-    for (int m = 0; m < MB; m++) sum[m] = 0.0f;
-    for (int c = 0; c < C; c++) {
+    constexpr int MSTRIDE = 64 * EXACT_PAIR_STRIDE + 8;  // floats per activation row
+    __shared__ float s_s[MB * MSTRIDE];
+    const int T = blockIdx.x, tid = threadIdx.x;
+    const int r = tid >> 3, q = tid & 7, half = r >> 3, g = r & 7;
+    const int i = q >> 1, t0 = (q & 1) * 2;              // this thread's quant block of the chunk and its two nibble words
+    const int cm = tid >> 4, cr = tid & 15;              // chain role: activation row, weight row
+    const bool chain = cm < M && cm < MB;
+    float sum = 0.0f;
+    // this thread's weight words and scales of chunk c (loaded one chunk ahead: the global latency hides behind a whole step)
+    uint32_t nw0 = 0, nw1 = 0;
+    float nd0 = 0.f, nm0 = 0.f;
+    auto fetch = [&](int c) {
         const uint8_t *chunk = wt + ((size_t)T * C + c) * CH;
-        uint4 w[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) w[t] = *reinterpret_cast<const uint4 *>(chunk + half * 512 + (g * 4 + t) * 16);
-        const float4 d04 = *reinterpret_cast<const float4 *>(chunk + 1024 + r * 16);
-        float4 m04 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (QT == 1) m04 = *reinterpret_cast<const float4 *>(chunk + 1280 + r * 16);
-        const float d0v[4] = {d04.x, d04.y, d04.z, d04.w}, m0v[4] = {m04.x, m04.y, m04.z, m04.w};
-#pragma unroll
-        for (int i = 0; i < CHUNK_BLKS; i++) {
-            const int blk = c * CHUNK_BLKS + i;
-            if (blk >= nb) break;                        // padding blocks are not part of the reference's sum
-            const float d0 = d0v[i], m0 = m0v[i];
+        nw0 = __ldg(reinterpret_cast<const uint32_t *>(chunk + half * 512 + (g * 4 + t0) * 16) + i);
+        nw1 = __ldg(reinterpret_cast<const uint32_t *>(chunk + half * 512 + (g * 4 + t0 + 1) * 16) + i);
+        nd0 = __ldg(reinterpret_cast<const float *>(chunk + 1024) + r * 4 + i);
+        if (QT == 1) nm0 = __ldg(reinterpret_cast<const float *>(chunk + 1280) + r * 4 + i);
+    };
+    fetch(0);
+    for (int c = 0; c < C; c++) {
+        const int blk = c * CHUNK_BLKS + i;
+        const uint32_t w2[2] = {nw0, nw1};
+        const float d0 = nd0, m0 = nm0;
+        if (c + 1 < C) fetch(c + 1);
+        if (blk < nb) {
             const float *a = deq + (size_t)blk * QK;
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const uint32_t word = u4_get(w[t], i);   // bytes 4t .. 4t+3 of the block
+            for (int bw = 0; bw < 2; bw++) {
+                const int t = t0 + bw;
+                float4 fa[MB], fb[MB];                   // f2, f3 of byte pairs 4t .. 4t+3 (broadcast loads)
+#pragma unroll
+                for (int m = 0; m < MB; m++) {           // rows >= M recompute row M-1: no branches, the loads pipeline
+                    const size_t mo = (size_t)(m < M ? m : M - 1) * K;
+                    fa[m] = __ldg(reinterpret_cast<const float4 *>(a + mo + 8 * t));
+                    fb[m] = __ldg(reinterpret_cast<const float4 *>(a + mo + 8 * t + 4));
+                }
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
-                    const uint32_t byte = (word >> (8 * b)) & 255u;
-                    const int j = 4 * t + b;
+                    const uint32_t byte = (w2[bw] >> (8 * b)) & 255u;
                     float f0, f1;
                     if (QT == 0) {
                         f0 = __fmul_rn(d0, (float)((int)(byte & 15u) - 8));
@@ -1453,20 +1473,32 @@ __global__ void __launch_bounds__(128) mul_mat_exact_kernel(const uint8_t *__res
                         f0 = __fadd_rn(__fmul_rn(d0, (float)(byte & 15u)), m0);
                         f1 = __fadd_rn(__fmul_rn(d0, (float)(byte >> 4)), m0);
                     }
+                    const int p = i * 16 + 4 * t + b;    // pair index inside the chunk = the reference's (block, j) order
 #pragma unroll
                     for (int m = 0; m < MB; m++) {
-                        if (m < M) {
-                            const float2 f23 = __ldg(reinterpret_cast<const float2 *>(a + (size_t)m * K + 2 * j));
-                            sum[m] = __fadd_rn(sum[m], __fadd_rn(__fmul_rn(f0, f23.x), __fmul_rn(f1, f23.y)));
-                        }
+                        const float4 &v = b < 2 ? fa[m] : fb[m];
+                        const float f2 = (b & 1) ? v.z : v.x, f3 = (b & 1) ? v.w : v.y;
+                        s_s[m * MSTRIDE + p * EXACT_PAIR_STRIDE + r] = __fadd_rn(__fmul_rn(f0, f2), __fmul_rn(f1, f3));
                     }
                 }
             }
         }
-    }
+        __syncthreads();
+        if (chain) {
+            const int np = min(64, (nb - c * CHUNK_BLKS) * 16);      // padding blocks are not part of the reference's sum
+            const float *sp = s_s + cm * MSTRIDE + cr;
+            for (int p0 = 0; p0 < np; p0 += 16) {        // np is a multiple of 16: the loads of a batch first, then the chain
+                float v[16];
 #pragma unroll
-    for (int m = 0; m < MB; m++)
-        if (m < M) y[(size_t)m * y_stride + n] = sum[m];
+                for (int k = 0; k < 16; k++) v[k] = sp[(p0 + k) * EXACT_PAIR_STRIDE];
+#pragma unroll
+                for (int k = 0; k < 16; k++) sum = __fadd_rn(sum, v[k]);
+            }
+        }
+        __syncthreads();
+    }
+    const int n = T * TILE_ROWS + cr;
+    if (chain && n < N) y[(size_t)cm * y_stride + n] = sum;
 }
 
 // ---------------------------------------------------------------------------
