@@ -59,6 +59,7 @@ struct Ctx {
     bool exact = false;              // b200q4_set_exact / B200Q4_EXACT=1: the reference's own fp32 rounding sequence (bit-identical Y)
     uint8_t *d_exq = nullptr; size_t exq_cap = 0;       // exact mode: reference-format quantized activation rows
     float *d_exdeq = nullptr; size_t exdeq_cap = 0;     // exact mode: the floats the reference's dot product forms from them
+    int b8_min_stages = 3;           // B200Q4_B8_MIN_STAGES: the 256-byte-per-block code layout is used when this many stages still fit (0 = never)
     int slice_min_c = 0;             // B200Q4_SLICE_MIN_C: tiles longer than this many units (4 quant blocks each) are K-sliced; 0 = default rule
     int pipe_flags = 0;              // B200Q4_PIPE_FLAGS: development knobs of the decode kernel (PipeParams::flags)
     uint64_t launches = 0;
@@ -168,7 +169,7 @@ PipePlan pipe_plan(const b200q4_weight *w, int M, bool fuse)
     } else {
         pp.ncw = 16;
         const size_t stage = stage_of(pp.MP, 16);
-        pp.b8 = pp.MP == 2 && fixed(2, pp.m1, true) + 3 * stage <= optin;
+        pp.b8 = pp.MP == 2 && g.b8_min_stages > 0 && fixed(2, pp.m1, true) + g.b8_min_stages * stage <= optin;
         if (fixed(pp.MP, pp.m1, pp.b8) + 2 * stage > optin) { pp.MP = 0; return pp; }
         long st = (long)((optin - fixed(pp.MP, pp.m1, pp.b8)) / stage);
         pp.stages = (int)(st > PIPE_MAX_STAGES ? PIPE_MAX_STAGES : st);
@@ -629,6 +630,7 @@ int b200q4_init(int device)
     if (const char *e = getenv("B200Q4_PIPE_FLAGS")) g.pipe_flags = atoi(e);
     if (const char *e = getenv("B200Q4_SLICE_MIN_C")) g.slice_min_c = atoi(e) < 16 ? 16 : atoi(e);
     if (const char *e = getenv("B200Q4_ZERO_COPY")) g.zero_copy = atoi(e) != 0;
+    if (const char *e = getenv("B200Q4_B8_MIN_STAGES")) g.b8_min_stages = atoi(e);
     if (const char *e = getenv("B200Q4_EXACT")) g.exact = atoi(e) != 0;
     if (cudaHostAlloc(reinterpret_cast<void **>(&g.h_flag), 64, cudaHostAllocMapped) == cudaSuccess &&
         cudaHostGetDevicePointer(reinterpret_cast<void **>(&g.d_flag), g.h_flag, 0) == cudaSuccess) {
