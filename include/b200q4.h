@@ -155,6 +155,17 @@ int b200q4_mul_mat_dev_allgather(const b200q4_weight *w, const float *d_x, int M
 int b200q4_wait_flags(const uint32_t *local_flags, int world, const uint32_t *seq_counter, void *stream);
 int b200q4_sync(void *stream);
 
+/* ---- offline weight quantizers (row f-4) -----------------------------------------
+ * utils.cpp:424-481 ggml_quantize_q4_0 / utils.cpp:483-541 ggml_quantize_q4_1 -- what
+ * quantize_gptneox.cpp & co. run over every 2-D tensor of a model file -- on the device:
+ * n_rows rows of K floats at src (host, src_stride bytes apart, 0 = tight) -> the
+ * reference row image at dst (host, tight), BYTE FOR BYTE including q4_1's
+ * numeric_limits<float>::min() start value of the running maximum (utils.cpp:503);
+ * hist (may be NULL) is the reference's 16-bin code histogram and is ADDED to, as the
+ * reference does across the tensors of a file.  Streams the input in 256 MB slabs.  */
+int b200q4_quantize_weights(int type, const float *src, long long n_rows, int K, size_t src_stride,
+                            void *dst, long long *hist);
+
 /* ---- exact mode ----------------------------------------------------------------
  * on != 0: every mul_mat entry point computes ggml_vec_dot_q4_0/_q4_1's own rounding
  * sequence (ggml.c:484-510, 525-552 == imax.c:1210-1228: one strictly sequential

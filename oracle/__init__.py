@@ -128,6 +128,38 @@ class Oracle:
         return y
 
 
+def quantize_weights(qtype: int, w: np.ndarray):
+    """Oracle restatement of the reference's OFFLINE weight quantizers (utils.cpp:424-541): rows [n][k] fp32 ->
+    (reference-format rows uint8 [n][row_bytes], histogram int64[16])."""
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    n, k = w.shape
+    L = C.CDLL(str(HERE / "libq4oracle.so"))
+    L.q4o_quantize_weights.argtypes = [C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p]
+    L.q4o_quantize_weights.restype = C.c_size_t
+    out = np.zeros((n, row_bytes(qtype, k)), np.uint8)
+    hist = np.zeros(16, np.int64)
+    L.q4o_quantize_weights(qtype, w.ctypes.data, n, k, out.ctypes.data, hist.ctypes.data)
+    return out, hist
+
+
+def reference_quantize_weights(qtype: int, w: np.ndarray):
+    """The UNMODIFIED reference functions ggml_quantize_q4_0/_q4_1 of utils.cpp (oracle/_ref/libutils_ref.so)."""
+    so = REF_DIR / "libutils_ref.so"
+    if not so.exists():
+        raise FileNotFoundError(f"{so} missing: run `make -C oracle ref` where /root/reference is mounted")
+    L = C.CDLL(str(so))
+    C.c_int.in_dll(L, "do_print").value = 0                 # utils.cpp:423: silences the debug printf of the first block
+    fn = getattr(L, "_Z18ggml_quantize_q4_0PfPviiiPl" if qtype == Q4_0 else "_Z18ggml_quantize_q4_1PfPviiiPl")
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    fn.restype = C.c_size_t
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    n, k = w.shape
+    out = np.zeros((n, row_bytes(qtype, k)), np.uint8)
+    hist = np.zeros(16, np.int64)
+    fn(w.ctypes.data, out.ctypes.data, n * k, k, 32, hist.ctypes.data)
+    return out, hist
+
+
 def have_reference() -> bool:
     return (REF_DIR / "libggml_ref.so").exists()
 

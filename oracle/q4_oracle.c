@@ -351,3 +351,68 @@ int q4o_mul_mat_transposed(int type, const void *Wt, int N, int K,
     free(part);
     return 0;
 }
+
+/* ---- offline WEIGHT quantizers ------------------------------------------
+ * utils.cpp:424-481 ggml_quantize_q4_0 and utils.cpp:483-541 ggml_quantize_q4_1, the functions quantize_*.cpp
+ * run over every 2-D tensor of a model file.  Same block formats and rounding as the activation quantizers
+ * above, with two differences: (1) a 16-bin histogram of the emitted codes, (2) q4_1 starts its running
+ * maximum at std::numeric_limits<float>::min() -- the smallest POSITIVE normal float, not the most negative
+ * one (utils.cpp:503) -- so a block whose values are all <= 1.17549435e-38 gets max = 1.17549435e-38.
+ * n_rows rows of k floats, tightly packed; returns the bytes written. */
+size_t q4o_quantize_weights(int type, const float *src, long n_rows, int k, void *dst, int64_t *hist)
+{
+    const int nblk = k / Q4O_QK;
+    const size_t row_size = (size_t)nblk * (type == 0 ? Q4O_BS0 : 24);
+    for (long row = 0; row < n_rows; row++) {
+        const float *x = src + (size_t)row * k;
+        uint8_t *out = (uint8_t *)dst + (size_t)row * row_size;
+        if (type == 0) {
+            for (int i = 0; i < nblk; i++) {
+                const float *xb = x + (size_t)i * Q4O_QK;
+                float amax = 0.0f;
+                for (int l = 0; l < Q4O_QK; l++) {
+                    const float a = fabsf(xb[l]);
+                    amax = (amax < a) ? a : amax;        /* std::max(amax, fabsf(v)), utils.cpp:447 */
+                }
+                const float d  = amax / 7.0f;
+                const float id = (d != 0.0f) ? 1.0f / d : 0.0f;
+                uint8_t *blk = out + (size_t)i * Q4O_BS0;
+                memcpy(blk, &d, sizeof(float));
+                for (int l = 0; l < Q4O_QK; l += 2) {
+                    const float v0 = xb[l] * id, v1 = xb[l + 1] * id;
+                    const uint8_t c0 = (uint8_t)((int8_t)q4o_round_to_int(v0) + 8);
+                    const uint8_t c1 = (uint8_t)((int8_t)q4o_round_to_int(v1) + 8);
+                    hist[c0 & 15]++;
+                    hist[c1 & 15]++;
+                    blk[4 + l / 2] = (uint8_t)(c0 | (c1 << 4));
+                }
+            }
+        } else {
+            float   *pm = (float *)out;
+            float   *pd = pm + nblk;
+            uint8_t *pb = (uint8_t *)(pd + nblk);
+            for (int i = 0; i < nblk; i++) {
+                const float *xb = x + (size_t)i * Q4O_QK;
+                float mn = FLT_MAX, mx = FLT_MIN;        /* utils.cpp:502-503: numeric_limits<float>::max() / ::min() */
+                for (int l = 0; l < Q4O_QK; l++) {
+                    const float v = xb[l];
+                    if (v < mn) mn = v;
+                    if (v > mx) mx = v;
+                }
+                const float d  = (mx - mn) / 15.0f;
+                const float id = (d != 0.0f) ? 1.0f / d : 0.0f;
+                pm[i] = mn;
+                pd[i] = d;
+                for (int l = 0; l < Q4O_QK; l += 2) {
+                    const float v0 = (xb[l] - mn) * id, v1 = (xb[l + 1] - mn) * id;
+                    const uint8_t c0 = (uint8_t)q4o_round_to_int(v0);
+                    const uint8_t c1 = (uint8_t)q4o_round_to_int(v1);
+                    hist[c0 & 15]++;
+                    hist[c1 & 15]++;
+                    pb[i * 16 + l / 2] = (uint8_t)(c0 | (c1 << 4));
+                }
+            }
+        }
+    }
+    return (size_t)n_rows * row_size;
+}

@@ -7,9 +7,9 @@ Run in the build container (where /root/reference is mounted):
 
 The reference has no golden vectors of its own; these
 files pin the hot path's behaviour to the outputs of the reference's own
-code: quantize_row_q4_0/_q4_1 (ggml.c:209-298), and ggml_mul_mat +
-ggml_graph_compute on Q4_0/Q4_1 weights (ggml.c:4891-5453, imax.c:1133-1230),
-both called through ctypes.  Inputs are stored next to the outputs, so the
+code: quantize_row_q4_0/_q4_1 (ggml.c:209-298), ggml_mul_mat +
+ggml_graph_compute on Q4_0/Q4_1 weights (ggml.c:4891-5453, imax.c:1133-1230), and the
+offline weight quantizers ggml_quantize_q4_0/_q4_1 (utils.cpp:424-541), all called through ctypes.  Inputs are stored next to the outputs, so the
 fixtures do not depend on numpy's RNG staying stable.
 """
 from __future__ import annotations
@@ -21,7 +21,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
-from oracle import Q4_0, Q4_1, Reference  # noqa: E402
+from oracle import Q4_0, Q4_1, Reference, reference_quantize_weights  # noqa: E402
 
 OUT = Path(__file__).resolve().parent
 
@@ -117,6 +117,17 @@ def main() -> None:
             for nth in (1, 3):
                 tt[f"{tag}_y_m{m}_t{nth}"] = ref.mul_mat_transposed(qt, wq, n, k, x, nth=nth)
     np.savez_compressed(OUT / "mul_mat_transposed_kat.npz", **tt)
+
+    # ---- offline weight quantizers (utils.cpp ggml_quantize_q4_0/_q4_1; row f-4) -----------------
+    wk = {}
+    for k in (64, 256):
+        x = np.concatenate([edge_rows(k), rng.uniform(-0.05, 0.05, (8, k)).astype(np.float32)])
+        wk[f"x_k{k}"] = x
+        for qt, tag in ((Q4_0, "q4_0"), (Q4_1, "q4_1")):
+            rows, hist = reference_quantize_weights(qt, x)
+            wk[f"{tag}_k{k}"] = rows
+            wk[f"{tag}_hist_k{k}"] = hist
+    np.savez_compressed(OUT / "quantize_weights_kat.npz", **wk)
 
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size, "bytes")

@@ -343,6 +343,30 @@ def test_k_slicing_forced_on_short_rows(gpu, oracle, qt, tag, n, k, m):
     w.free()
 
 
+# ---- offline weight quantizers on the device (row f-4) ---------------------------------------------
+@pytest.mark.parametrize("k", [64, 256])
+@pytest.mark.parametrize("qt,tag", TYPES)
+def test_weight_quantizer_golden_bit_exact(gpu, golden, qt, tag, k):
+    g = golden["quantize_weights_kat"]
+    rows, hist = gpu.quantize_weights(qt, g[f"x_k{k}"])
+    assert np.array_equal(rows, g[f"{tag}_k{k}"])
+    assert np.array_equal(hist, g[f"{tag}_hist_k{k}"])
+
+
+@pytest.mark.parametrize("qt,tag", TYPES)
+def test_weight_quantizer_random_vs_oracle_incl_strided_input(gpu, qt, tag):
+    from oracle import quantize_weights
+    rng = np.random.default_rng(8)
+    big = (rng.standard_normal((3000, 4096 + 64)) * 0.05).astype(np.float32)
+    big[7] = 0.0
+    big[8] = -np.abs(big[8]) - 1.0
+    x = big[:, :4096]                                      # rows 4160 floats apart
+    rows, hist = gpu.quantize_weights(qt, x)
+    want, whist = quantize_weights(qt, np.ascontiguousarray(x))
+    assert np.array_equal(rows, want)
+    assert np.array_equal(hist, whist) and hist.sum() == x.size
+
+
 # ---- BASELINE.json microbench shape, full size -----------------------------------
 @pytest.mark.parametrize("qt,tag", TYPES)
 @pytest.mark.parametrize("m", [1, 8])

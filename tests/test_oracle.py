@@ -133,3 +133,43 @@ def test_mul_mat_live_vs_reference(oracle, reference, qt, m, nth):
     want = reference.mul_mat(qt, wq, n, k, x, nth=nth)      # ggml_graph_compute, IMAX hook for Q4_0
     got = oracle.mul_mat(qt, wq, n, k, x, nth=nth)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+# ---- offline weight quantizers (utils.cpp:424-541) -------------------------
+@pytest.mark.parametrize("k", [64, 256])
+@pytest.mark.parametrize("qt,tag", TYPES)
+def test_weight_quantizer_matches_golden(golden, qt, tag, k):
+    from oracle import quantize_weights
+    g = golden["quantize_weights_kat"]
+    rows, hist = quantize_weights(qt, g[f"x_k{k}"])
+    assert np.array_equal(rows, g[f"{tag}_k{k}"])
+    assert np.array_equal(hist, g[f"{tag}_hist_k{k}"])
+    assert hist.sum() == g[f"x_k{k}"].size
+
+
+def test_weight_quantizer_q4_1_keeps_the_numeric_limits_min_quirk(oracle):
+    """utils.cpp:503 starts the running max at numeric_limits<float>::min() (smallest POSITIVE float): an all-negative
+    block gets max = 1.17549435e-38, unlike quantize_row_q4_1 (ggml.c:269, -FLT_MAX)."""
+    from oracle import quantize_weights
+    x = -np.abs(np.random.default_rng(0).standard_normal((1, 32))).astype(np.float32) - 0.5
+    w, _ = quantize_weights(Q4_1, x)
+    a = oracle.quantize_rows(Q4_1, x)
+    mn, d = w.view(np.float32)[0, 0], w.view(np.float32)[0, 1]
+    assert mn == x.min() and d == np.float32((np.float32(1.17549435e-38) - x.min()) / np.float32(15.0))
+    assert not np.array_equal(w, a)
+    # Q4_0: the two quantizers are the same function
+    assert np.array_equal(quantize_weights(Q4_0, x)[0], oracle.quantize_rows(Q4_0, x))
+
+
+@pytest.mark.parametrize("qt,tag", TYPES)
+def test_weight_quantizer_live_vs_reference(qt, tag):
+    from oracle import REF_DIR, quantize_weights, reference_quantize_weights
+    if not (REF_DIR / "libutils_ref.so").exists():
+        pytest.skip("oracle/_ref/libutils_ref.so not built (needs /root/reference at build time)")
+    rng = np.random.default_rng(77)
+    x = (rng.standard_normal((64, 1024)) * np.exp(rng.uniform(-3, 3, (64, 1)))).astype(np.float32)
+    x[5] = 0.0
+    x[6] = -np.abs(x[6])
+    a, ha = quantize_weights(qt, x)
+    b, hb = reference_quantize_weights(qt, x)
+    assert np.array_equal(a, b) and np.array_equal(ha, hb)

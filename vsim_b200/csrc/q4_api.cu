@@ -899,6 +899,51 @@ int b200q4_quantize_rows(int type, const float *x, int M, int K, size_t x_stride
     return B200Q4_OK;
 }
 
+int b200q4_quantize_weights(int type, const float *src, long long n_rows, int K, size_t src_stride, void *dst, long long *hist)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    if ((type != 0 && type != 1) || n_rows < 0 || K < 0 || K % QK != 0 || (n_rows > 0 && K > 0 && (!src || !dst)))
+        return fail(B200Q4_EINVAL, "quantize_weights: bad argument");
+    if (src_stride == 0) src_stride = (size_t)K * 4;
+    if (src_stride % 4 || src_stride < (size_t)K * 4) return fail(B200Q4_EINVAL, "quantize_weights: bad stride");
+    unsigned long long *d_hist = nullptr;
+    CK(cudaMalloc(&d_hist, 16 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, 16 * sizeof(unsigned long long), g.stream);
+    const int nb = K / QK;
+    const size_t rb = (size_t)nb * (type == 0 ? 20 : 24);
+    int rc = B200Q4_OK;
+    if (e == cudaSuccess && n_rows > 0 && K > 0) {
+        long long slab = (64ll << 20) / K;               // rows per slab: <= 256 MB of fp32 in flight
+        if (slab < 1) slab = 1;
+        if (slab > n_rows) slab = n_rows;
+        if (!(rc = ensure(g.d_x, g.x_cap, (size_t)slab * K * 4)) && !(rc = ensure(g.d_tmp, g.tmp_cap, rb * (size_t)slab))) {
+            for (long long r0 = 0; r0 < n_rows && e == cudaSuccess; r0 += slab) {
+                const long long nr = n_rows - r0 < slab ? n_rows - r0 : slab;
+                e = cudaMemcpy2DAsync(g.d_x, (size_t)K * 4, (const char *)src + (size_t)r0 * src_stride, src_stride, (size_t)K * 4, (size_t)nr,
+                                      cudaMemcpyHostToDevice, g.stream);
+                if (e != cudaSuccess) break;
+                const long long warps = nr * nb;
+                const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+                if (type == 0) quantize_weights_kernel<0><<<blocks, 256, 0, g.stream>>>(g.d_x, (size_t)K, (long)nr, nb, g.d_tmp, d_hist);
+                else           quantize_weights_kernel<1><<<blocks, 256, 0, g.stream>>>(g.d_x, (size_t)K, (long)nr, nb, g.d_tmp, d_hist);
+                g.launches++;
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaMemcpyAsync((char *)dst + (size_t)r0 * rb, g.d_tmp, rb * (size_t)nr, cudaMemcpyDeviceToHost, g.stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);       // the staging buffers are reused by the next slab
+            }
+        }
+    }
+    unsigned long long h[16] = {0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_hist, sizeof h, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    cudaFree(d_hist);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(B200Q4_ECUDA, "quantize_weights: %s", cudaGetErrorString(e));
+    if (hist) for (int i = 0; i < 16; i++) hist[i] += (long long)h[i];
+    return B200Q4_OK;
+}
+
 int b200q4_mul_mat_transposed(const b200q4_weight *wt, const float *x, int M, size_t x_stride, float *y, size_t y_stride)
 {
     std::lock_guard<std::recursive_mutex> lk(g.mu);

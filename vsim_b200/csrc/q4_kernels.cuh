@@ -320,6 +320,70 @@ __global__ void quantize_rows_ref_kernel(const float *__restrict__ x, size_t x_s
 }
 
 // ---------------------------------------------------------------------------
+// Offline WEIGHT quantizers: utils.cpp:424-481 ggml_quantize_q4_0 and
+// utils.cpp:483-541 ggml_quantize_q4_1, what quantize_*.cpp runs over every 2-D tensor of a model.  Same row
+// formats and rounding as the activation quantizers; q4_1 differs in ONE place that has to be kept to stay
+// byte-identical: the running maximum starts at std::numeric_limits<float>::min() (the smallest positive
+// normal float, utils.cpp:503), so a block with nothing above 1.17549435e-38 gets that as its max.
+// Also fills the 16-bin histogram of emitted codes (hist, 64-bit counters).  One warp per (row, block).
+// ---------------------------------------------------------------------------
+template <int QT>
+__global__ void quantize_weights_kernel(const float *__restrict__ x, size_t x_stride, long n_rows, int nb,
+                                        uint8_t *__restrict__ out, unsigned long long *__restrict__ hist)
+{
+    __shared__ unsigned int s_hist[16];
+    if (threadIdx.x < 16) s_hist[threadIdx.x] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w < n_rows * nb) {                               // (whole warps: w is warp-uniform)
+        const long m = w / nb;
+        const int blk = (int)(w - m * nb);
+        const float xv = x[(size_t)m * x_stride + (size_t)blk * QK + lane];
+        BlockQ q;
+        if (QT == 0) {
+            q = quantize_block<0>(xv);
+        } else {
+            float mn = xv, mx = xv;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            // strict left-to-right compares: of equal minima (+0.0 / -0.0) the FIRST one's bits are kept
+            const unsigned first_mn = __ffs(__ballot_sync(0xffffffffu, xv == mn)) - 1;
+            mn = __shfl_sync(0xffffffffu, xv, first_mn);
+            mx = (mx > 1.17549435e-38f) ? mx : 1.17549435e-38f;      // numeric_limits<float>::min() start value
+            const float d  = __fdiv_rn(__fsub_rn(mx, mn), 15.0f);
+            const float id = (d != 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+            q.code = (int)(uint8_t)round_to_int_ref(__fmul_rn(__fsub_rn(xv, mn), id));
+            q.d = d;
+            q.mn = mn;
+        }
+        atomicAdd(&s_hist[q.code & 15], 1u);
+        uint32_t word = (uint32_t)(q.code & 15) << (4 * (lane & 7));
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        word |= __shfl_xor_sync(0xffffffffu, word, 4);
+        if (QT == 0) {
+            uint8_t *b = out + ((size_t)m * nb + blk) * 20;
+            if (lane == 0) *reinterpret_cast<float *>(b) = q.d;
+            if ((lane & 7) == 0) *reinterpret_cast<uint32_t *>(b + 4 + (lane >> 3) * 4) = word;
+        } else {
+            uint8_t *row = out + (size_t)m * nb * 24;
+            if (lane == 0) {
+                reinterpret_cast<float *>(row)[blk] = q.mn;
+                reinterpret_cast<float *>(row)[nb + blk] = q.d;
+            }
+            if ((lane & 7) == 0)
+                *reinterpret_cast<uint32_t *>(row + (size_t)nb * 8 + (size_t)blk * 16 + (lane >> 3) * 4) = word;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)s_hist[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------
 // Weight re-tiling: reference row format (tightly packed rows on the device) -> wtile.
 // One thread per 16-byte output slot.  Rows >= N and blocks >= nb are padding
 // (scale 0, nibbles 8 / 0) so they contribute exactly 0.

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "b200q4_weight_cols", "b200q4_weight_type", "b200q4_weight_device_bytes", "b200q4_weight_download",
     "b200q4_mul_mat", "b200q4_mul_mat_wdata", "b200q4_quantize_rows", "b200q4_weight_upload_transposed",
     "b200q4_mul_mat_transposed", "b200q4_mul_mat_dev", "b200q4_quantize_rows_dev", "b200q4_sync",
-    "b200q4_mul_mat_dev_allgather", "b200q4_wait_flags", "b200q4_set_exact",
+    "b200q4_mul_mat_dev_allgather", "b200q4_wait_flags", "b200q4_set_exact", "b200q4_quantize_weights",
     "b200q4_host_alloc", "b200q4_host_free", "b200q4_launch_count", "b200q4_launch_count_reset",
     "b200q4_kernel_for", "b200q4_time_mul_mat_dev",
 ]
@@ -79,6 +79,7 @@ def load_library(build: bool = True) -> C.CDLL:
         "b200q4_quantize_rows_dev": (i, [i, vp, i, i, sz, vp, vp]),
         "b200q4_sync": (i, [vp]),
         "b200q4_set_exact": (i, [i]),
+        "b200q4_quantize_weights": (i, [i, f32p, C.c_longlong, i, sz, vp, vp]),
         "b200q4_mul_mat_dev_allgather": (i, [vp, vp, i, sz, C.POINTER(vp), i, i, i, sz, C.POINTER(vp), vp, vp]),
         "b200q4_wait_flags": (i, [vp, i, vp, vp]),
         "b200q4_host_alloc": (vp, [sz]),
@@ -215,6 +216,22 @@ def mul_mat_wdata(w: Q4Weight, wdata: np.ndarray, m: int) -> np.ndarray:
     y = np.empty((m, w.n), dtype=np.float32)
     _check(L, L.b200q4_mul_mat_wdata(w.handle, wdata.ctypes.data, m, y.ctypes.data, max(w.n, 1) * 4), "b200q4_mul_mat_wdata")
     return y
+
+
+def quantize_weights(qtype: int, w: np.ndarray):
+    """ggml_quantize_q4_0/_q4_1 (utils.cpp:424-541) on the device: fp32 rows [n][k] -> (reference-format rows, histogram int64[16])."""
+    L = load_library()
+    w = np.asarray(w, dtype=np.float32)
+    if w.ndim != 2 or w.strides[1] != 4:
+        w = np.ascontiguousarray(w)
+    n, k = w.shape
+    out = np.zeros((n, row_bytes(qtype, k)), np.uint8)
+    hist = np.zeros(16, np.int64)
+    rc = L.b200q4_quantize_weights(qtype, w.ctypes.data, n, k, w.strides[0] if n > 1 else 0,
+                                   out.ctypes.data, hist.ctypes.data)
+    if rc:
+        raise B200Q4Error(f"b200q4_quantize_weights failed (rc={rc}): {_err(L)}")
+    return out, hist
 
 
 def mul_mat_transposed(wt: Q4Weight, x: np.ndarray) -> np.ndarray:
