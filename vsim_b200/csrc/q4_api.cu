@@ -15,6 +15,7 @@ using b200q4::PIPE_TILE_SPLIT;
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 using namespace b200q4;
 
@@ -56,6 +57,11 @@ struct Ctx {
     bool zero_copy = true;           // B200Q4_ZERO_COPY=0: always stage host buffers through cudaMemcpy
     uint32_t *h_flag = nullptr, *d_flag = nullptr;   // mapped host word the stream writes when a zero-copy call is complete
     uint32_t hseq = 0;
+    struct HostBlock { const char *base; size_t size; char *dev; };
+    std::vector<HostBlock> host_blocks;              // b200q4_host_alloc'ed ranges: their device aliases are known without a driver query
+    // cuStreamWriteValue32 (driver API, fetched through the runtime: no link-time dependency on libcuda): the
+    // completion word is written by the stream's front end instead of a one-thread kernel
+    int (*stream_write32)(cudaStream_t, unsigned long long, uint32_t, unsigned int) = nullptr;
     bool exact = false;              // b200q4_set_exact / B200Q4_EXACT=1: the reference's own fp32 rounding sequence (bit-identical Y)
     uint8_t *d_exq = nullptr; size_t exq_cap = 0;       // exact mode: reference-format quantized activation rows
     float *d_exdeq = nullptr; size_t exdeq_cap = 0;     // exact mode: the floats the reference's dot product forms from them
@@ -522,6 +528,8 @@ __global__ void signal_host_kernel(uint32_t *flag, uint32_t v)
 // device alias of a pinned (cudaHostAlloc / cudaHostRegister) host pointer, or NULL for pageable memory
 void *pinned_alias(const void *p)
 {
+    for (const auto &hb : g.host_blocks)
+        if ((const char *)p >= hb.base && (const char *)p < hb.base + hb.size) return hb.dev + ((const char *)p - hb.base);
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
@@ -638,6 +646,14 @@ int b200q4_init(int device)
     if (cudaHostAlloc(reinterpret_cast<void **>(&g.h_flag), 64, cudaHostAllocMapped) == cudaSuccess &&
         cudaHostGetDevicePointer(reinterpret_cast<void **>(&g.d_flag), g.h_flag, 0) == cudaSuccess) {
         *g.h_flag = 0; g.hseq = 0;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        const char *sw = getenv("B200Q4_STREAM_WRITE");
+        if ((!sw || atoi(sw) != 0) && cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess && fn)
+            g.stream_write32 = reinterpret_cast<int (*)(cudaStream_t, unsigned long long, uint32_t, unsigned int)>(fn);
+        else
+            cudaGetLastError();
     } else {
         cudaGetLastError();
         g.h_flag = nullptr; g.d_flag = nullptr;          // no mapped memory: the copy path serves every call
@@ -829,9 +845,12 @@ int b200q4_mul_mat(const b200q4_weight *w, const float *x, int M, size_t x_strid
             g.launches++;
             if (int rc = mul_mat_dev_locked(w, g.d_x, M, (size_t)w->K * 4, ya, y_stride, g.stream, nullptr)) return rc;
             const uint32_t seq = ++g.hseq;
-            signal_host_kernel<<<1, 1, 0, g.stream>>>(g.d_flag, seq);
-            g.launches++;
-            CK(cudaGetLastError());
+            if (!g.stream_write32 || g.stream_write32(g.stream, (unsigned long long)(uintptr_t)g.d_flag, seq, 0) != 0) {
+                g.stream_write32 = nullptr;              // not supported here: a one-thread kernel writes the word
+                signal_host_kernel<<<1, 1, 0, g.stream>>>(g.d_flag, seq);
+                g.launches++;
+                CK(cudaGetLastError());
+            }
             return wait_host_flag(seq);
         }
     }
@@ -992,12 +1011,23 @@ void *b200q4_host_alloc(size_t bytes)
         fail(B200Q4_ENOMEM, "cudaMallocHost(%zu) failed", bytes);
         return nullptr;
     }
+    void *dev = nullptr;
+    if (cudaHostGetDevicePointer(&dev, p, 0) == cudaSuccess && dev)
+        g.host_blocks.push_back({(const char *)p, bytes ? bytes : 1, (char *)dev});
+    else
+        cudaGetLastError();
     return p;
 }
 
 void b200q4_host_free(void *p)
 {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    {
+        std::lock_guard<std::recursive_mutex> lk(g.mu);
+        for (size_t i = 0; i < g.host_blocks.size(); i++)
+            if (g.host_blocks[i].base == (const char *)p) { g.host_blocks.erase(g.host_blocks.begin() + (long)i); break; }
+    }
+    cudaFreeHost(p);
 }
 
 // development aid (not part of b200q4.h): copies the [256][16] timeline of the last decode launch
