@@ -155,6 +155,16 @@ int b200q4_mul_mat_dev_allgather(const b200q4_weight *w, const float *d_x, int M
 int b200q4_wait_flags(const uint32_t *local_flags, int world, const uint32_t *seq_counter, void *stream);
 int b200q4_sync(void *stream);
 
+/* ---- next-weight hint ------------------------------------------------------------
+ * A decode graph visits its weight tensors in a fixed order.  Telling the library which
+ * tensor the NEXT decode call (M_next rows) will use lets the current launch, once it has
+ * requested its own last bytes, ask L2 to prefetch the chunks the next launch will read
+ * first: HBM keeps streaming through the tail of one launch and the head of the next.
+ * One-shot (consumed by the next device-side decode launch); purely a performance hint --
+ * a wrong or missing hint changes nothing but timing.  The ggml hook learns the order by
+ * itself (the tensor that followed this one last time).                              */
+int b200q4_hint_next_weight(const b200q4_weight *next, int M_next);
+
 /* ---- offline weight quantizers (row f-4) -----------------------------------------
  * utils.cpp:424-481 ggml_quantize_q4_0 / utils.cpp:483-541 ggml_quantize_q4_1 -- what
  * quantize_gptneox.cpp & co. run over every 2-D tensor of a model file -- on the device:

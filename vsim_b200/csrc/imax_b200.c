@@ -63,9 +63,10 @@ typedef struct b200q4_ggml_compute_params hook_params;
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static int g_ready = 0, g_use_wdata = 0, g_verbose = 0;
 
-struct reg_entry { const void *key; int type, N, K; b200q4_weight *w; };
+struct reg_entry { const void *key; int type, N, K; b200q4_weight *w; b200q4_weight *next_w; };
 static struct reg_entry *g_reg = NULL;
 static size_t g_reg_cap = 0, g_reg_n = 0;
+static size_t g_prev = (size_t)-1;      /* registry slot of the previous call: a graph visits its tensors in a fixed order */
 
 static void die(const char *what)
 {
@@ -95,7 +96,7 @@ void init_xmax(void)
     pthread_mutex_unlock(&g_mu);
 }
 
-static b200q4_weight *resident_weight(const hook_tensor *src0)
+static b200q4_weight *resident_weight(const hook_tensor *src0, size_t *slot)
 {
     const void *key = src0->data;
     const int type = (int)src0->type, K = src0->ne[0], N = src0->ne[1];
@@ -112,19 +113,23 @@ static b200q4_weight *resident_weight(const hook_tensor *src0)
             }
         free(g_reg);
         g_reg = nr; g_reg_cap = ncap;
+        g_prev = (size_t)-1;
     }
     mask = g_reg_cap - 1;
     h = ((size_t)key >> 4) * 0x9E3779B97F4A7C15ull & mask;
     while (g_reg[h].key) {
-        if (g_reg[h].key == key && g_reg[h].type == type && g_reg[h].N == N && g_reg[h].K == K)
+        if (g_reg[h].key == key && g_reg[h].type == type && g_reg[h].N == N && g_reg[h].K == K) {
+            *slot = h;
             return g_reg[h].w;
+        }
         h = (h + 1) & mask;
     }
     b200q4_weight *w = b200q4_weight_upload(type, src0->data, N, K, src0->nb[1]);
     if (!w) die("weight upload");
     if (g_verbose) printf("imax_b200: resident weight %p type=%d N=%d K=%d (%zu B)\n", key, type, N, K, b200q4_weight_device_bytes(w));
-    g_reg[h].key = key; g_reg[h].type = type; g_reg[h].N = N; g_reg[h].K = K; g_reg[h].w = w;
+    g_reg[h].key = key; g_reg[h].type = type; g_reg[h].N = N; g_reg[h].K = K; g_reg[h].w = w; g_reg[h].next_w = NULL;
     g_reg_n++;
+    *slot = h;
     return w;
 }
 
@@ -143,10 +148,16 @@ static void hook_mul_mat(int want_type, const char *who, const hook_params *para
                 src1->ne[0], src1->ne[1], src1->ne[2], src1->ne[3]);
         exit(1);
     }
-    pthread_mutex_lock(&g_mu);
-    b200q4_weight *w = resident_weight(src0);
-    pthread_mutex_unlock(&g_mu);
     const int M = src1->ne[1];
+    pthread_mutex_lock(&g_mu);
+    size_t slot = 0;
+    b200q4_weight *w = resident_weight(src0, &slot);
+    /* learned order: remember that this tensor followed the previous one, and tell the library which tensor
+     * followed THIS one last time -- it prefetches that tensor's first chunks into L2 while this call drains */
+    if (g_prev != (size_t)-1 && g_prev != slot) g_reg[g_prev].next_w = w;
+    if (g_reg[slot].next_w) b200q4_hint_next_weight(g_reg[slot].next_w, M);
+    g_prev = slot;
+    pthread_mutex_unlock(&g_mu);
     int rc;
     if (g_use_wdata)
         rc = b200q4_mul_mat_wdata(w, params->wdata, M, (float *)dst->data, dst->nb[1]);

@@ -65,6 +65,9 @@ struct Ctx {
     bool exact = false;              // b200q4_set_exact / B200Q4_EXACT=1: the reference's own fp32 rounding sequence (bit-identical Y)
     uint8_t *d_exq = nullptr; size_t exq_cap = 0;       // exact mode: reference-format quantized activation rows
     float *d_exdeq = nullptr; size_t exdeq_cap = 0;     // exact mode: the floats the reference's dot product forms from them
+    const b200q4_weight *hint_w = nullptr; int hint_m = 1;   // b200q4_hint_next_weight: consumed by the next decode launch
+    int prefetch_stages = 2;         // B200Q4_PREFETCH_STAGES: tasks per CTA of the hinted next launch to pull into L2 (0 = off); measured: 2 fills
+                                     // the ~2 us gap between two launches (12 MB), more only competes with the launch's own last stages
     int b8_min_stages = 3;           // B200Q4_B8_MIN_STAGES: the 256-byte-per-block code layout is used when this many stages still fit (0 = never)
     int slice_min_c = 0;             // B200Q4_SLICE_MIN_C: tiles longer than this many units (4 quant blocks each) are K-sliced; 0 = default rule
     int pipe_flags = 0;              // B200Q4_PIPE_FLAGS: development knobs of the decode kernel (PipeParams::flags)
@@ -235,6 +238,19 @@ int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, con
     p.U = w->n_tiles * w->C; p.N = w->N; p.M = mc; p.C = w->C; p.n_tiles = w->n_tiles; p.nb = w->nb;
     p.ntasks = pl.ntasks; p.PP = pl.PP; p.TS = pl.TS; p.stages = pl.stages; p.gnbp = pl.gnbp; p.flags = g.pipe_flags;
     p.dbg = g.d_dbg;
+    p.next = NextHint{};
+    if (g.hint_w && g.prefetch_stages > 0 && !g.hint_w->transposed && g.hint_w->wt_bytes &&
+        !(g.tile_min_m > 0 && g.hint_m >= g.tile_min_m) && !g.exact) {
+        const b200q4_weight *h = g.hint_w;
+        const PipePlan hp = pipe_plan(h, g.hint_m, true);
+        if (hp.MP > 0) {
+            const int hslots = g.sms * (hp.ncw == 8 ? 2 : 1);
+            p.next.wt = h->d_wt; p.next.C = h->C; p.next.TS = hp.TS; p.next.PP = hp.PP; p.next.U = h->n_tiles * h->C;
+            p.next.n_tiles = h->n_tiles; p.next.ntasks = hp.ntasks; p.next.grid = hp.ntasks < hslots ? hp.ntasks : hslots;
+            p.next.chunk = chunk_bytes(h->type); p.next.stages = g.prefetch_stages;
+        }
+    }
+    g.hint_w = nullptr;                                  // one-shot
     const int slots = g.sms * (pl.ncw == 8 ? 2 : 1);
     const int grid = pl.ntasks < slots ? pl.ntasks : slots;
     const bool m1 = pl.m1 && mc == 1;
@@ -642,6 +658,7 @@ int b200q4_init(int device)
     if (const char *e = getenv("B200Q4_SLICE_MIN_C")) g.slice_min_c = atoi(e) < 16 ? 16 : atoi(e);
     if (const char *e = getenv("B200Q4_ZERO_COPY")) g.zero_copy = atoi(e) != 0;
     if (const char *e = getenv("B200Q4_B8_MIN_STAGES")) g.b8_min_stages = atoi(e);
+    if (const char *e = getenv("B200Q4_PREFETCH_STAGES")) g.prefetch_stages = atoi(e);
     if (const char *e = getenv("B200Q4_EXACT")) g.exact = atoi(e) != 0;
     if (cudaHostAlloc(reinterpret_cast<void **>(&g.h_flag), 64, cudaHostAllocMapped) == cudaSuccess &&
         cudaHostGetDevicePointer(reinterpret_cast<void **>(&g.d_flag), g.h_flag, 0) == cudaSuccess) {
@@ -729,6 +746,7 @@ void b200q4_weight_free(b200q4_weight *w)
 {
     if (!w) return;
     std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (g.hint_w == w) g.hint_w = nullptr;
     if (g.device >= 0) {
         cudaStreamSynchronize(g.stream);
         cudaFree(w->d_wt);
@@ -985,6 +1003,15 @@ int b200q4_mul_mat_transposed(const b200q4_weight *wt, const float *x, int M, si
     return B200Q4_OK;
 }
 
+int b200q4_hint_next_weight(const b200q4_weight *next, int M_next)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (int rc = need_init()) return rc;
+    g.hint_w = next;
+    g.hint_m = M_next > 0 ? M_next : 1;
+    return B200Q4_OK;
+}
+
 int b200q4_set_exact(int on)
 {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
@@ -1089,6 +1116,7 @@ double b200q4_time_mul_mat_dev(b200q4_weight *const *ws, int nw, const float *d_
     if (cudaEventRecord(g.ev0, g.stream) != cudaSuccess) return fail(B200Q4_ECUDA, "event record failed");
     for (int i = 0; i < iters; i++) {
         const b200q4_weight *w = ws[i % nw];
+        g.hint_w = ws[(i + 1) % nw]; g.hint_m = M;      // the caller's rotation is known: hint the next tensor
         if (int rc = mul_mat_dev_locked(w, d_x, M, (size_t)w->K * 4, d_y, (size_t)w->N * 4, g.stream, nullptr)) return rc;
     }
     if (cudaEventRecord(g.ev1, g.stream) != cudaSuccess) return fail(B200Q4_ECUDA, "event record failed");

@@ -716,6 +716,15 @@ __global__ void scatter_slice_kernel(const float *__restrict__ src, size_t src_s
     if (threadIdx.x == 0) peer_count_done(po);
 }
 
+// Geometry of the NEXT decode launch in the stream, when the caller knows it (b200q4_hint_next_weight; the ggml hook
+// learns the order of a model's tensors): once a CTA has issued its last copy it asks L2 to prefetch the chunks the
+// next launch's CTAs will request first, so the HBM channels keep working through this launch's tail and the next
+// launch's first stages are L2 hits.  wt == NULL: no hint.
+struct NextHint {
+    const uint8_t *wt;
+    int C, TS, PP, U, n_tiles, ntasks, grid, chunk, stages;   // stages: tasks per CTA to prefetch
+};
+
 struct PipeParams {
     const uint8_t *wt;
     const float   *x;        // fused quantization (M <= 2)
@@ -737,7 +746,32 @@ struct PipeParams {
     // columns are stored straight into every rank's Y over NVLink (peer-mapped pointers), then the last
     // CTA signals `seq` into slot `rank` of every rank's flag array.
     PeerOut        peer;
+    NextHint       next;
 };
+
+__device__ __forceinline__ void l2_prefetch_bulk(const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
+}
+// the chunks CTA b of the hinted launch will ask for first (its static tasks, same formulas as the producer below)
+__device__ __forceinline__ void prefetch_next_launch(const NextHint &h, int b)
+{
+    if (!h.wt || b >= h.grid) return;
+    const bool sliced = h.PP > 1;
+    const int cls = sliced ? b % h.PP : 0;
+    const int idx = sliced ? b / h.PP : b;
+    const int ncls = sliced ? (h.grid - cls + h.PP - 1) / h.PP : h.grid;
+    const int limit = sliced ? h.n_tiles : h.ntasks;
+    for (int k = 0; k < h.stages; k++) {
+        const int t = idx + k * ncls;
+        if (t >= limit) break;
+        long u0; int n;
+        if (sliced) { u0 = (long)t * h.C + cls * h.TS; n = min(h.TS, h.C - cls * h.TS); }
+        else if (h.C >= PIPE_TILE_SPLIT) { u0 = (long)t * h.C; n = h.C; }
+        else { u0 = (long)t * h.TS; n = (int)min((long)h.TS, (long)h.U - u0); }
+        l2_prefetch_bulk(h.wt + (size_t)u0 * h.chunk, (uint32_t)n * (uint32_t)h.chunk);
+    }
+}
 
 __device__ __forceinline__ unsigned long long gtimer()
 {
@@ -1132,6 +1166,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
                 cur = nxt;
             }
             PIPE_STAMP(10);                              // last copy issued
+            prefetch_next_launch(p.next, (int)blockIdx.x);
             mbar_wait(&bar_empty[s], ph);                // stop marker
             s_desc[s] = make_int4(-1, 0, 0, 0);
             mbar_arrive(&bar_full[s]);

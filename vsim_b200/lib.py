@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "b200q4_weight_cols", "b200q4_weight_type", "b200q4_weight_device_bytes", "b200q4_weight_download",
     "b200q4_mul_mat", "b200q4_mul_mat_wdata", "b200q4_quantize_rows", "b200q4_weight_upload_transposed",
     "b200q4_mul_mat_transposed", "b200q4_mul_mat_dev", "b200q4_quantize_rows_dev", "b200q4_sync",
-    "b200q4_mul_mat_dev_allgather", "b200q4_wait_flags", "b200q4_set_exact", "b200q4_quantize_weights",
+    "b200q4_mul_mat_dev_allgather", "b200q4_wait_flags", "b200q4_set_exact", "b200q4_quantize_weights", "b200q4_hint_next_weight",
     "b200q4_host_alloc", "b200q4_host_free", "b200q4_launch_count", "b200q4_launch_count_reset",
     "b200q4_kernel_for", "b200q4_time_mul_mat_dev",
 ]
@@ -79,6 +79,7 @@ def load_library(build: bool = True) -> C.CDLL:
         "b200q4_quantize_rows_dev": (i, [i, vp, i, i, sz, vp, vp]),
         "b200q4_sync": (i, [vp]),
         "b200q4_set_exact": (i, [i]),
+        "b200q4_hint_next_weight": (i, [vp, i]),
         "b200q4_quantize_weights": (i, [i, f32p, C.c_longlong, i, sz, vp, vp]),
         "b200q4_mul_mat_dev_allgather": (i, [vp, vp, i, sz, C.POINTER(vp), i, i, i, sz, C.POINTER(vp), vp, vp]),
         "b200q4_wait_flags": (i, [vp, i, vp, vp]),
