@@ -343,6 +343,33 @@ def test_k_slicing_forced_on_short_rows(gpu, oracle, qt, tag, n, k, m):
     w.free()
 
 
+@pytest.mark.parametrize("qt,tag", TYPES)
+def test_next_weight_hint_changes_nothing_but_timing(gpu, oracle, qt, tag):
+    """b200q4_hint_next_weight is a pure performance hint: same bits with no hint, the right hint, a hint for a tensor of
+    another shape (K-sliced), another type, a batch size the tile kernel serves, and a hinted tensor freed before the call."""
+    L = gpu.load_library()
+    rng = np.random.default_rng(12)
+    n, k = 1500, 4096
+    wq = oracle.quantize_rows(qt, rng.uniform(-0.05, 0.05, (n, k)).astype(np.float32))
+    x = rng.standard_normal((2, k)).astype(np.float32)
+    w = gpu.Q4Weight(qt, wq, n, k)
+    others = [gpu.Q4Weight(qt, oracle.quantize_rows(qt, rng.uniform(-0.05, 0.05, (300, 16384)).astype(np.float32)), 300, 16384),
+              gpu.Q4Weight(1 - qt, oracle.quantize_rows(1 - qt, rng.uniform(-0.05, 0.05, (40, 64)).astype(np.float32)), 40, 64)]
+    base = [gpu.mul_mat(w, x[:m]) for m in (1, 2)]
+    for hint, hm in ((w, 1), (others[0], 1), (others[0], 8), (others[1], 2), (w, 64)):
+        for i, m in enumerate((1, 2)):
+            assert L.b200q4_hint_next_weight(hint.handle, hm) == 0
+            assert np.array_equal(gpu.mul_mat(w, x[:m]).view(np.uint32), base[i].view(np.uint32))
+    gone = gpu.Q4Weight(qt, wq[:64], 64, k)
+    assert L.b200q4_hint_next_weight(gone.handle, 1) == 0
+    gone.free()                                            # the library drops a hint that points at a freed tensor
+    assert np.array_equal(gpu.mul_mat(w, x[:1]).view(np.uint32), base[0].view(np.uint32))
+    assert L.b200q4_hint_next_weight(None, 1) == 0
+    for o in others:
+        o.free()
+    w.free()
+
+
 # ---- offline weight quantizers on the device (row f-4) ---------------------------------------------
 @pytest.mark.parametrize("k", [64, 256])
 @pytest.mark.parametrize("qt,tag", TYPES)
