@@ -1105,11 +1105,12 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < p.stages; i++) {
-            mbar_init(&bar_full[i], 1);
-            mbar_init(&bar_empty[i], 1);                 // released by the reducer (which waited for every consumer)
-            mbar_init(&bar_done[i], PIPE_CONSUMERS);
+    if (threadIdx.x < 3 * PIPE_MAX_STAGES) {             // one barrier per thread: a single round of shared-memory latency
+        const int i = threadIdx.x % PIPE_MAX_STAGES, which = threadIdx.x / PIPE_MAX_STAGES;
+        if (i < p.stages) {
+            if (which == 0) mbar_init(&bar_full[i], 1);
+            else if (which == 1) mbar_init(&bar_empty[i], 1);   // released by the reducer (which waited for every consumer)
+            else mbar_init(&bar_done[i], PIPE_CONSUMERS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
