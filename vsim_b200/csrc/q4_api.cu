@@ -68,6 +68,7 @@ struct Ctx {
     const b200q4_weight *hint_w = nullptr; int hint_m = 1;   // b200q4_hint_next_weight: consumed by the next decode launch
     int prefetch_stages = 2;         // B200Q4_PREFETCH_STAGES: tasks per CTA of the hinted next launch to pull into L2 (0 = off); measured: 2 fills
                                      // the ~2 us gap between two launches (12 MB), more only competes with the launch's own last stages
+    int static_tasks = 0;            // B200Q4_STATIC_TASKS: tasks per CTA issued before the grid dependency resolves (0 = kernel default, 3)
     int b8_min_stages = 3;           // B200Q4_B8_MIN_STAGES: the 256-byte-per-block code layout is used when this many stages still fit (0 = never)
     int slice_min_c = 0;             // B200Q4_SLICE_MIN_C: tiles longer than this many units (4 quant blocks each) are K-sliced; 0 = default rule
     int pipe_flags = 0;              // B200Q4_PIPE_FLAGS: development knobs of the decode kernel (PipeParams::flags)
@@ -236,7 +237,7 @@ int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, con
     p.ticket = g.d_ticket;
     p.x_stride = x_stride_f; p.y_stride = y_stride_f;
     p.U = w->n_tiles * w->C; p.N = w->N; p.M = mc; p.C = w->C; p.n_tiles = w->n_tiles; p.nb = w->nb;
-    p.ntasks = pl.ntasks; p.PP = pl.PP; p.TS = pl.TS; p.stages = pl.stages; p.gnbp = pl.gnbp; p.flags = g.pipe_flags;
+    p.ntasks = pl.ntasks; p.PP = pl.PP; p.TS = pl.TS; p.stages = pl.stages; p.gnbp = pl.gnbp; p.flags = g.pipe_flags; p.nstatic = g.static_tasks;
     p.dbg = g.d_dbg;
     p.next = NextHint{};
     if (g.hint_w && g.prefetch_stages > 0 && !g.hint_w->transposed && g.hint_w->wt_bytes &&
@@ -658,6 +659,7 @@ int b200q4_init(int device)
     if (const char *e = getenv("B200Q4_SLICE_MIN_C")) g.slice_min_c = atoi(e) < 16 ? 16 : atoi(e);
     if (const char *e = getenv("B200Q4_ZERO_COPY")) g.zero_copy = atoi(e) != 0;
     if (const char *e = getenv("B200Q4_B8_MIN_STAGES")) g.b8_min_stages = atoi(e);
+    if (const char *e = getenv("B200Q4_STATIC_TASKS")) g.static_tasks = atoi(e);
     if (const char *e = getenv("B200Q4_PREFETCH_STAGES")) g.prefetch_stages = atoi(e);
     if (const char *e = getenv("B200Q4_EXACT")) g.exact = atoi(e) != 0;
     if (cudaHostAlloc(reinterpret_cast<void **>(&g.h_flag), 64, cudaHostAllocMapped) == cudaSuccess &&

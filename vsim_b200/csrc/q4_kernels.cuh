@@ -739,6 +739,7 @@ struct PipeParams {
     int            PP;       // K-slices (pieces) per tile; 1 = unsliced
     int            TS;       // units per task
     int            gnbp;     // quant blocks per row in the global apack (non-fused launches): plane stride = gnbp * rows
+    int            nstatic;  // static tasks per CTA (0 = PIPE_STATIC_TASKS)
     int            flags;    // development knob: 1 = the reducer polls its barriers instead of try_wait (measured: no gain)
     int            stages;
     unsigned long long *dbg; // optional timeline (B200Q4_TIMELINE builds), else NULL
@@ -1150,7 +1151,8 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             const int idx = sliced ? (int)blockIdx.x / p.PP : (int)blockIdx.x;
             const int ncls = sliced ? ((int)gridDim.x - cls + p.PP - 1) / p.PP : (int)gridDim.x;     // CTAs in this class
             const int limit = sliced ? p.n_tiles : p.ntasks;
-            for (int k = 0; k < PIPE_STATIC_TASKS; k++) {
+            const int nstatic = p.nstatic > 0 ? p.nstatic : PIPE_STATIC_TASKS;
+            for (int k = 0; k < nstatic; k++) {
                 const int t = idx + k * ncls;
                 if (t < limit) issue_seq(t);
             }
@@ -1159,7 +1161,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             PIPE_STAMP(2);
             // then dynamic tickets, fetched one task ahead so the atomic's latency hides behind the copies
             int *tk = sliced ? p.ticket + 2 + cls : p.ticket;
-            const int base = PIPE_STATIC_TASKS * ncls;
+            const int base = nstatic * ncls;
             int cur = base + atomicAdd(tk, 1);
             while (cur < limit) {
                 const int nxt = base + atomicAdd(tk, 1);
