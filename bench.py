@@ -142,6 +142,8 @@ def cpu_baseline(qt: int, m: int, wq: np.ndarray, x: np.ndarray, budget_s: float
         _, us = ref.mul_mat(qt, wq, N_ROWS, K_DIM, x, nth=nth, reps=reps, return_time=True)
         sample = (f"oracle/_ref (reference ggml.c+imax.c, Makefile-ubuntu flags) ggml_graph_compute of one "
                   f"Q4_{qt} mul_mat K={K_DIM} N={N_ROWS} M={m}, best of {reps} calls, {nth} threads")
+        _, us_t1 = ref.mul_mat(qt, wq, N_ROWS, K_DIM, x, nth=1, reps=5, return_time=True)     # T = 1 beside T = nproc
+        one_thread = {"value": nbytes / (us_t1 * 1e-6) / 1e9, "ms_per_call": us_t1 / 1e3, "sample": "best of 5 calls, 1 thread"}
     else:
         o = orc.Oracle()
         kind = "port"
@@ -153,8 +155,9 @@ def cpu_baseline(qt: int, m: int, wq: np.ndarray, x: np.ndarray, budget_s: float
             us = min(us, (time.perf_counter() - t0) * 1e6)
         sample = (f"oracle port (q4_oracle.c) of one Q4_{qt} mul_mat K={K_DIM} N={N_ROWS} M={m}, "
                   f"best of {reps} calls, {nth} threads")
+        one_thread = None
     return {"value": nbytes / (us * 1e-6) / 1e9, "unit": "GB/s", "cores": nth, "kind": kind,
-            "sample": sample, "ms_per_call": us / 1e3}
+            "sample": sample, "ms_per_call": us / 1e3, "one_thread": one_thread}
 
 
 # GPT-J-6B (BASELINE.json configs[2]): n_embd 4096, 28 layers, vocab 50400 -- the Q4 mul_mats of one decode step
