@@ -155,6 +155,25 @@ int b200q4_mul_mat_dev_allgather(const b200q4_weight *w, const float *d_x, int M
 int b200q4_wait_flags(const uint32_t *local_flags, int world, const uint32_t *seq_counter, void *stream);
 int b200q4_sync(void *stream);
 
+/* ---- model files (row f-3, first half) -----------------------------------------------
+ * The reference's on-disk format (vsim.cpp:108-458): magic 0x67676d6c,
+ * n_header_ints int32 hyper-parameters (7 for the GPT-NeoX files vsim.cpp loads: n_vocab, n_embd,
+ * n_head, n_layer, n_rot, use_parallel_residual, ftype; 6 for the files of quantize_{gptj,gpt2,
+ * bloom}.cpp), the vocabulary (with a leading count when vocab_has_count != 0, as the quantize_*
+ * tools write it; vsim.cpp:155 reads none), then tensor records {n_dims, name length, ftype
+ * (0 f32, 1 f16, 2 q4_0, 3 q4_1), dims, name, data}.  The file is memory-mapped; with upload != 0
+ * every 2-D Q4 tensor goes from the mapping straight to HBM (no second host copy) and stays
+ * resident until b200q4_model_free().  upload == 0 only indexes the file (needs no GPU).     */
+typedef struct b200q4_model b200q4_model;
+b200q4_model *b200q4_model_load(const char *path, int n_header_ints, int vocab_has_count, int upload);
+int  b200q4_model_header(const b200q4_model *m, int i);
+int  b200q4_model_tensor_count(const b200q4_model *m);
+int  b200q4_model_tensor_info(const b200q4_model *m, int i, const char **name, int *n_dims, int *ftype,
+                              int *ne0, int *ne1, size_t *file_offset, size_t *nbytes);
+b200q4_weight *b200q4_model_weight(const b200q4_model *m, int i);      /* resident Q4 tensor or NULL */
+const void *b200q4_model_tensor_data(const b200q4_model *m, int i);    /* the tensor's bytes in the mapping */
+void b200q4_model_free(b200q4_model *m);
+
 /* ---- next-weight hint ------------------------------------------------------------
  * A decode graph visits its weight tensors in a fixed order.  Telling the library which
  * tensor the NEXT decode call (M_next rows) will use lets the current launch, once it has

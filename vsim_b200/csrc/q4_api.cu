@@ -17,6 +17,11 @@ using b200q4::PIPE_TILE_SPLIT;
 #include <string>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 using namespace b200q4;
 
 struct b200q4_weight {
@@ -1003,6 +1008,111 @@ int b200q4_mul_mat_transposed(const b200q4_weight *wt, const float *x, int M, si
     CK(cudaMemcpy2DAsync(y, y_stride, g.d_y, (size_t)N * 4, (size_t)N * 4, M, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     return B200Q4_OK;
+}
+
+// ---- model files (row f-3, first half): the reference's on-disk format, Q4 tensors straight from the mapping to HBM ----
+struct b200q4_model_tensor { std::string name; int n_dims, ftype, ne[2]; size_t offset, nbytes; b200q4_weight *w; };
+struct b200q4_model {
+    std::vector<int> header;
+    std::vector<b200q4_model_tensor> tensors;
+    void *map = nullptr; size_t map_size = 0;
+};
+
+b200q4_model *b200q4_model_load(const char *path, int n_header_ints, int vocab_has_count, int upload)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!path || n_header_ints < 1 || n_header_ints > 32) { fail(B200Q4_EINVAL, "model_load: bad argument"); return nullptr; }
+    if (upload && need_init()) return nullptr;
+    const int fd = open(path, O_RDONLY);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0) { if (fd >= 0) close(fd); fail(B200Q4_EINVAL, "model_load: cannot open '%s'", path); return nullptr; }
+    const size_t size = (size_t)st.st_size;
+    void *map = size ? mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    close(fd);
+    if (!map || map == MAP_FAILED) { fail(B200Q4_EINVAL, "model_load: cannot map '%s'", path); return nullptr; }
+    const unsigned char *b = static_cast<const unsigned char *>(map);
+    b200q4_model *m = new b200q4_model();
+    m->map = map; m->map_size = size;
+    size_t off = 0;
+    auto bail = [&](const char *what) { fail(B200Q4_EINVAL, "model_load: %s (offset %zu of '%s')", what, off, path); b200q4_model_free(m); return (b200q4_model *)nullptr; };
+    auto rd32 = [&](int32_t &v) { if (off + 4 > size) return false; memcpy(&v, b + off, 4); off += 4; return true; };
+    int32_t magic = 0;
+    if (!rd32(magic) || magic != 0x67676d6c) return bail("bad magic");                  // vsim.cpp:121-126
+    for (int i = 0; i < n_header_ints; i++) { int32_t v; if (!rd32(v)) return bail("truncated header"); m->header.push_back(v); }
+    int32_t n_vocab = m->header[0];                                                        // first header int in every family
+    if (vocab_has_count && (!rd32(n_vocab) || n_vocab != m->header[0])) return bail("bad vocab size");   // quantize_gptj.cpp:101-110
+    if (n_vocab < 0) return bail("bad vocab size");
+    for (int i = 0; i < n_vocab; i++) {                                                    // vsim.cpp:163-173
+        int32_t len;
+        if (!rd32(len) || len < 0 || off + (size_t)len > size) return bail("truncated vocabulary");
+        off += (size_t)len;
+    }
+    while (off < size) {                                                                   // vsim.cpp:375-448
+        int32_t n_dims, length, ftype;
+        if (!rd32(n_dims) || !rd32(length) || !rd32(ftype)) return bail("truncated tensor header");
+        if (n_dims < 1 || n_dims > 2 || length < 0 || ftype < 0 || ftype > 3) return bail("bad tensor header");
+        b200q4_model_tensor t;
+        t.n_dims = n_dims; t.ftype = ftype; t.ne[0] = t.ne[1] = 1; t.w = nullptr;
+        for (int i = 0; i < n_dims; i++) {
+            int32_t v;
+            if (!rd32(v)) return bail("truncated tensor shape");
+            if (v < 0) return bail("bad tensor shape");
+            t.ne[i] = v;
+        }
+        if (off + (size_t)length > size) return bail("truncated tensor name");
+        t.name.assign(reinterpret_cast<const char *>(b + off), (size_t)length);
+        off += (size_t)length;
+        const size_t nel = (size_t)t.ne[0] * (size_t)t.ne[1];
+        if (ftype >= 2 && t.ne[0] % QK) return bail("quantized tensor whose row length is not a multiple of 32");
+        t.nbytes = ftype == 0 ? nel * 4 : ftype == 1 ? nel * 2 : nel / QK * (ftype == 2 ? 20 : 24);
+        t.offset = off;
+        if (off + t.nbytes > size) return bail("truncated tensor data");
+        off += t.nbytes;
+        m->tensors.push_back(t);
+    }
+    if (upload)
+        for (auto &t : m->tensors)
+            if (t.n_dims == 2 && t.ftype >= 2) {
+                t.w = b200q4_weight_upload(t.ftype - 2, b + t.offset, t.ne[1], t.ne[0], 0);   // rows = ne[1], K = ne[0]
+                if (!t.w) { b200q4_model_free(m); return nullptr; }
+            }
+    return m;
+}
+
+int b200q4_model_header(const b200q4_model *m, int i) { return (m && i >= 0 && i < (int)m->header.size()) ? m->header[(size_t)i] : B200Q4_EINVAL; }
+int b200q4_model_tensor_count(const b200q4_model *m) { return m ? (int)m->tensors.size() : B200Q4_EINVAL; }
+
+int b200q4_model_tensor_info(const b200q4_model *m, int i, const char **name, int *n_dims, int *ftype, int *ne0, int *ne1,
+                             size_t *file_offset, size_t *nbytes)
+{
+    if (!m || i < 0 || i >= (int)m->tensors.size()) return fail(B200Q4_EINVAL, "model_tensor_info: bad index");
+    const b200q4_model_tensor &t = m->tensors[(size_t)i];
+    if (name) *name = t.name.c_str();
+    if (n_dims) *n_dims = t.n_dims;
+    if (ftype) *ftype = t.ftype;
+    if (ne0) *ne0 = t.ne[0];
+    if (ne1) *ne1 = t.ne[1];
+    if (file_offset) *file_offset = t.offset;
+    if (nbytes) *nbytes = t.nbytes;
+    return B200Q4_OK;
+}
+
+b200q4_weight *b200q4_model_weight(const b200q4_model *m, int i)
+{
+    return (m && i >= 0 && i < (int)m->tensors.size()) ? m->tensors[(size_t)i].w : nullptr;
+}
+
+const void *b200q4_model_tensor_data(const b200q4_model *m, int i)
+{
+    return (m && i >= 0 && i < (int)m->tensors.size()) ? static_cast<const unsigned char *>(m->map) + m->tensors[(size_t)i].offset : nullptr;
+}
+
+void b200q4_model_free(b200q4_model *m)
+{
+    if (!m) return;
+    for (auto &t : m->tensors) if (t.w) b200q4_weight_free(t.w);
+    if (m->map) munmap(m->map, m->map_size);
+    delete m;
 }
 
 int b200q4_hint_next_weight(const b200q4_weight *next, int M_next)

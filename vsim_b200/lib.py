@@ -24,6 +24,8 @@ ABI_SYMBOLS = [
     "b200q4_mul_mat", "b200q4_mul_mat_wdata", "b200q4_quantize_rows", "b200q4_weight_upload_transposed",
     "b200q4_mul_mat_transposed", "b200q4_mul_mat_dev", "b200q4_quantize_rows_dev", "b200q4_sync",
     "b200q4_mul_mat_dev_allgather", "b200q4_wait_flags", "b200q4_set_exact", "b200q4_quantize_weights", "b200q4_hint_next_weight",
+    "b200q4_model_load", "b200q4_model_header", "b200q4_model_tensor_count", "b200q4_model_tensor_info",
+    "b200q4_model_weight", "b200q4_model_tensor_data", "b200q4_model_free",
     "b200q4_host_alloc", "b200q4_host_free", "b200q4_launch_count", "b200q4_launch_count_reset",
     "b200q4_kernel_for", "b200q4_time_mul_mat_dev",
 ]
@@ -80,6 +82,14 @@ def load_library(build: bool = True) -> C.CDLL:
         "b200q4_sync": (i, [vp]),
         "b200q4_set_exact": (i, [i]),
         "b200q4_hint_next_weight": (i, [vp, i]),
+        "b200q4_model_load": (vp, [C.c_char_p, i, i, i]),
+        "b200q4_model_header": (i, [vp, i]),
+        "b200q4_model_tensor_count": (i, [vp]),
+        "b200q4_model_tensor_info": (i, [vp, i, C.POINTER(C.c_char_p), C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i),
+                                         C.POINTER(sz), C.POINTER(sz)]),
+        "b200q4_model_weight": (vp, [vp, i]),
+        "b200q4_model_tensor_data": (vp, [vp, i]),
+        "b200q4_model_free": (None, [vp]),
         "b200q4_quantize_weights": (i, [i, f32p, C.c_longlong, i, sz, vp, vp]),
         "b200q4_mul_mat_dev_allgather": (i, [vp, vp, i, sz, C.POINTER(vp), i, i, i, sz, C.POINTER(vp), vp, vp]),
         "b200q4_wait_flags": (i, [vp, i, vp, vp]),
