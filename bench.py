@@ -396,9 +396,11 @@ def main() -> int:
                 barrier()
                 try:
                     graph = torch.cuda.CUDAGraph()
+                    lc0 = vs.launch_count()
                     with torch.cuda.graph(graph, stream=stream):
                         for i in range(gsteps):
                             step(i, m, ws, stream)
+                    timed.launches_per_step = (vs.launch_count() - lc0) / gsteps    # kernels captured per step (replays bypass the counter)
                     graph.replay()                         # untimed: instantiation / upload
                 except Exception:                          # noqa: BLE001
                     graph = None
@@ -430,7 +432,8 @@ def main() -> int:
     ms_total = timed(M_HEAD, w0, args.steps, args.warmup)
     launches_total = vs.launch_count()
     # graph replays re-issue captured launches without passing through the library's counter: M=1 is one launch per step
-    launches_timed = args.steps if getattr(timed, "graphed", False) else launches_total * args.steps // (args.steps + args.warmup)
+    launches_timed = (int(round(args.steps * getattr(timed, "launches_per_step", 1))) if getattr(timed, "graphed", False)
+                      else launches_total * args.steps // (args.steps + args.warmup))
     ms_step = ms_total / args.steps
     value = alg_bytes(0, M_HEAD) * world / (ms_step * 1e-3) / 1e9
 
