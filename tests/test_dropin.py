@@ -50,10 +50,13 @@ def _logits(stdout):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("qt,tag", [(Q4_0, "q4_0"), (Q4_1, "q4_1")])
-def test_reference_graph_executor_on_b200_backend(qt, tag):
+def test_reference_graph_executor_on_b200_backend(qt, tag, monkeypatch):
     """ggml_mul_mat + ggml_graph_compute of the reference, hook served by the GPU, vs the CPU reference."""
     if not B200_LIB.exists():
         pytest.skip("oracle/_ref/libggml_b200.so not built")
+    # this test is about the FAST kernels behind the hook; the hook itself would default the (process-wide) library
+    # to exact mode, which the later GPU test modules of this pytest process must not inherit
+    monkeypatch.setenv("B200Q4_EXACT", "0")
     from oracle import Reference
     ref = Reference()
     L = C.CDLL(str(B200_LIB))
@@ -80,13 +83,14 @@ def test_vsim_neox_end_to_end_tokens_and_logits(tmp_path, qt, tag):
     from tests.helpers.neox_file import write_neox
     model = tmp_path / f"tiny-{tag}.bin"
     write_neox(model, qt)
+    fast = {"B200Q4_EXACT": "0"}                           # the hook defaults to exact mode: this test is about the fast kernels
     lr = _logits(_run(REF_BIN, model, logits=True))
-    lg = _logits(_run(B200_BIN, model, logits=True))
+    lg = _logits(_run(B200_BIN, model, logits=True, env=fast))
     assert lr.shape == lg.shape and lr.shape[1] == 256
     # north_star: logits within 1e-3 relative (of the row's scale)
     assert np.abs(lg - lr).max() <= 1e-3 * np.abs(lr).max(), np.abs(lg - lr).max() / np.abs(lr).max()
     tr = _tokens(_run(REF_BIN, model, n_predict=12))
-    tg = _tokens(_run(B200_BIN, model, n_predict=12))
+    tg = _tokens(_run(B200_BIN, model, n_predict=12, env=fast))
     assert tr == tg, (tr, tg)
 
 
@@ -101,7 +105,7 @@ def test_vsim_neox_exact_mode_reproduces_the_reference_bit_for_bit(tmp_path, qt,
     from tests.helpers.neox_file import write_neox
     model = tmp_path / f"exact-{tag}.bin"
     write_neox(model, qt, n_vocab=512, n_embd=512, n_head=8, n_layer=6, n_rot=32, seed=3)
-    ex = {"B200Q4_EXACT": "1"}
+    ex = {}                                                # exact mode is the hook's default
     lr = _logits(_run(REF_BIN, model, logits=True))
     lg = _logits(_run(B200_BIN, model, logits=True, env=ex))
     assert lr.shape == lg.shape

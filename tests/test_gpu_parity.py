@@ -22,6 +22,8 @@ FLOOR = 1e-5         # x max|y_ref| of the row: outputs that cancel to ~0
 def gpu():
     import vsim_b200
     vsim_b200.init(0)
+    vsim_b200.load_library().b200q4_set_exact(0)           # these are the tests of the default (fast) kernels
+    assert not vsim_b200.kernel_for(0, 1, 64, 64).endswith("_exact")
     yield vsim_b200
     # leave the context up: other modules share the process
 

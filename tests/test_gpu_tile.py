@@ -21,6 +21,7 @@ RTOL, FLOOR = 1e-3, 1e-5
 def gpu():
     import vsim_b200
     vsim_b200.init(0)
+    vsim_b200.load_library().b200q4_set_exact(0)           # the tile kernel is a fast-mode kernel
     return vsim_b200
 
 

@@ -89,6 +89,7 @@ def test_upload_straight_from_the_mapping(tmp_path, oracle, qt):
     from tests.helpers.neox_file import write_neox
     vsim_b200.init(0)
     L = _lib()
+    L.b200q4_set_exact(0)
     path = tmp_path / "m.bin"
     write_neox(path, qt, n_vocab=128, n_embd=256, n_head=4, n_layer=1, n_rot=16)
     m = L.b200q4_model_load(str(path).encode(), 7, 0, 1)

@@ -127,8 +127,7 @@ def main() -> int:
     ap.add_argument("--keep", action="store_true", help="keep the model file")
     ap.add_argument("--timeout", type=int, default=900)
     args = ap.parse_args()
-    if args.exact:
-        GPU_ENV["B200Q4_EXACT"] = "1"
+    GPU_ENV["B200Q4_EXACT"] = "1" if args.exact else "0"      # (the hook's own default is exact mode)
     cpu_bin, gpu_bin = REF / "vsim-ubuntu", REF / "vsim-b200"
     if not (cpu_bin.exists() and gpu_bin.exists()):
         print(json.dumps({"unavailable": "oracle/_ref/vsim-ubuntu / vsim-b200 not built (make -C oracle needs /root/reference)"}))
@@ -158,7 +157,7 @@ def main() -> int:
             "threads": {"cpu_reference": args.threads, "b200_hook": args.gpu_threads}, "host_cores": os.cpu_count(),
             "prompt_logits_max_abs_diff_over_max_abs": float(np.abs(lg - lc).max() / np.abs(lc).max()),
             "prompt_logits_argmax": {"cpu_reference": int(lc.argmax()), "b200_hook": int(lg.argmax())},
-            "random_model_gain": args.gain, "b200_mode": "exact (B200Q4_EXACT=1)" if args.exact else "default",
+            "random_model_gain": args.gain, "b200_mode": "exact (B200Q4_EXACT=1, the hook's default)" if args.exact else "fast kernels (B200Q4_EXACT=0)",
             "n_predict": {"cpu_reference": c["n_predict"], "b200_hook": g["n_predict"]}, "prompt_tokens": 5,
             "t_predict_s": {"cpu_reference": c["t_predict_s"], "b200_hook": g["t_predict_s"]},
             "cpu_reference_ms_per_token": c["ms_per_token"], "b200_hook_ms_per_token": g["ms_per_token"],

@@ -16,7 +16,7 @@ def logits(binary, threads, env=None):
         return np.zeros(50400)
     return rows[0]
 res = {}
-for tag, b, env in (("cpu", d.REF / 'vsim-ubuntu', None), ("gpu-default", d.REF / 'vsim-b200', None), ("gpu-exact", d.REF / 'vsim-b200', {"B200Q4_EXACT": "1"})):
+for tag, b, env in (("cpu", d.REF / 'vsim-ubuntu', None), ("gpu-fast", d.REF / 'vsim-b200', {"B200Q4_EXACT": "0"}), ("gpu-exact", d.REF / 'vsim-b200', {"B200Q4_EXACT": "1"})):
     for th in (1, 4, 16):
         res[(tag, th)] = logits(b, th, env)
 for k, v in res.items():

@@ -13,7 +13,7 @@ p = Path('/dev/shm/chk.bin'); d.write_model(p, nv, ne, nh, nl, nr)
 dump = Path(tempfile.mkdtemp(dir='/dev/shm'))
 cmd = [str(d.REF / 'vsim-b200'), "gptneox", "-m", str(p), "--prompt", "1 2 3 4 5", "--seed", "42", "--threads", "4", "--n_predict", "2",
        "--top_k", "1", "--top_p", "1.0", "--temp", "1.0", "--repeat_penalty", "1.0"]
-r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "B200Q4_DUMP_DIR": str(dump)})
+r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "B200Q4_EXACT": "0", "B200Q4_DUMP_DIR": str(dump)})
 print("rc", r.returncode, r.stderr[-300:])
 # Q4 tensors of the file in order
 blob = np.memmap(p, dtype=np.uint8, mode='r')
