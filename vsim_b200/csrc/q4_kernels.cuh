@@ -641,10 +641,13 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p)
 __device__ __forceinline__ void peer_wait_one(const uint32_t *flags, int r, uint32_t seq)
 {
     const uint32_t exp = seq * PEER_UNIT;
-    for (;;) {
+    for (uint32_t spins = 0;; spins++) {
         uint32_t v;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
         if ((int32_t)(v - exp) >= 0) break;
+        // A peer that never arrives (a rank that died) must not hang this GPU for good: after roughly a minute of
+        // polling the kernel traps, the stream reports an error and the process ends instead of spinning forever.
+        if (spins > (1u << 26)) __trap();
         __nanosleep(20);
     }
 }
