@@ -1207,6 +1207,26 @@ int b200q4_debug_set_slice_min_c(int c)
     return old;
 }
 
+// development / test aid (not part of b200q4.h): the decode launch plan for a (type, N, K, M) problem, computed on the host
+// alone (no device needed: without one the shared-memory limits default to the B200's).  out[0..11] = MP, PP, TS, ntasks,
+// grid, stages, nbp, gnbp, b8, m1, C, n_tiles; returns the dynamic shared-memory bytes (or a negative error).
+long long b200q4_debug_plan(int type, int N, int K, int M, int *out)
+{
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if ((type != 0 && type != 1) || N < 1 || K < QK || K % QK || M < 1 || M > 8 || !out) return B200Q4_EINVAL;
+    b200q4_weight w{};
+    w.type = type; w.N = N; w.K = K; w.nb = K / QK; w.transposed = false;
+    w.C = (w.nb + CHUNK_BLKS - 1) / CHUNK_BLKS;
+    w.n_tiles = (N + TILE_ROWS - 1) / TILE_ROWS;
+    const PipePlan pp = pipe_plan(&w, M, true);
+    if (pp.MP < 1) return B200Q4_EINVAL;
+    const int slots = (g.sms > 0 ? g.sms : 148) * (pp.ncw == 8 ? 2 : 1);
+    const int vals[12] = {pp.MP, pp.PP, pp.TS, pp.ntasks, pp.ntasks < slots ? pp.ntasks : slots, pp.stages, pp.nbp, pp.gnbp,
+                          pp.b8 ? 1 : 0, pp.m1 ? 1 : 0, w.C, w.n_tiles};
+    for (int i = 0; i < 12; i++) out[i] = vals[i];
+    return (long long)pp.smem;
+}
+
 uint64_t b200q4_launch_count(void) { return g.launches; }
 void b200q4_launch_count_reset(void) { g.launches = 0; }
 
