@@ -14,6 +14,7 @@ from oracle import Q4_0, Q4_1, REF_DIR
 
 REF_BIN = REF_DIR / "vsim-ubuntu"
 B200_BIN = REF_DIR / "vsim-b200"
+ORACLE_BIN = REF_DIR / "vsim-oracle"
 B200_LIB = REF_DIR / "libggml_b200.so"
 
 
@@ -111,3 +112,20 @@ def test_vsim_neox_exact_mode_reproduces_the_reference_bit_for_bit(tmp_path, qt,
     assert lr.shape == lg.shape
     assert np.array_equal(lr, lg), np.abs(lr - lg).max()
     assert _tokens(_run(REF_BIN, model, n_predict=24)) == _tokens(_run(B200_BIN, model, n_predict=24, env=ex))
+
+
+@pytest.mark.parametrize("qt,tag", [(Q4_0, "q4_0"), (Q4_1, "q4_1")])
+def test_patched_reference_with_oracle_hook_equals_unmodified_reference(tmp_path, qt, tag):
+    """CPU: the three-line ggml.c patch + the hook contract (thread 0 does the whole operator from src1->data, the
+    CPU INIT quantization skipped) change nothing -- vsim-oracle (patched sources, hook served by the CPU oracle)
+    prints exactly what the unmodified vsim-ubuntu prints.  Whatever vsim-b200 then differs by is the GPU back-end's."""
+    if not (REF_BIN.exists() and ORACLE_BIN.exists()):
+        pytest.skip("oracle/_ref vsim binaries not built")
+    from tests.helpers.neox_file import write_neox
+    model = tmp_path / f"o-{tag}.bin"
+    write_neox(model, qt, n_vocab=128, n_embd=128, n_head=4, n_layer=3, n_rot=16, seed=5)
+    for th in (1, 3):
+        lr = _logits(_run(REF_BIN, model, logits=True, threads=th))
+        lo = _logits(_run(ORACLE_BIN, model, logits=True, threads=th))
+        assert np.array_equal(lr, lo)
+    assert _tokens(_run(REF_BIN, model, n_predict=10)) == _tokens(_run(ORACLE_BIN, model, n_predict=10))
