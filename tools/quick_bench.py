@@ -22,6 +22,8 @@ def main():
     shapes = [(16384, 4096)]
     if "--all" in sys.argv:
         shapes += [(4096, 4096), (4096, 16384), (50400, 4096), (6144, 24576)]
+    if "--bloom" in sys.argv:                              # BLOOM-7b1 shapes (BASELINE.json configs[3]: Q4_1 prefill of 2048 tokens)
+        shapes = [(4096, 4096), (16384, 4096), (4096, 16384), (250880, 4096)]
     if "--neox" in sys.argv:
         shapes = [(6144, 6144), (24576, 6144), (6144, 24576), (5120, 5120), (20480, 5120)]
     ms_list = [1, 8, 16, 64] if "--m" not in sys.argv else [int(v) for v in sys.argv[sys.argv.index("--m") + 1].split(",")]
@@ -29,7 +31,7 @@ def main():
     L = vsim_b200.load_library()
     rng = np.random.default_rng(1)
     for n, k in shapes:
-        for qt in (0, 1):
+        for qt in ((1,) if "--bloom" in sys.argv else (0, 1)):
             rb = vlib.row_bytes(qt, k)
             nw = max(2, int(np.ceil(400e6 / (n * rb))))
             ws = []
