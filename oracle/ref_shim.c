@@ -148,4 +148,51 @@ void ref_tensor_layout(size_t out[8])
     out[6] = offsetof(struct ggml_tensor, src1);
     out[7] = offsetof(struct ggml_tensor, data);
 }
-#endif
+
+/* ---- one-op graphs of the NON-hot ops of the NeoX graph (row f-1 groundwork: pins oracle/neox_ops_oracle.c) ----
+ * op: 0 norm, 1 gelu, 2 soft_max, 3 gptneox_rope(n_past = a, n_dims = b, mode = c) on x[ne2][ne1][ne0],
+ *     4 diag_mask_inf(n_past = a).  x is copied into a fresh tensor, y receives the result tensor's data. */
+int ref_op(int op, const float *x, int ne0, int ne1, int ne2, int a, int b, int c, float *y, int n_threads)
+{
+    const size_t n = (size_t)ne0 * ne1 * ne2;
+    struct ggml_init_params ip = { n * 4 * 4 + (1u << 20), NULL };
+    struct ggml_context *ctx = ggml_init(ip);
+    if (!ctx) return -1;
+    struct ggml_tensor *t = ggml_new_tensor_3d(ctx, GGML_TYPE_F32, ne0, ne1, ne2);
+    memcpy(t->data, x, n * 4);
+    struct ggml_tensor *r = NULL;
+    switch (op) {
+    case 0: r = ggml_norm(ctx, t); break;
+    case 1: r = ggml_gelu(ctx, t); break;
+    case 2: r = ggml_soft_max(ctx, t); break;
+    case 3: r = ggml_gptneox_rope(ctx, t, a, b, c); break;
+    case 4: r = ggml_diag_mask_inf(ctx, t, a); break;
+    default: ggml_free(ctx); return -2;
+    }
+    struct ggml_cgraph gf = ggml_build_forward(r);
+    gf.n_threads = n_threads;
+    ggml_graph_compute(ctx, &gf);
+    memcpy(y, r->data, n * 4);
+    ggml_free(ctx);
+    return 0;
+}
+
+int ref_get_rows(int type, const void *W, int N, int K, const int *ids, int n_ids, float *y)
+{
+    const size_t wbytes = (size_t)N * (K / 32) * (type == 0 ? 20 : 24);
+    struct ggml_init_params ip = { wbytes + (size_t)n_ids * K * 4 + (size_t)n_ids * 4 + (1u << 20), NULL };
+    struct ggml_context *ctx = ggml_init(ip);
+    if (!ctx) return -1;
+    struct ggml_tensor *w = ggml_new_tensor_2d(ctx, (enum ggml_type)type, K, N);
+    struct ggml_tensor *idt = ggml_new_tensor_1d(ctx, GGML_TYPE_I32, n_ids);
+    memcpy(w->data, W, wbytes);
+    memcpy(idt->data, ids, (size_t)n_ids * 4);
+    struct ggml_tensor *r = ggml_get_rows(ctx, w, idt);
+    struct ggml_cgraph gf = ggml_build_forward(r);
+    gf.n_threads = 1;
+    ggml_graph_compute(ctx, &gf);
+    memcpy(y, r->data, (size_t)n_ids * K * 4);
+    ggml_free(ctx);
+    return 0;
+}
+#endif /* REF_SHIM_LIB */
