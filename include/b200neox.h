@@ -1,0 +1,37 @@
+/*
+ * b200neox.h -- device-resident GPT-NeoX forward pass (first slice).
+ *
+ * Replaces, for the graph the reference runs, gptneox_eval (vsim.cpp:470-747) + ggml_graph_compute (ggml.c:8245-8700):
+ * token ids in, logits of the last token out, every tensor in between resident in HBM.  The Q4 mul_mats are this
+ * library's own (include/b200q4.h: the fast kernels, or -- after b200q4_set_exact(1) -- the bit-identical ones); the
+ * other ops follow the reference's arithmetic exactly (ggml.c:4246-4303 norm, :819-827 gelu through the fp16 table,
+ * :5825-5893 soft_max, :6086-6153 gptneox_rope, :4355-4553 the two f32 mul_mat branches of attention).  With exact-mode
+ * mul_mats the logits equal the reference program's bit for bit, INCLUDING their dependence on ggml's thread count
+ * (the per-thread partial sums of V^T x softmax, ggml.c:4463-4481): n_threads_emulated selects which --threads value
+ * of the reference to reproduce.
+ *
+ * Model files: the reference's GPT-NeoX format with Q4_0 or Q4_1 weights (vsim.cpp:108-458), use_parallel_residual = 1.
+ * Plain C ABI; every function returns B200Q4_OK (0) / a negative B200Q4_E* code or NULL and records a message for
+ * b200neox_last_error().  Needs b200q4_init() first.  No CPU fallback.
+ */
+#ifndef B200NEOX_H
+#define B200NEOX_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200neox b200neox;
+
+/* n_ctx: positions of KV memory (the reference uses 512, vsim.cpp:758); max_batch: most tokens one eval may carry */
+b200neox *b200neox_load(const char *path, int n_ctx, int max_batch);
+int  b200neox_n_vocab(const b200neox *m);
+/* gptneox_eval(model, n_threads, n_past, tokens[N]) -> logits of the last token (host, n_vocab floats) */
+int  b200neox_eval(b200neox *m, const int *tokens, int N, int n_past, int n_threads_emulated, float *logits_out);
+void b200neox_free(b200neox *m);
+const char *b200neox_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

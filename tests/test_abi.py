@@ -15,9 +15,12 @@ ROOT = Path(__file__).resolve().parents[1]
 
 
 def _declared_in_header():
-    text = (ROOT / "include" / "b200q4.h").read_text()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200q4_[a-z0-9_]+)\s*\(", text)))
+    names = set()
+    for hdr in ("b200q4.h", "b200neox.h"):               # every public header of include/
+        text = (ROOT / "include" / hdr).read_text()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(b200(?:q4|neox)_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_header_symbols_all_exported():

@@ -26,6 +26,7 @@ ABI_SYMBOLS = [
     "b200q4_mul_mat_dev_allgather", "b200q4_wait_flags", "b200q4_set_exact", "b200q4_quantize_weights", "b200q4_hint_next_weight",
     "b200q4_model_load", "b200q4_model_header", "b200q4_model_tensor_count", "b200q4_model_tensor_info",
     "b200q4_model_weight", "b200q4_model_tensor_data", "b200q4_model_free",
+    "b200neox_load", "b200neox_n_vocab", "b200neox_eval", "b200neox_free", "b200neox_last_error",
     "b200q4_host_alloc", "b200q4_host_free", "b200q4_launch_count", "b200q4_launch_count_reset",
     "b200q4_kernel_for", "b200q4_time_mul_mat_dev",
 ]
@@ -90,6 +91,11 @@ def load_library(build: bool = True) -> C.CDLL:
         "b200q4_model_weight": (vp, [vp, i]),
         "b200q4_model_tensor_data": (vp, [vp, i]),
         "b200q4_model_free": (None, [vp]),
+        "b200neox_load": (vp, [C.c_char_p, i, i]),
+        "b200neox_n_vocab": (i, [vp]),
+        "b200neox_eval": (i, [vp, vp, i, i, i, vp]),
+        "b200neox_free": (None, [vp]),
+        "b200neox_last_error": (C.c_char_p, []),
         "b200q4_quantize_weights": (i, [i, f32p, C.c_longlong, i, sz, vp, vp]),
         "b200q4_mul_mat_dev_allgather": (i, [vp, vp, i, sz, C.POINTER(vp), i, i, i, sz, C.POINTER(vp), vp, vp]),
         "b200q4_wait_flags": (i, [vp, i, vp, vp]),
