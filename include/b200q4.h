@@ -206,6 +206,7 @@ int b200q4_quantize_weights(int type, const float *src, long long n_rows, int K,
  * re-quantization amplify downstream).  Returns the previous setting.  Also
  * selectable with the environment variable B200Q4_EXACT=1 at b200q4_init().      */
 int b200q4_set_exact(int on);
+int b200q4_exact_enabled(void);
 
 /* Pinned host memory for callers that want zero-staging H2D/D2H copies.      */
 void *b200q4_host_alloc(size_t bytes);

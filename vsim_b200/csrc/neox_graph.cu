@@ -79,6 +79,43 @@ __global__ void k_layernorm(const float *__restrict__ x, int n_rows, int n, cons
     for (int i = 0; i < n; i++) yr[i] = __fadd_rn(__fmul_rn(w[i], __fmul_rn(yr[i], scale)), b[i]);
 }
 
+// The same operator for the fast mode (exact mode off): one 256-thread block per row, the two double accumulations as
+// parallel tree reductions.  Every float operation is the one above; only the ORDER of the double additions differs,
+// i.e. mean and variance may move by an ulp of a double (1e-16) before they are rounded to the float scale.
+__global__ void __launch_bounds__(256) k_layernorm_fast(const float *__restrict__ x, int n, const float *__restrict__ w,
+                                                         const float *__restrict__ b, float *__restrict__ y)
+{
+    __shared__ double sh[256];
+    const float *xr = x + (size_t)blockIdx.x * n;
+    float *yr = y + (size_t)blockIdx.x * n;
+    const int tid = threadIdx.x;
+    auto block_sum = [&](double v) {
+        sh[tid] = v;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) sh[tid] = __dadd_rn(sh[tid], sh[tid + o]);
+            __syncthreads();
+        }
+        const double t = sh[0];
+        __syncthreads();
+        return t;
+    };
+    double s = 0.0;
+    for (int i = tid; i < n; i += 256) s = __dadd_rn(s, (double)xr[i]);
+    const double mean = block_sum(s) / (double)n;
+    double s2 = 0.0;
+    for (int i = tid; i < n; i += 256) {
+        const double v = __dsub_rn((double)xr[i], mean);
+        s2 = __dadd_rn(s2, __dmul_rn(v, v));
+    }
+    const double eps = (double)1e-5f;
+    const float scale = (float)(1.0 / sqrt(__dadd_rn(block_sum(s2) / (double)n, eps)));
+    for (int i = tid; i < n; i += 256) {
+        const float v = (float)__dsub_rn((double)xr[i], mean);
+        yr[i] = __fadd_rn(__fmul_rn(w[i], __fmul_rn(v, scale)), b[i]);
+    }
+}
+
 // y[r][i] = a[r][i] + bias[i]   (ggml_add with a repeated bias; float addition commutes)
 __global__ void k_add_bias(float *__restrict__ a, const float *__restrict__ bias, long total, int n)
 {
@@ -292,6 +329,7 @@ int b200neox_eval(b200neox *m, const int *tokens, int N, int n_past, int n_threa
         return nfail(B200Q4_EINVAL, "neox_eval: bad argument");
     const int E = m->n_embd, H = m->n_head, d = E / H, P = n_past + N, nth = n_threads_emulated;
     cudaStream_t st = m->st;
+    const bool exact = b200q4_exact_enabled() != 0;                                          // exact mode covers the graph ops too
     auto W = [&](const std::string &name) { auto it = m->index.find(name); return it == m->index.end() ? nullptr : b200q4_model_weight(m->file, it->second); };
     auto F = [&](const std::string &name) { auto it = m->f32.find(name); return it == m->f32.end() ? nullptr : it->second; };
     auto mm = [&](const std::string &name, const float *x, int rows_in, float *y) -> int {   // ggml_mul_mat on a Q4 weight
@@ -309,7 +347,8 @@ int b200neox_eval(b200neox *m, const int *tokens, int N, int n_past, int n_threa
     auto ln = [&](const float *x, const std::string &name, float *y) -> int {
         const float *w = F(name + ".weight"), *b = F(name + ".bias");
         if (!w || !b) return nfail(B200Q4_EINVAL, "neox_eval: missing tensor " + name);
-        k_layernorm<<<nblk(N, 32), 32, 0, st>>>(x, N, E, w, b, y);
+        if (exact) k_layernorm<<<nblk(N, 32), 32, 0, st>>>(x, N, E, w, b, y);       // the reference's own summation order
+        else       k_layernorm_fast<<<N, 256, 0, st>>>(x, E, w, b, y);
         return 0;
     };
     NCK(cudaMemcpyAsync(m->ids, tokens, (size_t)N * 4, cudaMemcpyHostToDevice, st));

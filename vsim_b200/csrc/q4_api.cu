@@ -1132,6 +1132,8 @@ int b200q4_set_exact(int on)
     return old;
 }
 
+int b200q4_exact_enabled(void) { return g.exact ? 1 : 0; }
+
 int b200q4_sync(void *stream)
 {
     std::lock_guard<std::recursive_mutex> lk(g.mu);

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "b200q4_weight_cols", "b200q4_weight_type", "b200q4_weight_device_bytes", "b200q4_weight_download",
     "b200q4_mul_mat", "b200q4_mul_mat_wdata", "b200q4_quantize_rows", "b200q4_weight_upload_transposed",
     "b200q4_mul_mat_transposed", "b200q4_mul_mat_dev", "b200q4_quantize_rows_dev", "b200q4_sync",
-    "b200q4_mul_mat_dev_allgather", "b200q4_wait_flags", "b200q4_set_exact", "b200q4_quantize_weights", "b200q4_hint_next_weight",
+    "b200q4_mul_mat_dev_allgather", "b200q4_wait_flags", "b200q4_set_exact", "b200q4_exact_enabled", "b200q4_quantize_weights", "b200q4_hint_next_weight",
     "b200q4_model_load", "b200q4_model_header", "b200q4_model_tensor_count", "b200q4_model_tensor_info",
     "b200q4_model_weight", "b200q4_model_tensor_data", "b200q4_model_free",
     "b200neox_load", "b200neox_n_vocab", "b200neox_eval", "b200neox_free", "b200neox_last_error",
@@ -82,6 +82,7 @@ def load_library(build: bool = True) -> C.CDLL:
         "b200q4_quantize_rows_dev": (i, [i, vp, i, i, sz, vp, vp]),
         "b200q4_sync": (i, [vp]),
         "b200q4_set_exact": (i, [i]),
+        "b200q4_exact_enabled": (i, []),
         "b200q4_hint_next_weight": (i, [vp, i]),
         "b200q4_model_load": (vp, [C.c_char_p, i, i, i]),
         "b200q4_model_header": (i, [vp, i]),
