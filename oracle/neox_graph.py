@@ -129,12 +129,17 @@ class NeoxOracle:
                 kqv = part if kqv is None else (kqv + part).astype(_F)
             merged = np.ascontiguousarray(kqv.transpose(1, 0, 2).reshape(N, E))                    # permute(0,2,1,3) + cpy
             att = f.t[p + "attention.dense.bias"] + self._mm(p + "attention.dense.weight", merged)
-            assert f.par_res == 1
-            ff = self._ln(x, p + "post_attention_layernorm")
+            if f.par_res == 0:                                                                     # vsim.cpp:636-665
+                ff = self._ln((att + x).astype(_F), p + "post_attention_layernorm")                # inpFF = norm(cur + inpL)
+            else:                                                                                  # vsim.cpp:666-696
+                ff = self._ln(x, p + "post_attention_layernorm")
             ff = f.t[p + "mlp.dense_h_to_4h.bias"] + self._mm(p + "mlp.dense_h_to_4h.weight", ff)
             ff = self._gelu(ff)
             ff = f.t[p + "mlp.dense_4h_to_h.bias"] + self._mm(p + "mlp.dense_4h_to_h.weight", ff)
-            ff = (att + ff).astype(_F)
-            x = (x + ff).astype(_F)
+            if f.par_res == 0:
+                x = (ff + x).astype(_F)                                                            # inpL = inpFF + inpL  (attention output only feeds the MLP)
+            else:
+                ff = (att + ff).astype(_F)
+                x = (x + ff).astype(_F)
         x = self._ln(x, "gpt_neox.final_layer_norm")
         return self._mm("embed_out.weight", x)[N - 1]                                              # logits of the last token

@@ -13,7 +13,7 @@ import numpy as np
 from oracle import Oracle, Q4_0, Q4_1
 
 
-def write_neox(path: Path, qtype: int, n_vocab=256, n_embd=256, n_head=4, n_layer=2, n_rot=32, seed=0) -> None:
+def write_neox(path: Path, qtype: int, n_vocab=256, n_embd=256, n_head=4, n_layer=2, n_rot=32, seed=0, par_res=1) -> None:
     orc = Oracle()
     rng = np.random.default_rng(seed)
     ftype = 2 if qtype == Q4_0 else 3
@@ -30,7 +30,7 @@ def write_neox(path: Path, qtype: int, n_vocab=256, n_embd=256, n_head=4, n_laye
         return struct.pack("<iii", 1, len(nm), 0) + struct.pack("<i", n) + nm + v.tobytes()
 
     out = [struct.pack("<i", 0x67676d6c),
-           struct.pack("<iiiiiii", n_vocab, n_embd, n_head, n_layer, n_rot, 1, ftype)]
+           struct.pack("<iiiiiii", n_vocab, n_embd, n_head, n_layer, n_rot, par_res, ftype)]
     for i in range(n_vocab):
         tok = f"t{i}".encode()
         out.append(struct.pack("<I", len(tok)) + tok)
