@@ -10,7 +10,14 @@
  * (the per-thread partial sums of V^T x softmax, ggml.c:4463-4481): n_threads_emulated selects which --threads value
  * of the reference to reproduce.
  *
- * Model files: the reference's GPT-NeoX format with Q4_0 or Q4_1 weights (vsim.cpp:108-458), use_parallel_residual = 1.
+ * Decode steps (N = 1, exact mode off) are ONE persistent kernel launch: b200neox_load compiles the token's graph --
+ * every mul_mat, both layer-norms, gelu, rope + KV store + attention of every layer, the residual stream -- into a
+ * device-resident work-list for q4_prog_kernel (vsim_b200/csrc/q4_prog.cuh); the weights stream through shared memory
+ * without a kernel boundary between dependent mul_mats.  Prompts (N > 1) and exact mode run one kernel per op.
+ *
+ * Model files: the reference's GPT-NeoX format with Q4_0 or Q4_1 weights (vsim.cpp:108-458), use_parallel_residual = 0
+ * (vsim.cpp:636-665) or 1 (vsim.cpp:666-696).  Every tensor's shape is checked against the hyper-parameters at load
+ * ("has wrong shape in model file", vsim.cpp:375-448).  All device work is ordered on the library's own stream.
  * Plain C ABI; every function returns B200Q4_OK (0) / a negative B200Q4_E* code or NULL and records a message for
  * b200neox_last_error().  Needs b200q4_init() first.  No CPU fallback.
  */
@@ -28,6 +35,8 @@ b200neox *b200neox_load(const char *path, int n_ctx, int max_batch);
 int  b200neox_n_vocab(const b200neox *m);
 /* gptneox_eval(model, n_threads, n_past, tokens[N]) -> logits of the last token (host, n_vocab floats) */
 int  b200neox_eval(b200neox *m, const int *tokens, int N, int n_past, int n_threads_emulated, float *logits_out);
+/* 1 when decode steps run as one persistent launch, 0 when they fall back to one kernel per op (b200neox_last_error says why) */
+int  b200neox_decode_is_program(const b200neox *m);
 void b200neox_free(b200neox *m);
 const char *b200neox_last_error(void);
 

@@ -34,7 +34,12 @@
  * into fprintf(stderr) + exit(1) exactly like the reference.
  *
  * Threading: calls are serialised internally (one device context per process,
- * one stream); the ggml hook may be entered from any pool thread.
+ * one stream); the ggml hook may be entered from any pool thread.  The
+ * device-resident entry points (*_dev, chains) enqueue on the stream they are
+ * given but share ONE set of device scratch buffers: work enqueued through them
+ * must be on a single stream at a time (or the caller orders the streams with
+ * events) -- b200neox_eval and the host-buffer entry points use the library's
+ * own stream.
  */
 #ifndef B200Q4_H
 #define B200Q4_H
@@ -121,6 +126,24 @@ int b200q4_mul_mat_dev(const b200q4_weight *w, const float *d_x, int M, size_t x
                        float *d_y, size_t y_stride, void *stream);
 int b200q4_quantize_rows_dev(int type, const float *d_x, int M, int K, size_t x_stride,
                              void *d_out, void *stream);
+
+/* ---- chains: several dependent decode (M = 1) mul_mats in ONE persistent launch ----------
+ * Batch-1 decode is a chain of dependent mul_mats (ggml_graph_compute runs them node by
+ * node, ggml.c:8543-8662); launched one kernel each, every link pays a kernel boundary
+ * that is longer than the weight stream of a small tensor.  A chain is a device-resident
+ * work-list: op i computes d_y[i][0..N_i) = W_i . quantize_row(d_x[i][0..K_i)) exactly like
+ * b200q4_mul_mat_dev with M = 1 (same kernels' arithmetic, bit-identical Y), and may start
+ * only when op deps[i] (an index < i, or -1) is complete -- normally the op that wrote its
+ * d_x.  One launch of q4_prog_kernel walks the list: the thread blocks stay resident, the
+ * weights of op i+1 are already streaming into shared memory while op i's outputs are
+ * being published.  All weights of a chain must have the same quant type; d_x / d_y are
+ * 16-byte aligned device pointers that stay valid for the life of the chain.           */
+typedef struct b200q4_chain b200q4_chain;
+b200q4_chain *b200q4_chain_create(int n, const b200q4_weight *const *ws, const float *const *d_x,
+                                  float *const *d_y, const int *deps);
+int  b200q4_chain_run(b200q4_chain *c, void *stream);       /* asynchronous on `stream` */
+int  b200q4_chain_info(const b200q4_chain *c, int *n_ops, int *stages, size_t *smem_bytes);
+void b200q4_chain_free(b200q4_chain *c);
 
 /* ---- multi-GPU: row shards with the all-gather fused into the kernel ---------
  * The reference splits a mul_mat by output rows across its threads

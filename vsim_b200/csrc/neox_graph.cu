@@ -8,10 +8,16 @@
 // -- the order of every accumulation, double where ggml.c uses ggml_float, no FMA contraction, gelu and exp through
 // fp16 tables built on the host with the same libm calls as ggml_init (ggml.c:1240-1255), rope angles from the host's
 // pow/cos/sin -- so that with exact-mode mul_mats the logits equal the reference program's bit for bit
-// (tests/test_gpu_neox_graph.py checks exactly that).  Making them fast (fused, parallel reductions where the order allows) is the
-// next step; at batch 1 they are microseconds next to the weight stream.
+// (tests/test_gpu_neox_graph.py checks exactly that).
+//
+// Decode steps (one token, exact mode off) do not use these kernels at all: b200neox_load compiles the whole token --
+// every mul_mat, layer-norm, gelu, the attention of every layer, the residual stream -- into ONE device-resident
+// work-list executed by one persistent launch of q4_prog_kernel (q4_prog.cuh).  Prompts (N > 1) and exact mode run
+// the per-op kernels below.
 #include "../../include/b200neox.h"
 #include "../../include/b200q4.h"
+#define Q4_PROG_TYPES_ONLY                               // the work-list structures, not the kernel
+#include "q4_prog_host.h"
 
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -216,12 +222,20 @@ inline unsigned nblk(long total, int threads = 256) { return (unsigned)((total +
 
 }  // namespace
 
+struct NeoxLayer {
+    b200q4_weight *wq, *wk, *wv, *wo, *w1, *w2;
+    const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *bq, *bk, *bv, *bo, *b1, *b2;
+};
+
 struct b200neox {
     b200q4_model *file = nullptr;
     int n_vocab = 0, n_embd = 0, n_head = 0, n_layer = 0, n_rot = 0, par_res = 0, ftype = 0, n_ctx = 0;
-    std::map<std::string, int> index;                    // tensor name -> index in the file
-    std::map<std::string, float *> f32;                  // 1-D tensors, device copies
+    std::vector<NeoxLayer> layers;                       // every tensor resolved once, at load
+    b200q4_weight *w_head = nullptr;
+    const float *lnf_w = nullptr, *lnf_b = nullptr;
+    std::vector<float *> f32;                            // device copies of the 1-D tensors (owned)
     unsigned char *d_wte = nullptr;                      // embedding matrix in the reference's row format (get_rows dequantizes it)
+    int wte_type = 0;
     float *mem_k = nullptr, *mem_v = nullptr;            // [n_layer][n_ctx][n_embd]   (vsim.cpp:318-330)
     unsigned short *t_gelu = nullptr, *t_exp = nullptr;  // ggml_init's fp16 tables
     double2 *rope_cs = nullptr;                          // [n_ctx][n_rot/2] {cos, sin}
@@ -229,8 +243,117 @@ struct b200neox {
           *kq = nullptr, *merged = nullptr, *logits = nullptr;
     int *ids = nullptr;
     int max_n = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;                           // the library's stream: all device work of this process is ordered on it
+    // decode program (one persistent launch per token)
+    b200q4::Prog prog;
+    bool have_prog = false;
+    std::string prog_why;                                // why no program was built
+    std::vector<float *> prog_bufs;                      // its scratch vectors (owned)
 };
+
+namespace {
+
+using namespace b200q4;
+
+// Compiles one decode step (N = 1) into a work-list for q4_prog_kernel.  Graph: gptneox_eval, vsim.cpp:518-718.
+int build_decode_program(b200neox *m)
+{
+    const int E = m->n_embd, H = m->n_head, d = E / H, L = m->n_layer, V = m->n_vocab;
+    if (d > PG_ATT_MAX_D) { m->prog_why = "head size above 512"; return 1; }
+    if (m->wte_type != m->ftype - 2) { m->prog_why = "embedding matrix of another quant type"; return 1; }
+    ProgBuild b;
+    auto dev = [&](size_t floats) {
+        float *p = nullptr;
+        if (cudaMalloc(&p, (floats + 4) * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return (float *)nullptr; }
+        cudaMemset(p, 0, (floats + 4) * sizeof(float));
+        m->prog_bufs.push_back(p);
+        return p;
+    };
+    // the output of a mul_mat as a list of sources: the finished vector, or its K-slice partials plus the bias
+    struct Out { std::vector<PgSrc> src; int op; };
+    bool oom = false;
+    auto matvec = [&](b200q4_weight *w, const float *bias, int dep, int in_mode, int res, const std::vector<PgSrc> &src,
+                      const float *lw, const float *lb, float *y_fixed) {
+        Out o;
+        const PgGeo g = pg_geometry(w);
+        const int N = b200q4_weight_rows(w);
+        if (g.PP == 1) {
+            float *y = y_fixed ? y_fixed : dev((size_t)N);
+            if (!y) { oom = true; o.op = -1; return o; }
+            o.op = b.add_matvec(w, dep, in_mode, res, src.data(), (int)src.size(), lw, lb, m->t_gelu, y, bias, 0);
+            o.src.push_back(pg_src_f32(y));
+        } else {
+            const int stride = (N + 3) & ~3;
+            float *part = dev((size_t)g.PP * stride);
+            if (!part) { oom = true; o.op = -1; return o; }
+            o.op = b.add_matvec(w, dep, in_mode, res, src.data(), (int)src.size(), lw, lb, m->t_gelu, part, nullptr, stride);
+            o.src.push_back(pg_src_f32(part, g.PP, stride));
+            if (bias) o.src.push_back(pg_src_f32(bias));
+        }
+        return o;
+    };
+    float *q = dev(E), *k = dev(E), *v = dev(E), *att = dev(E);
+    float *part = dev((size_t)H * ((m->n_ctx + PG_ATT_CHUNK - 1) / PG_ATT_CHUNK) * (d + 2));
+    if (!q || !k || !v || !att || !part) { m->prog_why = "device allocation failed"; return 1; }
+    const float scale = (float)(1.0 / sqrt((double)((float)E / (float)H)));                  // vsim.cpp:590
+    // what the next layer-norm op has to add to the residual stream first
+    std::vector<PgSrc> pending;
+    int pending_res = PG_RES_SET, last = -1;
+    PgSrc emb{m->d_wte, nullptr, m->wte_type, E, 1.0f, PG_SRC_Q4ROW};                         // ggml_get_rows(wte, embd), vsim.cpp:516
+    pending.push_back(emb);
+    const std::vector<PgSrc> none;
+    bool bad = false;
+    auto chk = [&](const Out &o) { if (o.op < 0) bad = true; return o; };
+    for (int l = 0; l < L && !bad; l++) {
+        const NeoxLayer &ly = m->layers[(size_t)l];
+        float *mk = m->mem_k + (size_t)l * m->n_ctx * E, *mv = m->mem_v + (size_t)l * m->n_ctx * E;
+        if ((int)pending.size() > PG_MAX_SRC) { m->prog_why = "too many residual sources"; return 1; }
+        const Out oq = chk(matvec(ly.wq, ly.bq, last, PG_IN_LN, pending_res, pending, ly.ln1_w, ly.ln1_b, q));
+        const Out ok = chk(matvec(ly.wk, ly.bk, -1, PG_IN_LN, PG_RES_KEEP, none, ly.ln1_w, ly.ln1_b, k));
+        const Out ov = chk(matvec(ly.wv, ly.bv, -1, PG_IN_LN, PG_RES_KEEP, none, ly.ln1_w, ly.ln1_b, v));
+        if (bad) break;
+        if (oq.src.size() != 1 || ok.src.size() != 1 || ov.src.size() != 1) { m->prog_why = "n_embd above 8192 (K-sliced Q/K/V)"; return 1; }
+        pending.clear();
+        if (m->par_res == 1) {
+            // vsim.cpp:666-696: the MLP reads the layer input, so its first matrix needs nothing from the attention
+            const Out o1 = chk(matvec(ly.w1, ly.b1, -1, PG_IN_LN, PG_RES_KEEP, none, ly.ln2_w, ly.ln2_b, nullptr));
+            if (bad) break;
+            const int oa = b.add_attn(ov.op, q, k, v, mk, mv, att, part, m->rope_cs, H, d, m->n_rot, m->n_ctx, scale);
+            const Out o2 = chk(matvec(ly.w2, ly.b2, o1.op, PG_IN_GELU, PG_RES_KEEP, o1.src, nullptr, nullptr, nullptr));
+            const std::vector<PgSrc> a_in{pg_src_f32(att)};
+            const Out oo = chk(matvec(ly.wo, ly.bo, oa, PG_IN_PLAIN, PG_RES_KEEP, a_in, nullptr, nullptr, nullptr));
+            if (bad || oa < 0) { bad = true; break; }
+            pending = oo.src;                                                                // inpL = inpL + (cur + inpFF)
+            pending.insert(pending.end(), o2.src.begin(), o2.src.end());
+            last = oo.op;
+        } else {
+            // vsim.cpp:636-665: inpFF = norm(cur + inpL) -> MLP; inpL = inpFF + inpL (the attention output only feeds the MLP)
+            const int oa = b.add_attn(ov.op, q, k, v, mk, mv, att, part, m->rope_cs, H, d, m->n_rot, m->n_ctx, scale);
+            const std::vector<PgSrc> a_in{pg_src_f32(att)};
+            const Out oo = chk(matvec(ly.wo, ly.bo, oa, PG_IN_PLAIN, PG_RES_KEEP, a_in, nullptr, nullptr, nullptr));
+            if (bad || oa < 0) { bad = true; break; }
+            const Out o1 = chk(matvec(ly.w1, ly.b1, oo.op, PG_IN_LN, PG_RES_TEMP, oo.src, ly.ln2_w, ly.ln2_b, nullptr));
+            if (bad) break;
+            const Out o2 = chk(matvec(ly.w2, ly.b2, o1.op, PG_IN_GELU, PG_RES_KEEP, o1.src, nullptr, nullptr, nullptr));
+            if (bad) break;
+            pending = o2.src;
+            last = o2.op;
+        }
+        pending_res = PG_RES_ADD;
+    }
+    if (!bad) {
+        if ((int)pending.size() > PG_MAX_SRC) { m->prog_why = "too many residual sources"; return 1; }
+        const PgGeo g = pg_geometry(m->w_head);
+        Out oh = chk(matvec(m->w_head, nullptr, last, PG_IN_LN, pending_res, pending, m->lnf_w, m->lnf_b, g.PP == 1 ? m->logits : nullptr));
+        if (!bad && g.PP > 1 && b.add_sum(oh.op, oh.src[0], m->logits, V) < 0) bad = true;
+    }
+    if (bad) { m->prog_why = oom ? "device allocation failed" : std::string("program builder: ") + b200q4_last_error(); return 1; }
+    if (prog_finalize(b, m->prog)) { m->prog_why = std::string("program: ") + b200q4_last_error(); return 1; }
+    m->have_prog = true;
+    return 0;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -240,11 +363,12 @@ void b200neox_free(b200neox *m)
 {
     if (!m) return;
     if (m->st) cudaStreamSynchronize(m->st);
-    for (auto &kv : m->f32) cudaFree(kv.second);
+    if (m->have_prog) b200q4::prog_free(m->prog);
+    for (float *p : m->prog_bufs) cudaFree(p);
+    for (float *p : m->f32) cudaFree(p);
     float *bufs[] = {m->mem_k, m->mem_v, m->x, m->cur, m->q, m->k, m->v, m->att, m->ff, m->ff2, m->kq, m->merged, m->logits};
     for (float *b : bufs) cudaFree(b);
     cudaFree(m->d_wte); cudaFree(m->t_gelu); cudaFree(m->t_exp); cudaFree(m->rope_cs); cudaFree(m->ids);
-    if (m->st) cudaStreamDestroy(m->st);
     if (m->file) b200q4_model_free(m->file);
     delete m;
 }
@@ -260,29 +384,73 @@ b200neox *b200neox_load(const char *path, int n_ctx, int max_batch)
     for (int i = 0; i < 7; i++) *hp[i] = b200q4_model_header(f, i);
     m->n_ctx = n_ctx; m->max_n = max_batch;
     auto bail = [&](const std::string &why) { nfail(B200Q4_EINVAL, "neox_load: " + why); b200neox_free(m); return (b200neox *)nullptr; };
-    if (m->par_res != 1) return bail("only use_parallel_residual == 1 graphs are built (what the reference's models use)");
-    if (m->n_embd % m->n_head || m->n_rot % 2 || m->n_rot > m->n_embd / m->n_head) return bail("bad hyper-parameters");
-    if (cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
+    // hyper-parameters (the reference trusts the file; a bad one must not reach a kernel)
+    if (m->n_vocab < 1 || m->n_embd < 1 || m->n_head < 1 || m->n_layer < 0 || m->n_rot < 0) return bail("bad hyper-parameters");
+    if (m->n_embd % 32 || m->n_embd % m->n_head || m->n_rot % 2 || m->n_rot > m->n_embd / m->n_head) return bail("bad hyper-parameters");
+    if (m->par_res != 0 && m->par_res != 1) return bail("use_parallel_residual must be 0 or 1 (vsim.cpp:697-700)");
+    if (m->ftype != 2 && m->ftype != 3) return bail("only q4_0 / q4_1 model files are built (ftype 2 / 3)");
+    m->st = b200q4::dev_info().stream;
+    if (!m->st) return bail("b200q4_init() has not succeeded");
+    const int E = m->n_embd, V = m->n_vocab;
+    // every tensor by name, with the shape the hyper-parameters imply ("has wrong shape in model file", vsim.cpp:375-448)
+    std::map<std::string, int> index;
     const int nt = b200q4_model_tensor_count(f);
     for (int i = 0; i < nt; i++) {
-        const char *name; int nd, ft, ne0, ne1; size_t off, nb;
-        b200q4_model_tensor_info(f, i, &name, &nd, &ft, &ne0, &ne1, &off, &nb);
-        m->index[name] = i;
-        if (nd == 1) {
-            if (ft != 0) return bail(std::string("1-D tensor '") + name + "' is not f32");
-            float *d = nullptr;
-            if (cudaMalloc(&d, nb) != cudaSuccess || cudaMemcpy(d, b200q4_model_tensor_data(f, i), nb, cudaMemcpyHostToDevice) != cudaSuccess)
-                return bail("device copy of a 1-D tensor failed");
-            m->f32[name] = d;
-        } else if (ft < 2) return bail(std::string("2-D tensor '") + name + "' is not Q4 (f16/f32 model files are not built)");
+        const char *name;
+        b200q4_model_tensor_info(f, i, &name, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        index[name] = i;
     }
+    std::string err;
+    auto vec = [&](const std::string &name, int n) -> const float * {          // 1-D f32 tensor of n elements -> device copy
+        auto it = index.find(name);
+        if (it == index.end()) { if (err.empty()) err = "missing tensor " + name; return nullptr; }
+        const char *nm; int nd, ft, ne0, ne1; size_t off, nb;
+        b200q4_model_tensor_info(f, it->second, &nm, &nd, &ft, &ne0, &ne1, &off, &nb);
+        if (nd != 1 || ft != 0 || ne0 != n) { if (err.empty()) err = "tensor '" + name + "' has wrong shape in model file"; return nullptr; }
+        float *d = nullptr;
+        if (cudaMalloc(&d, nb) != cudaSuccess || cudaMemcpy(d, b200q4_model_tensor_data(f, it->second), nb, cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaGetLastError(); cudaFree(d);
+            if (err.empty()) err = "device copy of a 1-D tensor failed";
+            return nullptr;
+        }
+        m->f32.push_back(d);
+        return d;
+    };
+    auto mat = [&](const std::string &name, int K, int N, int *tensor_index = nullptr) -> b200q4_weight * {   // 2-D Q4 tensor [N rows][K]
+        auto it = index.find(name);
+        if (it == index.end()) { if (err.empty()) err = "missing tensor " + name; return nullptr; }
+        const char *nm; int nd, ft, ne0, ne1; size_t off, nb;
+        b200q4_model_tensor_info(f, it->second, &nm, &nd, &ft, &ne0, &ne1, &off, &nb);
+        if (nd != 2 || ne0 != K || ne1 != N) { if (err.empty()) err = "tensor '" + name + "' has wrong shape in model file"; return nullptr; }
+        if (ft != m->ftype) { if (err.empty()) err = "tensor '" + name + "' is not of the file's quant type"; return nullptr; }
+        if (tensor_index) *tensor_index = it->second;
+        return b200q4_model_weight(f, it->second);
+    };
+    int wte_index = -1;
+    mat("gpt_neox.embed_in.weight", E, V, &wte_index);
+    m->lnf_w = vec("gpt_neox.final_layer_norm.weight", E);
+    m->lnf_b = vec("gpt_neox.final_layer_norm.bias", E);
+    m->w_head = mat("embed_out.weight", E, V);
+    m->layers.resize((size_t)m->n_layer);
+    for (int l = 0; l < m->n_layer && err.empty(); l++) {
+        const std::string p = "gpt_neox.layers." + std::to_string(l) + ".";
+        NeoxLayer &ly = m->layers[(size_t)l];
+        ly.ln1_w = vec(p + "input_layernorm.weight", E);           ly.ln1_b = vec(p + "input_layernorm.bias", E);
+        ly.ln2_w = vec(p + "post_attention_layernorm.weight", E);  ly.ln2_b = vec(p + "post_attention_layernorm.bias", E);
+        ly.wq = mat(p + "attention.query.weight", E, E);           ly.bq = vec(p + "attention.query.bias", E);
+        ly.wk = mat(p + "attention.key.weight", E, E);             ly.bk = vec(p + "attention.key.bias", E);
+        ly.wv = mat(p + "attention.value.weight", E, E);           ly.bv = vec(p + "attention.value.bias", E);
+        ly.wo = mat(p + "attention.dense.weight", E, E);           ly.bo = vec(p + "attention.dense.bias", E);
+        ly.w1 = mat(p + "mlp.dense_h_to_4h.weight", E, 4 * E);     ly.b1 = vec(p + "mlp.dense_h_to_4h.bias", 4 * E);
+        ly.w2 = mat(p + "mlp.dense_4h_to_h.weight", 4 * E, E);     ly.b2 = vec(p + "mlp.dense_4h_to_h.bias", E);
+    }
+    if (!err.empty()) return bail(err);
     {   // the embedding matrix is read by get_rows in the reference's row format
-        auto it = m->index.find("gpt_neox.embed_in.weight");
-        if (it == m->index.end()) return bail("no gpt_neox.embed_in.weight");
         const char *name; int nd, ft, ne0, ne1; size_t off, nb;
-        b200q4_model_tensor_info(f, it->second, &name, &nd, &ft, &ne0, &ne1, &off, &nb);
+        b200q4_model_tensor_info(f, wte_index, &name, &nd, &ft, &ne0, &ne1, &off, &nb);
+        m->wte_type = ft - 2;
         if (cudaMalloc(&m->d_wte, nb) != cudaSuccess ||
-            cudaMemcpy(m->d_wte, b200q4_model_tensor_data(f, it->second), nb, cudaMemcpyHostToDevice) != cudaSuccess)
+            cudaMemcpy(m->d_wte, b200q4_model_tensor_data(f, wte_index), nb, cudaMemcpyHostToDevice) != cudaSuccess)
             return bail("device copy of the embedding matrix failed");
     }
     // ggml_init's tables (ggml.c:1240-1255), with this host's libm like the reference build
@@ -302,66 +470,80 @@ b200neox *b200neox_load(const char *path, int n_ctx, int max_batch)
             const double theta = pow(10000.0, 2 * ((double)-i0) / m->n_rot);             // ggml.c:6126
             cs[(size_t)p * half + i0] = make_double2(cos(p * theta), sin(p * theta));
         }
-    const size_t E = (size_t)m->n_embd, Nmax = (size_t)max_batch, kv = (size_t)m->n_layer * n_ctx * E * 4;
+    const size_t Es = (size_t)E, Nmax = (size_t)max_batch, kv = (size_t)m->n_layer * n_ctx * Es * 4 + 16;
     bool ok = cudaMalloc(&m->t_gelu, 1 << 17) == cudaSuccess && cudaMalloc(&m->t_exp, 1 << 17) == cudaSuccess &&
               cudaMalloc(&m->rope_cs, cs.size() * sizeof(double2) + 16) == cudaSuccess &&
               cudaMalloc(&m->mem_k, kv) == cudaSuccess && cudaMalloc(&m->mem_v, kv) == cudaSuccess &&
-              cudaMalloc(&m->x, Nmax * E * 4) == cudaSuccess && cudaMalloc(&m->cur, Nmax * E * 4) == cudaSuccess &&
-              cudaMalloc(&m->q, Nmax * E * 4) == cudaSuccess && cudaMalloc(&m->k, Nmax * E * 4) == cudaSuccess &&
-              cudaMalloc(&m->v, Nmax * E * 4) == cudaSuccess && cudaMalloc(&m->att, Nmax * E * 4) == cudaSuccess &&
-              cudaMalloc(&m->merged, Nmax * E * 4) == cudaSuccess && cudaMalloc(&m->ff, Nmax * 4 * E * 4) == cudaSuccess &&
-              cudaMalloc(&m->ff2, Nmax * E * 4) == cudaSuccess &&
+              cudaMalloc(&m->x, Nmax * Es * 4) == cudaSuccess && cudaMalloc(&m->cur, Nmax * Es * 4) == cudaSuccess &&
+              cudaMalloc(&m->q, Nmax * Es * 4) == cudaSuccess && cudaMalloc(&m->k, Nmax * Es * 4) == cudaSuccess &&
+              cudaMalloc(&m->v, Nmax * Es * 4) == cudaSuccess && cudaMalloc(&m->att, Nmax * Es * 4) == cudaSuccess &&
+              cudaMalloc(&m->merged, Nmax * Es * 4) == cudaSuccess && cudaMalloc(&m->ff, Nmax * 4 * Es * 4) == cudaSuccess &&
+              cudaMalloc(&m->ff2, Nmax * Es * 4) == cudaSuccess &&
               cudaMalloc(&m->kq, (size_t)m->n_head * Nmax * n_ctx * 4) == cudaSuccess &&
-              cudaMalloc(&m->logits, Nmax * (size_t)m->n_vocab * 4) == cudaSuccess && cudaMalloc(&m->ids, Nmax * 4) == cudaSuccess;
+              cudaMalloc(&m->logits, Nmax * (size_t)m->n_vocab * 4 + 16) == cudaSuccess && cudaMalloc(&m->ids, Nmax * 4) == cudaSuccess;
     ok = ok && cudaMemset(m->mem_k, 0, kv) == cudaSuccess && cudaMemset(m->mem_v, 0, kv) == cudaSuccess &&
          cudaMemcpy(m->t_gelu, tg.data(), 1 << 17, cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(m->t_exp, te.data(), 1 << 17, cudaMemcpyHostToDevice) == cudaSuccess &&
          (cs.empty() || cudaMemcpy(m->rope_cs, cs.data(), cs.size() * sizeof(double2), cudaMemcpyHostToDevice) == cudaSuccess);
     if (!ok) return bail(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+    const char *pe = getenv("B200NEOX_PROGRAM");
+    if (pe && atoi(pe) == 0) m->prog_why = "disabled (B200NEOX_PROGRAM=0)";
+    else build_decode_program(m);                        // failure is not fatal: the per-op kernels serve decode steps too
     return m;
 }
 
 int b200neox_n_vocab(const b200neox *m) { return m ? m->n_vocab : B200Q4_EINVAL; }
 
+/* 1 when decode steps run as one persistent launch; 0 (and why, through b200neox_last_error) when not */
+int b200neox_decode_is_program(const b200neox *m)
+{
+    if (!m) return B200Q4_EINVAL;
+    if (!m->have_prog) g_nerr = m->prog_why;
+    return m->have_prog ? 1 : 0;
+}
+
 int b200neox_eval(b200neox *m, const int *tokens, int N, int n_past, int n_threads_emulated, float *logits_out)
 {
     if (!m || !tokens || !logits_out || N < 1 || N > m->max_n || n_past < 0 || n_past + N > m->n_ctx || n_threads_emulated < 1)
         return nfail(B200Q4_EINVAL, "neox_eval: bad argument");
+    for (int i = 0; i < N; i++)
+        if (tokens[i] < 0 || tokens[i] >= m->n_vocab) return nfail(B200Q4_EINVAL, "neox_eval: token id out of range");
     const int E = m->n_embd, H = m->n_head, d = E / H, P = n_past + N, nth = n_threads_emulated;
     cudaStream_t st = m->st;
     const bool exact = b200q4_exact_enabled() != 0;                                          // exact mode covers the graph ops too
-    auto W = [&](const std::string &name) { auto it = m->index.find(name); return it == m->index.end() ? nullptr : b200q4_model_weight(m->file, it->second); };
-    auto F = [&](const std::string &name) { auto it = m->f32.find(name); return it == m->f32.end() ? nullptr : it->second; };
-    auto mm = [&](const std::string &name, const float *x, int rows_in, float *y) -> int {   // ggml_mul_mat on a Q4 weight
-        b200q4_weight *w = W(name);
-        if (!w) return nfail(B200Q4_EINVAL, "neox_eval: missing tensor " + name);
-        if (int rc = b200q4_mul_mat_dev(w, x, rows_in, 0, y, 0, st)) return nfail(rc, std::string("neox_eval: ") + b200q4_last_error());
+    if (N == 1 && !exact && m->have_prog) {
+        // one token = one persistent launch: ids in, logits out
+        b200q4::ApiLock lk;
+        const int dyn[2] = {tokens[0], n_past};
+        NCK(cudaMemcpyAsync(m->prog.d_dyn, dyn, sizeof dyn, cudaMemcpyHostToDevice, st));
+        if (b200q4::prog_launch(m->prog, st)) return nfail(B200Q4_ECUDA, std::string("neox_eval: ") + b200q4_last_error());
+        NCK(cudaMemcpyAsync(logits_out, m->logits, (size_t)m->n_vocab * 4, cudaMemcpyDeviceToHost, st));
+        NCK(cudaStreamSynchronize(st));
+        return B200Q4_OK;
+    }
+    auto mm = [&](b200q4_weight *w, const float *x, float *y) -> int {                       // ggml_mul_mat on a Q4 weight
+        if (int rc = b200q4_mul_mat_dev(w, x, N, 0, y, 0, st)) return nfail(rc, std::string("neox_eval: ") + b200q4_last_error());
         return 0;
     };
-    auto bias = [&](float *a, const std::string &name, int n) -> int {
-        const float *b = F(name);
-        if (!b) return nfail(B200Q4_EINVAL, "neox_eval: missing tensor " + name);
-        k_add_bias<<<nblk((long)N * n), 256, 0, st>>>(a, b, (long)N * n, n);
-        return 0;
-    };
-    auto ln = [&](const float *x, const std::string &name, float *y) -> int {
-        const float *w = F(name + ".weight"), *b = F(name + ".bias");
-        if (!w || !b) return nfail(B200Q4_EINVAL, "neox_eval: missing tensor " + name);
-        if (exact) k_layernorm<<<nblk(N, 32), 32, 0, st>>>(x, N, E, w, b, y);       // the reference's own summation order
+    auto bias = [&](float *a, const float *b, int n) { k_add_bias<<<nblk((long)N * n), 256, 0, st>>>(a, b, (long)N * n, n); };
+    auto ln = [&](const float *x, const float *w, const float *b, float *y) {
+        if (exact) k_layernorm<<<nblk(N, 32), 32, 0, st>>>(x, N, E, w, b, y);               // the reference's own summation order
         else       k_layernorm_fast<<<N, 256, 0, st>>>(x, E, w, b, y);
-        return 0;
     };
     NCK(cudaMemcpyAsync(m->ids, tokens, (size_t)N * 4, cudaMemcpyHostToDevice, st));
-    k_get_rows_q4<<<nblk((long)N * E), 256, 0, st>>>(m->ftype - 2, m->d_wte, E, m->ids, N, m->x);
+    k_get_rows_q4<<<nblk((long)N * E), 256, 0, st>>>(m->wte_type, m->d_wte, E, m->ids, N, m->x);
     const float scale = (float)(1.0 / sqrt((double)((float)E / (float)H)));                 // vsim.cpp:590
     int rc;
     for (int l = 0; l < m->n_layer; l++) {
-        const std::string p = "gpt_neox.layers." + std::to_string(l) + ".";
+        const NeoxLayer &ly = m->layers[(size_t)l];
         float *mk = m->mem_k + (size_t)l * m->n_ctx * E, *mv = m->mem_v + (size_t)l * m->n_ctx * E;
-        if ((rc = ln(m->x, p + "input_layernorm", m->cur))) return rc;
-        if ((rc = mm(p + "attention.query.weight", m->cur, N, m->q)) || (rc = bias(m->q, p + "attention.query.bias", E))) return rc;
-        if ((rc = mm(p + "attention.key.weight", m->cur, N, m->k)) || (rc = bias(m->k, p + "attention.key.bias", E))) return rc;
-        if ((rc = mm(p + "attention.value.weight", m->cur, N, m->v)) || (rc = bias(m->v, p + "attention.value.bias", E))) return rc;
+        ln(m->x, ly.ln1_w, ly.ln1_b, m->cur);
+        if ((rc = mm(ly.wq, m->cur, m->q))) return rc;
+        bias(m->q, ly.bq, E);
+        if ((rc = mm(ly.wk, m->cur, m->k))) return rc;
+        bias(m->k, ly.bk, E);
+        if ((rc = mm(ly.wv, m->cur, m->v))) return rc;
+        bias(m->v, ly.bv, E);
         k_copy<<<nblk((long)N * E), 256, 0, st>>>(m->k, mk + (size_t)n_past * E, (long)N * E);          // cpy into the KV memory (:557-558)
         k_copy<<<nblk((long)N * E), 256, 0, st>>>(m->v, mv + (size_t)n_past * E, (long)N * E);
         k_rope<<<nblk((long)N * H * (m->n_rot / 2)), 256, 0, st>>>(m->q, d, H, N, n_past, m->n_rot, 0, m->rope_cs);
@@ -369,16 +551,29 @@ int b200neox_eval(b200neox *m, const int *tokens, int N, int n_past, int n_threa
         k_kq<<<nblk((long)H * N * P), 256, 0, st>>>(mk, m->q, H, N, P, d, n_past, scale, m->kq);
         k_soft_max<<<nblk((long)H * N, 32), 32, 0, st>>>(m->kq, H * N, P, m->t_exp);
         k_kqv<<<nblk((long)H * N * d), 256, 0, st>>>(mv, m->kq, H, N, P, d, nth, m->merged);
-        if ((rc = mm(p + "attention.dense.weight", m->merged, N, m->att)) || (rc = bias(m->att, p + "attention.dense.bias", E))) return rc;
-        if ((rc = ln(m->x, p + "post_attention_layernorm", m->cur))) return rc;
-        if ((rc = mm(p + "mlp.dense_h_to_4h.weight", m->cur, N, m->ff)) || (rc = bias(m->ff, p + "mlp.dense_h_to_4h.bias", 4 * E))) return rc;
+        if ((rc = mm(ly.wo, m->merged, m->att))) return rc;
+        bias(m->att, ly.bo, E);
+        if (m->par_res == 0) {
+            // vsim.cpp:636-665: inpFF = norm(cur + inpL) -> MLP;  inpL = inpFF + inpL
+            k_add<<<nblk((long)N * E), 256, 0, st>>>(m->att, m->x, m->att, (long)N * E);
+            ln(m->att, ly.ln2_w, ly.ln2_b, m->cur);
+        } else {
+            ln(m->x, ly.ln2_w, ly.ln2_b, m->cur);
+        }
+        if ((rc = mm(ly.w1, m->cur, m->ff))) return rc;
+        bias(m->ff, ly.b1, 4 * E);
         k_gelu<<<nblk((long)N * 4 * E), 256, 0, st>>>(m->ff, (long)N * 4 * E, m->t_gelu);
-        if ((rc = mm(p + "mlp.dense_4h_to_h.weight", m->ff, N, m->ff2)) || (rc = bias(m->ff2, p + "mlp.dense_4h_to_h.bias", E))) return rc;
-        k_add<<<nblk((long)N * E), 256, 0, st>>>(m->att, m->ff2, m->ff2, (long)N * E);                   // inpFF = cur + inpFF
-        k_add<<<nblk((long)N * E), 256, 0, st>>>(m->x, m->ff2, m->x, (long)N * E);                       // inpL = inpL + inpFF
+        if ((rc = mm(ly.w2, m->ff, m->ff2))) return rc;
+        bias(m->ff2, ly.b2, E);
+        if (m->par_res == 0) {
+            k_add<<<nblk((long)N * E), 256, 0, st>>>(m->ff2, m->x, m->x, (long)N * E);                   // inpL = inpFF + inpL
+        } else {
+            k_add<<<nblk((long)N * E), 256, 0, st>>>(m->att, m->ff2, m->ff2, (long)N * E);               // inpFF = cur + inpFF
+            k_add<<<nblk((long)N * E), 256, 0, st>>>(m->x, m->ff2, m->x, (long)N * E);                   // inpL = inpL + inpFF
+        }
     }
-    if ((rc = ln(m->x, "gpt_neox.final_layer_norm", m->cur))) return rc;
-    if ((rc = mm("embed_out.weight", m->cur, N, m->logits))) return rc;
+    ln(m->x, m->lnf_w, m->lnf_b, m->cur);
+    if ((rc = mm(m->w_head, m->cur, m->logits))) return rc;
     NCK(cudaGetLastError());
     NCK(cudaMemcpyAsync(logits_out, m->logits + (size_t)(N - 1) * m->n_vocab, (size_t)m->n_vocab * 4, cudaMemcpyDeviceToHost, st));
     NCK(cudaStreamSynchronize(st));

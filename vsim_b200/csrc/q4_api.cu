@@ -24,13 +24,7 @@ using b200q4::PIPE_TILE_SPLIT;
 
 using namespace b200q4;
 
-struct b200q4_weight {
-    int type, N, K, nb, C, n_tiles;
-    bool transposed;
-    uint8_t *d_wt;       // wtile (or raw reference rows when transposed)
-    size_t wt_bytes;
-    int *d_counters;     // one per 16-row tile
-};
+#include "q4_internal.h"
 
 namespace {
 
@@ -623,6 +617,23 @@ b200q4_weight *upload_impl(int type, const void *rows, int N, int K, size_t row_
 }
 
 } // namespace
+
+namespace b200q4 {
+DevInfo dev_info() { return DevInfo{g.device, g.sms, g.smem_optin, g.stream}; }
+int api_fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g.err = buf;
+    return code;
+}
+void api_count_launch(int n) { g.launches += (uint64_t)n; }
+void api_lock() { g.mu.lock(); }
+void api_unlock() { g.mu.unlock(); }
+} // namespace b200q4
 
 extern "C" {
 

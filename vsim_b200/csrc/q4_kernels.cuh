@@ -682,7 +682,7 @@ __device__ __forceinline__ void peer_signal(const PeerOut &po, int lane)
     if (lane == 0) peer_count_done(po);
 }
 // holds the stream until exchange *seq_ctr has landed from every rank (lane r watches rank r)
-__global__ void wait_flags_kernel(const uint32_t *flags, int world, const uint32_t *seq_ctr)
+static __global__ void wait_flags_kernel(const uint32_t *flags, int world, const uint32_t *seq_ctr)
 {
     const int r = threadIdx.x;
     if (r >= world) return;
@@ -693,7 +693,7 @@ __global__ void wait_flags_kernel(const uint32_t *flags, int world, const uint32
 // stores, then one system fence and one add of the whole exchange per rank.  Keeping the NVLink round trip of
 // the fence out of the decode kernel lets its CTAs exit -- and the next launch start filling its stage ring --
 // 1.7 us earlier (tools/p2pbench).  <<<1, 32>>>
-__global__ void peer_signal_kernel(PeerOut po)
+static __global__ void peer_signal_kernel(PeerOut po)
 {
     cudaTriggerProgrammaticLaunchCompletion();
     cudaGridDependencySynchronize();
@@ -704,7 +704,7 @@ __global__ void peer_signal_kernel(PeerOut po)
 }
 // unfused variant for launches whose kernel has no peer epilogue (the tile kernel): copies this rank's
 // [M][ncols] slice from a local buffer into every rank's Y, then signals like peer_signal
-__global__ void scatter_slice_kernel(const float *__restrict__ src, size_t src_stride, int M, int ncols, size_t y_stride, PeerOut po)
+static __global__ void scatter_slice_kernel(const float *__restrict__ src, size_t src_stride, int M, int ncols, size_t y_stride, PeerOut po)
 {
     const int b = (int)((ld_volatile_u32(po.seq_ctr) + 1) & 1u);
     const long total = (long)M * ncols;

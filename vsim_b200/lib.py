@@ -26,7 +26,8 @@ ABI_SYMBOLS = [
     "b200q4_mul_mat_dev_allgather", "b200q4_wait_flags", "b200q4_set_exact", "b200q4_exact_enabled", "b200q4_quantize_weights", "b200q4_hint_next_weight",
     "b200q4_model_load", "b200q4_model_header", "b200q4_model_tensor_count", "b200q4_model_tensor_info",
     "b200q4_model_weight", "b200q4_model_tensor_data", "b200q4_model_free",
-    "b200neox_load", "b200neox_n_vocab", "b200neox_eval", "b200neox_free", "b200neox_last_error",
+    "b200neox_load", "b200neox_n_vocab", "b200neox_eval", "b200neox_free", "b200neox_last_error", "b200neox_decode_is_program",
+    "b200q4_chain_create", "b200q4_chain_run", "b200q4_chain_info", "b200q4_chain_free",
     "b200q4_host_alloc", "b200q4_host_free", "b200q4_launch_count", "b200q4_launch_count_reset",
     "b200q4_kernel_for", "b200q4_time_mul_mat_dev",
 ]
@@ -96,6 +97,11 @@ def load_library(build: bool = True) -> C.CDLL:
         "b200neox_n_vocab": (i, [vp]),
         "b200neox_eval": (i, [vp, vp, i, i, i, vp]),
         "b200neox_free": (None, [vp]),
+        "b200neox_decode_is_program": (i, [vp]),
+        "b200q4_chain_create": (vp, [i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i)]),
+        "b200q4_chain_run": (i, [vp, vp]),
+        "b200q4_chain_info": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(sz)]),
+        "b200q4_chain_free": (None, [vp]),
         "b200neox_last_error": (C.c_char_p, []),
         "b200q4_quantize_weights": (i, [i, f32p, C.c_longlong, i, sz, vp, vp]),
         "b200q4_mul_mat_dev_allgather": (i, [vp, vp, i, sz, C.POINTER(vp), i, i, i, sz, C.POINTER(vp), vp, vp]),
@@ -199,6 +205,41 @@ class Q4Weight:
     def free(self) -> None:
         if getattr(self, "handle", None):
             self._L.b200q4_weight_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Chain:
+    """b200q4_chain: n dependent M = 1 mul_mats (device pointers) executed by one persistent launch."""
+
+    def __init__(self, weights, x_ptrs, y_ptrs, deps=None):
+        L = self._L = load_library()
+        n = len(weights)
+        ws = (C.c_void_p * n)(*[w.handle for w in weights])
+        xs = (C.c_void_p * n)(*x_ptrs)
+        ys = (C.c_void_p * n)(*y_ptrs)
+        dp = (C.c_int * n)(*deps) if deps is not None else None
+        self.handle = L.b200q4_chain_create(n, ws, xs, ys, dp)
+        if not self.handle:
+            raise B200Q4Error(f"b200q4_chain_create failed: {_err(L)}")
+        self.n = n
+
+    def run(self, stream=None) -> None:
+        _check(self._L, self._L.b200q4_chain_run(self.handle, stream), "b200q4_chain_run")
+
+    def info(self):
+        n, st, sm = C.c_int(0), C.c_int(0), C.c_size_t(0)
+        self._L.b200q4_chain_info(self.handle, C.byref(n), C.byref(st), C.byref(sm))
+        return {"ops": n.value, "stages": st.value, "smem": sm.value}
+
+    def free(self) -> None:
+        if getattr(self, "handle", None):
+            self._L.b200q4_chain_free(self.handle)
             self.handle = None
 
     def __del__(self):
