@@ -426,6 +426,27 @@ def test_microbench_shape_m64_sampled_rows(gpu, oracle, qt, tag):
     w.free()
 
 
+@pytest.mark.parametrize("qt,tag", TYPES)
+def test_microbench_shape_m512_sampled_rows(gpu, oracle, qt, tag):
+    """The M=512 microbench point (BASELINE configs[1], tcgen05 tile kernel) at full N, K: oracle on a 128-row sample of
+    W that hits every 128-row MMA tile position (first / last rows of tiles, the tensor's last tile), all 512 columns."""
+    rng = np.random.default_rng(99)
+    n, k, m = 16384, 4096, 512
+    wq = oracle.quantize_rows(qt, rng.uniform(-0.05, 0.05, (n, k)).astype(np.float32))
+    x = rng.standard_normal((m, k)).astype(np.float32)
+    w = gpu.Q4Weight(qt, wq, n, k)
+    y = gpu.mul_mat(w, x)
+    rows = np.unique(np.concatenate([rng.choice(n, 96, replace=False), [0, 15, 16, 127, 128, 8191, 8192, n - 129, n - 128, n - 17, n - 16, n - 1]]))
+    yr = oracle.mul_mat(qt, wq[rows], len(rows), k, x, nth=8)
+    assert assert_close(y[:, rows], yr, f"{tag} M=512 sampled") < 1e-5
+    # size-independent property at the full size: rows of X that are equal give equal rows of Y (batch consistency)
+    x2 = x.copy(); x2[511] = x2[0]
+    y2 = gpu.mul_mat(w, x2)
+    assert np.array_equal(y2[511].view(np.uint32), y2[0].view(np.uint32))
+    assert np.array_equal(y2[1:511].view(np.uint32), y[1:511].view(np.uint32))
+    w.free()
+
+
 # ---- transposed-src0 branch (row f-2) ----------------------------------------------
 @pytest.mark.parametrize("qt,tag", TYPES)
 def test_transposed_branch_golden_bit_exact(gpu, golden, qt, tag):

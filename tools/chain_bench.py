@@ -35,7 +35,7 @@ def time_chain(L, chain, reps, warm=3):
     for _ in range(warm):
         chain.run()
     L.b200q4_sync(None)
-    st = torch.cuda.current_stream()
+    st = time_chain.stream = getattr(time_chain, "stream", None) or torch.cuda.Stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
     for _ in range(reps):

@@ -1,0 +1,56 @@
+"""Per-op timeline of the decode program kernel (development aid).  Needs a -DB200Q4_TIMELINE build:
+    B200Q4_TIMELINE=1 B200Q4_LIB_OUT=vsim_b200/libb200q4_tl.so python -m vsim_b200.build --force
+    B200Q4_LIB=vsim_b200/libb200q4_tl.so B200Q4_DBG=1 python tools/prog_timeline.py [dep|l2]
+stamps per (CTA, op): 0 producer starts issuing, 1 consumers reach the op, 2 dependency satisfied, 3 pack built, 5 CTA published."""
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import vsim_b200
+from tools.chain_bench import rand_q4
+
+vsim_b200.init(0)
+L = vsim_b200.load_library()
+L.b200q4_chain_timeline.restype = C.c_int
+L.b200q4_chain_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+rng = np.random.default_rng(1)
+what = sys.argv[1] if len(sys.argv) > 1 else "dep"
+if what == "l2":
+    n = k = 4096; nops = 12
+    w = vsim_b200.Q4Weight(0, rand_q4(rng, 0, n, k), n, k)
+    ws = [w] * nops
+    ys = [torch.zeros(n, device="cuda") for _ in range(2)]
+    xs = [ys[(i + 1) & 1].data_ptr() for i in range(nops)]
+    yp = [ys[i & 1].data_ptr() for i in range(nops)]
+else:
+    n, k, nops = 16384, 4096, 10
+    ws = [vsim_b200.Q4Weight(0, rand_q4(rng, 0, n, k), n, k) for _ in range(nops)]
+    x0 = torch.randn(k, device="cuda")
+    ys = [torch.zeros(n, device="cuda") for _ in range(nops)]
+    xs = [x0.data_ptr()] + [ys[i - 1].data_ptr() for i in range(1, nops)]
+    yp = [y.data_ptr() for y in ys]
+ch = vsim_b200.Chain(ws, xs, yp, [-1] + list(range(nops - 1)))
+for _ in range(4):
+    ch.run()
+L.b200q4_sync(None)
+info = ch.info()
+buf = np.zeros(148 * info["ops"] * 8 + 8, np.uint64)
+g = L.b200q4_chain_timeline(ch.handle, buf.ctypes.data, buf.size)
+assert g > 0, g
+t = buf[: g * info["ops"] * 8].reshape(g, info["ops"], 8).astype(np.int64)
+t0 = t[:, 0, 0].min()
+t = np.where(t > 0, t - t0, -1)
+print(f"{what}: grid {g}, {info}")
+print(" op | producer start (min/med) | reach op (med) | dep ok (med) | pack built (med) | published (med / max) | op time (max pub - prev max pub)")
+prev = 0
+for o in range(nops):
+    col = lambda i: t[:, o, i][t[:, o, i] >= 0]
+    med = lambda i: float(np.median(col(i))) / 1e3 if col(i).size else float("nan")
+    mx = lambda i: float(col(i).max()) / 1e3 if col(i).size else float("nan")
+    mn = lambda i: float(col(i).min()) / 1e3 if col(i).size else float("nan")
+    print(f"{o:3d} | {mn(0):7.2f} {med(0):7.2f} | {med(1):7.2f} | {med(2):7.2f} | {med(3):7.2f} | {med(5):7.2f} {mx(5):7.2f} | {mx(5) - prev:6.2f}")
+    prev = mx(5)

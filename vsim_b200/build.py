@@ -39,7 +39,8 @@ def is_stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES)]
+    out = Path(os.environ["B200Q4_LIB_OUT"]) if os.environ.get("B200Q4_LIB_OUT") else LIB     # development: a second build beside the product
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(out), *map(str, SOURCES)]
     if os.environ.get("B200Q4_TIMELINE"):          # development: per-CTA %globaltimer stamps (tools/timeline.py)
         cmd.insert(1, "-DB200Q4_TIMELINE")
     if verbose:
@@ -50,7 +51,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed building libb200q4.so")
     if verbose:
         sys.stderr.write(r.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

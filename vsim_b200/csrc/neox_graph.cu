@@ -269,36 +269,42 @@ int build_decode_program(b200neox *m)
         m->prog_bufs.push_back(p);
         return p;
     };
-    // the output of a mul_mat as a list of sources: the finished vector, or its K-slice partials plus the bias
-    struct Out { std::vector<PgSrc> src; int op; };
+    // Every vector an op hands to a later op is a buffer of {value, tag} pairs (q4_prog.cuh): the reader polls the data.
+    // The output of a mul_mat as a list of sources: the finished vector, or its K-slice partials plus the bias.
+    struct Out { std::vector<PgSrc> src; int op; float *buf; };
     bool oom = false;
-    auto matvec = [&](b200q4_weight *w, const float *bias, int dep, int in_mode, int res, const std::vector<PgSrc> &src,
-                      const float *lw, const float *lb, float *y_fixed) {
+    auto matvec = [&](b200q4_weight *w, const float *bias, int in_mode, int res, const std::vector<PgSrc> &src,
+                      const float *lw, const float *lb, float *plain_y, bool same_pack) {
         Out o;
+        o.buf = nullptr;
         const PgGeo g = pg_geometry(w);
         const int N = b200q4_weight_rows(w);
         if (g.PP == 1) {
-            float *y = y_fixed ? y_fixed : dev((size_t)N);
+            float *y = plain_y ? plain_y : dev(2 * (size_t)N);
             if (!y) { oom = true; o.op = -1; return o; }
-            o.op = b.add_matvec(w, dep, in_mode, res, src.data(), (int)src.size(), lw, lb, m->t_gelu, y, bias, 0);
-            o.src.push_back(pg_src_f32(y));
+            o.op = b.add_matvec(w, -1, in_mode, res, src.data(), (int)src.size(), lw, lb, m->t_gelu, y, bias, 0, !plain_y, same_pack);
+            o.src.push_back(pg_src_tag(y, o.op));
+            o.buf = y;
         } else {
             const int stride = (N + 3) & ~3;
-            float *part = dev((size_t)g.PP * stride);
+            float *part = dev(2 * (size_t)g.PP * stride);
             if (!part) { oom = true; o.op = -1; return o; }
-            o.op = b.add_matvec(w, dep, in_mode, res, src.data(), (int)src.size(), lw, lb, m->t_gelu, part, nullptr, stride);
-            o.src.push_back(pg_src_f32(part, g.PP, stride));
+            o.op = b.add_matvec(w, -1, in_mode, res, src.data(), (int)src.size(), lw, lb, m->t_gelu, part, nullptr, stride, true, same_pack);
+            o.src.push_back(pg_src_tag(part, o.op, g.PP, stride));
             if (bias) o.src.push_back(pg_src_f32(bias));
+            o.buf = part;
         }
         return o;
     };
-    float *q = dev(E), *k = dev(E), *v = dev(E), *att = dev(E);
-    float *part = dev((size_t)H * ((m->n_ctx + PG_ATT_CHUNK - 1) / PG_ATT_CHUNK) * (d + 2));
-    if (!q || !k || !v || !att || !part) { m->prog_why = "device allocation failed"; return 1; }
+    float *att = dev(2 * (size_t)E);
+    const size_t chunks = (size_t)(m->n_ctx + PG_ATT_CHUNK - 1) / PG_ATT_CHUNK;
+    float *part = dev((size_t)H * chunks * d), *att_sc = dev((size_t)H * (m->n_ctx + chunks));
+    double *att_sum = reinterpret_cast<double *>(dev(2 * (size_t)H * chunks + 2));
+    if (!att || !part || !att_sc || !att_sum) { m->prog_why = "device allocation failed"; return 1; }
     const float scale = (float)(1.0 / sqrt((double)((float)E / (float)H)));                  // vsim.cpp:590
     // what the next layer-norm op has to add to the residual stream first
     std::vector<PgSrc> pending;
-    int pending_res = PG_RES_SET, last = -1;
+    int pending_res = PG_RES_SET;
     PgSrc emb{m->d_wte, nullptr, m->wte_type, E, 1.0f, PG_SRC_Q4ROW};                         // ggml_get_rows(wte, embd), vsim.cpp:516
     pending.push_back(emb);
     const std::vector<PgSrc> none;
@@ -308,44 +314,47 @@ int build_decode_program(b200neox *m)
         const NeoxLayer &ly = m->layers[(size_t)l];
         float *mk = m->mem_k + (size_t)l * m->n_ctx * E, *mv = m->mem_v + (size_t)l * m->n_ctx * E;
         if ((int)pending.size() > PG_MAX_SRC) { m->prog_why = "too many residual sources"; return 1; }
-        const Out oq = chk(matvec(ly.wq, ly.bq, last, PG_IN_LN, pending_res, pending, ly.ln1_w, ly.ln1_b, q));
-        const Out ok = chk(matvec(ly.wk, ly.bk, -1, PG_IN_LN, PG_RES_KEEP, none, ly.ln1_w, ly.ln1_b, k));
-        const Out ov = chk(matvec(ly.wv, ly.bv, -1, PG_IN_LN, PG_RES_KEEP, none, ly.ln1_w, ly.ln1_b, v));
+        // (per-layer output buffers: a vector is only overwritten by ops that cannot start before all its readers are done)
+        const Out oq = chk(matvec(ly.wq, ly.bq, PG_IN_LN, pending_res, pending, ly.ln1_w, ly.ln1_b, nullptr, false));
+        const Out ok = chk(matvec(ly.wk, ly.bk, PG_IN_LN, PG_RES_KEEP, none, ly.ln1_w, ly.ln1_b, nullptr, true));
+        const Out ov = chk(matvec(ly.wv, ly.bv, PG_IN_LN, PG_RES_KEEP, none, ly.ln1_w, ly.ln1_b, nullptr, true));
         if (bad) break;
-        if (oq.src.size() != 1 || ok.src.size() != 1 || ov.src.size() != 1) { m->prog_why = "n_embd above 8192 (K-sliced Q/K/V)"; return 1; }
+        if (oq.src.size() != 1 || oq.src[0].np != 1) { m->prog_why = "n_embd above 8192 (K-sliced Q/K/V)"; return 1; }
         pending.clear();
+        auto attn = [&]() { return b.add_attn(-1, oq.buf, ok.buf, ov.buf, oq.op, ok.op, ov.op, mk, mv, att, part, att_sc, att_sum,
+                                              m->rope_cs, m->t_exp, H, d, m->n_rot, m->n_ctx, scale); };
         if (m->par_res == 1) {
             // vsim.cpp:666-696: the MLP reads the layer input, so its first matrix needs nothing from the attention
-            const Out o1 = chk(matvec(ly.w1, ly.b1, -1, PG_IN_LN, PG_RES_KEEP, none, ly.ln2_w, ly.ln2_b, nullptr));
+            const Out o1 = chk(matvec(ly.w1, ly.b1, PG_IN_LN, PG_RES_KEEP, none, ly.ln2_w, ly.ln2_b, nullptr, false));
             if (bad) break;
-            const int oa = b.add_attn(ov.op, q, k, v, mk, mv, att, part, m->rope_cs, H, d, m->n_rot, m->n_ctx, scale);
-            const Out o2 = chk(matvec(ly.w2, ly.b2, o1.op, PG_IN_GELU, PG_RES_KEEP, o1.src, nullptr, nullptr, nullptr));
-            const std::vector<PgSrc> a_in{pg_src_f32(att)};
-            const Out oo = chk(matvec(ly.wo, ly.bo, oa, PG_IN_PLAIN, PG_RES_KEEP, a_in, nullptr, nullptr, nullptr));
+            const int oa = attn();
+            const Out o2 = chk(matvec(ly.w2, ly.b2, PG_IN_GELU, PG_RES_KEEP, o1.src, nullptr, nullptr, nullptr, false));
             if (bad || oa < 0) { bad = true; break; }
+            const std::vector<PgSrc> a_in{pg_src_tag(att, oa)};
+            const Out oo = chk(matvec(ly.wo, ly.bo, PG_IN_PLAIN, PG_RES_KEEP, a_in, nullptr, nullptr, nullptr, false));
+            if (bad) break;
             pending = oo.src;                                                                // inpL = inpL + (cur + inpFF)
             pending.insert(pending.end(), o2.src.begin(), o2.src.end());
-            last = oo.op;
         } else {
             // vsim.cpp:636-665: inpFF = norm(cur + inpL) -> MLP; inpL = inpFF + inpL (the attention output only feeds the MLP)
-            const int oa = b.add_attn(ov.op, q, k, v, mk, mv, att, part, m->rope_cs, H, d, m->n_rot, m->n_ctx, scale);
-            const std::vector<PgSrc> a_in{pg_src_f32(att)};
-            const Out oo = chk(matvec(ly.wo, ly.bo, oa, PG_IN_PLAIN, PG_RES_KEEP, a_in, nullptr, nullptr, nullptr));
-            if (bad || oa < 0) { bad = true; break; }
-            const Out o1 = chk(matvec(ly.w1, ly.b1, oo.op, PG_IN_LN, PG_RES_TEMP, oo.src, ly.ln2_w, ly.ln2_b, nullptr));
+            const int oa = attn();
+            if (oa < 0) { bad = true; break; }
+            const std::vector<PgSrc> a_in{pg_src_tag(att, oa)};
+            const Out oo = chk(matvec(ly.wo, ly.bo, PG_IN_PLAIN, PG_RES_KEEP, a_in, nullptr, nullptr, nullptr, false));
             if (bad) break;
-            const Out o2 = chk(matvec(ly.w2, ly.b2, o1.op, PG_IN_GELU, PG_RES_KEEP, o1.src, nullptr, nullptr, nullptr));
+            const Out o1 = chk(matvec(ly.w1, ly.b1, PG_IN_LN, PG_RES_TEMP, oo.src, ly.ln2_w, ly.ln2_b, nullptr, false));
+            if (bad) break;
+            const Out o2 = chk(matvec(ly.w2, ly.b2, PG_IN_GELU, PG_RES_KEEP, o1.src, nullptr, nullptr, nullptr, false));
             if (bad) break;
             pending = o2.src;
-            last = o2.op;
         }
         pending_res = PG_RES_ADD;
     }
     if (!bad) {
         if ((int)pending.size() > PG_MAX_SRC) { m->prog_why = "too many residual sources"; return 1; }
         const PgGeo g = pg_geometry(m->w_head);
-        Out oh = chk(matvec(m->w_head, nullptr, last, PG_IN_LN, pending_res, pending, m->lnf_w, m->lnf_b, g.PP == 1 ? m->logits : nullptr));
-        if (!bad && g.PP > 1 && b.add_sum(oh.op, oh.src[0], m->logits, V) < 0) bad = true;
+        Out oh = chk(matvec(m->w_head, nullptr, PG_IN_LN, pending_res, pending, m->lnf_w, m->lnf_b, g.PP == 1 ? m->logits : nullptr, false));
+        if (!bad && g.PP > 1 && b.add_sum(-1, oh.src[0], m->logits, V) < 0) bad = true;
     }
     if (bad) { m->prog_why = oom ? "device allocation failed" : std::string("program builder: ") + b200q4_last_error(); return 1; }
     if (prog_finalize(b, m->prog)) { m->prog_why = std::string("program: ") + b200q4_last_error(); return 1; }
@@ -546,8 +555,10 @@ int b200neox_eval(b200neox *m, const int *tokens, int N, int n_past, int n_threa
         bias(m->v, ly.bv, E);
         k_copy<<<nblk((long)N * E), 256, 0, st>>>(m->k, mk + (size_t)n_past * E, (long)N * E);          // cpy into the KV memory (:557-558)
         k_copy<<<nblk((long)N * E), 256, 0, st>>>(m->v, mv + (size_t)n_past * E, (long)N * E);
-        k_rope<<<nblk((long)N * H * (m->n_rot / 2)), 256, 0, st>>>(m->q, d, H, N, n_past, m->n_rot, 0, m->rope_cs);
-        k_rope<<<nblk((long)N * H * (m->n_rot / 2)), 256, 0, st>>>(mk, d, H, P, n_past, m->n_rot, 1, m->rope_cs);   // in place on the memory view
+        if (m->n_rot > 0) {
+            k_rope<<<nblk((long)N * H * (m->n_rot / 2)), 256, 0, st>>>(m->q, d, H, N, n_past, m->n_rot, 0, m->rope_cs);
+            k_rope<<<nblk((long)N * H * (m->n_rot / 2)), 256, 0, st>>>(mk, d, H, P, n_past, m->n_rot, 1, m->rope_cs);   // in place on the memory view
+        }
         k_kq<<<nblk((long)H * N * P), 256, 0, st>>>(mk, m->q, H, N, P, d, n_past, scale, m->kq);
         k_soft_max<<<nblk((long)H * N, 32), 32, 0, st>>>(m->kq, H * N, P, m->t_exp);
         k_kqv<<<nblk((long)H * N * d), 256, 0, st>>>(mv, m->kq, H, N, P, d, nth, m->merged);

@@ -32,6 +32,7 @@
 // Everything here is M = 1 (one activation row); prompts (M > 1) use the per-op kernels.
 #pragma once
 #include <cuda_fp16.h>
+#include <cstddef>
 #include "q4_kernels.cuh"
 
 namespace b200q4 {
@@ -47,29 +48,39 @@ constexpr int PG_ATT_MAX_D = 512;                        // largest head size th
 
 enum { PG_MATVEC = 0, PG_ATTN = 1, PG_SUM = 2 };
 enum { PG_IN_PLAIN = 0, PG_IN_LN = 1, PG_IN_GELU = 2 };
-enum { PG_SRC_F32 = 0, PG_SRC_Q4ROW = 1 };
+enum { PG_SRC_F32 = 0, PG_SRC_Q4ROW = 1, PG_SRC_TAG = 2 };
 enum { PG_RES_KEEP = 0, PG_RES_ADD = 1, PG_RES_SET = 2, PG_RES_TEMP = 3 };
 
-// One input vector:  v[k] = scale * sum_{p < np} ptr[p * stride + k]        (PG_SRC_F32; np > 1: K-slice partials)
+// One input vector:  v[k] = scale * sum_{p < np} ptr[p * stride + k]        (PG_SRC_F32: plain floats; np > 1: K-slice partials)
+//                    the same over {value, tag} pairs                       (PG_SRC_TAG: the output of op `kind >> 8` of THIS launch)
 //                    v[k] = dequantize_row(ptr, row *row)[k]                (PG_SRC_Q4ROW: ggml_get_rows on the Q4
 //                           embedding matrix, ggml.c:300-362; np = quant type, stride = row length K)
+// Tagged vectors are how one op hands its result to the next without a fence or a counter: the producer stores every
+// value together with a tag (launch epoch, op index) in ONE 8-byte store, the consumer polls the pair until the tag is
+// this launch's -- the data is its own flag (the idea of NCCL's LL protocol).  A dependent op starts one store-to-load
+// latency after the last output was written, instead of store -> fence -> atomic -> poll -> load.
 struct PgSrc {
     const void *ptr;
     const int  *row;
     int   np, stride;
     float scale;
-    int   kind;
+    int   kind;              // low 8 bits: PG_SRC_*; PG_SRC_TAG: the producing op's index << 8
 };
+inline PgSrc pg_src_tag(const void *p, int op, int np = 1, int stride = 0, float scale = 1.0f) { return PgSrc{p, nullptr, np, stride, scale, PG_SRC_TAG | (op << 8)}; }
 
-struct PgOp {
+struct alignas(16) PgOp {
     int kind;                // PG_MATVEC / PG_ATTN / PG_SUM (y[n] = src[0] summed over its K-slice partials, n < N; spread over all CTAs)
     int dep;                 // index of the op that must be complete before this op's inputs are read (-1: none)
     // ---- PG_MATVEC:  Y[n] = sum_k W[n][k] * quantize(a)[k] (+ bias[n]) ---------------------------------------
     const uint8_t *wt;       // wtile
     int C, n_tiles, N, nb, U;
     int PP, TS, ntasks;      // K-slicing geometry (slice_geometry of q4_api.cu)
-    int nstatic;             // tasks per CTA taken without a ticket
+    int nstatic;             // tasks per CTA taken without a ticket: task = ((idx + rot) % ncls) + k * ncls, k < nstatic
+    int rot;                 // rotation of the static assignment: consecutive small ops hand their odd tasks to different CTAs
+    int dynamic;             // != 0: the tasks beyond nstatic * ncls are drawn from a ticket counter
     int tk_off;              // first ticket counter of this op in PgParams::ctr (one per K-slice class)
+    int next_mv;             // index of the next PG_MATVEC op (n_ops: none) and what the producer needs of it ahead of time:
+    int nx_tk_off, nx_PP, nx_dynamic;    //   its ticket counters (the first ticket is drawn one op early)
     int in_mode;             // a = v (PLAIN) | gelu(v) (GELU) | layernorm(residual)(LN), v = sum of the sources
     int res;                 // LN: KEEP = residual and its statistics as they are; ADD = residual += v first;
                              //     SET = residual = v; TEMP = normalise (residual + v) without storing it
@@ -77,37 +88,84 @@ struct PgOp {
     PgSrc src[PG_MAX_SRC];
     const float *ln_w, *ln_b;
     const uint16_t *gelu_tab;
-    float *y;                // PP == 1: Y;  PP > 1: slice p of the raw sums at y[p * y_slice + n]
+    float *y;                // PP == 1: Y;  PP > 1: slice p of the raw sums at y[p * y_slice + n].  y_tag: {value, tag} pairs
     const float *bias;       // PP == 1 only (may be NULL)
-    int y_slice, pad0;
+    int y_slice, dep_mv;     // dep_mv: the op `dep` is a PG_MATVEC (its completion implies that of every earlier op)
+    int y_tag, publish;      // publish: a later op names this one as its `dep`: count the CTAs that are done with it
+    float *y_plain;          // PP == 1, optional: an untagged copy of Y as well (what a caller outside the list reads)
+    int pack_of, pad3;       // index of the first op of a run of ops with the SAME activation pack (Q, K, V): built once
+    // (everything above is what a PG_MATVEC needs: the first PG_OPC_WORDS words are what the shared-memory op cache holds)
     // ---- PG_ATTN: the new token's attention for one layer (decode, one query row) -----------------------------
-    const float *q, *k, *v;          // [H * d] (biases already added)
+    const float *q, *k, *v;          // [H * d] {value, tag} pairs written by ops tq, tk, tv (biases already added)
+    int tq, tk, tv, pad4;
     float *mem_k, *mem_v;            // this layer's KV memory [n_ctx][H * d], vsim.cpp:318-330
-    float *att_out;                  // [H * d] merged heads (vsim.cpp:621-627)
-    float *att_part;                 // [H][max_chunks][d + 2] partial (sum, max, denominator) per position chunk
+    float *att_out;                  // [H * d] merged heads (vsim.cpp:621-627), {value, tag} pairs
+    float *att_part;                 // [H][max_chunks][d] weighted V sums per position chunk (several chunks per head only)
+    float *att_sc;                   // [H][n_ctx] scaled scores, [H][max_chunks] chunk maxima behind them
+    double *att_sum;                 // [H][max_chunks] chunk denominators
     const double2 *rope;             // [n_ctx][n_rot / 2] {cos, sin}(p * theta_i), host libm like ggml.c:6126-6129
-    int H, d, n_rot, max_chunks, cnt_off, pad1;
+    const uint16_t *exp_tab;         // ggml_init's fp16 exp table (ggml.c:1240-1255), what ggml_soft_max looks its exponentials up in
+    int H, d, n_rot, max_chunks, cnt_off, n_ctx;   // cnt_off: 2 * H counters (scores published / partials published)
     float att_scale; int pad2;
 };
 
+constexpr int PG_OPC = 8;                                // mul_mat ops cached in shared memory (ring; > PG_MAX_STAGES + 1)
+constexpr int PG_OPC_WORDS = 84;                         // 336 bytes per entry: one 16-byte load for each of 21 producer lanes (the PG_MATVEC part of PgOp)
+static_assert(offsetof(PgOp, q) <= PG_OPC_WORDS * 4, "the PG_MATVEC part of PgOp must fit a cache entry");
+
 struct PgParams {
     const PgOp *ops;
-    int  n_ops;
+    int  n_ops, first_mv;
     int *ctr;                // [0] CTAs finished; [1 + o] CTAs done with op o; tickets; attention head counters.  All zero
     int  n_ctr;              //   between launches: the last CTA to leave clears them.
-    const int *dyn;          // [0] token id (through PgSrc::row), [1] n_past
+    int *dyn;                // [0] token id (through PgSrc::row), [1] n_past, [2] launch epoch (the last CTA to leave advances it)
     int *err;                // set (op index + 1) before the kernel traps on a wait that can never end
     int  stages, e_cap, nbp_cap, att_cap;    // shared-memory sizing: residual floats, apack quant blocks, attention floats
+    unsigned long long *dbg; // optional timeline [grid][n_ops][8] of %globaltimer stamps (B200Q4_DBG=1), else NULL
 };
 
 __host__ __device__ constexpr size_t pg_stage_bytes(int qt) { return (size_t)PG_UNITS * chunk_bytes(qt) + (size_t)PG_UNITS * PG_RW * 4; }
 __host__ __device__ constexpr size_t pg_fixed_bytes(int e_cap, int nbp_cap, int att_cap)
 {
     return (size_t)e_cap * 4 + (size_t)nbp_cap * 32 + (size_t)nbp_cap * 12 + (size_t)att_cap * 4 + 40 * 8 +
-           3 * PG_MAX_STAGES * 8 + PG_MAX_STAGES * 16 + 64 + 128;
+           3 * PG_MAX_STAGES * 8 + PG_MAX_STAGES * 16 + 64 + 128 + PG_OPC * PG_OPC_WORDS * 4;
 }
 
 #ifndef Q4_PROG_TYPES_ONLY                               // (host-only includers stop here)
+
+// Shared-memory map of q4_prog_kernel.  The out-of-line helpers recompute it from the parameter copy instead of taking
+// pointers as arguments: whatever the main loop does not need stays out of its registers.
+struct PgSmem {
+    uint8_t *stage; float *red, *x; uint8_t *aq; float *ap, *att; double *stat;
+    uint64_t *bar_full, *bar_empty, *bar_done; int4 *desc; int *dop, *flag; uint32_t *opc;
+};
+extern __shared__ __align__(128) uint8_t pg_smem_base[];
+__device__ __forceinline__ PgSmem pg_smem(const PgParams &p, int qt)
+{
+    PgSmem m;
+    m.stage = pg_smem_base;
+    m.red = reinterpret_cast<float *>(pg_smem_base + (size_t)p.stages * PG_UNITS * chunk_bytes(qt));
+    m.x = m.red + (size_t)p.stages * PG_UNITS * PG_RW;
+    m.aq = reinterpret_cast<uint8_t *>(m.x + p.e_cap);
+    m.ap = reinterpret_cast<float *>(m.aq + (size_t)p.nbp_cap * 32);
+    m.att = m.ap + 3 * (size_t)p.nbp_cap;
+    m.stat = reinterpret_cast<double *>(m.att + p.att_cap);
+    m.bar_full = reinterpret_cast<uint64_t *>(m.stat + 40);
+    m.bar_empty = m.bar_full + PG_MAX_STAGES;
+    m.bar_done = m.bar_empty + PG_MAX_STAGES;
+    m.desc = reinterpret_cast<int4 *>(m.bar_done + PG_MAX_STAGES);     // {units (0: none, -2: STOP), first chunk index, first tile, task}
+    m.dop = reinterpret_cast<int *>(m.desc + PG_MAX_STAGES);           // op index of the stage | PG_END when it is the CTA's last of that op
+    m.flag = m.dop + PG_MAX_STAGES + 2;                                // [0] scratch flag, [1] waited_mv, [2..4] current op: C, first chunk of the K-slice, plane stride,
+                                                                       // [5] op whose activation pack is in shared memory, [6] tag base of this launch
+    m.opc = reinterpret_cast<uint32_t *>(m.flag + 8);                  // op cache [PG_OPC][PG_OPC_WORDS]
+    return m;
+}
+
+#ifdef B200Q4_TIMELINE
+#define PG_STAMP(o, slot) do { if (p.dbg && (o) < p.n_ops) p.dbg[((size_t)blockIdx.x * p.n_ops + (o)) * 8 + (slot)] = gtimer(); } while (0)
+#else
+#define PG_STAMP(o, slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ int ld_acquire_gpu(const int *p)
 {
@@ -122,7 +180,7 @@ __device__ __forceinline__ void pg_wait_ctr(const int *c, int target, int *err, 
     const long long t0 = clock64();
     for (unsigned spins = 0;; spins++) {
         if (ld_acquire_gpu(c) >= target) return;
-        if (spins > 64) __nanosleep(40);
+        if (spins > 4096) __nanosleep(64);
         if ((spins & 1023) == 1023 && clock64() - t0 > 4000000000ll) {
             if (err) *err = code;
             __threadfence_system();
@@ -147,10 +205,66 @@ __device__ __forceinline__ void pg_mbar_wait(uint64_t *b, uint32_t parity)
 }
 __device__ __forceinline__ void pg_bar() { asm volatile("bar.sync 1, %0;" :: "n"(PG_CTHREADS) : "memory"); }
 
-// four consecutive elements k .. k+3 of one source (k % 4 == 0)
-__device__ __forceinline__ float4 pg_src4(const PgSrc &s, int k)
+__device__ __forceinline__ float4 ld_relaxed_f4(const void *p)
 {
-    if (s.kind == PG_SRC_F32) {
+    float4 r;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float2 ld_relaxed_f2(const void *p)
+{
+    float2 r;
+    asm volatile("ld.relaxed.gpu.global.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_tagged(float *y2, size_t idx, float v, int tag)
+{
+    asm volatile("st.relaxed.gpu.global.v2.f32 [%0], {%1,%2};" :: "l"(y2 + 2 * idx), "f"(v), "f"(__int_as_float(tag)) : "memory");
+}
+__device__ __noinline__ void pg_tag_timeout(int *err, int code)
+{
+    if (err) *err = code;
+    __threadfence_system();
+    __trap();
+}
+// one tagged element: spins until the pair carries this launch's tag
+__device__ __forceinline__ float pg_ld_tag1(const float *base2, size_t idx, int tag, int *err)
+{
+    const long long t0 = clock64();
+    for (unsigned spins = 0;; spins++) {
+        const float2 v = ld_relaxed_f2(base2 + 2 * idx);
+        if (__float_as_int(v.y) == tag) return v.x;
+        if ((spins & 1023) == 1023 && clock64() - t0 > 4000000000ll) pg_tag_timeout(err, -tag);
+    }
+}
+// four consecutive tagged elements (idx % 4 == 0)
+__device__ __forceinline__ float4 pg_ld_tag4(const float *base2, size_t idx, int tag, int *err)
+{
+    const long long t0 = clock64();
+    for (unsigned spins = 0;; spins++) {
+        const float4 a = ld_relaxed_f4(base2 + 2 * idx), b = ld_relaxed_f4(base2 + 2 * idx + 4);
+        if (__float_as_int(a.y) == tag && __float_as_int(a.w) == tag && __float_as_int(b.y) == tag && __float_as_int(b.w) == tag)
+            return make_float4(a.x, a.z, b.x, b.z);
+        if ((spins & 1023) == 1023 && clock64() - t0 > 4000000000ll) pg_tag_timeout(err, -tag);
+    }
+}
+
+// four consecutive elements k .. k+3 of one source (k % 4 == 0)
+__device__ __forceinline__ float4 pg_src4(const PgSrc &s, int k, int tagbase, int *err)
+{
+    const int kind = s.kind & 255;
+    if (kind == PG_SRC_TAG) {
+        const int tag = tagbase | ((s.kind >> 8) + 1);
+        const float *b = static_cast<const float *>(s.ptr);
+        float4 a = pg_ld_tag4(b, (size_t)k, tag, err);
+        for (int p = 1; p < s.np; p++) {
+            const float4 t = pg_ld_tag4(b, (size_t)p * s.stride + k, tag, err);
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        if (s.scale != 1.0f) { a.x *= s.scale; a.y *= s.scale; a.z *= s.scale; a.w *= s.scale; }
+        return a;
+    }
+    if (kind == PG_SRC_F32) {
         const float *b = static_cast<const float *>(s.ptr) + k;
         float4 a = __ldcg(reinterpret_cast<const float4 *>(b));
         for (int p = 1; p < s.np; p++) {
@@ -179,11 +293,11 @@ __device__ __forceinline__ float4 pg_src4(const PgSrc &s, int k)
     return make_float4(r[0], r[1], r[2], r[3]);
 }
 // sum of the op's sources in list order (fixed association: every CTA computes the same bits)
-__device__ __forceinline__ float4 pg_sum_src4(const PgOp &op, int nsrc, int k)
+__device__ __forceinline__ float4 pg_sum_src4(const PgOp &op, int nsrc, int k, int tagbase, int *err)
 {
-    float4 a = pg_src4(op.src[0], k);
+    float4 a = pg_src4(op.src[0], k, tagbase, err);
     for (int j = 1; j < nsrc; j++) {
-        const float4 t = pg_src4(op.src[j], k);
+        const float4 t = pg_src4(op.src[j], k, tagbase, err);
         a.x = __fadd_rn(a.x, t.x); a.y = __fadd_rn(a.y, t.y); a.z = __fadd_rn(a.z, t.z); a.w = __fadd_rn(a.w, t.w);
     }
     return a;
@@ -202,8 +316,13 @@ __device__ __forceinline__ float pg_rope(float x_self, float x_pair, bool first_
                       : (float)__dadd_rn(__dmul_rn(cs.x, (double)x_self), __dmul_rn(cs.y, (double)x_pair));
 }
 
-__device__ __noinline__ void pg_attn(const PgParams &p, int o, int n_past, float *s_att, int *s_flag)
+__device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
 {
+    const PgParams &p = *pp;                                 // (a copy in shared memory: nothing here may live on the stack)
+    const PgSmem sm = pg_smem(p, qt);
+    float *s_att = sm.att;
+    int *s_flag = sm.flag;
+    const int n_past = p.dyn ? __ldg(p.dyn + 1) : 0;
     const PgOp &op = p.ops[o];
     const int ctid = threadIdx.x, lane = ctid & 31, warp = ctid >> 5;
     const int H = op.H, d = op.d, E = H * d, half = op.n_rot / 2, P = n_past + 1;
@@ -213,21 +332,30 @@ __device__ __noinline__ void pg_attn(const PgParams &p, int o, int n_past, float
     const float *gq = op.q, *gk = op.k, *gv = op.v;
     float *mk = op.mem_k, *mv = op.mem_v;
     const float scale = op.att_scale;
+    const uint16_t *etab = op.exp_tab;
     const int dj = (d + 31) & ~31, ng = PG_CTHREADS / dj;
+    float *g_sc = op.att_sc, *g_mx = op.att_sc + (size_t)H * op.n_ctx;
+    int *cnt1 = p.ctr + op.cnt_off, *cnt2 = cnt1 + H;
+    const int tagbase = sm.flag[6];
+    const int tag_q = tagbase | (op.tq + 1), tag_k = tagbase | (op.tk + 1), tag_v = tagbase | (op.tv + 1), tag_o = tagbase | (o + 1);
+    // ggml_soft_max's exponential (ggml.c:5862-5870): fp16(x - max) -> table -> fp32
+    auto texp = [&](float x) { return __half2float(__ushort_as_half(__ldg(etab + __half_as_ushort(__float2half_rn(x))))); };
+
+    // ---- pass A: rope, KV store, the chunk's scaled scores and their maximum --------------------------------------
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int h = item / nch, c = item - h * nch;
         const int p_lo = c * PG_ATT_CHUNK, np = min(PG_ATT_CHUNK, P - p_lo);
         const bool has_new = p_lo + np == P;
         pg_bar();                                            // the previous item's scratch is no longer read
         for (int j = ctid; j < d; j += PG_CTHREADS) {
-            float qv = __ldcg(gq + h * d + j), kv = 0.f, vv = 0.f;
-            if (has_new) { kv = __ldcg(gk + h * d + j); vv = __ldcg(gv + h * d + j); }
+            float qv = pg_ld_tag1(gq, (size_t)h * d + j, tag_q, p.err), kv = 0.f, vv = 0.f;
+            if (has_new) { kv = pg_ld_tag1(gk, (size_t)h * d + j, tag_k, p.err); vv = pg_ld_tag1(gv, (size_t)h * d + j, tag_v, p.err); }
             if (j < 2 * half) {
                 const bool fh = j < half;
                 const int jp = fh ? j + half : j - half, i0 = fh ? j : j - half;
                 const double2 cs = op.rope[(size_t)n_past * half + i0];
-                qv = pg_rope(qv, __ldcg(gq + h * d + jp), fh, cs);
-                if (has_new) kv = pg_rope(kv, __ldcg(gk + h * d + jp), fh, cs);
+                qv = pg_rope(qv, pg_ld_tag1(gq, (size_t)h * d + jp, tag_q, p.err), fh, cs);
+                if (has_new) kv = pg_rope(kv, pg_ld_tag1(gk, (size_t)h * d + jp, tag_k, p.err), fh, cs);
             }
             s_q[j] = qv;
             if (has_new) {
@@ -237,117 +365,180 @@ __device__ __noinline__ void pg_attn(const PgParams &p, int o, int n_past, float
             }
         }
         pg_bar();
-        for (int pl = warp; pl < np; pl += GEMV_WARPS) {     // K . Q  (ggml.c:4484-4516), then ggml_scale
+        for (int pl = warp; pl < np; pl += GEMV_WARPS) {     // K . Q (ggml.c:4484-4516: float products summed in double), then ggml_scale
             const int pos = p_lo + pl;
-            float sum = 0.f;
-            if (pos == n_past) { for (int j = lane; j < d; j += 32) sum = fmaf(s_kn[j], s_q[j], sum); }
+            double sum = 0.0;
+            if (pos == n_past) { for (int j = lane; j < d; j += 32) sum = __dadd_rn(sum, (double)__fmul_rn(s_kn[j], s_q[j])); }
             else {
                 const float *kr = mk + (size_t)pos * E + h * d;
-                for (int j = lane; j < d; j += 32) sum = fmaf(__ldcg(kr + j), s_q[j], sum);
+                for (int j = lane; j < d; j += 32) sum = __dadd_rn(sum, (double)__fmul_rn(__ldcg(kr + j), s_q[j]));
             }
 #pragma unroll
-            for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
-            if (lane == 0) s_sc[pl] = sum * scale;
+            for (int of = 16; of > 0; of >>= 1) sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, of));
+            if (lane == 0) s_sc[pl] = __fmul_rn((float)sum, scale);
         }
         pg_bar();
-        if (warp == 0) {                                     // soft_max of the chunk (ggml.c:5825-5893), local max / denominator
+        if (nch > 1) {                                       // publish the chunk: the row maximum needs every chunk
+            if (ctid < np) g_sc[(size_t)h * op.n_ctx + p_lo + ctid] = s_sc[ctid];
+            if (warp == 0) {
+                float m = fmaxf(lane < np ? s_sc[lane] : -INFINITY, lane + 32 < np ? s_sc[lane + 32] : -INFINITY);
+#pragma unroll
+                for (int of = 16; of > 0; of >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, of));
+                if (lane == 0) g_mx[(size_t)h * op.max_chunks + c] = m;
+            }
+            __threadfence();
+            pg_bar();
+            if (ctid == 0) atomicAdd(cnt1 + h, 1);
+            continue;
+        }
+        // ---- one chunk per head: soft_max and V^T . softmax right here (ggml.c:5825-5893, 4517-4553) ----------------
+        if (warp == 0) {
             const float v0 = lane < np ? s_sc[lane] : -INFINITY, v1 = lane + 32 < np ? s_sc[lane + 32] : -INFINITY;
             float m = fmaxf(v0, v1);
 #pragma unroll
             for (int of = 16; of > 0; of >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, of));
-            const float e0 = lane < np ? expf(v0 - m) : 0.f, e1 = lane + 32 < np ? expf(v1 - m) : 0.f;
-            float l = e0 + e1;
+            const float e0 = lane < np ? texp(__fsub_rn(v0, m)) : 0.f, e1 = lane + 32 < np ? texp(__fsub_rn(v1, m)) : 0.f;
+            double l = __dadd_rn((double)e0, (double)e1);
 #pragma unroll
-            for (int of = 16; of > 0; of >>= 1) l += __shfl_xor_sync(0xffffffffu, l, of);
-            s_sc[lane] = e0; s_sc[lane + 32] = e1;
-            if (lane == 0) { s_sc[PG_ATT_CHUNK] = m; s_sc[PG_ATT_CHUNK + 1] = l; }
+            for (int of = 16; of > 0; of >>= 1) l = __dadd_rn(l, __shfl_xor_sync(0xffffffffu, l, of));
+            const float inv = (float)(1.0 / l);
+            s_sc[lane] = __fmul_rn(e0, inv); s_sc[lane + 32] = __fmul_rn(e1, inv);
         }
         pg_bar();
-        {                                                    // V^T . softmax (ggml.c:4517-4553): position groups in parallel, merged in order
+        {
             const int g = ctid / dj, j = ctid - g * dj;
             if (g < ng && j < d) {
                 float a = 0.f;
                 for (int pl = g; pl < np; pl += ng) {
                     const int pos = p_lo + pl;
                     const float vv = pos == n_past ? s_vn[j] : __ldcg(mv + (size_t)pos * E + h * d + j);
-                    a = fmaf(s_sc[pl], vv, a);
+                    a = __fadd_rn(a, __fmul_rn(vv, s_sc[pl]));
                 }
                 s_o[g * dj + j] = a;
             }
         }
         pg_bar();
         if (ctid < d) {
-            float a = 0.f;
-            for (int g = 0; g < ng; g++) a += s_o[g * dj + ctid];
-            if (nch == 1) op.att_out[h * d + ctid] = a / s_sc[PG_ATT_CHUNK + 1];
-            else {
-                float *pt = op.att_part + ((size_t)h * op.max_chunks + c) * (d + 2);
-                pt[ctid] = a;
-                if (ctid == 0) { pt[d] = s_sc[PG_ATT_CHUNK]; pt[d + 1] = s_sc[PG_ATT_CHUNK + 1]; }
-            }
+            float a = s_o[ctid];
+            for (int g = 1; g < ng; g++) a = __fadd_rn(a, s_o[g * dj + ctid]);
+            st_tagged(op.att_out, (size_t)h * d + ctid, a, tag_o);
         }
-        if (nch > 1) {                                       // the head's last chunk to arrive merges the partials
+    }
+    // ---- pass B (several chunks per head): exponentials against the ROW maximum, chunk denominators, weighted V sums; the
+    //      head's last chunk to finish adds the pieces up.  Every CTA has published all of its chunks before it waits here.
+    if (nch > 1) {
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int h = item / nch, c = item - h * nch;
+            const int p_lo = c * PG_ATT_CHUNK, np = min(PG_ATT_CHUNK, P - p_lo);
+            pg_bar();
+            if (ctid == 0) pg_wait_ctr(cnt1 + h, nch, p.err, o + 1);
+            pg_bar();
+            if (warp == 0) {
+                float M = -INFINITY;
+                for (int cc = lane; cc < nch; cc += 32) M = fmaxf(M, __ldcg(g_mx + (size_t)h * op.max_chunks + cc));
+#pragma unroll
+                for (int of = 16; of > 0; of >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, of));
+                const float *sc = g_sc + (size_t)h * op.n_ctx + p_lo;
+                const float e0 = lane < np ? texp(__fsub_rn(__ldcg(sc + lane), M)) : 0.f;
+                const float e1 = lane + 32 < np ? texp(__fsub_rn(__ldcg(sc + lane + 32), M)) : 0.f;
+                double l = __dadd_rn((double)e0, (double)e1);
+#pragma unroll
+                for (int of = 16; of > 0; of >>= 1) l = __dadd_rn(l, __shfl_xor_sync(0xffffffffu, l, of));
+                s_sc[lane] = e0; s_sc[lane + 32] = e1;
+                if (lane == 0) op.att_sum[(size_t)h * op.max_chunks + c] = l;
+            }
+            if (p_lo + np == P)                              // the new position's V row (its K / V went to memory in pass A)
+                for (int j = ctid; j < d; j += PG_CTHREADS) s_vn[j] = pg_ld_tag1(gv, (size_t)h * d + j, tag_v, p.err);
+            pg_bar();
+            {
+                const int g = ctid / dj, j = ctid - g * dj;
+                if (g < ng && j < d) {
+                    float a = 0.f;
+                    for (int pl = g; pl < np; pl += ng) {
+                        const int pos = p_lo + pl;
+                        const float vv = pos == n_past ? s_vn[j] : __ldcg(mv + (size_t)pos * E + h * d + j);
+                        a = __fadd_rn(a, __fmul_rn(vv, s_sc[pl]));
+                    }
+                    s_o[g * dj + j] = a;
+                }
+            }
+            pg_bar();
+            if (ctid < d) {
+                float a = s_o[ctid];
+                for (int g = 1; g < ng; g++) a = __fadd_rn(a, s_o[g * dj + ctid]);
+                op.att_part[((size_t)h * op.max_chunks + c) * d + ctid] = a;
+            }
             __threadfence();
             pg_bar();
             if (ctid == 0) {
-                int *cnt = p.ctr + op.cnt_off + h;
-                const int last = atomicAdd(cnt, 1) == nch - 1;
-                if (last) *cnt = 0;
+                const int last = atomicAdd(cnt2 + h, 1) == nch - 1;
+                if (last) { cnt1[h] = 0; cnt2[h] = 0; }      // every chunk of the head is past both counters
                 *s_flag = last;
             }
             pg_bar();
             if (*s_flag) {
                 __threadfence();
                 if (ctid < d) {
-                    const float *pt = op.att_part + (size_t)h * op.max_chunks * (d + 2);
-                    float M = -INFINITY;
-                    for (int cc = 0; cc < nch; cc++) M = fmaxf(M, __ldcg(pt + (size_t)cc * (d + 2) + d));
-                    float L = 0.f, O = 0.f;
-                    for (int cc = 0; cc < nch; cc++) {
-                        const float w = expf(__ldcg(pt + (size_t)cc * (d + 2) + d) - M);
-                        L = fmaf(__ldcg(pt + (size_t)cc * (d + 2) + d + 1), w, L);
-                        O = fmaf(__ldcg(pt + (size_t)cc * (d + 2) + ctid), w, O);
-                    }
-                    op.att_out[h * d + ctid] = O / L;
+                    double S = 0.0;
+                    for (int cc = 0; cc < nch; cc++) S = __dadd_rn(S, __ldcg(op.att_sum + (size_t)h * op.max_chunks + cc));
+                    const float inv = (float)(1.0 / S);
+                    float O = 0.f;
+                    for (int cc = 0; cc < nch; cc++) O = __fadd_rn(O, __ldcg(op.att_part + ((size_t)h * op.max_chunks + cc) * d + ctid));
+                    st_tagged(op.att_out, (size_t)h * d + ctid, __fmul_rn(O, inv), tag_o);
                 }
             }
         }
     }
-    __threadfence();
-    pg_bar();
-    if (ctid == 0) atomicAdd(p.ctr + 1 + o, 1);
+    if (op.publish) {
+        __threadfence();
+        pg_bar();
+        if (ctid == 0) atomicAdd(p.ctr + 1 + o, 1);
+    }
 }
 
 // y[n] = sum of the K-slice partials of a sliced mul_mat (only where a caller wants the finished vector in memory;
 // inside a program the next op adds the slices itself while it builds its activation pack)
-__device__ __noinline__ void pg_sum(const PgParams &p, int o)
+__device__ __noinline__ void pg_sum(const PgParams *pp, int o, int qt)
 {
+    const PgParams &p = *pp;
+    const PgSmem sm = pg_smem(p, qt);
+    const int tagbase = sm.flag[6];
     const PgOp &op = p.ops[o];
     const int ctid = threadIdx.x;
     const int n4 = op.N / 4;
     for (int i = (int)blockIdx.x * PG_CTHREADS + ctid; i < n4; i += (int)gridDim.x * PG_CTHREADS)
-        reinterpret_cast<float4 *>(op.y)[i] = pg_src4(op.src[0], i * 4);
+        reinterpret_cast<float4 *>(op.y)[i] = pg_src4(op.src[0], i * 4, tagbase, p.err);
     for (int n = n4 * 4 + (int)blockIdx.x * PG_CTHREADS + ctid; n < op.N; n += (int)gridDim.x * PG_CTHREADS) {   // N % 4 tail
-        const float *b = static_cast<const float *>(op.src[0].ptr) + n;
-        float a = __ldcg(b);
-        for (int q = 1; q < op.src[0].np; q++) a += __ldcg(b + (size_t)q * op.src[0].stride);
-        op.y[n] = a * op.src[0].scale;
+        const PgSrc &sr = op.src[0];
+        float a = 0.f;
+        for (int q = 0; q < sr.np; q++) {
+            const size_t idx = (size_t)q * sr.stride + n;
+            a += (sr.kind & 255) == PG_SRC_TAG ? pg_ld_tag1(static_cast<const float *>(sr.ptr), idx, tagbase | ((sr.kind >> 8) + 1), p.err)
+                                               : __ldcg(static_cast<const float *>(sr.ptr) + idx);
+        }
+        op.y[n] = a * sr.scale;
     }
-    __threadfence();
-    pg_bar();
-    if (ctid == 0) atomicAdd(p.ctr + 1 + o, 1);
+    if (op.publish) {
+        __threadfence();
+        pg_bar();
+        if (ctid == 0) atomicAdd(p.ctr + 1 + o, 1);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Start of a mul_mat op on the consumer side: dependency wait + activation pack.  Returns the op's geometry.
 // ---------------------------------------------------------------------------------------------------------------
-struct PgGeom { int C, cbase, plane; };
-
+// waited_mv (the latest mul_mat op this CTA knows to be complete) lives in shared memory: sm.flag[1].
 template <int QT>
-__device__ __noinline__ PgGeom pg_begin_op(const PgParams &p, int o, int &waited_mv, float *s_x, uint8_t *s_aq, float *s_ap, double *s_stat)
+__device__ __noinline__ void pg_begin_op(const PgParams *pp, const PgOp *opp, int o, bool has_data)
 {
     constexpr int NP = (QT == 0) ? 2 : 3;
-    const PgOp &op = p.ops[o];
+    const PgParams &p = *pp;                                 // both in shared memory: nothing here may live on the stack
+    const PgOp &op = *opp;
+    const PgSmem sm = pg_smem(p, QT);
+    float *s_x = sm.x, *s_ap = sm.ap;
+    uint8_t *s_aq = sm.aq;
+    double *s_stat = sm.stat;
     const int ctid = threadIdx.x, lane = ctid & 31, warp = ctid >> 5;
     const bool sliced = op.PP > 1;
     const int cls = sliced ? (int)blockIdx.x % op.PP : 0;
@@ -356,17 +547,30 @@ __device__ __noinline__ PgGeom pg_begin_op(const PgParams &p, int o, int &waited
     const int nb_l = min(op.nb - blk0, nbp);
     const int plane = nbp;
     const int in_mode = op.in_mode, res = op.res, nsrc = op.nsrc, K = op.K;
+    // A CTA without a task of this op needs no activation pack; only an update of the residual stream has to happen
+    // everywhere (every CTA carries its own copy).
+    const bool res_update = in_mode == PG_IN_LN && (res == PG_RES_ADD || res == PG_RES_SET);
+    if (!has_data && !res_update) return;
+    // The pack of a run of ops with the same activation (Q, K, V: same input, same layer-norm weights) is built once.
+    // (flag[5] was written before a barrier every consumer thread has passed since.)
+    if (!res_update && sm.flag[5] == op.pack_of) return;
     pg_bar();                                                // every consumer warp is done with the previous op's pack
-    // records of padded blocks (weight scale 0, but 0 x garbage could be NaN) read as zero
-    for (int i = nb_l * 4 + ctid; i < nbp * 4; i += PG_CTHREADS) reinterpret_cast<uint2 *>(s_aq)[i] = make_uint2(0u, 0u);
-    for (int pl = 0; pl < NP; pl++)
-        for (int i = nb_l + ctid; i < nbp; i += PG_CTHREADS) s_ap[pl * plane + i] = 0.0f;
+    const int waited_mv = sm.flag[1];
+    const int tagbase = sm.flag[6];
+    int *err = p.err;
+    if (has_data) {
+        // records of padded blocks (weight scale 0, but 0 x garbage could be NaN) read as zero
+        for (int i = nb_l * 4 + ctid; i < nbp * 4; i += PG_CTHREADS) reinterpret_cast<uint2 *>(s_aq)[i] = make_uint2(0u, 0u);
+        for (int pl = 0; pl < NP; pl++)
+            for (int i = nb_l + ctid; i < nbp; i += PG_CTHREADS) s_ap[pl * plane + i] = 0.0f;
+    }
     const int dep = op.dep;
     if (dep >= 0 && dep > waited_mv) {
         if (ctid == 0) pg_wait_ctr(p.ctr + 1 + dep, (int)gridDim.x, p.err, o + 1);
-        pg_bar();
-        if (p.ops[dep].kind == PG_MATVEC) waited_mv = dep;   // a complete mul_mat op implies every earlier op is complete
+        pg_bar();                                            // (everybody has read flag[1] by now)
+        if (ctid == 0 && op.dep_mv) sm.flag[1] = dep;        // a complete mul_mat op implies every earlier op is complete
     }
+    if (ctid == 0) PG_STAMP(o, 2);
     auto block_sum = [&](double v) {
 #pragma unroll
         for (int of = 16; of > 0; of >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, of));
@@ -385,7 +589,7 @@ __device__ __noinline__ PgGeom pg_begin_op(const PgParams &p, int o, int &waited
         auto ln_in = [&](int k4) {
             float4 a = sx4[k4];
             if (res == PG_RES_TEMP) {
-                const float4 t = pg_sum_src4(op, nsrc, k4 * 4);
+                const float4 t = pg_sum_src4(op, nsrc, k4 * 4, tagbase, err);
                 a.x = __fadd_rn(a.x, t.x); a.y = __fadd_rn(a.y, t.y); a.z = __fadd_rn(a.z, t.z); a.w = __fadd_rn(a.w, t.w);
             }
             return a;
@@ -397,7 +601,7 @@ __device__ __noinline__ PgGeom pg_begin_op(const PgParams &p, int o, int &waited
                 float4 a;
                 if (res == PG_RES_TEMP) a = ln_in(k4);
                 else {
-                    a = pg_sum_src4(op, nsrc, k4 * 4);
+                    a = pg_sum_src4(op, nsrc, k4 * 4, tagbase, err);
                     if (res == PG_RES_ADD) {
                         const float4 x = sx4[k4];
                         a.x = __fadd_rn(x.x, a.x); a.y = __fadd_rn(x.y, a.y); a.z = __fadd_rn(x.z, a.z); a.w = __fadd_rn(x.w, a.w);
@@ -424,7 +628,7 @@ __device__ __noinline__ PgGeom pg_begin_op(const PgParams &p, int o, int &waited
         const double mean = s_stat[32];
         const float rstd = (float)s_stat[33];
         const float *lw = op.ln_w, *lb = op.ln_b;
-        for (int base = 0; base < items; base += PG_CTHREADS) {
+        for (int base = 0; has_data && base < items; base += PG_CTHREADS) {
             const int id = base + ctid;
             const bool valid = id < items;
             const int blk = valid ? id >> 2 : 0;
@@ -457,8 +661,8 @@ __device__ __noinline__ PgGeom pg_begin_op(const PgParams &p, int o, int &waited
             const int k = (blk0 + blk) * QK + (lane & 3) * 8;
             float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
             if (valid) {
-                lo = pg_sum_src4(op, nsrc, k);
-                hi = pg_sum_src4(op, nsrc, k + 4);
+                lo = pg_sum_src4(op, nsrc, k, tagbase, err);
+                hi = pg_sum_src4(op, nsrc, k + 4, tagbase, err);
                 if (in_mode == PG_IN_GELU) {
                     // ggml_gelu (ggml.c:819-827, GGML_GELU_FP16): x -> fp16 -> table -> fp32
                     auto gl = [&](float x) { return __half2float(__ushort_as_half(__ldg(tab + __half_as_ushort(__float2half_rn(x))))); };
@@ -469,210 +673,228 @@ __device__ __noinline__ PgGeom pg_begin_op(const PgParams &p, int o, int &waited
             quantize8_emit<QT>(lo, hi, valid, lane, s_aq + (size_t)blk * 32, s_ap + blk, plane);
         }
     }
+    if (ctid == 0 && has_data) { sm.flag[2] = op.C; sm.flag[3] = cbase; sm.flag[4] = plane; sm.flag[5] = op.pack_of; }
     pg_bar();
-    PgGeom gm;
-    gm.C = op.C; gm.cbase = cbase; gm.plane = plane;
-    return gm;
 }
 
-template <int QT>
-__global__ void __launch_bounds__(PG_THREADS, 1) q4_prog_kernel(const PgParams p)
+constexpr int PG_END = 1 << 30;                          // flag in a stage's op word: the CTA's last stage of that op
+
+__device__ __forceinline__ const PgOp &pg_cached_op(const PgSmem &sm, int o)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
+    return *reinterpret_cast<const PgOp *>(sm.opc + (size_t)(o & (PG_OPC - 1)) * PG_OPC_WORDS);
+}
+
+// Each role is an out-of-line function that derives its pointers from the parameter copy in shared memory: every role
+// gets its own register allocation, and nothing a role does not use stays live in another role's loop.
+
+// ===================== producer =====================
+// All 32 lanes keep the op cache filled (lane l < 21 carries 16 bytes of the NEXT mul_mat op while lane 0 issues the
+// copies of the current one); lane 0 alone talks to the stage ring.
+template <int QT>
+__device__ __noinline__ void pg_producer(const PgParams *pp)
+{
     constexpr int CH = chunk_bytes(QT);
     constexpr int STAGE_BYTES = PG_UNITS * CH;
-    uint8_t *s_stage = smem;
-    float   *s_red = reinterpret_cast<float *>(smem + (size_t)p.stages * STAGE_BYTES);
-    float   *s_x = s_red + (size_t)p.stages * PG_UNITS * PG_RW;
-    uint8_t *s_aq = reinterpret_cast<uint8_t *>(s_x + p.e_cap);
-    float   *s_ap = reinterpret_cast<float *>(s_aq + (size_t)p.nbp_cap * 32);
-    float   *s_att = s_ap + 3 * (size_t)p.nbp_cap;
-    double  *s_stat = reinterpret_cast<double *>(s_att + p.att_cap);
-    uint64_t *bar_full = reinterpret_cast<uint64_t *>(s_stat + 40);
-    uint64_t *bar_empty = bar_full + PG_MAX_STAGES;
-    uint64_t *bar_done = bar_empty + PG_MAX_STAGES;
-    int4     *s_desc = reinterpret_cast<int4 *>(bar_done + PG_MAX_STAGES);   // {units (-1 END of op, -2 STOP), first chunk index, first tile, task}
-    int      *s_dop = reinterpret_cast<int *>(s_desc + PG_MAX_STAGES);       // op index of the stage
-    int      *s_flag = s_dop + PG_MAX_STAGES + 2;
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PgParams &p = *pp;
+    const PgSmem sm = pg_smem(p, QT);
+    const int lane = threadIdx.x & 31;
     const int bid = (int)blockIdx.x, grid = (int)gridDim.x;
-
-    if (threadIdx.x < 3 * PG_MAX_STAGES) {
-        const int i = threadIdx.x % PG_MAX_STAGES, which = threadIdx.x / PG_MAX_STAGES;
-        if (i < p.stages) {
-            if (which == 0) mbar_init(&bar_full[i], 1);
-            else if (which == 1) mbar_init(&bar_empty[i], 1);
-            else mbar_init(&bar_done[i], GEMV_WARPS);
+    int s = 0;
+    uint32_t ph = 1;
+    auto put = [&](int cnt, int c0, int T, int task, int otag, const uint8_t *src) {
+        pg_mbar_wait(&sm.bar_empty[s], ph);
+        sm.desc[s] = make_int4(cnt, c0, T, task);
+        sm.dop[s] = otag;
+        if (cnt > 0) {
+            mbar_arrive_expect_tx(&sm.bar_full[s], (uint32_t)cnt * CH);
+            bulk_g2s(sm.stage + (size_t)s * STAGE_BYTES, src, (uint32_t)cnt * CH, &sm.bar_full[s]);
+        } else {
+            mbar_arrive(&sm.bar_full[s]);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+    };
+    auto fetch = [&](int o) {
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (o < p.n_ops && lane < PG_OPC_WORDS / 4) w = __ldg(reinterpret_cast<const uint4 *>(p.ops + o) + lane);
+        return w;
+    };
+    int o = p.first_mv;
+    uint4 cw = fetch(o);
+    int pre_ticket = 0;                                      // first ticket of op o, drawn while the previous op was issued
+    if (lane == 0 && o < p.n_ops) {
+        const PgOp &g0 = p.ops[o];
+        if (g0.dynamic) pre_ticket = atomicAdd(p.ctr + g0.tk_off + (g0.PP > 1 ? bid % g0.PP : 0), 1);
     }
-    __syncthreads();
-
-    if (warp == GEMV_WARPS) {
-        // ===================== producer =====================
+    while (o < p.n_ops) {
+        if (lane < PG_OPC_WORDS / 4) reinterpret_cast<uint4 *>(sm.opc + (size_t)(o & (PG_OPC - 1)) * PG_OPC_WORDS)[lane] = cw;
+        __syncwarp();
+        const PgOp &op = pg_cached_op(sm, o);
+        const int nxt_o = op.next_mv;
+        cw = fetch(nxt_o);                                   // lands while this op's tasks are issued
         if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 1;
-            auto put = [&](int cnt, int c0, int T, int task, int o, const uint8_t *src) {
-                pg_mbar_wait(&bar_empty[s], ph);
-                s_desc[s] = make_int4(cnt, c0, T, task);
-                s_dop[s] = o;
-                if (cnt > 0) {
-                    mbar_arrive_expect_tx(&bar_full[s], (uint32_t)cnt * CH);
-                    bulk_g2s(s_stage + (size_t)s * STAGE_BYTES, src, (uint32_t)cnt * CH, &bar_full[s]);
-                } else {
-                    mbar_arrive(&bar_full[s]);
+            PG_STAMP(o, 0);
+            int nx_ticket = 0;
+            if (nxt_o < p.n_ops && op.nx_dynamic) nx_ticket = atomicAdd(p.ctr + op.nx_tk_off + (op.nx_PP > 1 ? bid % op.nx_PP : 0), 1);
+            const uint8_t *wt = op.wt;
+            const int C = op.C, PP = op.PP, TS = op.TS, U = op.U, nstatic = op.nstatic;
+            const bool sliced = PP > 1;
+            const int cls = sliced ? bid % PP : 0, cbase = cls * TS;
+            const int ncls = sliced ? (grid - cls + PP - 1) / PP : grid;
+            int idx = (sliced ? bid / PP : bid) + op.rot;
+            idx -= (idx / ncls) * ncls;
+            const int limit = sliced ? op.n_tiles : op.ntasks;
+            // tasks are issued one behind, so that the CTA's last stage of the op can carry the END flag
+            int pend = -1;
+            auto issue = [&](int u0, int n, int T, int c0, int task, bool last_task) {
+                for (int r = 0; r < n; r += PG_UNITS) {
+                    const int cnt = min(PG_UNITS, n - r);
+                    put(cnt, c0, T, task, (last_task && r + PG_UNITS >= n) ? (o | PG_END) : o, wt + (size_t)(u0 + r) * CH);
+                    c0 += cnt;
+                    while (c0 >= C) { c0 -= C; ++T; }
                 }
-                if (++s == p.stages) { s = 0; ph ^= 1; }
             };
-            for (int o = 0; o < p.n_ops; o++) {
-                const PgOp &op = p.ops[o];
-                if (op.kind != PG_MATVEC) continue;
-                const uint8_t *wt = op.wt;
-                const int C = op.C, PP = op.PP, TS = op.TS, U = op.U, nstatic = op.nstatic;
-                const bool sliced = PP > 1;
-                const int cls = sliced ? bid % PP : 0, cbase = cls * TS;
-                const int idx = sliced ? bid / PP : bid;
-                const int ncls = sliced ? (grid - cls + PP - 1) / PP : grid;
-                const int limit = sliced ? op.n_tiles : op.ntasks;
-                auto issue = [&](int u0, int n, int T, int c0, int task) {
-                    for (int r = 0; r < n; r += PG_UNITS) {
-                        const int cnt = min(PG_UNITS, n - r);
-                        put(cnt, c0, T, task, o, wt + (size_t)(u0 + r) * CH);
-                        c0 += cnt;
-                        while (c0 >= C) { c0 -= C; ++T; }
-                    }
-                };
-                auto issue_seq = [&](int t) {
-                    if (sliced) issue(t * C + cbase, min(TS, C - cbase), t, cbase, t * PP + cls);
-                    else if (C >= PIPE_TILE_SPLIT) issue(t * C, C, t, 0, t);                 // one whole tile
-                    else issue(t * TS, min(TS, U - t * TS), t * (TS / C), 0, t);            // short tiles: TS / C whole tiles
-                };
-                for (int k = 0; k < nstatic; k++) {
-                    const int t = idx + k * ncls;
-                    if (t < limit) issue_seq(t);
-                }
+            auto issue_seq = [&](int t, bool last_task) {
+                if (sliced) issue(t * C + cbase, min(TS, C - cbase), t, cbase, t * PP + cls, last_task);
+                else if (C >= PIPE_TILE_SPLIT) issue(t * C, C, t, 0, t, last_task);               // one whole tile
+                else issue(t * TS, min(TS, U - t * TS), t * (TS / C), 0, t, last_task);          // short tiles: TS / C whole tiles
+            };
+            auto push = [&](int t) { if (pend >= 0) issue_seq(pend, false); pend = t; };
+            for (int k = 0; k < nstatic; k++) {
+                const int t = idx + k * ncls;
+                if (t < limit) push(t);
+            }
+            if (op.dynamic) {
                 int *tk = p.ctr + op.tk_off + cls;
                 const int base = nstatic * ncls;
-                int cur = base + atomicAdd(tk, 1);
+                int cur = base + pre_ticket;
                 while (cur < limit) {
-                    const int nxt = base + atomicAdd(tk, 1);       // one task ahead: the atomic's latency hides behind the copies
-                    issue_seq(cur);
+                    const int nxt = base + atomicAdd(tk, 1);   // one task ahead: the atomic's latency hides behind the copies
+                    push(cur);
                     cur = nxt;
                 }
-                put(-1, 0, 0, 0, o, nullptr);
             }
-            put(-2, 0, 0, 0, p.n_ops, nullptr);
+            if (pend >= 0) issue_seq(pend, true);
+            else put(0, 0, 0, 0, o | PG_END, nullptr);       // no task of this op for this CTA: a bare marker
+            pre_ticket = nx_ticket;
         }
-        return;
+        __syncwarp();
+        o = nxt_o;
     }
+    if (lane == 0) put(-2, 0, 0, 0, p.n_ops, nullptr);
+}
 
-    if (warp == GEMV_WARPS + 1) {
-        // ===================== reducer =====================
-        constexpr float post = (QT == 0) ? 0.0625f : 1.0f;   // undo the 16x of the A/B code scaling (exact)
-        float acc = 0.f;
-        int curT = -1, curTask = -1, curOp = -1;
-        float *y = nullptr;
-        const float *bias = nullptr;
-        int N = 0, C = 1, PP = 1, y_slice = 0;
-        const int rl = lane & 15;
-        auto emit = [&]() {
-            if (curT < 0) return;
-            const int n = curT * TILE_ROWS + lane;
-            if (lane < TILE_ROWS && n < N) {
-                if (PP == 1) y[n] = bias ? __fadd_rn(acc * post, __ldg(bias + n)) : acc * post;
-                else y[(size_t)(curTask - curT * PP) * y_slice + n] = acc * post;
+// ===================== reducer =====================
+template <int QT>
+__device__ __noinline__ void pg_reducer(const PgParams *pp)
+{
+    const PgParams &p = *pp;
+    const PgSmem sm = pg_smem(p, QT);
+    const int lane = threadIdx.x & 31;
+    constexpr float post = (QT == 0) ? 0.0625f : 1.0f;       // undo the 16x of the A/B code scaling (exact)
+    float acc = 0.f, bcur = 0.f;
+    int curT = -1, curTask = -1, curOp = -1;
+    float *y = nullptr, *y_plain = nullptr;
+    const float *bias = nullptr;
+    int N = 0, C = 1, PP = 1, y_slice = 0, ytag = 0, publish = 0;
+    const int rl = lane & 15;
+    const int tagbase = sm.flag[6];
+    auto emit = [&]() {
+        if (curT < 0) return;
+        const int n = curT * TILE_ROWS + lane;
+        if (lane < TILE_ROWS && n < N) {
+            const float v = (PP == 1 && bias) ? __fadd_rn(acc * post, bcur) : acc * post;
+            const size_t idx = PP == 1 ? (size_t)n : (size_t)(curTask - curT * PP) * y_slice + n;
+            if (ytag) st_tagged(y, idx, v, ytag);            // value and tag in one 8-byte store: the data is its own flag
+            else y[idx] = v;
+            if (y_plain) y_plain[n] = v;
+        }
+        curT = -1;
+    };
+    int s = 0;
+    uint32_t ph = 0;
+    for (;;) {
+        pg_mbar_wait(&sm.bar_done[s], ph);                   // every consumer warp has passed this slot (markers included)
+        const int4 dsc = sm.desc[s];
+        const int otag = sm.dop[s], o = otag & (PG_END - 1);
+        if (dsc.x == -2) break;
+        if (o != curOp) {
+            const PgOp &op = pg_cached_op(sm, o);
+            y = op.y; y_plain = op.y_plain; bias = op.bias; N = op.N; C = op.C; PP = op.PP; y_slice = op.y_slice;
+            ytag = op.y_tag ? (tagbase | (o + 1)) : 0; publish = op.publish;
+            curOp = o;
+        }
+        if (dsc.x > 0) {
+            const int task = dsc.w;
+            int T = dsc.z;
+            int left = C - dsc.y;
+            const float *red = sm.red + (size_t)s * PG_UNITS * PG_RW + rl;
+            int j = 0;
+            while (j < dsc.x) {
+                if (T != curT || task != curTask) {
+                    emit();
+                    acc = 0.f;
+                    curT = T; curTask = task;
+                    if (bias && PP == 1) {                   // asked for now, needed when the tile is complete
+                        const int n = T * TILE_ROWS + lane;
+                        bcur = (lane < TILE_ROWS && n < N) ? __ldg(bias + n) : 0.f;
+                    }
+                }
+                const int run = min(dsc.x - j, left);
+                if (run == PG_UNITS) {
+                    float v[PG_UNITS];
+#pragma unroll
+                    for (int k = 0; k < PG_UNITS; k++) v[k] = red[k * PG_RW];
+                    float q[PG_UNITS / 4];
+#pragma unroll
+                    for (int h = 0; h < PG_UNITS / 4; h++) q[h] = (v[4 * h] + v[4 * h + 1]) + (v[4 * h + 2] + v[4 * h + 3]);
+                    acc += ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+                } else {
+                    int k = j;
+                    for (; k + 4 <= j + run; k += 4)
+                        acc += (red[k * PG_RW] + red[(k + 1) * PG_RW]) + (red[(k + 2) * PG_RW] + red[(k + 3) * PG_RW]);
+                    for (; k < j + run; k++) acc += red[k * PG_RW];
+                }
+                j += run;
+                left -= run;
+                if (left == 0) { ++T; left = C; }
             }
-            curT = -1;
-        };
-        int s = 0;
-        uint32_t ph = 0;
-        for (;;) {
-            pg_mbar_wait(&bar_done[s], ph);                  // every consumer warp has passed this slot (markers included)
-            const int4 dsc = s_desc[s];
-            const int o = s_dop[s];
-            if (dsc.x == -2) break;
-            if (o != curOp) {
-                const PgOp &op = p.ops[o];
-                y = op.y; bias = op.bias; N = op.N; C = op.C; PP = op.PP; y_slice = op.y_slice;
-                curOp = o;
-            }
-            if (dsc.x < 0) {                                 // END of op o for this CTA: publish
-                emit();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.bar_empty[s]);        // the slot goes back to the producer before anything slow happens
+        if (otag & PG_END) {                                 // this CTA is done with op o: flush, and publish if somebody counts
+            emit();
+            if (publish) {
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) atomicAdd(p.ctr + 1 + o, 1);
-            } else {
-                const int task = dsc.w;
-                int T = dsc.z;
-                int left = C - dsc.y;
-                const float *red = s_red + (size_t)s * PG_UNITS * PG_RW + rl;
-                int j = 0;
-                while (j < dsc.x) {
-                    if (T != curT || task != curTask) {
-                        emit();
-                        acc = 0.f;
-                        curT = T; curTask = task;
-                    }
-                    const int run = min(dsc.x - j, left);
-                    if (run == PG_UNITS) {
-                        float v[PG_UNITS];
-#pragma unroll
-                        for (int k = 0; k < PG_UNITS; k++) v[k] = red[k * PG_RW];
-                        float q[PG_UNITS / 4];
-#pragma unroll
-                        for (int h = 0; h < PG_UNITS / 4; h++) q[h] = (v[4 * h] + v[4 * h + 1]) + (v[4 * h + 2] + v[4 * h + 3]);
-                        acc += ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
-                    } else {
-                        int k = j;
-                        for (; k + 4 <= j + run; k += 4)
-                            acc += (red[k * PG_RW] + red[(k + 1) * PG_RW]) + (red[(k + 2) * PG_RW] + red[(k + 3) * PG_RW]);
-                        for (; k < j + run; k++) acc += red[k * PG_RW];
-                    }
-                    j += run;
-                    left -= run;
-                    if (left == 0) { ++T; left = C; }
-                }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_empty[s]);
-            if (++s == p.stages) { s = 0; ph ^= 1; }
+            if (lane == 0) PG_STAMP(o, 5);
         }
-        // the last CTA to get here clears every counter for the next launch (nobody polls or draws any more:
-        // each CTA's consumers and producer are past their last use when its reducer sees STOP)
-        __syncwarp();
-        int last = 0;
-        if (lane == 0) { __threadfence(); last = atomicAdd(p.ctr, 1) == grid - 1; }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-            __threadfence();
-            for (int i = lane; i < p.n_ctr; i += 32) p.ctr[i] = 0;
-        }
-        return;
+        if (++s == p.stages) { s = 0; ph ^= 1; }
     }
+    // the last CTA to get here clears every counter for the next launch (nobody polls or draws any more:
+    // each CTA's consumers and producer are past their last use when its reducer sees STOP)
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) { __threadfence(); last = atomicAdd(p.ctr, 1) == (int)gridDim.x - 1; }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+        __threadfence();
+        for (int i = lane; i < p.n_ctr; i += 32) p.ctr[i] = 0;
+        if (lane == 0) p.dyn[2] = p.dyn[2] + 1;              // next launch, next epoch: this launch's tags become stale
+    }
+}
 
-    // ===================== consumers =====================
-    const int n_past = p.dyn ? p.dyn[1] : 0;
-    int s = 0;
-    uint32_t ph = 0;
-    int cur = -1, waited_mv = -1;
-    PgGeom gm;
-    gm.C = 1; gm.cbase = 0; gm.plane = 0;
-    auto run_attn_ops = [&](int from, int to) {
-        for (int a = from; a < to; a++) {
-            if (p.ops[a].kind == PG_MATVEC) continue;
-            const int dep = p.ops[a].dep;
-            if (dep >= 0 && dep > waited_mv) {
-                pg_bar();
-                if (threadIdx.x == 0) pg_wait_ctr(p.ctr + 1 + dep, grid, p.err, a + 1);
-                pg_bar();
-                if (p.ops[dep].kind == PG_MATVEC) waited_mv = dep;
-            }
-            if (p.ops[a].kind == PG_ATTN) pg_attn(p, a, n_past, s_att, s_flag);
-            else pg_sum(p, a);
-        }
-    };
+// ===================== consumers =====================
+// one stage: this warp's two units (an octet of quant blocks) against the activation pack
+template <int QT>
+__device__ __forceinline__ void pg_consume_stage(const PgSmem &sm, int gC, int gcbase, int gplane, int s, int cnt, int c0, int T0)
+{
+    constexpr int CH = chunk_bytes(QT);
+    constexpr int STAGE_BYTES = PG_UNITS * CH;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint8_t *s_aq = sm.aq;
+    const float *s_ap = sm.ap;
     const int uA = 2 * warp, uB = uA + 1;
     auto put_rows = [&](float *slot, float v0, float v2) {
         v0 += __shfl_xor_sync(0xffffffffu, v0, 1); v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
@@ -680,46 +902,116 @@ __global__ void __launch_bounds__(PG_THREADS, 1) q4_prog_kernel(const PgParams p
         const int g = lane >> 2, t = lane & 3;
         if (t < 2) slot[g + 8 * t] = t ? v2 : v0;
     };
-    for (;;) {
-        pg_mbar_wait(&bar_full[s], ph);
-        const int4 dsc = s_desc[s];
-        const int o = s_dop[s];
-        if (o != cur) {
-            run_attn_ops(cur + 1, o);                        // (STOP carries o = n_ops: trailing attention ops run too)
-            if (dsc.x != -2) gm = pg_begin_op<QT>(p, o, waited_mv, s_x, s_aq, s_ap, s_stat);
-            cur = o;
+    const bool hA = uA < cnt, hB = uB < cnt;
+    int TA = T0, TB = T0;
+    int cA = c0 + uA, cB = c0 + uB;
+    while (cA >= gC) { cA -= gC; ++TA; }
+    while (cB >= gC) { cB -= gC; ++TB; }
+    const uint8_t *chA = sm.stage + (size_t)s * STAGE_BYTES + (size_t)uA * CH, *chB = chA + CH;
+    float *slotA = sm.red + ((size_t)s * PG_UNITS + uA) * PG_RW, *slotB = slotA + PG_RW;
+    if (hA && hB && TA == TB && !(cA & 1)) {                 // an aligned octet: the common case
+        float v0, v2;
+        compute_octet<QT, false>(chA, chB, (cA - gcbase) >> 1, s_aq, s_ap, gplane, lane, v0, v2);
+        put_rows(slotA, v0, v2);
+        if (lane < TILE_ROWS) slotB[lane] = 0.f;
+    } else {                                                 // half octets (odd start, tile boundary, ragged tail)
+        if (hA) {
+            float v0, v2;
+            compute_octet<QT, false>((cA & 1) ? nullptr : chA, (cA & 1) ? chA : nullptr, (cA - gcbase) >> 1, s_aq, s_ap, gplane, lane, v0, v2);
+            put_rows(slotA, v0, v2);
         }
-        if (dsc.x > 0) {
-            const bool hA = uA < dsc.x, hB = uB < dsc.x;
-            int TA = dsc.z, TB = dsc.z;
-            int cA = dsc.y + uA, cB = dsc.y + uB;
-            while (cA >= gm.C) { cA -= gm.C; ++TA; }
-            while (cB >= gm.C) { cB -= gm.C; ++TB; }
-            const uint8_t *chA = s_stage + (size_t)s * STAGE_BYTES + (size_t)uA * CH, *chB = chA + CH;
-            float *slotA = s_red + ((size_t)s * PG_UNITS + uA) * PG_RW, *slotB = slotA + PG_RW;
-            if (hA && hB && TA == TB && !(cA & 1)) {         // an aligned octet: the common case
-                float v0, v2;
-                compute_octet<QT, false>(chA, chB, (cA - gm.cbase) >> 1, s_aq, s_ap, gm.plane, lane, v0, v2);
-                put_rows(slotA, v0, v2);
-                if (lane < TILE_ROWS) slotB[lane] = 0.f;
-            } else {                                         // half octets (odd start, tile boundary, ragged tail)
-                if (hA) {
-                    float v0, v2;
-                    compute_octet<QT, false>((cA & 1) ? nullptr : chA, (cA & 1) ? chA : nullptr, (cA - gm.cbase) >> 1, s_aq, s_ap, gm.plane, lane, v0, v2);
-                    put_rows(slotA, v0, v2);
-                }
-                if (hB) {
-                    float v0, v2;
-                    compute_octet<QT, false>((cB & 1) ? nullptr : chB, (cB & 1) ? chB : nullptr, (cB - gm.cbase) >> 1, s_aq, s_ap, gm.plane, lane, v0, v2);
-                    put_rows(slotB, v0, v2);
-                }
-            }
+        if (hB) {
+            float v0, v2;
+            compute_octet<QT, false>((cB & 1) ? nullptr : chB, (cB & 1) ? chB : nullptr, (cB - gcbase) >> 1, s_aq, s_ap, gplane, lane, v0, v2);
+            put_rows(slotB, v0, v2);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_done[s]);
-        if (dsc.x == -2) break;
-        if (++s == p.stages) { s = 0; ph ^= 1; }
     }
+}
+
+// The stages of ONE op, from slot s on, up to and including the CTA's last stage of that op (END flag) or the STOP
+// marker: a loop without calls, so that its state stays in registers.  Returns the next slot | parity << 8 | stop << 9.
+template <int QT>
+__device__ __noinline__ int pg_consume_op(const PgParams *pp, int s, uint32_t ph)
+{
+    const PgSmem sm = pg_smem(*pp, QT);
+    const int stages = pp->stages;
+    const int lane = threadIdx.x & 31;
+    const int gC = sm.flag[2], gcbase = sm.flag[3], gplane = sm.flag[4];     // the op's geometry, left by pg_begin_op
+    for (;;) {
+        pg_mbar_wait(&sm.bar_full[s], ph);
+        const int4 dsc = sm.desc[s];
+        const int otag = sm.dop[s];
+        if (dsc.x > 0) pg_consume_stage<QT>(sm, gC, gcbase, gplane, s, dsc.x, dsc.y, dsc.z);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.bar_done[s]);
+        const bool stop = dsc.x == -2;
+        if (!stop && ++s == stages) { s = 0; ph ^= 1; }
+        if (stop || (otag & PG_END)) return s | (int)(ph << 8) | (stop ? 1 << 9 : 0);
+    }
+}
+
+template <int QT>
+__device__ __noinline__ void pg_consumer(const PgParams *pp)
+{
+    const PgParams &p = *pp;
+    const PgSmem sm = pg_smem(p, QT);
+    int s = 0;
+    uint32_t ph = 0;
+    int cur = -1;
+    for (;;) {
+        pg_mbar_wait(&sm.bar_full[s], ph);                   // peek: which op does the next stage belong to?
+        const int4 dsc = sm.desc[s];
+        const int o = sm.dop[s] & (PG_END - 1);
+        for (int a = cur + 1; a < o; a++) {                  // side ops between two mul_mats (STOP carries o = n_ops: trailing ones too)
+            const int kind = p.ops[a].kind;
+            if (kind == PG_MATVEC) continue;
+            const int dep = p.ops[a].dep;
+            pg_bar();
+            const int wmv = sm.flag[1];
+            if (dep >= 0 && dep > wmv) {
+                if (threadIdx.x == 0) pg_wait_ctr(p.ctr + 1 + dep, (int)gridDim.x, p.err, a + 1);
+                pg_bar();                                    // (everybody has read flag[1] by now)
+                if (threadIdx.x == 0 && p.ops[dep].kind == PG_MATVEC) sm.flag[1] = dep;
+            }
+            if (kind == PG_ATTN) pg_attn(pp, a, QT);
+            else pg_sum(pp, a, QT);
+        }
+        if (dsc.x != -2) {
+            if (threadIdx.x == 0) PG_STAMP(o, 1);
+            pg_begin_op<QT>(pp, &pg_cached_op(sm, o), o, dsc.x > 0);
+            if (threadIdx.x == 0) PG_STAMP(o, 3);
+        }
+        cur = o;
+        const int r = pg_consume_op<QT>(pp, s, ph);
+        if (r & (1 << 9)) break;
+        s = r & 255; ph = (uint32_t)(r >> 8) & 1u;
+    }
+}
+
+template <int QT>
+__global__ void __launch_bounds__(PG_THREADS, 1) q4_prog_kernel(const PgParams p)
+{
+    __shared__ PgParams s_p;                                 // what the roles read (a by-reference kernel parameter would be copied to the stack)
+    const PgSmem sm = pg_smem(p, QT);
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x < 3 * PG_MAX_STAGES) {
+        const int i = threadIdx.x % PG_MAX_STAGES, which = threadIdx.x / PG_MAX_STAGES;
+        if (i < p.stages) {
+            if (which == 0) mbar_init(&sm.bar_full[i], 1);
+            else if (which == 1) mbar_init(&sm.bar_empty[i], 1);
+            else mbar_init(&sm.bar_done[i], GEMV_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x == PG_THREADS - 1) {
+        s_p = p;
+        sm.flag[1] = -1; sm.flag[5] = -1;
+        sm.flag[6] = (int)(((unsigned)p.dyn[2] & 0x7ffffu) << 12);           // tag = epoch << 12 | (op index + 1)
+    }
+    __syncthreads();
+    if (warp == GEMV_WARPS) pg_producer<QT>(&s_p);
+    else if (warp == GEMV_WARPS + 1) pg_reducer<QT>(&s_p);
+    else pg_consumer<QT>(&s_p);
 }
 
 #endif // Q4_PROG_TYPES_ONLY

@@ -3,6 +3,7 @@
 #include "q4_prog_host.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace b200q4 {
@@ -35,7 +36,8 @@ PgGeo pg_geometry(const b200q4_weight *w)
 }
 
 int ProgBuild::add_matvec(const b200q4_weight *w, int dep, int in_mode, int res, const PgSrc *src, int nsrc,
-                          const float *ln_w, const float *ln_b, const uint16_t *gelu_tab, float *y, const float *bias, int y_slice)
+                          const float *ln_w, const float *ln_b, const uint16_t *gelu_tab, float *y, const float *bias, int y_slice,
+                          bool y_tag, bool same_pack, float *y_plain)
 {
     if (!w || w->transposed || !w->d_wt || w->N < 1 || w->K < QK) return api_fail(B200Q4_EINVAL, "program: bad weight");
     if (qt < 0) qt = w->type;
@@ -53,16 +55,38 @@ int ProgBuild::add_matvec(const b200q4_weight *w, int dep, int in_mode, int res,
     op.kind = PG_MATVEC; op.dep = dep;
     op.wt = w->d_wt; op.C = w->C; op.n_tiles = w->n_tiles; op.N = w->N; op.nb = w->nb; op.U = w->n_tiles * w->C;
     op.PP = g.PP; op.TS = g.TS; op.ntasks = g.ntasks;
-    // static tasks: all but (at least) the last task of a CTA; small ops are dealt out by tickets alone so that
-    // whoever is ahead takes more
-    const int ncls = g.PP > 1 ? grid / g.PP : grid;
-    const int per = (g.PP > 1 ? w->n_tiles : g.ntasks) / (ncls > 0 ? ncls : 1);
-    op.nstatic = per - 1 < 0 ? 0 : per - 1 > PIPE_STATIC_TASKS ? PIPE_STATIC_TASKS : per - 1;
+    // Scheduling.  Small ops (<= 3 tasks per CTA) are dealt out statically -- no atomics on their short critical path --
+    // with a rotation that moves the CTAs holding one task more from op to op; large ops take their first tasks
+    // statically and the tail from a ticket counter, so that whoever is ahead takes more.
+    const int ncls = g.PP > 1 ? grid / g.PP : grid;      // CTAs per K-slice class (at least)
+    const int limit = g.PP > 1 ? w->n_tiles : g.ntasks;
+    const int per_up = (limit + ncls - 1) / ncls;
+    if (per_up <= PIPE_STATIC_TASKS) {
+        op.nstatic = per_up; op.dynamic = 0;
+        op.rot = rot_acc % ncls;
+        rot_acc += limit % ncls;
+    } else {
+        op.nstatic = PIPE_STATIC_TASKS < limit / ncls - 1 ? PIPE_STATIC_TASKS : limit / ncls - 1;
+        op.dynamic = 1; op.rot = 0;
+    }
     op.tk_off = n_tk; n_tk += g.PP;
     op.in_mode = in_mode; op.res = res; op.nsrc = nsrc; op.K = w->K;
     for (int i = 0; i < nsrc; i++) op.src[i] = src[i];
     op.ln_w = ln_w; op.ln_b = ln_b; op.gelu_tab = gelu_tab;
     op.y = y; op.bias = bias; op.y_slice = y_slice;
+    op.dep_mv = dep >= 0 && ops[(size_t)dep].kind == PG_MATVEC;
+    op.y_tag = y_tag ? 1 : 0;
+    op.y_plain = g.PP == 1 ? y_plain : nullptr;
+    if (ops.size() >= 4095) return api_fail(B200Q4_EINVAL, "program: too many ops");
+    op.pack_of = (int)ops.size();
+    if (same_pack) {
+        if (last_mv < 0) return api_fail(B200Q4_EINVAL, "program: same_pack without a previous mul_mat");
+        const PgOp &pv = ops[(size_t)last_mv];
+        if (pv.K != op.K || pv.PP != op.PP || pv.TS != op.TS || pv.C != op.C || res != PG_RES_KEEP)
+            return api_fail(B200Q4_EINVAL, "program: same_pack ops must share their input geometry");
+        op.pack_of = pv.pack_of;
+    }
+    last_mv = (int)ops.size();
     const int nbp = g.PP > 1 ? g.TS * CHUNK_BLKS : ((w->C * CHUNK_BLKS + 7) & ~7);
     if (nbp > nbp_cap) nbp_cap = nbp;
     if (in_mode == PG_IN_LN && w->K > e_cap) e_cap = w->K;
@@ -70,8 +94,9 @@ int ProgBuild::add_matvec(const b200q4_weight *w, int dep, int in_mode, int res,
     return (int)ops.size() - 1;
 }
 
-int ProgBuild::add_attn(int dep, const float *q, const float *k, const float *v, float *mem_k, float *mem_v, float *att_out,
-                        float *att_part, const double2 *rope, int H, int d, int n_rot, int n_ctx, float scale)
+int ProgBuild::add_attn(int dep, const float *q, const float *k, const float *v, int tq, int tk, int tv, float *mem_k, float *mem_v, float *att_out,
+                        float *att_part, float *att_sc, double *att_sum, const double2 *rope, const uint16_t *exp_tab,
+                        int H, int d, int n_rot, int n_ctx, float scale)
 {
     if (H < 1 || d < 1 || d > PG_ATT_MAX_D || n_rot < 0 || n_rot % 2 || n_rot > d || n_ctx < 1 || dep >= (int)ops.size())
         return api_fail(B200Q4_EINVAL, "program: bad attention op (H=%d d=%d n_rot=%d)", H, d, n_rot);
@@ -79,8 +104,10 @@ int ProgBuild::add_attn(int dep, const float *q, const float *k, const float *v,
     memset(&op, 0, sizeof op);
     op.kind = PG_ATTN; op.dep = dep;
     op.q = q; op.k = k; op.v = v; op.mem_k = mem_k; op.mem_v = mem_v; op.att_out = att_out; op.att_part = att_part; op.rope = rope;
+    op.att_sc = att_sc; op.att_sum = att_sum; op.exp_tab = exp_tab; op.n_ctx = n_ctx;
+    op.tq = tq; op.tk = tk; op.tv = tv;
     op.H = H; op.d = d; op.n_rot = n_rot; op.max_chunks = (n_ctx + PG_ATT_CHUNK - 1) / PG_ATT_CHUNK;
-    op.cnt_off = n_cnt; n_cnt += H;
+    op.cnt_off = n_cnt; n_cnt += 2 * H;
     op.att_scale = scale;
     const int need = 3 * ((d + 3) & ~3) + PG_ATT_CHUNK + 8 + PG_CTHREADS;
     if (need > att_cap) att_cap = need;
@@ -98,10 +125,14 @@ int ProgBuild::add_sum(int dep, const PgSrc &src, float *y, int N)
     return (int)ops.size() - 1;
 }
 
+// dynamic shared memory the kernel may use: the opt-in limit minus its static shared memory (the parameter copy)
 template <int QT>
-static int set_attr(int smem_optin)
+static int set_attr(int smem_optin, int *avail)
 {
-    PCK(cudaFuncSetAttribute(q4_prog_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+    cudaFuncAttributes fa;
+    PCK(cudaFuncGetAttributes(&fa, q4_prog_kernel<QT>));
+    *avail = smem_optin - (int)fa.sharedSizeBytes;
+    PCK(cudaFuncSetAttribute(q4_prog_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, *avail));
     return B200Q4_OK;
 }
 
@@ -113,10 +144,12 @@ int prog_finalize(const ProgBuild &b, Prog &out)
     Prog pg;
     pg.qt = b.qt; pg.grid = di.sms; pg.n_ops = (int)b.ops.size();
     pg.e_cap = (b.e_cap + 3) & ~3; pg.nbp_cap = (b.nbp_cap + 7) & ~7; pg.att_cap = (b.att_cap + 3) & ~3;
+    int avail = 0;
+    if (int rc = (pg.qt == 0 ? set_attr<0>(di.smem_optin, &avail) : set_attr<1>(di.smem_optin, &avail))) return rc;
     const size_t fixed = pg_fixed_bytes(pg.e_cap, pg.nbp_cap, pg.att_cap), stage = pg_stage_bytes(pg.qt);
-    if (fixed + 2 * stage > (size_t)di.smem_optin)
+    if (fixed + 2 * stage > (size_t)avail)
         return api_fail(B200Q4_EINVAL, "program: %zu bytes of per-CTA state leave no room for two weight stages", fixed);
-    long st = (long)(((size_t)di.smem_optin - fixed) / stage);
+    long st = (long)(((size_t)avail - fixed) / stage);
     pg.stages = (int)(st > PG_MAX_STAGES ? PG_MAX_STAGES : st);
     pg.smem = fixed + (size_t)pg.stages * stage;
     for (const PgOp &op : b.ops) if (op.kind == PG_MATVEC) pg.n_matvec++;
@@ -124,8 +157,16 @@ int prog_finalize(const ProgBuild &b, Prog &out)
     std::vector<PgOp> ops = b.ops;
     const int tk0 = 1 + pg.n_ops, cnt0 = tk0 + b.n_tk;
     for (PgOp &op : ops) { if (op.kind == PG_MATVEC) op.tk_off += tk0; if (op.kind == PG_ATTN) op.cnt_off += cnt0; }
+    for (const PgOp &op : b.ops) if (op.dep >= 0) ops[(size_t)op.dep].publish = 1;     // only ops somebody waits for are counted
+    int nxt = pg.n_ops;                                  // chain the mul_mat ops for the producer
+    for (int i = pg.n_ops - 1; i >= 0; i--) {
+        PgOp &op = ops[(size_t)i];
+        op.next_mv = nxt;
+        if (nxt < pg.n_ops) { op.nx_tk_off = ops[(size_t)nxt].tk_off; op.nx_PP = ops[(size_t)nxt].PP; op.nx_dynamic = ops[(size_t)nxt].dynamic; }
+        if (op.kind == PG_MATVEC) nxt = i;
+    }
+    pg.first_mv = nxt;
     pg.n_ctr = cnt0 + b.n_cnt;
-    if (int rc = (pg.qt == 0 ? set_attr<0>(di.smem_optin) : set_attr<1>(di.smem_optin))) return rc;
     PCK(cudaMalloc(&pg.d_ops, ops.size() * sizeof(PgOp)));
     if (cudaMalloc(&pg.d_ctr, (size_t)pg.n_ctr * sizeof(int)) != cudaSuccess || cudaMalloc(&pg.d_dyn, 16) != cudaSuccess ||
         cudaMalloc(&pg.d_err, 16) != cudaSuccess) {
@@ -133,10 +174,19 @@ int prog_finalize(const ProgBuild &b, Prog &out)
         prog_free(pg);
         return api_fail(B200Q4_ENOMEM, "program: device allocation failed");
     }
+    for (PgOp &op : ops)                                  // embedding rows are selected by the token id in dyn[0]
+        for (int i = 0; i < op.nsrc; i++)
+            if (op.src[i].kind == PG_SRC_Q4ROW && !op.src[i].row) op.src[i].row = pg.d_dyn;
     cudaError_t e = cudaMemcpy(pg.d_ops, ops.data(), ops.size() * sizeof(PgOp), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(pg.d_ctr, 0, (size_t)pg.n_ctr * sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(pg.d_dyn, 0, 16);
+    const int dyn0[4] = {0, 0, 1, 0};                    // epoch 1: zeroed buffers never carry a valid tag
+    if (e == cudaSuccess) e = cudaMemcpy(pg.d_dyn, dyn0, 16, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(pg.d_err, 0, 16);
+    if (e == cudaSuccess && getenv("B200Q4_DBG") && atoi(getenv("B200Q4_DBG")) != 0) {    // timeline builds only (-DB200Q4_TIMELINE)
+        const size_t n = (size_t)pg.grid * pg.n_ops * 8 * sizeof(unsigned long long);
+        e = cudaMalloc(&pg.d_dbg, n);
+        if (e == cudaSuccess) e = cudaMemset(pg.d_dbg, 0, n);
+    }
     if (e != cudaSuccess) { prog_free(pg); return api_fail(B200Q4_ECUDA, "program: upload failed: %s", cudaGetErrorString(e)); }
     out = pg;
     return B200Q4_OK;
@@ -145,7 +195,7 @@ int prog_finalize(const ProgBuild &b, Prog &out)
 int prog_launch(const Prog &pg, cudaStream_t st)
 {
     PgParams p;
-    p.ops = pg.d_ops; p.n_ops = pg.n_ops; p.ctr = pg.d_ctr; p.n_ctr = pg.n_ctr; p.dyn = pg.d_dyn; p.err = pg.d_err;
+    p.ops = pg.d_ops; p.n_ops = pg.n_ops; p.first_mv = pg.first_mv; p.dbg = pg.d_dbg; p.ctr = pg.d_ctr; p.n_ctr = pg.n_ctr; p.dyn = pg.d_dyn; p.err = pg.d_err;
     p.stages = pg.stages; p.e_cap = pg.e_cap; p.nbp_cap = pg.nbp_cap; p.att_cap = pg.att_cap;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pg.grid); cfg.blockDim = dim3(PG_THREADS); cfg.dynamicSmemBytes = pg.smem; cfg.stream = st;
@@ -161,7 +211,7 @@ int prog_launch(const Prog &pg, cudaStream_t st)
 
 void prog_free(Prog &pg)
 {
-    cudaFree(pg.d_ops); cudaFree(pg.d_ctr); cudaFree(pg.d_dyn); cudaFree(pg.d_err);
+    cudaFree(pg.d_ops); cudaFree(pg.d_ctr); cudaFree(pg.d_dyn); cudaFree(pg.d_err); cudaFree(pg.d_dbg);
     pg = Prog{};
 }
 
@@ -184,9 +234,14 @@ b200q4_chain *b200q4_chain_create(int n, const b200q4_weight *const *ws, const f
     if (n < 1 || !ws || !d_x || !d_y) { api_fail(B200Q4_EINVAL, "chain_create: bad argument"); return nullptr; }
     b200q4_chain *c = new b200q4_chain();
     ProgBuild b;
-    struct Out { const float *y; int N, PP, stride; float *part; int op; };
+    // An op whose output a later op of the chain reads keeps it in an internal buffer of {value, tag} pairs (the reader
+    // polls the data itself: no fence, no counter); the caller's plain d_y is filled from it at the end of the list.
+    struct Out { const float *y; int N, PP, stride; float *buf; bool tagged; int op; };
     std::vector<Out> outs((size_t)n);
     auto bail = [&]() { for (float *p : c->partials) cudaFree(p); delete c; return (b200q4_chain *)nullptr; };
+    auto reads = [&](int i, int j) {                      // does op i read from the output of op j?
+        return d_x[i] >= d_y[j] && d_x[i] + ws[i]->K <= d_y[j] + ws[j]->N;
+    };
     for (int i = 0; i < n; i++) {
         const b200q4_weight *w = ws[i];
         if (!w || w->transposed || !d_x[i] || !d_y[i] || (deps && (deps[i] >= i || deps[i] < -1))) {
@@ -197,34 +252,45 @@ b200q4_chain *b200q4_chain_create(int n, const b200q4_weight *const *ws, const f
             api_fail(B200Q4_EINVAL, "chain_create: op %d: x and y must be 16-byte aligned", i);
             return bail();
         }
-        // the input: caller memory, or -- when it lies inside the output of an earlier K-sliced op -- that op's partials
+    }
+    for (int i = 0; i < n; i++) {
+        const b200q4_weight *w = ws[i];
+        int from = -1;
+        for (int j = i - 1; j >= 0 && from < 0; j--) if (reads(i, j)) from = j;         // the latest writer of that memory
         PgSrc src = pg_src_f32(d_x[i]);
-        for (int j = 0; j < i; j++)
-            if (outs[(size_t)j].PP > 1 && d_x[i] >= outs[(size_t)j].y && d_x[i] + w->K <= outs[(size_t)j].y + outs[(size_t)j].N)
-                src = pg_src_f32(outs[(size_t)j].part + (d_x[i] - outs[(size_t)j].y), outs[(size_t)j].PP, outs[(size_t)j].stride);
+        if (from >= 0) {
+            const Out &f = outs[(size_t)from];
+            src = pg_src_tag(f.buf + 2 * (d_x[i] - f.y), f.op, f.PP, f.stride);
+        }
+        // a dependency that is not simply "reads its output" still goes through the arrival counters
+        const int dep = deps && deps[i] >= 0 && deps[i] != from ? outs[(size_t)deps[i]].op : -1;
         const PgGeo g = pg_geometry(w);
-        Out o{d_y[i], w->N, g.PP, 0, nullptr, -1};
+        bool read_later = false;
+        for (int k = i + 1; k < n && !read_later; k++) if (ws[k] && reads(k, i)) read_later = true;
+        Out o{d_y[i], w->N, g.PP, 0, nullptr, read_later || g.PP > 1, -1};
         float *y = d_y[i];
-        if (g.PP > 1) {
+        if (o.tagged) {
             o.stride = (w->N + 3) & ~3;
-            if (cudaMalloc(&o.part, (size_t)g.PP * o.stride * sizeof(float)) != cudaSuccess) {
+            if (cudaMalloc(&o.buf, (size_t)g.PP * o.stride * 2 * sizeof(float)) != cudaSuccess) {
                 cudaGetLastError();
                 api_fail(B200Q4_ENOMEM, "chain_create: cudaMalloc failed");
                 return bail();
             }
-            c->partials.push_back(o.part);
-            y = o.part;
+            cudaMemset(o.buf, 0, (size_t)g.PP * o.stride * 2 * sizeof(float));
+            c->partials.push_back(o.buf);
+            y = o.buf;
         }
-        const int dep = deps && deps[i] >= 0 ? outs[(size_t)deps[i]].op : -1;
-        o.op = b.add_matvec(w, dep, PG_IN_PLAIN, PG_RES_KEEP, &src, 1, nullptr, nullptr, nullptr, y, nullptr, o.stride);
+        // (an unsliced op stores the caller's plain copy itself, next to the tagged one)
+        o.op = b.add_matvec(w, dep, PG_IN_PLAIN, PG_RES_KEEP, &src, 1, nullptr, nullptr, nullptr, y, nullptr, o.stride, o.tagged, false,
+                            o.tagged ? d_y[i] : nullptr);
         if (o.op < 0) return bail();
         outs[(size_t)i] = o;
     }
-    // the finished vectors of K-sliced ops, summed at the end of the list (nobody inside the list waits for them)
-    for (int i = 0; i < n; i++)
-        if (outs[(size_t)i].PP > 1 &&
-            b.add_sum(outs[(size_t)i].op, pg_src_f32(outs[(size_t)i].part, outs[(size_t)i].PP, outs[(size_t)i].stride), d_y[i], outs[(size_t)i].N) < 0)
-            return bail();
+    // the caller's copies of the internally kept outputs, at the end of the list (nobody inside the list waits for them)
+    for (int i = 0; i < n; i++) {
+        const Out &o = outs[(size_t)i];
+        if (o.tagged && o.PP > 1 && b.add_sum(-1, pg_src_tag(o.buf, o.op, o.PP, o.stride), d_y[i], o.N) < 0) return bail();
+    }
     if (prog_finalize(b, c->pg)) return bail();
     return c;
 }
@@ -234,6 +300,16 @@ int b200q4_chain_run(b200q4_chain *c, void *stream)
     ApiLock lk;
     if (!c) return api_fail(B200Q4_EINVAL, "chain_run: NULL chain");
     return prog_launch(c->pg, stream ? (cudaStream_t)stream : dev_info().stream);
+}
+
+/* development aid (timeline builds): copies the [grid][n_ops][8] stamps of the last run; returns grid or a negative error */
+int b200q4_chain_timeline(const b200q4_chain *c, unsigned long long *out, size_t cap_words)
+{
+    if (!c || !c->pg.d_dbg) return B200Q4_EINVAL;
+    const size_t n = (size_t)c->pg.grid * c->pg.n_ops * 8;
+    if (cap_words < n) return B200Q4_EINVAL;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(out, c->pg.d_dbg, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? c->pg.grid : B200Q4_ECUDA;
 }
 
 int b200q4_chain_info(const b200q4_chain *c, int *n_ops, int *stages, size_t *smem_bytes)

@@ -16,23 +16,32 @@ struct ProgBuild {
     int qt = -1;                         // quant type shared by every mul_mat of the program
     std::vector<PgOp> ops;
     int n_tk = 0, n_cnt = 0;             // ticket counters / attention head counters handed out so far
+    int rot_acc = 0;                     // running rotation of the static task assignment
+    int last_mv = -1;                    // previous mul_mat op (pack reuse)
     int e_cap = 4, nbp_cap = 8, att_cap = 4;
     // Appends Y = W . quantize(in(sources)); returns the op index or a negative error.  For a K-sliced weight
-    // (pg_geometry(w).PP > 1) y receives PP slices of raw sums, y_slice floats apart, and bias must be NULL.
+    // (pg_geometry(w).PP > 1) y receives PP slices of raw sums, y_slice elements apart, and bias must be NULL.
+    // y_tag: y holds {value, tag} pairs (8 bytes per element) that later ops of the list read as PG_SRC_TAG sources;
+    // same_pack: the activation is that of the previous mul_mat op (same input, mode, layer-norm weights): built once.
     int add_matvec(const b200q4_weight *w, int dep, int in_mode, int res, const PgSrc *src, int nsrc,
-                   const float *ln_w, const float *ln_b, const uint16_t *gelu_tab, float *y, const float *bias, int y_slice);
-    int add_attn(int dep, const float *q, const float *k, const float *v, float *mem_k, float *mem_v, float *att_out,
-                 float *att_part, const double2 *rope, int H, int d, int n_rot, int n_ctx, float scale);
+                   const float *ln_w, const float *ln_b, const uint16_t *gelu_tab, float *y, const float *bias, int y_slice,
+                   bool y_tag = false, bool same_pack = false, float *y_plain = nullptr);
+    // att_part [H][chunks][d], att_sc [H][n_ctx + chunks], att_sum [H][chunks] (chunks = ceil(n_ctx / PG_ATT_CHUNK)): scratch
+    // q, k, v: tagged vectors written by ops tq, tk, tv; att_out: tagged
+    int add_attn(int dep, const float *q, const float *k, const float *v, int tq, int tk, int tv, float *mem_k, float *mem_v, float *att_out,
+                 float *att_part, float *att_sc, double *att_sum, const double2 *rope, const uint16_t *exp_tab,
+                 int H, int d, int n_rot, int n_ctx, float scale);
     int add_sum(int dep, const PgSrc &src, float *y, int N);
 };
 
 struct Prog {
     PgOp *d_ops = nullptr;
-    int   n_ops = 0, n_matvec = 0;
+    int   n_ops = 0, n_matvec = 0, first_mv = 0;
     int  *d_ctr = nullptr;
     int   n_ctr = 0;
-    int  *d_dyn = nullptr;               // [0] token id, [1] n_past
+    int  *d_dyn = nullptr;               // [0] token id, [1] n_past, [2] launch epoch
     int  *d_err = nullptr;
+    unsigned long long *d_dbg = nullptr; // timeline (development builds)
     int   qt = 0, stages = 0, grid = 0, e_cap = 0, nbp_cap = 0, att_cap = 0;
     size_t smem = 0;
 };
