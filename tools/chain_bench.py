@@ -45,16 +45,17 @@ def time_chain(L, chain, reps, warm=3):
     return e0.elapsed_time(e1) / reps
 
 
-def micro(L, rng, qt, dep, n=16384, k=4096, nw=10):
+def micro(L, rng, qt, dep, n=16384, k=4096, nw=10, distinct_x=False):
     ws = [vsim_b200.Q4Weight(qt, rand_q4(rng, qt, n, k), n, k) for _ in range(nw)]
     x0 = torch.randn(k, device="cuda")
+    xd = [torch.randn(k, device="cuda") for _ in range(nw)]
     ys = [torch.zeros(n, device="cuda") for _ in range(nw)]
-    xs = [x0.data_ptr()] + [(ys[i - 1] if dep else x0).data_ptr() for i in range(1, nw)]
+    xs = [x0.data_ptr()] + [(ys[i - 1] if dep else (xd[i] if distinct_x else x0)).data_ptr() for i in range(1, nw)]
     ch = vsim_b200.Chain(ws, xs, [y.data_ptr() for y in ys], [-1] + [(i - 1 if dep else -1) for i in range(1, nw)])
     ms = time_chain(L, ch, 30)
     wb = n * (k // 32) * (20 if qt == 0 else 24) + 4 * k + 4 * n
     us = ms * 1e3 / nw
-    print(f"micro q4_{qt} N={n} K={k} {'dependent' if dep else 'independent'} x{nw}: {us:.2f} us/op  {wb / us / 1e3:.0f} GB/s  "
+    print(f"micro q4_{qt} N={n} K={k} {'dependent' if dep else 'independent, distinct inputs' if distinct_x else 'independent, one shared input (one pack)'} x{nw}: {us:.2f} us/op  {wb / us / 1e3:.0f} GB/s  "
           f"{wb / us / 1e3 / PEAK * 100:.1f}% of measured peak   {ch.info()}", flush=True)
     ch.free()
     for w in ws:
@@ -116,6 +117,9 @@ def main():
         micro(L, rng, 0, True); micro(L, rng, 1, True)
     if "indep" in what:
         micro(L, rng, 0, False)
+        micro(L, rng, 0, False, distinct_x=True)
+        micro(L, rng, 0, False, nw=1)
+        micro(L, rng, 0, False, nw=40)
     if "l2" in what:
         l2(L, rng)
     for name in ("gptj", "neox20b"):

@@ -38,9 +38,10 @@ for _ in range(4):
     ch.run()
 L.b200q4_sync(None)
 info = ch.info()
-buf = np.zeros(148 * info["ops"] * 8 + 8, np.uint64)
+buf = np.zeros(148 * info["ops"] * 8 + 148 * 16 + 8, np.uint64)
 g = L.b200q4_chain_timeline(ch.handle, buf.ctypes.data, buf.size)
 assert g > 0, g
+acc = buf[g * info["ops"] * 8: g * info["ops"] * 8 + g * 16].reshape(g, 16).astype(np.float64) / 1.9e3     # cycles -> us at ~1.9 GHz
 t = buf[: g * info["ops"] * 8].reshape(g, info["ops"], 8).astype(np.int64)
 t0 = t[:, 0, 0].min()
 t = np.where(t > 0, t - t0, -1)
@@ -54,3 +55,9 @@ for o in range(nops):
     mn = lambda i: float(col(i).min()) / 1e3 if col(i).size else float("nan")
     print(f"{o:3d} | {mn(0):7.2f} {med(0):7.2f} | {med(1):7.2f} | {med(2):7.2f} | {med(3):7.2f} | {med(5):7.2f} {mx(5):7.2f} | {mx(5) - prev:6.2f}")
     prev = mx(5)
+
+names = ["producer waits for a free slot", "consumer warp 0 waits for a full stage", "consumer warp 0 in pg_begin_op", "reducer waits for consumers", "reducer total", "consumer warp 0 computing its units"]
+print(f"  stages per CTA: median {np.median(acc[:, 6]) * 1.9e3:.0f};  waited-for stages: {np.median(acc[:, 9]) * 1.9e3:.0f}, their issue-to-arrival latency: {np.median(acc[:, 8] / np.maximum(acc[:, 9], 1e-9)):.2f} us")
+print(f"  consumer warp 0 waits for the first stage of an op (peek): median {np.median(acc[:, 7]):8.2f} us")
+for i, nm in enumerate(names):
+    print(f"  {nm}: median {np.median(acc[:, i]):8.2f} us   min {acc[:, i].min():8.2f}   max {acc[:, i].max():8.2f}   (per launch of {nops} ops)")

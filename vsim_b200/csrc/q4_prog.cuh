@@ -42,7 +42,16 @@ constexpr int PG_MAX_STAGES = 6;
 constexpr int PG_UNITS = 2 * GEMV_WARPS;                 // units per stage (32)
 constexpr int PG_RW = 16;                                // floats per unit in the reduction ring (16 weight rows)
 constexpr int PG_CTHREADS = GEMV_WARPS * 32;             // consumer threads (512)
-constexpr int PG_THREADS = (GEMV_WARPS + 2) * 32;
+// "prep" warps that build the next op's activation pack while the consumers stream.  Measured (B200): with 2 warps a
+// 4096-element pack takes 9-12 us (IEEE divisions, 8 items per thread, lowest issue priority) -- longer than the op it is
+// meant to hide behind -- so the shipped configuration has none: the 512 consumer threads build every pack themselves
+// (about 1.5 us + the wait for the inputs).  The code path is kept for wider-SM parts.
+constexpr int PG_PWARPS = 0;
+constexpr int PG_PTHREADS = PG_PWARPS * 32;
+constexpr int PG_THREADS = (GEMV_WARPS + 2 + PG_PWARPS) * 32;
+// Warp roles: [0, PG_PWARPS) prep, then GEMV_WARPS consumers, the producer, the reducer.  The SM's warp arbiter favours
+// high warp ids: the prep warps, which may poll for a long time, must not take issue slots from anybody.
+constexpr int PG_C0 = PG_PTHREADS;                       // first consumer thread
 constexpr int PG_ATT_CHUNK = 64;                         // KV positions per attention work item
 constexpr int PG_ATT_MAX_D = 512;                        // largest head size the attention step handles
 
@@ -93,7 +102,13 @@ struct alignas(16) PgOp {
     int y_slice, dep_mv;     // dep_mv: the op `dep` is a PG_MATVEC (its completion implies that of every earlier op)
     int y_tag, publish;      // publish: a later op names this one as its `dep`: count the CTAs that are done with it
     float *y_plain;          // PP == 1, optional: an untagged copy of Y as well (what a caller outside the list reads)
-    int pack_of, pad3;       // index of the first op of a run of ops with the SAME activation pack (Q, K, V): built once
+    int cobuild, pad5;       // consumer-built packs: index of a LATER op whose pack is built in the same pause (it needs nothing that
+                             // is not there yet: the MLP's layer-norm of the residual stream next to the attention's), or -1
+    int builder, wait_pack;  // who builds the pack: 0 the prep warps (ahead of time), 1 the consumers themselves (a residual update or gelu:
+                             // big gathers, and the consumers would wait for the inputs anyway); wait_pack: for a prep-built layer-norm
+                             // pack, the number of the consumer-built pack that updated the residual stream it reads (-1: none)
+    int pack_of, pack_seq;   // index of the first op of a run of ops with the SAME activation pack (Q, K, V): built once;
+                             // pack_seq: running number of that pack (its shared-memory buffer is pack_seq & 1)
     // (everything above is what a PG_MATVEC needs: the first PG_OPC_WORDS words are what the shared-memory op cache holds)
     // ---- PG_ATTN: the new token's attention for one layer (decode, one query row) -----------------------------
     const float *q, *k, *v;          // [H * d] {value, tag} pairs written by ops tq, tk, tv (biases already added)
@@ -110,7 +125,7 @@ struct alignas(16) PgOp {
 };
 
 constexpr int PG_OPC = 8;                                // mul_mat ops cached in shared memory (ring; > PG_MAX_STAGES + 1)
-constexpr int PG_OPC_WORDS = 84;                         // 336 bytes per entry: one 16-byte load for each of 21 producer lanes (the PG_MATVEC part of PgOp)
+constexpr int PG_OPC_WORDS = 88;                         // 352 bytes per entry: one 16-byte load for each of 22 producer lanes (the PG_MATVEC part of PgOp)
 static_assert(offsetof(PgOp, q) <= PG_OPC_WORDS * 4, "the PG_MATVEC part of PgOp must fit a cache entry");
 
 struct PgParams {
@@ -128,7 +143,8 @@ __host__ __device__ constexpr size_t pg_stage_bytes(int qt) { return (size_t)PG_
 __host__ __device__ constexpr size_t pg_fixed_bytes(int e_cap, int nbp_cap, int att_cap)
 {
     return (size_t)e_cap * 4 + (size_t)nbp_cap * 32 + (size_t)nbp_cap * 12 + (size_t)att_cap * 4 + 40 * 8 +
-           3 * PG_MAX_STAGES * 8 + PG_MAX_STAGES * 16 + 64 + 128 + PG_OPC * PG_OPC_WORDS * 4;
+           (size_t)nbp_cap * 44 /* the second pack buffer */ + 4 * 8 + 32 +
+           3 * PG_MAX_STAGES * 8 + PG_MAX_STAGES * 16 + 64 + 128 + GEMV_WARPS * 16 + (PG_OPC + 1) * PG_OPC_WORDS * 4;
 }
 
 #ifndef Q4_PROG_TYPES_ONLY                               // (host-only includers stop here)
@@ -136,8 +152,9 @@ __host__ __device__ constexpr size_t pg_fixed_bytes(int e_cap, int nbp_cap, int 
 // Shared-memory map of q4_prog_kernel.  The out-of-line helpers recompute it from the parameter copy instead of taking
 // pointers as arguments: whatever the main loop does not need stays out of its registers.
 struct PgSmem {
-    uint8_t *stage; float *red, *x; uint8_t *aq; float *ap, *att; double *stat;
-    uint64_t *bar_full, *bar_empty, *bar_done; int4 *desc; int *dop, *flag; uint32_t *opc;
+    uint8_t *stage; float *red, *x; uint8_t *aq; float *ap, *att; double *stat;     // aq / ap: pack buffer 0; buffer 1 follows at pack_stride bytes
+    uint64_t *bar_full, *bar_empty, *bar_done, *pack_full, *pack_empty; int4 *desc; int *dop, *flag, *wst, *geo; uint32_t *opc;
+    int pack_stride;
 };
 extern __shared__ __align__(128) uint8_t pg_smem_base[];
 __device__ __forceinline__ PgSmem pg_smem(const PgParams &p, int qt)
@@ -146,25 +163,36 @@ __device__ __forceinline__ PgSmem pg_smem(const PgParams &p, int qt)
     m.stage = pg_smem_base;
     m.red = reinterpret_cast<float *>(pg_smem_base + (size_t)p.stages * PG_UNITS * chunk_bytes(qt));
     m.x = m.red + (size_t)p.stages * PG_UNITS * PG_RW;
+    m.pack_stride = p.nbp_cap * 44;                                    // one pack: codes [nbp_cap][32] + three planes [nbp_cap] floats
     m.aq = reinterpret_cast<uint8_t *>(m.x + p.e_cap);
     m.ap = reinterpret_cast<float *>(m.aq + (size_t)p.nbp_cap * 32);
-    m.att = m.ap + 3 * (size_t)p.nbp_cap;
+    m.att = reinterpret_cast<float *>(m.aq + 2 * (size_t)m.pack_stride);
     m.stat = reinterpret_cast<double *>(m.att + p.att_cap);
     m.bar_full = reinterpret_cast<uint64_t *>(m.stat + 40);
     m.bar_empty = m.bar_full + PG_MAX_STAGES;
     m.bar_done = m.bar_empty + PG_MAX_STAGES;
-    m.desc = reinterpret_cast<int4 *>(m.bar_done + PG_MAX_STAGES);     // {units (0: none, -2: STOP), first chunk index, first tile, task}
+    m.pack_full = m.bar_done + PG_MAX_STAGES;                          // [2] the prep warps have built pack buffer b
+    m.pack_empty = m.pack_full + 2;                                    // [2] every consumer warp is done with pack buffer b
+    m.desc = reinterpret_cast<int4 *>(m.pack_empty + 2);               // {units (0: none, -2: STOP), first chunk index, first tile, task}
     m.dop = reinterpret_cast<int *>(m.desc + PG_MAX_STAGES);           // op index of the stage | PG_END when it is the CTA's last of that op
-    m.flag = m.dop + PG_MAX_STAGES + 2;                                // [0] scratch flag, [1] waited_mv, [2..4] current op: C, first chunk of the K-slice, plane stride,
-                                                                       // [5] op whose activation pack is in shared memory, [6] tag base of this launch
-    m.opc = reinterpret_cast<uint32_t *>(m.flag + 8);                  // op cache [PG_OPC][PG_OPC_WORDS]
+    m.flag = m.dop + PG_MAX_STAGES + 2;                                // [0] scratch flag, [1] waited_mv (consumers), [5] latest consumer-built pack, [6] tag base of this launch,
+                                                                       // [7] waited_mv (prep warps)
+    m.geo = m.flag + 8;                                                // [2][4] per pack buffer: C, first chunk of the K-slice, plane stride
+    m.wst = m.geo + 8;                                                 // per consumer warp: slot, parity, current op, current pack
+    m.opc = reinterpret_cast<uint32_t *>(m.wst + GEMV_WARPS * 4);      // op cache [PG_OPC][PG_OPC_WORDS]
     return m;
 }
 
 #ifdef B200Q4_TIMELINE
 #define PG_STAMP(o, slot) do { if (p.dbg && (o) < p.n_ops) p.dbg[((size_t)blockIdx.x * p.n_ops + (o)) * 8 + (slot)] = gtimer(); } while (0)
+// wait-time accumulators behind the stamps: [grid][16] cycles (0 producer waiting for a free slot, 1 consumer warp 0
+// waiting for a full stage, 2 consumer warp 0 in pg_begin_op, 3 reducer waiting for the consumers, 4 reducer total)
+#define PG_ACC(pp_, slot, cyc) do { if ((pp_)->dbg) atomicAdd((pp_)->dbg + (size_t)gridDim.x * (pp_)->n_ops * 8 + (size_t)blockIdx.x * 16 + (slot), (unsigned long long)(cyc)); } while (0)
+#define PG_CLK() clock64()
 #else
 #define PG_STAMP(o, slot) do { } while (0)
+#define PG_ACC(pp_, slot, cyc) do { } while (0)
+#define PG_CLK() 0ll
 #endif
 
 __device__ __forceinline__ int ld_acquire_gpu(const int *p)
@@ -188,6 +216,23 @@ __device__ __forceinline__ void pg_wait_ctr(const int *c, int target, int *err, 
         }
     }
 }
+// "probably complete" hint: CTAs add to an op's counter after their last (tagged) stores WITHOUT a fence, one thread
+// polls it with back-off, then everybody reads the tagged data (which is what guarantees correctness).  Gives up after
+// ~1 ms: the tags decide.
+__device__ __forceinline__ void pg_wait_hint(const int *c, int target)
+{
+    const long long t0 = clock64();
+    for (;;) {
+        int v;
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+        if (v >= target || clock64() - t0 > 2000000ll) return;
+        __nanosleep(100);
+    }
+}
+__device__ __forceinline__ void pg_add_hint(int *c)
+{
+    asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" :: "l"(c) : "memory");
+}
 __device__ __forceinline__ void pg_mbar_wait(uint64_t *b, uint32_t parity)
 {
     const long long t0 = clock64();
@@ -204,6 +249,7 @@ __device__ __forceinline__ void pg_mbar_wait(uint64_t *b, uint32_t parity)
     }
 }
 __device__ __forceinline__ void pg_bar() { asm volatile("bar.sync 1, %0;" :: "n"(PG_CTHREADS) : "memory"); }
+__device__ __forceinline__ void pg_pbar() { asm volatile("bar.sync 2, %0;" :: "n"(PG_PTHREADS > 0 ? PG_PTHREADS : 32) : "memory"); }   // the prep warps' own barrier
 
 __device__ __forceinline__ float4 ld_relaxed_f4(const void *p)
 {
@@ -324,7 +370,7 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
     int *s_flag = sm.flag;
     const int n_past = p.dyn ? __ldg(p.dyn + 1) : 0;
     const PgOp &op = p.ops[o];
-    const int ctid = threadIdx.x, lane = ctid & 31, warp = ctid >> 5;
+    const int ctid = threadIdx.x - PG_C0, lane = ctid & 31, warp = ctid >> 5;
     const int H = op.H, d = op.d, E = H * d, half = op.n_rot / 2, P = n_past + 1;
     const int nch = (P + PG_ATT_CHUNK - 1) / PG_ATT_CHUNK, items = H * nch;
     const int dpad = (d + 3) & ~3;
@@ -371,6 +417,7 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
             if (pos == n_past) { for (int j = lane; j < d; j += 32) sum = __dadd_rn(sum, (double)__fmul_rn(s_kn[j], s_q[j])); }
             else {
                 const float *kr = mk + (size_t)pos * E + h * d;
+#pragma unroll 8
                 for (int j = lane; j < d; j += 32) sum = __dadd_rn(sum, (double)__fmul_rn(__ldcg(kr + j), s_q[j]));
             }
 #pragma unroll
@@ -409,6 +456,7 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
             const int g = ctid / dj, j = ctid - g * dj;
             if (g < ng && j < d) {
                 float a = 0.f;
+#pragma unroll 8
                 for (int pl = g; pl < np; pl += ng) {
                     const int pos = p_lo + pl;
                     const float vv = pos == n_past ? s_vn[j] : __ldcg(mv + (size_t)pos * E + h * d + j);
@@ -454,6 +502,7 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
                 const int g = ctid / dj, j = ctid - g * dj;
                 if (g < ng && j < d) {
                     float a = 0.f;
+#pragma unroll 8
                     for (int pl = g; pl < np; pl += ng) {
                         const int pos = p_lo + pl;
                         const float vv = pos == n_past ? s_vn[j] : __ldcg(mv + (size_t)pos * E + h * d + j);
@@ -493,6 +542,9 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
         __threadfence();
         pg_bar();
         if (ctid == 0) atomicAdd(p.ctr + 1 + o, 1);
+    } else {
+        pg_bar();
+        if (ctid == 0) pg_add_hint(p.ctr + 1 + o);           // (no fence: only tells pollers that looking at the tags is worth it)
     }
 }
 
@@ -504,7 +556,7 @@ __device__ __noinline__ void pg_sum(const PgParams *pp, int o, int qt)
     const PgSmem sm = pg_smem(p, qt);
     const int tagbase = sm.flag[6];
     const PgOp &op = p.ops[o];
-    const int ctid = threadIdx.x;
+    const int ctid = threadIdx.x - PG_C0;
     const int n4 = op.N / 4;
     for (int i = (int)blockIdx.x * PG_CTHREADS + ctid; i < n4; i += (int)gridDim.x * PG_CTHREADS)
         reinterpret_cast<float4 *>(op.y)[i] = pg_src4(op.src[0], i * 4, tagbase, p.err);
@@ -526,20 +578,26 @@ __device__ __noinline__ void pg_sum(const PgParams *pp, int o, int qt)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Start of a mul_mat op on the consumer side: dependency wait + activation pack.  Returns the op's geometry.
+// The activation pack of a mul_mat op, built by the PG_PTHREADS prep threads into pack buffer b: dependency wait (tagged
+// inputs are polled, a counted dependency is waited for), residual update / layer-norm / gelu, quantization.
 // ---------------------------------------------------------------------------------------------------------------
-// waited_mv (the latest mul_mat op this CTA knows to be complete) lives in shared memory: sm.flag[1].
-template <int QT>
-__device__ __noinline__ void pg_begin_op(const PgParams *pp, const PgOp *opp, int o, bool has_data)
+// GROUP 0: the PG_PTHREADS prep threads (ahead of the consumers); GROUP 1: the PG_CTHREADS consumer threads themselves.
+// waited_mv (the latest mul_mat op this CTA knows to be complete) lives in shared memory: sm.flag[7] / sm.flag[1].
+template <int QT, int GROUP>
+__device__ __noinline__ void pg_build_pack(const PgParams *pp, const PgOp *opp, int o, int b)
 {
     constexpr int NP = (QT == 0) ? 2 : 3;
-    const PgParams &p = *pp;                                 // both in shared memory: nothing here may live on the stack
+    constexpr int NT = GROUP == 0 ? PG_PTHREADS : PG_CTHREADS, NW = NT / 32, WFLAG = GROUP == 0 ? 7 : 1;
+    auto gbar = [] { if (GROUP == 0) pg_pbar(); else pg_bar(); };
+    const PgParams &p = *pp;                                 // in shared memory: nothing here may live on the stack
     const PgOp &op = *opp;
     const PgSmem sm = pg_smem(p, QT);
-    float *s_x = sm.x, *s_ap = sm.ap;
-    uint8_t *s_aq = sm.aq;
+    float *s_x = sm.x;
+    uint8_t *s_aq = sm.aq + (size_t)b * sm.pack_stride;
+    float *s_ap = reinterpret_cast<float *>(s_aq + (size_t)p.nbp_cap * 32);
     double *s_stat = sm.stat;
-    const int ctid = threadIdx.x, lane = ctid & 31, warp = ctid >> 5;
+    constexpr bool has_data = true;                          // (the prep warps build every pack: they cannot know the CTA's tasks ahead of time)
+    const int ctid = GROUP == 0 ? (int)threadIdx.x : (int)threadIdx.x - PG_C0, lane = ctid & 31, warp = ctid >> 5;
     const bool sliced = op.PP > 1;
     const int cls = sliced ? (int)blockIdx.x % op.PP : 0;
     const int cbase = cls * op.TS, blk0 = cbase * CHUNK_BLKS;
@@ -549,37 +607,37 @@ __device__ __noinline__ void pg_begin_op(const PgParams *pp, const PgOp *opp, in
     const int in_mode = op.in_mode, res = op.res, nsrc = op.nsrc, K = op.K;
     // A CTA without a task of this op needs no activation pack; only an update of the residual stream has to happen
     // everywhere (every CTA carries its own copy).
-    const bool res_update = in_mode == PG_IN_LN && (res == PG_RES_ADD || res == PG_RES_SET);
-    if (!has_data && !res_update) return;
-    // The pack of a run of ops with the same activation (Q, K, V: same input, same layer-norm weights) is built once.
-    // (flag[5] was written before a barrier every consumer thread has passed since.)
-    if (!res_update && sm.flag[5] == op.pack_of) return;
-    pg_bar();                                                // every consumer warp is done with the previous op's pack
-    const int waited_mv = sm.flag[1];
+    if (GROUP == 1) gbar();                                  // every consumer warp is done with this buffer's previous pack
+    const int waited_mv = sm.flag[WFLAG];
     const int tagbase = sm.flag[6];
     int *err = p.err;
     if (has_data) {
         // records of padded blocks (weight scale 0, but 0 x garbage could be NaN) read as zero
-        for (int i = nb_l * 4 + ctid; i < nbp * 4; i += PG_CTHREADS) reinterpret_cast<uint2 *>(s_aq)[i] = make_uint2(0u, 0u);
+        for (int i = nb_l * 4 + ctid; i < nbp * 4; i += NT) reinterpret_cast<uint2 *>(s_aq)[i] = make_uint2(0u, 0u);
         for (int pl = 0; pl < NP; pl++)
-            for (int i = nb_l + ctid; i < nbp; i += PG_CTHREADS) s_ap[pl * plane + i] = 0.0f;
+            for (int i = nb_l + ctid; i < nbp; i += NT) s_ap[pl * plane + i] = 0.0f;
     }
     const int dep = op.dep;
     if (dep >= 0 && dep > waited_mv) {
         if (ctid == 0) pg_wait_ctr(p.ctr + 1 + dep, (int)gridDim.x, p.err, o + 1);
-        pg_bar();                                            // (everybody has read flag[1] by now)
-        if (ctid == 0 && op.dep_mv) sm.flag[1] = dep;        // a complete mul_mat op implies every earlier op is complete
+        gbar();                                            // (everybody has read flag[1] by now)
+        if (ctid == 0 && op.dep_mv) sm.flag[WFLAG] = dep;        // a complete mul_mat op implies every earlier op is complete
     }
-    if (ctid == 0) PG_STAMP(o, 2);
+    if (ctid == 0) {                                         // tagged inputs: one thread waits until they are probably all there
+        for (int j = 0; j < nsrc; j++)
+            if ((op.src[j].kind & 255) == PG_SRC_TAG) pg_wait_hint(p.ctr + 1 + (op.src[j].kind >> 8), (int)gridDim.x);
+        PG_STAMP(o, 2);
+    }
+    gbar();
     auto block_sum = [&](double v) {
 #pragma unroll
         for (int of = 16; of > 0; of >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, of));
         if (lane == 0) s_stat[warp] = v;
-        pg_bar();
+        gbar();
         double t = 0.0;
 #pragma unroll
-        for (int i = 0; i < GEMV_WARPS; i++) t = __dadd_rn(t, s_stat[i]);
-        pg_bar();
+        for (int i = 0; i < NW; i++) t = __dadd_rn(t, s_stat[i]);
+        gbar();
         return t;
     };
     const int items = nb_l * 4;                              // one item = 8 consecutive elements of one quant block
@@ -597,7 +655,7 @@ __device__ __noinline__ void pg_begin_op(const PgParams *pp, const PgOp *opp, in
         if (res != PG_RES_KEEP) {
             // ggml_norm (ggml.c:4282-4298): mean and variance accumulated in double (tree order here), two passes
             double ls = 0.0;
-            for (int k4 = ctid; k4 < K / 4; k4 += PG_CTHREADS) {
+            for (int k4 = ctid; k4 < K / 4; k4 += NT) {
                 float4 a;
                 if (res == PG_RES_TEMP) a = ln_in(k4);
                 else {
@@ -612,7 +670,7 @@ __device__ __noinline__ void pg_begin_op(const PgParams *pp, const PgOp *opp, in
             }
             const double mean = block_sum(ls) / (double)K;
             double l2 = 0.0;
-            for (int k4 = ctid; k4 < K / 4; k4 += PG_CTHREADS) {
+            for (int k4 = ctid; k4 < K / 4; k4 += NT) {
                 const float4 a = ln_in(k4);
                 const double v0 = __dsub_rn((double)a.x, mean), v1 = __dsub_rn((double)a.y, mean);
                 const double v2 = __dsub_rn((double)a.z, mean), v3 = __dsub_rn((double)a.w, mean);
@@ -623,12 +681,12 @@ __device__ __noinline__ void pg_begin_op(const PgParams *pp, const PgOp *opp, in
                 s_stat[32] = mean;
                 s_stat[33] = (double)(float)(1.0 / sqrt(__dadd_rn(var, (double)1e-5f)));
             }
-            pg_bar();
+            gbar();
         }
         const double mean = s_stat[32];
         const float rstd = (float)s_stat[33];
         const float *lw = op.ln_w, *lb = op.ln_b;
-        for (int base = 0; has_data && base < items; base += PG_CTHREADS) {
+        for (int base = 0; has_data && base < items; base += NT) {
             const int id = base + ctid;
             const bool valid = id < items;
             const int blk = valid ? id >> 2 : 0;
@@ -652,9 +710,60 @@ __device__ __noinline__ void pg_begin_op(const PgParams *pp, const PgOp *opp, in
             quantize8_emit<QT>(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), valid, lane,
                                s_aq + (size_t)blk * 32, s_ap + blk, plane);
         }
+    } else if (GROUP == 0 && in_mode == PG_IN_PLAIN && nsrc == 1 && op.src[0].np == 1 && op.src[0].scale == 1.0f &&
+               (op.src[0].kind & 255) != PG_SRC_Q4ROW) {
+        // The prep warps' common case (one plain or tagged vector).  64 threads cover the slice with several items each:
+        // the loads of a whole batch are issued before anything is looked at, so that a batch costs one memory round trip.
+        constexpr int B = 4;                                 // items per thread and batch
+        const PgSrc &sr = op.src[0];
+        const bool tagged = (sr.kind & 255) == PG_SRC_TAG;
+        const int tag = tagbase | ((sr.kind >> 8) + 1);
+        const float *sp = static_cast<const float *>(sr.ptr);
+        for (int base = 0; base < items; base += NT * B) {
+            float4 r[B][4];                                  // tagged: 4 x {v, t, v, t};  plain: 2 x float4
+            int kk[B];
+#pragma unroll
+            for (int i = 0; i < B; i++) {
+                const int id = base + i * NT + ctid;
+                const int blk = id < items ? id >> 2 : 0;
+                kk[i] = (blk0 + blk) * QK + (lane & 3) * 8;
+                if (id < items) {
+                    if (tagged) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) r[i][j] = ld_relaxed_f4(sp + 2 * (size_t)kk[i] + 4 * j);
+                    } else {
+                        r[i][0] = __ldcg(reinterpret_cast<const float4 *>(sp + kk[i]));
+                        r[i][1] = __ldcg(reinterpret_cast<const float4 *>(sp + kk[i] + 4));
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < B; i++) {
+                const int id = base + i * NT + ctid;
+                if (base + i * NT >= items) break;           // (warp-uniform: whole warps stop together)
+                const bool valid = id < items;
+                const int blk = valid ? id >> 2 : 0;
+                float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+                if (valid) {
+                    if (tagged) {
+                        bool ok = true;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) ok = ok && __float_as_int(r[i][j].y) == tag && __float_as_int(r[i][j].w) == tag;
+                        if (ok) {
+                            lo = make_float4(r[i][0].x, r[i][0].z, r[i][1].x, r[i][1].z);
+                            hi = make_float4(r[i][2].x, r[i][2].z, r[i][3].x, r[i][3].z);
+                        } else {                             // not there yet after all: poll
+                            lo = pg_ld_tag4(sp, (size_t)kk[i], tag, err);
+                            hi = pg_ld_tag4(sp, (size_t)kk[i] + 4, tag, err);
+                        }
+                    } else { lo = r[i][0]; hi = r[i][1]; }
+                }
+                quantize8_emit<QT>(lo, hi, valid, lane, s_aq + (size_t)blk * 32, s_ap + blk, plane);
+            }
+        }
     } else {
         const uint16_t *tab = op.gelu_tab;
-        for (int base = 0; base < items; base += PG_CTHREADS) {
+        for (int base = 0; base < items; base += NT) {
             const int id = base + ctid;
             const bool valid = id < items;
             const int blk = valid ? id >> 2 : 0;
@@ -673,8 +782,39 @@ __device__ __noinline__ void pg_begin_op(const PgParams *pp, const PgOp *opp, in
             quantize8_emit<QT>(lo, hi, valid, lane, s_aq + (size_t)blk * 32, s_ap + blk, plane);
         }
     }
-    if (ctid == 0 && has_data) { sm.flag[2] = op.C; sm.flag[3] = cbase; sm.flag[4] = plane; sm.flag[5] = op.pack_of; }
-    pg_bar();
+    if (ctid == 0) { sm.geo[b * 4] = op.C; sm.geo[b * 4 + 1] = cbase; sm.geo[b * 4 + 2] = plane; if (GROUP == 1) sm.flag[5] = op.pack_seq; }
+    if (ctid == 0) PG_STAMP(o, 3);
+    gbar();                                               // every prep thread's part of the pack is written ...
+    if (ctid == 0) mbar_arrive(&sm.pack_full[b]);            // ... before the consumers are told
+}
+
+// ===================== prep warps =====================
+// Walk the mul_mat ops in list order, one pack ahead of the consumers: pack number q goes to buffer q & 1 as soon as
+// every consumer warp has released that buffer (pack q - 2).  Packs the consumers build themselves are skipped.
+template <int QT>
+__device__ __noinline__ void pg_prep(const PgParams *pp)
+{
+    const PgParams &p = *pp;
+    const PgSmem sm = pg_smem(p, QT);
+    const int ptid = threadIdx.x;
+    PgOp *my = reinterpret_cast<PgOp *>(sm.opc + (size_t)PG_OPC * PG_OPC_WORDS);      // the prep warps' own copy of the op they work on
+    for (int o = p.first_mv; o < p.n_ops;) {
+        pg_pbar();                                           // (the previous pack's readers of *my are done)
+        if (ptid < PG_OPC_WORDS / 4) reinterpret_cast<uint4 *>(my)[ptid] = __ldg(reinterpret_cast<const uint4 *>(p.ops + o) + ptid);
+        pg_pbar();
+        const int nxt = my->next_mv;
+        if (my->pack_of == o && my->builder == 0) {          // a new pack of ours (ops that reuse the previous one need nothing)
+            const int q = my->pack_seq, b = q & 1, wq = my->wait_pack;
+            if (ptid == 0) {
+                pg_mbar_wait(&sm.pack_empty[b], (uint32_t)((q >> 1) & 1) ^ 1u);
+                // a layer-norm pack reads the residual stream the consumers updated while they built pack wq
+                if (wq >= 0) pg_mbar_wait(&sm.pack_full[wq & 1], (uint32_t)(wq >> 1) & 1u);
+            }
+            pg_pbar();
+            pg_build_pack<QT, 0>(pp, my, o, b);
+        }
+        o = nxt;
+    }
 }
 
 constexpr int PG_END = 1 << 30;                          // flag in a stage's op word: the CTA's last stage of that op
@@ -702,9 +842,14 @@ __device__ __noinline__ void pg_producer(const PgParams *pp)
     int s = 0;
     uint32_t ph = 1;
     auto put = [&](int cnt, int c0, int T, int task, int otag, const uint8_t *src) {
+        const long long tw = PG_CLK();
         pg_mbar_wait(&sm.bar_empty[s], ph);
+        PG_ACC(pp, 0, PG_CLK() - tw);
         sm.desc[s] = make_int4(cnt, c0, T, task);
         sm.dop[s] = otag;
+#ifdef B200Q4_TIMELINE
+        reinterpret_cast<long long *>(sm.stat + 8)[s] = clock64();   // (scratch doubles 8..13 are free while the consumers run stages)
+#endif
         if (cnt > 0) {
             mbar_arrive_expect_tx(&sm.bar_full[s], (uint32_t)cnt * CH);
             bulk_g2s(sm.stage + (size_t)s * STAGE_BYTES, src, (uint32_t)cnt * CH, &sm.bar_full[s]);
@@ -812,8 +957,11 @@ __device__ __noinline__ void pg_reducer(const PgParams *pp)
     };
     int s = 0;
     uint32_t ph = 0;
+    const long long tr0 = PG_CLK();
     for (;;) {
+        const long long tw = PG_CLK();
         pg_mbar_wait(&sm.bar_done[s], ph);                   // every consumer warp has passed this slot (markers included)
+        if (lane == 0) PG_ACC(pp, 3, PG_CLK() - tw);
         const int4 dsc = sm.desc[s];
         const int otag = sm.dop[s], o = otag & (PG_END - 1);
         if (dsc.x == -2) break;
@@ -867,11 +1015,15 @@ __device__ __noinline__ void pg_reducer(const PgParams *pp)
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) atomicAdd(p.ctr + 1 + o, 1);
+            } else if (ytag) {
+                __syncwarp();
+                if (lane == 0) pg_add_hint(p.ctr + 1 + o);   // (no fence: only tells pollers that looking at the tags is worth it)
             }
             if (lane == 0) PG_STAMP(o, 5);
         }
         if (++s == p.stages) { s = 0; ph ^= 1; }
     }
+    if (lane == 0) PG_ACC(pp, 4, PG_CLK() - tr0);
     // the last CTA to get here clears every counter for the next launch (nobody polls or draws any more:
     // each CTA's consumers and producer are past their last use when its reducer sees STOP)
     __syncwarp();
@@ -888,13 +1040,12 @@ __device__ __noinline__ void pg_reducer(const PgParams *pp)
 // ===================== consumers =====================
 // one stage: this warp's two units (an octet of quant blocks) against the activation pack
 template <int QT>
-__device__ __forceinline__ void pg_consume_stage(const PgSmem &sm, int gC, int gcbase, int gplane, int s, int cnt, int c0, int T0)
+__device__ __forceinline__ void pg_consume_stage(const PgSmem &sm, const uint8_t *s_aq, const float *s_ap, int gC, int gcbase, int gplane,
+                                                 int s, int cnt, int c0, int T0)
 {
     constexpr int CH = chunk_bytes(QT);
     constexpr int STAGE_BYTES = PG_UNITS * CH;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint8_t *s_aq = sm.aq;
-    const float *s_ap = sm.ap;
+    const int lane = threadIdx.x & 31, warp = (threadIdx.x - PG_C0) >> 5;
     const int uA = 2 * warp, uB = uA + 1;
     auto put_rows = [&](float *slot, float v0, float v2) {
         v0 += __shfl_xor_sync(0xffffffffu, v0, 1); v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
@@ -928,63 +1079,128 @@ __device__ __forceinline__ void pg_consume_stage(const PgSmem &sm, int gC, int g
     }
 }
 
-// The stages of ONE op, from slot s on, up to and including the CTA's last stage of that op (END flag) or the STOP
-// marker: a loop without calls, so that its state stays in registers.  Returns the next slot | parity << 8 | stop << 9.
+// The stages of ONE op, from the warp's current slot on, up to and including the CTA's last stage of that op (END
+// flag) or the STOP marker: a loop without calls, so that its state stays in registers.  The slot / parity live in
+// shared memory between calls (wst[0], wst[1]): no register is live across a call in the driver below, so nothing goes
+// through the stack (local memory has no L1 to speak of next to 224 KB of shared memory: a reload is an L2 round trip).
+// Returns 1 after the STOP marker.
 template <int QT>
-__device__ __noinline__ int pg_consume_op(const PgParams *pp, int s, uint32_t ph)
+__device__ __noinline__ int pg_consume_op(const PgParams *pp)
 {
     const PgSmem sm = pg_smem(*pp, QT);
     const int stages = pp->stages;
     const int lane = threadIdx.x & 31;
-    const int gC = sm.flag[2], gcbase = sm.flag[3], gplane = sm.flag[4];     // the op's geometry, left by pg_begin_op
+    int *wst = sm.wst + ((threadIdx.x - PG_C0) >> 5) * 4;
+    int s = wst[0];
+    uint32_t ph = (uint32_t)wst[1];
+    const int b = wst[3] & 1;                                // the op's pack buffer and its geometry, left there by the prep warps
+    const int gC = sm.geo[b * 4], gcbase = sm.geo[b * 4 + 1], gplane = sm.geo[b * 4 + 2];
+    const uint8_t *s_aq = sm.aq + (size_t)b * sm.pack_stride;
+    const float *s_ap = reinterpret_cast<const float *>(s_aq + (size_t)pp->nbp_cap * 32);
     for (;;) {
+        const long long tw = PG_CLK();
         pg_mbar_wait(&sm.bar_full[s], ph);
+        if (threadIdx.x == PG_C0) PG_ACC(pp, 1, PG_CLK() - tw);
+#ifdef B200Q4_TIMELINE
+        if (threadIdx.x == PG_C0 && PG_CLK() - tw > 200) { PG_ACC(pp, 8, PG_CLK() - reinterpret_cast<long long *>(sm.stat + 8)[s]); PG_ACC(pp, 9, 1); }
+#endif
         const int4 dsc = sm.desc[s];
         const int otag = sm.dop[s];
-        if (dsc.x > 0) pg_consume_stage<QT>(sm, gC, gcbase, gplane, s, dsc.x, dsc.y, dsc.z);
+        const long long tc = PG_CLK();
+        if (dsc.x > 0) pg_consume_stage<QT>(sm, s_aq, s_ap, gC, gcbase, gplane, s, dsc.x, dsc.y, dsc.z);
         __syncwarp();
+        if (threadIdx.x == PG_C0 && dsc.x > 0) { PG_ACC(pp, 5, PG_CLK() - tc); PG_ACC(pp, 6, 1); }
         if (lane == 0) mbar_arrive(&sm.bar_done[s]);
         const bool stop = dsc.x == -2;
         if (!stop && ++s == stages) { s = 0; ph ^= 1; }
-        if (stop || (otag & PG_END)) return s | (int)(ph << 8) | (stop ? 1 << 9 : 0);
+        if (stop || (otag & PG_END)) {
+            if (lane == 0) { wst[0] = s; wst[1] = (int)ph; }
+            __syncwarp();
+            return stop ? 1 : 0;
+        }
+    }
+}
+
+// side ops between two mul_mats (attention, final sums), in list order
+template <int QT>
+__device__ __noinline__ void pg_side_ops(const PgParams *pp, int from, int to)
+{
+    const PgParams &p = *pp;
+    const PgSmem sm = pg_smem(p, QT);
+    for (int a = from; a < to; a++) {
+        const int kind = p.ops[a].kind;
+        if (kind == PG_MATVEC) continue;
+        const int dep = p.ops[a].dep;
+        pg_bar();
+        const int wmv = sm.flag[1];
+        if (dep >= 0 && dep > wmv) {
+            if (threadIdx.x == PG_C0) pg_wait_ctr(p.ctr + 1 + dep, (int)gridDim.x, p.err, a + 1);
+            pg_bar();                                        // (everybody has read flag[1] by now)
+            if (threadIdx.x == PG_C0 && p.ops[dep].kind == PG_MATVEC) sm.flag[1] = dep;
+        }
+        if (kind == PG_ATTN) pg_attn(pp, a, QT);
+        else pg_sum(pp, a, QT);
     }
 }
 
 template <int QT>
 __device__ __noinline__ void pg_consumer(const PgParams *pp)
 {
-    const PgParams &p = *pp;
-    const PgSmem sm = pg_smem(p, QT);
-    int s = 0;
-    uint32_t ph = 0;
-    int cur = -1;
+    {
+        const PgSmem sm = pg_smem(*pp, QT);
+        int *wst = sm.wst + ((threadIdx.x - PG_C0) >> 5) * 4;
+        if ((threadIdx.x & 31) == 0) { wst[0] = 0; wst[1] = 0; wst[2] = -1; wst[3] = -1; }
+        __syncwarp();
+    }
     for (;;) {
-        pg_mbar_wait(&sm.bar_full[s], ph);                   // peek: which op does the next stage belong to?
-        const int4 dsc = sm.desc[s];
-        const int o = sm.dop[s] & (PG_END - 1);
-        for (int a = cur + 1; a < o; a++) {                  // side ops between two mul_mats (STOP carries o = n_ops: trailing ones too)
-            const int kind = p.ops[a].kind;
-            if (kind == PG_MATVEC) continue;
-            const int dep = p.ops[a].dep;
-            pg_bar();
-            const int wmv = sm.flag[1];
-            if (dep >= 0 && dep > wmv) {
-                if (threadIdx.x == 0) pg_wait_ctr(p.ctr + 1 + dep, (int)gridDim.x, p.err, a + 1);
-                pg_bar();                                    // (everybody has read flag[1] by now)
-                if (threadIdx.x == 0 && p.ops[dep].kind == PG_MATVEC) sm.flag[1] = dep;
+        // peek: which op does the next stage belong to?  (every value below is re-read from shared memory after a call)
+        {
+            const PgSmem sm = pg_smem(*pp, QT);
+            int *wst = sm.wst + ((threadIdx.x - PG_C0) >> 5) * 4;
+            const int s = wst[0];
+            const long long tw = PG_CLK();
+            pg_mbar_wait(&sm.bar_full[s], (uint32_t)wst[1]);
+            if (threadIdx.x == PG_C0) PG_ACC(pp, 7, PG_CLK() - tw);
+            const int o = sm.dop[s] & (PG_END - 1), cur = wst[2];
+            if (o > cur + 1) pg_side_ops<QT>(pp, cur + 1, o);     // (STOP carries o = n_ops: trailing side ops run too)
+        }
+        {
+            const PgSmem sm = pg_smem(*pp, QT);
+            int *wst = sm.wst + ((threadIdx.x - PG_C0) >> 5) * 4;
+            const int s = wst[0];
+            const int o = sm.dop[s] & (PG_END - 1), cnt = sm.desc[s].x;
+            const int lane = threadIdx.x & 31;
+            __syncwarp();
+            if (lane == 0) wst[2] = o;
+            if (cnt != -2) {
+                // the op's activation pack: wait until the prep warps have built it; hand the previous buffer back first
+                const int q = pg_cached_op(sm, o).pack_seq, cq = wst[3];
+                if (q != cq) {
+                    { const PgParams &p = *pp; if (threadIdx.x == PG_C0) PG_STAMP(o, 1); (void)p; }
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (cq >= 0) mbar_arrive(&sm.pack_empty[cq & 1]);
+                        wst[3] = q;
+                    }
+                    const long long tw = PG_CLK();
+                    // consumer-built packs: all 512 threads; flag[5] = the latest pack built so far (a pack may have been built
+                    // early, in the pause of an earlier op).  Prep-built packs (PG_PWARPS > 0) are waited for.
+                    if (pg_cached_op(sm, o).builder == 1) {
+                        if (q > sm.flag[5]) {
+                            const int co = pg_cached_op(sm, o).cobuild;
+                            PgOp *my = reinterpret_cast<PgOp *>(sm.opc + (size_t)PG_OPC * PG_OPC_WORDS);
+                            if (co >= 0 && (int)threadIdx.x - PG_C0 < PG_OPC_WORDS / 4)        // its op record arrives while the first pack is built
+                                reinterpret_cast<uint4 *>(my)[threadIdx.x - PG_C0] = __ldg(reinterpret_cast<const uint4 *>(pp->ops + co) + (threadIdx.x - PG_C0));
+                            pg_build_pack<QT, 1>(pp, &pg_cached_op(sm, o), o, q & 1);
+                            if (co >= 0) pg_build_pack<QT, 1>(pp, my, co, (q + 1) & 1);
+                        }
+                    } else pg_mbar_wait(&sm.pack_full[q & 1], (uint32_t)(q >> 1) & 1u);
+                    if (threadIdx.x == PG_C0) PG_ACC(pp, 2, PG_CLK() - tw);
+                    __syncwarp();
+                }
             }
-            if (kind == PG_ATTN) pg_attn(pp, a, QT);
-            else pg_sum(pp, a, QT);
         }
-        if (dsc.x != -2) {
-            if (threadIdx.x == 0) PG_STAMP(o, 1);
-            pg_begin_op<QT>(pp, &pg_cached_op(sm, o), o, dsc.x > 0);
-            if (threadIdx.x == 0) PG_STAMP(o, 3);
-        }
-        cur = o;
-        const int r = pg_consume_op<QT>(pp, s, ph);
-        if (r & (1 << 9)) break;
-        s = r & 255; ph = (uint32_t)(r >> 8) & 1u;
+        if (pg_consume_op<QT>(pp)) break;
     }
 }
 
@@ -994,24 +1210,28 @@ __global__ void __launch_bounds__(PG_THREADS, 1) q4_prog_kernel(const PgParams p
     __shared__ PgParams s_p;                                 // what the roles read (a by-reference kernel parameter would be copied to the stack)
     const PgSmem sm = pg_smem(p, QT);
     const int warp = threadIdx.x >> 5;
-    if (threadIdx.x < 3 * PG_MAX_STAGES) {
+    if (threadIdx.x < 3 * PG_MAX_STAGES + 4) {
         const int i = threadIdx.x % PG_MAX_STAGES, which = threadIdx.x / PG_MAX_STAGES;
-        if (i < p.stages) {
-            if (which == 0) mbar_init(&sm.bar_full[i], 1);
-            else if (which == 1) mbar_init(&sm.bar_empty[i], 1);
-            else mbar_init(&sm.bar_done[i], GEMV_WARPS);
-        }
+        if (which < 3) {
+            if (i < p.stages) {
+                if (which == 0) mbar_init(&sm.bar_full[i], 1);
+                else if (which == 1) mbar_init(&sm.bar_empty[i], 1);
+                else mbar_init(&sm.bar_done[i], GEMV_WARPS);
+            }
+        } else if (i < 2) mbar_init(&sm.pack_full[i], 1);
+        else if (i < 4) mbar_init(&sm.pack_empty[i - 2], GEMV_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x == PG_THREADS - 1) {
         s_p = p;
-        sm.flag[1] = -1; sm.flag[5] = -1;
+        sm.flag[1] = -1; sm.flag[5] = -1; sm.flag[7] = -1;
         sm.flag[6] = (int)(((unsigned)p.dyn[2] & 0x7ffffu) << 12);           // tag = epoch << 12 | (op index + 1)
     }
     __syncthreads();
-    if (warp == GEMV_WARPS) pg_producer<QT>(&s_p);
-    else if (warp == GEMV_WARPS + 1) pg_reducer<QT>(&s_p);
-    else pg_consumer<QT>(&s_p);
+    if (PG_PWARPS > 0 && warp < PG_PWARPS) pg_prep<QT>(&s_p);
+    else if (warp < PG_PWARPS + GEMV_WARPS) pg_consumer<QT>(&s_p);
+    else if (warp == PG_PWARPS + GEMV_WARPS) pg_producer<QT>(&s_p);
+    else pg_reducer<QT>(&s_p);
 }
 
 #endif // Q4_PROG_TYPES_ONLY

@@ -79,13 +79,35 @@ int ProgBuild::add_matvec(const b200q4_weight *w, int dep, int in_mode, int res,
     op.y_plain = g.PP == 1 ? y_plain : nullptr;
     if (ops.size() >= 4095) return api_fail(B200Q4_EINVAL, "program: too many ops");
     op.pack_of = (int)ops.size();
+    op.pack_seq = n_packs;
+    // who builds the pack (q4_prog.cuh): the consumers, when it is a residual update (they own the residual stream), a
+    // layer-norm over a temporary sum, or gelu; the prep warps otherwise, ahead of time
+    const bool res_upd = in_mode == PG_IN_LN && res != PG_RES_KEEP;
+    op.builder = (PG_PWARPS == 0 || res_upd || in_mode == PG_IN_GELU) ? 1 : 0;
+    op.cobuild = -1;
+    op.wait_pack = -1;
+    if (in_mode == PG_IN_LN && res == PG_RES_KEEP) {
+        if (last_res_pack < 0) return api_fail(B200Q4_EINVAL, "program: layer-norm op before any residual update");
+        op.wait_pack = last_res_pack;
+    }
+    if (in_mode == PG_IN_LN && (res == PG_RES_ADD || res == PG_RES_SET)) last_res_pack = n_packs;
     if (same_pack) {
         if (last_mv < 0) return api_fail(B200Q4_EINVAL, "program: same_pack without a previous mul_mat");
         const PgOp &pv = ops[(size_t)last_mv];
         if (pv.K != op.K || pv.PP != op.PP || pv.TS != op.TS || pv.C != op.C || res != PG_RES_KEEP)
             return api_fail(B200Q4_EINVAL, "program: same_pack ops must share their input geometry");
         op.pack_of = pv.pack_of;
+        op.pack_seq = pv.pack_seq;
+        op.builder = pv.builder;
+        op.wait_pack = pv.wait_pack;
+    } else {
+        // a layer-norm pack that only re-reads the residual stream can be built in the pause of the pack that updated it,
+        // if it is the very next pack (the two buffers alternate)
+        if (PG_PWARPS == 0 && in_mode == PG_IN_LN && res == PG_RES_KEEP && last_res_pack == n_packs - 1 && last_res_op >= 0)
+            ops[(size_t)last_res_op].cobuild = (int)ops.size();
+        n_packs++;
     }
+    if (in_mode == PG_IN_LN && (res == PG_RES_ADD || res == PG_RES_SET)) last_res_op = (int)ops.size();
     last_mv = (int)ops.size();
     const int nbp = g.PP > 1 ? g.TS * CHUNK_BLKS : ((w->C * CHUNK_BLKS + 7) & ~7);
     if (nbp > nbp_cap) nbp_cap = nbp;
@@ -151,6 +173,10 @@ int prog_finalize(const ProgBuild &b, Prog &out)
         return api_fail(B200Q4_EINVAL, "program: %zu bytes of per-CTA state leave no room for two weight stages", fixed);
     long st = (long)(((size_t)avail - fixed) / stage);
     pg.stages = (int)(st > PG_MAX_STAGES ? PG_MAX_STAGES : st);
+    if (const char *e = getenv("B200Q4_PROG_STAGES")) {  // development: a shallower ring leaves the SM some L1
+        const int v = atoi(e);
+        if (v >= 2 && v < pg.stages) pg.stages = v;
+    }
     pg.smem = fixed + (size_t)pg.stages * stage;
     for (const PgOp &op : b.ops) if (op.kind == PG_MATVEC) pg.n_matvec++;
     // counters: [0] exit, [1 + o] arrivals, tickets, attention head counters
@@ -183,7 +209,7 @@ int prog_finalize(const ProgBuild &b, Prog &out)
     if (e == cudaSuccess) e = cudaMemcpy(pg.d_dyn, dyn0, 16, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(pg.d_err, 0, 16);
     if (e == cudaSuccess && getenv("B200Q4_DBG") && atoi(getenv("B200Q4_DBG")) != 0) {    // timeline builds only (-DB200Q4_TIMELINE)
-        const size_t n = (size_t)pg.grid * pg.n_ops * 8 * sizeof(unsigned long long);
+        const size_t n = ((size_t)pg.grid * pg.n_ops * 8 + (size_t)pg.grid * 16) * sizeof(unsigned long long);
         e = cudaMalloc(&pg.d_dbg, n);
         if (e == cudaSuccess) e = cudaMemset(pg.d_dbg, 0, n);
     }
@@ -281,7 +307,13 @@ b200q4_chain *b200q4_chain_create(int n, const b200q4_weight *const *ws, const f
             y = o.buf;
         }
         // (an unsliced op stores the caller's plain copy itself, next to the tagged one)
-        o.op = b.add_matvec(w, dep, PG_IN_PLAIN, PG_RES_KEEP, &src, 1, nullptr, nullptr, nullptr, y, nullptr, o.stride, o.tagged, false,
+        // consecutive ops on the very same input (Q, K, V) share one activation pack
+        bool same_pack = false;
+        if (i > 0 && d_x[i] == d_x[i - 1] && dep < 0 && ws[i - 1]->K == w->K && (src.kind & 255) == PG_SRC_F32) {
+            const PgGeo gp = pg_geometry(ws[i - 1]);
+            same_pack = gp.PP == g.PP && gp.TS == g.TS && ws[i - 1]->C == w->C;
+        }
+        o.op = b.add_matvec(w, dep, PG_IN_PLAIN, PG_RES_KEEP, &src, 1, nullptr, nullptr, nullptr, y, nullptr, o.stride, o.tagged, same_pack,
                             o.tagged ? d_y[i] : nullptr);
         if (o.op < 0) return bail();
         outs[(size_t)i] = o;
@@ -299,6 +331,9 @@ int b200q4_chain_run(b200q4_chain *c, void *stream)
 {
     ApiLock lk;
     if (!c) return api_fail(B200Q4_EINVAL, "chain_run: NULL chain");
+    if (c->pg.d_dbg)                                      // (timeline builds: the accumulators cover one run)
+        cudaMemsetAsync(c->pg.d_dbg + (size_t)c->pg.grid * c->pg.n_ops * 8, 0, (size_t)c->pg.grid * 16 * sizeof(unsigned long long),
+                        stream ? (cudaStream_t)stream : dev_info().stream);
     return prog_launch(c->pg, stream ? (cudaStream_t)stream : dev_info().stream);
 }
 
@@ -306,7 +341,7 @@ int b200q4_chain_run(b200q4_chain *c, void *stream)
 int b200q4_chain_timeline(const b200q4_chain *c, unsigned long long *out, size_t cap_words)
 {
     if (!c || !c->pg.d_dbg) return B200Q4_EINVAL;
-    const size_t n = (size_t)c->pg.grid * c->pg.n_ops * 8;
+    const size_t n = (size_t)c->pg.grid * c->pg.n_ops * 8 + (size_t)c->pg.grid * 16;
     if (cap_words < n) return B200Q4_EINVAL;
     cudaDeviceSynchronize();
     return cudaMemcpy(out, c->pg.d_dbg, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? c->pg.grid : B200Q4_ECUDA;

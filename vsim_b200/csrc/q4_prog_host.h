@@ -18,6 +18,8 @@ struct ProgBuild {
     int n_tk = 0, n_cnt = 0;             // ticket counters / attention head counters handed out so far
     int rot_acc = 0;                     // running rotation of the static task assignment
     int last_mv = -1;                    // previous mul_mat op (pack reuse)
+    int n_packs = 0;                     // activation packs so far
+    int last_res_pack = -1, last_res_op = -1;   // pack / op during whose construction the residual stream was last updated
     int e_cap = 4, nbp_cap = 8, att_cap = 4;
     // Appends Y = W . quantize(in(sources)); returns the op index or a negative error.  For a K-sliced weight
     // (pg_geometry(w).PP > 1) y receives PP slices of raw sums, y_slice elements apart, and bias must be NULL.
