@@ -60,10 +60,16 @@ def test_device_forward_pass_equals_the_restatement(tmp_path, qt, tag, threads):
 
 @pytest.mark.parametrize("par_res", [1, 0])
 @pytest.mark.parametrize("qt,tag", [(Q4_0, "q4_0"), (Q4_1, "q4_1")])
-def test_decode_program_follows_the_restatement(tmp_path, qt, tag, par_res):
-    """Decode steps as ONE persistent launch (q4_prog_kernel): prompt through the per-op kernels, then greedy decode steps
-    through the program; logits within 1e-3 of the scale of the restated gptneox_eval at every step (both residual
-    variants, vsim.cpp:636-696), and the KV memory it leaves behind serves later steps."""
+def test_decode_program_equals_the_per_op_kernels(tmp_path, monkeypatch, qt, tag, par_res):
+    """Decode steps as ONE persistent launch (q4_prog_kernel) against the per-op kernels the tests above pin to the
+    restated gptneox_eval, both residual variants (vsim.cpp:636-696).  The KV memory is brought to n positions by an
+    exact-mode prompt (bit-identical to the reference on both instances), then ONE fast decode step is compared: the
+    two paths share the mul_mat arithmetic and follow the same graph arithmetic (double-accumulated scores, fp16 exp and
+    gelu tables, layer-norm in double), so they agree to rounding -- 1e-5 of the scale -- at every context length, across
+    the 64-position attention chunks too.  (Steps are compared one at a time because the reference graph re-quantizes
+    its activations to 4 bits at every mul_mat: a rounding-level difference that flips one code shows up as an O(1e-2)
+    jump and stays in the KV memory -- the reference differs from itself that way between thread counts, DESIGN.md.)
+    The program must also be deterministic: the same step twice gives the same bits."""
     import vsim_b200
     from oracle.neox_graph import NeoxOracle
     from tests.helpers.neox_file import write_neox
@@ -71,35 +77,57 @@ def test_decode_program_follows_the_restatement(tmp_path, qt, tag, par_res):
     L = vsim_b200.load_library()
     model = tmp_path / f"p-{tag}-{par_res}.bin"
     write_neox(model, qt, n_vocab=160, n_embd=256, n_head=4, n_layer=3, n_rot=32, seed=11, par_res=par_res)
+    monkeypatch.setenv("B200NEOX_PROGRAM", "1")
+    a = L.b200neox_load(str(model).encode(), 160, 136)
+    monkeypatch.setenv("B200NEOX_PROGRAM", "0")
+    b = L.b200neox_load(str(model).encode(), 160, 136)
+    assert a and b, L.b200neox_last_error()
     g = NeoxOracle(model, n_ctx=160)
-    m = L.b200neox_load(str(model).encode(), 160, 8)
-    assert m, L.b200neox_last_error()
     old = L.b200q4_set_exact(0)
     try:
-        assert L.b200neox_decode_is_program(m) == 1, L.b200neox_last_error()
-        nv = L.b200neox_n_vocab(m)
+        assert L.b200neox_decode_is_program(a) == 1, L.b200neox_last_error()
+        assert L.b200neox_decode_is_program(b) == 0
+        nv = L.b200neox_n_vocab(a)
 
-        def dev(tokens, n_past):
+        def ev(m, tokens, n_past):
             t = np.asarray(tokens, np.int32)
             out = np.empty(nv, np.float32)
             rc = L.b200neox_eval(m, t.ctypes.data, len(tokens), n_past, 1, out.ctypes.data)
             assert rc == 0, L.b200neox_last_error()
             return out
 
-        prompt = [1, 2, 3, 4, 5]
-        lo, ld = g.eval(prompt, 0, 1), dev(prompt, 0)
-        assert np.abs(ld - lo).max() <= 1e-3 * np.abs(lo).max()
-        n_past, nxt = len(prompt), int(np.argmax(lo))
-        launches = vsim_b200.launch_count()
-        for step in range(70):                        # past one attention chunk (64 positions): the merged-partials path too
-            lo, ld = g.eval([nxt], n_past, 1), dev([nxt], n_past)
-            assert np.abs(ld - lo).max() <= 1e-3 * np.abs(lo).max(), (step, np.abs(ld - lo).max(), np.abs(lo).max())
+        rng = np.random.default_rng(3)
+        worst_oracle = 0.0
+        for n in (5, 8, 9, 40, 63, 64, 65, 130):
+            prompt = rng.integers(0, nv, n).tolist()
+            L.b200q4_set_exact(1)
+            ev(a, prompt, 0); ev(b, prompt, 0)                 # identical KV memories, the reference's bits
+            L.b200q4_set_exact(0)
+            tok = int(rng.integers(0, nv))
+            launches = vsim_b200.launch_count()
+            la = ev(a, [tok], n)
+            assert vsim_b200.launch_count() - launches == 1    # one launch per token
+            lb = ev(b, [tok], n)
+            scale = np.abs(lb).max()
+            assert np.abs(la - lb).max() <= 1e-5 * scale, (n, np.abs(la - lb).max(), scale)
+            la2 = ev(a, [tok], n)                              # same step again (it rewrites position n with the same values)
+            assert np.array_equal(la.view(np.uint32), la2.view(np.uint32)), n
+            if n in (5, 65):                                   # and the direct link to the restated reference graph
+                g.eval(prompt, 0, 1)
+                lo = g.eval([tok], n, 1)
+                worst_oracle = max(worst_oracle, float(np.abs(la - lo).max() / np.abs(lo).max()))
+        assert worst_oracle <= 1e-3, worst_oracle
+        # a greedy run: every step one launch, finite logits, token ids in range
+        n_past, nxt = 131, int(np.argmax(la))
+        for _ in range(20):
+            lg = ev(a, [nxt], n_past)
+            assert np.all(np.isfinite(lg))
             n_past += 1
-            nxt = int(np.argmax(lo))
-        assert vsim_b200.launch_count() - launches == 70      # one launch per token
+            nxt = int(np.argmax(lg))
     finally:
         L.b200q4_set_exact(old)
-        L.b200neox_free(m)
+        L.b200neox_free(a)
+        L.b200neox_free(b)
 
 
 def test_exact_mode_serial_residual_graph_is_bit_identical(tmp_path):
