@@ -40,6 +40,7 @@ sys.path.insert(0, str(ROOT))
 K_DIM, N_ROWS = 4096, 16384
 METRIC = "Q4 mul_mat GB/s & %HBM peak"
 L2_BYTES = 126e6
+WORKLOAD = f"Q4_0 mul_mat microbench K={K_DIM} N={N_ROWS} M=1 (BASELINE.json configs[1])"      # the same string in both arms
 
 
 def alg_bytes(qt: int, m: int, n: int = N_ROWS, k: int = K_DIM) -> int:
@@ -256,6 +257,180 @@ def model_decode(vs, L, torch, dist, rank, world, stream, peak, use_nccl, which=
             "tokens_timed": tokens, "launch": mode}
 
 
+def persistent_legs(vs, L, torch, w0, d_x, peak, stream):
+    """The microbench shape through the decode program kernel (q4_prog_kernel, b200q4_chain_*): the 10 rotated weight
+    tensors as ONE persistent launch -- thread blocks stay resident, weights stream without kernel boundaries."""
+    nw = len(w0)
+    xs_shared = [d_x.data_ptr()] * nw
+    x_distinct = torch.randn(nw, K_DIM, device="cuda", dtype=torch.float32)
+    ys = torch.zeros(nw, N_ROWS, device="cuda", dtype=torch.float32)
+    yp = [ys[i].data_ptr() for i in range(nw)]
+    out = {"what": f"{nw} microbench-shape mul_mats (distinct weights, {nw * alg_bytes(0, 0) / 1e6:.0f} MB) in one persistent launch; us per mul_mat"}
+
+    def run(xs, deps, key, note):
+        ch = vs.Chain(w0, xs, yp, deps)
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                ch.run(stream.cuda_stream)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 30
+            e0.record(stream)
+            for _ in range(reps):
+                ch.run(stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / reps / nw * 1e3
+        out[key] = {"us_per_mul_mat": us, "GBps": alg_bytes(0, 1) / us / 1e3, "frac_hbm_peak": alg_bytes(0, 1) / us / 1e3 / peak, "note": note}
+        ch.free()
+
+    run(xs_shared, [-1] * nw, "independent_shared_input",
+        "every op reads the same X (like Q, K, V of one layer): its activation pack is quantized once per launch -- the weight stream alone")
+    run([x_distinct[i].data_ptr() for i in range(nw)], [-1] * nw, "independent_distinct_inputs",
+        "every op quantizes its own X (the full hot path per mul_mat); the pack is built by the 512 consumer threads between two ops")
+    run([d_x.data_ptr()] + [ys[i - 1].data_ptr() for i in range(1, nw)], [-1] + list(range(nw - 1)), "dependent_chain",
+        "op i reads op i-1's output (the first K of it): every link is a true dependency, handed over as {value, tag} pairs")
+    return out
+
+
+def model_decode_full(vs, L, which, peak, n_ctx=512, tokens=32):
+    """BASELINE.json configs[2] / [4]: batch-1 greedy decode of a random-init model in the reference's file format through
+    b200neox_eval -- the WHOLE graph (embedding, both layer-norms, Q/K/V/attention with a 512-token context, MLP with gelu,
+    lm_head): token id in, logits out, one persistent launch per token.  Timed with the host clock around the public C call
+    (H2D of the token, the launch, D2H of the logits, argmax on the host)."""
+    from tools.synth_model import SHAPES, write_model, q4_weight_bytes
+    import shutil
+    shape = SHAPES[which]
+    need = q4_weight_bytes(shape[0], shape[1], shape[3]) + shape[0] * shape[1] * 20 // 32 + (64 << 20)
+    base = None
+    for cand in ("/dev/shm", "/tmp", str(ROOT / "gpurun_out")):
+        try:
+            if Path(cand).is_dir() and shutil.disk_usage(cand).free > need:
+                base = Path(cand)
+                break
+        except OSError:
+            pass
+    if base is None:
+        return {"error": f"no scratch directory with {need / 1e9:.1f} GB free for the synthetic model file"}
+    path = base / f"b200bench_{which}_{os.getpid()}.bin"
+    try:
+        size = write_model(path, *shape)
+        t0 = time.perf_counter()
+        m = L.b200neox_load(str(path).encode(), n_ctx, 8)
+        t_load = time.perf_counter() - t0
+    finally:
+        if path.exists():
+            path.unlink()
+    if not m:
+        return {"error": (L.b200neox_last_error() or b"").decode(errors="replace")}
+    try:
+        nv = L.b200neox_n_vocab(m)
+        out = np.empty(nv, np.float32)
+        prompt = np.array([1, 2, 3, 4, 5], np.int32)
+        if L.b200neox_eval(m, prompt.ctypes.data, 5, 0, 1, out.ctypes.data):
+            return {"error": (L.b200neox_last_error() or b"").decode(errors="replace")}
+        res = {}
+        for label, n0 in (("context_32", 5), ("context_512", n_ctx - tokens)):
+            nxt, n_past = int(out.argmax()), n0
+            t = np.array([nxt], np.int32)
+            L.b200neox_eval(m, t.ctypes.data, 1, n_past, 1, out.ctypes.data)          # warm-up (same position again below)
+            launches = vs.launch_count()
+            t0 = time.perf_counter()
+            for _ in range(tokens):
+                t = np.array([nxt], np.int32)
+                if L.b200neox_eval(m, t.ctypes.data, 1, n_past, 1, out.ctypes.data):
+                    return {"error": (L.b200neox_last_error() or b"").decode(errors="replace")}
+                n_past += 1
+                nxt = int(out.argmax())
+            ms = (time.perf_counter() - t0) / tokens * 1e3
+            res[label] = {"ms_per_token": ms, "tok_per_s": 1e3 / ms, "positions": [n0, n0 + tokens],
+                          "launches_per_token": (vs.launch_count() - launches) / tokens}
+        wb = q4_weight_bytes(shape[0], shape[1], shape[3])
+        ms = res["context_512"]["ms_per_token"]
+        return {"model": f"{which}: n_vocab {shape[0]}, n_embd {shape[1]}, n_head {shape[2]}, n_layer {shape[3]}, n_rot {shape[4]}, "
+                         f"Q4_0, random-init, use_parallel_residual 1, {size / 1e9:.2f} GB file in the reference's format",
+                "scope": "whole graph, token id in / logits out (b200neox_eval): one persistent launch per token",
+                "program": bool(L.b200neox_decode_is_program(m)), "load_and_upload_s": t_load,
+                "tok_per_s": res["context_512"]["tok_per_s"], "ms_per_token": ms, **res,
+                "weight_bytes_per_token": wb, "weight_GBps": wb / ms / 1e6, "frac_hbm_peak": wb / ms / 1e6 / peak,
+                "h2d_bytes_per_token": 8, "d2h_bytes_per_token": nv * 4, "tokens_timed": tokens}
+    finally:
+        L.b200neox_free(m)
+
+
+def prefill_bloom(vs, L, torch, tpeak, stream):
+    """BASELINE.json configs[3]: BLOOM-7b1 Q4_1 prefill of 2048 tokens -- the four Q4_1 mul_mat shapes of that model
+    (n_embd 4096, 30 layers, vocab 250880) at M = 2048 on the tcgen05 tile kernel."""
+    rng = np.random.default_rng(3)
+    m = 2048
+    out, total_ms = [], 0.0
+    for name, n, k, per_layer in (("qkv/dense 4096x4096", 4096, 4096, 4), ("fc_in 16384x4096", 16384, 4096, 1),
+                                  ("fc_out 4096x16384", 4096, 16384, 1), ("lm_head 250880x4096", 250880, 4096, 0)):
+        rb = (k // 32) * 24
+        raw = rng.integers(0, 256, size=(min(n, 8192), rb), dtype=np.uint8)
+        raw[:, : (k // 32) * 8] = np.full((raw.shape[0], k // 32 * 2), 0.01, np.float32).view(np.uint8).reshape(raw.shape[0], -1)
+        raw = np.ascontiguousarray(np.tile(raw, ((n + raw.shape[0] - 1) // raw.shape[0], 1))[:n])
+        w = vs.Q4Weight(1, raw, n, k)
+        x = torch.randn(m, k, device="cuda", dtype=torch.float32)
+        y = torch.empty(m, n, device="cuda", dtype=torch.float32)
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                L.b200q4_mul_mat_dev(w.handle, x.data_ptr(), m, 0, y.data_ptr(), 0, stream.cuda_stream)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            e0.record(stream)
+            for _ in range(reps):
+                L.b200q4_mul_mat_dev(w.handle, x.data_ptr(), m, 0, y.data_ptr(), 0, stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
+        out.append({"shape": name, "ms": ms, "TFLOPs": tf, "frac_bf16_peak": tf / tpeak})
+        total_ms += ms * (per_layer * 30 if per_layer else 1)
+        w.free()
+        del x, y
+    return {"workload": "BLOOM-7b1 shapes, Q4_1, M = 2048 (BASELINE.json configs[3])", "shapes": out,
+            "q4_mul_mat_ms_per_2048_token_prompt": total_ms,
+            "note": "the Q4_1 mul_mats of one 2048-token prompt (30 layers x 6 + lm_head); includes the activation pack kernels"}
+
+
+def exchange_parity(vs, L, torch, dist, rank, world, stream):
+    """N > 1: the fused all-gather's Y on EVERY rank against a single-GPU b200q4_mul_mat_dev on the unsharded tensor,
+    bit for bit (no reduction crosses GPUs: imax.c:1185-1188 splits by output rows).  M = 1 and M = 8, an unsliced and a
+    K-sliced shape.  Returns {max_abs_diff, ranks_checked, cases}; the caller fails the run on a mismatch."""
+    from vsim_b200.shard import PeerOutput, shard_rows
+    rng = np.random.default_rng(4242)                      # the same on every rank
+    worst, cases = 0.0, 0
+    po = PeerOutput(L, 8, 4096)
+    for n, k in ((4096, 4096), (2048, 16384)):
+        raw = rng.integers(0, 256, size=(n, (k // 32) * 20), dtype=np.uint8)
+        raw.reshape(n, k // 32, 20)[:, :, :4] = np.full((n, k // 32), 0.01, np.float32).view(np.uint8).reshape(n, k // 32, 4)
+        full = vs.Q4Weight(0, raw, n, k)
+        r0, nr = shard_rows(n, world, rank)
+        shard = vs.Q4Weight(0, raw, n, k, row0=r0, nrows=nr)
+        for m in (1, 8):
+            x = torch.from_numpy(rng.standard_normal((m, k)).astype(np.float32)).cuda()
+            y_one = torch.empty(m, n, device="cuda", dtype=torch.float32)
+            with torch.cuda.stream(stream):
+                for _ in range(2):                         # both ping-pong buffers
+                    y = po.mul_mat(shard, x, m, n_total=n, stream=stream).clone()
+                rc = L.b200q4_mul_mat_dev(full.handle, x.data_ptr(), m, 0, y_one.data_ptr(), 0, stream.cuda_stream)
+                if rc:
+                    raise RuntimeError(vs.lib._err(L))
+                torch.cuda.synchronize()
+            bits_equal = torch.equal(y.view(torch.int32), y_one.view(torch.int32))
+            diff = float((y - y_one).abs().max())
+            worst = max(worst, diff if not bits_equal else 0.0)
+            cases += 1
+        full.free(); shard.free()
+    t = torch.tensor([worst], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"max_abs_diff": float(t.item()), "ranks_checked": world, "cases_per_rank": cases,
+            "what": "gathered Y of the fused exchange vs single-GPU b200q4_mul_mat_dev on the unsharded tensor, bit for bit: "
+                    "Q4_0, (N, K) in {(4096, 4096), (2048, 16384) K-sliced}, M in {1, 8}"}
+
+
 def prefill_roofline(points, tpeak, tpeak_src, world):
     """The M=512 point of the tcgen05 tile kernel against the measured dense bf16 tensor peak (the judge's
     yardstick for the prefill path); the kernel's own bound is TMEM read bandwidth, see DESIGN.md."""
@@ -304,7 +479,7 @@ def run_reference(args) -> int:
         "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (scalar fp32 dequant-dot, ggml.c:472-553)", "data": "synthetic",
-        "config": {"workload": f"Q4_0 mul_mat microbench K={K_DIM} N={N_ROWS} M={m} (BASELINE.json configs[1])",
+        "config": {"workload": WORKLOAD,
                    "step": "one ggml_graph_compute of a resident ggml_mul_mat node (reference ggml.c scheduler, "
                            "quantize_row_q4_0 + IMAX-hook scalar loop, host memory)" if have_ref else "one q4o_mul_mat call",
                    "threads": nth},
@@ -390,9 +565,9 @@ def main() -> int:
             for i in range(warm):
                 step(i, m, ws, stream, nccl)
             graph, gsteps = None, len(ws)
-            if po is not None and not nccl and steps >= gsteps:
-                # N>1 product path: the exchange is sequenced on the device, so one rotation over the weight
-                # tensors is captured as a CUDA graph and replayed -- no host work between dependent launches
+            if (po is not None or world == 1) and not nccl and steps >= gsteps and not getattr(timed, "no_graph", False):
+                # One rotation over the weight tensors is captured as a CUDA graph and replayed, so that the timed loop is
+                # not bound by Python / ctypes between 9 us launches (N>1: the exchange is sequenced on the device)
                 barrier()
                 try:
                     graph = torch.cuda.CUDAGraph()
@@ -503,10 +678,30 @@ def main() -> int:
         ms_nccl = timed(M_HEAD, w0, min(args.steps, 200), 5, nccl=True) / min(args.steps, 200)
         exchange = {"fused_peer_store_us_per_step": ms_step * 1e3, "nccl_all_gather_us_per_step": ms_nccl * 1e3,
                     "bytes_per_rank_per_step": M_HEAD * N_ROWS * 4}
-    model = model20 = None
+    if world > 1 and po is not None:
+        exchange = exchange or {}
+        exchange["parity"] = exchange_parity(vs, L, torch, dist, rank, world, stream)
+    persistent = prefill = None
+    if world == 1 and not args.no_points:
+        persistent = persistent_legs(vs, L, torch, w0, d_x, peak, stream)
+        prefill = prefill_bloom(vs, L, torch, tpeak, stream)
+    model = model20 = full = full20 = None
     if not args.no_model:
         model = model_decode(vs, L, torch, dist, rank, world, stream, peak, args.nccl, "gptj6b")
         model20 = model_decode(vs, L, torch, dist, rank, world, stream, peak, args.nccl, "neox20b", tokens=12)
+        if world == 1:                                     # the whole graph through b200neox_eval (one persistent launch per token)
+            for w in w0:
+                w.free()
+            w0 = []
+            for which in ("gptj6b", "neox20b"):
+                try:
+                    r = model_decode_full(vs, L, which, peak, tokens=32 if which == "gptj6b" else 16)
+                except Exception as e:                     # noqa: BLE001  (a scratch-space or memory problem must not lose the bench line)
+                    r = {"error": repr(e)}
+                if which == "gptj6b":
+                    full = r
+                else:
+                    full20 = r
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -523,8 +718,8 @@ def main() -> int:
             "dtype": "u8 x s8 -> s32 block sums (IMMA, decode M<=8) / e4m3 x e4m3 -> f32 block sums + bf16x3 scale products "
                      "(tcgen05, M>=9); fp32 accumulation", "data": "synthetic",
             "config": {
-                "workload": f"Q4_0 mul_mat microbench K={K_DIM} N={N_ROWS} M={M_HEAD} per GPU (BASELINE.json configs[1]; "
-                            f"decode GEMV); other (type, M) points under 'points'",
+                "workload": WORKLOAD,
+                "detail": f"K={K_DIM}, N={N_ROWS} weight rows per GPU, M={M_HEAD} (decode GEMV); other (type, M) points under 'points'",
                 "weights": "random-init fp32 U(-0.05,0.05), seed 1234, quantized to the reference Q4 row format",
                 "activations": "fp32 N(0,1), seed 5678, quantized on the device every step",
                 "l2": f"defeated: every loop rotates over {nw} distinct {alg_bytes(0, 0) / 1e6:.0f} MB weight tensors "
@@ -543,6 +738,7 @@ def main() -> int:
                     "api": "b200q4_mul_mat (C ABI, pinned host X and Y, synchronous): fetch kernel pulls X over PCIe, the decode "
                            "epilogue stores Y into the host buffer, completion = polled host word"},
             "gpu_launches": int(launches_timed),
+            "timed_loop": "a CUDA graph of one rotation over the weight tensors, replayed" if getattr(timed, "graphed", False) else "eager launches",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": "q4_gemv_pipe_kernel<Q4_0, chain4, fused quantization> (M=1: one launch per call), CUDA events on "
@@ -552,8 +748,12 @@ def main() -> int:
             "points": points,
             "roofline_prefill": prefill_roofline(points, tpeak, tpeak_src, world),
             "exact_mode": exact,
+            "persistent": persistent,
+            "prefill_bloom7b1_2048": prefill,
             "model_decode": model,
             "model_decode_neox20b": model20,
+            "model_decode_full": full,
+            "model_decode_full_neox20b": full20,
             "exchange": exchange,
             "checksum_y": float(np.abs(y_e2e).sum()),
         }
@@ -564,9 +764,13 @@ def main() -> int:
     L.b200q4_host_free(hy)
     for w in w0:
         w.free()
+    bad_parity = bool(world > 1 and exchange and exchange.get("parity") and exchange["parity"]["max_abs_diff"] != 0.0)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if bad_parity:
+        sys.stderr.write("bench.py: the fused all-gather's Y differs from the single-GPU result\n")
+        return 3
     return 0
 
 

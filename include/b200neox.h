@@ -35,6 +35,17 @@ b200neox *b200neox_load(const char *path, int n_ctx, int max_batch);
 int  b200neox_n_vocab(const b200neox *m);
 /* gptneox_eval(model, n_threads, n_past, tokens[N]) -> logits of the last token (host, n_vocab floats) */
 int  b200neox_eval(b200neox *m, const int *tokens, int N, int n_past, int n_threads_emulated, float *logits_out);
+/* ---- row-sharded decode over the GPUs of one NVLink domain ---------------------------------------
+ * One process per GPU.  Rank `rank` of `world` (<= 8) owns rows [rank N/world, (rank+1) N/world) of every 2-D tensor -- the
+ * split the reference's threads use (imax.c:1185-1188) -- and heads [rank H/world, ...): Q, K, V and the KV memory stay
+ * local; every other vector a later op reads (attention output, MLP hidden and output, logits) is stored by the thread
+ * blocks that compute it straight into EVERY rank's exchange pool over NVLink, as {value, tag} pairs the readers poll: no
+ * collective call, no fence, no reduction across GPUs (results equal the single-GPU program's bit for bit).
+ *   pool_peers[r]  rank r's exchange pool mapped into this process (CUDA IPC / symmetric memory; entry `rank` is local),
+ *                  b200neox_sharded_pool_bytes() bytes, zero-initialised, at the same layout on every rank.
+ * Every rank calls b200neox_eval with the same token and n_past (N = 1, exact mode off); each gets the full logits.     */
+size_t b200neox_sharded_pool_bytes(int n_vocab, int n_embd, int n_layer);
+b200neox *b200neox_load_sharded(const char *path, int n_ctx, int rank, int world, void *const *pool_peers, size_t pool_bytes);
 /* 1 when decode steps run as one persistent launch, 0 when they fall back to one kernel per op (b200neox_last_error says why) */
 int  b200neox_decode_is_program(const b200neox *m);
 void b200neox_free(b200neox *m);

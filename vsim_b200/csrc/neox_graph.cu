@@ -244,6 +244,11 @@ struct b200neox {
     int *ids = nullptr;
     int max_n = 0;
     cudaStream_t st = nullptr;                           // the library's stream: all device work of this process is ordered on it
+    // row-sharded over `world` GPUs (decode program only): this rank's shards, the peers' exchange pools
+    int rank = 0, world = 1;
+    std::vector<b200q4_weight *> shards;                 // owned (the file's own tensors are not uploaded when sharded)
+    char *pool[8] = {nullptr};
+    size_t pool_bytes = 0;
     // decode program (one persistent launch per token)
     b200q4::Prog prog;
     bool have_prog = false;
@@ -256,11 +261,45 @@ namespace {
 using namespace b200q4;
 
 // Compiles one decode step (N = 1) into a work-list for q4_prog_kernel.  Graph: gptneox_eval, vsim.cpp:518-718.
+// Exchange-pool layout of a sharded program: [counters][per layer: attention output, MLP hidden, MLP output (K-slice
+// partials), attention projection][logits], every vector as {value, tag} pairs.  The same on every rank.
+struct PoolLayout {
+    size_t ctr_bytes, total;
+    size_t att, hid, out, proj, layer_stride, logits;
+    int pp_out, pp_hid, pp_proj, pp_head, st_E, st_H, st_V;
+};
+PoolLayout pool_layout(int E, int L, int V, int n_ops_bound)
+{
+    PoolLayout p{};
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    p.st_E = (E + 3) & ~3; p.st_H = (4 * E + 3) & ~3; p.st_V = (V + 3) & ~3;
+    p.pp_proj = pg_geometry_dims(E, E).PP;                 // (the slicing depends on K only: a shard slices like the full tensor)
+    p.pp_hid = pg_geometry_dims(4 * E, E).PP;
+    p.pp_out = pg_geometry_dims(E, 4 * E).PP;
+    p.pp_head = pg_geometry_dims(V, E).PP;
+    p.ctr_bytes = al((size_t)n_ops_bound * 4);
+    size_t off = 0;
+    p.att = off; off += al((size_t)2 * p.st_E * 4);
+    p.hid = off; off += al((size_t)2 * p.pp_hid * p.st_H * 4);
+    p.out = off; off += al((size_t)2 * p.pp_out * p.st_E * 4);
+    p.proj = off; off += al((size_t)2 * p.pp_proj * p.st_E * 4);
+    p.layer_stride = off;
+    p.logits = p.ctr_bytes + (size_t)L * p.layer_stride;
+    p.total = p.logits + al((size_t)2 * p.pp_head * p.st_V * 4);
+    return p;
+}
+int ops_bound(int L) { return 64 + 16 * (L * 8 + 4) + 8 * 64 * (L + 1); }      // counters: arrivals, tickets (<= 8 classes), head counters
+
+// Compiles one decode step (N = 1) into a work-list for q4_prog_kernel.  Graph: gptneox_eval, vsim.cpp:518-718.
+// world > 1: rank g owns rows [g N/G, (g+1) N/G) of every 2-D tensor (imax.c:1185-1188) and heads [g H/G, (g+1) H/G);
+// Q, K, V and the KV memory stay local, every other vector is stored by its producers into EVERY rank's exchange pool.
 int build_decode_program(b200neox *m)
 {
-    const int E = m->n_embd, H = m->n_head, d = E / H, L = m->n_layer, V = m->n_vocab;
+    const int E = m->n_embd, H = m->n_head, d = E / H, L = m->n_layer, V = m->n_vocab, G = m->world, R = m->rank;
     if (d > PG_ATT_MAX_D) { m->prog_why = "head size above 512"; return 1; }
     if (m->wte_type != m->ftype - 2) { m->prog_why = "embedding matrix of another quant type"; return 1; }
+    const int Hl = H / G, El = E / G;
+    const PoolLayout pl = pool_layout(E, L, V, ops_bound(L));
     ProgBuild b;
     auto dev = [&](size_t floats) {
         float *p = nullptr;
@@ -269,38 +308,47 @@ int build_decode_program(b200neox *m)
         m->prog_bufs.push_back(p);
         return p;
     };
+    auto pool_ptr = [&](int r, size_t off) { return reinterpret_cast<float *>(m->pool[r] + off); };
     // Every vector an op hands to a later op is a buffer of {value, tag} pairs (q4_prog.cuh): the reader polls the data.
     // The output of a mul_mat as a list of sources: the finished vector, or its K-slice partials plus the bias.
     struct Out { std::vector<PgSrc> src; int op; float *buf; };
     bool oom = false;
+    // xoff: sharded and exchanged -> offset of the (full) vector in every rank's pool; (size_t)-1: a local vector
     auto matvec = [&](b200q4_weight *w, const float *bias, int in_mode, int res, const std::vector<PgSrc> &src,
-                      const float *lw, const float *lb, float *plain_y, bool same_pack) {
+                      const float *lw, const float *lb, float *plain_y, bool same_pack, size_t xoff, int stride_full) {
         Out o;
         o.buf = nullptr;
         const PgGeo g = pg_geometry(w);
-        const int N = b200q4_weight_rows(w);
+        const int Nl = b200q4_weight_rows(w);
+        const bool exch = G > 1 && xoff != (size_t)-1;
+        const int row0 = exch ? R * Nl : 0;
+        const int stride = exch ? stride_full : (Nl + 3) & ~3;
+        float *y = plain_y;
+        if (!y) y = exch ? pool_ptr(R, xoff) : dev(2 * (size_t)g.PP * stride);
+        if (!y) { oom = true; o.op = -1; return o; }
         if (g.PP == 1) {
-            float *y = plain_y ? plain_y : dev(2 * (size_t)N);
-            if (!y) { oom = true; o.op = -1; return o; }
-            o.op = b.add_matvec(w, -1, in_mode, res, src.data(), (int)src.size(), lw, lb, m->t_gelu, y, bias, 0, !plain_y, same_pack);
+            o.op = b.add_matvec(w, -1, in_mode, res, src.data(), (int)src.size(), lw, lb, m->t_gelu, y, bias ? bias + row0 : nullptr, 0,
+                                !plain_y, same_pack);
             o.src.push_back(pg_src_tag(y, o.op));
-            o.buf = y;
         } else {
-            const int stride = (N + 3) & ~3;
-            float *part = dev(2 * (size_t)g.PP * stride);
-            if (!part) { oom = true; o.op = -1; return o; }
-            o.op = b.add_matvec(w, -1, in_mode, res, src.data(), (int)src.size(), lw, lb, m->t_gelu, part, nullptr, stride, true, same_pack);
-            o.src.push_back(pg_src_tag(part, o.op, g.PP, stride));
+            o.op = b.add_matvec(w, -1, in_mode, res, src.data(), (int)src.size(), lw, lb, m->t_gelu, y, nullptr, stride, true, same_pack);
+            o.src.push_back(pg_src_tag(y, o.op, g.PP, stride));
             if (bias) o.src.push_back(pg_src_f32(bias));
-            o.buf = part;
         }
+        if (o.op >= 0 && exch) {
+            PgOp &op = b.ops[(size_t)o.op];
+            op.row0 = row0;
+            for (int r = 0; r < G; r++) op.y_peer[r] = pool_ptr(r, xoff);
+        }
+        o.buf = y;
         return o;
     };
-    float *att = dev(2 * (size_t)E);
+    const size_t LOCAL = (size_t)-1;
     const size_t chunks = (size_t)(m->n_ctx + PG_ATT_CHUNK - 1) / PG_ATT_CHUNK;
-    float *part = dev((size_t)H * chunks * d), *att_sc = dev((size_t)H * (m->n_ctx + chunks));
-    double *att_sum = reinterpret_cast<double *>(dev(2 * (size_t)H * chunks + 2));
-    if (!att || !part || !att_sc || !att_sum) { m->prog_why = "device allocation failed"; return 1; }
+    float *part = dev((size_t)Hl * chunks * d), *att_sc = dev((size_t)Hl * (m->n_ctx + chunks));
+    double *att_sum = reinterpret_cast<double *>(dev(2 * (size_t)Hl * chunks + 2));
+    float *att_local = G == 1 ? dev(2 * (size_t)E) : nullptr;
+    if (!part || !att_sc || !att_sum || (G == 1 && !att_local)) { m->prog_why = "device allocation failed"; return 1; }
     const float scale = (float)(1.0 / sqrt((double)((float)E / (float)H)));                  // vsim.cpp:590
     // what the next layer-norm op has to add to the residual stream first
     std::vector<PgSrc> pending;
@@ -312,26 +360,36 @@ int build_decode_program(b200neox *m)
     auto chk = [&](const Out &o) { if (o.op < 0) bad = true; return o; };
     for (int l = 0; l < L && !bad; l++) {
         const NeoxLayer &ly = m->layers[(size_t)l];
-        float *mk = m->mem_k + (size_t)l * m->n_ctx * E, *mv = m->mem_v + (size_t)l * m->n_ctx * E;
+        float *mk = m->mem_k + (size_t)l * m->n_ctx * El, *mv = m->mem_v + (size_t)l * m->n_ctx * El;
+        const size_t lo = pl.ctr_bytes + (size_t)l * pl.layer_stride;
         if ((int)pending.size() > PG_MAX_SRC) { m->prog_why = "too many residual sources"; return 1; }
         // (per-layer output buffers: a vector is only overwritten by ops that cannot start before all its readers are done)
-        const Out oq = chk(matvec(ly.wq, ly.bq, PG_IN_LN, pending_res, pending, ly.ln1_w, ly.ln1_b, nullptr, false));
-        const Out ok = chk(matvec(ly.wk, ly.bk, PG_IN_LN, PG_RES_KEEP, none, ly.ln1_w, ly.ln1_b, nullptr, true));
-        const Out ov = chk(matvec(ly.wv, ly.bv, PG_IN_LN, PG_RES_KEEP, none, ly.ln1_w, ly.ln1_b, nullptr, true));
+        const Out oq = chk(matvec(ly.wq, ly.bq ? ly.bq + R * El : nullptr, PG_IN_LN, pending_res, pending, ly.ln1_w, ly.ln1_b, nullptr, false, LOCAL, 0));
+        const Out ok = chk(matvec(ly.wk, ly.bk ? ly.bk + R * El : nullptr, PG_IN_LN, PG_RES_KEEP, none, ly.ln1_w, ly.ln1_b, nullptr, true, LOCAL, 0));
+        const Out ov = chk(matvec(ly.wv, ly.bv ? ly.bv + R * El : nullptr, PG_IN_LN, PG_RES_KEEP, none, ly.ln1_w, ly.ln1_b, nullptr, true, LOCAL, 0));
         if (bad) break;
         if (oq.src.size() != 1 || oq.src[0].np != 1) { m->prog_why = "n_embd above 8192 (K-sliced Q/K/V)"; return 1; }
         pending.clear();
-        auto attn = [&]() { return b.add_attn(-1, oq.buf, ok.buf, ov.buf, oq.op, ok.op, ov.op, mk, mv, att, part, att_sc, att_sum,
-                                              m->rope_cs, m->t_exp, H, d, m->n_rot, m->n_ctx, scale); };
+        float *att = G == 1 ? att_local : pool_ptr(R, lo + pl.att);
+        auto attn = [&]() {
+            const int oa = b.add_attn(-1, oq.buf, ok.buf, ov.buf, oq.op, ok.op, ov.op, mk, mv, att, part, att_sc, att_sum,
+                                      m->rope_cs, m->t_exp, Hl, d, m->n_rot, m->n_ctx, scale);
+            if (oa >= 0 && G > 1) {
+                PgOp &op = b.ops[(size_t)oa];
+                op.head0 = R * Hl;
+                for (int r = 0; r < G; r++) op.att_peer[r] = pool_ptr(r, lo + pl.att);
+            }
+            return oa;
+        };
         if (m->par_res == 1) {
             // vsim.cpp:666-696: the MLP reads the layer input, so its first matrix needs nothing from the attention
-            const Out o1 = chk(matvec(ly.w1, ly.b1, PG_IN_LN, PG_RES_KEEP, none, ly.ln2_w, ly.ln2_b, nullptr, false));
+            const Out o1 = chk(matvec(ly.w1, ly.b1, PG_IN_LN, PG_RES_KEEP, none, ly.ln2_w, ly.ln2_b, nullptr, false, lo + pl.hid, pl.st_H));
             if (bad) break;
             const int oa = attn();
-            const Out o2 = chk(matvec(ly.w2, ly.b2, PG_IN_GELU, PG_RES_KEEP, o1.src, nullptr, nullptr, nullptr, false));
+            const Out o2 = chk(matvec(ly.w2, ly.b2, PG_IN_GELU, PG_RES_KEEP, o1.src, nullptr, nullptr, nullptr, false, lo + pl.out, pl.st_E));
             if (bad || oa < 0) { bad = true; break; }
             const std::vector<PgSrc> a_in{pg_src_tag(att, oa)};
-            const Out oo = chk(matvec(ly.wo, ly.bo, PG_IN_PLAIN, PG_RES_KEEP, a_in, nullptr, nullptr, nullptr, false));
+            const Out oo = chk(matvec(ly.wo, ly.bo, PG_IN_PLAIN, PG_RES_KEEP, a_in, nullptr, nullptr, nullptr, false, lo + pl.proj, pl.st_E));
             if (bad) break;
             pending = oo.src;                                                                // inpL = inpL + (cur + inpFF)
             pending.insert(pending.end(), o2.src.begin(), o2.src.end());
@@ -340,11 +398,11 @@ int build_decode_program(b200neox *m)
             const int oa = attn();
             if (oa < 0) { bad = true; break; }
             const std::vector<PgSrc> a_in{pg_src_tag(att, oa)};
-            const Out oo = chk(matvec(ly.wo, ly.bo, PG_IN_PLAIN, PG_RES_KEEP, a_in, nullptr, nullptr, nullptr, false));
+            const Out oo = chk(matvec(ly.wo, ly.bo, PG_IN_PLAIN, PG_RES_KEEP, a_in, nullptr, nullptr, nullptr, false, lo + pl.proj, pl.st_E));
             if (bad) break;
-            const Out o1 = chk(matvec(ly.w1, ly.b1, PG_IN_LN, PG_RES_TEMP, oo.src, ly.ln2_w, ly.ln2_b, nullptr, false));
+            const Out o1 = chk(matvec(ly.w1, ly.b1, PG_IN_LN, PG_RES_TEMP, oo.src, ly.ln2_w, ly.ln2_b, nullptr, false, lo + pl.hid, pl.st_H));
             if (bad) break;
-            const Out o2 = chk(matvec(ly.w2, ly.b2, PG_IN_GELU, PG_RES_KEEP, o1.src, nullptr, nullptr, nullptr, false));
+            const Out o2 = chk(matvec(ly.w2, ly.b2, PG_IN_GELU, PG_RES_KEEP, o1.src, nullptr, nullptr, nullptr, false, lo + pl.out, pl.st_E));
             if (bad) break;
             pending = o2.src;
         }
@@ -353,11 +411,18 @@ int build_decode_program(b200neox *m)
     if (!bad) {
         if ((int)pending.size() > PG_MAX_SRC) { m->prog_why = "too many residual sources"; return 1; }
         const PgGeo g = pg_geometry(m->w_head);
-        Out oh = chk(matvec(m->w_head, nullptr, PG_IN_LN, pending_res, pending, m->lnf_w, m->lnf_b, g.PP == 1 ? m->logits : nullptr, false));
-        if (!bad && g.PP > 1 && b.add_sum(-1, oh.src[0], m->logits, V) < 0) bad = true;
+        const bool plain = G == 1 && g.PP == 1;                                              // (sharded: the slices meet in the pool first)
+        Out oh = chk(matvec(m->w_head, nullptr, PG_IN_LN, pending_res, pending, m->lnf_w, m->lnf_b, plain ? m->logits : nullptr, false,
+                            pl.logits, pl.st_V));
+        if (!bad && !plain && b.add_sum(-1, oh.src[0], m->logits, V) < 0) bad = true;
     }
     if (bad) { m->prog_why = oom ? "device allocation failed" : std::string("program builder: ") + b200q4_last_error(); return 1; }
-    if (prog_finalize(b, m->prog)) { m->prog_why = std::string("program: ") + b200q4_last_error(); return 1; }
+    if (G > 1) {
+        if (prog_counter_ints(b) * 4 > (int)pl.ctr_bytes) { m->prog_why = "counter area of the exchange pool too small"; return 1; }
+        int *ctrs[8];
+        for (int r = 0; r < G; r++) ctrs[r] = reinterpret_cast<int *>(m->pool[r]);
+        if (prog_finalize_sharded(b, m->prog, R, G, ctrs)) { m->prog_why = std::string("program: ") + b200q4_last_error(); return 1; }
+    } else if (prog_finalize(b, m->prog)) { m->prog_why = std::string("program: ") + b200q4_last_error(); return 1; }
     m->have_prog = true;
     return 0;
 }
@@ -374,6 +439,7 @@ void b200neox_free(b200neox *m)
     if (m->st) cudaStreamSynchronize(m->st);
     if (m->have_prog) b200q4::prog_free(m->prog);
     for (float *p : m->prog_bufs) cudaFree(p);
+    for (b200q4_weight *w : m->shards) b200q4_weight_free(w);
     for (float *p : m->f32) cudaFree(p);
     float *bufs[] = {m->mem_k, m->mem_v, m->x, m->cur, m->q, m->k, m->v, m->att, m->ff, m->ff2, m->kq, m->merged, m->logits};
     for (float *b : bufs) cudaFree(b);
@@ -382,13 +448,18 @@ void b200neox_free(b200neox *m)
     delete m;
 }
 
-b200neox *b200neox_load(const char *path, int n_ctx, int max_batch)
+static b200neox *neox_load_impl(const char *path, int n_ctx, int max_batch, int rank, int world, void *const *pool_peers, size_t pool_bytes)
 {
-    if (!path || n_ctx < 1 || max_batch < 1) { nfail(B200Q4_EINVAL, "neox_load: bad argument"); return nullptr; }
-    b200q4_model *f = b200q4_model_load(path, 7, 0, 1);           // vsim.cpp:119-138: 7 header ints, no vocabulary count
+    if (!path || n_ctx < 1 || max_batch < 1 || world < 1 || world > 8 || rank < 0 || rank >= world || (world > 1 && !pool_peers)) {
+        nfail(B200Q4_EINVAL, "neox_load: bad argument");
+        return nullptr;
+    }
+    b200q4_model *f = b200q4_model_load(path, 7, 0, world == 1 ? 1 : 0);   // vsim.cpp:119-138: 7 header ints, no vocabulary count
     if (!f) { nfail(B200Q4_EINVAL, std::string("neox_load: ") + b200q4_last_error()); return nullptr; }
     b200neox *m = new b200neox();
     m->file = f;
+    m->rank = rank; m->world = world; m->pool_bytes = pool_bytes;
+    for (int r = 0; r < world && pool_peers; r++) m->pool[r] = static_cast<char *>(pool_peers[r]);
     int *hp[] = {&m->n_vocab, &m->n_embd, &m->n_head, &m->n_layer, &m->n_rot, &m->par_res, &m->ftype};
     for (int i = 0; i < 7; i++) *hp[i] = b200q4_model_header(f, i);
     m->n_ctx = n_ctx; m->max_n = max_batch;
@@ -398,6 +469,12 @@ b200neox *b200neox_load(const char *path, int n_ctx, int max_batch)
     if (m->n_embd % 32 || m->n_embd % m->n_head || m->n_rot % 2 || m->n_rot > m->n_embd / m->n_head) return bail("bad hyper-parameters");
     if (m->par_res != 0 && m->par_res != 1) return bail("use_parallel_residual must be 0 or 1 (vsim.cpp:697-700)");
     if (m->ftype != 2 && m->ftype != 3) return bail("only q4_0 / q4_1 model files are built (ftype 2 / 3)");
+    if (world > 1) {
+        if (m->n_head % world || m->n_embd % (16 * world) || m->n_vocab % world)
+            return bail("the model does not shard evenly over this many GPUs (heads, 16-row tiles of n_embd, vocabulary rows)");
+        for (int r = 0; r < world; r++) if (!m->pool[r]) return bail("NULL exchange pool");
+        if (pool_bytes < pool_layout(m->n_embd, m->n_layer, m->n_vocab, ops_bound(m->n_layer)).total) return bail("exchange pool too small");
+    }
     m->st = b200q4::dev_info().stream;
     if (!m->st) return bail("b200q4_init() has not succeeded");
     const int E = m->n_embd, V = m->n_vocab;
@@ -433,7 +510,12 @@ b200neox *b200neox_load(const char *path, int n_ctx, int max_batch)
         if (nd != 2 || ne0 != K || ne1 != N) { if (err.empty()) err = "tensor '" + name + "' has wrong shape in model file"; return nullptr; }
         if (ft != m->ftype) { if (err.empty()) err = "tensor '" + name + "' is not of the file's quant type"; return nullptr; }
         if (tensor_index) *tensor_index = it->second;
-        return b200q4_model_weight(f, it->second);
+        if (world == 1 || tensor_index) return b200q4_model_weight(f, it->second);        // (tensor_index: the caller only wants the record)
+        // sharded: this rank's rows [rank N/G, (rank+1) N/G) straight from the file mapping (imax.c:1185-1188 splits by rows)
+        b200q4_weight *w = b200q4_weight_upload_rows(ft - 2, b200q4_model_tensor_data(f, it->second), N, K, 0, rank * (N / world), N / world);
+        if (!w) { if (err.empty()) err = std::string("shard upload failed: ") + b200q4_last_error(); return nullptr; }
+        m->shards.push_back(w);
+        return w;
     };
     int wte_index = -1;
     mat("gpt_neox.embed_in.weight", E, V, &wte_index);
@@ -479,7 +561,7 @@ b200neox *b200neox_load(const char *path, int n_ctx, int max_batch)
             const double theta = pow(10000.0, 2 * ((double)-i0) / m->n_rot);             // ggml.c:6126
             cs[(size_t)p * half + i0] = make_double2(cos(p * theta), sin(p * theta));
         }
-    const size_t Es = (size_t)E, Nmax = (size_t)max_batch, kv = (size_t)m->n_layer * n_ctx * Es * 4 + 16;
+    const size_t Es = (size_t)E, Nmax = (size_t)max_batch, kv = (size_t)m->n_layer * n_ctx * (Es / world) * 4 + 16;
     bool ok = cudaMalloc(&m->t_gelu, 1 << 17) == cudaSuccess && cudaMalloc(&m->t_exp, 1 << 17) == cudaSuccess &&
               cudaMalloc(&m->rope_cs, cs.size() * sizeof(double2) + 16) == cudaSuccess &&
               cudaMalloc(&m->mem_k, kv) == cudaSuccess && cudaMalloc(&m->mem_v, kv) == cudaSuccess &&
@@ -501,6 +583,25 @@ b200neox *b200neox_load(const char *path, int n_ctx, int max_batch)
     return m;
 }
 
+b200neox *b200neox_load(const char *path, int n_ctx, int max_batch) { return neox_load_impl(path, n_ctx, max_batch, 0, 1, nullptr, 0); }
+
+b200neox *b200neox_load_sharded(const char *path, int n_ctx, int rank, int world, void *const *pool_peers, size_t pool_bytes)
+{
+    b200neox *m = neox_load_impl(path, n_ctx, 1, rank, world, pool_peers, pool_bytes);
+    if (m && world > 1 && !m->have_prog) {                // a sharded model has nothing but the decode program
+        nfail(B200Q4_EINVAL, "neox_load_sharded: " + m->prog_why);
+        b200neox_free(m);
+        return nullptr;
+    }
+    return m;
+}
+
+size_t b200neox_sharded_pool_bytes(int n_vocab, int n_embd, int n_layer)
+{
+    if (n_vocab < 1 || n_embd < 32 || n_layer < 0) return 0;
+    return pool_layout(n_embd, n_layer, n_vocab, ops_bound(n_layer)).total;
+}
+
 int b200neox_n_vocab(const b200neox *m) { return m ? m->n_vocab : B200Q4_EINVAL; }
 
 /* 1 when decode steps run as one persistent launch; 0 (and why, through b200neox_last_error) when not */
@@ -520,6 +621,8 @@ int b200neox_eval(b200neox *m, const int *tokens, int N, int n_past, int n_threa
     const int E = m->n_embd, H = m->n_head, d = E / H, P = n_past + N, nth = n_threads_emulated;
     cudaStream_t st = m->st;
     const bool exact = b200q4_exact_enabled() != 0;                                          // exact mode covers the graph ops too
+    if (m->world > 1 && (N != 1 || exact || !m->have_prog))
+        return nfail(B200Q4_EINVAL, "neox_eval: a sharded model runs decode steps (N = 1, exact mode off) only");
     if (N == 1 && !exact && m->have_prog) {
         // one token = one persistent launch: ids in, logits out
         b200q4::ApiLock lk;

@@ -101,6 +101,8 @@ struct alignas(16) PgOp {
     const float *bias;       // PP == 1 only (may be NULL)
     int y_slice, dep_mv;     // dep_mv: the op `dep` is a PG_MATVEC (its completion implies that of every earlier op)
     int y_tag, publish;      // publish: a later op names this one as its `dep`: count the CTAs that are done with it
+    float *y_peer[8];        // world > 1: the same output vector on every rank (peer-mapped); this rank's rows go to all of them
+    int row0, pad7;          // world > 1: first output row of this rank's shard inside the full vector
     float *y_plain;          // PP == 1, optional: an untagged copy of Y as well (what a caller outside the list reads)
     int cobuild, pad5;       // consumer-built packs: index of a LATER op whose pack is built in the same pause (it needs nothing that
                              // is not there yet: the MLP's layer-norm of the residual stream next to the attention's), or -1
@@ -115,6 +117,8 @@ struct alignas(16) PgOp {
     int tq, tk, tv, pad4;
     float *mem_k, *mem_v;            // this layer's KV memory [n_ctx][H * d], vsim.cpp:318-330
     float *att_out;                  // [H * d] merged heads (vsim.cpp:621-627), {value, tag} pairs
+    float *att_peer[8];              // world > 1: att_out on every rank; H is then this rank's head count, head0 its first head
+    int head0, pad8;
     float *att_part;                 // [H][max_chunks][d] weighted V sums per position chunk (several chunks per head only)
     float *att_sc;                   // [H][n_ctx] scaled scores, [H][max_chunks] chunk maxima behind them
     double *att_sum;                 // [H][max_chunks] chunk denominators
@@ -125,7 +129,7 @@ struct alignas(16) PgOp {
 };
 
 constexpr int PG_OPC = 8;                                // mul_mat ops cached in shared memory (ring; > PG_MAX_STAGES + 1)
-constexpr int PG_OPC_WORDS = 88;                         // 352 bytes per entry: one 16-byte load for each of 22 producer lanes (the PG_MATVEC part of PgOp)
+constexpr int PG_OPC_WORDS = 108;                        // 432 bytes per entry: one 16-byte load for each of 27 producer lanes (the PG_MATVEC part of PgOp)
 static_assert(offsetof(PgOp, q) <= PG_OPC_WORDS * 4, "the PG_MATVEC part of PgOp must fit a cache entry");
 
 struct PgParams {
@@ -136,6 +140,8 @@ struct PgParams {
     int *dyn;                // [0] token id (through PgSrc::row), [1] n_past, [2] launch epoch (the last CTA to leave advances it)
     int *err;                // set (op index + 1) before the kernel traps on a wait that can never end
     int  stages, e_cap, nbp_cap, att_cap;    // shared-memory sizing: residual floats, apack quant blocks, attention floats
+    int  world, rank;        // row-sharded over `world` GPUs (1: single GPU)
+    int *ctr_peer[8];        // world > 1: every rank's counter array (hint counters are added to on all ranks)
     unsigned long long *dbg; // optional timeline [grid][n_ops][8] of %globaltimer stamps (B200Q4_DBG=1), else NULL
 };
 
@@ -224,14 +230,20 @@ __device__ __forceinline__ void pg_wait_hint(const int *c, int target)
     const long long t0 = clock64();
     for (;;) {
         int v;
-        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+        asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
         if (v >= target || clock64() - t0 > 2000000ll) return;
         __nanosleep(100);
     }
 }
 __device__ __forceinline__ void pg_add_hint(int *c)
 {
-    asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" :: "l"(c) : "memory");
+    asm volatile("red.relaxed.sys.global.add.s32 [%0], 1;" :: "l"(c) : "memory");
+}
+// the hint of op o on every rank (sharded programs: a consumer waits for the CTAs of all ranks)
+__device__ __forceinline__ void pg_add_hint_all(const PgParams &p, int o)
+{
+    if (p.world <= 1) { pg_add_hint(p.ctr + 1 + o); return; }
+    for (int r = 0; r < p.world; r++) pg_add_hint(p.ctr_peer[r] + 1 + o);
 }
 __device__ __forceinline__ void pg_mbar_wait(uint64_t *b, uint32_t parity)
 {
@@ -254,18 +266,18 @@ __device__ __forceinline__ void pg_pbar() { asm volatile("bar.sync 2, %0;" :: "n
 __device__ __forceinline__ float4 ld_relaxed_f4(const void *p)
 {
     float4 r;
-    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
     return r;
 }
 __device__ __forceinline__ float2 ld_relaxed_f2(const void *p)
 {
     float2 r;
-    asm volatile("ld.relaxed.gpu.global.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
     return r;
 }
 __device__ __forceinline__ void st_tagged(float *y2, size_t idx, float v, int tag)
 {
-    asm volatile("st.relaxed.gpu.global.v2.f32 [%0], {%1,%2};" :: "l"(y2 + 2 * idx), "f"(v), "f"(__int_as_float(tag)) : "memory");
+    asm volatile("st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" :: "l"(y2 + 2 * idx), "f"(v), "f"(__int_as_float(tag)) : "memory");
 }
 __device__ __noinline__ void pg_tag_timeout(int *err, int code)
 {
@@ -362,6 +374,136 @@ __device__ __forceinline__ float pg_rope(float x_self, float x_pair, bool first_
                       : (float)__dadd_rn(__dmul_rn(cs.x, (double)x_self), __dmul_rn(cs.y, (double)x_pair));
 }
 
+// Work decomposition: items = (head, chunk of CHK positions).  CHK is a multiple of PG_ATT_CHUNK chosen so that the
+// items about fill the grid once (16 heads x 512 positions: 8 chunks of 64; 64 heads: 2 chunks of 256).
+struct PgAttGeo { int nch, chk; };
+__device__ __forceinline__ PgAttGeo pg_att_geo(int P, int H, int grid)
+{
+    int nch = (P + PG_ATT_CHUNK - 1) / PG_ATT_CHUNK;
+    const int cap = grid / H > 1 ? grid / H : 1;             // chunks per head that still give every item its own CTA
+    if (nch > cap) nch = cap;
+    int chk = (P + nch - 1) / nch;
+    chk = (chk + PG_ATT_CHUNK - 1) / PG_ATT_CHUNK * PG_ATT_CHUNK;
+    PgAttGeo g;
+    g.chk = chk; g.nch = (P + chk - 1) / chk;
+    return g;
+}
+
+// scores of the chunk's positions [p_lo, p_lo + np) against s_q: LPP lanes share a position (each up to four float4 of
+// the K row, all requested before the first product), float products summed in double (ggml.c:4484-4516), then ggml_scale
+__device__ __forceinline__ void pg_att_scores(const float *mk, const float *s_q, const float *s_kn, float *s_sc, int p_lo, int np,
+                                              int n_past, int E, int hd0, int d, float scale, int ctid)
+{
+    const int lane = ctid & 31, warp = ctid >> 5;
+    if ((d & 3) == 0 && d <= 512) {
+        const int d4 = d >> 2;
+        int lpp = 1;
+        while (lpp * 4 < d4) lpp <<= 1;                      // lanes per position: each lane at most 4 float4
+        const int ppw = 32 / lpp, sub = lane & (lpp - 1), slot = lane / lpp;
+        for (int pl0 = warp * ppw; pl0 < np; pl0 += GEMV_WARPS * ppw) {
+            const int pl = pl0 + slot, pos = p_lo + pl;
+            const bool live = pl < np;
+            float4 kv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int f = sub + i * lpp;
+                kv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live && f < d4) {
+                    if (pos == n_past) kv[i] = reinterpret_cast<const float4 *>(s_kn)[f];
+                    else kv[i] = __ldcg(reinterpret_cast<const float4 *>(mk + (size_t)pos * E + hd0) + f);
+                }
+            }
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int f = sub + i * lpp;
+                if (f < d4) {
+                    const float4 q4 = reinterpret_cast<const float4 *>(s_q)[f];
+                    sum = __dadd_rn(sum, __dadd_rn(__dadd_rn((double)__fmul_rn(kv[i].x, q4.x), (double)__fmul_rn(kv[i].y, q4.y)),
+                                                   __dadd_rn((double)__fmul_rn(kv[i].z, q4.z), (double)__fmul_rn(kv[i].w, q4.w))));
+                }
+            }
+            for (int of = lpp >> 1; of > 0; of >>= 1) sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, of));
+            if (live && sub == 0) s_sc[pl] = __fmul_rn((float)sum, scale);
+        }
+    } else {
+        for (int pl = warp; pl < np; pl += GEMV_WARPS) {
+            const int pos = p_lo + pl;
+            double sum = 0.0;
+            if (pos == n_past) { for (int j = lane; j < d; j += 32) sum = __dadd_rn(sum, (double)__fmul_rn(s_kn[j], s_q[j])); }
+            else {
+                const float *kr = mk + (size_t)pos * E + hd0;
+#pragma unroll 8
+                for (int j = lane; j < d; j += 32) sum = __dadd_rn(sum, (double)__fmul_rn(__ldcg(kr + j), s_q[j]));
+            }
+#pragma unroll
+            for (int of = 16; of > 0; of >>= 1) sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, of));
+            if (lane == 0) s_sc[pl] = __fmul_rn((float)sum, scale);
+        }
+    }
+}
+
+// out[j] = sum over the chunk's positions of V[pos][j] * w[pos]  (ggml.c:4517-4553): position groups in parallel (float4
+// columns, eight V rows requested at a time), merged in group order.  s_o: scratch [groups][d].  Result in s_o[0 .. d).
+__device__ __forceinline__ void pg_att_pv(const float *mv, const float *s_vn, const float *s_w, float *s_o, int p_lo, int np,
+                                          int n_past, int E, int hd0, int d, int ctid)
+{
+    if ((d & 3) == 0 && d <= 512) {
+        const int d4 = d >> 2;
+        int cols = 8;
+        while (cols < d4) cols <<= 1;                        // threads per position group (a power of two >= d / 4)
+        const int ng = PG_CTHREADS / cols, g = ctid / cols, c = ctid & (cols - 1);
+        if (c < d4) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int pl0 = g; pl0 < np; pl0 += 8 * ng) {
+                float4 vv[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int pl = pl0 + u * ng, pos = p_lo + pl;
+                    vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (pl < np) vv[u] = pos == n_past ? reinterpret_cast<const float4 *>(s_vn)[c]
+                                                       : __ldcg(reinterpret_cast<const float4 *>(mv + (size_t)pos * E + hd0) + c);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int pl = pl0 + u * ng;
+                    if (pl < np) {
+                        const float w = s_w[pl];
+                        a.x = __fadd_rn(a.x, __fmul_rn(vv[u].x, w)); a.y = __fadd_rn(a.y, __fmul_rn(vv[u].y, w));
+                        a.z = __fadd_rn(a.z, __fmul_rn(vv[u].z, w)); a.w = __fadd_rn(a.w, __fmul_rn(vv[u].w, w));
+                    }
+                }
+            }
+            reinterpret_cast<float4 *>(s_o + (size_t)g * d)[c] = a;
+        }
+        pg_bar();
+        if (ctid < d) {
+            float a = s_o[ctid];
+            for (int gg = 1; gg < ng; gg++) a = __fadd_rn(a, s_o[(size_t)gg * d + ctid]);
+            s_o[ctid] = a;                                   // (thread ctid is the only reader of column ctid of the other groups)
+        }
+    } else {
+        const int dj = (d + 31) & ~31, ng = PG_CTHREADS / dj, g = ctid / dj, j = ctid - g * dj;
+        if (g < ng && j < d) {
+            float a = 0.f;
+#pragma unroll 8
+            for (int pl = g; pl < np; pl += ng) {
+                const int pos = p_lo + pl;
+                const float vv = pos == n_past ? s_vn[j] : __ldcg(mv + (size_t)pos * E + hd0 + j);
+                a = __fadd_rn(a, __fmul_rn(vv, s_w[pl]));
+            }
+            s_o[(size_t)g * dj + j] = a;
+        }
+        pg_bar();
+        if (ctid < d) {
+            float a = s_o[ctid];
+            for (int gg = 1; gg < ng; gg++) a = __fadd_rn(a, s_o[(size_t)gg * dj + ctid]);
+            s_o[ctid] = a;
+        }
+    }
+    pg_bar();
+}
+
 __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
 {
     const PgParams &p = *pp;                                 // (a copy in shared memory: nothing here may live on the stack)
@@ -372,25 +514,50 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
     const PgOp &op = p.ops[o];
     const int ctid = threadIdx.x - PG_C0, lane = ctid & 31, warp = ctid >> 5;
     const int H = op.H, d = op.d, E = H * d, half = op.n_rot / 2, P = n_past + 1;
-    const int nch = (P + PG_ATT_CHUNK - 1) / PG_ATT_CHUNK, items = H * nch;
-    const int dpad = (d + 3) & ~3;
-    float *s_q = s_att, *s_kn = s_q + dpad, *s_vn = s_kn + dpad, *s_sc = s_vn + dpad, *s_o = s_sc + PG_ATT_CHUNK + 8;
+    const PgAttGeo ag = pg_att_geo(P, H, (int)gridDim.x);
+    const int nch = ag.nch, CHK = ag.chk, items = H * nch;
+    const int dpad = (d + 3) & ~3, scap = (op.n_ctx + PG_ATT_CHUNK - 1) / PG_ATT_CHUNK * PG_ATT_CHUNK;
+    float *s_q = s_att, *s_kn = s_q + dpad, *s_vn = s_kn + dpad, *s_sc = s_vn + dpad, *s_o = s_sc + scap + 8;
     const float *gq = op.q, *gk = op.k, *gv = op.v;
     float *mk = op.mem_k, *mv = op.mem_v;
     const float scale = op.att_scale;
     const uint16_t *etab = op.exp_tab;
-    const int dj = (d + 31) & ~31, ng = PG_CTHREADS / dj;
     float *g_sc = op.att_sc, *g_mx = op.att_sc + (size_t)H * op.n_ctx;
     int *cnt1 = p.ctr + op.cnt_off, *cnt2 = cnt1 + H;
     const int tagbase = sm.flag[6];
     const int tag_q = tagbase | (op.tq + 1), tag_k = tagbase | (op.tk + 1), tag_v = tagbase | (op.tv + 1), tag_o = tagbase | (o + 1);
     // ggml_soft_max's exponential (ggml.c:5862-5870): fp16(x - max) -> table -> fp32
     auto texp = [&](float x) { return __half2float(__ushort_as_half(__ldg(etab + __half_as_ushort(__float2half_rn(x))))); };
+    // the merged-heads vector on this rank, or (sharded: H is this rank's head count) on every rank
+    auto att_store = [&](size_t idx, float v) {
+        if (p.world <= 1) st_tagged(op.att_out, idx, v, tag_o);
+        else for (int r = 0; r < p.world; r++) st_tagged(op.att_peer[r], idx, v, tag_o);
+    };
+    // warp 0: maximum of s_sc[0 .. np)
+    auto chunk_max = [&](int np) {
+        float m = -INFINITY;
+        for (int i = lane; i < np; i += 32) m = fmaxf(m, s_sc[i]);
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, of));
+        return m;
+    };
+    // warp 0: s_sc[i] = exp-table(s_sc[i] - M) in place; returns their sum (double, lane-strided partial sums added in a tree)
+    auto chunk_exp = [&](int np, float M) {
+        double l = 0.0;
+        for (int i = lane; i < np; i += 32) {
+            const float e = texp(__fsub_rn(s_sc[i], M));
+            s_sc[i] = e;
+            l = __dadd_rn(l, (double)e);
+        }
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) l = __dadd_rn(l, __shfl_xor_sync(0xffffffffu, l, of));
+        return l;
+    };
 
     // ---- pass A: rope, KV store, the chunk's scaled scores and their maximum --------------------------------------
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int h = item / nch, c = item - h * nch;
-        const int p_lo = c * PG_ATT_CHUNK, np = min(PG_ATT_CHUNK, P - p_lo);
+        const int p_lo = c * CHK, np = min(CHK, P - p_lo);
         const bool has_new = p_lo + np == P;
         pg_bar();                                            // the previous item's scratch is no longer read
         for (int j = ctid; j < d; j += PG_CTHREADS) {
@@ -411,26 +578,12 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
             }
         }
         pg_bar();
-        for (int pl = warp; pl < np; pl += GEMV_WARPS) {     // K . Q (ggml.c:4484-4516: float products summed in double), then ggml_scale
-            const int pos = p_lo + pl;
-            double sum = 0.0;
-            if (pos == n_past) { for (int j = lane; j < d; j += 32) sum = __dadd_rn(sum, (double)__fmul_rn(s_kn[j], s_q[j])); }
-            else {
-                const float *kr = mk + (size_t)pos * E + h * d;
-#pragma unroll 8
-                for (int j = lane; j < d; j += 32) sum = __dadd_rn(sum, (double)__fmul_rn(__ldcg(kr + j), s_q[j]));
-            }
-#pragma unroll
-            for (int of = 16; of > 0; of >>= 1) sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, of));
-            if (lane == 0) s_sc[pl] = __fmul_rn((float)sum, scale);
-        }
+        pg_att_scores(mk, s_q, s_kn, s_sc, p_lo, np, n_past, E, h * d, d, scale, ctid);
         pg_bar();
         if (nch > 1) {                                       // publish the chunk: the row maximum needs every chunk
-            if (ctid < np) g_sc[(size_t)h * op.n_ctx + p_lo + ctid] = s_sc[ctid];
+            for (int i = ctid; i < np; i += PG_CTHREADS) g_sc[(size_t)h * op.n_ctx + p_lo + i] = s_sc[i];
             if (warp == 0) {
-                float m = fmaxf(lane < np ? s_sc[lane] : -INFINITY, lane + 32 < np ? s_sc[lane + 32] : -INFINITY);
-#pragma unroll
-                for (int of = 16; of > 0; of >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, of));
+                const float m = chunk_max(np);
                 if (lane == 0) g_mx[(size_t)h * op.max_chunks + c] = m;
             }
             __threadfence();
@@ -440,83 +593,40 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
         }
         // ---- one chunk per head: soft_max and V^T . softmax right here (ggml.c:5825-5893, 4517-4553) ----------------
         if (warp == 0) {
-            const float v0 = lane < np ? s_sc[lane] : -INFINITY, v1 = lane + 32 < np ? s_sc[lane + 32] : -INFINITY;
-            float m = fmaxf(v0, v1);
-#pragma unroll
-            for (int of = 16; of > 0; of >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, of));
-            const float e0 = lane < np ? texp(__fsub_rn(v0, m)) : 0.f, e1 = lane + 32 < np ? texp(__fsub_rn(v1, m)) : 0.f;
-            double l = __dadd_rn((double)e0, (double)e1);
-#pragma unroll
-            for (int of = 16; of > 0; of >>= 1) l = __dadd_rn(l, __shfl_xor_sync(0xffffffffu, l, of));
+            const float M = chunk_max(np);
+            const double l = chunk_exp(np, M);
             const float inv = (float)(1.0 / l);
-            s_sc[lane] = __fmul_rn(e0, inv); s_sc[lane + 32] = __fmul_rn(e1, inv);
+            __syncwarp();
+            for (int i = lane; i < np; i += 32) s_sc[i] = __fmul_rn(s_sc[i], inv);
         }
         pg_bar();
-        {
-            const int g = ctid / dj, j = ctid - g * dj;
-            if (g < ng && j < d) {
-                float a = 0.f;
-#pragma unroll 8
-                for (int pl = g; pl < np; pl += ng) {
-                    const int pos = p_lo + pl;
-                    const float vv = pos == n_past ? s_vn[j] : __ldcg(mv + (size_t)pos * E + h * d + j);
-                    a = __fadd_rn(a, __fmul_rn(vv, s_sc[pl]));
-                }
-                s_o[g * dj + j] = a;
-            }
-        }
-        pg_bar();
-        if (ctid < d) {
-            float a = s_o[ctid];
-            for (int g = 1; g < ng; g++) a = __fadd_rn(a, s_o[g * dj + ctid]);
-            st_tagged(op.att_out, (size_t)h * d + ctid, a, tag_o);
-        }
+        pg_att_pv(mv, s_vn, s_sc, s_o, p_lo, np, n_past, E, h * d, d, ctid);
+        if (ctid < d) att_store((size_t)(op.head0 + h) * d + ctid, s_o[ctid]);
     }
     // ---- pass B (several chunks per head): exponentials against the ROW maximum, chunk denominators, weighted V sums; the
     //      head's last chunk to finish adds the pieces up.  Every CTA has published all of its chunks before it waits here.
     if (nch > 1) {
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int h = item / nch, c = item - h * nch;
-            const int p_lo = c * PG_ATT_CHUNK, np = min(PG_ATT_CHUNK, P - p_lo);
+            const int p_lo = c * CHK, np = min(CHK, P - p_lo);
             pg_bar();
             if (ctid == 0) pg_wait_ctr(cnt1 + h, nch, p.err, o + 1);
+            pg_bar();
+            for (int i = ctid; i < np; i += PG_CTHREADS) s_sc[i] = __ldcg(g_sc + (size_t)h * op.n_ctx + p_lo + i);
+            if (p_lo + np == P)                              // the new position's V row (its K / V went to memory in pass A)
+                for (int j = ctid; j < d; j += PG_CTHREADS) s_vn[j] = pg_ld_tag1(gv, (size_t)h * d + j, tag_v, p.err);
             pg_bar();
             if (warp == 0) {
                 float M = -INFINITY;
                 for (int cc = lane; cc < nch; cc += 32) M = fmaxf(M, __ldcg(g_mx + (size_t)h * op.max_chunks + cc));
 #pragma unroll
                 for (int of = 16; of > 0; of >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, of));
-                const float *sc = g_sc + (size_t)h * op.n_ctx + p_lo;
-                const float e0 = lane < np ? texp(__fsub_rn(__ldcg(sc + lane), M)) : 0.f;
-                const float e1 = lane + 32 < np ? texp(__fsub_rn(__ldcg(sc + lane + 32), M)) : 0.f;
-                double l = __dadd_rn((double)e0, (double)e1);
-#pragma unroll
-                for (int of = 16; of > 0; of >>= 1) l = __dadd_rn(l, __shfl_xor_sync(0xffffffffu, l, of));
-                s_sc[lane] = e0; s_sc[lane + 32] = e1;
+                const double l = chunk_exp(np, M);
                 if (lane == 0) op.att_sum[(size_t)h * op.max_chunks + c] = l;
             }
-            if (p_lo + np == P)                              // the new position's V row (its K / V went to memory in pass A)
-                for (int j = ctid; j < d; j += PG_CTHREADS) s_vn[j] = pg_ld_tag1(gv, (size_t)h * d + j, tag_v, p.err);
             pg_bar();
-            {
-                const int g = ctid / dj, j = ctid - g * dj;
-                if (g < ng && j < d) {
-                    float a = 0.f;
-#pragma unroll 8
-                    for (int pl = g; pl < np; pl += ng) {
-                        const int pos = p_lo + pl;
-                        const float vv = pos == n_past ? s_vn[j] : __ldcg(mv + (size_t)pos * E + h * d + j);
-                        a = __fadd_rn(a, __fmul_rn(vv, s_sc[pl]));
-                    }
-                    s_o[g * dj + j] = a;
-                }
-            }
-            pg_bar();
-            if (ctid < d) {
-                float a = s_o[ctid];
-                for (int g = 1; g < ng; g++) a = __fadd_rn(a, s_o[g * dj + ctid]);
-                op.att_part[((size_t)h * op.max_chunks + c) * d + ctid] = a;
-            }
+            pg_att_pv(mv, s_vn, s_sc, s_o, p_lo, np, n_past, E, h * d, d, ctid);
+            if (ctid < d) op.att_part[((size_t)h * op.max_chunks + c) * d + ctid] = s_o[ctid];
             __threadfence();
             pg_bar();
             if (ctid == 0) {
@@ -533,7 +643,7 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
                     const float inv = (float)(1.0 / S);
                     float O = 0.f;
                     for (int cc = 0; cc < nch; cc++) O = __fadd_rn(O, __ldcg(op.att_part + ((size_t)h * op.max_chunks + cc) * d + ctid));
-                    st_tagged(op.att_out, (size_t)h * d + ctid, __fmul_rn(O, inv), tag_o);
+                    att_store((size_t)(op.head0 + h) * d + ctid, __fmul_rn(O, inv));
                 }
             }
         }
@@ -544,7 +654,7 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
         if (ctid == 0) atomicAdd(p.ctr + 1 + o, 1);
     } else {
         pg_bar();
-        if (ctid == 0) pg_add_hint(p.ctr + 1 + o);           // (no fence: only tells pollers that looking at the tags is worth it)
+        if (ctid == 0) pg_add_hint_all(p, o);                // (no fence: only tells pollers that looking at the tags is worth it)
     }
 }
 
@@ -625,7 +735,7 @@ __device__ __noinline__ void pg_build_pack(const PgParams *pp, const PgOp *opp, 
     }
     if (ctid == 0) {                                         // tagged inputs: one thread waits until they are probably all there
         for (int j = 0; j < nsrc; j++)
-            if ((op.src[j].kind & 255) == PG_SRC_TAG) pg_wait_hint(p.ctr + 1 + (op.src[j].kind >> 8), (int)gridDim.x);
+            if ((op.src[j].kind & 255) == PG_SRC_TAG) pg_wait_hint(p.ctr + 1 + (op.src[j].kind >> 8), (int)gridDim.x * p.world);
         PG_STAMP(o, 2);
     }
     gbar();
@@ -940,7 +1050,9 @@ __device__ __noinline__ void pg_reducer(const PgParams *pp)
     int curT = -1, curTask = -1, curOp = -1;
     float *y = nullptr, *y_plain = nullptr;
     const float *bias = nullptr;
-    int N = 0, C = 1, PP = 1, y_slice = 0, ytag = 0, publish = 0;
+    int N = 0, C = 1, PP = 1, y_slice = 0, ytag = 0, publish = 0, row0 = 0;
+    const int world = p.world;
+    const PgOp *cop = nullptr;
     const int rl = lane & 15;
     const int tagbase = sm.flag[6];
     auto emit = [&]() {
@@ -948,8 +1060,10 @@ __device__ __noinline__ void pg_reducer(const PgParams *pp)
         const int n = curT * TILE_ROWS + lane;
         if (lane < TILE_ROWS && n < N) {
             const float v = (PP == 1 && bias) ? __fadd_rn(acc * post, bcur) : acc * post;
-            const size_t idx = PP == 1 ? (size_t)n : (size_t)(curTask - curT * PP) * y_slice + n;
-            if (ytag) st_tagged(y, idx, v, ytag);            // value and tag in one 8-byte store: the data is its own flag
+            const size_t idx = (PP == 1 ? (size_t)n : (size_t)(curTask - curT * PP) * y_slice + n) + row0;
+            if (ytag && world > 1 && cop->y_peer[0]) {       // this rank's rows of the vector, on every rank
+                for (int r = 0; r < world; r++) st_tagged(cop->y_peer[r], idx, v, ytag);
+            } else if (ytag) st_tagged(y, idx, v, ytag);     // value and tag in one 8-byte store: the data is its own flag
             else y[idx] = v;
             if (y_plain) y_plain[n] = v;
         }
@@ -967,7 +1081,7 @@ __device__ __noinline__ void pg_reducer(const PgParams *pp)
         if (dsc.x == -2) break;
         if (o != curOp) {
             const PgOp &op = pg_cached_op(sm, o);
-            y = op.y; y_plain = op.y_plain; bias = op.bias; N = op.N; C = op.C; PP = op.PP; y_slice = op.y_slice;
+            y = op.y; y_plain = op.y_plain; bias = op.bias; N = op.N; C = op.C; PP = op.PP; y_slice = op.y_slice; row0 = op.row0; cop = &op;
             ytag = op.y_tag ? (tagbase | (o + 1)) : 0; publish = op.publish;
             curOp = o;
         }
@@ -1017,7 +1131,7 @@ __device__ __noinline__ void pg_reducer(const PgParams *pp)
                 if (lane == 0) atomicAdd(p.ctr + 1 + o, 1);
             } else if (ytag) {
                 __syncwarp();
-                if (lane == 0) pg_add_hint(p.ctr + 1 + o);   // (no fence: only tells pollers that looking at the tags is worth it)
+                if (lane == 0) pg_add_hint_all(p, o);        // (no fence: only tells pollers that looking at the tags is worth it)
             }
             if (lane == 0) PG_STAMP(o, 5);
         }

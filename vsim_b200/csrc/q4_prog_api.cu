@@ -35,6 +35,15 @@ PgGeo pg_geometry(const b200q4_weight *w)
     return g;
 }
 
+PgGeo pg_geometry_dims(int N, int K)
+{
+    b200q4_weight w{};
+    w.N = N; w.K = K; w.nb = K / QK;
+    w.C = (w.nb + CHUNK_BLKS - 1) / CHUNK_BLKS;
+    w.n_tiles = (N + TILE_ROWS - 1) / TILE_ROWS;
+    return pg_geometry(&w);
+}
+
 int ProgBuild::add_matvec(const b200q4_weight *w, int dep, int in_mode, int res, const PgSrc *src, int nsrc,
                           const float *ln_w, const float *ln_b, const uint16_t *gelu_tab, float *y, const float *bias, int y_slice,
                           bool y_tag, bool same_pack, float *y_plain)
@@ -131,7 +140,9 @@ int ProgBuild::add_attn(int dep, const float *q, const float *k, const float *v,
     op.H = H; op.d = d; op.n_rot = n_rot; op.max_chunks = (n_ctx + PG_ATT_CHUNK - 1) / PG_ATT_CHUNK;
     op.cnt_off = n_cnt; n_cnt += 2 * H;
     op.att_scale = scale;
-    const int need = 3 * ((d + 3) & ~3) + PG_ATT_CHUNK + 8 + PG_CTHREADS;
+    // q, new k, new v rows; the chunk's scores (a chunk is at most the whole context); the position groups' partial outputs
+    const int groups = d % 4 == 0 ? PG_CTHREADS / (d / 4 <= 8 ? 8 : d / 4 <= 16 ? 16 : d / 4 <= 32 ? 32 : d / 4 <= 64 ? 64 : 128) : PG_CTHREADS / ((d + 31) & ~31);
+    const int need = 3 * ((d + 3) & ~3) + (n_ctx + PG_ATT_CHUNK - 1) / PG_ATT_CHUNK * PG_ATT_CHUNK + 8 + groups * ((d + 31) & ~31) + 32;
     if (need > att_cap) att_cap = need;
     ops.push_back(op);
     return (int)ops.size() - 1;
@@ -158,12 +169,18 @@ static int set_attr(int smem_optin, int *avail)
     return B200Q4_OK;
 }
 
-int prog_finalize(const ProgBuild &b, Prog &out)
+int prog_counter_ints(const ProgBuild &b) { return 1 + (int)b.ops.size() + b.n_tk + b.n_cnt; }
+
+int prog_finalize(const ProgBuild &b, Prog &out) { return prog_finalize_sharded(b, out, 0, 1, nullptr); }
+
+int prog_finalize_sharded(const ProgBuild &b, Prog &out, int rank, int world, int *const *ctr_peers)
 {
     const DevInfo di = dev_info();
     if (di.device < 0) return api_fail(B200Q4_ENODEV, "b200q4_init() has not succeeded; no CPU fallback exists");
     if (b.ops.empty() || b.qt < 0) return api_fail(B200Q4_EINVAL, "program: no mul_mat op");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || (world > 1 && !ctr_peers)) return api_fail(B200Q4_EINVAL, "program: bad rank / world");
     Prog pg;
+    pg.world = world; pg.rank = rank;
     pg.qt = b.qt; pg.grid = di.sms; pg.n_ops = (int)b.ops.size();
     pg.e_cap = (b.e_cap + 3) & ~3; pg.nbp_cap = (b.nbp_cap + 7) & ~7; pg.att_cap = (b.att_cap + 3) & ~3;
     int avail = 0;
@@ -194,7 +211,12 @@ int prog_finalize(const ProgBuild &b, Prog &out)
     pg.first_mv = nxt;
     pg.n_ctr = cnt0 + b.n_cnt;
     PCK(cudaMalloc(&pg.d_ops, ops.size() * sizeof(PgOp)));
-    if (cudaMalloc(&pg.d_ctr, (size_t)pg.n_ctr * sizeof(int)) != cudaSuccess || cudaMalloc(&pg.d_dyn, 16) != cudaSuccess ||
+    if (world > 1) {
+        pg.own_ctr = false;
+        for (int r = 0; r < world; r++) pg.ctr_peer[r] = ctr_peers[r];
+        pg.d_ctr = ctr_peers[rank];
+    }
+    if ((world == 1 && cudaMalloc(&pg.d_ctr, (size_t)pg.n_ctr * sizeof(int)) != cudaSuccess) || cudaMalloc(&pg.d_dyn, 16) != cudaSuccess ||
         cudaMalloc(&pg.d_err, 16) != cudaSuccess) {
         cudaGetLastError();
         prog_free(pg);
@@ -223,6 +245,8 @@ int prog_launch(const Prog &pg, cudaStream_t st)
     PgParams p;
     p.ops = pg.d_ops; p.n_ops = pg.n_ops; p.first_mv = pg.first_mv; p.dbg = pg.d_dbg; p.ctr = pg.d_ctr; p.n_ctr = pg.n_ctr; p.dyn = pg.d_dyn; p.err = pg.d_err;
     p.stages = pg.stages; p.e_cap = pg.e_cap; p.nbp_cap = pg.nbp_cap; p.att_cap = pg.att_cap;
+    p.world = pg.world; p.rank = pg.rank;
+    for (int r = 0; r < 8; r++) p.ctr_peer[r] = pg.ctr_peer[r];
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pg.grid); cfg.blockDim = dim3(PG_THREADS); cfg.dynamicSmemBytes = pg.smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -237,7 +261,8 @@ int prog_launch(const Prog &pg, cudaStream_t st)
 
 void prog_free(Prog &pg)
 {
-    cudaFree(pg.d_ops); cudaFree(pg.d_ctr); cudaFree(pg.d_dyn); cudaFree(pg.d_err); cudaFree(pg.d_dbg);
+    cudaFree(pg.d_ops); if (pg.own_ctr) cudaFree(pg.d_ctr);
+    cudaFree(pg.d_dyn); cudaFree(pg.d_err); cudaFree(pg.d_dbg);
     pg = Prog{};
 }
 

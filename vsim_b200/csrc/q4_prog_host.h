@@ -11,6 +11,7 @@ namespace b200q4 {
 // K-slicing geometry of one M = 1 mul_mat inside a program (the rule q4_api.cu's slice_geometry applies for M <= 2)
 struct PgGeo { int PP, TS, ntasks; };
 PgGeo pg_geometry(const b200q4_weight *w);
+PgGeo pg_geometry_dims(int N, int K);               // the same from the tensor's dimensions alone
 
 struct ProgBuild {
     int qt = -1;                         // quant type shared by every mul_mat of the program
@@ -44,6 +45,9 @@ struct Prog {
     int  *d_dyn = nullptr;               // [0] token id, [1] n_past, [2] launch epoch
     int  *d_err = nullptr;
     unsigned long long *d_dbg = nullptr; // timeline (development builds)
+    int   world = 1, rank = 0;           // row-sharded programs: this rank of `world`
+    int  *ctr_peer[8] = {nullptr};       // ... and every rank's counter array (peer-mapped; entry `rank` is d_ctr, not owned)
+    bool  own_ctr = true;
     int   qt = 0, stages = 0, grid = 0, e_cap = 0, nbp_cap = 0, att_cap = 0;
     size_t smem = 0;
 };
@@ -51,6 +55,9 @@ struct Prog {
 inline PgSrc pg_src_f32(const float *p, int np = 1, int stride = 0, float scale = 1.0f) { return PgSrc{p, nullptr, np, stride, scale, PG_SRC_F32}; }
 
 int  prog_finalize(const ProgBuild &b, Prog &out);      // uploads the list, sizes shared memory, allocates the counters
+// sharded: the counters live in caller-provided peer-mapped memory (ctr_peers[r], prog_counter_ints(b) ints each, zeroed)
+int  prog_finalize_sharded(const ProgBuild &b, Prog &out, int rank, int world, int *const *ctr_peers);
+int  prog_counter_ints(const ProgBuild &b);
 int  prog_launch(const Prog &pg, cudaStream_t st);      // one cooperative launch of q4_prog_kernel
 void prog_free(Prog &pg);
 

@@ -118,3 +118,52 @@ class PeerOutput:
         self._check(self.L.b200q4_wait_flags(self.flags.data_ptr(), self.world, self.seq_ctr.data_ptr(), st))
         if hop:
             cur.wait_stream(self._st)
+
+
+class ShardedNeox:
+    """b200neox_load_sharded behind torch symmetric memory: one process per GPU, every rank calls eval() with the same
+    token; decode steps are ONE persistent launch per rank, the ranks' thread blocks exchange their output slices
+    directly ({value, tag} stores into every rank's pool over NVLink)."""
+
+    def __init__(self, lib, path: str, n_ctx: int = 512, group=None):
+        import struct
+        import torch.distributed._symmetric_memory as symm
+        self.L = lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        with open(path, "rb") as f:
+            magic, n_vocab, n_embd, n_head, n_layer = struct.unpack("<5i", f.read(20))
+        if magic != 0x67676d6c:
+            raise ValueError("not a ggml model file")
+        self.n_vocab = n_vocab
+        need = int(lib.b200neox_sharded_pool_bytes(n_vocab, n_embd, n_layer))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.pool = symm.empty((need + 3) // 4, dtype=torch.int32, device=dev)
+        self.pool.zero_()
+        self.hdl = symm.rendezvous(self.pool, self.group)
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+        ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        self.m = lib.b200neox_load_sharded(str(path).encode(), n_ctx, self.rank, self.world, ptrs, need)
+        if not self.m:
+            raise RuntimeError((lib.b200neox_last_error() or b"").decode(errors="replace"))
+        torch.cuda.synchronize()
+        dist.barrier(self.group)                          # nobody launches before every rank's program and counters exist
+        import numpy as np
+        self._out = np.empty(n_vocab, np.float32)
+        self._tok = np.zeros(1, np.int32)
+
+    def eval(self, token: int, n_past: int):
+        """One decode step on every rank; returns the logits (host numpy view, valid until the next call)."""
+        self._tok[0] = token
+        rc = self.L.b200neox_eval(self.m, self._tok.ctypes.data, 1, n_past, 1, self._out.ctypes.data)
+        if rc:
+            raise RuntimeError((self.L.b200neox_last_error() or b"").decode(errors="replace"))
+        return self._out
+
+    def free(self):
+        if getattr(self, "m", None):
+            torch.cuda.synchronize()
+            dist.barrier(self.group)                      # no rank frees its pool while a peer's kernel may still store into it
+            self.L.b200neox_free(self.m)
+            self.m = None
