@@ -358,6 +358,60 @@ def model_decode_full(vs, L, which, peak, n_ctx=512, tokens=32):
         L.b200neox_free(m)
 
 
+def model_decode_full_sharded(vs, L, torch, dist, rank, world, which, peak, n_ctx=512, tokens=32):
+    """The same whole-graph decode at N > 1: every 2-D tensor row-sharded over the ranks (imax.c:1185-1188), attention by
+    heads, one persistent launch per token and rank; the ranks' thread blocks store their output slices into every rank's
+    exchange pool over NVLink ({value, tag} pairs, no collective call).  Strong scaling of one token stream."""
+    import shutil
+    from tools.synth_model import SHAPES, write_model, q4_weight_bytes
+    from vsim_b200.shard import ShardedNeox
+    shape = SHAPES[which]
+    path = Path("/dev/shm" if Path("/dev/shm").is_dir() else "/tmp") / f"b200bench_{which}_shared.bin"
+    err = torch.zeros(1, device="cuda")
+    if rank == 0:
+        try:
+            need = q4_weight_bytes(shape[0], shape[1], shape[3]) + shape[0] * shape[1] * 20 // 32 + (64 << 20)
+            if shutil.disk_usage(path.parent).free < need:
+                raise OSError("not enough scratch space")
+            write_model(path, *shape)
+        except Exception:                                   # noqa: BLE001
+            err += 1
+    dist.all_reduce(err)
+    if float(err.item()) > 0:
+        return {"error": "could not write the synthetic model file"}
+    t0 = time.perf_counter()
+    sh = ShardedNeox(L, str(path), n_ctx=n_ctx)
+    t_load = time.perf_counter() - t0
+    dist.barrier()
+    if rank == 0:
+        path.unlink()
+    res = {}
+    tok = 1
+    for label, n0 in (("context_32", 5), ("context_512", n_ctx - tokens)):
+        lg = sh.eval(tok, n0)                              # warm-up (the same position again below)
+        torch.cuda.synchronize(); dist.barrier()
+        n_past = n0
+        t0 = time.perf_counter()
+        for _ in range(tokens):
+            lg = sh.eval(tok, n_past)
+            n_past += 1
+            tok = int(lg.argmax())
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        ms = float(dt.item()) / tokens * 1e3
+        res[label] = {"ms_per_token": ms, "tok_per_s": 1e3 / ms, "positions": [n0, n0 + tokens]}
+    sh.free()
+    wb = q4_weight_bytes(shape[0], shape[1], shape[3])
+    ms = res["context_512"]["ms_per_token"]
+    return {"model": f"{which}: n_vocab {shape[0]}, n_embd {shape[1]}, n_head {shape[2]}, n_layer {shape[3]}, Q4_0, random-init",
+            "scope": "whole graph, token id in / logits out on every rank: one persistent launch per token and rank",
+            "parallelism": f"rows of every 2-D tensor and attention heads sharded over {world} GPUs; output slices stored into every "
+                           f"rank's exchange pool by the producing thread blocks (peer memory over NVLink, tagged values, no collective)",
+            "scaling": "strong", "load_and_upload_s": t_load, "tok_per_s": 1e3 / ms, "ms_per_token": ms, **res,
+            "weight_bytes_per_token_per_gpu": wb // world, "weight_GBps_per_gpu": wb / world / ms / 1e6,
+            "frac_hbm_peak_per_gpu": wb / world / ms / 1e6 / peak, "tokens_timed": tokens}
+
+
 def prefill_bloom(vs, L, torch, tpeak, stream):
     """BASELINE.json configs[3]: BLOOM-7b1 Q4_1 prefill of 2048 tokens -- the four Q4_1 mul_mat shapes of that model
     (n_embd 4096, 30 layers, vocab 250880) at M = 2048 on the tcgen05 tile kernel."""
@@ -689,6 +743,19 @@ def main() -> int:
     if not args.no_model:
         model = model_decode(vs, L, torch, dist, rank, world, stream, peak, args.nccl, "gptj6b")
         model20 = model_decode(vs, L, torch, dist, rank, world, stream, peak, args.nccl, "neox20b", tokens=12)
+        if world > 1 and not args.nccl:
+            for w in w0:
+                w.free()
+            w0 = []
+            for which in ("gptj6b", "neox20b"):
+                try:
+                    r = model_decode_full_sharded(vs, L, torch, dist, rank, world, which, peak, tokens=32 if which == "gptj6b" else 16)
+                except Exception as e:                     # noqa: BLE001
+                    r = {"error": repr(e)}
+                if which == "gptj6b":
+                    full = r
+                else:
+                    full20 = r
         if world == 1:                                     # the whole graph through b200neox_eval (one persistent launch per token)
             for w in w0:
                 w.free()

@@ -135,8 +135,8 @@ static_assert(offsetof(PgOp, q) <= PG_OPC_WORDS * 4, "the PG_MATVEC part of PgOp
 struct PgParams {
     const PgOp *ops;
     int  n_ops, first_mv;
-    int *ctr;                // [0] CTAs finished; [1 + o] CTAs done with op o; tickets; attention head counters.  All zero
-    int  n_ctr;              //   between launches: the last CTA to leave clears them.
+    int *ctr;                // [0] CTAs finished; [1 + o] CTAs done with op o, summed over all launches (never reset); tickets;
+    int  n_ctr;              //   attention head counters (zero between launches: the last CTA to leave clears them).
     int *dyn;                // [0] token id (through PgSrc::row), [1] n_past, [2] launch epoch (the last CTA to leave advances it)
     int *err;                // set (op index + 1) before the kernel traps on a wait that can never end
     int  stages, e_cap, nbp_cap, att_cap;    // shared-memory sizing: residual floats, apack quant blocks, attention floats
@@ -181,7 +181,7 @@ __device__ __forceinline__ PgSmem pg_smem(const PgParams &p, int qt)
     m.pack_empty = m.pack_full + 2;                                    // [2] every consumer warp is done with pack buffer b
     m.desc = reinterpret_cast<int4 *>(m.pack_empty + 2);               // {units (0: none, -2: STOP), first chunk index, first tile, task}
     m.dop = reinterpret_cast<int *>(m.desc + PG_MAX_STAGES);           // op index of the stage | PG_END when it is the CTA's last of that op
-    m.flag = m.dop + PG_MAX_STAGES + 2;                                // [0] scratch flag, [1] waited_mv (consumers), [5] latest consumer-built pack, [6] tag base of this launch,
+    m.flag = m.dop + PG_MAX_STAGES + 2;                                // [0] scratch flag, [1] waited_mv (consumers), [2] launch epoch, [5] latest consumer-built pack, [6] tag base of this launch,
                                                                        // [7] waited_mv (prep warps)
     m.geo = m.flag + 8;                                                // [2][4] per pack buffer: C, first chunk of the K-slice, plane stride
     m.wst = m.geo + 8;                                                 // per consumer warp: slot, parity, current op, current pack
@@ -729,13 +729,13 @@ __device__ __noinline__ void pg_build_pack(const PgParams *pp, const PgOp *opp, 
     }
     const int dep = op.dep;
     if (dep >= 0 && dep > waited_mv) {
-        if (ctid == 0) pg_wait_ctr(p.ctr + 1 + dep, (int)gridDim.x, p.err, o + 1);
+        if (ctid == 0) pg_wait_ctr(p.ctr + 1 + dep, (int)gridDim.x * sm.flag[2], p.err, o + 1);
         gbar();                                            // (everybody has read flag[1] by now)
         if (ctid == 0 && op.dep_mv) sm.flag[WFLAG] = dep;        // a complete mul_mat op implies every earlier op is complete
     }
     if (ctid == 0) {                                         // tagged inputs: one thread waits until they are probably all there
         for (int j = 0; j < nsrc; j++)
-            if ((op.src[j].kind & 255) == PG_SRC_TAG) pg_wait_hint(p.ctr + 1 + (op.src[j].kind >> 8), (int)gridDim.x * p.world);
+            if ((op.src[j].kind & 255) == PG_SRC_TAG) pg_wait_hint(p.ctr + 1 + (op.src[j].kind >> 8), (int)gridDim.x * p.world * sm.flag[2]);
         PG_STAMP(o, 2);
     }
     gbar();
@@ -1146,8 +1146,8 @@ __device__ __noinline__ void pg_reducer(const PgParams *pp)
     last = __shfl_sync(0xffffffffu, last, 0);
     if (last) {
         __threadfence();
-        for (int i = lane; i < p.n_ctr; i += 32) p.ctr[i] = 0;
-        if (lane == 0) p.dyn[2] = p.dyn[2] + 1;              // next launch, next epoch: this launch's tags become stale
+        for (int i = 1 + p.n_ops + lane; i < p.n_ctr; i += 32) p.ctr[i] = 0;     // tickets, attention head counters
+        if (lane == 0) { p.ctr[0] = 0; p.dyn[2] = p.dyn[2] + 1; }                 // next launch, next epoch: this launch's tags become stale
     }
 }
 
@@ -1248,7 +1248,7 @@ __device__ __noinline__ void pg_side_ops(const PgParams *pp, int from, int to)
         pg_bar();
         const int wmv = sm.flag[1];
         if (dep >= 0 && dep > wmv) {
-            if (threadIdx.x == PG_C0) pg_wait_ctr(p.ctr + 1 + dep, (int)gridDim.x, p.err, a + 1);
+            if (threadIdx.x == PG_C0) pg_wait_ctr(p.ctr + 1 + dep, (int)gridDim.x * sm.flag[2], p.err, a + 1);
             pg_bar();                                        // (everybody has read flag[1] by now)
             if (threadIdx.x == PG_C0 && p.ops[dep].kind == PG_MATVEC) sm.flag[1] = dep;
         }
@@ -1340,6 +1340,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) q4_prog_kernel(const PgParams p
         s_p = p;
         sm.flag[1] = -1; sm.flag[5] = -1; sm.flag[7] = -1;
         sm.flag[6] = (int)(((unsigned)p.dyn[2] & 0x7ffffu) << 12);           // tag = epoch << 12 | (op index + 1)
+        sm.flag[2] = p.dyn[2];                                               // the launch epoch itself: arrival / hint counters are
+                                                                             // never reset, op o is complete at epoch * (CTAs that add)
     }
     __syncthreads();
     if (PG_PWARPS > 0 && warp < PG_PWARPS) pg_prep<QT>(&s_p);
