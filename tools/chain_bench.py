@@ -80,8 +80,9 @@ def l2(L, rng):
     w.free()
 
 
-def model(L, rng, name):
-    NL, E, F, V = {"gptj": (28, 4096, 16384, 50400), "neox20b": (44, 6144, 24576, 50432)}[name]
+def model_chain(rng, name, NL=None):
+    NL0, E, F, V = {"gptj": (28, 4096, 16384, 50400), "neox20b": (44, 6144, 24576, 50432)}[name]
+    NL = NL or NL0
     host = [rand_q4(rng, 0, n, k) for n, k in [(E, E)] * 4 + [(F, E), (E, F)]]
     shapes = [(E, E)] * 4 + [(F, E), (E, F)]
     layers = [[vsim_b200.Q4Weight(0, host[j], *shapes[j]) for j in range(6)] for _ in range(NL)]
@@ -101,8 +102,14 @@ def model(L, rng, name):
         last = base + 5
     ws.append(head); xs.append(att.data_ptr()); ys.append(logits.data_ptr()); deps.append(last)
     ch = vsim_b200.Chain(ws, xs, ys, deps)
+    ch.keep = (layers, head, x, q, k_, v, att, ffo, ff, logits)
+    return ch, sum(h.size for h in host) * NL + V * (E // 32) * 20, len(ws)
+
+
+def model(L, rng, name):
+    ch, wbytes, nws = model_chain(rng, name)
+    ws = [None] * nws
     ms = time_chain(L, ch, 10)
-    wbytes = sum(h.size for h in host) * NL + V * (E // 32) * 20
     print(f"{name}-shaped token, {len(ws)} mul_mats in one launch: {ms:.3f} ms/token  {1e3 / ms:.0f} tok/s  "
           f"{wbytes / ms / 1e6:.0f} GB/s = {wbytes / ms / 1e6 / PEAK * 100:.1f}% of measured peak   {ch.info()}", flush=True)
     ch.free()

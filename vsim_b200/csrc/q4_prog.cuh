@@ -928,6 +928,14 @@ __device__ __noinline__ void pg_prep(const PgParams *pp)
 }
 
 constexpr int PG_END = 1 << 30;                          // flag in a stage's op word: the CTA's last stage of that op
+constexpr int PG_FAST = 1 << 29;                         // ... 32 units of one tile from an even chunk on: every warp has one whole, aligned octet
+constexpr int PG_OPMASK = PG_FAST - 1;
+// Consumers -> reducer hand-off of ring slot s: named barrier PG_BAR_DONE + s.  The 512 consumer threads arrive
+// (bar.arrive, non-blocking), the reducer warp syncs on it: 16 arrivals on one mbarrier cost every warp ~350 cycles
+// of contention per stage (tools/octetbench.cu), the barrier unit takes them in a few.
+constexpr int PG_BAR_DONE = 3;
+__device__ __forceinline__ void pg_done_arrive(int s) { asm volatile("bar.arrive %0, %1;" :: "r"(PG_BAR_DONE + s), "n"(PG_CTHREADS + 32) : "memory"); }
+__device__ __forceinline__ void pg_done_sync(int s) { asm volatile("bar.sync %0, %1;" :: "r"(PG_BAR_DONE + s), "n"(PG_CTHREADS + 32) : "memory"); }
 
 __device__ __forceinline__ const PgOp &pg_cached_op(const PgSmem &sm, int o)
 {
@@ -1003,7 +1011,8 @@ __device__ __noinline__ void pg_producer(const PgParams *pp)
             auto issue = [&](int u0, int n, int T, int c0, int task, bool last_task) {
                 for (int r = 0; r < n; r += PG_UNITS) {
                     const int cnt = min(PG_UNITS, n - r);
-                    put(cnt, c0, T, task, (last_task && r + PG_UNITS >= n) ? (o | PG_END) : o, wt + (size_t)(u0 + r) * CH);
+                    const int fast = (cnt == PG_UNITS && !(c0 & 1) && c0 + cnt <= C) ? PG_FAST : 0;
+                    put(cnt, c0, T, task, ((last_task && r + PG_UNITS >= n) ? (o | PG_END) : o) | fast, wt + (size_t)(u0 + r) * CH);
                     c0 += cnt;
                     while (c0 >= C) { c0 -= C; ++T; }
                 }
@@ -1074,10 +1083,10 @@ __device__ __noinline__ void pg_reducer(const PgParams *pp)
     const long long tr0 = PG_CLK();
     for (;;) {
         const long long tw = PG_CLK();
-        pg_mbar_wait(&sm.bar_done[s], ph);                   // every consumer warp has passed this slot (markers included)
+        pg_done_sync(s);                                     // every consumer warp has passed this slot (markers included)
         if (lane == 0) PG_ACC(pp, 3, PG_CLK() - tw);
         const int4 dsc = sm.desc[s];
-        const int otag = sm.dop[s], o = otag & (PG_END - 1);
+        const int otag = sm.dop[s], o = otag & PG_OPMASK;
         if (dsc.x == -2) break;
         if (o != curOp) {
             const PgOp &op = pg_cached_op(sm, o);
@@ -1102,7 +1111,15 @@ __device__ __noinline__ void pg_reducer(const PgParams *pp)
                     }
                 }
                 const int run = min(dsc.x - j, left);
-                if (run == PG_UNITS) {
+                if (otag & PG_FAST) {                        // aligned octets: the odd slots would all be zero (run == PG_UNITS)
+                    float v[PG_UNITS / 2];
+#pragma unroll
+                    for (int k = 0; k < PG_UNITS / 2; k++) v[k] = red[2 * k * PG_RW];
+                    float q[PG_UNITS / 4];
+#pragma unroll
+                    for (int h = 0; h < PG_UNITS / 4; h++) q[h] = v[2 * h] + v[2 * h + 1];
+                    acc += ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+                } else if (run == PG_UNITS) {
                     float v[PG_UNITS];
 #pragma unroll
                     for (int k = 0; k < PG_UNITS; k++) v[k] = red[k * PG_RW];
@@ -1155,12 +1172,22 @@ __device__ __noinline__ void pg_reducer(const PgParams *pp)
 // one stage: this warp's two units (an octet of quant blocks) against the activation pack
 template <int QT>
 __device__ __forceinline__ void pg_consume_stage(const PgSmem &sm, const uint8_t *s_aq, const float *s_ap, int gC, int gcbase, int gplane,
-                                                 int s, int cnt, int c0, int T0)
+                                                 int s, int cnt, int c0, int T0, bool fast)
 {
     constexpr int CH = chunk_bytes(QT);
     constexpr int STAGE_BYTES = PG_UNITS * CH;
     const int lane = threadIdx.x & 31, warp = (threadIdx.x - PG_C0) >> 5;
     const int uA = 2 * warp, uB = uA + 1;
+    if (fast) {                                              // units 2 warp, 2 warp + 1 = one aligned octet of tile T0
+        const uint8_t *chA = sm.stage + (size_t)s * STAGE_BYTES + (size_t)uA * CH;
+        float v0, v2;
+        compute_octet<QT, false>(chA, chA + CH, (c0 + uA - gcbase) >> 1, s_aq, s_ap, gplane, lane, v0, v2);
+        v0 += __shfl_xor_sync(0xffffffffu, v0, 1); v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, 1); v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
+        const int g = lane >> 2, t = lane & 3;
+        if (t < 2) sm.red[((size_t)s * PG_UNITS + uA) * PG_RW + g + 8 * t] = t ? v2 : v0;
+        return;
+    }
     auto put_rows = [&](float *slot, float v0, float v2) {
         v0 += __shfl_xor_sync(0xffffffffu, v0, 1); v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
         v2 += __shfl_xor_sync(0xffffffffu, v2, 1); v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
@@ -1221,10 +1248,9 @@ __device__ __noinline__ int pg_consume_op(const PgParams *pp)
         const int4 dsc = sm.desc[s];
         const int otag = sm.dop[s];
         const long long tc = PG_CLK();
-        if (dsc.x > 0) pg_consume_stage<QT>(sm, s_aq, s_ap, gC, gcbase, gplane, s, dsc.x, dsc.y, dsc.z);
-        __syncwarp();
+        if (dsc.x > 0) pg_consume_stage<QT>(sm, s_aq, s_ap, gC, gcbase, gplane, s, dsc.x, dsc.y, dsc.z, (otag & PG_FAST) != 0);
         if (threadIdx.x == PG_C0 && dsc.x > 0) { PG_ACC(pp, 5, PG_CLK() - tc); PG_ACC(pp, 6, 1); }
-        if (lane == 0) mbar_arrive(&sm.bar_done[s]);
+        pg_done_arrive(s);
         const bool stop = dsc.x == -2;
         if (!stop && ++s == stages) { s = 0; ph ^= 1; }
         if (stop || (otag & PG_END)) {
@@ -1275,14 +1301,14 @@ __device__ __noinline__ void pg_consumer(const PgParams *pp)
             const long long tw = PG_CLK();
             pg_mbar_wait(&sm.bar_full[s], (uint32_t)wst[1]);
             if (threadIdx.x == PG_C0) PG_ACC(pp, 7, PG_CLK() - tw);
-            const int o = sm.dop[s] & (PG_END - 1), cur = wst[2];
+            const int o = sm.dop[s] & PG_OPMASK, cur = wst[2];
             if (o > cur + 1) pg_side_ops<QT>(pp, cur + 1, o);     // (STOP carries o = n_ops: trailing side ops run too)
         }
         {
             const PgSmem sm = pg_smem(*pp, QT);
             int *wst = sm.wst + ((threadIdx.x - PG_C0) >> 5) * 4;
             const int s = wst[0];
-            const int o = sm.dop[s] & (PG_END - 1), cnt = sm.desc[s].x;
+            const int o = sm.dop[s] & PG_OPMASK, cnt = sm.desc[s].x;
             const int lane = threadIdx.x & 31;
             __syncwarp();
             if (lane == 0) wst[2] = o;
