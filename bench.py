@@ -39,6 +39,7 @@ sys.path.insert(0, str(ROOT))
 
 K_DIM, N_ROWS = 4096, 16384
 METRIC = "Q4 mul_mat GB/s & %HBM peak"
+OPS_PER_LAUNCH = 100                    # N=1 headline: mul_mats (steps) per persistent launch of the decode program kernel
 L2_BYTES = 126e6
 WORKLOAD = f"Q4_0 mul_mat microbench K={K_DIM} N={N_ROWS} M=1 (BASELINE.json configs[1])"      # the same string in both arms
 
@@ -555,6 +556,8 @@ def main() -> int:
     ap.add_argument("--no-points", action="store_true", help="skip the (type, M) sweep")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-model", action="store_true", help="skip the GPT-J-6B- and GPT-NeoX-20B-shaped decode legs")
+    ap.add_argument("--per-call", action="store_true", help="N=1: time the headline as one kernel launch per step (CUDA graph of a rotation) "
+                                                            "instead of persistent launches of the decode program kernel")
     ap.add_argument("--nccl", action="store_true", help="N>1: exchange output slices with an NCCL all-gather instead of the fused epilogue")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -654,30 +657,97 @@ def main() -> int:
         timed.graphed = graph is not None
         return ms
 
+    def timed_program(steps: int, warm: int):
+        """N=1 headline: the K steps as persistent launches of the decode program kernel (q4_prog_kernel, b200q4_chain_*):
+        step i = one mul_mat of weight tensor i % nw with ITS OWN fp32 input row (x_host[i % 512]: quantized inside the launch,
+        one activation pack per step) into its own output row; the steps are independent, up to OPS_PER_LAUNCH per launch."""
+        per = min(steps, OPS_PER_LAUNCH)
+        nl = (steps + per - 1) // per
+        ws = [w0[i % nw] for i in range(per)]
+        xs = [d_x[i % 512].data_ptr() for i in range(per)]
+        ys = [d_yloc[i % 512].data_ptr() for i in range(per)]
+        ch = vs.Chain(ws, xs, ys, [-1] * per)
+        tail = None
+        if steps % per:
+            r = steps % per
+            tail = vs.Chain(ws[:r], xs[:r], ys[:r], [-1] * r)
+        try:
+            for _ in range(max(1, (warm + per - 1) // per)):
+                ch.run(stream.cuda_stream)
+            if tail is not None:
+                tail.run(stream.cuda_stream)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps // per):
+                ch.run(stream.cuda_stream)
+            if tail is not None:
+                tail.run(stream.cuda_stream)
+            e1.record(stream)
+            barrier()
+            ms = e0.elapsed_time(e1)
+            # parity of the product path, inside the run: step 1's output row against the per-op kernel on the same inputs
+            y_prog = d_yloc[1 % 512].clone()
+            rc = L.b200q4_mul_mat_dev(w0[1 % nw].handle, d_x[1 % 512].data_ptr(), 1, K_DIM * 4, d_y.data_ptr(), N_ROWS * 4, stream.cuda_stream)
+            barrier()
+            diff = float((y_prog - d_y.view(-1)[:N_ROWS]).abs().max()) if rc == 0 else float("nan")
+        finally:
+            ch.free()
+            if tail is not None:
+                tail.free()
+        return ms, nl, per, diff
+
     sampler.start()
     # ---- headline: Q4_0, M=1, K steps -----------------------------------------------------------
     M_HEAD = 1
     vs.launch_count_reset()
-    ms_total = timed(M_HEAD, w0, args.steps, args.warmup)
-    launches_total = vs.launch_count()
-    # graph replays re-issue captured launches without passing through the library's counter: M=1 is one launch per step
-    launches_timed = (int(round(args.steps * getattr(timed, "launches_per_step", 1))) if getattr(timed, "graphed", False)
-                      else launches_total * args.steps // (args.steps + args.warmup))
+    headline = None
+    if world == 1 and not args.per_call:
+        ms_total, launches_timed, per_launch, hdiff = timed_program(args.steps, args.warmup)
+        headline = {"ops_per_launch": per_launch, "launches": launches_timed, "max_abs_diff_vs_per_call_kernel": hdiff}
+        ms_call = timed(M_HEAD, w0, args.steps, args.warmup) / args.steps      # the same steps as one launch per call, for the record
+        headline["per_call_launches_us_per_step"] = ms_call * 1e3
+    else:
+        ms_total = timed(M_HEAD, w0, args.steps, args.warmup)
+        launches_total = vs.launch_count()
+        # graph replays re-issue captured launches without passing through the library's counter: M=1 is one launch per step
+        launches_timed = (int(round(args.steps * getattr(timed, "launches_per_step", 1))) if getattr(timed, "graphed", False)
+                          else launches_total * args.steps // (args.steps + args.warmup))
     ms_step = ms_total / args.steps
     value = alg_bytes(0, M_HEAD) * world / (ms_step * 1e-3) / 1e9
 
-    # ---- roofline: the dominant kernel alone (pack once, then the GEMV kernel back to back) --------
+    # ---- roofline: the dominant kernel ------------------------------------------------------------------
+    # N=1: q4_prog_kernel is the only kernel of the timed region -- CUDA events on its stream around the launches (the
+    # measurement above); per launch it processes ops_per_launch mul_mats.  N>1: the per-call decode kernel, back to back.
     kern_ms = L.b200q4_time_mul_mat_dev(handles0, nw, d_x.data_ptr(), M_HEAD, d_yloc.data_ptr(), max(args.steps, 200))
     if kern_ms < 0:
         raise RuntimeError(vs.lib._err(L))
-    achieved = alg_bytes(0, M_HEAD) / (kern_ms * 1e-3) / 1e9
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
-            traffic = json.load(open(tp)).get("q4_0_m1_dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("q4_0_m1_prog_dram_bytes_per_launch" if headline else "q4_0_m1_dram_bytes_per_launch")
         except Exception:                  # noqa: BLE001
             traffic = None
+    if headline:
+        launch_ms = ms_total / headline["launches"]
+        units = args.steps / headline["launches"]                              # mul_mats per launch (average)
+        roof = {"achieved": alg_bytes(0, M_HEAD) * units / (launch_ms * 1e-3) / 1e9,
+                "kernel": "q4_prog_kernel<Q4_0> (persistent: producer warp + 16 consumer warps + reducer warp per SM; "
+                          f"{headline['ops_per_launch']} independent M=1 mul_mats per launch, each with its own activation quantization), "
+                          "CUDA events on the launching stream around the timed launches",
+                "algorithmic_bytes_per_launch": int(alg_bytes(0, M_HEAD) * units), "us_per_launch": launch_ms * 1e3,
+                "units_per_launch": units, "algorithmic_bytes_per_unit": alg_bytes(0, M_HEAD),
+                "per_call_kernel": {"kernel": "q4_gemv_pipe_kernel<Q4_0, chain4, fused quantization> (one launch per call), back to back",
+                                    "us_per_launch": kern_ms * 1e3, "achieved": alg_bytes(0, M_HEAD) / (kern_ms * 1e-3) / 1e9,
+                                    "frac": alg_bytes(0, M_HEAD) / (kern_ms * 1e-3) / 1e9 / peak}}
+    else:
+        roof = {"achieved": alg_bytes(0, M_HEAD) / (kern_ms * 1e-3) / 1e9,
+                "kernel": "q4_gemv_pipe_kernel<Q4_0, chain4, fused quantization> (M=1: one launch per call), CUDA events on "
+                          "the library stream around back-to-back launches rotating weights",
+                "algorithmic_bytes_per_launch": alg_bytes(0, M_HEAD), "us_per_launch": kern_ms * 1e3}
+    achieved = roof.pop("achieved")
 
     # ---- e2e: host buffers through the C ABI --------------------------------------------------------
     hx = L.b200q4_host_alloc(M_HEAD * K_DIM * 4)
@@ -790,14 +860,14 @@ def main() -> int:
                 "weights": "random-init fp32 U(-0.05,0.05), seed 1234, quantized to the reference Q4 row format",
                 "activations": "fp32 N(0,1), seed 5678, quantized on the device every step",
                 "l2": f"defeated: every loop rotates over {nw} distinct {alg_bytes(0, 0) / 1e6:.0f} MB weight tensors "
-                      f"({nw * alg_bytes(0, 0) / 1e6:.0f} MB > 3x the 126 MB L2); the caller hints the next tensor "
-                      f"(b200q4_hint_next_weight), whose first 12 MB are prefetched into L2 during the tail of the current launch",
+                      f"({nw * alg_bytes(0, 0) / 1e6:.0f} MB > 3x the 126 MB L2)" + ("" if headline else "; the caller hints the next tensor "
+                      f"(b200q4_hint_next_weight), whose first 12 MB are prefetched into L2 during the tail of the current launch"),
                 "parallelism": "single GPU" if world == 1 else
                                f"{world}-way row shard of a {N_ROWS * world}-row tensor; fp32 output slices " +
                                ("all-gathered with NCCL" if po is None else
                                 "stored into every rank's Y by the kernel epilogue (peer memory over NVLink) + arrival counters; "
                                 "the timed loop replays a CUDA graph of one rotation over the weight tensors"),
-                "kernel": vs.kernel_for(0, M_HEAD, N_ROWS, K_DIM),
+                "kernel": "q4_prog_kernel<Q4_0>" if headline else vs.kernel_for(0, M_HEAD, N_ROWS, K_DIM),
                 "frac_hbm_peak": value / (peak * world),
             },
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": M_HEAD * K_DIM * 4,
@@ -805,12 +875,12 @@ def main() -> int:
                     "api": "b200q4_mul_mat (C ABI, pinned host X and Y, synchronous): fetch kernel pulls X over PCIe, the decode "
                            "epilogue stores Y into the host buffer, completion = polled host word"},
             "gpu_launches": int(launches_timed),
-            "timed_loop": "a CUDA graph of one rotation over the weight tensors, replayed" if getattr(timed, "graphed", False) else "eager launches",
+            "timed_loop": (f"persistent launches of the decode program kernel, {headline['ops_per_launch']} independent steps per launch "
+                           "(every step quantizes its own input row)" if headline else
+                           "a CUDA graph of one rotation over the weight tensors, replayed" if getattr(timed, "graphed", False) else "eager launches"),
+            "headline": headline,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "q4_gemv_pipe_kernel<Q4_0, chain4, fused quantization> (M=1: one launch per call), CUDA events on "
-                                   "the library stream around back-to-back launches rotating weights",
-                         "algorithmic_bytes_per_launch": alg_bytes(0, M_HEAD), "us_per_launch": kern_ms * 1e3},
+                         "traffic": traffic, "peak_source": peak_src, **roof},
             "clocks": sampler.summary(),
             "points": points,
             "roofline_prefill": prefill_roofline(points, tpeak, tpeak_src, world),

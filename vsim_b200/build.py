@@ -43,6 +43,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(out), *map(str, SOURCES)]
     if os.environ.get("B200Q4_TIMELINE"):          # development: per-CTA %globaltimer stamps (tools/timeline.py)
         cmd.insert(1, "-DB200Q4_TIMELINE")
+    if os.environ.get("B200Q4_DEFS"):              # development: extra -D switches
+        cmd[1:1] = ["-D" + d for d in os.environ["B200Q4_DEFS"].split(",")]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)

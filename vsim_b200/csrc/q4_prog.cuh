@@ -102,15 +102,22 @@ struct alignas(16) PgOp {
     int y_slice, dep_mv;     // dep_mv: the op `dep` is a PG_MATVEC (its completion implies that of every earlier op)
     int y_tag, publish;      // publish: a later op names this one as its `dep`: count the CTAs that are done with it
     float *y_peer[8];        // world > 1: the same output vector on every rank (peer-mapped); this rank's rows go to all of them
-    int row0, pad7;          // world > 1: first output row of this rank's shard inside the full vector
+    int row0, prebuilt;      // world > 1: first output row of this rank's shard inside the full vector.  prebuilt: this op's pack was
+                             // prepared while the previous pack's ops were streaming (it is some earlier op's `early`); 2: and every
+                             // consumer warp reads only the quant blocks it wrote itself (a stage is always the same 128 blocks
+                             // of the pack: warp w has blocks 8w .. 8w+7), likewise for the pack that had the buffer before: no barrier
     float *y_plain;          // PP == 1, optional: an untagged copy of Y as well (what a caller outside the list reads)
-    int cobuild, pad5;       // consumer-built packs: index of a LATER op whose pack is built in the same pause (it needs nothing that
+    int cobuild, early;      // early (> 0): index of the LATER op whose pack every consumer warp prepares its share of before it starts
+                             // on this op's stages (that op reads one plain vector nobody in the list writes: no pause at all);
+                             // cobuild: consumer-built packs: index of a LATER op whose pack is built in the same pause (it needs nothing that
                              // is not there yet: the MLP's layer-norm of the residual stream next to the attention's), or -1
     int builder, wait_pack;  // who builds the pack: 0 the prep warps (ahead of time), 1 the consumers themselves (a residual update or gelu:
                              // big gathers, and the consumers would wait for the inputs anyway); wait_pack: for a prep-built layer-norm
                              // pack, the number of the consumer-built pack that updated the residual stream it reads (-1: none)
     int pack_of, pack_seq;   // index of the first op of a run of ops with the SAME activation pack (Q, K, V): built once;
                              // pack_seq: running number of that pack (its shared-memory buffer is pack_seq & 1)
+    const float *early_x;    // early > 0: that op's input vector, tensor geometry and pack number (all pg_consume_op needs to
+    int e_C, e_PP, e_TS, e_nb, e_seq, pad9;      // prepare its pack between two stages of this op)
     // (everything above is what a PG_MATVEC needs: the first PG_OPC_WORDS words are what the shared-memory op cache holds)
     // ---- PG_ATTN: the new token's attention for one layer (decode, one query row) -----------------------------
     const float *q, *k, *v;          // [H * d] {value, tag} pairs written by ops tq, tk, tv (biases already added)
@@ -1238,6 +1245,26 @@ __device__ __noinline__ int pg_consume_op(const PgParams *pp)
     const int gC = sm.geo[b * 4], gcbase = sm.geo[b * 4 + 1], gplane = sm.geo[b * 4 + 2];
     const uint8_t *s_aq = sm.aq + (size_t)b * sm.pack_stride;
     const float *s_ap = reinterpret_cast<const float *>(s_aq + (size_t)pp->nbp_cap * 32);
+    // A later op whose input is a plain vector nobody in the list writes (PgOp::early): this thread's eight elements of it
+    // are requested now and quantized into the OTHER pack buffer after the first stage -- no pause, no barrier here.
+    float4 elo = make_float4(0.f, 0.f, 0.f, 0.f), ehi = elo;
+    int e_items = -1, e_blk0 = 0, e_nbp = 0;
+    {
+        const PgOp &cop = pg_cached_op(sm, wst[2]);
+        if (wst[2] < pp->n_ops && cop.early > 0) {          // (the STOP marker has no op record)
+            const int ctid = (int)threadIdx.x - PG_C0;
+            const bool sliced = cop.e_PP > 1;
+            const int cbase = sliced ? ((int)blockIdx.x % cop.e_PP) * cop.e_TS : 0;
+            e_blk0 = cbase * CHUNK_BLKS;
+            e_nbp = sliced ? cop.e_TS * CHUNK_BLKS : ((cop.e_C * CHUNK_BLKS + 7) & ~7);
+            e_items = min(cop.e_nb - e_blk0, e_nbp) * 4;                          // <= PG_CTHREADS (the list builder checks)
+            if (ctid < e_items) {
+                const float *xp = cop.early_x + (size_t)(e_blk0 + (ctid >> 2)) * QK + (lane & 3) * 8;
+                elo = __ldcg(reinterpret_cast<const float4 *>(xp));
+                ehi = __ldcg(reinterpret_cast<const float4 *>(xp + 4));
+            }
+        }
+    }
     for (;;) {
         const long long tw = PG_CLK();
         pg_mbar_wait(&sm.bar_full[s], ph);
@@ -1251,6 +1278,26 @@ __device__ __noinline__ int pg_consume_op(const PgParams *pp)
         if (dsc.x > 0) pg_consume_stage<QT>(sm, s_aq, s_ap, gC, gcbase, gplane, s, dsc.x, dsc.y, dsc.z, (otag & PG_FAST) != 0);
         if (threadIdx.x == PG_C0 && dsc.x > 0) { PG_ACC(pp, 5, PG_CLK() - tc); PG_ACC(pp, 6, 1); }
         pg_done_arrive(s);
+        if (e_items >= 0) {                                  // (once per op, after its first ring entry)
+            constexpr int NP = (QT == 0) ? 2 : 3;
+            const int ctid = (int)threadIdx.x - PG_C0;
+            uint8_t *d_aq = sm.aq + (size_t)(b ^ 1) * sm.pack_stride;
+            float *d_ap = reinterpret_cast<float *>(d_aq + (size_t)pp->nbp_cap * 32);
+            for (int i = e_items + ctid; i < e_nbp * 4; i += PG_CTHREADS) reinterpret_cast<uint2 *>(d_aq)[i] = make_uint2(0u, 0u);
+            for (int pl = 0; pl < NP; pl++)
+                for (int i = (e_items >> 2) + ctid; i < e_nbp; i += PG_CTHREADS) d_ap[pl * e_nbp + i] = 0.0f;
+            if ((ctid & ~31) < e_items) {
+                const bool valid = ctid < e_items;
+                const int blk = valid ? ctid >> 2 : 0;
+                quantize8_emit<QT>(elo, ehi, valid, lane, d_aq + (size_t)blk * 32, d_ap + blk, e_nbp);
+            }
+            if (lane == 0) {                                 // (every warp: the next op may start without a barrier; same values)
+                const PgOp &cop = pg_cached_op(sm, wst[2]);
+                sm.geo[(b ^ 1) * 4] = cop.e_C; sm.geo[(b ^ 1) * 4 + 1] = e_blk0 / CHUNK_BLKS; sm.geo[(b ^ 1) * 4 + 2] = e_nbp; sm.flag[5] = cop.e_seq;
+            }
+            __syncwarp();
+            e_items = -1;
+        }
         const bool stop = dsc.x == -2;
         if (!stop && ++s == stages) { s = 0; ph ^= 1; }
         if (stop || (otag & PG_END)) {
@@ -1318,19 +1365,19 @@ __device__ __noinline__ void pg_consumer(const PgParams *pp)
                 if (q != cq) {
                     { const PgParams &p = *pp; if (threadIdx.x == PG_C0) PG_STAMP(o, 1); (void)p; }
                     __syncwarp();
-                    if (lane == 0) {
-                        if (cq >= 0) mbar_arrive(&sm.pack_empty[cq & 1]);
-                        wst[3] = q;
-                    }
+                    if (lane == 0) wst[3] = q;
                     const long long tw = PG_CLK();
                     // consumer-built packs: all 512 threads; flag[5] = the latest pack built so far (a pack may have been built
                     // early, in the pause of an earlier op).  Prep-built packs (PG_PWARPS > 0) are waited for.
                     if (pg_cached_op(sm, o).builder == 1) {
-                        if (q > sm.flag[5]) {
-                            const int co = pg_cached_op(sm, o).cobuild;
-                            PgOp *my = reinterpret_cast<PgOp *>(sm.opc + (size_t)PG_OPC * PG_OPC_WORDS);
-                            if (co >= 0 && (int)threadIdx.x - PG_C0 < PG_OPC_WORDS / 4)        // its op record arrives while the first pack is built
-                                reinterpret_cast<uint4 *>(my)[threadIdx.x - PG_C0] = __ldg(reinterpret_cast<const uint4 *>(pp->ops + co) + (threadIdx.x - PG_C0));
+                        const int co = pg_cached_op(sm, o).cobuild;
+                        PgOp *my = reinterpret_cast<PgOp *>(sm.opc + (size_t)PG_OPC * PG_OPC_WORDS);
+                        if (co >= 0 && (int)threadIdx.x - PG_C0 < PG_OPC_WORDS / 4)           // its op record arrives while the first pack is built
+                            reinterpret_cast<uint4 *>(my)[threadIdx.x - PG_C0] = __ldg(reinterpret_cast<const uint4 *>(pp->ops + co) + (threadIdx.x - PG_C0));
+                        if (pg_cached_op(sm, o).prebuilt) {
+                            if (pg_cached_op(sm, o).prebuilt == 1) pg_bar();                        // every warp has stored its share of the pack (pg_consume_op of the previous
+                                                             // pack's first op), and nobody reads the other buffer any more
+                        } else if (q > sm.flag[5]) {
                             pg_build_pack<QT, 1>(pp, &pg_cached_op(sm, o), o, q & 1);
                             if (co >= 0) pg_build_pack<QT, 1>(pp, my, co, (q + 1) & 1);
                         }

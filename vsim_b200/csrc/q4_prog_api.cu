@@ -112,8 +112,35 @@ int ProgBuild::add_matvec(const b200q4_weight *w, int dep, int in_mode, int res,
     } else {
         // a layer-norm pack that only re-reads the residual stream can be built in the pause of the pack that updated it,
         // if it is the very next pack (the two buffers alternate)
-        if (PG_PWARPS == 0 && in_mode == PG_IN_LN && res == PG_RES_KEEP && last_res_pack == n_packs - 1 && last_res_op >= 0)
+        bool cobuilt = false;
+        if (PG_PWARPS == 0 && in_mode == PG_IN_LN && res == PG_RES_KEEP && last_res_pack == n_packs - 1 && last_res_op >= 0 &&
+            ops[(size_t)last_res_op].early == 0) {
             ops[(size_t)last_res_op].cobuild = (int)ops.size();
+            cobuilt = true;
+        }
+        // A pack made of one plain vector that nothing in the list writes needs no pause at all: every consumer warp
+        // prepares its share between two stages of the previous pack's first op (q4_prog.cuh, pg_consume_op).  That op
+        // must start with a barrier of its own (built there, or itself prepared ahead), and one item per thread must do.
+        const int nbp_new = g.PP > 1 ? g.TS * CHUNK_BLKS : ((w->C * CHUNK_BLKS + 7) & ~7);
+        const bool selfc = (g.PP == 1 && w->C == PG_UNITS) || (g.PP > 1 && g.TS == PG_UNITS && w->C % g.TS == 0);
+        if (PG_PWARPS == 0 && in_mode == PG_IN_PLAIN && nsrc == 1 && (src[0].kind & 255) == PG_SRC_F32 && src[0].np == 1 &&
+            src[0].scale == 1.0f && dep < 0 && last_pack_op >= 0 && !last_pack_cobuilt && ops[(size_t)last_pack_op].cobuild < 0 &&
+            ops[(size_t)last_pack_op].early == 0 && nbp_new * 4 <= PG_CTHREADS && !getenv("B200Q4_PROG_NO_EARLY")) {
+            PgOp &host = ops[(size_t)last_pack_op];
+            host.early = (int)ops.size();
+            host.early_x = static_cast<const float *>(src[0].ptr);
+            host.e_C = w->C; host.e_PP = g.PP; host.e_TS = g.TS; host.e_nb = w->nb; host.e_seq = n_packs;
+            op.prebuilt = 1;
+            // no barrier at this op's start if nobody reads what another warp wrote: this pack is self-contained, and the
+            // buffer it went into was free for sure -- the host op started with a barrier, or without one but then the
+            // pack before it (the buffer's previous content) was self-contained as well
+            const bool host_bar = host.prebuilt != 2;
+            const bool prev_selfc = n_packs >= 2 && pack_selfc[(size_t)n_packs - 2];
+            if (selfc && (host_bar || prev_selfc) && !getenv("B200Q4_PROG_EARLY_BARRIER")) op.prebuilt = 2;
+        }
+        last_pack_cobuilt = cobuilt;
+        pack_selfc.push_back(selfc ? 1 : 0);
+        last_pack_op = (int)ops.size();
         n_packs++;
     }
     if (in_mode == PG_IN_LN && (res == PG_RES_ADD || res == PG_RES_SET)) last_res_op = (int)ops.size();

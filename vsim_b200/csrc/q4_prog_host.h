@@ -20,6 +20,9 @@ struct ProgBuild {
     int rot_acc = 0;                     // running rotation of the static task assignment
     int last_mv = -1;                    // previous mul_mat op (pack reuse)
     int n_packs = 0;                     // activation packs so far
+    int last_pack_op = -1;               // first op of the latest activation pack
+    bool last_pack_cobuilt = false;      // ... which is built in the pause of an earlier op (no barrier at its own start)
+    std::vector<char> pack_selfc;        // per pack: every stage of its ops covers the same 128 quant blocks (warp w reads blocks 8w .. 8w+7)
     int last_res_pack = -1, last_res_op = -1;   // pack / op during whose construction the residual stream was last updated
     int e_cap = 4, nbp_cap = 8, att_cap = 4;
     // Appends Y = W . quantize(in(sources)); returns the op index or a negative error.  For a K-sliced weight
