@@ -84,7 +84,7 @@ def test_vsim_neox_end_to_end_tokens_and_logits(tmp_path, qt, tag):
     from tests.helpers.neox_file import write_neox
     model = tmp_path / f"tiny-{tag}.bin"
     write_neox(model, qt)
-    fast = {"B200Q4_EXACT": "0"}                           # the hook defaults to exact mode: this test is about the fast kernels
+    fast = {"B200Q4_EXACT": "0"}                           # the fast kernels (the hook's default; pinned here all the same)
     lr = _logits(_run(REF_BIN, model, logits=True))
     lg = _logits(_run(B200_BIN, model, logits=True, env=fast))
     assert lr.shape == lg.shape and lr.shape[1] == 256
@@ -106,7 +106,7 @@ def test_vsim_neox_exact_mode_reproduces_the_reference_bit_for_bit(tmp_path, qt,
     from tests.helpers.neox_file import write_neox
     model = tmp_path / f"exact-{tag}.bin"
     write_neox(model, qt, n_vocab=512, n_embd=512, n_head=8, n_layer=6, n_rot=32, seed=3)
-    ex = {}                                                # exact mode is the hook's default
+    ex = {"B200Q4_EXACT": "1"}                             # exact mode is opt-in (the hook defaults to the fast kernels)
     lr = _logits(_run(REF_BIN, model, logits=True))
     lg = _logits(_run(B200_BIN, model, logits=True, env=ex))
     assert lr.shape == lg.shape

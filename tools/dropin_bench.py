@@ -31,6 +31,7 @@ SHAPES = {  # name: (n_vocab, n_embd, n_head, n_layer, n_rot)
     "gptj6b": (50400, 4096, 16, 28, 64),
     "neox20b": (50432, 6144, 64, 44, 24),
     "mid": (8192, 2048, 16, 8, 32),
+    "gpt2_117m": (50257, 768, 12, 12, 16),       # BASELINE.json configs[0] as a NeoX-shaped stand-in (the reference ships no GPT-2 driver)
     "gptj6b_4l": (50400, 4096, 16, 4, 64),     # GPT-J widths, 4 layers: how far rounding-level differences have grown by then
     "gptj6b_12l": (50400, 4096, 16, 12, 64),
 }
@@ -124,6 +125,7 @@ def main() -> int:
     ap.add_argument("--cpu-n", default="4,20", help="n_predict pair for the CPU build")
     ap.add_argument("--gpu-n", default="16,272", help="n_predict pair for the GPU-backed build (n_ctx is 512)")
     ap.add_argument("--exact", action="store_true", help="GPU-backed build in exact mode (B200Q4_EXACT=1: bit-identical mul_mats)")
+    ap.add_argument("--cpu-only", action="store_true", help="only the unmodified CPU build (no GPU needed): BASELINE.json configs[0]")
     ap.add_argument("--keep", action="store_true", help="keep the model file")
     ap.add_argument("--timeout", type=int, default=900)
     args = ap.parse_args()
@@ -141,6 +143,17 @@ def main() -> int:
     t_write = time.perf_counter() - t0
     try:
         res = {}
+        if args.cpu_only:
+            n0, n1 = (int(v) for v in args.cpu_n.split(","))
+            pa, wa, _ = run(cpu_bin, model, n0, args.threads, args.timeout)
+            pb, wb, toks = run(cpu_bin, model, n1, args.threads, args.timeout)
+            ms = (pb - pa) / (n1 - n0) * 1e3
+            print(json.dumps({"what": "unmodified reference main program (oracle/_ref/vsim-ubuntu: vsim.cpp + ggml.c + imax.c, Makefile-ubuntu flags), "
+                                      "greedy decode, batch 1, CPU only",
+                              "model": f"{args.model}: n_vocab {nv}, n_embd {ne}, n_head {nh}, n_layer {nl}, n_rot {nr}, Q4_0, random-init, {size / 1e6:.0f} MB file",
+                              "threads": args.threads, "host_cores": os.cpu_count(), "n_predict": [n0, n1], "t_predict_s": [pa, pb],
+                              "ms_per_token": ms, "tok_per_s": 1e3 / ms, "tokens_decoded": len(toks), "first_tokens": toks[:12]}))
+            return 0
         lg = prompt_logits(gpu_bin, model, args.gpu_threads, args.timeout)
         lc = prompt_logits(cpu_bin, model, args.threads, args.timeout)
         for tag, b, pair, th in (("b200_hook", gpu_bin, args.gpu_n, args.gpu_threads), ("cpu_reference", cpu_bin, args.cpu_n, args.threads)):

@@ -15,6 +15,7 @@ SHAPES = {  # name: (n_vocab, n_embd, n_head, n_layer, n_rot)
     "neox20b": (50432, 6144, 64, 44, 24),
     "pythia12b": (50288, 5120, 40, 36, 32),
     "mid": (8192, 2048, 16, 8, 32),
+    "gpt2_117m": (50257, 768, 12, 12, 16),       # BASELINE.json configs[0] as a NeoX-shaped stand-in (the reference ships no GPT-2 driver)
     "tiny": (512, 256, 4, 2, 32),
 }
 

@@ -612,6 +612,23 @@ int b200neox_decode_is_program(const b200neox *m)
     return m->have_prog ? 1 : 0;
 }
 
+#ifdef B200Q4_TIMELINE
+/* development aid (timeline builds, B200Q4_DBG=1): the decode program's [grid][n_ops][8] stamps of the last step, and the
+ * kind of every op (0 mul_mat, 1 attention, 2 sum); returns the grid size, n_ops through *n_ops */
+int b200neox_debug_timeline(const b200neox *m, unsigned long long *out, size_t cap_words, int *n_ops, int *kinds, int cap_kinds)
+{
+    if (!m || !m->have_prog || !m->prog.d_dbg) return B200Q4_EINVAL;
+    const size_t n = (size_t)m->prog.grid * m->prog.n_ops * 8 + (size_t)m->prog.grid * 16;
+    if (cap_words < n || cap_kinds < m->prog.n_ops) return B200Q4_EINVAL;
+    cudaDeviceSynchronize();
+    std::vector<b200q4::PgOp> ops((size_t)m->prog.n_ops);
+    if (cudaMemcpy(ops.data(), m->prog.d_ops, ops.size() * sizeof(b200q4::PgOp), cudaMemcpyDeviceToHost) != cudaSuccess) return B200Q4_ECUDA;
+    for (int i = 0; i < m->prog.n_ops; i++) kinds[i] = ops[(size_t)i].kind | (ops[(size_t)i].N << 4);
+    *n_ops = m->prog.n_ops;
+    return cudaMemcpy(out, m->prog.d_dbg, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? m->prog.grid : B200Q4_ECUDA;
+}
+#endif
+
 int b200neox_eval(b200neox *m, const int *tokens, int N, int n_past, int n_threads_emulated, float *logits_out)
 {
     if (!m || !tokens || !logits_out || N < 1 || N > m->max_n || n_past < 0 || n_past + N > m->n_ctx || n_threads_emulated < 1)

@@ -1301,6 +1301,9 @@ __device__ __noinline__ int pg_consume_op(const PgParams *pp)
         const bool stop = dsc.x == -2;
         if (!stop && ++s == stages) { s = 0; ph ^= 1; }
         if (stop || (otag & PG_END)) {
+#ifdef B200Q4_TIMELINE
+            if (threadIdx.x == PG_C0 && !stop) { const PgParams &p = *pp; PG_STAMP(otag & PG_OPMASK, 4); }
+#endif
             if (lane == 0) { wst[0] = s; wst[1] = (int)ph; }
             __syncwarp();
             return stop ? 1 : 0;
@@ -1325,8 +1328,10 @@ __device__ __noinline__ void pg_side_ops(const PgParams *pp, int from, int to)
             pg_bar();                                        // (everybody has read flag[1] by now)
             if (threadIdx.x == PG_C0 && p.ops[dep].kind == PG_MATVEC) sm.flag[1] = dep;
         }
+        if (threadIdx.x == PG_C0) PG_STAMP(a, 1);
         if (kind == PG_ATTN) pg_attn(pp, a, QT);
         else pg_sum(pp, a, QT);
+        if (threadIdx.x == PG_C0) PG_STAMP(a, 3);
     }
 }
 
