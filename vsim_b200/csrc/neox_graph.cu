@@ -382,14 +382,24 @@ int build_decode_program(b200neox *m)
             return oa;
         };
         if (m->par_res == 1) {
-            // vsim.cpp:666-696: the MLP reads the layer input, so its first matrix needs nothing from the attention
+            // vsim.cpp:666-696: the MLP reads the layer input, so it needs nothing from the attention.  List order: attention
+            // right behind Q, K, V, then the MLP's first matrix, the attention's output projection, the MLP's second matrix --
+            // no op reads what the op just before it wrote.  While only a few thread blocks have heads to work on (short
+            // contexts, sharded models) their producers draw no task of the MLP's first matrix before their consumers are
+            // through the attention (PgOp::hold_a): the other blocks stream it meanwhile.
+            const int oa = attn();
+            if (oa < 0) { bad = true; break; }
             const Out o1 = chk(matvec(ly.w1, ly.b1, PG_IN_LN, PG_RES_KEEP, none, ly.ln2_w, ly.ln2_b, nullptr, false, lo + pl.hid, pl.st_H));
             if (bad) break;
-            const int oa = attn();
-            const Out o2 = chk(matvec(ly.w2, ly.b2, PG_IN_GELU, PG_RES_KEEP, o1.src, nullptr, nullptr, nullptr, false, lo + pl.out, pl.st_E));
-            if (bad || oa < 0) { bad = true; break; }
+            if (!getenv("B200NEOX_NO_HOLD")) {
+                PgOp &h = b.ops[(size_t)o1.op];
+                h.hold_a = oa + 1; h.hold_H = Hl;
+                h.dynamic = 1;                               // (in hold mode part of its tasks come from the ticket counter)
+            }
             const std::vector<PgSrc> a_in{pg_src_tag(att, oa)};
             const Out oo = chk(matvec(ly.wo, ly.bo, PG_IN_PLAIN, PG_RES_KEEP, a_in, nullptr, nullptr, nullptr, false, lo + pl.proj, pl.st_E));
+            if (bad) break;
+            const Out o2 = chk(matvec(ly.w2, ly.b2, PG_IN_GELU, PG_RES_KEEP, o1.src, nullptr, nullptr, nullptr, false, lo + pl.out, pl.st_E));
             if (bad) break;
             pending = oo.src;                                                                // inpL = inpL + (cur + inpFF)
             pending.insert(pending.end(), o2.src.begin(), o2.src.end());

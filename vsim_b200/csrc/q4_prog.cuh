@@ -117,7 +117,11 @@ struct alignas(16) PgOp {
     int pack_of, pack_seq;   // index of the first op of a run of ops with the SAME activation pack (Q, K, V): built once;
                              // pack_seq: running number of that pack (its shared-memory buffer is pack_seq & 1)
     const float *early_x;    // early > 0: that op's input vector, tensor geometry and pack number (all pg_consume_op needs to
-    int e_C, e_PP, e_TS, e_nb, e_seq, pad9;      // prepare its pack between two stages of this op)
+    int e_C, e_PP, e_TS, e_nb, e_seq;            // prepare its pack between two stages of this op)
+    int hold_a, hold_H, pad9;    // hold_a (> 0): this op follows the attention op hold_a - 1 (hold_H heads) without needing its result.
+                             // While few CTAs have attention work (items <= grid / 2), the producer of such a CTA draws no task of
+                             // this op before its consumers are through the attention: the other CTAs stream the op meanwhile
+                             // (all of its tasks come from the ticket counter), instead of everybody waiting for the few
     // (everything above is what a PG_MATVEC needs: the first PG_OPC_WORDS words are what the shared-memory op cache holds)
     // ---- PG_ATTN: the new token's attention for one layer (decode, one query row) -----------------------------
     const float *q, *k, *v;          // [H * d] {value, tag} pairs written by ops tq, tk, tv (biases already added)
@@ -368,6 +372,61 @@ __device__ __forceinline__ float4 pg_sum_src4(const PgOp &op, int nsrc, int k, i
     return a;
 }
 
+// pg_sum_src4 for TWO quads of elements at once (kA, and kB when hasB): for every (source, partial) pair the loads of both
+// quads are issued before either is looked at, which halves the number of memory round trips of a gather (a layer-norm
+// after a K-sliced MLP reads 6 pairs per quad, two quads per thread).  Same additions in the same order: same bits.
+__device__ __forceinline__ void pg_sum_src4x2(const PgOp &op, int nsrc, int kA, int kB, bool hasB, int tagbase, int *err, float4 &oA, float4 &oB)
+{
+    float4 accA = make_float4(0.f, 0.f, 0.f, 0.f), accB = accA;
+    for (int j = 0; j < nsrc; j++) {
+        const PgSrc &s = op.src[j];
+        const int kind = s.kind & 255;
+        float4 a, b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kind == PG_SRC_Q4ROW) {
+            a = pg_src4(s, kA, tagbase, err);
+            if (hasB) b = pg_src4(s, kB, tagbase, err);
+        } else {
+            const int tag = tagbase | ((s.kind >> 8) + 1);
+            for (int p = 0; p < s.np; p++) {
+                float4 tA, tB = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kind == PG_SRC_TAG) {
+                    const float *base = static_cast<const float *>(s.ptr) + 2 * (size_t)p * s.stride;
+                    const float4 a0 = ld_relaxed_f4(base + 2 * (size_t)kA), a1 = ld_relaxed_f4(base + 2 * (size_t)kA + 4);
+                    float4 b0 = a0, b1 = a1;
+                    if (hasB) { b0 = ld_relaxed_f4(base + 2 * (size_t)kB); b1 = ld_relaxed_f4(base + 2 * (size_t)kB + 4); }
+                    if (__float_as_int(a0.y) == tag && __float_as_int(a0.w) == tag && __float_as_int(a1.y) == tag && __float_as_int(a1.w) == tag)
+                        tA = make_float4(a0.x, a0.z, a1.x, a1.z);
+                    else tA = pg_ld_tag4(base, (size_t)kA, tag, err);
+                    if (hasB) {
+                        if (__float_as_int(b0.y) == tag && __float_as_int(b0.w) == tag && __float_as_int(b1.y) == tag && __float_as_int(b1.w) == tag)
+                            tB = make_float4(b0.x, b0.z, b1.x, b1.z);
+                        else tB = pg_ld_tag4(base, (size_t)kB, tag, err);
+                    }
+                } else {
+                    const float *base = static_cast<const float *>(s.ptr) + (size_t)p * s.stride;
+                    tA = __ldcg(reinterpret_cast<const float4 *>(base + kA));
+                    if (hasB) tB = __ldcg(reinterpret_cast<const float4 *>(base + kB));
+                }
+                if (p == 0) { a = tA; b = tB; }
+                else {
+                    a.x += tA.x; a.y += tA.y; a.z += tA.z; a.w += tA.w;
+                    b.x += tB.x; b.y += tB.y; b.z += tB.z; b.w += tB.w;
+                }
+            }
+            if (s.scale != 1.0f) {
+                a.x *= s.scale; a.y *= s.scale; a.z *= s.scale; a.w *= s.scale;
+                b.x *= s.scale; b.y *= s.scale; b.z *= s.scale; b.w *= s.scale;
+            }
+        }
+        if (j == 0) { accA = a; accB = b; }
+        else {
+            accA.x = __fadd_rn(accA.x, a.x); accA.y = __fadd_rn(accA.y, a.y); accA.z = __fadd_rn(accA.z, a.z); accA.w = __fadd_rn(accA.w, a.w);
+            accB.x = __fadd_rn(accB.x, b.x); accB.y = __fadd_rn(accB.y, b.y); accB.z = __fadd_rn(accB.z, b.z); accB.w = __fadd_rn(accB.w, b.w);
+        }
+    }
+    oA = accA; oB = accB;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Attention for the token at position n_past (decode): work items = (head, chunk of PG_ATT_CHUNK positions), dealt
 // to the CTAs round-robin.  An item ropes Q (and, if its chunk holds the new position, ropes K and stores K and V into
@@ -551,10 +610,13 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
     // warp 0: s_sc[i] = exp-table(s_sc[i] - M) in place; returns their sum (double, lane-strided partial sums added in a tree)
     auto chunk_exp = [&](int np, float M) {
         double l = 0.0;
-        for (int i = lane; i < np; i += 32) {
-            const float e = texp(__fsub_rn(s_sc[i], M));
-            s_sc[i] = e;
-            l = __dadd_rn(l, (double)e);
+        for (int i0 = lane; i0 < np; i0 += 128) {            // four table look-ups in flight per lane; added in index order
+            float e[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) e[u] = i0 + 32 * u < np ? texp(__fsub_rn(s_sc[i0 + 32 * u], M)) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (i0 + 32 * u < np) { s_sc[i0 + 32 * u] = e[u]; l = __dadd_rn(l, (double)e[u]); }
         }
 #pragma unroll
         for (int of = 16; of > 0; of >>= 1) l = __dadd_rn(l, __shfl_xor_sync(0xffffffffu, l, of));
@@ -568,14 +630,24 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
         const bool has_new = p_lo + np == P;
         pg_bar();                                            // the previous item's scratch is no longer read
         for (int j = ctid; j < d; j += PG_CTHREADS) {
-            float qv = pg_ld_tag1(gq, (size_t)h * d + j, tag_q, p.err), kv = 0.f, vv = 0.f;
-            if (has_new) { kv = pg_ld_tag1(gk, (size_t)h * d + j, tag_k, p.err); vv = pg_ld_tag1(gv, (size_t)h * d + j, tag_v, p.err); }
-            if (j < 2 * half) {
-                const bool fh = j < half;
-                const int jp = fh ? j + half : j - half, i0 = fh ? j : j - half;
-                const double2 cs = op.rope[(size_t)n_past * half + i0];
-                qv = pg_rope(qv, pg_ld_tag1(gq, (size_t)h * d + jp, tag_q, p.err), fh, cs);
-                if (has_new) kv = pg_rope(kv, pg_ld_tag1(gk, (size_t)h * d + jp, tag_k, p.err), fh, cs);
+            // everything this element needs is requested at once (one memory round trip); a value whose tag is not this
+            // launch's yet is polled for afterwards
+            const bool roped = j < 2 * half, fh = j < half;
+            const int jp = roped ? (fh ? j + half : j - half) : j, i0 = fh ? j : j - half;
+            const size_t e = (size_t)h * d + j, ep = (size_t)h * d + jp;
+            const float2 q2 = ld_relaxed_f2(gq + 2 * e), qp2 = ld_relaxed_f2(gq + 2 * ep);
+            float2 k2 = make_float2(0.f, 0.f), kp2 = k2, v2 = k2;
+            if (has_new) { k2 = ld_relaxed_f2(gk + 2 * e); kp2 = ld_relaxed_f2(gk + 2 * ep); v2 = ld_relaxed_f2(gv + 2 * e); }
+            double2 cs = make_double2(1.0, 0.0);
+            if (roped) cs = op.rope[(size_t)n_past * half + i0];
+            float qv = __float_as_int(q2.y) == tag_q ? q2.x : pg_ld_tag1(gq, e, tag_q, p.err), kv = 0.f, vv = 0.f;
+            if (has_new) {
+                kv = __float_as_int(k2.y) == tag_k ? k2.x : pg_ld_tag1(gk, e, tag_k, p.err);
+                vv = __float_as_int(v2.y) == tag_v ? v2.x : pg_ld_tag1(gv, e, tag_v, p.err);
+            }
+            if (roped) {
+                qv = pg_rope(qv, __float_as_int(qp2.y) == tag_q ? qp2.x : pg_ld_tag1(gq, ep, tag_q, p.err), fh, cs);
+                if (has_new) kv = pg_rope(kv, __float_as_int(kp2.y) == tag_k ? kp2.x : pg_ld_tag1(gk, ep, tag_k, p.err), fh, cs);
             }
             s_q[j] = qv;
             if (has_new) {
@@ -772,18 +844,29 @@ __device__ __noinline__ void pg_build_pack(const PgParams *pp, const PgOp *opp, 
         if (res != PG_RES_KEEP) {
             // ggml_norm (ggml.c:4282-4298): mean and variance accumulated in double (tree order here), two passes
             double ls = 0.0;
-            for (int k4 = ctid; k4 < K / 4; k4 += NT) {
-                float4 a;
-                if (res == PG_RES_TEMP) a = ln_in(k4);
-                else {
-                    a = pg_sum_src4(op, nsrc, k4 * 4, tagbase, err);
-                    if (res == PG_RES_ADD) {
-                        const float4 x = sx4[k4];
-                        a.x = __fadd_rn(x.x, a.x); a.y = __fadd_rn(x.y, a.y); a.z = __fadd_rn(x.z, a.z); a.w = __fadd_rn(x.w, a.w);
-                    }
-                    sx4[k4] = a;
+            if (res == PG_RES_TEMP) {
+                for (int k4 = ctid; k4 < K / 4; k4 += NT) {
+                    const float4 a = ln_in(k4);
+                    ls = __dadd_rn(ls, __dadd_rn(__dadd_rn((double)a.x, (double)a.y), __dadd_rn((double)a.z, (double)a.w)));
                 }
-                ls = __dadd_rn(ls, __dadd_rn(__dadd_rn((double)a.x, (double)a.y), __dadd_rn((double)a.z, (double)a.w)));
+            } else {
+                for (int kb = ctid; kb < K / 4; kb += 2 * NT) {     // this thread's quads two at a time: their loads travel together
+                    const bool second = kb + NT < K / 4;
+                    float4 av[2];
+                    pg_sum_src4x2(op, nsrc, kb * 4, (kb + NT) * 4, second, tagbase, err, av[0], av[1]);
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        if (u == 1 && !second) break;
+                        const int k4 = kb + u * NT;
+                        float4 a = av[u];
+                        if (res == PG_RES_ADD) {
+                            const float4 x = sx4[k4];
+                            a.x = __fadd_rn(x.x, a.x); a.y = __fadd_rn(x.y, a.y); a.z = __fadd_rn(x.z, a.z); a.w = __fadd_rn(x.w, a.w);
+                        }
+                        sx4[k4] = a;
+                        ls = __dadd_rn(ls, __dadd_rn(__dadd_rn((double)a.x, (double)a.y), __dadd_rn((double)a.z, (double)a.w)));
+                    }
+                }
             }
             const double mean = block_sum(ls) / (double)K;
             double l2 = 0.0;
@@ -887,8 +970,7 @@ __device__ __noinline__ void pg_build_pack(const PgParams *pp, const PgOp *opp, 
             const int k = (blk0 + blk) * QK + (lane & 3) * 8;
             float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
             if (valid) {
-                lo = pg_sum_src4(op, nsrc, k, tagbase, err);
-                hi = pg_sum_src4(op, nsrc, k + 4, tagbase, err);
+                pg_sum_src4x2(op, nsrc, k, k + 4, true, tagbase, err, lo, hi);
                 if (in_mode == PG_IN_GELU) {
                     // ggml_gelu (ggml.c:819-827, GGML_GELU_FP16): x -> fp16 -> table -> fp32
                     auto gl = [&](float x) { return __half2float(__ushort_as_half(__ldg(tab + __half_as_ushort(__float2half_rn(x))))); };
@@ -1002,16 +1084,37 @@ __device__ __noinline__ void pg_producer(const PgParams *pp)
         const int nxt_o = op.next_mv;
         cw = fetch(nxt_o);                                   // lands while this op's tasks are issued
         if (lane == 0) {
+            bool hold_mode = false;                         // (the same decision in every CTA: it depends on n_past alone)
+            int items_h = 0;                                // hold mode: the CTAs 0 .. items_h - 1 have attention work
+            if (op.hold_a > 0) {
+                const PgAttGeo ag = pg_att_geo((p.dyn ? __ldg(p.dyn + 1) : 0) + 1, op.hold_H, grid);
+                items_h = op.hold_H * ag.nch;
+                hold_mode = items_h * 2 <= grid;
+                if (!hold_mode) items_h = 0;
+                if (hold_mode && bid < items_h && *reinterpret_cast<volatile int *>(sm.flag + 3) < op.hold_a) {
+                    put(0, 0, 0, 0, o, nullptr);             // a bare entry of this op: what makes the consumers run the attention before it
+                    const long long t0 = clock64();
+                    while (*reinterpret_cast<volatile int *>(sm.flag + 3) < op.hold_a) {
+                        __nanosleep(200);
+                        if (clock64() - t0 > 8000000000ll) __trap();
+                    }
+                }
+                if (op.dynamic) pre_ticket = atomicAdd(p.ctr + op.tk_off + (op.PP > 1 ? bid % op.PP : 0), 1);   // (none was drawn ahead)
+            }
             PG_STAMP(o, 0);
             int nx_ticket = 0;
             if (nxt_o < p.n_ops && op.nx_dynamic) nx_ticket = atomicAdd(p.ctr + op.nx_tk_off + (op.nx_PP > 1 ? bid % op.nx_PP : 0), 1);
             const uint8_t *wt = op.wt;
-            const int C = op.C, PP = op.PP, TS = op.TS, U = op.U, nstatic = op.nstatic;
+            const int C = op.C, PP = op.PP, TS = op.TS, U = op.U;
             const bool sliced = PP > 1;
             const int cls = sliced ? bid % PP : 0, cbase = cls * TS;
-            const int ncls = sliced ? (grid - cls + PP - 1) / PP : grid;
-            int idx = (sliced ? bid / PP : bid) + op.rot;
-            idx -= (idx / ncls) * ncls;
+            // hold mode: the static tasks are dealt to the CTAs without attention work only (hcls CTAs of this class have some:
+            // the lowest block indices); whatever is left comes from the ticket counter, for everybody
+            const int hcls = sliced ? (items_h > cls ? (items_h - cls + PP - 1) / PP : 0) : items_h;
+            const int ncls = (sliced ? (grid - cls + PP - 1) / PP : grid) - hcls;
+            const int nstatic = (hold_mode && bid < items_h) ? 0 : op.nstatic;
+            int idx = (sliced ? bid / PP : bid) - hcls + (hold_mode ? 0 : op.rot);
+            if (idx >= ncls) idx -= (idx / ncls) * ncls;
             const int limit = sliced ? op.n_tiles : op.ntasks;
             // tasks are issued one behind, so that the CTA's last stage of the op can carry the END flag
             int pend = -1;
@@ -1036,7 +1139,7 @@ __device__ __noinline__ void pg_producer(const PgParams *pp)
             }
             if (op.dynamic) {
                 int *tk = p.ctr + op.tk_off + cls;
-                const int base = nstatic * ncls;
+                const int base = op.nstatic * ncls;
                 int cur = base + pre_ticket;
                 while (cur < limit) {
                     const int nxt = base + atomicAdd(tk, 1);   // one task ahead: the atomic's latency hides behind the copies
@@ -1331,7 +1434,7 @@ __device__ __noinline__ void pg_side_ops(const PgParams *pp, int from, int to)
         if (threadIdx.x == PG_C0) PG_STAMP(a, 1);
         if (kind == PG_ATTN) pg_attn(pp, a, QT);
         else pg_sum(pp, a, QT);
-        if (threadIdx.x == PG_C0) PG_STAMP(a, 3);
+        if (threadIdx.x == PG_C0) { PG_STAMP(a, 3); *reinterpret_cast<volatile int *>(sm.flag + 3) = a + 1; }     // (what a holding producer waits for)
     }
 }
 
@@ -1416,7 +1519,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) q4_prog_kernel(const PgParams p
     }
     if (threadIdx.x == PG_THREADS - 1) {
         s_p = p;
-        sm.flag[1] = -1; sm.flag[5] = -1; sm.flag[7] = -1;
+        sm.flag[1] = -1; sm.flag[5] = -1; sm.flag[7] = -1; sm.flag[3] = 0;
         sm.flag[6] = (int)(((unsigned)p.dyn[2] & 0x7ffffu) << 12);           // tag = epoch << 12 | (op index + 1)
         sm.flag[2] = p.dyn[2];                                               // the launch epoch itself: arrival / hint counters are
                                                                              // never reset, op o is complete at epoch * (CTAs that add)

@@ -232,7 +232,10 @@ int prog_finalize_sharded(const ProgBuild &b, Prog &out, int rank, int world, in
     for (int i = pg.n_ops - 1; i >= 0; i--) {
         PgOp &op = ops[(size_t)i];
         op.next_mv = nxt;
-        if (nxt < pg.n_ops) { op.nx_tk_off = ops[(size_t)nxt].tk_off; op.nx_PP = ops[(size_t)nxt].PP; op.nx_dynamic = ops[(size_t)nxt].dynamic; }
+        if (nxt < pg.n_ops) {
+            op.nx_tk_off = ops[(size_t)nxt].tk_off; op.nx_PP = ops[(size_t)nxt].PP;
+            op.nx_dynamic = ops[(size_t)nxt].hold_a > 0 ? 0 : ops[(size_t)nxt].dynamic;      // (a holding op draws its first ticket itself)
+        }
         if (op.kind == PG_MATVEC) nxt = i;
     }
     pg.first_mv = nxt;
