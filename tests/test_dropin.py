@@ -14,6 +14,7 @@ from oracle import Q4_0, Q4_1, REF_DIR
 
 REF_BIN = REF_DIR / "vsim-ubuntu"
 B200_BIN = REF_DIR / "vsim-b200"
+DEV_BIN = B200_BIN.parent / "vsim-b200dev"      # the same program on the device-resident graph (vsim.cpp + 3-line patch)
 ORACLE_BIN = REF_DIR / "vsim-oracle"
 B200_LIB = REF_DIR / "libggml_b200.so"
 
@@ -112,6 +113,35 @@ def test_vsim_neox_exact_mode_reproduces_the_reference_bit_for_bit(tmp_path, qt,
     assert lr.shape == lg.shape
     assert np.array_equal(lr, lg), np.abs(lr - lg).max()
     assert _tokens(_run(REF_BIN, model, n_predict=24)) == _tokens(_run(B200_BIN, model, n_predict=24, env=ex))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("qt,tag", [(Q4_0, "q4_0"), (Q4_1, "q4_1")])
+def test_vsim_neox_on_the_device_resident_graph(tmp_path, qt, tag):
+    """Row f-1 inside the reference program: vsim.cpp with the three-line patch of INTEGRATION.md hands gptneox_eval to
+    b200neox_eval (token ids in, logits out, nothing of the graph on the host).  Exact mode: the SAME printed logits and
+    greedy tokens as the unmodified CPU binary (prompt batch and decode steps; decode steps run the per-op exact kernels).
+    Default mode (the decode program kernel): prompt logits within 1e-3."""
+    if not (REF_BIN.exists() and DEV_BIN.exists()):
+        pytest.skip("oracle/_ref vsim binaries not built")
+    from tests.helpers.neox_file import write_neox
+    model = tmp_path / f"dev-{tag}.bin"
+    write_neox(model, qt, n_vocab=512, n_embd=512, n_head=8, n_layer=6, n_rot=32, seed=3)
+    lr = _logits(_run(REF_BIN, model, logits=True))
+    tr = _tokens(_run(REF_BIN, model, n_predict=24))
+    ex = {"B200Q4_EXACT": "1"}
+    le = _logits(_run(DEV_BIN, model, logits=True, env=ex))
+    assert lr.shape == le.shape and np.array_equal(lr, le), np.abs(lr - le).max()
+    assert tr == _tokens(_run(DEV_BIN, model, n_predict=24, env=ex))
+    fast = {"B200Q4_EXACT": "0"}
+    lf = _logits(_run(DEV_BIN, model, logits=True, env=fast))
+    assert np.abs(lf - lr).max() <= 1e-3 * np.abs(lr).max(), np.abs(lf - lr).max() / np.abs(lr).max()
+    # (greedy tokens of a random-init model are not compared in this mode: its logits have near-ties, and a difference in
+    # the seventh digit picks another token; the decode program itself is checked against the oracle in test_gpu_neox_graph)
+    tf = _tokens(_run(DEV_BIN, model, n_predict=24, env=fast))
+    assert len(tf) == len(tr) and tf[:6] == tr[:6]
+    # and with the binding switched off the program is the hook-only drop-in again
+    assert tr == _tokens(_run(DEV_BIN, model, n_predict=24, env={"B200NEOX": "0", "B200Q4_EXACT": "1"}))
 
 
 @pytest.mark.parametrize("qt,tag", [(Q4_0, "q4_0"), (Q4_1, "q4_1")])

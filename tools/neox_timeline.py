@@ -53,6 +53,11 @@ for o in range(n):
     if lay * per_layer <= o < (lay + 2) * per_layer or o >= n - 3:
         step = (end - prev) if (prev is not None and end == end) else float("nan")
         print(f"{o:3d} {['mv','attn','sum'][k]:5s} {int(kinds[o]) >> 4:6d} | {med(0):8.2f} | {med(1):8.2f} {mx(1):8.2f} | {med(2):8.2f} | {med(3):8.2f} {mx(3):8.2f} | {med(4):8.2f} {mx(4):8.2f} | {med(5):8.2f} {mx(5):8.2f} | {step:6.2f}")
+    if k == 1 and lay * per_layer <= o < (lay + 2) * per_layer:
+        has = t[:, o, 0] >= 0
+        if has.any():
+            seg = [float(np.median(t[has, o, i] - t[has, o, 1])) / 1e3 for i in (0, 2, 4, 5, 6, 7, 3)]
+            print(f"      attention on the {int(has.sum())} CTAs with an item, us after reaching the op: item start {seg[0]:.2f} | q/k/v+rope {seg[1]:.2f} | scores {seg[2]:.2f} | softmax {seg[3]:.2f} | PV {seg[4]:.2f} | stored {seg[5]:.2f} | left {seg[6]:.2f}")
     if end == end:
         prev = end
 print(f"last stamp at {tot_end:.1f} us")

@@ -629,6 +629,7 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
         const int p_lo = c * CHK, np = min(CHK, P - p_lo);
         const bool has_new = p_lo + np == P;
         pg_bar();                                            // the previous item's scratch is no longer read
+        if (ctid == 0) PG_STAMP(o, 0);
         for (int j = ctid; j < d; j += PG_CTHREADS) {
             // everything this element needs is requested at once (one memory round trip); a value whose tag is not this
             // launch's yet is polled for afterwards
@@ -657,8 +658,10 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
             }
         }
         pg_bar();
+        if (ctid == 0) PG_STAMP(o, 2);
         pg_att_scores(mk, s_q, s_kn, s_sc, p_lo, np, n_past, E, h * d, d, scale, ctid);
         pg_bar();
+        if (ctid == 0) PG_STAMP(o, 4);
         if (nch > 1) {                                       // publish the chunk: the row maximum needs every chunk
             for (int i = ctid; i < np; i += PG_CTHREADS) g_sc[(size_t)h * op.n_ctx + p_lo + i] = s_sc[i];
             if (warp == 0) {
@@ -679,8 +682,11 @@ __device__ __noinline__ void pg_attn(const PgParams *pp, int o, int qt)
             for (int i = lane; i < np; i += 32) s_sc[i] = __fmul_rn(s_sc[i], inv);
         }
         pg_bar();
+        if (ctid == 0) PG_STAMP(o, 5);
         pg_att_pv(mv, s_vn, s_sc, s_o, p_lo, np, n_past, E, h * d, d, ctid);
+        if (ctid == 0) PG_STAMP(o, 6);
         if (ctid < d) att_store((size_t)(op.head0 + h) * d + ctid, s_o[ctid]);
+        if (ctid == 0) PG_STAMP(o, 7);
     }
     // ---- pass B (several chunks per head): exponentials against the ROW maximum, chunk denominators, weighted V sums; the
     //      head's last chunk to finish adds the pieces up.  Every CTA has published all of its chunks before it waits here.
