@@ -19,6 +19,7 @@ SOURCES = [CSRC / "q4_api.cu", CSRC / "q4_prog_api.cu", CSRC / "neox_graph.cu", 
 DEPS = SOURCES + [CSRC / "q4_kernels.cuh", CSRC / "q4_tile.cuh", CSRC / "q4_prog.cuh", CSRC / "q4_prog_host.h", CSRC / "q4_internal.h", PKG.parent / "include" / "b200q4.h",
                   PKG.parent / "include" / "b200q4_ggml_abi.h", PKG.parent / "include" / "b200neox.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-cudart", "shared",            # the runtime stays a shared library: no copy of its symbol table inside the artefact
               "-Xcompiler", "-fPIC", "-shared"]
 
 

@@ -61,6 +61,7 @@ struct Ctx {
     // cuStreamWriteValue32 (driver API, fetched through the runtime: no link-time dependency on libcuda): the
     // completion word is written by the stream's front end instead of a one-thread kernel
     int (*stream_write32)(cudaStream_t, unsigned long long, uint32_t, unsigned int) = nullptr;
+    int  init_gen = 0;               // bumped by every successful b200q4_init (per-device function attributes are set again)
     bool exact = false;              // b200q4_set_exact / B200Q4_EXACT=1: the reference's own fp32 rounding sequence (bit-identical Y)
     uint8_t *d_exq = nullptr; size_t exq_cap = 0;       // exact mode: reference-format quantized activation rows
     float *d_exdeq = nullptr; size_t exdeq_cap = 0;     // exact mode: the floats the reference's dot product forms from them
@@ -195,12 +196,12 @@ PipePlan pipe_plan(const b200q4_weight *w, int M, bool fuse)
 template <int QT, int MP, bool FUSED, bool M1, bool B8, int NCW>
 int launch_pipe(const PipeParams &p, int grid, size_t smem, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static int attr_gen = -1;                                // (function attributes are per device and context: redone after every b200q4_init)
+    if (attr_gen != g.init_gen) {
         CK(cudaFuncSetAttribute(q4_gemv_pipe_kernel<QT, MP, FUSED, M1, B8, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_optin));
         if (NCW == 8)
             CK(cudaFuncSetAttribute(q4_gemv_pipe_kernel<QT, MP, FUSED, M1, B8, NCW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set = true;
+        attr_gen = g.init_gen;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3((NCW + 2) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -309,10 +310,10 @@ TilePlan tile_plan(const b200q4_weight *w, int M)
 template <int QT, int MT>
 int launch_tile(const TileParams &p, int grid, size_t smem, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static int attr_gen = -1;
+    if (attr_gen != g.init_gen) {
         CK(cudaFuncSetAttribute(q4_tile_kernel<QT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_optin));
-        attr_set = true;
+        attr_gen = g.init_gen;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TK_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -678,6 +679,7 @@ int b200q4_init(int device)
     if (const char *e = getenv("B200Q4_STATIC_TASKS")) g.static_tasks = atoi(e);
     if (const char *e = getenv("B200Q4_PREFETCH_STAGES")) g.prefetch_stages = atoi(e);
     if (const char *e = getenv("B200Q4_EXACT")) g.exact = atoi(e) != 0;
+    g.init_gen++;
     if (cudaHostAlloc(reinterpret_cast<void **>(&g.h_flag), 64, cudaHostAllocMapped) == cudaSuccess &&
         cudaHostGetDevicePointer(reinterpret_cast<void **>(&g.d_flag), g.h_flag, 0) == cudaSuccess) {
         *g.h_flag = 0; g.hseq = 0;
@@ -1070,14 +1072,15 @@ b200q4_model *b200q4_model_load(const char *path, int n_header_ints, int vocab_h
             if (v < 0) return bail("bad tensor shape");
             t.ne[i] = v;
         }
-        if (off + (size_t)length > size) return bail("truncated tensor name");
+        if ((size_t)length > size - off) return bail("truncated tensor name");
         t.name.assign(reinterpret_cast<const char *>(b + off), (size_t)length);
         off += (size_t)length;
-        const size_t nel = (size_t)t.ne[0] * (size_t)t.ne[1];
+        const size_t nel = (size_t)t.ne[0] * (size_t)t.ne[1];                      // (both < 2^31: no wrap)
         if (ftype >= 2 && t.ne[0] % QK) return bail("quantized tensor whose row length is not a multiple of 32");
+        if (nel > (size_t)-1 / 4) return bail("tensor too large");                  // nel * bytes per element must not wrap either
         t.nbytes = ftype == 0 ? nel * 4 : ftype == 1 ? nel * 2 : nel / QK * (ftype == 2 ? 20 : 24);
         t.offset = off;
-        if (off + t.nbytes > size) return bail("truncated tensor data");
+        if (t.nbytes > size - off) return bail("truncated tensor data");
         off += t.nbytes;
         m->tensors.push_back(t);
     }
