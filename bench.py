@@ -666,11 +666,19 @@ def main() -> int:
         ws = [w0[i % nw] for i in range(per)]
         xs = [d_x[i % 512].data_ptr() for i in range(per)]
         ys = [d_yloc[i % 512].data_ptr() for i in range(per)]
-        ch = vs.Chain(ws, xs, ys, [-1] * per)
         tail = None
-        if steps % per:
-            r = steps % per
-            tail = vs.Chain(ws[:r], xs[:r], ys[:r], [-1] * r)
+        if world > 1:
+            # N > 1: every rank streams its own shard of a (world x N_ROWS)-row tensor per step and the reducer warps store the
+            # output slice into EVERY rank's pool over NVLink ({value, tag} pairs): the all-gather of every step is inside
+            # the launch.  A remainder of steps % per runs through the same list (fewer ops would need a second pool).
+            from vsim_b200.shard import ShardedChain
+            ch = ShardedChain(L, ws, xs)
+            nl = (steps + per - 1) // per
+        else:
+            ch = vs.Chain(ws, xs, ys, [-1] * per)
+            if steps % per:
+                r = steps % per
+                tail = vs.Chain(ws[:r], xs[:r], ys[:r], [-1] * r)
         try:
             for _ in range(max(1, (warm + per - 1) // per)):
                 ch.run(stream.cuda_stream)
@@ -679,15 +687,21 @@ def main() -> int:
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            for _ in range(steps // per):
+            for _ in range(steps // per if world == 1 else nl):
                 ch.run(stream.cuda_stream)
             if tail is not None:
                 tail.run(stream.cuda_stream)
             e1.record(stream)
             barrier()
             ms = e0.elapsed_time(e1)
+            if world > 1:
+                ms = ms * steps / (nl * per)                 # (whole launches were timed: nl * per >= steps of them)
+                t = torch.tensor([ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
             # parity of the product path, inside the run: step 1's output row against the per-op kernel on the same inputs
-            y_prog = d_yloc[1 % 512].clone()
+            # (N > 1: this rank's slice of the gathered vector in its own pool)
+            y_prog = (d_yloc[1 % 512] if world == 1 else ch.gathered(1)[rank * N_ROWS:(rank + 1) * N_ROWS]).clone()
             rc = L.b200q4_mul_mat_dev(w0[1 % nw].handle, d_x[1 % 512].data_ptr(), 1, K_DIM * 4, d_y.data_ptr(), N_ROWS * 4, stream.cuda_stream)
             barrier()
             diff = float((y_prog - d_y.view(-1)[:N_ROWS]).abs().max()) if rc == 0 else float("nan")
@@ -702,7 +716,7 @@ def main() -> int:
     M_HEAD = 1
     vs.launch_count_reset()
     headline = None
-    if world == 1 and not args.per_call:
+    if not args.per_call and not args.nccl:
         ms_total, launches_timed, per_launch, hdiff = timed_program(args.steps, args.warmup)
         headline = {"ops_per_launch": per_launch, "launches": launches_timed, "max_abs_diff_vs_per_call_kernel": hdiff}
         ms_call = timed(M_HEAD, w0, args.steps, args.warmup) / args.steps      # the same steps as one launch per call, for the record
@@ -732,7 +746,7 @@ def main() -> int:
             traffic = None
     if headline:
         launch_ms = ms_total / headline["launches"]
-        units = args.steps / headline["launches"]                              # mul_mats per launch (average)
+        units = args.steps / headline["launches"]                              # mul_mats per launch and rank (average)
         roof = {"achieved": alg_bytes(0, M_HEAD) * units / (launch_ms * 1e-3) / 1e9,
                 "kernel": "q4_prog_kernel<Q4_0> (persistent: producer warp + 16 consumer warps + reducer warp per SM; "
                           f"{headline['ops_per_launch']} independent M=1 mul_mats per launch, each with its own activation quantization), "
@@ -800,7 +814,8 @@ def main() -> int:
     exchange = None
     if world > 1 and po is not None:                       # the same M=1 step with an NCCL all-gather, for comparison
         ms_nccl = timed(M_HEAD, w0, min(args.steps, 200), 5, nccl=True) / min(args.steps, 200)
-        exchange = {"fused_peer_store_us_per_step": ms_step * 1e3, "nccl_all_gather_us_per_step": ms_nccl * 1e3,
+        exchange = {"fused_peer_store_us_per_step": (headline["per_call_launches_us_per_step"] if headline else ms_step * 1e3),
+                    "program_peer_store_us_per_step": ms_step * 1e3 if headline else None, "nccl_all_gather_us_per_step": ms_nccl * 1e3,
                     "bytes_per_rank_per_step": M_HEAD * N_ROWS * 4}
     if world > 1 and po is not None:
         exchange = exchange or {}
@@ -865,6 +880,8 @@ def main() -> int:
                 "parallelism": "single GPU" if world == 1 else
                                f"{world}-way row shard of a {N_ROWS * world}-row tensor; fp32 output slices " +
                                ("all-gathered with NCCL" if po is None else
+                                "stored into every rank's pool by the reducer warps of the persistent launch ({value, tag} pairs, peer memory "
+                                "over NVLink): the all-gather of every step is inside the launch" if headline else
                                 "stored into every rank's Y by the kernel epilogue (peer memory over NVLink) + arrival counters; "
                                 "the timed loop replays a CUDA graph of one rotation over the weight tensors"),
                 "kernel": "q4_prog_kernel<Q4_0>" if headline else vs.kernel_for(0, M_HEAD, N_ROWS, K_DIM),

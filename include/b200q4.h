@@ -141,6 +141,15 @@ int b200q4_quantize_rows_dev(int type, const float *d_x, int M, int K, size_t x_
 typedef struct b200q4_chain b200q4_chain;
 b200q4_chain *b200q4_chain_create(int n, const b200q4_weight *const *ws, const float *const *d_x,
                                   float *const *d_y, const int *deps);
+/* The same for row shards on several GPUs (one process per GPU): op i is this rank's shard (N_i rows)
+ * of a tensor with world * N_i rows, the split of imax.c:1185-1188; its outputs are stored by the kernel into EVERY rank's
+ * pool (pool_peers[r]: rank r's pool mapped into this process, CUDA IPC / symmetric memory; pool_bytes each, zeroed, same
+ * layout everywhere) at byte offset y_off[i] as {value, tag} pairs (8 bytes per element, 2 * world * N_i floats per op):
+ * the all-gather of the output slices is part of the mul_mat, no collective call.  The pool begins with
+ * b200q4_chain_sharded_ctr_bytes(n) bytes of counters.  Inputs d_x[i] are local fp32 vectors (K <= 8192).              */
+size_t b200q4_chain_sharded_ctr_bytes(int n);
+b200q4_chain *b200q4_chain_create_sharded(int n, const b200q4_weight *const *ws, const float *const *d_x, int rank, int world,
+                                          void *const *pool_peers, size_t pool_bytes, const size_t *y_off);
 int  b200q4_chain_run(b200q4_chain *c, void *stream);       /* asynchronous on `stream` */
 int  b200q4_chain_info(const b200q4_chain *c, int *n_ops, int *stages, size_t *smem_bytes);
 void b200q4_chain_free(b200q4_chain *c);

@@ -1357,7 +1357,7 @@ __device__ __noinline__ int pg_consume_op(const PgParams *pp)
     // A later op whose input is a plain vector nobody in the list writes (PgOp::early): this thread's eight elements of it
     // are requested now and quantized into the OTHER pack buffer after the first stage -- no pause, no barrier here.
     float4 elo = make_float4(0.f, 0.f, 0.f, 0.f), ehi = elo;
-    int e_items = -1, e_blk0 = 0, e_nbp = 0;
+    int e_items = -1, e_blk0 = 0, e_nbp = 0, e_seen = 0;
     {
         const PgOp &cop = pg_cached_op(sm, wst[2]);
         if (wst[2] < pp->n_ops && cop.early > 0) {          // (the STOP marker has no op record)
@@ -1387,7 +1387,9 @@ __device__ __noinline__ int pg_consume_op(const PgParams *pp)
         if (dsc.x > 0) pg_consume_stage<QT>(sm, s_aq, s_ap, gC, gcbase, gplane, s, dsc.x, dsc.y, dsc.z, (otag & PG_FAST) != 0);
         if (threadIdx.x == PG_C0 && dsc.x > 0) { PG_ACC(pp, 5, PG_CLK() - tc); PG_ACC(pp, 6, 1); }
         pg_done_arrive(s);
-        if (e_items >= 0) {                                  // (once per op, after its first ring entry)
+        // (once per op: after the third ring entry -- the input vector comes from HBM and takes longer than one stage
+        // to arrive -- or the op's last entry if that comes first)
+        if (e_items >= 0 && (++e_seen >= 3 || (otag & PG_END) || dsc.x == -2)) {
             constexpr int NP = (QT == 0) ? 2 : 3;
             const int ctid = (int)threadIdx.x - PG_C0;
             uint8_t *d_aq = sm.aq + (size_t)(b ^ 1) * sm.pack_stride;

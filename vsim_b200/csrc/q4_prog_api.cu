@@ -382,6 +382,53 @@ b200q4_chain *b200q4_chain_create(int n, const b200q4_weight *const *ws, const f
     return c;
 }
 
+/* Row-sharded list (one process per GPU): op i is this rank's row shard of a tensor with world * N_i rows; its outputs go
+ * into EVERY rank's pool as {value, tag} pairs at byte offset y_off[i] (rows rank * N_i ...), stored by the reducer warps
+ * over NVLink -- the all-gather is part of the mul_mat, no collective call.  Inputs are plain local vectors.
+ * The pool starts with the counter area (b200q4_chain_sharded_ctr_bytes(n) bytes, zeroed, at the same place on every rank). */
+size_t b200q4_chain_sharded_ctr_bytes(int n) { return (((size_t)(64 + 16 * (n + 4)) * 4) + 255) & ~(size_t)255; }
+
+b200q4_chain *b200q4_chain_create_sharded(int n, const b200q4_weight *const *ws, const float *const *d_x, int rank, int world,
+                                          void *const *pool_peers, size_t pool_bytes, const size_t *y_off)
+{
+    ApiLock lk;
+    if (dev_info().device < 0) { api_fail(B200Q4_ENODEV, "b200q4_init() has not succeeded; no CPU fallback exists"); return nullptr; }
+    if (n < 1 || !ws || !d_x || !pool_peers || !y_off || world < 2 || world > 8 || rank < 0 || rank >= world) {
+        api_fail(B200Q4_EINVAL, "chain_create_sharded: bad argument");
+        return nullptr;
+    }
+    b200q4_chain *c = new b200q4_chain();
+    ProgBuild b;
+    const size_t ctr_bytes = b200q4_chain_sharded_ctr_bytes(n);
+    for (int i = 0; i < n; i++) {
+        const b200q4_weight *w = ws[i];
+        if (!w || w->transposed || !d_x[i] || (reinterpret_cast<uintptr_t>(d_x[i]) & 15) || (y_off[i] & 15) || y_off[i] < ctr_bytes ||
+            y_off[i] + (size_t)2 * 4 * w->N * world > pool_bytes) {
+            api_fail(B200Q4_EINVAL, "chain_create_sharded: bad op %d", i);
+            delete c;
+            return nullptr;
+        }
+        if (pg_geometry(w).PP > 1) {
+            api_fail(B200Q4_EINVAL, "chain_create_sharded: op %d: K > 8192 is not supported here", i);
+            delete c;
+            return nullptr;
+        }
+        const PgSrc src = pg_src_f32(d_x[i]);
+        const bool same_pack = i > 0 && d_x[i] == d_x[i - 1] && ws[i - 1]->K == w->K && ws[i - 1]->C == w->C;
+        float *y = reinterpret_cast<float *>(static_cast<char *>(pool_peers[rank]) + y_off[i]);
+        const int o = b.add_matvec(w, -1, PG_IN_PLAIN, PG_RES_KEEP, &src, 1, nullptr, nullptr, nullptr, y, nullptr, 0, true, same_pack, nullptr);
+        if (o < 0) { delete c; return nullptr; }
+        PgOp &op = b.ops[(size_t)o];
+        op.row0 = rank * w->N;
+        for (int r = 0; r < world; r++) op.y_peer[r] = reinterpret_cast<float *>(static_cast<char *>(pool_peers[r]) + y_off[i]);
+    }
+    if ((size_t)prog_counter_ints(b) * 4 > ctr_bytes) { api_fail(B200Q4_EINVAL, "chain_create_sharded: counter area too small"); delete c; return nullptr; }
+    int *ctrs[8] = {nullptr};
+    for (int r = 0; r < world; r++) ctrs[r] = static_cast<int *>(pool_peers[r]);
+    if (prog_finalize_sharded(b, c->pg, rank, world, ctrs)) { delete c; return nullptr; }
+    return c;
+}
+
 int b200q4_chain_run(b200q4_chain *c, void *stream)
 {
     ApiLock lk;

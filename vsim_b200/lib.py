@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "b200q4_model_weight", "b200q4_model_tensor_data", "b200q4_model_free",
     "b200neox_load", "b200neox_n_vocab", "b200neox_eval", "b200neox_free", "b200neox_last_error", "b200neox_decode_is_program", "b200neox_load_sharded", "b200neox_sharded_pool_bytes",
     "b200q4_chain_create", "b200q4_chain_run", "b200q4_chain_info", "b200q4_chain_free",
+    "b200q4_chain_sharded_ctr_bytes", "b200q4_chain_create_sharded",
     "b200q4_host_alloc", "b200q4_host_free", "b200q4_launch_count", "b200q4_launch_count_reset",
     "b200q4_kernel_for", "b200q4_time_mul_mat_dev",
 ]
@@ -101,6 +102,8 @@ def load_library(build: bool = True) -> C.CDLL:
         "b200neox_load_sharded": (vp, [C.c_char_p, i, i, i, C.POINTER(vp), sz]),
         "b200neox_sharded_pool_bytes": (sz, [i, i, i]),
         "b200q4_chain_create": (vp, [i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i)]),
+        "b200q4_chain_sharded_ctr_bytes": (sz, [i]),
+        "b200q4_chain_create_sharded": (vp, [i, C.POINTER(vp), C.POINTER(vp), i, i, C.POINTER(vp), sz, C.POINTER(sz)]),
         "b200q4_chain_run": (i, [vp, vp]),
         "b200q4_chain_info": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(sz)]),
         "b200q4_chain_free": (None, [vp]),

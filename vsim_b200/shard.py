@@ -20,6 +20,8 @@ import ctypes as C
 import torch
 import torch.distributed as dist
 
+from .lib import B200Q4Error, _err
+
 
 def shard_rows(n: int, world: int, rank: int) -> tuple[int, int]:
     """(first row, row count) of rank's shard.  N must divide evenly (every listed model does)."""
@@ -167,3 +169,54 @@ class ShardedNeox:
             dist.barrier(self.group)                      # no rank frees its pool while a peer's kernel may still store into it
             self.L.b200neox_free(self.m)
             self.m = None
+
+
+class ShardedChain:
+    """b200q4_chain_create_sharded behind torch symmetric memory: one process per GPU; op i is this rank's row shard of a
+    tensor with world * N_i rows, and one persistent launch per rank runs the whole list -- the reducer warps store every
+    output slice as {value, tag} pairs into EVERY rank's pool over NVLink (the all-gather is part of the mul_mat)."""
+
+    def __init__(self, lib, weights, x_ptrs, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.L = lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        n = self.n = len(weights)
+        off = int(lib.b200q4_chain_sharded_ctr_bytes(n))
+        self.offs, self.rows = [], []
+        for w in weights:
+            self.offs.append(off)
+            self.rows.append(w.n * self.world)
+            off += (2 * 4 * w.n * self.world + 255) & ~255
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.pool = symm.empty(off // 4, dtype=torch.int32, device=dev)
+        self.pool.zero_()
+        self.hdl = symm.rendezvous(self.pool, self.group)
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+        ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        ws = (C.c_void_p * n)(*[w.handle for w in weights])
+        xs = (C.c_void_p * n)(*x_ptrs)
+        yo = (C.c_size_t * n)(*self.offs)
+        self.handle = lib.b200q4_chain_create_sharded(n, ws, xs, self.rank, self.world, ptrs, off, yo)
+        if not self.handle:
+            raise B200Q4Error(f"b200q4_chain_create_sharded failed: {_err(lib)}")
+        torch.cuda.synchronize()
+        dist.barrier(self.group)                          # nobody launches before every rank's list and counters exist
+
+    def run(self, stream=None) -> None:
+        rc = self.L.b200q4_chain_run(self.handle, stream)
+        if rc:
+            raise B200Q4Error(f"b200q4_chain_run failed (rc={rc}): {_err(self.L)}")
+
+    def gathered(self, i: int) -> torch.Tensor:
+        """The full output vector of op i as it stands in THIS rank's pool (values of the {value, tag} pairs)."""
+        v = self.pool.view(torch.float32)[self.offs[i] // 4: self.offs[i] // 4 + 2 * self.rows[i]]
+        return v[0::2]
+
+    def free(self):
+        if getattr(self, "handle", None):
+            torch.cuda.synchronize()
+            dist.barrier(self.group)                      # no rank frees its pool while a peer's kernel may still store into it
+            self.L.b200q4_chain_free(self.handle)
+            self.handle = None
