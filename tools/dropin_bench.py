@@ -101,10 +101,11 @@ def prompt_logits(binary: Path, model: Path, threads: int, timeout: int):
 
 
 def run(binary: Path, model: Path, n_predict: int, threads: int, timeout: int):
+    global GPU_ENV
     cmd = [str(binary), "gptneox", "-m", str(model), "--prompt", "1 2 3 4 5", "--seed", "42", "--threads", str(threads),
            "--n_predict", str(n_predict), "--top_k", "1", "--top_p", "1.0", "--temp", "1.0", "--repeat_penalty", "1.0"]
     t0 = time.perf_counter()
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env={**os.environ, **(GPU_ENV if binary.name == "vsim-b200" else {})})
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env={**os.environ, **(GPU_ENV if binary.name.startswith("vsim-b200") else {})})
     dt = time.perf_counter() - t0
     if r.returncode != 0:
         raise RuntimeError(f"{binary.name} failed: {r.stderr[-800:]}{r.stdout[-800:]}")
@@ -156,7 +157,11 @@ def main() -> int:
             return 0
         lg = prompt_logits(gpu_bin, model, args.gpu_threads, args.timeout)
         lc = prompt_logits(cpu_bin, model, args.threads, args.timeout)
-        for tag, b, pair, th in (("b200_hook", gpu_bin, args.gpu_n, args.gpu_threads), ("cpu_reference", cpu_bin, args.cpu_n, args.threads)):
+        legs = [("b200_hook", gpu_bin, args.gpu_n, args.gpu_threads), ("cpu_reference", cpu_bin, args.cpu_n, args.threads)]
+        dev_bin = REF / "vsim-b200dev"
+        if dev_bin.exists():                               # the same program on the device-resident graph (vsim.cpp + 3-line patch)
+            legs.insert(1, ("b200_device_graph", dev_bin, args.gpu_n, 1))
+        for tag, b, pair, th in legs:
             n0, n1 = (int(v) for v in pair.split(","))
             pa, wa, _ = run(b, model, n0, th, args.timeout)
             pb, wb, toks_b = run(b, model, n1, th, args.timeout)
@@ -176,6 +181,8 @@ def main() -> int:
             "cpu_reference_ms_per_token": c["ms_per_token"], "b200_hook_ms_per_token": g["ms_per_token"],
             "tok_per_s": {"cpu_reference": 1e3 / c["ms_per_token"], "b200_hook": 1e3 / g["ms_per_token"]},
             "speedup": c["ms_per_token"] / g["ms_per_token"],
+            "b200_device_graph_ms_per_token": res.get("b200_device_graph", {}).get("ms_per_token"),
+            "b200_device_graph_first_tokens": res.get("b200_device_graph", {}).get("tokens", [])[:12],
             "wall_s": {"cpu_reference": c["wall_s"], "b200_hook": g["wall_s"], "write_model": t_write},
             "greedy_tokens_identical_on_common_prefix": c["tokens"] == g["tokens"][:len(c["tokens"])],
             "first_tokens": {"cpu_reference": c["tokens"][:12], "b200_hook": g["tokens"][:12]},
