@@ -250,11 +250,8 @@ uint64_t b200q4_launch_count(void);
 void     b200q4_launch_count_reset(void);
 /* Name of the kernel variant b200q4_mul_mat would pick for (type, M, N, K).  */
 const char *b200q4_kernel_for(int type, int M, int N, int K);
-/* Times `iters` back-to-back device-resident mul_mats with CUDA events on the
- * library stream, rotating over `nw` weight handles (L2 defeat); returns the
- * mean milliseconds per call or a negative error code.                      */
-double b200q4_time_mul_mat_dev(b200q4_weight *const *ws, int nw, const float *d_x, int M,
-                               float *d_y, int iters);
+/* (bench / test / development helpers -- kernel timing loops, launch-plan dumps, dispatch overrides, timelines -- are
+ * declared in b200q4_dev.h: exported by the same library, not part of the product ABI.)                              */
 
 #ifdef __cplusplus
 }

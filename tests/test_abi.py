@@ -16,7 +16,7 @@ ROOT = Path(__file__).resolve().parents[1]
 
 def _declared_in_header():
     names = set()
-    for hdr in ("b200q4.h", "b200neox.h"):               # every public header of include/
+    for hdr in ("b200q4.h", "b200neox.h", "b200q4_dev.h"):   # every header of include/ (the last one: bench / test helpers)
         text = (ROOT / "include" / hdr).read_text()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names |= set(re.findall(r"\b(b200(?:q4|neox)_[a-z0-9_]+)\s*\(", text))

@@ -30,7 +30,10 @@ ABI_SYMBOLS = [
     "b200q4_chain_create", "b200q4_chain_run", "b200q4_chain_info", "b200q4_chain_free",
     "b200q4_chain_sharded_ctr_bytes", "b200q4_chain_create_sharded",
     "b200q4_host_alloc", "b200q4_host_free", "b200q4_launch_count", "b200q4_launch_count_reset",
-    "b200q4_kernel_for", "b200q4_time_mul_mat_dev",
+    "b200q4_kernel_for",
+    # include/b200q4_dev.h: bench / test / development helpers, not part of the product ABI
+    "b200q4_time_mul_mat_dev", "b200q4_debug_plan", "b200q4_debug_set_tile_min_m", "b200q4_debug_set_fuse_max_k",
+    "b200q4_debug_set_slice_min_c", "b200q4_debug_timeline", "b200q4_chain_timeline",
 ]
 HOOK_SYMBOLS = ["init_xmax", "imax_ggml_compute_forward_mul_mat_q4_0_f32",
                 "imax_ggml_compute_forward_mul_mat_q4_1_f32", "b200q4_hook_shutdown"]
