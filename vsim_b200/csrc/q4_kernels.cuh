@@ -608,6 +608,7 @@ __device__ __forceinline__ void compute_unit_m8(const Frag<QT> &f, const uint8_t
 // between back-to-back mul_mats.
 constexpr int PIPE_TILE_SPLIT = 16;                     // tiles of >= this many units are scheduled as tile pieces
 constexpr int PIPE_MAX_STAGES = 6;
+constexpr int PIPE_BAR_DONE = 2;                        // named barriers 2 .. 2 + PIPE_MAX_STAGES - 1: consumers -> reducer, one per ring slot
 constexpr int PIPE_STATIC_TASKS = 3;                    // per CTA, before the first ticket is drawn
 
 constexpr int MAX_PEERS = 8;
@@ -1208,13 +1209,13 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             // bar_done implies bar_full (every consumer passed it), so one wait per stage suffices;
             // the stop marker carries no consumer arrivals and is announced on bar_full alone.
             // (pure polling: the one reducer warp should notice a finished stage at once, not after a suspended try_wait)
-            if (!mbar_test(&bar_done[s], ph)) {
-                if (p.flags & 1) mbar_spin(&bar_full[s], ph); else mbar_wait(&bar_full[s], ph);
-                if (s_desc[s].x < 0) break;
-                if (p.flags & 1) mbar_spin(&bar_done[s], ph); else mbar_wait(&bar_done[s], ph);
-            }
+            // Consumers -> reducer: named barrier PIPE_BAR_DONE + s (bar.arrive by the consumer threads, bar.sync here): the
+            // barrier unit takes 16 warps' arrivals in a few cycles where 16 arrivals on one mbarrier cost every warp ~350
+            // cycles of contention per stage (tools/octetbench.cu).  The stop marker has no arrivals: look at the stage first.
+            if (p.flags & 1) mbar_spin(&bar_full[s], ph); else mbar_wait(&bar_full[s], ph);
             const int4 dsc = s_desc[s];
             if (dsc.x < 0) break;
+            asm volatile("bar.sync %0, %1;" :: "r"(PIPE_BAR_DONE + s), "n"(PIPE_CONSUMERS * 32 + 32) : "memory");
             if (lane == 0) PIPE_STAMP(11);               // (timeline builds) the last stage's partials became visible
             const int task = dsc.w;
             int T = dsc.z;
@@ -1466,8 +1467,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
                 put4(slotA, aA);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_done[s]);
+        asm volatile("bar.arrive %0, %1;" :: "r"(PIPE_BAR_DONE + s), "n"(PIPE_CONSUMERS * 32 + 32) : "memory");
         if (++s == p.stages) { s = 0; ph ^= 1; }
     }
     if (threadIdx.x == 0) PIPE_STAMP(6);
