@@ -66,6 +66,56 @@ __global__ void __launch_bounds__(576, 1) k(int iters, long long *out, float *si
     if (lane == 0) out[blockIdx.x * 16 + warp] = t1 - t0;
 }
 
+// the 8-row kernel's consumer work on one stage: two units (4 quant blocks x 16 rows x 8 activation rows each) per warp,
+// partials combined and stored as one float4 per lane
+template <int QT, int V>
+__global__ void __launch_bounds__(576, 1) k8(int iters, long long *out, float *sink)
+{
+    extern __shared__ __align__(128) uint8_t sm[];
+    constexpr int CH = chunk_bytes(QT);
+    uint8_t *stage = sm;                                   // 3 stages x 32 units
+    uint8_t *s_aq = sm + 3 * 32 * CH;                      // 128 blocks x 8 rows x 32 B
+    float *s_ap = reinterpret_cast<float *>(s_aq + 128 * 256);
+    float *red = s_ap + 3 * 128 * 8;
+    const int total = 3 * 32 * CH + 128 * 256 + 3 * 128 * 8 * 4 + 16 * 128 * 4;
+    for (int i = threadIdx.x; i < total / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(sm)[i] = (i * 2654435761u) >> 7 & 0x3f3f3f3fu;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= 16) return;
+    float sink_acc = 0.f;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+        const int s = it % 3;
+        const uint8_t *chA = stage + (size_t)s * 32 * CH + (size_t)(2 * warp) * CH, *chB = chA + CH;
+        Frag<QT> fA, fB;
+        load_frag_smem<QT>(fA, chA, lane);
+        load_frag_smem<QT>(fB, chB, lane);
+        float aA[4] = {0.f, 0.f, 0.f, 0.f}, aB[4] = {0.f, 0.f, 0.f, 0.f};
+        compute_unit_m8<QT>(fA, chA, 2 * warp, s_aq, s_ap, 128 * 8, lane, aA);
+        compute_unit_m8<QT>(fB, chB, 2 * warp + 1, s_aq, s_ap, 128 * 8, lane, aB);
+        aA[0] += aB[0]; aA[1] += aB[1]; aA[2] += aB[2]; aA[3] += aB[3];
+        if (V >= 1) *reinterpret_cast<float4 *>(red + warp * 128 + lane * 4) = make_float4(aA[0], aA[1], aA[2], aA[3]);
+        else sink_acc += aA[0] + aA[1] + aA[2] + aA[3];
+    }
+    const long long t1 = clock64();
+    if (sink_acc == 123.456f) *sink = sink_acc;
+    if (lane == 0) out[blockIdx.x * 16 + warp] = t1 - t0;
+}
+
+template <int QT, int V>
+static void run8(const char *what, long long *d_out, float *d_sink)
+{
+    const int iters = 2048;
+    const size_t smem = 3 * 32 * chunk_bytes(QT) + 128 * 256 + 3 * 128 * 8 * 4 + 16 * 128 * 4;
+    cudaFuncSetAttribute(k8<QT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int rep = 0; rep < 2; rep++) { k8<QT, V><<<148, 576, smem>>>(iters, d_out, d_sink); cudaDeviceSynchronize(); }
+    long long h[16];
+    cudaMemcpy(h, d_out, sizeof h, cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (int i = 0; i < 16; i++) mx = h[i] > mx ? h[i] : mx;
+    printf("q4_%d M=8 %-40s: a 32-unit stage every %7.1f cycles per SM  (%s)\n", QT, what, (double)mx / iters, cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int QT, int V, int OPW>
 static void run(const char *what, long long *d_out, float *d_sink)
 {
@@ -95,5 +145,8 @@ int main()
     run<0, 3, 4>("+ wait for the group", d_out, d_sink);
     run<1, 1, 1>("+ quad shuffles + store", d_out, d_sink);
     run<1, 1, 4>("+ quad shuffles + store", d_out, d_sink);
+    run8<0, 0>("compute_unit_m8 x 2 only", d_out, d_sink);
+    run8<0, 1>("+ store of the combined partial", d_out, d_sink);
+    run8<1, 1>("+ store of the combined partial", d_out, d_sink);
     return 0;
 }

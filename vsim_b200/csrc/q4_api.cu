@@ -119,7 +119,7 @@ int need_init()
 }
 
 // ---- pipelined decode kernel (q4_gemv_pipe_kernel) ---------------------------------------------
-struct PipePlan { int MP, stages, PP, TS, ntasks, ncw, nbp, gnbp; bool b8, m1; size_t smem; };
+struct PipePlan { int MP, stages, PP, TS, ntasks, ncw, nbp, gnbp; bool b8, m1; size_t smem; int rslots; };
 
 constexpr int PIPE_MAX_CLASSES = 62;                   // K-slices per tile the ticket array has room for (K <= 253,952)
 
@@ -187,6 +187,20 @@ PipePlan pipe_plan(const b200q4_weight *w, int M, bool fuse)
         long st = (long)((optin - fixed(pp.MP, pp.m1, pp.b8)) / stage);
         pp.stages = (int)(st > PIPE_MAX_STAGES ? PIPE_MAX_STAGES : st);
         pp.smem = fixed(pp.MP, pp.m1, pp.b8) + (size_t)pp.stages * stage;
+        // 8-row kernel: a reduction ring of its own (2 entries of one 16 x 8 partial per consumer warp, 8 KB each) instead of
+        // 16 KB of partials per weight stage, whenever a warp's two units always belong to one tile (whole tiles of >= 16
+        // units, K-slices, or an even number of units per tile) and a weight stage more fits that way
+        // (measured, 16384 x 4096, M = 8: Q4_1 2 -> 3 stages 21.5 -> 18.8 us; Q4_0 3 -> 4 stages 15.1 -> 16.1 us: with three stages
+        // the ring is deep enough and the extra wait per stage costs more than the fourth stage buys)
+        if (pp.MP == 8 && pp.stages < 3 && (pp.PP > 1 || w->C >= PIPE_TILE_SPLIT || w->C % 2 == 0) && !getenv("B200Q4_NO_RDEC")) {
+            const size_t wstage = (size_t)2 * 16 * chunk_bytes(type), rring = (size_t)2 * 16 * 512;
+            const long st2 = (long)((optin - fixed(8, false, false) - rring) / wstage);
+            const int stages2 = (int)(st2 > PIPE_MAX_STAGES ? PIPE_MAX_STAGES : st2);
+            if (stages2 > pp.stages) {
+                pp.rslots = 2; pp.stages = stages2;
+                pp.smem = fixed(8, false, false) + rring + (size_t)stages2 * wstage;
+            }
+        }
     }
     pp.nbp = nbp_of(pp.m1);
     pp.gnbp = pp.PP > 1 ? pp.PP * pp.TS * CHUNK_BLKS : pp.nbp;     // global pack: every slice fully backed
@@ -237,7 +251,7 @@ int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, con
     p.ticket = g.d_ticket;
     p.x_stride = x_stride_f; p.y_stride = y_stride_f;
     p.U = w->n_tiles * w->C; p.N = w->N; p.M = mc; p.C = w->C; p.n_tiles = w->n_tiles; p.nb = w->nb;
-    p.ntasks = pl.ntasks; p.PP = pl.PP; p.TS = pl.TS; p.stages = pl.stages; p.gnbp = pl.gnbp; p.flags = g.pipe_flags; p.nstatic = g.static_tasks;
+    p.ntasks = pl.ntasks; p.PP = pl.PP; p.TS = pl.TS; p.stages = pl.stages; p.rslots = pl.rslots; p.gnbp = pl.gnbp; p.flags = g.pipe_flags; p.nstatic = g.static_tasks;
     p.dbg = g.d_dbg;
     p.next = NextHint{};
     if (g.hint_w && g.prefetch_stages > 0 && !g.hint_w->transposed && g.hint_w->wt_bytes &&
@@ -261,7 +275,8 @@ int run_pipe(const b200q4_weight *w, int mc, const PipePlan &pl, bool fused, con
                              : launch_pipe<QT, 2, true, false, true, 8>(p, grid, pl.smem, st);                     \
         return launch_pipe<QT, 2, false, false, true, 8>(p, grid, pl.smem, st);                                    \
     }                                                                                                              \
-    if (pl.MP == 8) return launch_pipe<QT, 8, false, false, false, 16>(p, grid, pl.smem, st);                      \
+    if (pl.MP == 8) return pl.rslots > 0 ? launch_pipe<QT, 8, false, false, true, 16>(p, grid, pl.smem, st)        \
+                                         : launch_pipe<QT, 8, false, false, false, 16>(p, grid, pl.smem, st);      \
     if (fused) {                                                                                                   \
         if (pl.b8) return m1 ? launch_pipe<QT, 2, true, true, true, 16>(p, grid, pl.smem, st)                      \
                              : launch_pipe<QT, 2, true, false, true, 16>(p, grid, pl.smem, st);                    \

@@ -746,6 +746,9 @@ struct PipeParams {
     int            nstatic;  // static tasks per CTA (0 = PIPE_STATIC_TASKS)
     int            flags;    // development knob: 1 = the reducer polls its barriers instead of try_wait (measured: no gain)
     int            stages;
+    int            rslots;   // > 0 (8-row kernel): the reduction ring has its own `rslots` entries, apart from the weight ring, of one
+                             // 16 x 8 partial per consumer WARP (its two units belong to one tile): 8 KB per entry instead of 16 KB per
+                             // weight stage -- one more weight stage fits.  0: one entry of 2 slots per warp per weight stage
     unsigned long long *dbg; // optional timeline (B200Q4_TIMELINE builds), else NULL
     // Row-sharded launch with the all-gather fused into the epilogue (world > 1): this rank's output
     // columns are stored straight into every rank's Y over NVLink (peer-mapped pointers), then the last
@@ -1101,7 +1104,10 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
     // shared-memory map: [stages x STAGE_BYTES][red ring][apack codes][planes][barriers][desc]
     uint8_t *s_stage = smem;
     float   *s_red = reinterpret_cast<float *>(smem + (size_t)p.stages * STAGE_BYTES);
-    uint8_t *s_aq = reinterpret_cast<uint8_t *>(s_red + (size_t)p.stages * PIPE_UNITS * RW);
+    constexpr bool rdec = MP != 2 && B8;                   // decoupled, compact reduction ring (PipeParams::rslots > 0; the 8-row
+                                                           // kernel has no use for B8's own meaning, the 8-column code layout)
+    const int  rent = rdec ? PIPE_CONSUMERS : PIPE_UNITS;   // slots per ring entry
+    uint8_t *s_aq = reinterpret_cast<uint8_t *>(s_red + (size_t)(rdec ? p.rslots : p.stages) * rent * RW);
     float   *s_ap = reinterpret_cast<float *>(s_aq + (size_t)nbp * AQ_BLK);
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_ap) + (((size_t)NP * plane * 4 + 15) & ~(size_t)15));
     uint64_t *bar_empty = bar_full + PIPE_MAX_STAGES;
@@ -1115,7 +1121,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
         if (i < p.stages) {
             if (which == 0) mbar_init(&bar_full[i], 1);
             else if (which == 1) mbar_init(&bar_empty[i], 1);   // released by the reducer (which waited for every consumer)
-            else mbar_init(&bar_done[i], PIPE_CONSUMERS);
+            else mbar_init(&bar_done[i], 1);             // (decoupled reduction ring: entry i is free again; arrived by the reducer)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1196,6 +1202,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
         int curT = -1, curTask = -1;
         int s = 0;
         uint32_t ph = 0;
+        unsigned rq = 0;                                 // stages summed so far (decoupled reduction ring: entry rq % rslots)
         constexpr int NV = (MP == 2) ? 1 : 4;
         // sliced launches: a finished piece is parked in its workspace slot with plain stores -- no fence, no
         // atomic; pipe_finalize_kernel (the next launch in the stream) adds the pieces and stores Y
@@ -1220,7 +1227,8 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             const int task = dsc.w;
             int T = dsc.z;
             int left = p.C - dsc.y;                      // units of tile T from the stage's first unit on
-            const float *red = s_red + (size_t)s * PIPE_UNITS * RW + (MP == 2 ? lane : lane * 4);
+            const int re = rdec ? (int)(rq % (unsigned)p.rslots) : s;
+            const float *red = s_red + (size_t)re * rent * RW + (MP == 2 ? lane : lane * 4);
             int j = 0;
             while (j < dsc.x) {
                 if (T != curT || task != curTask) {
@@ -1229,7 +1237,22 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
                     curT = T; curTask = task;
                 }
                 const int run = min(dsc.x - j, left);    // units of this stage that belong to tile T
-                if (run == PIPE_UNITS && MP == 2) {
+                if (MP != 2 && rdec) {
+                    // one slot per warp = unit pair (j and run are even here): pairs of slots, then a single one -- the order the
+                    // unit-wise loop below gives when every other slot is zero
+                    if constexpr (MP != 2) {
+                        int k = j >> 1;
+                        const int ke = (j + run + 1) >> 1;       // (an odd count only ends a whole tile of an odd number of units: its last warp has one unit)
+                        for (; k + 2 <= ke; k += 2) {
+                            const float4 a = *reinterpret_cast<const float4 *>(red + k * RW), c = *reinterpret_cast<const float4 *>(red + (k + 1) * RW);
+                            acc[0] += a.x + c.x; acc[1] += a.y + c.y; acc[2] += a.z + c.z; acc[3] += a.w + c.w;
+                        }
+                        for (; k < ke; k++) {
+                            const float4 v = *reinterpret_cast<const float4 *>(red + k * RW);
+                            acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+                        }
+                    }
+                } else if (run == PIPE_UNITS && MP == 2) {
                     // common case, the whole stage is one tile: eight independent chains of four
                     // (fixed association -> bit-reproducible, short dependent latency)
                     float v[PIPE_UNITS];
@@ -1267,6 +1290,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
             __syncwarp();
             if (lane == 0) PIPE_STAMP(12);               // (timeline builds) the last stage is summed
             if (lane == 0) mbar_arrive(&bar_empty[s]);
+            if (rdec) { if (lane == 0) mbar_arrive(&bar_done[re]); ++rq; }
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (lane == 0) PIPE_STAMP(13);                   // (timeline builds) stop marker seen
@@ -1409,6 +1433,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
 
     int s = 0;
     uint32_t ph = 0;
+    unsigned cq = 0;                                     // stages consumed so far (decoupled reduction ring)
     bool first = true;
     for (;;) {
         mbar_wait(&bar_full[s], ph);
@@ -1421,6 +1446,13 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
         const int cA = chunk_of(dsc, uA, TA), cB = chunk_of(dsc, uB, TB);
         const uint8_t *chA = s_stage + (size_t)s * STAGE_BYTES + (size_t)uA * CH, *chB = chA + CH;
         float *slotA = s_red + ((size_t)s * PIPE_UNITS + uA) * RW, *slotB = slotA + RW;
+        if (rdec) {                                      // this warp's one slot of entry cq % rslots, once the reducer has read its previous content
+            const unsigned re = cq % (unsigned)p.rslots, use = cq / (unsigned)p.rslots;
+            if (dsc.x >= 0) mbar_wait(&bar_done[re], (use & 1u) ^ 1u);
+            slotA = s_red + ((size_t)re * PIPE_CONSUMERS + warp) * RW;
+            slotB = slotA;
+            ++cq;
+        }
         if constexpr (M1) {
             if (hA && hB && TA == TB && !(cA & 1)) {     // an aligned octet: the common case
                 float v0, v2;
@@ -1457,7 +1489,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
                 if (TA == TB) {                          // same tile: one partial for both units
                     aA[0] += aB[0]; aA[1] += aB[1]; aA[2] += aB[2]; aA[3] += aB[3];
                     put4(slotA, aA);
-                    put_zero(slotB);
+                    if (!rdec) put_zero(slotB);
                 } else {
                     put4(slotA, aA);
                     put4(slotB, aB);
