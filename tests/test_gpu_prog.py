@@ -101,6 +101,42 @@ def test_chain_independent_ops_and_repeated_weights():
         w.free()
 
 
+@pytest.mark.parametrize("qt", [Q4_0, Q4_1])
+def test_chain_independent_steps_with_their_own_inputs(qt):
+    """bench.py's headline shape of list: independent ops, every one with its OWN plain input vector -- the activation packs
+    are prepared ahead of time, between two stages of the previous op (no pause; no barrier where every stage covers the
+    same 128 quant blocks: K = 4096 and K-slices of 4096).  Mixed with geometries that do need the barrier (K = 2048,
+    ragged K = 992), a K-sliced op, a dependent op in the middle, ops sharing an input, and tiny ops that have no stage
+    at all on most thread blocks.  Every output equals the per-call kernel's bit for bit, on every repetition."""
+    torch, vs, L = _setup()
+    orc = Oracle()
+    rng = np.random.default_rng(31 + qt)
+    shapes = [(4096, 4096), (4096, 4096), (1024, 2048), (4096, 4096), (96, 992), (2048, 16384), (4096, 4096), (32, 64), (16384, 4096),
+              (1024, 2048), (1024, 2048)]
+    ws = [_rand_weight(vs, orc, rng, qt, n, k)[1] for n, k in shapes]
+    xs = [torch.from_numpy(rng.standard_normal(k).astype(np.float32)).cuda() for _, k in shapes]
+    xs[10] = xs[9]                                       # the last two share an input (one pack)
+    ys = [torch.zeros(n, device="cuda", dtype=torch.float32) for n, _ in shapes]
+    xptr = [x.data_ptr() for x in xs]
+    xptr[3] = ys[1].data_ptr()                           # op 3 reads op 1's output: a true dependency between the independent ones
+    deps = [-1] * len(shapes)
+    ref = []
+    for i, ((n, k), w) in enumerate(zip(shapes, ws)):
+        xin = ref[1] if i == 3 else xs[i]
+        ref.append(_per_op(L, torch, w, xin, n))
+    chain = vs.Chain(ws, xptr, [y.data_ptr() for y in ys], deps)
+    for rep in range(3):
+        for y in ys:
+            y.zero_()
+        chain.run()
+        L.b200q4_sync(None)
+        for i, y in enumerate(ys):
+            assert torch.equal(y.view(torch.int32), ref[i].view(torch.int32)), (rep, i, shapes[i], (y - ref[i]).abs().max().item())
+    chain.free()
+    for w in ws:
+        w.free()
+
+
 def test_chain_rejects_bad_arguments():
     torch, vs, L = _setup()
     orc = Oracle()
