@@ -841,6 +841,21 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
 }
 
+// The same with an L2 eviction-priority hint: a weight tensor is read once per token and is far larger than what else a
+// decode step touches (activations, layer-norm weights, biases, the gelu / exp tables, the KV rows) -- streamed
+// evict-first it does not push those out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *b, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)), "l"(policy) : "memory");
+}
+
 // First unit u0, unit count n, tile T and chunk index c0 of the first unit of task t.
 // No integer division on the common path (the producer is one thread; a division costs ~150
 // cycles of pure latency there).
@@ -1134,6 +1149,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
         if (lane == 0) {
             int s = 0;                                   // stage index
             uint32_t ph = 1;                             // parity to wait for on bar_empty (first lap: passes at once)
+            const uint64_t wpol = l2_policy_evict_first();   // the weight stream must not push the activations and tables out of L2
             auto issue = [&](int u0, int n, int T, int c0, int task) {
                 for (int r = 0; r < n; r += PIPE_UNITS) {
                     mbar_wait(&bar_empty[s], ph);
@@ -1142,7 +1158,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, NCW == 8 ? 2 : 1) q4_gemv_pipe
                     c0 += cnt;
                     while (c0 >= p.C) { c0 -= p.C; ++T; }
                     mbar_arrive_expect_tx(&bar_full[s], (uint32_t)cnt * CH);
-                    bulk_g2s(s_stage + (size_t)s * STAGE_BYTES, p.wt + (size_t)(u0 + r) * CH, (uint32_t)cnt * CH, &bar_full[s]);
+                    bulk_g2s_hint(s_stage + (size_t)s * STAGE_BYTES, p.wt + (size_t)(u0 + r) * CH, (uint32_t)cnt * CH, &bar_full[s], wpol);
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             };

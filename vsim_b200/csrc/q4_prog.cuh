@@ -151,6 +151,7 @@ struct PgParams {
     int *dyn;                // [0] token id (through PgSrc::row), [1] n_past, [2] launch epoch (the last CTA to leave advances it)
     int *err;                // set (op index + 1) before the kernel traps on a wait that can never end
     int  stages, e_cap, nbp_cap, att_cap;    // shared-memory sizing: residual floats, apack quant blocks, attention floats
+    int  wt_evict_first;     // != 0: the weight stream carries an L2 evict-first hint (what else a token touches stays in L2)
     int  world, rank;        // row-sharded over `world` GPUs (1: single GPU)
     int *ctr_peer[8];        // world > 1: every rank's counter array (hint counters are added to on all ranks)
     unsigned long long *dbg; // optional timeline [grid][n_ops][8] of %globaltimer stamps (B200Q4_DBG=1), else NULL
@@ -1054,6 +1055,7 @@ __device__ __noinline__ void pg_producer(const PgParams *pp)
     const int bid = (int)blockIdx.x, grid = (int)gridDim.x;
     int s = 0;
     uint32_t ph = 1;
+    const uint64_t wpol = l2_policy_evict_first();
     auto put = [&](int cnt, int c0, int T, int task, int otag, const uint8_t *src) {
         const long long tw = PG_CLK();
         pg_mbar_wait(&sm.bar_empty[s], ph);
@@ -1065,7 +1067,8 @@ __device__ __noinline__ void pg_producer(const PgParams *pp)
 #endif
         if (cnt > 0) {
             mbar_arrive_expect_tx(&sm.bar_full[s], (uint32_t)cnt * CH);
-            bulk_g2s(sm.stage + (size_t)s * STAGE_BYTES, src, (uint32_t)cnt * CH, &sm.bar_full[s]);
+            if (p.wt_evict_first) bulk_g2s_hint(sm.stage + (size_t)s * STAGE_BYTES, src, (uint32_t)cnt * CH, &sm.bar_full[s], wpol);
+            else bulk_g2s(sm.stage + (size_t)s * STAGE_BYTES, src, (uint32_t)cnt * CH, &sm.bar_full[s]);
         } else {
             mbar_arrive(&sm.bar_full[s]);
         }

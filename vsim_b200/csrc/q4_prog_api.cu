@@ -275,6 +275,7 @@ int prog_launch(const Prog &pg, cudaStream_t st)
     PgParams p;
     p.ops = pg.d_ops; p.n_ops = pg.n_ops; p.first_mv = pg.first_mv; p.dbg = pg.d_dbg; p.ctr = pg.d_ctr; p.n_ctr = pg.n_ctr; p.dyn = pg.d_dyn; p.err = pg.d_err;
     p.stages = pg.stages; p.e_cap = pg.e_cap; p.nbp_cap = pg.nbp_cap; p.att_cap = pg.att_cap;
+    { const char *e = getenv("B200Q4_PROG_EVICT_FIRST"); p.wt_evict_first = e ? atoi(e) : 1; }
     p.world = pg.world; p.rank = pg.rank;
     for (int r = 0; r < 8; r++) p.ctr_peer[r] = pg.ctr_peer[r];
     cudaLaunchConfig_t cfg = {};
