@@ -18,7 +18,7 @@ LIB = PKG / "libb200q4.so"
 SOURCES = [CSRC / "q4_api.cu", CSRC / "q4_prog_api.cu", CSRC / "neox_graph.cu", CSRC / "imax_b200.c"]
 DEPS = SOURCES + [CSRC / "q4_kernels.cuh", CSRC / "q4_tile.cuh", CSRC / "q4_prog.cuh", CSRC / "q4_prog_host.h", CSRC / "q4_internal.h", PKG.parent / "include" / "b200q4.h",
                   PKG.parent / "include" / "b200q4_ggml_abi.h", PKG.parent / "include" / "b200neox.h"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-t", "0",
               "-cudart", "shared",            # the runtime stays a shared library: no copy of its symbol table inside the artefact
               "-Xcompiler", "-fPIC", "-shared"]
 

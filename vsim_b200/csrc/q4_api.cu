@@ -331,7 +331,7 @@ int launch_tile(const TileParams &p, int grid, size_t smem, cudaStream_t st)
         attr_gen = g.init_gen;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TK_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tk_threads(QT, MT)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -358,9 +358,23 @@ int run_tile(const b200q4_weight *w, const float *d_x, size_t x_stride_f, const 
     }
     const long warps = (long)tp.m_tiles * w->C * CHUNK_BLKS * tp.MT;
     const int blocks = (int)((warps * 32 + 255) / 256);
+    static const int dev_skip = getenv("B200Q4_TILE_SKIP") ? atoi(getenv("B200Q4_TILE_SKIP")) : 0;    // development: 1 = no pack kernel, 2 = no tile kernel
+    // A pack grid that is resident at once is a programmatic dependent launch too: it is set up while the kernel before it
+    // drains and waits for that kernel's results (X; the previous call's tile kernel reading d_tpack) at its first
+    // instruction.  (Larger grids: the tile kernel launches when every pack CTA has started, i.e. at the end anyway.)
+    const bool pack_pdl = g.use_pdl && blocks <= 8 * 148;
+    cudaLaunchConfig_t pcfg = {};
+    pcfg.gridDim = dim3(blocks); pcfg.blockDim = dim3(256); pcfg.dynamicSmemBytes = 0; pcfg.stream = st;
+    cudaLaunchAttribute pat[1];
+    pat[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pat[0].val.programmaticStreamSerializationAllowed = 1;
+    pcfg.attrs = pat; pcfg.numAttrs = 1;
 #define TILE_PACK(QT)                                                                                                  \
-    if (d_wdata) tile_pack_kernel<QT, true><<<blocks, 256, 0, st>>>(nullptr, 0, d_wdata, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack); \
-    else         tile_pack_kernel<QT, false><<<blocks, 256, 0, st>>>(d_x, x_stride_f, nullptr, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack);
+    if (dev_skip == 1) { }                                                                                             \
+    else if (pack_pdl && d_wdata) CK(cudaLaunchKernelEx(&pcfg, tile_pack_kernel<QT, true, true>, (const float *)nullptr, (size_t)0, d_wdata, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack)); \
+    else if (pack_pdl)            CK(cudaLaunchKernelEx(&pcfg, tile_pack_kernel<QT, false, true>, d_x, x_stride_f, (const uint8_t *)nullptr, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack)); \
+    else if (d_wdata) tile_pack_kernel<QT, true, false><<<blocks, 256, 0, st>>>(nullptr, 0, d_wdata, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack); \
+    else              tile_pack_kernel<QT, false, false><<<blocks, 256, 0, st>>>(d_x, x_stride_f, nullptr, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack);
     if (w->type == 0) { TILE_PACK(0) } else { TILE_PACK(1) }
 #undef TILE_PACK
     g.launches++;
@@ -370,6 +384,7 @@ int run_tile(const b200q4_weight *w, const float *d_x, size_t x_stride_f, const 
     p.y_stride = y_stride_f; p.N = w->N; p.M = M; p.C = w->C; p.n_t16 = w->n_tiles; p.m_tiles = tp.m_tiles;
     p.ntiles = tp.ntiles; p.nraw = tp.nraw; p.nact = tp.nact; p.nconv = tp.nconv;
     p.dbg = g.d_dbg;
+    if (dev_skip == 2) return B200Q4_OK;
 #define TILE_DISPATCH(QT)                                                              \
     switch (tp.MT) {                                                                   \
     case 16:  return launch_tile<QT, 16>(p, tp.grid, tp.smem, st);                     \

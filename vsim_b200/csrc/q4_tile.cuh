@@ -35,16 +35,17 @@
 // The kernel is bounded by TMEM read bandwidth (8 B per value; ~400 B/cycle/SM measured with
 // tools/tmembench.cu) for large M, by the weight stream (HBM) for small M.
 //
-// Warp roles (512 threads, one CTA per SM, persistent; register budgets moved with setmaxnreg):
+// Warp roles (640 threads where TMEM holds four buffers, else 512 with the two issuers in warps 1 and 2; one CTA per SM,
+// persistent; register budgets moved with setmaxnreg):
 //   warp 0      producer: cp.async.bulk (TMA 1-D) of weight chunks, 8 x 1280/1536 B per 128 rows x 4
 //               blocks straight from the decode kernel's "wtile" layout (one weight copy in HBM serves
 //               both kernels); full/empty mbarriers.
 //   warp 3      producer of the activation stages (codes + bf16 scale pieces, already in operand layout).
-//   warp 1      MMA issuer (one elected thread), tcgen05.commit to the epilogue and back to the rings.
 //   warp 2      TMEM allocator (512 columns).
 //   warps 4-7   converters: nibble words -> bytes in the UMMA canonical layout (K-major, no swizzle: core
 //               matrix = 8 rows x 16 B), bf16 pieces of d0 (and d0*S0, m0).
 //   warps 8-15  epilogue: tcgen05.ld x16 double-buffered, FFMA2, final store / stream-K combine.
+//   warps 16-19 MMA issuers (one elected thread each, one TMEM buffer each), tcgen05.commit to the epilogue and back to the rings.
 #pragma once
 #include "q4_kernels.cuh"
 
@@ -54,10 +55,15 @@ constexpr int TK_ROWS = 128;                 // weight rows per tile (MMA M)
 constexpr int TK_T16 = TK_ROWS / TILE_ROWS;  // wtile tiles per tile
 constexpr int TK_CONV_WARPS = 4;
 constexpr int TK_EPI_WARPS = 8;
-constexpr int TK_THREADS = (4 + TK_CONV_WARPS + TK_EPI_WARPS) * 32;
+constexpr int TK_ISSUERS = 4;                // MMA issuer warps where TMEM holds four buffers: a warp group of their own behind the epilogue warps
+constexpr int TK_THREADS_BASE = (4 + TK_CONV_WARPS + TK_EPI_WARPS) * 32;    // two buffers: the two issuers are warps 1 and 2
+constexpr int TK_THREADS_MAX = TK_THREADS_BASE + TK_ISSUERS * 32;
 constexpr int TK_MAX_RAW = 16, TK_MAX_ACT = 8, TK_MAX_CONV = 8, TK_MAX_TM = 4;
-// register budgets after setmaxnreg (launch: 512 threads x 128): 128*(40 + 72 + 2*200) = 65536
-constexpr int TK_REGS_MISC = 40, TK_REGS_CONV = 72, TK_REGS_EPI = 200;
+// register budgets after setmaxnreg: 640 threads (launched with 96): 128*(2*32 + 72 + 2*168) = 60416 <= 61440;
+// 512 threads (launched with 128): 128*(40 + 72 + 2*200) = 65536
+__host__ __device__ constexpr int tk_regs_misc(int nthr) { return nthr > TK_THREADS_BASE ? 32 : 40; }
+__host__ __device__ constexpr int tk_regs_epi(int nthr) { return nthr > TK_THREADS_BASE ? 168 : 200; }
+constexpr int TK_REGS_CONV = 72;
 constexpr int TK_OP_TILE = TK_ROWS * 32;     // one 128-row operand tile of one block (fp8 K=32 or bf16 K=16)
 
 __host__ __device__ constexpr int tk_nop(int qt) { return qt == 0 ? 2 : 3; }          // operand tiles per block and side
@@ -71,9 +77,30 @@ __host__ __device__ inline size_t tk_smem_bytes(int qt, int mt, int nraw, int na
     return (size_t)TK_OP_TILE + (size_t)nraw * tk_raw_stage(qt) + (size_t)nact * tk_act_stage(qt, mt) +
            (size_t)nconv * tk_conv_slot(qt) + tk_bar_bytes();
 }
-// blocks per TMEM buffer; two buffers of G x [V | T (| R)] x MT columns: Q4_0 2 x 256 (2 x 128 at MT = 16), Q4_1 2 x 192
-__host__ __device__ constexpr int tk_g(int qt, int mt) { return qt == 0 ? (128 / mt < CHUNK_BLKS ? 128 / mt : CHUNK_BLKS) : (64 / mt < CHUNK_BLKS ? 64 / mt : CHUNK_BLKS); }
-__host__ __device__ constexpr int tk_nbuf(int qt) { return 2; }
+// blocks per TMEM buffer; NBUF buffers of G x [V | T (| R)] x MT columns
+// TMEM map.  One block's tiles [V | T (| R)] take NT x MT columns; where a quarter of TMEM cannot hold that (Q4_0 at
+// MT = 128, Q4_1 at MT = 64) the tile is issued as two half-width MMAs (SPLIT) into buffers of their own, so that there
+// are always FOUR buffers in flight: the issuer -> epilogue -> issuer round trip (commit, mbarrier, tcgen05.ld, arrive,
+// and an issuing thread's mbarrier waits do not return before its own MMAs have finished: tools/mmabench.cu) paces
+// the kernel, and what hides it is the number of hand-offs in flight, not their size.
+#ifdef TK_SPLIT
+__host__ __device__ constexpr bool tk_split(int qt, int mt) { return tk_nop(qt) * mt > 128; }
+#else
+__host__ __device__ constexpr bool tk_split(int qt, int mt) { return false; }           // measured: no gain (profiles/r02_tile_kernel_experiments.txt)
+#endif
+__host__ __device__ constexpr int tk_sw(int qt, int mt) { return tk_split(qt, mt) ? mt / 2 : mt; }      // MMA N
+__host__ __device__ constexpr int tk_g(int qt, int mt)                                                   // blocks per buffer
+{
+    const int g = 128 / (tk_nop(qt) * tk_sw(qt, mt));
+    return g < 1 ? 1 : g > CHUNK_BLKS ? CHUNK_BLKS : g;
+}
+__host__ __device__ constexpr int tk_nbuf(int qt, int mt)
+{
+    const int n = 512 / (tk_g(qt, mt) * tk_nop(qt) * tk_sw(qt, mt));
+    return n > TK_MAX_TM ? TK_MAX_TM : n;
+}
+
+__host__ __device__ constexpr int tk_threads(int qt, int mt) { return tk_nbuf(qt, mt) == 4 ? TK_THREADS_MAX : TK_THREADS_BASE; }
 
 struct TileParams {
     const uint8_t *wt;       // wtile
@@ -97,6 +124,13 @@ struct TileParams {
 #define TK_WAIT(bar, ph, slot) mbar_wait((bar), (ph))
 #define TK_PROF_DECL do { } while (0)
 #define TK_PROF_FLUSH(total_slot, cond) do { } while (0)
+#endif
+
+// second profiling aid (-DTK_TRACE, tools/tile_trace.py): CTA 0 stamps the first 32 chunk steps of every role
+#ifdef TK_TRACE
+#define TK_STAMP(ev, step, cond) do { if (p.dbg && blockIdx.x == 0 && (step) < 32 && (cond)) p.dbg[(ev) * 32 + (step)] = (unsigned long long)clock64(); } while (0)
+#else
+#define TK_STAMP(ev, step, cond) do { } while (0)
 #endif
 
 // ---- e4m3 encoding of v * 2^s for an integer |v| <= 15 (exact) ----------------------------------
@@ -169,11 +203,13 @@ __device__ __forceinline__ int tk_operand_off(int r, int p) { return (r >> 3) * 
 // Stage (m tile, chunk) = [4 blocks x codes tile][4 blocks x scale-piece tile]([4 blocks x rank-2 tile]),
 // every tile MT rows x 32 B in operand layout.  One warp per (stage row m_local, block), padding included.
 // SRC_WDATA: rows already quantized by the reference's INIT phase (params->wdata image).
-template <int QT, bool SRC_WDATA>
+// DEP: launched with the programmatic-dependent-launch attribute (small grids, see run_tile).
+template <int QT, bool SRC_WDATA, bool DEP>
 __global__ void tile_pack_kernel(const float *__restrict__ x, size_t x_stride, const uint8_t *__restrict__ wdata,
                                  int M, int MT, int nb, int C, int m_tiles, uint8_t *__restrict__ tpack)
 {
     cudaTriggerProgrammaticLaunchCompletion();           // the tile kernel may start its weight stream now
+    if (DEP) cudaGridDependencySynchronize();            // launched as a programmatic dependent: X is ready, the previous call's tile kernel is through with tpack
     const int lane = threadIdx.x & 31;
     const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long total = (long)m_tiles * C * CHUNK_BLKS * MT;
@@ -367,26 +403,43 @@ __device__ __forceinline__ int tk_owner(const TileParams &p, int x, int G)
 
 // ---------------------------------------------------------------------------------------------------
 // MT: activation rows per tile (MMA N): 16, 32, 64 (and 128 for Q4_0).
-// TMEM: NBUF buffers of G blocks x [V: MT columns | T: MT columns (| R: MT columns, Q4_1)].
+// TMEM: NBUF buffers of G blocks x [V: SW columns | T: SW columns (| R: SW columns, Q4_1)], SW = MT or MT / 2 (SPLIT).
 // ---------------------------------------------------------------------------------------------------
 template <int QT, int MT>
-__global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams p)
+__global__ void __launch_bounds__(tk_threads(QT, MT), 1) q4_tile_kernel(const TileParams p)
 {
+    // (no early cudaTriggerProgrammaticLaunchCompletion here: measured slower at every M -- the next launch's CTAs only
+    // compete with this launch's tail for the SMs' shared memory)
+    constexpr int TK_THREADS = tk_threads(QT, MT);
+    constexpr int TK_REGS_MISC = tk_regs_misc(TK_THREADS), TK_REGS_EPI = tk_regs_epi(TK_THREADS);
     static_assert(MT <= tk_max_mt(QT), "tile too wide for the TMEM map");
     constexpr int CH = chunk_bytes(QT);
     constexpr int RAW_STAGE = tk_raw_stage(QT), ACT_STAGE = tk_act_stage(QT, MT), CONV_SLOT = tk_conv_slot(QT);
     constexpr int B_TILE = MT * 32;                                           // one block's activation-side operand tile
     constexpr int A_PLANE = CHUNK_BLKS * TK_OP_TILE, B_PLANE = CHUNK_BLKS * B_TILE;
+    constexpr bool SPLIT = tk_split(QT, MT);                                  // two half-width MMAs per block and operand
+    constexpr int SW = tk_sw(QT, MT);                                         // MMA N = columns of one TMEM tile
     constexpr int G = tk_g(QT, MT);                                           // blocks per TMEM buffer
-    constexpr int STEPS = CHUNK_BLKS / G;                                     // TMEM buffers per chunk
-    constexpr int NBUF = tk_nbuf(QT);
+    constexpr int STEPS = SPLIT ? 2 * CHUNK_BLKS : CHUNK_BLKS / G;            // TMEM hand-offs per chunk
+    constexpr int NBUF = tk_nbuf(QT, MT);
     constexpr int NT = tk_nop(QT);                                            // TMEM tiles per block: V, T (, R)
-    constexpr int BUFC = G * NT * MT;                                         // columns per TMEM buffer
-    static_assert(NBUF * BUFC <= 512, "TMEM map");
+    constexpr int BUFC = G * NT * SW;                                         // columns per TMEM buffer
+    static_assert(NBUF * BUFC <= 512 && (NBUF == 2 || NBUF == 4) && (!SPLIT || G == 1), "TMEM map: one issuer per buffer");
+    constexpr int W = NBUF;                                                   // issuers at work
+    // hand-off k of this CTA's chunk number cc is hand-off cc * STEPS + k of the CTA: its TMEM buffer and the parity of that
+    // buffer's use (compile-time functions of k wherever STEPS allows)
+    auto tm_buf = [](int cc, int k) -> int {
+        if constexpr (STEPS % NBUF == 0) return k % NBUF; else return (cc * STEPS + k) % NBUF;
+    };
+    auto tm_par = [](int cc, int k) -> uint32_t {
+        if constexpr (STEPS % (2 * NBUF) == 0) return (uint32_t)(k / NBUF) & 1u;
+        else if constexpr (STEPS % NBUF == 0) return (uint32_t)(cc * (STEPS / NBUF) + k / NBUF) & 1u;
+        else return (uint32_t)((cc * STEPS + k) / NBUF) & 1u;
+    };
     constexpr int HC = MT / 2;                                                // columns per epilogue thread
     constexpr int LW = HC >= 16 ? 16 : HC;                                    // columns per tcgen05.ld
     constexpr int NSB = HC / LW;                                              // loads per block and operand
-    constexpr uint32_t IDESC8 = umma_idesc_f8(MT), IDESC16 = umma_idesc_bf16(MT);
+    constexpr uint32_t IDESC8 = umma_idesc_f8(SW), IDESC16 = umma_idesc_bf16(SW);
 
     // (plain pointer arithmetic on the shared array only: an integer round trip would make every
     // access below a generic LD/ST instead of LDS/STS; the no-swizzle operand layout needs 16 B alignment)
@@ -408,9 +461,9 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
     const int G_ = (int)gridDim.x;
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nraw; i++) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], TK_CONV_WARPS); }
-        for (int i = 0; i < p.nact; i++) { mbar_init(&act_full[i], 1); mbar_init(&act_empty[i], 1); }
-        for (int i = 0; i < p.nconv; i++) { mbar_init(&conv_full[i], TK_CONV_WARPS); mbar_init(&conv_empty[i], 1); }
-        for (int i = 0; i < NBUF; i++) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], TK_EPI_WARPS); }
+        for (int i = 0; i < p.nact; i++) { mbar_init(&act_full[i], 1); mbar_init(&act_empty[i], W); }
+        for (int i = 0; i < p.nconv; i++) { mbar_init(&conv_full[i], TK_CONV_WARPS); mbar_init(&conv_empty[i], W); }
+        for (int i = 0; i < NBUF; i++) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], SPLIT ? TK_EPI_WARPS / 2 : TK_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -431,6 +484,64 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
     const uint32_t tmem = *s_tmem;
     const TkRange rg = tk_range(p, (int)blockIdx.x, G_);
 
+    auto issuer = [&](const int w) {
+            // ===================== MMA issuers =====================
+            // W = NBUF of them (one elected thread each); TMEM hand-off n = 0, 1, 2 ... of this CTA goes to buffer n % NBUF
+            // and to issuer n % W, so every buffer has one issuer.  Why several: after tcgen05.mma / tcgen05.commit a
+            // thread's next mbarrier wait takes 100-250 cycles even on a barrier that completed long ago, and does not return
+            // before the thread's own MMAs have (tools/mmabench.cu, profiles/r02_mmabench.txt) -- one issuer alone leaves the
+            // tensor pipe idle for most of every hand-off.  Every issuer waits for the operand slots of EVERY chunk and arrives
+            // on their empty barriers (count W), also for chunks it issues nothing from: skipping chunks would let a
+            // parity wait run two phases ahead of its barrier.
+            TK_PROF_DECL;
+            RingPos ar(p.nact), cr(p.nconv);
+            const uint32_t a8 = smem_u32(s_a8);
+            for (int x = rg.lo; x < rg.hi && w < W; x++) {
+                {
+                    TK_WAIT(&conv_full[cr.idx], cr.ph, 5);
+                    TK_STAMP(10, x - rg.lo, w == 0);
+                    TK_WAIT(&act_full[ar.idx], ar.ph, 6);
+                    TK_STAMP(4, x - rg.lo, w == 0);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(s_conv + (size_t)cr.idx * CONV_SLOT);
+                    const uint32_t b_base = smem_u32(s_act + (size_t)ar.idx * ACT_STAGE);
+                    const int cc = x - rg.lo;
+#pragma unroll
+                    for (int st = 0; st < STEPS; st++) {
+                        const int tb = tm_buf(cc, st);                                        // W == NBUF: the buffer's issuer has its number
+                        if (tb != w) continue;
+                        const uint32_t tph = tm_par(cc, st);
+                        TK_WAIT(&tm_empty[tb], tph ^ 1u, 7);
+                        tc_fence_after();
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+#ifdef TK_EXP_NOMMA
+                            continue;
+#endif
+                            const int bi = SPLIT ? st >> 1 : st * G + g;                      // block of the chunk
+                            const int bo = SPLIT ? (st & 1) * SW * 32 : 0;                    // activation rows [SW, 2 SW) of the tile
+                            const uint32_t dv = tmem + (uint32_t)(tb * BUFC + g * NT * SW);
+                            const uint64_t bd = umma_desc(b_base + bi * B_TILE + bo);
+                            umma_f8(dv, umma_desc(a_base + bi * TK_OP_TILE), bd, IDESC8, 0u);
+#ifndef TK_EXP_NOA8
+                            umma_f8(dv, umma_desc(a8), bd, IDESC8, 1u);
+#endif
+                            umma_bf16(dv + SW, umma_desc(a_base + A_PLANE + bi * TK_OP_TILE), umma_desc(b_base + B_PLANE + bi * B_TILE + bo), IDESC16, 0u);
+                            if constexpr (QT == 1)
+                                umma_bf16(dv + 2 * SW, umma_desc(a_base + 2 * A_PLANE + bi * TK_OP_TILE),
+                                          umma_desc(b_base + 2 * B_PLANE + bi * B_TILE + bo), IDESC16, 0u);
+                        }
+                        umma_commit(&tm_full[tb]);
+                    }
+                    umma_commit(&conv_empty[cr.idx]);
+                    umma_commit(&act_empty[ar.idx]);
+                    TK_STAMP(5, x - rg.lo, w == 0);
+                    cr.next(); ar.next();
+                }
+            }
+            TK_PROF_FLUSH(4, w == 0);
+    };
+
     if (warp < 4) {
         reg_dec<TK_REGS_MISC>();
         if (warp == 0 && elect_one()) {
@@ -448,6 +559,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
                 const uint8_t *src = p.wt + ((size_t)(nt * TK_T16) * p.C + c0) * CH;
                 for (int c = 0; c < nc; c++, src += CH) {
                     TK_WAIT(&raw_empty[rr.idx], rr.ph ^ 1u, 1);
+                    TK_STAMP(0, x + c - rg.lo, true);
                     const uint32_t bar = smem_u32(&raw_full[rr.idx]);
                     const uint32_t dst = raw0 + (uint32_t)rr.idx * RAW_STAGE;
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)ntl * CH) : "memory");
@@ -469,7 +581,9 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
         } else if (warp == 3 && elect_one()) {
             // ===================== producer: activation stages =====================
             TK_PROF_DECL;
+            TK_STAMP(8, 0, true);
             cudaGridDependencySynchronize();             // the pack kernel's output
+            TK_STAMP(8, 1, true);
             RingPos ar(p.nact);
             const uint32_t act0 = smem_u32(s_act);
             int x = rg.lo;
@@ -480,7 +594,11 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
                 const uint8_t *src = p.tpack + ((size_t)mt * p.C + c0) * ACT_STAGE;
                 for (int c = 0; c < nc; c++, src += ACT_STAGE) {
                     TK_WAIT(&act_empty[ar.idx], ar.ph ^ 1u, 3);
+                    TK_STAMP(9, x + c - rg.lo, true);
                     const uint32_t bar = smem_u32(&act_full[ar.idx]);
+#ifdef TK_EXP_NOACT
+                    if (p.N > 0) { mbar_arrive(&act_full[ar.idx]); ar.next(); continue; }
+#endif
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)ACT_STAGE) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                  :: "r"(act0 + (uint32_t)ar.idx * ACT_STAGE), "l"(src), "r"((uint32_t)ACT_STAGE), "r"(bar) : "memory");
@@ -489,43 +607,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
                 x += nc;
             }
             TK_PROF_FLUSH(2, true);
-        } else if (warp == 1 && elect_one()) {
-            // ===================== MMA issuer =====================
-            TK_PROF_DECL;
-            RingPos ar(p.nact), cr(p.nconv), tr(NBUF);
-            const uint32_t a8 = smem_u32(s_a8);
-            for (int x = rg.lo; x < rg.hi; x++) {
-                {
-                    TK_WAIT(&conv_full[cr.idx], cr.ph, 5);
-                    TK_WAIT(&act_full[ar.idx], ar.ph, 6);
-                    tc_fence_after();
-                    const uint32_t a_base = smem_u32(s_conv + (size_t)cr.idx * CONV_SLOT);
-                    const uint32_t b_base = smem_u32(s_act + (size_t)ar.idx * ACT_STAGE);
-#pragma unroll
-                    for (int st = 0; st < STEPS; st++) {
-                        TK_WAIT(&tm_empty[tr.idx], tr.ph ^ 1u, 7);
-                        tc_fence_after();
-#pragma unroll
-                        for (int g = 0; g < G; g++) {
-                            const int bi = st * G + g;
-                            const uint32_t dv = tmem + (uint32_t)(tr.idx * BUFC + g * NT * MT);
-                            const uint64_t bd = umma_desc(b_base + bi * B_TILE);
-                            umma_f8(dv, umma_desc(a_base + bi * TK_OP_TILE), bd, IDESC8, 0u);
-                            umma_f8(dv, umma_desc(a8), bd, IDESC8, 1u);
-                            umma_bf16(dv + MT, umma_desc(a_base + A_PLANE + bi * TK_OP_TILE), umma_desc(b_base + B_PLANE + bi * B_TILE), IDESC16, 0u);
-                            if constexpr (QT == 1)
-                                umma_bf16(dv + 2 * MT, umma_desc(a_base + 2 * A_PLANE + bi * TK_OP_TILE),
-                                          umma_desc(b_base + 2 * B_PLANE + bi * B_TILE), IDESC16, 0u);
-                        }
-                        umma_commit(&tm_full[tr.idx]);
-                        tr.next();
-                    }
-                    umma_commit(&conv_empty[cr.idx]);
-                    umma_commit(&act_empty[ar.idx]);
-                    cr.next(); ar.next();
-                }
-            }
-            TK_PROF_FLUSH(4, true);
+        } else if (TK_THREADS == TK_THREADS_BASE && (warp == 1 || warp == 2) && elect_one()) {
+            issuer(warp - 1);
         }
         __syncwarp();
     } else if (warp < 4 + TK_CONV_WARPS) {
@@ -536,9 +619,14 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
         RingPos rr(p.nraw), cr(p.nconv);
         for (int x = rg.lo; x < rg.hi; x++) {
             TK_WAIT(&raw_full[rr.idx], rr.ph, 9);
+            TK_STAMP(1, x - rg.lo, cw == 0 && lane == 0);
             TK_WAIT(&conv_empty[cr.idx], cr.ph ^ 1u, 10);
+            TK_STAMP(2, x - rg.lo, cw == 0 && lane == 0);
             const uint8_t *raw = s_rawr + (size_t)rr.idx * RAW_STAGE;
             uint8_t *conv = s_conv + (size_t)cr.idx * CONV_SLOT;
+#ifdef TK_EXP_NOCONV
+            if (p.N > 0) { __syncwarp(); if (lane == 0) { mbar_arrive(&conv_full[cr.idx]); mbar_arrive(&raw_empty[rr.idx]); } rr.next(); cr.next(); continue; }
+#endif
             // nibble words: lane (g, t) = (row g of an 8-row group, word t); scale path: lane (g2, t2) =
             // (row g2, block t2) so that 8 consecutive lanes store 8 consecutive 16-byte operand rows
             const int g2 = lane & 7, t2 = lane >> 3;
@@ -584,20 +672,22 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
             fence_proxy_async();                         // generic-proxy stores -> visible to the tensor core's reads
             __syncwarp();
             if (lane == 0) { mbar_arrive(&conv_full[cr.idx]); mbar_arrive(&raw_empty[rr.idx]); }
+            TK_STAMP(3, x - rg.lo, cw == 0 && lane == 0);
             rr.next(); cr.next();
         }
         TK_PROF_FLUSH(8, warp == 4 && lane == 0);
-    } else {
+    } else if (warp < 4 + TK_CONV_WARPS + TK_EPI_WARPS) {
         // ===================== epilogue =====================
         reg_inc<TK_REGS_EPI>();
         const int ew = warp - (4 + TK_CONV_WARPS);
         const int q = ew & 3, h = ew >> 2;               // TMEM lane quarter (= warp id % 4), column half
         const int row = q * 32 + lane;                   // weight row inside the tile
         const int etid = ew * 32 + lane;
-        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * HC);
+        // this thread's columns: all of half-tile h (SPLIT: a TMEM tile of its own), else columns [h HC, (h + 1) HC) of the tile
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(SPLIT ? 0 : h * HC);
         TK_PROF_DECL;
         cudaGridDependencySynchronize();                 // Y, the piece workspace and its counters belong to earlier launches until now
-        RingPos tr(NBUF);
+        TK_STAMP(8, 2, ew == 0 && lane == 0);
         int x = rg.lo;
         while (x < rg.hi) {
             const int tile = x / p.C, c0 = x - tile * p.C;
@@ -611,32 +701,51 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
                 // in flight while the FFMA2s of load i run
                 constexpr int NL = CHUNK_BLKS * NSB;
                 float v[2][LW], s[2][LW], r[2][QT == 1 ? LW : 1];
-                TK_WAIT(&tm_full[tr.idx], tr.ph, 14);
-                tc_fence_after();
-                tmem_ld<LW>(t_lane + (uint32_t)(tr.idx * BUFC), v[0]);
-                tmem_ld<LW>(t_lane + (uint32_t)(tr.idx * BUFC + MT), s[0]);
-                if constexpr (QT == 1) tmem_ld<LW>(t_lane + (uint32_t)(tr.idx * BUFC + 2 * MT), r[0]);
-#pragma unroll
-                for (int i = 0; i < NL; i++) {
-                    const int bi = i / NSB, sb = i % NSB, g = bi % G;
-                    if constexpr (QT == 1) tmem_wait_ld3<LW>(v[i & 1], s[i & 1], r[i & 1]);
-                    else                   tmem_wait_ld<LW>(v[i & 1], s[i & 1]);
-                    if (g == G - 1 && sb == NSB - 1) {   // that was the last read of this TMEM buffer: hand it back
+                const int cc = x + c - rg.lo;            // chunk number of this CTA
+                // load i = (block i / NSB, column group i % NSB): its hand-off inside the chunk and first column
+                auto step_of  = [&](int i) { const int bi = i / NSB; return SPLIT ? 2 * bi + h : bi / G; };
+                auto first_of = [&](int i) { return i % NSB == 0 && (SPLIT || (i / NSB) % G == 0); };
+                auto last_of  = [&](int i) { return i % NSB == NSB - 1 && (SPLIT || (i / NSB) % G == G - 1); };
+                auto column   = [&](int i) { return (uint32_t)(tm_buf(cc, step_of(i)) * BUFC + (SPLIT ? 0 : ((i / NSB) % G) * NT * SW) + (i % NSB) * LW); };
+#ifdef TK_EXP_NOEPI
+                if (p.N > 0) {
+                    for (int i = 0; i < NL; i++) if (last_of(i)) {
+                        TK_WAIT(&tm_full[tm_buf(cc, step_of(i))], tm_par(cc, step_of(i)), 14);
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tm_empty[tr.idx]);
-                        tr.next();
+                        if (lane == 0) mbar_arrive(&tm_empty[tm_buf(cc, step_of(i))]);
+                    }
+                    continue;
+                }
+#endif
+                {
+                    TK_WAIT(&tm_full[tm_buf(cc, step_of(0))], tm_par(cc, step_of(0)), 14);
+                    TK_STAMP(6, x + c - rg.lo, ew == 0 && lane == 0);
+                    tc_fence_after();
+                    const uint32_t col = column(0);
+                    tmem_ld<LW>(t_lane + col, v[0]);
+                    tmem_ld<LW>(t_lane + col + SW, s[0]);
+                    if constexpr (QT == 1) tmem_ld<LW>(t_lane + col + 2 * SW, r[0]);
+                }
+#pragma unroll
+                for (int i = 0; i < NL; i++) {
+                    const int sb = i % NSB;
+                    if constexpr (QT == 1) tmem_wait_ld3<LW>(v[i & 1], s[i & 1], r[i & 1]);
+                    else                   tmem_wait_ld<LW>(v[i & 1], s[i & 1]);
+                    if (last_of(i)) {                    // that was the last read of this TMEM buffer: hand it back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tm_empty[tm_buf(cc, step_of(i))]);
                     }
                     if (i + 1 < NL) {
-                        const int bn = (i + 1) / NSB, sn = (i + 1) % NSB, gn = bn % G;
-                        if (gn == 0 && sn == 0) {        // first read of the next buffer
-                            TK_WAIT(&tm_full[tr.idx], tr.ph, 14);
+                        if (first_of(i + 1)) {           // first read of the next buffer
+                            TK_WAIT(&tm_full[tm_buf(cc, step_of(i + 1))], tm_par(cc, step_of(i + 1)), 14);
                             tc_fence_after();
                         }
-                        const uint32_t col = (uint32_t)(tr.idx * BUFC + gn * NT * MT + sn * LW);
+                        const uint32_t col = column(i + 1);
                         tmem_ld<LW>(t_lane + col, v[(i + 1) & 1]);
-                        tmem_ld<LW>(t_lane + col + MT, s[(i + 1) & 1]);
-                        if constexpr (QT == 1) tmem_ld<LW>(t_lane + col + 2 * MT, r[(i + 1) & 1]);
+                        tmem_ld<LW>(t_lane + col + SW, s[(i + 1) & 1]);
+                        if constexpr (QT == 1) tmem_ld<LW>(t_lane + col + 2 * SW, r[(i + 1) & 1]);
                     }
 #pragma unroll
                     for (int j = 0; j < LW / 2; j++) {
@@ -645,6 +754,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
                         acc[sb * (LW / 2) + j] = a2;
                     }
                 }
+                TK_STAMP(7, x + c - rg.lo, ew == 0 && lane == 0);
             }
             // ---- this CTA's share of the tile is done: store, or park the piece and let the last one combine ----
             const float post = 16.0f;
@@ -703,9 +813,15 @@ __global__ void __launch_bounds__(TK_THREADS, 1) q4_tile_kernel(const TileParams
             x += nc;
         }
         TK_PROF_FLUSH(11, ew == 0 && lane == 0);
+    } else {
+        reg_dec<TK_REGS_MISC>();
+        if (elect_one()) issuer(warp - (4 + TK_CONV_WARPS + TK_EPI_WARPS));
+        __syncwarp();
     }
+    TK_STAMP(8, 3, threadIdx.x == 0);
     tc_fence_before();
     __syncthreads();
+    TK_STAMP(8, 4, threadIdx.x == 0);
     if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
