@@ -356,13 +356,14 @@ int run_tile(const b200q4_weight *w, const float *d_x, size_t x_stride_f, const 
         if ((rc = ensure(g.d_tcounters, g.tcounters_cap, need))) return rc;
         CK(cudaMemsetAsync(g.d_tcounters, 0, g.tcounters_cap, st));
     }
-    const long warps = (long)tp.m_tiles * w->C * CHUNK_BLKS * tp.MT;
-    const int blocks = (int)((warps * 32 + 255) / 256);
+    // activation pack: small grids (M <= 64) one warp per (stage row, block) as a programmatic dependent launch -- set up while
+    // the kernel before it drains, waiting for that kernel's results (X; the previous call's tile kernel reading d_tpack) at
+    // its first instruction; larger ones one thread per (stage row, block), launched plainly (the tile kernel launches when
+    // every pack CTA has started, i.e. at the end of a grid that is not resident at once anyway)
+    const long pack_units = (long)tp.m_tiles * w->C * CHUNK_BLKS * tp.MT;
+    const bool pack_warp = M <= 64;
+    const int blocks = pack_warp ? (int)((pack_units * 32 + 255) / 256) : (int)((pack_units + 127) / 128);
     static const int dev_skip = getenv("B200Q4_TILE_SKIP") ? atoi(getenv("B200Q4_TILE_SKIP")) : 0;    // development: 1 = no pack kernel, 2 = no tile kernel
-    // A pack grid that is resident at once is a programmatic dependent launch too: it is set up while the kernel before it
-    // drains and waits for that kernel's results (X; the previous call's tile kernel reading d_tpack) at its first
-    // instruction.  (Larger grids: the tile kernel launches when every pack CTA has started, i.e. at the end anyway.)
-    const bool pack_pdl = g.use_pdl && blocks <= 8 * 148;
     cudaLaunchConfig_t pcfg = {};
     pcfg.gridDim = dim3(blocks); pcfg.blockDim = dim3(256); pcfg.dynamicSmemBytes = 0; pcfg.stream = st;
     cudaLaunchAttribute pat[1];
@@ -371,10 +372,12 @@ int run_tile(const b200q4_weight *w, const float *d_x, size_t x_stride_f, const 
     pcfg.attrs = pat; pcfg.numAttrs = 1;
 #define TILE_PACK(QT)                                                                                                  \
     if (dev_skip == 1) { }                                                                                             \
-    else if (pack_pdl && d_wdata) CK(cudaLaunchKernelEx(&pcfg, tile_pack_kernel<QT, true, true>, (const float *)nullptr, (size_t)0, d_wdata, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack)); \
-    else if (pack_pdl)            CK(cudaLaunchKernelEx(&pcfg, tile_pack_kernel<QT, false, true>, d_x, x_stride_f, (const uint8_t *)nullptr, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack)); \
-    else if (d_wdata) tile_pack_kernel<QT, true, false><<<blocks, 256, 0, st>>>(nullptr, 0, d_wdata, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack); \
-    else              tile_pack_kernel<QT, false, false><<<blocks, 256, 0, st>>>(d_x, x_stride_f, nullptr, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack);
+    else if (pack_warp && g.use_pdl && d_wdata) CK(cudaLaunchKernelEx(&pcfg, tile_pack_warp_kernel<QT, true, true>, (const float *)nullptr, (size_t)0, d_wdata, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack)); \
+    else if (pack_warp && g.use_pdl)            CK(cudaLaunchKernelEx(&pcfg, tile_pack_warp_kernel<QT, false, true>, d_x, x_stride_f, (const uint8_t *)nullptr, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack)); \
+    else if (pack_warp && d_wdata) tile_pack_warp_kernel<QT, true, false><<<blocks, 256, 0, st>>>(nullptr, 0, d_wdata, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack); \
+    else if (pack_warp)            tile_pack_warp_kernel<QT, false, false><<<blocks, 256, 0, st>>>(d_x, x_stride_f, nullptr, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack); \
+    else if (d_wdata) tile_pack_kernel<QT, true><<<blocks, 128, 0, st>>>(nullptr, 0, d_wdata, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack); \
+    else              tile_pack_kernel<QT, false><<<blocks, 128, 0, st>>>(d_x, x_stride_f, nullptr, M, tp.MT, w->nb, w->C, tp.m_tiles, g.d_tpack);
     if (w->type == 0) { TILE_PACK(0) } else { TILE_PACK(1) }
 #undef TILE_PACK
     g.launches++;

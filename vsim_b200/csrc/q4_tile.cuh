@@ -201,11 +201,120 @@ __device__ __forceinline__ int tk_operand_off(int r, int p) { return (r >> 3) * 
 
 // ---- activation pack for the tile kernel ----------------------------------------------------------
 // Stage (m tile, chunk) = [4 blocks x codes tile][4 blocks x scale-piece tile]([4 blocks x rank-2 tile]),
-// every tile MT rows x 32 B in operand layout.  One warp per (stage row m_local, block), padding included.
+// every tile MT rows x 32 B in operand layout.  One THREAD per (stage row m_local, block), padding included: the
+// block's 32 floats arrive as eight float4, the scale arithmetic (two IEEE divisions) runs once per block instead of in
+// all 32 lanes of a warp, and the operand row leaves as two 16-byte stores -- adjacent threads are adjacent rows, i.e.
+// eight threads write one 128-byte core matrix.  Same arithmetic as quantize_block (q4_kernels.cuh): the codes are the
+// reference's quantize_row_q4_0 / _q4_1 codes bit for bit.
 // SRC_WDATA: rows already quantized by the reference's INIT phase (params->wdata image).
-// DEP: launched with the programmatic-dependent-launch attribute (small grids, see run_tile).
+template <int QT, bool SRC_WDATA>
+__global__ void __launch_bounds__(128) tile_pack_kernel(const float *__restrict__ x, size_t x_stride, const uint8_t *__restrict__ wdata,
+                                                        int M, int MT, int nb, int C, int m_tiles, uint8_t *__restrict__ tpack)
+{
+    cudaTriggerProgrammaticLaunchCompletion();           // the tile kernel may start its weight stream now
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)m_tiles * C * CHUNK_BLKS * MT;
+    if (t >= total) return;
+    const int ml = (int)(t % MT);
+    long r = t / MT;
+    const int bi = (int)(r % CHUNK_BLKS); r /= CHUNK_BLKS;
+    const int c = (int)(r % C);
+    const int mt = (int)(r / C);
+    const int m = mt * MT + ml, blk = c * CHUNK_BLKS + bi;
+    const bool real = (m < M) && (blk < nb);
+    float d = 0.0f, mn = 0.0f;
+    int code[QK];                                        // padding: centred code 0, zero scales
+#pragma unroll
+    for (int e = 0; e < QK; e++) code[e] = 8;
+    if (real) {
+        if (SRC_WDATA) {
+            const uint8_t *nib;
+            if (QT == 0) {
+                const uint8_t *b = wdata + ((size_t)m * nb + blk) * 20;
+                d = *reinterpret_cast<const float *>(b);
+                nib = b + 4;
+            } else {
+                const uint8_t *row = wdata + (size_t)m * nb * 24;
+                mn = reinterpret_cast<const float *>(row)[blk];
+                d  = reinterpret_cast<const float *>(row)[nb + blk];
+                nib = row + (size_t)nb * 8 + (size_t)blk * 16;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t wv = reinterpret_cast<const uint32_t *>(nib)[i];
+#pragma unroll
+                for (int j = 0; j < 8; j++) code[8 * i + j] = (int)((wv >> (4 * j)) & 15u);
+            }
+        } else {
+            float v[QK];
+            const float4 *src = reinterpret_cast<const float4 *>(x + (size_t)m * x_stride + (size_t)blk * QK);
+            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+                for (int i = 0; i < QK / 4; i++) { const float4 f = __ldg(src + i); v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w; }
+            } else {
+#pragma unroll
+                for (int e = 0; e < QK; e++) v[e] = x[(size_t)m * x_stride + (size_t)blk * QK + e];
+            }
+            if (QT == 0) {
+                float amax = fabsf(v[0]);
+#pragma unroll
+                for (int e = 1; e < QK; e++) amax = fmaxf(amax, fabsf(v[e]));
+                d = __fdiv_rn(amax, 7.0f);
+                const float id = (d != 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+#pragma unroll
+                for (int e = 0; e < QK; e++) code[e] = (int)(uint8_t)((int8_t)round_to_int_ref(__fmul_rn(v[e], id)) + 8);
+            } else {
+                float lo = v[0], hi = v[0];
+#pragma unroll
+                for (int e = 1; e < QK; e++) { lo = fminf(lo, v[e]); hi = fmaxf(hi, v[e]); }
+                // of several numerically equal extrema (+0.0 / -0.0) the reference keeps the FIRST one's bits (ggml.c:268-274)
+                float lo_b = lo, hi_b = hi;
+#pragma unroll
+                for (int e = QK - 1; e >= 0; e--) { if (v[e] == lo) lo_b = v[e]; if (v[e] == hi) hi_b = v[e]; }
+                mn = lo_b;
+                d = __fdiv_rn(__fsub_rn(hi_b, mn), 15.0f);
+                const float id = (d != 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+#pragma unroll
+                for (int e = 0; e < QK; e++) code[e] = (int)(uint8_t)round_to_int_ref(__fmul_rn(__fsub_rn(v[e], mn), id));
+            }
+        }
+    }
+    // operand row: K byte 4t + j = element 8t + 2j (the weight words' low nibbles), 16 + 4t + j = element 8t + 2j + 1 (tk_kpos)
+    uint32_t wlo[4], whi[4];
+    int s = 0;
+#pragma unroll
+    for (int tq = 0; tq < 4; tq++) {
+        wlo[tq] = 0u; whi[tq] = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int a0 = (code[8 * tq + 2 * j] & 15) - 8, a1 = (code[8 * tq + 2 * j + 1] & 15) - 8;
+            wlo[tq] |= e4m3_of_int(a0, 5) << (8 * j);
+            whi[tq] |= e4m3_of_int(a1, 5) << (8 * j);
+            s += a0 + a1;
+        }
+    }
+    uint8_t *stage = tpack + ((size_t)mt * C + c) * tk_act_stage(QT, MT);
+    const size_t tile = (size_t)MT * 32, plane = (size_t)CHUNK_BLKS * tile;
+    uint8_t *t1 = stage + (size_t)bi * tile;
+    *reinterpret_cast<uint4 *>(t1 + tk_operand_off(ml, 0)) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
+    *reinterpret_cast<uint4 *>(t1 + tk_operand_off(ml, 16)) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+    if (QT == 1) {                                       // rank-2 right factors: m1' = m1c/16, Z' = (d1*sum(q1-8) + 32*m1c)/16
+        uint4 lo, hi;
+        const float m1c = __fadd_rn(mn, 8.0f * d);
+        bf16_slots2_right(m1c * 0.0625f, fmaf(d, (float)s, 32.0f * m1c) * 0.0625f, lo, hi);
+        uint8_t *t4 = stage + 2 * plane + (size_t)bi * tile;
+        *reinterpret_cast<uint4 *>(t4 + tk_operand_off(ml, 0)) = lo;
+        *reinterpret_cast<uint4 *>(t4 + tk_operand_off(ml, 16)) = hi;
+    }
+    uint8_t *t3 = stage + plane + (size_t)bi * tile;     // the eight slots of d1 (the upper eight stay zero)
+    *reinterpret_cast<uint4 *>(t3 + tk_operand_off(ml, 0)) = bf16_slots_right(d);
+    *reinterpret_cast<uint4 *>(t3 + tk_operand_off(ml, 16)) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// The same stage, one WARP per (stage row m_local, block): more parallel, more instructions -- the faster of the two for the
+// small grids of M <= 64 (3.2 us against 4.6), where it is launched as a programmatic dependent (DEP; see run_tile).
 template <int QT, bool SRC_WDATA, bool DEP>
-__global__ void tile_pack_kernel(const float *__restrict__ x, size_t x_stride, const uint8_t *__restrict__ wdata,
+__global__ void tile_pack_warp_kernel(const float *__restrict__ x, size_t x_stride, const uint8_t *__restrict__ wdata,
                                  int M, int MT, int nb, int C, int m_tiles, uint8_t *__restrict__ tpack)
 {
     cudaTriggerProgrammaticLaunchCompletion();           // the tile kernel may start its weight stream now
