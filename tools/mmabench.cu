@@ -274,25 +274,22 @@ void run_hs()
 
 int main(int argc, char **argv)
 {
-    const bool trace_only = argc > 1;
-    g_trace = trace_only;
-    run_hs<16, 4, 8, 1, 0, 1, 1>(); run_hs<16, 4, 8, 1, 1, 1, 1>(); run_hs<16, 4, 8, 1, 1, 0, 1>(); run_hs<16, 4, 8, 1, 1, 1, 0>(); run_hs<16, 4, 8, 1, 0, 1, 0>(); run_hs<128, 4, 8, 1, 1, 1, 1>();
-    run_hs<128, 2, 7, 8, 0>(); run_hs<64, 4, 7, 8, 0>(); run_hs<16, 4, 7, 8, 0>(); run_hs<16, 4, 7, 8, 0, 1, 4>(); run_hs<128, 2, 7, 8, 1>(); run_hs<64, 4, 7, 8, 1>(); run_hs<64, 2, 7, 8, 1>(); run_hs<32, 4, 7, 8, 1, 1, 2>();
-    run_hs<128, 2, 6, 8, 0>(); run_hs<64, 4, 6, 8, 0>(); run_hs<16, 4, 6, 8, 0>(); run_hs<128, 2, 6, 8, 1>(); run_hs<64, 4, 6, 8, 1>();
-    run_hs<128, 2, 5, 8, 0>(); run_hs<64, 4, 5, 8, 0>(); run_hs<16, 4, 5, 8, 0>(); run_hs<128, 2, 5, 8, 1>(); run_hs<64, 4, 5, 8, 1>();
-    if (trace_only) { run_hs<16, 4, 1, 8, 0>(); run_hs<128, 2, 1, 8, 0>(); run_hs<128, 2, 1, 8, 1>(); return 0; }
-    run_hs<128, 2, 1, 8, 0, 0>(); run_hs<64, 4, 1, 8, 0, 0>(); run_hs<16, 4, 1, 8, 0, 0>(); run_hs<16, 4, 1, 8, 0, 1, 4>(); run_hs<16, 4, 1, 8, 0, 0, 4>(); run_hs<16, 4, 1, 1, 0, 0, 1>();
-    run_hs<16, 4, 0, 8, 0, 0, 1>(); run_hs<16, 4, 0, 8, 0, 1, 1>();
-    run_hs<128, 2, 0, 8, 0>(); run_hs<128, 2, 1, 8, 0>(); run_hs<128, 2, 2, 8, 0>(); run_hs<128, 2, 1, 8, 1>(); run_hs<128, 2, 2, 8, 1>();
-    run_hs<128, 2, 1, 1, 0>(); run_hs<128, 2, 2, 1, 0>();
-    run_hs<64, 4, 0, 8, 0>(); run_hs<64, 4, 1, 8, 0>(); run_hs<64, 4, 2, 8, 0>(); run_hs<64, 4, 1, 8, 1>(); run_hs<64, 4, 2, 8, 1>();
-    run_hs<64, 2, 1, 8, 1>();
-    run_hs<16, 4, 1, 8, 0>(); run_hs<16, 4, 2, 8, 0>();
+    g_trace = argc > 1;                                          // any argument: stamp traces of three hand-off variants only
+    if (g_trace) { run_hs<16, 4, 1, 8, 0>(); run_hs<128, 2, 1, 8, 0>(); run_hs<128, 2, 1, 8, 1>(); return 0; }
+    printf("-- cycles per tcgen05.mma (M = 128, K = 32 bytes, operands in shared memory), one issuing thread, no hand-off\n");
     run<16, 0, 0, 0>(); run<32, 0, 0, 0>(); run<64, 0, 0, 0>(); run<128, 0, 0, 0>();
     run<16, 1, 0, 0>(); run<32, 1, 0, 0>(); run<64, 1, 0, 0>(); run<128, 1, 0, 0>();
     run<16, 2, 0, 0>(); run<64, 2, 0, 0>();
     run<16, 0, 2, 0>(); run<64, 0, 2, 0>(); run<16, 0, 6, 0>(); run<64, 0, 6, 0>();
-    run<16, 1, 0, 4>(); run<64, 1, 0, 4>(); run<128, 1, 0, 4>();
-    run<16, 1, 0, 8>(); run<64, 1, 0, 8>();
+    run<16, 1, 0, 4>(); run<64, 1, 0, 4>(); run<128, 1, 0, 4>(); run<16, 1, 0, 8>(); run<64, 1, 0, 8>();
+    printf("-- what a wait costs the issuing thread (no partner warps)\n");
+    run_hs<16, 4, 8, 1, 0, 1, 1>(); run_hs<16, 4, 8, 1, 1, 1, 1>(); run_hs<16, 4, 8, 1, 1, 0, 1>(); run_hs<16, 4, 8, 1, 1, 1, 0>(); run_hs<16, 4, 8, 1, 0, 1, 0>();
+    printf("-- the TMEM hand-off (issuer: wait tm_empty, one block = 3 MMAs per block of the buffer, commit tm_full; epilogue warps: wait tm_full, arrive tm_empty)\n");
+    run_hs<128, 2, 0, 8, 0>(); run_hs<128, 2, 1, 8, 0>(); run_hs<128, 2, 2, 8, 0>(); run_hs<128, 2, 1, 1, 0>(); run_hs<128, 2, 5, 8, 0>(); run_hs<128, 2, 6, 8, 0>(); run_hs<128, 2, 7, 8, 0>();
+    run_hs<64, 4, 0, 8, 0>(); run_hs<64, 4, 1, 8, 0>(); run_hs<64, 4, 2, 8, 0>(); run_hs<64, 4, 5, 8, 0>(); run_hs<64, 4, 6, 8, 0>(); run_hs<64, 4, 7, 8, 0>();
+    run_hs<16, 4, 0, 8, 0>(); run_hs<16, 4, 1, 8, 0>(); run_hs<16, 4, 1, 8, 0, 0>(); run_hs<16, 4, 2, 8, 0>(); run_hs<16, 4, 5, 8, 0>(); run_hs<16, 4, 6, 8, 0>(); run_hs<16, 4, 7, 8, 0>();
+    run_hs<16, 4, 1, 8, 0, 1, 4>(); run_hs<16, 4, 7, 8, 0, 1, 4>();
+    printf("-- the same with the epilogue warps reading their part of the buffer (unpipelined tcgen05.ld x16 pairs)\n");
+    run_hs<128, 2, 1, 8, 1>(); run_hs<128, 2, 5, 8, 1>(); run_hs<64, 4, 1, 8, 1>(); run_hs<64, 2, 1, 8, 1>(); run_hs<64, 4, 5, 8, 1>(); run_hs<32, 4, 7, 8, 1, 1, 2>();
     return 0;
 }
