@@ -316,6 +316,16 @@ TilePlan tile_plan(const b200q4_weight *w, int M)
     long nraw = raw_fit();
     while (nraw < 3 && tp.nconv > 2) { tp.nconv--; nraw = raw_fit(); }
     while (nraw < 3 && tp.nact > 2) { tp.nact--; nraw = raw_fit(); }
+    // fewer TMEM hand-offs per chunk than issuers (small MT): ring depths that are multiples of the issuer-group count let an
+    // issuer skip the other groups' chunks (tk_groups, q4_tile.cuh) -- taken when at least four raw stages still fit
+    const int groups = tk_groups(qt, tp.MT);
+    if (groups > 1 && qt == 0) {                                              // (Q4_1, MT = 16: two 48 KB slots instead of three cost more than the waits)
+        const int keep_act = tp.nact, keep_conv = tp.nconv;
+        tp.nact = 4;
+        tp.nconv = 4;
+        if (raw_fit() >= 4) nraw = raw_fit();
+        else { tp.nact = keep_act; tp.nconv = keep_conv; }
+    }
     if (nraw > TK_MAX_RAW) nraw = TK_MAX_RAW;
     tp.nraw = (int)nraw;
     tp.smem = tk_smem_bytes(qt, tp.MT, tp.nraw, tp.nact, tp.nconv);

@@ -100,6 +100,11 @@ __host__ __device__ constexpr int tk_nbuf(int qt, int mt)
     return n > TK_MAX_TM ? TK_MAX_TM : n;
 }
 
+// TMEM hand-offs per chunk and issuer groups: with fewer hand-offs per chunk than issuers, a chunk belongs to ONE group of
+// issuers (chunk cc -> group cc % tk_groups); when the operand rings' depths are multiples of the group count a slot always
+// belongs to the same group, whose issuers then see every phase of its barriers in order and the others need not touch it.
+__host__ __device__ constexpr int tk_steps(int qt, int mt) { return tk_split(qt, mt) ? 2 * CHUNK_BLKS : CHUNK_BLKS / tk_g(qt, mt); }
+__host__ __device__ constexpr int tk_groups(int qt, int mt) { return tk_steps(qt, mt) >= tk_nbuf(qt, mt) ? 1 : tk_nbuf(qt, mt) / tk_steps(qt, mt); }
 __host__ __device__ constexpr int tk_threads(int qt, int mt) { return tk_nbuf(qt, mt) == 4 ? TK_THREADS_MAX : TK_THREADS_BASE; }
 
 struct TileParams {
@@ -535,6 +540,10 @@ __global__ void __launch_bounds__(tk_threads(QT, MT), 1) q4_tile_kernel(const Ti
     constexpr int BUFC = G * NT * SW;                                         // columns per TMEM buffer
     static_assert(NBUF * BUFC <= 512 && (NBUF == 2 || NBUF == 4) && (!SPLIT || G == 1), "TMEM map: one issuer per buffer");
     constexpr int W = NBUF;                                                   // issuers at work
+    constexpr int GROUPS = tk_groups(QT, MT);
+    static_assert(STEPS == tk_steps(QT, MT), "hand-offs per chunk");
+    const bool own_only = GROUPS > 1 && p.nconv % GROUPS == 0 && p.nact % GROUPS == 0;   // issuers touch their own group's chunks only
+    const int n_arrive = own_only ? STEPS : W;                                // issuers arriving on a slot's empty barrier
     // hand-off k of this CTA's chunk number cc is hand-off cc * STEPS + k of the CTA: its TMEM buffer and the parity of that
     // buffer's use (compile-time functions of k wherever STEPS allows)
     auto tm_buf = [](int cc, int k) -> int {
@@ -570,8 +579,8 @@ __global__ void __launch_bounds__(tk_threads(QT, MT), 1) q4_tile_kernel(const Ti
     const int G_ = (int)gridDim.x;
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nraw; i++) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], TK_CONV_WARPS); }
-        for (int i = 0; i < p.nact; i++) { mbar_init(&act_full[i], 1); mbar_init(&act_empty[i], W); }
-        for (int i = 0; i < p.nconv; i++) { mbar_init(&conv_full[i], TK_CONV_WARPS); mbar_init(&conv_empty[i], W); }
+        for (int i = 0; i < p.nact; i++) { mbar_init(&act_full[i], 1); mbar_init(&act_empty[i], n_arrive); }
+        for (int i = 0; i < p.nconv; i++) { mbar_init(&conv_full[i], TK_CONV_WARPS); mbar_init(&conv_empty[i], n_arrive); }
         for (int i = 0; i < NBUF; i++) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], SPLIT ? TK_EPI_WARPS / 2 : TK_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -599,13 +608,14 @@ __global__ void __launch_bounds__(tk_threads(QT, MT), 1) q4_tile_kernel(const Ti
             // and to issuer n % W, so every buffer has one issuer.  Why several: after tcgen05.mma / tcgen05.commit a
             // thread's next mbarrier wait takes 100-250 cycles even on a barrier that completed long ago, and does not return
             // before the thread's own MMAs have (tools/mmabench.cu, profiles/r02_mmabench.txt) -- one issuer alone leaves the
-            // tensor pipe idle for most of every hand-off.  Every issuer waits for the operand slots of EVERY chunk and arrives
-            // on their empty barriers (count W), also for chunks it issues nothing from: skipping chunks would let a
-            // parity wait run two phases ahead of its barrier.
+            // tensor pipe idle for most of every hand-off.  Unless a slot always belongs to the same issuer group (own_only, see
+            // tk_groups), every issuer waits for the operand slots of EVERY chunk and arrives on their empty barriers, also
+            // for chunks it issues nothing from: skipping chunks would let a parity wait run two phases ahead of its barrier.
             TK_PROF_DECL;
             RingPos ar(p.nact), cr(p.nconv);
             const uint32_t a8 = smem_u32(s_a8);
             for (int x = rg.lo; x < rg.hi && w < W; x++) {
+                if (own_only && (x - rg.lo) % GROUPS != w / STEPS) { cr.next(); ar.next(); continue; }     // another group's chunk
                 {
                     TK_WAIT(&conv_full[cr.idx], cr.ph, 5);
                     TK_STAMP(10, x - rg.lo, w == 0);
