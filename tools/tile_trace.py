@@ -30,8 +30,9 @@ L.b200q4_debug_timeline.argtypes = [C.c_void_p]
 assert L.b200q4_debug_timeline(buf.ctypes.data) == 0
 b = buf.reshape(-1)[: 11 * 32].reshape(11, 32).astype(np.int64)
 t0 = b[8, 0]
-print("kernel-level (cycles after the activation producer started): pack kernel done (act producer) %d, epilogue past the dependency sync %d, "
-      "thread 0 at the final barrier %d, past it %d" % tuple(b[8, 1:5] - t0))
+print("kernel-level (cycles after the activation producer started): kernel entry %d, prologue done %d, pack kernel done (act producer) %d, "
+      "epilogue past the dependency sync %d, raw producer at the final barrier %d, epilogue warp 0: last piece accumulated %d, "
+      "its store / stream-K combine done %d" % tuple(int(b[8, k] - t0) for k in (7, 8, 1, 2, 3, 5, 6)))
 hdr = ["raw issued", "conv: raw_full", "conv: conv_empty", "conv: done", "act issued", "mma: conv_full", "mma: act_full", "mma: committed", "epi: tm_full", "epi: chunk read"]
 rows = [0, 1, 2, 3, 9, 10, 4, 5, 6, 7]
 print("step " + " ".join(f"{h:>17s}" for h in hdr))

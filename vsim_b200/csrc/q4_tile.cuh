@@ -498,8 +498,8 @@ template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setma
 // Stream-K work split: the launch's chunk steps (tile-major: tile = n tile x m tile with the m tile
 // fastest, so CTAs that run side by side share their weight tile through L2) are cut into gridDim.x
 // equal contiguous ranges.  A CTA whose range starts or ends inside a tile produces a PIECE of that
-// tile; pieces are parked in a workspace and the last one to arrive adds them in CTA order (fixed ->
-// bit-reproducible) and stores Y.  One mechanism covers both the small-M case (few tiles, every SM
+// tile; pieces are parked in a workspace and the owner of the tile's first chunk -- the last to get to
+// the tile -- adds them in CTA order (fixed -> bit-reproducible) and stores Y.  One mechanism covers both the small-M case (few tiles, every SM
 // must stream weights) and the large-M tail (tile count not a multiple of the SM count).
 struct TkRange { int lo, hi; };                      // the host keeps ntiles * C below 2^31
 __device__ __forceinline__ TkRange tk_range(const TileParams &p, int b, int G)
@@ -576,6 +576,7 @@ __global__ void __launch_bounds__(tk_threads(QT, MT), 1) q4_tile_kernel(const Ti
 
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);    // provably warp-uniform
+    TK_STAMP(8, 7, threadIdx.x == 0);                                         // kernel entry
     const int G_ = (int)gridDim.x;
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nraw; i++) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], TK_CONV_WARPS); }
@@ -600,6 +601,7 @@ __global__ void __launch_bounds__(tk_threads(QT, MT), 1) q4_tile_kernel(const Ti
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
+    TK_STAMP(8, 8, threadIdx.x == 0);                                         // prologue done
     const TkRange rg = tk_range(p, (int)blockIdx.x, G_);
 
     auto issuer = [&](const int w) {
@@ -875,6 +877,7 @@ __global__ void __launch_bounds__(tk_threads(QT, MT), 1) q4_tile_kernel(const Ti
                 }
                 TK_STAMP(7, x + c - rg.lo, ew == 0 && lane == 0);
             }
+            TK_STAMP(8, 5, ew == 0 && lane == 0 && x + nc >= rg.hi);                  // last piece accumulated
             // ---- this CTA's share of the tile is done: store, or park the piece and let the last one combine ----
             const float post = 16.0f;
             const int n = nt * TK_ROWS + row;
@@ -882,37 +885,39 @@ __global__ void __launch_bounds__(tk_threads(QT, MT), 1) q4_tile_kernel(const Ti
             const bool whole = (c0 == 0) && (nc == p.C);
             bool store = true;
             if (!whole) {
+                // Stream-K fix-up.  The CTA whose range holds the tile's FIRST chunk gets to it at the END of its range: it is
+                // the combiner -- it keeps its piece in registers, waits until the other owners have parked theirs (they did
+                // so at the START of their ranges, long ago, or are finishing at the same moment), adds them in CTA order
+                // (fixed -> bit-reproducible) and stores Y.  Every other owner parks its piece, bumps the tile's counter and
+                // goes on at once: no atomic round trip, no "am I last" decision on anybody's critical path.
                 const int b = (int)blockIdx.x;
-                // piece slot: 0 if the tile began before this CTA's range (head piece), else 1 (tail piece)
-                float *ws = p.partial + ((size_t)(2 * b + (c0 == 0 ? 1 : 0)) * MT + (size_t)(h * HC)) * TK_ROWS + row;
-#pragma unroll
-                for (int j = 0; j < HC / 2; j++) {
-                    float a, bq;
-                    upk2(acc[j], a, bq);
-                    ws[(size_t)(2 * j) * TK_ROWS] = a;
-                    ws[(size_t)(2 * j + 1) * TK_ROWS] = bq;
-                }
-                __threadfence();
-                asm volatile("bar.sync 2, %0;" :: "n"(TK_EPI_WARPS * 32) : "memory");
                 const int t0 = tile * p.C;
                 const int bf = tk_owner(p, t0, G_), bl = tk_owner(p, t0 + p.C - 1, G_);
-                if (etid == 0) {
-                    const int old = atomicAdd(p.counters + tile, 1);
-                    const int last = (old == bl - bf);
-                    *s_flag = last;
-                    if (last) p.counters[tile] = 0;
-                }
-                asm volatile("bar.sync 2, %0;" :: "n"(TK_EPI_WARPS * 32) : "memory");
-                store = *s_flag != 0;
-                asm volatile("bar.sync 2, %0;" :: "n"(TK_EPI_WARPS * 32) : "memory");   // s_flag may be rewritten by the next tile
-                if (store) {
+                if (c0 != 0) {                                // b != bf: park (slot 2 b; slot 2 b + 1 is no longer used)
+                    float *ws = p.partial + ((size_t)(2 * b) * MT + (size_t)(h * HC)) * TK_ROWS + row;
+#pragma unroll
+                    for (int j = 0; j < HC / 2; j++) {
+                        float a, bq;
+                        upk2(acc[j], a, bq);
+                        ws[(size_t)(2 * j) * TK_ROWS] = a;
+                        ws[(size_t)(2 * j + 1) * TK_ROWS] = bq;
+                    }
+                    __threadfence();                          // every writer orders its own stores, then the barrier, then the count
+                    asm volatile("bar.sync 2, %0;" :: "n"(TK_EPI_WARPS * 32) : "memory");
+                    if (etid == 0) atomicAdd(p.counters + tile, 1);
+                    store = false;
+                } else {                                      // b == bf
+                    if (etid == 0) {
+                        while (*reinterpret_cast<volatile int *>(p.counters + tile) < bl - bf) { }
+                        p.counters[tile] = 0;                 // self-resetting: every other owner has counted
+                    }
+                    asm volatile("bar.sync 2, %0;" :: "n"(TK_EPI_WARPS * 32) : "memory");
                     __threadfence();
                     float sum[HC];
 #pragma unroll
-                    for (int j = 0; j < HC; j++) sum[j] = 0.0f;
-                    for (int bb = bf; bb <= bl; bb++) {      // CTA order: reproducible rounding
-                        const int slot = 2 * bb + (t0 < tk_range(p, bb, G_).lo ? 0 : 1);
-                        const float *rsrc = p.partial + ((size_t)slot * MT + (size_t)(h * HC)) * TK_ROWS + row;
+                    for (int j = 0; j < HC / 2; j++) upk2(acc[j], sum[2 * j], sum[2 * j + 1]);
+                    for (int bb = bf + 1; bb <= bl; bb++) {   // CTA order: reproducible rounding
+                        const float *rsrc = p.partial + ((size_t)(2 * bb) * MT + (size_t)(h * HC)) * TK_ROWS + row;
 #pragma unroll
                         for (int j = 0; j < HC; j++) sum[j] += __ldcg(rsrc + (size_t)j * TK_ROWS);
                     }
@@ -931,6 +936,7 @@ __global__ void __launch_bounds__(tk_threads(QT, MT), 1) q4_tile_kernel(const Ti
             }
             x += nc;
         }
+        TK_STAMP(8, 6, ew == 0 && lane == 0);                                     // last store / combine done
         TK_PROF_FLUSH(11, ew == 0 && lane == 0);
     } else {
         reg_dec<TK_REGS_MISC>();
