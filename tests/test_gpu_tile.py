@@ -115,6 +115,21 @@ def test_tile_deterministic_and_scale_exact(gpu, oracle, qt, tag):
 
 
 @pytest.mark.parametrize("qt,tag", TYPES)
+@pytest.mark.parametrize("n,k,m", [(130, 16384, 24), (128, 8192, 9), (700, 4096, 70)])
+def test_tile_stream_k_many_owners_repeatable(gpu, oracle, qt, tag, n, k, m):
+    """Tiles whose chunks are spread over many CTAs (up to 74 owners per tile): the owner of the tile's first chunk combines
+    the parked pieces in CTA order and re-arms the tile's counter -- five launches in a row give the same bits, and they
+    are the oracle's values."""
+    wq, x = make(oracle, qt, n, k, m, n + k + m)
+    w = gpu.Q4Weight(qt, wq, n, k)
+    ys = [gpu.mul_mat(w, x) for _ in range(5)]
+    for y in ys[1:]:
+        assert np.array_equal(y.view(np.uint32), ys[0].view(np.uint32))
+    assert check(ys[0], oracle.mul_mat(qt, wq, n, k, x, nth=4), f"{tag} many owners N={n} K={k} M={m}") < 1e-5
+    w.free()
+
+
+@pytest.mark.parametrize("qt,tag", TYPES)
 def test_tile_wdata_entry_bitwise(gpu, oracle, qt, tag):
     """Rows quantized by the reference's INIT phase (params->wdata) give the same bits as device quantization."""
     n, k, m = 500, 768, 70
