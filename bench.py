@@ -928,5 +928,37 @@ def main() -> int:
     return 0
 
 
+def _main_clean_stdout() -> int:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on the first
+    communicator): while the bench runs, file descriptor 1 points at stderr, and only the JSON line goes to the real one."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    rc = 1
+    try:
+        import io
+        buf = io.StringIO()
+        old, sys.stdout = sys.stdout, buf
+        try:
+            rc = main()
+        except SystemExit as e:                      # argparse (--help, bad flags)
+            rc = e.code if isinstance(e.code, int) else (0 if e.code is None else 2)
+        finally:
+            sys.stdout = old
+    finally:
+        sys.stdout.flush()
+        os.dup2(real, 1)
+        os.close(real)
+    out = buf.getvalue()
+    json_lines = [l for l in out.splitlines() if l.startswith("{")]
+    for l in out.splitlines():
+        if not l.startswith("{"):
+            sys.stderr.write(l + "\n")
+    for l in json_lines:
+        print(l)
+    sys.stdout.flush()
+    return rc
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(_main_clean_stdout())
