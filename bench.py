@@ -685,15 +685,21 @@ def main() -> int:
             if tail is not None:
                 tail.run(stream.cuda_stream)
             barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(steps // per if world == 1 else nl):
-                ch.run(stream.cuda_stream)
-            if tail is not None:
-                tail.run(stream.cuda_stream)
-            e1.record(stream)
-            barrier()
-            ms = e0.elapsed_time(e1)
+            if world == 1:
+                # events recorded from C around the launches (b200q4_chain_time, include/b200q4_dev.h): with torch events the
+                # interpreter's time between the first event and the first launch sits inside the timed region of an idle GPU
+                ms = L.b200q4_chain_time(ch.handle, tail.handle if tail is not None else None, steps // per, stream.cuda_stream)
+                if ms < 0:
+                    raise RuntimeError(f"b200q4_chain_time failed ({ms})")
+                barrier()
+            else:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(nl):
+                    ch.run(stream.cuda_stream)
+                e1.record(stream)
+                barrier()
+                ms = e0.elapsed_time(e1)
             if world > 1:
                 ms = ms * steps / (nl * per)                 # (whole launches were timed: nl * per >= steps of them)
                 t = torch.tensor([ms], device="cuda")
@@ -753,6 +759,7 @@ def main() -> int:
                           "CUDA events on the launching stream around the timed launches",
                 "algorithmic_bytes_per_launch": int(alg_bytes(0, M_HEAD) * units), "us_per_launch": launch_ms * 1e3,
                 "units_per_launch": units, "algorithmic_bytes_per_unit": alg_bytes(0, M_HEAD),
+                "traffic_note": "ncu capture of a 100-unit launch (profiles/traffic.json), scaled to this run's units per launch",
                 "per_call_kernel": {"kernel": "q4_gemv_pipe_kernel<Q4_0, chain4, fused quantization> (one launch per call), back to back",
                                     "us_per_launch": kern_ms * 1e3, "achieved": alg_bytes(0, M_HEAD) / (kern_ms * 1e-3) / 1e9,
                                     "frac": alg_bytes(0, M_HEAD) / (kern_ms * 1e-3) / 1e9 / peak}}
@@ -761,6 +768,8 @@ def main() -> int:
                 "kernel": "q4_gemv_pipe_kernel<Q4_0, chain4, fused quantization> (M=1: one launch per call), CUDA events on "
                           "the library stream around back-to-back launches rotating weights",
                 "algorithmic_bytes_per_launch": alg_bytes(0, M_HEAD), "us_per_launch": kern_ms * 1e3}
+    if headline and traffic is not None:
+        traffic = traffic * units / 100.0                                      # the capture is of a 100-unit launch
     achieved = roof.pop("achieved")
 
     # ---- e2e: host buffers through the C ABI --------------------------------------------------------
@@ -941,8 +950,12 @@ def _main_clean_stdout() -> int:
         old, sys.stdout = sys.stdout, buf
         try:
             rc = main()
-        except SystemExit as e:                      # argparse (--help, bad flags)
-            rc = e.code if isinstance(e.code, int) else (0 if e.code is None else 2)
+        except SystemExit as e:                      # argparse (--help, bad flags), sys.exit("message")
+            if isinstance(e.code, int) or e.code is None:
+                rc = e.code or 0
+            else:
+                sys.stderr.write(str(e.code) + "\n")
+                rc = 1
         finally:
             sys.stdout = old
     finally:

@@ -13,6 +13,9 @@ extern "C" {
 /* Times `iters` back-to-back device-resident mul_mats with CUDA events on the library stream, rotating over `nw` weight
  * handles (L2 defeat); returns the mean milliseconds per call or a negative error code.                              */
 double b200q4_time_mul_mat_dev(b200q4_weight *const *ws, int nw, const float *d_x, int M, float *d_y, int iters);
+/* Times `launches` runs of program list c followed by one of `tail` (may be NULL) with CUDA events recorded from C on
+ * `stream` (NULL = the library stream) and waits for them; returns the milliseconds or a negative error code.         */
+double b200q4_chain_time(b200q4_chain *c, b200q4_chain *tail, int launches, void *stream);
 /* Host-only: the launch plan b200q4_mul_mat would use for (type, N, K, M): out[0..] = grid, stages, static tasks, K-slices
  * ...; returns the dynamic shared memory in bytes (tests/test_plan_host.py).                                          */
 long long b200q4_debug_plan(int type, int N, int K, int M, int *out);

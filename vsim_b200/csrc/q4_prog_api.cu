@@ -440,6 +440,30 @@ int b200q4_chain_run(b200q4_chain *c, void *stream)
     return prog_launch(c->pg, stream ? (cudaStream_t)stream : dev_info().stream);
 }
 
+/* bench helper (b200q4_dev.h): `launches` runs of chain c, then one of `tail` (may be NULL), between two CUDA events recorded
+ * on `stream` from C -- no interpreter between the first event and the first launch; returns the milliseconds or a
+ * negative error code */
+double b200q4_chain_time(b200q4_chain *c, b200q4_chain *tail, int launches, void *stream)
+{
+    ApiLock lk;
+    if (!c || launches < 0) return api_fail(B200Q4_EINVAL, "chain_time: bad argument");
+    cudaStream_t st = stream ? (cudaStream_t)stream : dev_info().stream;
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return api_fail(B200Q4_ECUDA, "chain_time: event create failed");
+    double ms = B200Q4_ECUDA;
+    int rc = B200Q4_OK;
+    if (cudaEventRecord(e0, st) == cudaSuccess) {
+        for (int i = 0; i < launches && rc == B200Q4_OK; i++) rc = prog_launch(c->pg, st);
+        if (rc == B200Q4_OK && tail) rc = prog_launch(tail->pg, st);
+        if (rc == B200Q4_OK && cudaEventRecord(e1, st) == cudaSuccess && cudaEventSynchronize(e1) == cudaSuccess) {
+            float f = 0.f;
+            if (cudaEventElapsedTime(&f, e0, e1) == cudaSuccess) ms = f;
+        } else if (rc != B200Q4_OK) ms = rc;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms;
+}
+
 /* development aid (timeline builds): copies the [grid][n_ops][8] stamps of the last run; returns grid or a negative error */
 int b200q4_chain_timeline(const b200q4_chain *c, unsigned long long *out, size_t cap_words)
 {

@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "b200q4_kernel_for",
     # include/b200q4_dev.h: bench / test / development helpers, not part of the product ABI
     "b200q4_time_mul_mat_dev", "b200q4_debug_plan", "b200q4_debug_set_tile_min_m", "b200q4_debug_set_fuse_max_k",
-    "b200q4_debug_set_slice_min_c", "b200q4_debug_timeline", "b200q4_chain_timeline",
+    "b200q4_debug_set_slice_min_c", "b200q4_debug_timeline", "b200q4_chain_timeline", "b200q4_chain_time",
 ]
 HOOK_SYMBOLS = ["init_xmax", "imax_ggml_compute_forward_mul_mat_q4_0_f32",
                 "imax_ggml_compute_forward_mul_mat_q4_1_f32", "b200q4_hook_shutdown"]
@@ -120,6 +120,7 @@ def load_library(build: bool = True) -> C.CDLL:
         "b200q4_launch_count_reset": (None, []),
         "b200q4_kernel_for": (C.c_char_p, [i, i, i, i]),
         "b200q4_time_mul_mat_dev": (C.c_double, [C.POINTER(vp), i, vp, i, vp, i]),
+        "b200q4_chain_time": (C.c_double, [vp, vp, i, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
