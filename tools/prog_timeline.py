@@ -32,6 +32,14 @@ if what in ("l2", "l2i"):
         ch = vsim_b200.Chain(ws, xs, yp, [-1] + list(range(nops - 1)))
     else:
         ch = vsim_b200.Chain(ws, [ys[1].data_ptr()] * nops, [ys[0].data_ptr()] * nops, [-1] * nops)
+elif what == "hl":                                        # bench.py's headline launch: independent steps, own input rows, rotating weights
+    n, k = 16384, 4096
+    nops = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+    wl_ = [vsim_b200.Q4Weight(0, rand_q4(rng, 0, n, k), n, k) for _ in range(10)]
+    ws = [wl_[i % 10] for i in range(nops)]
+    xin = torch.randn(nops, k, device="cuda")
+    yout = torch.zeros(nops, n, device="cuda")
+    ch = vsim_b200.Chain(ws, [xin[i].data_ptr() for i in range(nops)], [yout[i].data_ptr() for i in range(nops)], [-1] * nops)
 elif what in ("gptj", "neox20b"):
     ch, _, nops = model_chain(rng, what, NL=4)
     show = list(range(6, 19))
