@@ -284,6 +284,8 @@ int prog_launch(const Prog &pg, cudaStream_t st)
     at[0].id = cudaLaunchAttributeCooperative;           // the CTAs wait on one another: all of them must be resident
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    { static const bool nocoop = getenv("B200Q4_PROG_NOCOOP") && atoi(getenv("B200Q4_PROG_NOCOOP")) != 0;   // development: what the cooperative launch costs
+      if (nocoop) cfg.numAttrs = 0; }
     if (pg.qt == 0) PCK(cudaLaunchKernelEx(&cfg, q4_prog_kernel<0>, p));
     else            PCK(cudaLaunchKernelEx(&cfg, q4_prog_kernel<1>, p));
     api_count_launch(1);
